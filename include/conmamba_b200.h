@@ -1,0 +1,216 @@
+/*
+ * conmamba_b200.h - C ABI of the B200-native ConMamba hot path.
+ *
+ * One shared library (libconmamba_b200.so, built by __graft_entry__.build()) exports the entry points
+ * below.  Every entry point
+ *   - takes a POD argument block of raw DEVICE pointers, element strides and sizes (no torch types),
+ *   - enqueues sm_100a kernels on the CUDA stream passed as `stream` (a cudaStream_t; NULL = default),
+ *   - never allocates, never synchronises the host, keeps no global state (thread-safe),
+ *   - returns 0 on success, a positive cudaError_t from the launch, or a negative CM_ERR_* code when
+ *     the arguments describe something this library does not implement.  There is no CPU fallback.
+ *
+ * The reference (mattmireles/Mamba-ASR) has no FFI of its own: its hot path calls two pybind11 extension
+ * modules that are pip dependencies (requirement.txt:7-8).  Each entry point cites the reference call site
+ * whose native callee it replaces; INTEGRATION.md shows the ctypes binding and the drop-in Python modules.
+ *
+ * Layout conventions
+ *   cm_tensor3 describes a (batch, channel-or-state, time) tensor by three ELEMENT strides, so both the
+ *   reference's time-contiguous (B, D, L) tensors (sl == 1) and this library's preferred channel-last
+ *   (B, L, D) buffers (sd == 1) are accepted without copies.  Channel-last is the fast path: one warp
+ *   lane per channel makes every global access of the scan a coalesced row segment.
+ */
+#ifndef CONMAMBA_B200_H_
+#define CONMAMBA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CM_ABI_VERSION 1
+
+/* element type of activations (u, delta, z, B, C, x, out, and their gradients) */
+enum { CM_F32 = 0, CM_BF16 = 1, CM_F16 = 2 };
+
+/* negative return codes */
+enum {
+  CM_ERR_BAD_ARG = -1,      /* null pointer, non-positive size, bad enum */
+  CM_ERR_UNSUPPORTED = -2   /* valid request outside the implemented envelope (e.g. dstate > 16) */
+};
+
+#define CM_MAX_DSTATE 16
+#define CM_SCAN_CKPT_STEPS 8   /* forward saves the recurrent state every 8 processed steps */
+#define CM_CONV_MAX_WIDTH 4
+
+/* flags */
+#define CM_FLAG_DELTA_SOFTPLUS 1u /* delta = softplus(delta + delta_bias)  (selective_scan_interface.py:109-112) */
+#define CM_FLAG_SILU 1u           /* conv: apply SiLU                       (selective_scan_interface.py:182)    */
+
+typedef struct {
+  void* ptr;      /* device pointer, NULL = tensor absent */
+  int64_t sb;     /* batch stride, elements */
+  int64_t sd;     /* channel (or state) stride, elements */
+  int64_t sl;     /* time stride, elements */
+} cm_tensor3;
+
+/* ------------------------------------------------------------------------------------------------------
+ * Selective scan.  Replaces selective_scan_cuda.fwd / .bwd of mamba-ssm 1.1.3.post1
+ * (reference call sites: modules/mamba/selective_scan_interface.py:42, :67, :218, :252), and additionally
+ * fuses what modules/mamba/bimamba.py:223-253 does around two such calls: the reversed-time second
+ * direction (no torch.flip), the shared z gate and the 0.5*(fwd + bwd) output add.
+ *
+ * Per direction r, channel d, state n, in fp32:
+ *   Delta = softplus(delta + delta_bias[d])                          (if CM_FLAG_DELTA_SOFTPLUS)
+ *   h     = exp(Delta * A[d,n]) * h + Delta * u * B[n]               time ascending, or descending if reverse
+ *   y_r   = sum_n C[n] * h[n] + Dskip[d] * u
+ * out_pre = sum_r y_r ;  out = out_scale * out_pre * silu(z)   (no gate if z.ptr == NULL)
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t reverse;          /* 0: time 0..L-1 ; 1: time L-1..0 */
+  int32_t bc_const;         /* 0: B, C are (batch, dstate, time) shared by all channels;
+                               1: B, C are per-channel fp32 constants (dim, dstate) regardless of `dtype`:
+                                  stride sb = channel, sd = state, sl unused */
+  cm_tensor3 u;             /* (batch, dim, time) */
+  cm_tensor3 delta;         /* (batch, dim, time) */
+  cm_tensor3 Bm, Cm;        /* see bc_const */
+  const float* A;           /* (dim, dstate) fp32 */
+  int64_t A_sd, A_sn;
+  const float* Dskip;       /* (dim) fp32 or NULL */
+  const float* delta_bias;  /* (dim) fp32 or NULL */
+  float* ckpt;              /* NULL (inference) or fp32 checkpoints [batch][dim][cm_scan_num_ckpt()][dstate16] */
+  int64_t ckpt_sb, ckpt_sd; /* strides (floats) of the batch / channel index; checkpoint j of a row starts at j*16 */
+  float* last_state;        /* NULL or (batch, dim, dstate) fp32: state after the last processed step */
+  int64_t ls_sb, ls_sd, ls_sn;
+} cm_scan_dir;
+
+typedef struct {
+  int32_t batch, dim, seqlen, dstate;
+  int32_t ndir;             /* 1 or 2 */
+  int32_t dtype;            /* CM_F32 / CM_BF16 / CM_F16 */
+  uint32_t flags;
+  float out_scale;          /* 1.0, or 0.5 for bimamba if_devide_out (bimamba.py:250-253) */
+  int32_t lanes_per_channel;/* 0 = choose; 1, 2 or 4 lanes cooperate on one channel's 16 states */
+  int32_t reserved;
+  cm_scan_dir dir[2];
+  cm_tensor3 z;             /* gate, shared by both directions; ptr NULL = none */
+  cm_tensor3 out;           /* gated output */
+  cm_tensor3 out_pre;       /* optional pre-gate sum over directions (saved for backward when z is given) */
+} cm_scan_fwd_args;
+
+/* number of fp32 [16] checkpoints per (batch, channel, direction) row that forward writes and backward reads */
+int cm_scan_num_ckpt(int32_t seqlen, int32_t ndir);
+/* channels handled by one warp (= the slab width of the dB/dC partial sums) for a lanes_per_channel choice */
+int cm_scan_slab_channels(int32_t lanes_per_channel);
+/* the lanes_per_channel the library would pick for this problem when the caller passes 0 */
+int cm_scan_pick_lanes(int32_t batch, int32_t dim, int32_t ndir);
+
+int cm_scan_fwd(const cm_scan_fwd_args* args, void* stream);
+
+typedef struct {
+  cm_scan_dir in;           /* same tensors as forward (ckpt required, last_state ignored) */
+  cm_tensor3 du;            /* (batch, dim, time) grad of u */
+  cm_tensor3 ddelta;        /* (batch, dim, time) grad of the raw (pre-softplus) delta */
+  float* dBC_part;          /* bc_const == 0: fp32 [batch][n_slab][seqlen][32] partial sums over a slab's channels,
+                               columns 0..15 = dB[n], 16..31 = dC[n];  reduce with cm_reduce_dbc().
+                               bc_const == 1: fp32 [batch][dim][32] per-row sums over time */
+  float* dA_part;           /* fp32 [batch][dim][16] per-row sums over time; reduce over batch with cm_reduce_rows() */
+  float* dD_part;           /* fp32 [batch][dim] or NULL */
+  float* dbias_part;        /* fp32 [batch][dim] or NULL */
+} cm_scan_bwd_dir;
+
+typedef struct {
+  int32_t batch, dim, seqlen, dstate;
+  int32_t ndir;
+  int32_t dtype;
+  uint32_t flags;
+  float out_scale;
+  int32_t lanes_per_channel;
+  int32_t reserved;
+  cm_scan_bwd_dir dir[2];
+  cm_tensor3 z;             /* or NULL */
+  cm_tensor3 out_pre;       /* required when z is given */
+  cm_tensor3 dout;          /* grad of the gated output */
+  cm_tensor3 dz;            /* grad of z (written when z is given) */
+} cm_scan_bwd_args;
+
+int cm_scan_bwd(const cm_scan_bwd_args* args, void* stream);
+
+/* dB[b,n,l] = sum_slab part[b][slab][l][n], dC likewise with column 16+n; written in `dtype` through strides. */
+int cm_reduce_dbc(const float* part, int32_t batch, int32_t n_slab, int32_t seqlen, int32_t dstate,
+                  int32_t dtype, cm_tensor3 dB, cm_tensor3 dC, void* stream);
+/* out[c] = sum_r part[r*cols + c]   (fp32; deterministic order) - dA, dD, d(delta_bias), conv dweight/dbias */
+int cm_reduce_rows(const float* part, int64_t rows, int64_t cols, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Depthwise causal conv1d (+ SiLU).  Replaces causal_conv1d_cuda.causal_conv1d_fwd / _bwd of
+ * causal-conv1d 1.1.3.post1 (reference call sites: selective_scan_interface.py:182, :244, :286;
+ * bimamba.py:282-287), and fuses the two BiMamba-v2 directions: one read of x produces
+ *   causal      out_f[l] = act(bias_f + sum_k w_f[k] * x[l-(W-1)+k])
+ *   anticausal  out_b[l] = act(bias_b + sum_k w_b[k] * x[l+(W-1)-k])     (= flip -> conv1d_b -> flip)
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t anticausal;
+  int32_t reserved;
+  const float* weight;      /* (dim, width) fp32 contiguous */
+  const float* bias;        /* (dim) fp32 or NULL */
+  cm_tensor3 out;           /* forward: output.  backward: grad of the output (input) */
+  float* dweight_part;      /* backward: fp32 [n_part][dim][width] partial sums; reduce with cm_reduce_rows() */
+  float* dbias_part;        /* backward: fp32 [n_part][dim] or NULL */
+} cm_conv_dir;
+
+typedef struct {
+  int32_t batch, dim, seqlen, width;
+  int32_t ndir;
+  int32_t dtype;
+  uint32_t flags;
+  int32_t reserved;
+  cm_tensor3 x;             /* (batch, dim, time) input */
+  cm_tensor3 dx;            /* backward only: grad of x, summed over directions */
+  cm_conv_dir dir[2];
+} cm_conv_args;
+
+int cm_conv_fwd(const cm_conv_args* args, void* stream);
+/* number of partial rows n_part that cm_conv_bwd writes per direction for this problem */
+int cm_conv_num_part(int32_t batch, int32_t seqlen);
+int cm_conv_bwd(const cm_conv_args* args, void* stream);
+
+/* single-token update (causal_conv1d_update, reference call site bimamba.py:335-341):
+ * rolls conv_state (batch, dim, width) left by one, appends x (batch, dim), returns act(bias + <state, w>) */
+int cm_conv_update(const void* x, void* conv_state, const float* weight, const float* bias, void* out,
+                   int32_t batch, int32_t dim, int32_t width, int32_t dtype, uint32_t flags, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Fbank tail.  Replaces the torch op chain behind speechbrain.lobes.features.Fbank after the STFT
+ * (reference call sites train_CTC.py:285, train_S2S.py:349; YAML hparams/CTC/conmamba_large.yaml:322-326):
+ *   power = re^2 + im^2 ; mel = power @ fbank ; db = 10*log10(max(mel, 1e-10)) ;
+ *   db = max(db, max_over_utterance(db) - top_db)
+ * cm_fbank_logmel does power -> mel -> dB and the per-utterance running max in one pass over the STFT;
+ * cm_fbank_floor applies the top_db floor.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch, frames, nbins, nmels;
+  const float* stft;        /* complex64 as float pairs; element (b, f, t) at b*s_b + f*s_f + t*s_t (complex units) */
+  int64_t s_b, s_f, s_t;
+  const float* fbank;       /* (nbins, nmels) fp32 row-major triangular filterbank */
+  float* out;               /* (batch, frames, nmels) fp32 contiguous */
+  float* utt_max;           /* (batch) fp32, must be pre-filled with -inf; receives max dB per utterance */
+  float amin;               /* 1e-10 */
+  float multiplier;         /* 10 */
+  float db_offset;          /* multiplier*log10(max(amin, ref_value)) = 0 */
+  float top_db;             /* 80 */
+} cm_fbank_args;
+
+int cm_fbank_logmel(const cm_fbank_args* args, void* stream);
+int cm_fbank_floor(const cm_fbank_args* args, void* stream);
+
+/* library identification: returns CM_ABI_VERSION; writes the compiled-for arch (e.g. 100) to *sm_arch if non-NULL */
+int cm_version(int32_t* sm_arch);
+/* sizeof() of the argument structs, for binding self-checks: 0 cm_tensor3, 1 cm_scan_dir, 2 cm_scan_fwd_args,
+ * 3 cm_scan_bwd_dir, 4 cm_scan_bwd_args, 5 cm_conv_dir, 6 cm_conv_args, 7 cm_fbank_args */
+int cm_abi_sizeof(int32_t which);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONMAMBA_B200_H_ */

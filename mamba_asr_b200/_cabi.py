@@ -1,0 +1,173 @@
+"""ctypes binding of include/conmamba_b200.h.
+
+The structures mirror the header field by field.  ``lib()`` loads ``lib/libconmamba_b200.so`` (built in-tree by
+``python -m mamba_asr_b200.build`` / ``__graft_entry__.build()``) and raises if it is missing: there is no
+CPU or Triton fallback behind this package.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libconmamba_b200.so")
+
+CM_F32, CM_BF16, CM_F16 = 0, 1, 2
+CM_ERR_BAD_ARG, CM_ERR_UNSUPPORTED = -1, -2
+CM_FLAG_DELTA_SOFTPLUS = 1
+CM_FLAG_SILU = 1
+CM_SCAN_CKPT_STEPS = 8
+CM_ABI_VERSION = 1
+
+EXPORTS = (
+    "cm_version", "cm_scan_num_ckpt", "cm_scan_slab_channels", "cm_scan_pick_lanes", "cm_scan_fwd", "cm_scan_bwd",
+    "cm_reduce_dbc", "cm_reduce_rows", "cm_conv_fwd", "cm_conv_num_part", "cm_conv_bwd", "cm_conv_update",
+    "cm_fbank_logmel", "cm_fbank_floor", "cm_abi_sizeof",
+)
+
+_DTYPES = {torch.float32: CM_F32, torch.bfloat16: CM_BF16, torch.float16: CM_F16}
+
+
+class Tensor3(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("sb", C.c_int64), ("sd", C.c_int64), ("sl", C.c_int64)]
+
+
+class ScanDir(C.Structure):
+    _fields_ = [
+        ("reverse", C.c_int32), ("bc_const", C.c_int32),
+        ("u", Tensor3), ("delta", Tensor3), ("Bm", Tensor3), ("Cm", Tensor3),
+        ("A", C.c_void_p), ("A_sd", C.c_int64), ("A_sn", C.c_int64),
+        ("Dskip", C.c_void_p), ("delta_bias", C.c_void_p),
+        ("ckpt", C.c_void_p), ("ckpt_sb", C.c_int64), ("ckpt_sd", C.c_int64),
+        ("last_state", C.c_void_p), ("ls_sb", C.c_int64), ("ls_sd", C.c_int64), ("ls_sn", C.c_int64),
+    ]
+
+
+class ScanFwdArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("dim", C.c_int32), ("seqlen", C.c_int32), ("dstate", C.c_int32),
+        ("ndir", C.c_int32), ("dtype", C.c_int32), ("flags", C.c_uint32), ("out_scale", C.c_float),
+        ("lanes_per_channel", C.c_int32), ("reserved", C.c_int32),
+        ("dir", ScanDir * 2),
+        ("z", Tensor3), ("out", Tensor3), ("out_pre", Tensor3),
+    ]
+
+
+class ScanBwdDir(C.Structure):
+    _fields_ = [
+        ("inp", ScanDir), ("du", Tensor3), ("ddelta", Tensor3),
+        ("dBC_part", C.c_void_p), ("dA_part", C.c_void_p), ("dD_part", C.c_void_p), ("dbias_part", C.c_void_p),
+    ]
+
+
+class ScanBwdArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("dim", C.c_int32), ("seqlen", C.c_int32), ("dstate", C.c_int32),
+        ("ndir", C.c_int32), ("dtype", C.c_int32), ("flags", C.c_uint32), ("out_scale", C.c_float),
+        ("lanes_per_channel", C.c_int32), ("reserved", C.c_int32),
+        ("dir", ScanBwdDir * 2),
+        ("z", Tensor3), ("out_pre", Tensor3), ("dout", Tensor3), ("dz", Tensor3),
+    ]
+
+
+class ConvDir(C.Structure):
+    _fields_ = [
+        ("anticausal", C.c_int32), ("reserved", C.c_int32),
+        ("weight", C.c_void_p), ("bias", C.c_void_p), ("out", Tensor3),
+        ("dweight_part", C.c_void_p), ("dbias_part", C.c_void_p),
+    ]
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("dim", C.c_int32), ("seqlen", C.c_int32), ("width", C.c_int32),
+        ("ndir", C.c_int32), ("dtype", C.c_int32), ("flags", C.c_uint32), ("reserved", C.c_int32),
+        ("x", Tensor3), ("dx", Tensor3),
+        ("dir", ConvDir * 2),
+    ]
+
+
+class FbankArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("frames", C.c_int32), ("nbins", C.c_int32), ("nmels", C.c_int32),
+        ("stft", C.c_void_p), ("s_b", C.c_int64), ("s_f", C.c_int64), ("s_t", C.c_int64),
+        ("fbank", C.c_void_p), ("out", C.c_void_p), ("utt_max", C.c_void_p),
+        ("amin", C.c_float), ("multiplier", C.c_float), ("db_offset", C.c_float), ("top_db", C.c_float),
+    ]
+
+
+ABI_STRUCTS = (Tensor3, ScanDir, ScanFwdArgs, ScanBwdDir, ScanBwdArgs, ConvDir, ConvArgs, FbankArgs)
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library; raises (never falls back) when it is absent or stale."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "mamba_asr_b200: %s is missing - build it with `python -m mamba_asr_b200.build` "
+                "(there is no CPU / Triton fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name in EXPORTS:
+            getattr(L, name).restype = C.c_int
+        L.cm_version.argtypes = [C.POINTER(C.c_int32)]
+        L.cm_scan_num_ckpt.argtypes = [C.c_int32, C.c_int32]
+        L.cm_scan_slab_channels.argtypes = [C.c_int32]
+        L.cm_scan_pick_lanes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+        L.cm_scan_fwd.argtypes = [C.POINTER(ScanFwdArgs), C.c_void_p]
+        L.cm_scan_bwd.argtypes = [C.POINTER(ScanBwdArgs), C.c_void_p]
+        L.cm_reduce_dbc.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, Tensor3, Tensor3,
+                                    C.c_void_p]
+        L.cm_reduce_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+        L.cm_conv_fwd.argtypes = [C.POINTER(ConvArgs), C.c_void_p]
+        L.cm_conv_bwd.argtypes = [C.POINTER(ConvArgs), C.c_void_p]
+        L.cm_conv_num_part.argtypes = [C.c_int32, C.c_int32]
+        L.cm_conv_update.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                     C.c_int32, C.c_int32, C.c_uint32, C.c_void_p]
+        L.cm_fbank_logmel.argtypes = [C.POINTER(FbankArgs), C.c_void_p]
+        L.cm_fbank_floor.argtypes = [C.POINTER(FbankArgs), C.c_void_p]
+        L.cm_abi_sizeof.argtypes = [C.c_int32]
+        if L.cm_version(None) != CM_ABI_VERSION:
+            raise RuntimeError("mamba_asr_b200: %s has a different ABI version; rebuild it" % LIB_PATH)
+        for i, st in enumerate(ABI_STRUCTS):
+            if L.cm_abi_sizeof(i) != C.sizeof(st):
+                raise RuntimeError("mamba_asr_b200: ctypes layout of %s (%d B) differs from the library's (%d B)"
+                                   % (st.__name__, C.sizeof(st), L.cm_abi_sizeof(i)))
+        _lib = L
+    return _lib
+
+
+def dtype_code(dt):
+    try:
+        return _DTYPES[dt]
+    except KeyError:
+        raise TypeError("mamba_asr_b200 kernels take float32, bfloat16 or float16 activations, got %s" % dt)
+
+
+def t3(t, order="bdl"):
+    """cm_tensor3 of a 3-D torch tensor whose dims are a permutation `order` of (b, d, l); None -> absent."""
+    if t is None:
+        return Tensor3(None, 0, 0, 0)
+    st = t.stride()
+    return Tensor3(t.data_ptr(), st[order.index("b")], st[order.index("d")], st[order.index("l")])
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def check(code, what):
+    if code == 0:
+        return
+    if code == CM_ERR_BAD_ARG:
+        raise ValueError("%s: bad argument" % what)
+    if code == CM_ERR_UNSUPPORTED:
+        raise NotImplementedError("%s: outside the implemented envelope (dstate <= 16, conv width 2..4, batch <= 65535)"
+                                  % what)
+    raise RuntimeError("%s: CUDA error %d" % (what, code))

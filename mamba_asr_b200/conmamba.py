@@ -1,0 +1,215 @@
+"""ConMamba layer API - drop-in for the classes of the reference's ``modules/Conmamba.py`` that sit directly
+around the hot path:
+
+  ConvolutionModule      reference modules/Conmamba.py:182-454
+  ConmambaEncoderLayer   :457-650   (calls ``self.mamba(x)`` at :642 - the hot path)
+  ConmambaEncoder        :653-727
+  MambaDecoderLayer      :730-953   (``self_mamba`` :920, ``cross_mamba`` on cat([memory, tgt]) :934)
+  MambaDecoder           :956-1031
+
+Same constructor arguments, forward signatures, return tuples and sub-module names (so state_dict keys line up
+with reference checkpoints).  The SpeechBrain building blocks the reference imports (``LayerNorm``,
+``PositionalwiseFeedForward``, ``Swish``; modules/Conmamba.py:112-121) are restated below in plain torch with
+SpeechBrain's parameter names; they stay cuBLAS / cuDNN work and are not part of the hand-written kernel scope
+(SURVEY.md section 2.1 row 3).  The Mamba mixers are the fused sm_100a ones from ``bimamba.py``.
+"""
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .bimamba import Mamba as BiMamba
+from .bimamba import UniMamba as Mamba
+
+LAYER_NORM_EPS = 1e-6        # reference ConMambaConstants.LAYER_NORM_EPS (Conmamba.py:687)
+FFN_RESIDUAL_SCALE = 0.5     # reference ConMambaConstants.FFN_RESIDUAL_SCALE (Conmamba.py:638,649)
+
+
+class Swish(nn.Module):
+    """speechbrain.nnet.activations.Swish: x * sigmoid(beta * x), beta = 1."""
+
+    def __init__(self, beta: float = 1.0):
+        super().__init__()
+        self.beta = beta
+
+    def forward(self, x):
+        return x * torch.sigmoid(self.beta * x)
+
+
+class LayerNorm(nn.Module):
+    """speechbrain.nnet.normalization.LayerNorm over the last dimension (parameters under ``.norm``)."""
+
+    def __init__(self, input_size, eps=1e-05, elementwise_affine=True):
+        super().__init__()
+        self.norm = nn.LayerNorm(input_size, eps=eps, elementwise_affine=elementwise_affine)
+
+    def forward(self, x):
+        return self.norm(x)
+
+
+class PositionalwiseFeedForward(nn.Module):
+    """speechbrain.nnet.attention.PositionalwiseFeedForward: Linear -> act -> Dropout -> Linear (under ``.ffn``)."""
+
+    def __init__(self, d_ffn, input_size, dropout=0.0, activation=nn.ReLU):
+        super().__init__()
+        self.ffn = nn.Sequential(nn.Linear(input_size, d_ffn), activation(), nn.Dropout(dropout),
+                                 nn.Linear(d_ffn, input_size))
+
+    def forward(self, x):
+        return self.ffn(x)
+
+
+class ConvolutionModule(nn.Module):
+    """LayerNorm -> pointwise conv (x2) + GLU -> depthwise conv (k=31) -> LayerNorm -> act -> Linear -> Dropout."""
+
+    def __init__(self, input_size, kernel_size=31, bias=True, activation=Swish, dropout=0.0, causal=False,
+                 dilation=1):
+        super().__init__()
+        self.kernel_size = kernel_size
+        self.causal = causal
+        self.dilation = dilation
+        full = (kernel_size - 1) * 2 ** (dilation - 1)
+        self.padding = full if causal else full // 2
+        self.layer_norm = nn.LayerNorm(input_size)
+        self.bottleneck = nn.Sequential(nn.Conv1d(input_size, 2 * input_size, kernel_size=1, stride=1, bias=bias),
+                                        nn.GLU(dim=1))
+        self.conv = nn.Conv1d(input_size, input_size, kernel_size=kernel_size, stride=1, padding=self.padding,
+                              dilation=dilation, groups=input_size, bias=bias)
+        self.after_conv = nn.Sequential(nn.LayerNorm(input_size), activation(), nn.Linear(input_size, input_size, bias=bias),
+                                        nn.Dropout(dropout))
+
+    def forward(self, x, mask: Optional[torch.Tensor] = None, dynchunktrain_config=None):
+        if dynchunktrain_config is not None:
+            raise NotImplementedError("Dynamic Chunk Training convolution is never enabled by the ConMamba encoder "
+                                      "(TransformerASR.py:783-788 passes no config)")
+        out = self.layer_norm(x).transpose(1, 2)
+        out = self.conv(self.bottleneck(out))
+        if self.causal:
+            out = out[..., :-self.padding]
+        out = self.after_conv(out.transpose(1, 2))
+        if mask is not None:
+            out.masked_fill_(mask, 0.0)
+        return out
+
+
+def _make_mixer(d_model, mamba_config, bidirectional_ok):
+    """Reference idiom (Conmamba.py:579-591): pop 'bidirectional', build, put the key back."""
+    assert mamba_config is not None
+    bidirectional = mamba_config.pop('bidirectional')
+    try:
+        if bidirectional_ok and bidirectional:
+            return BiMamba(d_model=d_model, bimamba_type='v2', **mamba_config)
+        return Mamba(d_model=d_model, **mamba_config)
+    finally:
+        mamba_config['bidirectional'] = bidirectional
+
+
+class ConmambaEncoderLayer(nn.Module):
+    def __init__(self, d_model, d_ffn, kernel_size=31, activation=Swish, bias=True, dropout=0.0, causal=False,
+                 mamba_config=None):
+        super().__init__()
+        self.mamba = _make_mixer(d_model, mamba_config, bidirectional_ok=not causal)
+        self.convolution_module = ConvolutionModule(d_model, kernel_size, bias, activation, dropout, causal=causal)
+        self.ffn_module1 = nn.Sequential(nn.LayerNorm(d_model),
+                                         PositionalwiseFeedForward(d_ffn=d_ffn, input_size=d_model, dropout=dropout,
+                                                                   activation=activation),
+                                         nn.Dropout(dropout))
+        self.ffn_module2 = nn.Sequential(nn.LayerNorm(d_model),
+                                         PositionalwiseFeedForward(d_ffn=d_ffn, input_size=d_model, dropout=dropout,
+                                                                   activation=activation),
+                                         nn.Dropout(dropout))
+        self.norm1 = LayerNorm(d_model)
+        self.norm2 = LayerNorm(d_model)
+        self.drop = nn.Dropout(dropout)
+
+    def forward(self, x, src_mask: Optional[torch.Tensor] = None, src_key_padding_mask: Optional[torch.Tensor] = None,
+                pos_embs: torch.Tensor = None, dynchunktrain_config=None):
+        # The reference builds a conv mask from src_key_padding_mask and then discards it (Conmamba.py:631-635):
+        # padding is never masked inside ConMamba.  Reproduced, not "fixed".
+        conv_mask = None
+        x = x + FFN_RESIDUAL_SCALE * self.ffn_module1(x)
+        skip = x
+        x = self.norm1(x)
+        x = self.mamba(x)
+        x = x + skip
+        x = x + self.convolution_module(x, conv_mask, dynchunktrain_config=dynchunktrain_config)
+        x = self.norm2(x + FFN_RESIDUAL_SCALE * self.ffn_module2(x))
+        return x
+
+
+class ConmambaEncoder(nn.Module):
+    def __init__(self, num_layers, d_model, d_ffn, kernel_size=31, activation=Swish, bias=True, dropout=0.0,
+                 causal=False, mamba_config=None):
+        super().__init__()
+        self.layers = nn.ModuleList([
+            ConmambaEncoderLayer(d_model=d_model, d_ffn=d_ffn, dropout=dropout, activation=activation,
+                                 kernel_size=kernel_size, bias=bias, causal=causal, mamba_config=mamba_config)
+            for _ in range(num_layers)])
+        self.norm = LayerNorm(d_model, eps=LAYER_NORM_EPS)
+
+    def forward(self, src, src_mask: Optional[torch.Tensor] = None, src_key_padding_mask: Optional[torch.Tensor] = None,
+                pos_embs: Optional[torch.Tensor] = None, dynchunktrain_config=None):
+        output = src
+        for enc_layer in self.layers:
+            output = enc_layer(output, src_mask=src_mask, src_key_padding_mask=src_key_padding_mask,
+                               pos_embs=pos_embs, dynchunktrain_config=dynchunktrain_config)
+        return self.norm(output), None
+
+
+class MambaDecoderLayer(nn.Module):
+    def __init__(self, d_model, d_ffn, activation=nn.ReLU, dropout=0.0, normalize_before=False, mamba_config=None):
+        super().__init__()
+        assert mamba_config is not None
+        bidirectional = mamba_config.pop('bidirectional')
+        self.self_mamba = Mamba(d_model=d_model, **mamba_config)
+        self.cross_mamba = Mamba(d_model=d_model, **mamba_config)
+        mamba_config['bidirectional'] = bidirectional
+        self.pos_ffn = PositionalwiseFeedForward(d_ffn=d_ffn, input_size=d_model, dropout=dropout,
+                                                 activation=activation)
+        self.norm1 = LayerNorm(d_model, eps=LAYER_NORM_EPS)
+        self.norm2 = LayerNorm(d_model, eps=LAYER_NORM_EPS)
+        self.norm3 = LayerNorm(d_model, eps=LAYER_NORM_EPS)
+        self.dropout1 = nn.Dropout(dropout)
+        self.dropout2 = nn.Dropout(dropout)
+        self.dropout3 = nn.Dropout(dropout)
+        self.normalize_before = normalize_before
+
+    def forward(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,
+                memory_key_padding_mask=None, pos_embs_tgt=None, pos_embs_src=None):
+        pre = self.normalize_before
+        t = self.norm1(tgt) if pre else tgt
+        tgt = tgt + self.dropout1(self.self_mamba(t))
+        if not pre:
+            tgt = self.norm1(tgt)
+        t = self.norm2(tgt) if pre else tgt
+        # causal scan over [memory ; tgt]: every target position sees the whole encoder output first
+        cross = self.cross_mamba(torch.cat([memory, t], dim=1))[:, -t.shape[1]:]
+        tgt = tgt + self.dropout2(cross)
+        if not pre:
+            tgt = self.norm2(tgt)
+        t = self.norm3(tgt) if pre else tgt
+        tgt = tgt + self.dropout3(self.pos_ffn(t))
+        if not pre:
+            tgt = self.norm3(tgt)
+        return tgt, None, None
+
+
+class MambaDecoder(nn.Module):
+    def __init__(self, num_layers, d_model, d_ffn, activation=nn.ReLU, dropout=0.0, normalize_before=False,
+                 mamba_config=None):
+        super().__init__()
+        self.layers = nn.ModuleList([
+            MambaDecoderLayer(d_model=d_model, d_ffn=d_ffn, activation=activation, dropout=dropout,
+                              normalize_before=normalize_before, mamba_config=mamba_config)
+            for _ in range(num_layers)])
+        self.norm = LayerNorm(d_model, eps=LAYER_NORM_EPS)
+
+    def forward(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,
+                memory_key_padding_mask=None, pos_embs_tgt=None, pos_embs_src=None):
+        output = tgt
+        for dec_layer in self.layers:
+            output, _, _ = dec_layer(output, memory, tgt_mask=tgt_mask, memory_mask=memory_mask,
+                                     tgt_key_padding_mask=tgt_key_padding_mask,
+                                     memory_key_padding_mask=memory_key_padding_mask,
+                                     pos_embs_tgt=pos_embs_tgt, pos_embs_src=pos_embs_src)
+        return self.norm(output), [None], [None]

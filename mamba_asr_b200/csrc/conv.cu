@@ -1,0 +1,520 @@
+// Depthwise causal conv1d (+SiLU) forward / backward for sm_100a, both BiMamba-v2 directions from one read.
+//
+// Replaces causal_conv1d_cuda.causal_conv1d_fwd / _bwd (reference call sites
+// modules/mamba/selective_scan_interface.py:182,244,286 and modules/mamba/bimamba.py:282-287).
+// Widths 2..4 are evaluated as 4 taps with left-zero-padded weights w4[j] = w[j-(4-W)]:
+//   causal      s_f[l] = bias_f + sum_j w4_f[j] * x[l-3+j]
+//   anticausal  s_b[l] = bias_b + sum_j w4_b[j] * x[l+3-j]      (conv1d_b on the flipped sequence, in place)
+//
+// Channel-last kernels (x.sd == 1, the layout the B200 Mamba block uses): one thread owns VEC adjacent channels
+// and 16 consecutive time steps; all 22 row loads (16 + 3 halo each side) are issued before the first FMA, every
+// access is a 64..256-byte coalesced row segment, HBM traffic is x once in, each output once out.
+// Generic kernels (any strides, e.g. the reference's time-contiguous (B, D, L)): lanes along time, halo re-reads
+// served by L1.  Weight/bias gradients are reduced in-CTA and written as per-(batch, 64-step chunk) partial rows
+// that cm_reduce_rows() sums in a fixed order (no atomics, deterministic).
+#include "common.cuh"
+
+namespace cm {
+
+constexpr int kTL = 16;        // time steps per thread (channel-last kernels)
+constexpr int kTY = 4;         // threadIdx.y: time chunks per CTA  -> 64 steps per CTA
+constexpr int kChunk = kTL * kTY;
+
+template <int BYTES> struct RawVec;
+template <> struct RawVec<2> { using type = unsigned short; };
+template <> struct RawVec<4> { using type = uint32_t; };
+template <> struct RawVec<8> { using type = uint2; };
+template <> struct RawVec<16> { using type = uint4; };
+
+template <typename T> __device__ __forceinline__ float bits_to_float(uint32_t lo16);
+template <> __device__ __forceinline__ float bits_to_float<__nv_bfloat16>(uint32_t v) { return __uint_as_float(v << 16); }
+template <> __device__ __forceinline__ float bits_to_float<__half>(uint32_t v) {
+  return __half2float(__ushort_as_half(static_cast<unsigned short>(v)));
+}
+template <typename T> __device__ __forceinline__ uint32_t float_to_bits(float f);
+template <> __device__ __forceinline__ uint32_t float_to_bits<__nv_bfloat16>(float f) {
+  return __bfloat16_as_ushort(__float2bfloat16_rn(f));
+}
+template <> __device__ __forceinline__ uint32_t float_to_bits<__half>(float f) {
+  return __half_as_ushort(__float2half_rn(f));
+}
+
+// VEC adjacent elements <-> fp32 registers through one aligned load/store
+template <typename T, int VEC>
+struct VecIO {
+  using Raw = typename RawVec<sizeof(T) * VEC>::type;
+  static __device__ __forceinline__ void ld(const T* p, float (&o)[VEC]) {
+    const Raw r = __ldg(reinterpret_cast<const Raw*>(p));
+    if constexpr (sizeof(T) == 4) {
+      const float* f = reinterpret_cast<const float*>(&r);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) o[i] = f[i];
+    } else {
+      const unsigned short* h = reinterpret_cast<const unsigned short*>(&r);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) o[i] = bits_to_float<T>(h[i]);
+    }
+  }
+  static __device__ __forceinline__ void st(T* p, const float (&v)[VEC]) {
+    Raw r;
+    if constexpr (sizeof(T) == 4) {
+      float* f = reinterpret_cast<float*>(&r);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) f[i] = v[i];
+    } else {
+      unsigned short* h = reinterpret_cast<unsigned short*>(&r);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) h[i] = static_cast<unsigned short>(float_to_bits<T>(v[i]));
+    }
+    *reinterpret_cast<Raw*>(p) = r;
+  }
+};
+
+__device__ __forceinline__ float silu_f(float s) { return s * sigmoidf_fast(s); }
+__device__ __forceinline__ float silu_grad(float s) {
+  const float sig = sigmoidf_fast(s);
+  return sig * fmaf(s, 1.f - sig, 1.f);
+}
+
+// 4-tap weights of VEC channels, left-zero-padded
+template <int VEC>
+struct Taps {
+  float w[VEC][4], b[VEC];
+  __device__ __forceinline__ void load(const cm_conv_dir& dr, int d0, int W) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = j - (4 - W);
+        w[v][j] = (k >= 0) ? __ldg(dr.weight + (int64_t)(d0 + v) * W + k) : 0.f;
+      }
+      b[v] = dr.bias ? __ldg(dr.bias + d0 + v) : 0.f;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// channel-last forward
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(32 * kTY) conv_fwd_cl_kernel(const cm_conv_args p) {
+  const int d0 = (blockIdx.x * 32 + threadIdx.x) * VEC;
+  const int l0 = (blockIdx.y * kTY + threadIdx.y) * kTL;
+  const int L = p.seqlen;
+  if (d0 >= p.dim || l0 >= L) return;
+  const int b = blockIdx.z;
+  const bool silu = (p.flags & CM_FLAG_SILU) != 0;
+
+  float xw[kTL + 6][VEC];
+  const T* xp = static_cast<const T*>(p.x.ptr) + b * p.x.sb + d0;
+#pragma unroll
+  for (int i = 0; i < kTL + 6; ++i) {
+    const int l = l0 - 3 + i;
+    if (l >= 0 && l < L) {
+      VecIO<T, VEC>::ld(xp + (int64_t)l * p.x.sl, xw[i]);
+    } else {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) xw[i][v] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    if (r < p.ndir) {
+      const cm_conv_dir& dr = p.dir[r];
+      Taps<VEC> tp;
+      tp.load(dr, d0, p.width);
+      const bool anti = dr.anticausal != 0;
+      T* op = static_cast<T*>(dr.out.ptr) + b * dr.out.sb + d0;
+#pragma unroll
+      for (int i = 0; i < kTL; ++i) {
+        const int l = l0 + i;
+        if (l < L) {
+          float o[VEC];
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            float acc = tp.b[v];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc = fmaf(tp.w[v][j], anti ? xw[i + 6 - j][v] : xw[i + j][v], acc);
+            o[v] = silu ? silu_f(acc) : acc;
+          }
+          VecIO<T, VEC>::st(op + (int64_t)l * dr.out.sl, o);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// channel-last backward: dx (summed over directions) + per-CTA partial dweight / dbias
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(32 * kTY) conv_bwd_cl_kernel(const cm_conv_args p) {
+  __shared__ float red[kTY][32][VEC * 5 + 1];
+  const int d0 = (blockIdx.x * 32 + threadIdx.x) * VEC;
+  const int l0 = (blockIdx.y * kTY + threadIdx.y) * kTL;
+  const int L = p.seqlen, W = p.width;
+  const bool active = (d0 < p.dim) && (l0 < L);
+  const int b = blockIdx.z;
+  const bool silu = (p.flags & CM_FLAG_SILU) != 0;
+  const int dsafe = (d0 < p.dim) ? d0 : 0;
+
+  float xw[kTL + 6][VEC];
+  float dxa[kTL][VEC];
+#pragma unroll
+  for (int i = 0; i < kTL; ++i)
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) dxa[i][v] = 0.f;
+  if (active) {
+    const T* xp = static_cast<const T*>(p.x.ptr) + b * p.x.sb + d0;
+#pragma unroll
+    for (int i = 0; i < kTL + 6; ++i) {
+      const int l = l0 - 3 + i;
+      if (l >= 0 && l < L) {
+        VecIO<T, VEC>::ld(xp + (int64_t)l * p.x.sl, xw[i]);
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) xw[i][v] = 0.f;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < kTL + 6; ++i)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) xw[i][v] = 0.f;
+  }
+
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    if (r < p.ndir) {   // CTA-uniform
+      const cm_conv_dir& dr = p.dir[r];
+      const bool anti = dr.anticausal != 0;
+      Taps<VEC> tp;
+      tp.load(dr, dsafe, W);
+      float dw[VEC][4], db[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        db[v] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dw[v][j] = 0.f;
+      }
+      if (active) {
+        const T* gp = static_cast<const T*>(dr.out.ptr) + b * dr.out.sb + d0;
+        // positions lq = l0 - 3 + q whose upstream gradient reaches this thread's dx rows:
+        //   causal:     l' in [l0, l0 + TL + 3)   -> q in [3, TL + 6)
+        //   anticausal: l' in [l0 - 3, l0 + TL)   -> q in [0, TL + 3)
+#pragma unroll
+        for (int q = 0; q < kTL + 6; ++q) {
+          const bool need = anti ? (q < kTL + 3) : (q >= 3);
+          const int lq = l0 - 3 + q;
+          if (need && lq >= 0 && lq < L) {
+            float go[VEC];
+            VecIO<T, VEC>::ld(gp + (int64_t)lq * dr.out.sl, go);
+            const bool own = (q >= 3) && (q < kTL + 3);   // lq in [l0, l0 + TL)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+              float g = go[v];
+              if (silu) {
+                float s = tp.b[v];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  // causal tap j reads x[lq-3+j] = xw[q-3+j+... ] ; window index of time t is t-(l0-3)
+                  const int xi = anti ? (q + 3 - j) : (q - 3 + j);
+                  const float xv = (xi >= 0 && xi < kTL + 6) ? xw[xi][v] : 0.f;
+                  s = fmaf(tp.w[v][j], xv, s);
+                }
+                g *= silu_grad(s);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int xi = anti ? (q + 3 - j) : (q - 3 + j);   // window index of the input this tap touches
+                const int di = xi - 3;                            // dx row (time l0 + di)
+                if (di >= 0 && di < kTL) dxa[di][v] = fmaf(tp.w[v][j], g, dxa[di][v]);
+                if (own) {
+                  const float xv = (xi >= 0 && xi < kTL + 6) ? xw[xi][v] : 0.f;
+                  dw[v][j] = fmaf(g, xv, dw[v][j]);
+                }
+              }
+              if (own) db[v] += g;
+            }
+          }
+        }
+      }
+      // reduce the kTY time chunks of this CTA, one partial row per (batch, 64-step chunk)
+      __syncthreads();
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) red[threadIdx.y][threadIdx.x][v * 5 + j] = dw[v][j];
+        red[threadIdx.y][threadIdx.x][v * 5 + 4] = db[v];
+      }
+      __syncthreads();
+      if (threadIdx.y == 0 && d0 < p.dim) {
+        const int64_t prow = (int64_t)b * gridDim.y + blockIdx.y;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float acc = 0.f;
+#pragma unroll
+            for (int y = 0; y < kTY; ++y) acc += red[y][threadIdx.x][v * 5 + j];
+            const int k = j - (4 - W);
+            if (k >= 0) dr.dweight_part[(prow * p.dim + d0 + v) * W + k] = acc;
+          }
+          if (dr.dbias_part) {
+            float acc = 0.f;
+#pragma unroll
+            for (int y = 0; y < kTY; ++y) acc += red[y][threadIdx.x][v * 5 + 4];
+            dr.dbias_part[prow * p.dim + d0 + v] = acc;
+          }
+        }
+      }
+    }
+  }
+  if (active) {
+    T* dxp = static_cast<T*>(p.dx.ptr) + b * p.dx.sb + d0;
+#pragma unroll
+    for (int i = 0; i < kTL; ++i) {
+      const int l = l0 + i;
+      if (l < L) VecIO<T, VEC>::st(dxp + (int64_t)l * p.dx.sl, dxa[i]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// generic-stride kernels: one thread per (b, d, l), lanes along time
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float ldx(const T* base, int64_t sl, int l, int L) {
+  return (l >= 0 && l < L) ? Elem<T>::ld(base + (int64_t)l * sl) : 0.f;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) conv_fwd_generic_kernel(const cm_conv_args p) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  const int d = blockIdx.y, b = blockIdx.z, L = p.seqlen, W = p.width;
+  if (l >= L) return;
+  const bool silu = (p.flags & CM_FLAG_SILU) != 0;
+  const T* xp = static_cast<const T*>(p.x.ptr) + b * p.x.sb + d * p.x.sd;
+  float xv[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) xv[i] = ldx(xp, p.x.sl, l - 3 + i, L);
+  for (int r = 0; r < p.ndir; ++r) {
+    const cm_conv_dir& dr = p.dir[r];
+    Taps<1> tp;
+    tp.load(dr, d, W);
+    float acc = tp.b[0];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc = fmaf(tp.w[0][j], dr.anticausal ? xv[6 - j] : xv[j], acc);
+    Elem<T>::st(static_cast<T*>(dr.out.ptr) + b * dr.out.sb + d * dr.out.sd + (int64_t)l * dr.out.sl,
+                silu ? silu_f(acc) : acc);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kChunk) conv_bwd_generic_kernel(const cm_conv_args p) {
+  __shared__ float red[kChunk / 32][5];
+  const int l = blockIdx.x * kChunk + threadIdx.x;
+  const int d = blockIdx.y, b = blockIdx.z, L = p.seqlen, W = p.width;
+  const bool silu = (p.flags & CM_FLAG_SILU) != 0;
+  const bool inb = l < L;
+  const T* xp = static_cast<const T*>(p.x.ptr) + b * p.x.sb + d * p.x.sd;
+  float xv[13];   // x[l-6 .. l+6]
+#pragma unroll
+  for (int i = 0; i < 13; ++i) xv[i] = inb ? ldx(xp, p.x.sl, l - 6 + i, L) : 0.f;
+  float dx = 0.f;
+  for (int r = 0; r < p.ndir; ++r) {
+    const cm_conv_dir& dr = p.dir[r];
+    const bool anti = dr.anticausal != 0;
+    Taps<1> tp;
+    tp.load(dr, d, W);
+    const T* gp = static_cast<const T*>(dr.out.ptr) + b * dr.out.sb + d * dr.out.sd;
+    float dw[4] = {0.f, 0.f, 0.f, 0.f}, db = 0.f;
+    if (inb) {
+      // upstream positions l' = l + o that touch x[l]:  causal o in [0,3] (tap j = 3-o), anticausal o in [-3,0] (tap j = 3+o)
+#pragma unroll
+      for (int oo = 0; oo < 4; ++oo) {
+        const int o = anti ? -oo : oo;
+        const int lp = l + o;
+        if (lp >= 0 && lp < L) {
+          float g = Elem<T>::ld(gp + (int64_t)lp * dr.out.sl);
+          if (silu) {
+            float s = tp.b[0];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int off = anti ? (o + 3 - j) : (o - 3 + j);   // input time relative to l
+              s = fmaf(tp.w[0][j], xv[6 + off], s);
+            }
+            g *= silu_grad(s);
+          }
+          dx = fmaf(tp.w[0][3 - oo], g, dx);
+          if (oo == 0) {   // own position: weight / bias gradients
+            db = g;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dw[j] = g * xv[6 + (anti ? (3 - j) : (j - 3))];
+          }
+        }
+      }
+    }
+    // CTA reduce of (dw[4], db)
+    float vals[5] = {dw[0], dw[1], dw[2], dw[3], db};
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) vals[i] += __shfl_xor_sync(0xffffffffu, vals[i], o);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) red[threadIdx.x >> 5][i] = vals[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < kChunk / 32; ++w) acc += red[w][threadIdx.x];
+      const int64_t prow = (int64_t)b * gridDim.x + blockIdx.x;
+      if (threadIdx.x < 4) {
+        const int k = threadIdx.x - (4 - W);
+        if (k >= 0) dr.dweight_part[(prow * p.dim + d) * W + k] = acc;
+      } else if (dr.dbias_part) {
+        dr.dbias_part[prow * p.dim + d] = acc;
+      }
+    }
+  }
+  if (inb) Elem<T>::st(static_cast<T*>(p.dx.ptr) + b * p.dx.sb + d * p.dx.sd + (int64_t)l * p.dx.sl, dx);
+}
+
+// single-token update --------------------------------------------------------------------------------
+template <typename T>
+__global__ void conv_update_kernel(const T* __restrict__ x, T* __restrict__ state, const float* __restrict__ w,
+                                   const float* __restrict__ bias, T* __restrict__ out, int batch, int dim, int W,
+                                   uint32_t flags) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)batch * dim) return;
+  const int d = idx % dim;
+  T* st = state + idx * W;
+  float acc = bias ? __ldg(bias + d) : 0.f;
+  for (int k = 0; k < W; ++k) {
+    const float v = (k + 1 < W) ? Elem<T>::round(static_cast<float>(st[k + 1])) : Elem<T>::ld(x + idx);
+    Elem<T>::st(st + k, v);
+    acc = fmaf(__ldg(w + (int64_t)d * W + k), v, acc);
+  }
+  Elem<T>::st(out + idx, (flags & CM_FLAG_SILU) ? silu_f(acc) : acc);
+}
+
+// ---- host dispatch ---------------------------------------------------------------------------------
+static bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+template <typename T>
+static int pick_vec(const cm_conv_args& a, bool bwd) {
+  // channel-last fast path needs unit channel stride everywhere
+  if (a.x.sd != 1) return 0;
+  if (bwd && a.dx.sd != 1) return 0;
+  for (int r = 0; r < a.ndir; ++r)
+    if (a.dir[r].out.sd != 1) return 0;
+  const int maxv = bwd ? 2 : 4;
+  for (int vec = maxv; vec >= 1; vec >>= 1) {
+    const size_t bytes = sizeof(T) * vec;
+    if (bytes > 16) continue;
+    bool ok = (a.dim % vec) == 0;
+    auto chk = [&](const cm_tensor3& t) {
+      ok = ok && aligned_to(t.ptr, bytes) && (t.sb % vec) == 0 && (t.sl % vec) == 0;
+    };
+    chk(a.x);
+    if (bwd) chk(a.dx);
+    for (int r = 0; r < a.ndir; ++r) chk(a.dir[r].out);
+    if (ok) return vec;
+  }
+  return 1;
+}
+
+template <typename T>
+static int launch_conv_t(const cm_conv_args& a, bool bwd, cudaStream_t st) {
+  const int vec = pick_vec<T>(a, bwd);
+  if (vec > 0) {
+    const dim3 block(32, kTY);
+    const dim3 grid(cm_ceil_div(cm_ceil_div(a.dim, vec), 32), cm_ceil_div(a.seqlen, kChunk), a.batch);
+    if (!bwd) {
+      if (vec == 4) conv_fwd_cl_kernel<T, 4><<<grid, block, 0, st>>>(a);
+      else if (vec == 2) conv_fwd_cl_kernel<T, 2><<<grid, block, 0, st>>>(a);
+      else conv_fwd_cl_kernel<T, 1><<<grid, block, 0, st>>>(a);
+    } else {
+      if (vec == 2) conv_bwd_cl_kernel<T, 2><<<grid, block, 0, st>>>(a);
+      else conv_bwd_cl_kernel<T, 1><<<grid, block, 0, st>>>(a);
+    }
+  } else {
+    if (a.dim > 65535) return CM_ERR_UNSUPPORTED;
+    if (!bwd) {
+      const dim3 grid(cm_ceil_div(a.seqlen, 128), a.dim, a.batch);
+      conv_fwd_generic_kernel<T><<<grid, 128, 0, st>>>(a);
+    } else {
+      const dim3 grid(cm_ceil_div(a.seqlen, kChunk), a.dim, a.batch);
+      conv_bwd_generic_kernel<T><<<grid, kChunk, 0, st>>>(a);
+    }
+  }
+  CM_LAUNCH_CHECK();
+  return 0;
+}
+
+static int check_conv(const cm_conv_args& a, bool bwd) {
+  if (a.batch <= 0 || a.dim <= 0 || a.seqlen <= 0) return CM_ERR_BAD_ARG;
+  if (a.ndir != 1 && a.ndir != 2) return CM_ERR_BAD_ARG;
+  if (!dtype_ok(a.dtype) || a.x.ptr == nullptr) return CM_ERR_BAD_ARG;
+  if (a.width < 2 || a.width > CM_CONV_MAX_WIDTH) return CM_ERR_UNSUPPORTED;
+  if (a.batch > 65535) return CM_ERR_UNSUPPORTED;
+  for (int r = 0; r < a.ndir; ++r) {
+    if (!a.dir[r].weight || !a.dir[r].out.ptr) return CM_ERR_BAD_ARG;
+    if (bwd && !a.dir[r].dweight_part) return CM_ERR_BAD_ARG;
+  }
+  if (bwd && a.dx.ptr == nullptr) return CM_ERR_BAD_ARG;
+  return 0;
+}
+
+}  // namespace cm
+
+extern "C" int cm_conv_num_part(int32_t batch, int32_t seqlen) {
+  if (batch <= 0 || seqlen <= 0) return 0;
+  return batch * cm_ceil_div(seqlen, cm::kChunk);
+}
+
+static int conv_dispatch(const cm_conv_args* args, bool bwd, void* stream) {
+  if (args == nullptr) return CM_ERR_BAD_ARG;
+  const int e = cm::check_conv(*args, bwd);
+  if (e) return e;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (args->dtype) {
+    case CM_F32: return cm::launch_conv_t<float>(*args, bwd, st);
+    case CM_BF16: return cm::launch_conv_t<__nv_bfloat16>(*args, bwd, st);
+    default: return cm::launch_conv_t<__half>(*args, bwd, st);
+  }
+}
+
+extern "C" int cm_conv_fwd(const cm_conv_args* args, void* stream) { return conv_dispatch(args, false, stream); }
+extern "C" int cm_conv_bwd(const cm_conv_args* args, void* stream) { return conv_dispatch(args, true, stream); }
+
+extern "C" int cm_conv_update(const void* x, void* conv_state, const float* weight, const float* bias, void* out,
+                              int32_t batch, int32_t dim, int32_t width, int32_t dtype, uint32_t flags, void* stream) {
+  if (!x || !conv_state || !weight || !out || batch <= 0 || dim <= 0) return CM_ERR_BAD_ARG;
+  if (!cm::dtype_ok(dtype)) return CM_ERR_BAD_ARG;
+  if (width < 2 || width > CM_CONV_MAX_WIDTH) return CM_ERR_UNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int threads = 128;
+  const unsigned blocks = (unsigned)(((int64_t)batch * dim + threads - 1) / threads);
+  switch (dtype) {
+    case CM_F32:
+      cm::conv_update_kernel<float><<<blocks, threads, 0, st>>>(static_cast<const float*>(x), static_cast<float*>(conv_state),
+                                                              weight, bias, static_cast<float*>(out), batch, dim, width, flags);
+      break;
+    case CM_BF16:
+      cm::conv_update_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>(
+          static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(conv_state), weight, bias,
+          static_cast<__nv_bfloat16*>(out), batch, dim, width, flags);
+      break;
+    default:
+      cm::conv_update_kernel<__half><<<blocks, threads, 0, st>>>(static_cast<const __half*>(x), static_cast<__half*>(conv_state),
+                                                               weight, bias, static_cast<__half*>(out), batch, dim, width, flags);
+      break;
+  }
+  CM_LAUNCH_CHECK();
+  return 0;
+}

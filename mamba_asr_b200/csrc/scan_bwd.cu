@@ -1,0 +1,398 @@
+// Selective-scan backward for sm_100a (both BiMamba directions in one launch).
+//
+// Replaces selective_scan_cuda.bwd (reference call sites modules/mamba/selective_scan_interface.py:67,252).
+// Same lane mapping as the forward kernel (one lane per channel, or LPC lanes per channel splitting the 16
+// states).  One CTA = one warp = 32/LPC channels of one batch row in one direction; grid.z = direction.
+//
+// The adjoint needs the forward state h_s and the reverse-time adjoint lambda_s at the same step.  Forward
+// saved h every CM_SCAN_CKPT_STEPS steps; here each 8-step tile (walked last -> first) is
+//   1. recomputed forward from its checkpoint, parking h_s for the 8 steps in shared memory (16 KB / warp),
+//   2. swept in reverse with   lambda = g*C + mu ;  mu <- a * lambda   carried in registers,
+// which never divides by the decay a = exp(Delta*A) (the reversible form is unstable when a underflows).
+// Adjoint formulas: SURVEY.md section 9.2; a*h_{s-1} is obtained as h_s - Delta*u*B.
+//
+// dB/dC need a sum over channels.  The reference kernel uses fp32 atomics per element; here the 32 channel
+// lanes of a warp are reduced through a padded shared-memory transpose (8 STS.128 + 32 LDS + 31 FADD per step)
+// and written as one coalesced 128-byte row of a [batch][slab][time][32] fp32 partial tensor that
+// cm_reduce_dbc() sums over slabs in a fixed order: deterministic, no atomics.
+// dA, dD, d(delta_bias) are per-row register sums written once per (batch, channel) and reduced over batch
+// by cm_reduce_rows().
+#include "common.cuh"
+
+namespace cm {
+
+constexpr int kTile = CM_SCAN_CKPT_STEPS;
+constexpr int kPitch = 36;
+
+template <int LPC>
+struct BwdSmem {
+  static constexpr int NS = 16 / LPC;
+  static constexpr int kRedPitch = 2 * NS + 4;
+  float4 h[kTile][NS / 4][32];    // recomputed states of the tile
+  float bc[kTile][kPitch];        // B (0..15) and C (16..31) of the tile's steps
+  float red[32][kRedPitch];       // cross-channel reduce scratch
+};
+
+template <int NS>
+__device__ __forceinline__ void load_row(const float* src, float (&dst)[NS]) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int i = 0; i < NS / 4; ++i) {
+    const float4 v = s4[i];
+    dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
+  }
+}
+
+template <typename T, int LPC, bool BC_CONST>
+__global__ void __launch_bounds__(32) scan_bwd_kernel(const cm_scan_bwd_args p) {
+  constexpr int NS = 16 / LPC, CPW = 32 / LPC;
+  using Smem = BwdSmem<LPC>;
+  __shared__ __align__(16) Smem sm;
+
+  const int lane = threadIdx.x;
+  const int r = blockIdx.z;
+  const cm_scan_bwd_dir& bd = (r == 0) ? p.dir[0] : p.dir[1];
+  const cm_scan_dir& dp = bd.in;
+  const int b = blockIdx.y, slab = blockIdx.x;
+  const int cl = lane / LPC, sg = lane % LPC;
+  int d = slab * CPW + cl;
+  const bool dvalid = d < p.dim;
+  if (!dvalid) d = p.dim - 1;
+  const int L = p.seqlen;
+  const bool rev = dp.reverse != 0;
+  const bool softplus = (p.flags & CM_FLAG_DELTA_SOFTPLUS) != 0;
+  const bool has_z = p.z.ptr != nullptr;
+  const bool do_dz = has_z && (r == 0);
+  const float scale = p.out_scale;
+  const float Dsk = dp.Dskip ? __ldg(dp.Dskip + d) : 0.f;
+  const float bias = dp.delta_bias ? __ldg(dp.delta_bias + d) : 0.f;
+
+  float kA[NS], mu[NS], dA[NS], Bc[NS], Cc[NS], dBacc[NS], dCacc[NS];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+    const int n = sg * NS + i;
+    kA[i] = (n < p.dstate) ? __ldg(dp.A + d * dp.A_sd + n * dp.A_sn) * kLog2e : 0.f;
+    mu[i] = 0.f; dA[i] = 0.f; Bc[i] = 0.f; Cc[i] = 0.f; dBacc[i] = 0.f; dCacc[i] = 0.f;
+    if (BC_CONST && n < p.dstate) {
+      Bc[i] = __ldg(static_cast<const float*>(dp.Bm.ptr) + d * dp.Bm.sb + n * dp.Bm.sd);   // constants are fp32
+      Cc[i] = __ldg(static_cast<const float*>(dp.Cm.ptr) + d * dp.Cm.sb + n * dp.Cm.sd);
+    }
+  }
+  float dD_acc = 0.f, dbias_acc = 0.f;
+
+  const T* up = static_cast<const T*>(dp.u.ptr) + b * dp.u.sb + d * dp.u.sd;
+  const T* dlp = static_cast<const T*>(dp.delta.ptr) + b * dp.delta.sb + d * dp.delta.sd;
+  const T* zp = has_z ? static_cast<const T*>(p.z.ptr) + b * p.z.sb + d * p.z.sd : nullptr;
+  const T* prep = do_dz ? static_cast<const T*>(p.out_pre.ptr) + b * p.out_pre.sb + d * p.out_pre.sd : nullptr;
+  const T* dop = static_cast<const T*>(p.dout.ptr) + b * p.dout.sb + d * p.dout.sd;
+  T* dzp = do_dz ? static_cast<T*>(p.dz.ptr) + b * p.dz.sb + d * p.dz.sd : nullptr;
+  T* dup = static_cast<T*>(bd.du.ptr) + b * bd.du.sb + d * bd.du.sd;
+  T* ddp = static_cast<T*>(bd.ddelta.ptr) + b * bd.ddelta.sb + d * bd.ddelta.sd;
+  const T* Bp = BC_CONST ? nullptr : static_cast<const T*>(dp.Bm.ptr) + b * dp.Bm.sb;
+  const T* Cp = BC_CONST ? nullptr : static_cast<const T*>(dp.Cm.ptr) + b * dp.Cm.sb;
+  const float* ckp = dp.ckpt + b * dp.ckpt_sb + d * dp.ckpt_sd;
+  float* partp = BC_CONST ? nullptr
+                          : bd.dBC_part + ((int64_t)b * gridDim.x + slab) * (int64_t)L * 32;
+
+  const int s1 = cm_first_range(L, p.ndir, dp.reverse);
+
+  // ranges are walked last -> first: [s1, L) (absent for ndir == 1) then [0, s1)
+  for (int range = (p.ndir == 2 ? 1 : 0); range >= 0; --range) {
+    const int s_begin = (range == 1) ? s1 : 0;
+    const int s_end = (range == 1) ? L : s1;
+    const int j0 = (range == 1) ? cm_ceil_div(s1, kTile) : 0;
+    const int ntile = cm_ceil_div(s_end - s_begin, kTile);
+    for (int t = ntile - 1; t >= 0; --t) {
+      const int s0 = s_begin + t * kTile;
+
+      // ---- phase 0: loads for the tile ----------------------------------------------------------
+      float uu[kTile], xx[kTile], gg[kTile];
+#pragma unroll
+      for (int k = 0; k < kTile; ++k) {
+        const int s = s0 + k;
+        uu[k] = 0.f; xx[k] = 0.f; gg[k] = 0.f;
+        if (s < s_end) {
+          const int64_t l = rev ? (L - 1 - s) : s;
+          uu[k] = Elem<T>::ld(up + l * dp.u.sl);
+          xx[k] = Elem<T>::ld(dlp + l * dp.delta.sl) + bias;
+          const float dov = Elem<T>::ld(dop + l * p.dout.sl) * scale;
+          if (has_z) {
+            const float zz = Elem<T>::ld(zp + l * p.z.sl);
+            const float sig = sigmoidf_fast(zz);
+            gg[k] = dov * zz * sig;
+            if (do_dz && sg == 0 && dvalid) {
+              const float ypre = Elem<T>::ld(prep + l * p.out_pre.sl);
+              Elem<T>::st(dzp + l * p.dz.sl, dov * ypre * sig * fmaf(zz, 1.f - sig, 1.f));
+            }
+          } else {
+            gg[k] = dov;
+          }
+        }
+      }
+      if (!BC_CONST) {
+        __syncwarp();
+        if (dp.Bm.sl == 1 && dp.Cm.sl == 1) {
+          // time-contiguous B/C: 4 lane groups x 8 steps, 8 passes over the 32 values
+          const int k = lane & 7, vq = lane >> 3;
+          const int s = s0 + k;
+#pragma unroll
+          for (int pass = 0; pass < 8; ++pass) {
+            const int v = pass * 4 + vq;
+            const int n = v & 15;
+            float val = 0.f;
+            if (s < s_end && n < p.dstate) {
+              const int64_t l = rev ? (L - 1 - s) : s;
+              val = (v < 16) ? Elem<T>::ld(Bp + n * dp.Bm.sd + l) : Elem<T>::ld(Cp + n * dp.Cm.sd + l);
+            }
+            sm.bc[k][v] = val;
+          }
+        } else {
+          const int n = lane & 15;
+          const T* src = (lane < 16) ? (Bp + n * dp.Bm.sd) : (Cp + n * dp.Cm.sd);
+          const int64_t sl = (lane < 16) ? dp.Bm.sl : dp.Cm.sl;
+#pragma unroll
+          for (int k = 0; k < kTile; ++k) {
+            const int s = s0 + k;
+            float val = 0.f;
+            if (s < s_end && n < p.dstate) val = Elem<T>::ld(src + (int64_t)(rev ? (L - 1 - s) : s) * sl);
+            sm.bc[k][lane] = val;
+          }
+        }
+        __syncwarp();
+      }
+
+      // ---- phase 1: recompute the tile's states from its checkpoint -------------------------------
+      float h[NS], dtv[kTile];
+      {
+        const float4* src = reinterpret_cast<const float4*>(ckp + (int64_t)(j0 + t) * 16 + sg * NS);
+#pragma unroll
+        for (int i = 0; i < NS / 4; ++i) {
+          const float4 v = __ldg(src + i);
+          h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kTile; ++k) {
+        dtv[k] = 0.f;
+        if (s0 + k < s_end) {
+          const float dt = softplus ? softplus_fwd<sizeof(T) == 4>(xx[k]) : xx[k];
+          dtv[k] = dt;
+          const float du_ = dt * uu[k];
+          float Bv[NS];
+          if (BC_CONST) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) Bv[i] = Bc[i];
+          } else {
+            load_row<NS>(&sm.bc[k][sg * NS], Bv);
+          }
+#pragma unroll
+          for (int i = 0; i < NS; ++i) h[i] = fmaf(ex2(dt * kA[i]), h[i], du_ * Bv[i]);
+#pragma unroll
+          for (int i = 0; i < NS / 4; ++i)
+            sm.h[k][i][lane] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+        }
+      }
+
+      // ---- phase 2: reverse sweep -----------------------------------------------------------------
+#pragma unroll
+      for (int k = kTile - 1; k >= 0; --k) {
+        const int s = s0 + k;
+        if (s < s_end) {
+          const int64_t l = rev ? (L - 1 - s) : s;
+          const float dt = dtv[k], u_ = uu[k], g = gg[k];
+          const float du_ = dt * u_;
+          float hk[NS];
+#pragma unroll
+          for (int i = 0; i < NS / 4; ++i) {
+            const float4 v = sm.h[k][i][lane];
+            hk[4 * i] = v.x; hk[4 * i + 1] = v.y; hk[4 * i + 2] = v.z; hk[4 * i + 3] = v.w;
+          }
+          float sLB = 0.f, sWA = 0.f;
+          float dBv[NS], dCv[NS], Bv[NS], Cv[NS];
+          if (BC_CONST) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) { Bv[i] = Bc[i]; Cv[i] = Cc[i]; }
+          } else {
+            load_row<NS>(&sm.bc[k][sg * NS], Bv);
+            load_row<NS>(&sm.bc[k][16 + sg * NS], Cv);
+          }
+#pragma unroll
+          for (int i = 0; i < NS; ++i) {
+            const float lam = fmaf(g, Cv[i], mu[i]);
+            dCv[i] = g * hk[i];
+            dBv[i] = lam * du_;
+            sLB = fmaf(lam, Bv[i], sLB);
+            const float hp = fmaf(-du_, Bv[i], hk[i]);   // = a * h_{s-1}
+            const float w = lam * hp;
+            sWA = fmaf(w, kA[i], sWA);
+            dA[i] = fmaf(w, dt, dA[i]);
+            mu[i] = ex2(dt * kA[i]) * lam;
+          }
+          if (LPC >= 2) {
+            sLB += __shfl_xor_sync(0xffffffffu, sLB, 1);
+            sWA += __shfl_xor_sync(0xffffffffu, sWA, 1);
+          }
+          if (LPC >= 4) {
+            sLB += __shfl_xor_sync(0xffffffffu, sLB, 2);
+            sWA += __shfl_xor_sync(0xffffffffu, sWA, 2);
+          }
+          const float du = fmaf(g, Dsk, dt * sLB);
+          const float ddt = fmaf(u_, sLB, kLn2 * sWA);
+          const float ddl = softplus ? ddt * softplus_grad(xx[k]) : ddt;
+          dD_acc = fmaf(g, u_, dD_acc);
+          dbias_acc += ddl;
+          if (sg == 0 && dvalid) {
+            Elem<T>::st(dup + l * bd.du.sl, du);
+            Elem<T>::st(ddp + l * bd.ddelta.sl, ddl);
+          }
+          if (BC_CONST) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) { dBacc[i] += dBv[i]; dCacc[i] += dCv[i]; }
+          } else {
+            // cross-channel reduce of the 32 per-step values
+            __syncwarp();
+            float4* dst = reinterpret_cast<float4*>(&sm.red[lane][0]);
+#pragma unroll
+            for (int i = 0; i < NS / 4; ++i) {
+              dst[i] = dvalid ? make_float4(dBv[4 * i], dBv[4 * i + 1], dBv[4 * i + 2], dBv[4 * i + 3])
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+              dst[NS / 4 + i] = dvalid ? make_float4(dCv[4 * i], dCv[4 * i + 1], dCv[4 * i + 2], dCv[4 * i + 3])
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncwarp();
+            const int n = lane & 15;
+            const int col = ((lane < 16) ? 0 : NS) + (n % NS);
+            const int row0 = n / NS;
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < CPW; c += 2) {
+              acc0 += sm.red[c * LPC + row0][col];
+              acc1 += sm.red[(c + 1) * LPC + row0][col];
+            }
+            partp[l * 32 + lane] = acc0 + acc1;
+          }
+        }
+      }
+    }
+  }
+
+  if (dvalid) {
+    const int64_t row = (int64_t)b * p.dim + d;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) bd.dA_part[row * 16 + sg * NS + i] = dA[i];
+    if (sg == 0) {
+      if (bd.dD_part) bd.dD_part[row] = dD_acc;
+      if (bd.dbias_part) bd.dbias_part[row] = dbias_acc;
+    }
+    if (BC_CONST) {
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        bd.dBC_part[row * 32 + sg * NS + i] = dBacc[i];
+        bd.dBC_part[row * 32 + 16 + sg * NS + i] = dCacc[i];
+      }
+    }
+  }
+}
+
+template <typename T>
+static int launch_bwd_t(const cm_scan_bwd_args& a, int lpc, bool bc_const, cudaStream_t st) {
+#define CM_BWD_CASE(LPC_, BCC_)                                                  \
+  {                                                                              \
+    const dim3 grid(cm_ceil_div(a.dim, 32 / LPC_), a.batch, a.ndir);             \
+    scan_bwd_kernel<T, LPC_, BCC_><<<grid, 32, 0, st>>>(a);                      \
+  }
+  if (!bc_const) {
+    if (lpc == 1) CM_BWD_CASE(1, false) else if (lpc == 2) CM_BWD_CASE(2, false) else CM_BWD_CASE(4, false)
+  } else {
+    if (lpc == 1) CM_BWD_CASE(1, true) else if (lpc == 2) CM_BWD_CASE(2, true) else CM_BWD_CASE(4, true)
+  }
+#undef CM_BWD_CASE
+  CM_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- deterministic reducers -----------------------------------------------------------------------
+template <typename T>
+__global__ void reduce_dbc_kernel(const float* __restrict__ part, int n_slab, int L, int dstate, cm_tensor3 dB,
+                                  cm_tensor3 dC) {
+  // one thread per (b, l, v): sums the slabs in order
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = idx & 31;
+  const int64_t bl = idx >> 5;
+  const int b = blockIdx.y;
+  if (bl >= L) return;
+  const float* src = part + ((int64_t)b * n_slab * L + bl) * 32 + v;
+  float acc = 0.f;
+  for (int s = 0; s < n_slab; ++s) acc += __ldg(src + (int64_t)s * L * 32);
+  const int n = v & 15;
+  if (n < dstate) {
+    const cm_tensor3& o = (v < 16) ? dB : dC;
+    Elem<T>::st(static_cast<T*>(o.ptr) + b * o.sb + n * o.sd + bl * o.sl, acc);
+  }
+}
+
+__global__ void reduce_rows_kernel(const float* __restrict__ part, int64_t rows, int64_t cols,
+                                   float* __restrict__ out) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float acc = 0.f;
+  for (int64_t r = 0; r < rows; ++r) acc += __ldg(part + r * cols + c);
+  out[c] = acc;
+}
+
+}  // namespace cm
+
+extern "C" int cm_scan_bwd(const cm_scan_bwd_args* args, void* stream) {
+  if (args == nullptr) return CM_ERR_BAD_ARG;
+  const cm_scan_bwd_args& a = *args;
+  if (a.batch <= 0 || a.dim <= 0 || a.seqlen <= 0 || a.dstate <= 0) return CM_ERR_BAD_ARG;
+  if (a.ndir != 1 && a.ndir != 2) return CM_ERR_BAD_ARG;
+  if (!cm::dtype_ok(a.dtype) || a.dout.ptr == nullptr) return CM_ERR_BAD_ARG;
+  if (a.dstate > CM_MAX_DSTATE || a.batch > 65535) return CM_ERR_UNSUPPORTED;
+  if (a.z.ptr != nullptr && (a.out_pre.ptr == nullptr || a.dz.ptr == nullptr)) return CM_ERR_BAD_ARG;
+  for (int r = 0; r < a.ndir; ++r) {
+    const cm_scan_bwd_dir& d = a.dir[r];
+    if (!d.in.u.ptr || !d.in.delta.ptr || !d.in.Bm.ptr || !d.in.Cm.ptr || !d.in.A || !d.in.ckpt) return CM_ERR_BAD_ARG;
+    if (!d.du.ptr || !d.ddelta.ptr || !d.dBC_part || !d.dA_part) return CM_ERR_BAD_ARG;
+  }
+  if (a.ndir == 2) {
+    if ((a.dir[0].in.reverse != 0) == (a.dir[1].in.reverse != 0)) return CM_ERR_BAD_ARG;
+    if (a.dir[0].in.bc_const != a.dir[1].in.bc_const) return CM_ERR_UNSUPPORTED;
+  }
+  int lpc = a.lanes_per_channel;
+  if (lpc == 0) lpc = cm_scan_pick_lanes(a.batch, a.dim, a.ndir);
+  if (lpc != 1 && lpc != 2 && lpc != 4) return CM_ERR_BAD_ARG;
+  const bool bcc = a.dir[0].in.bc_const != 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (a.dtype) {
+    case CM_F32: return cm::launch_bwd_t<float>(a, lpc, bcc, st);
+    case CM_BF16: return cm::launch_bwd_t<__nv_bfloat16>(a, lpc, bcc, st);
+    default: return cm::launch_bwd_t<__half>(a, lpc, bcc, st);
+  }
+}
+
+extern "C" int cm_reduce_dbc(const float* part, int32_t batch, int32_t n_slab, int32_t seqlen, int32_t dstate,
+                             int32_t dtype, cm_tensor3 dB, cm_tensor3 dC, void* stream) {
+  if (!part || !dB.ptr || !dC.ptr || batch <= 0 || n_slab <= 0 || seqlen <= 0 || dstate <= 0) return CM_ERR_BAD_ARG;
+  if (!cm::dtype_ok(dtype)) return CM_ERR_BAD_ARG;
+  if (dstate > CM_MAX_DSTATE || batch > 65535) return CM_ERR_UNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int threads = 256;
+  const dim3 grid(cm_ceil_div(seqlen * 32, threads), batch);
+  switch (dtype) {
+    case CM_F32: cm::reduce_dbc_kernel<float><<<grid, threads, 0, st>>>(part, n_slab, seqlen, dstate, dB, dC); break;
+    case CM_BF16: cm::reduce_dbc_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>(part, n_slab, seqlen, dstate, dB, dC); break;
+    default: cm::reduce_dbc_kernel<__half><<<grid, threads, 0, st>>>(part, n_slab, seqlen, dstate, dB, dC); break;
+  }
+  CM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cm_reduce_rows(const float* part, int64_t rows, int64_t cols, float* out, void* stream) {
+  if (!part || !out || rows <= 0 || cols <= 0) return CM_ERR_BAD_ARG;
+  const int threads = 128;
+  cm::reduce_rows_kernel<<<(unsigned)((cols + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      part, rows, cols, out);
+  CM_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,120 @@
+"""SpeechBrain-free assembly of the reference's CTC encoder stack, for the parity harness and ``bench.py``.
+
+Mirrors what ``train_CTC.py:ASR.compute_forward`` runs (reference train_CTC.py:285-302) with the objects the
+YAML builds (hparams/CTC/conmamba_large.yaml:187-227, 322-326):
+
+    Fbank -> InputNormalization(global) -> ConvolutionFrontEnd (2 x [conv 3x3 stride 2, LayerNorm, LeakyReLU])
+          -> TransformerASR.custom_src_module (Linear 640 -> d_model, Dropout)   (TransformerASR.py:773)
+          -> ConmambaEncoder (N x ConmambaEncoderLayer, final LayerNorm)
+          -> ctc_lin -> log_softmax
+
+Only Fbank and the Mamba mixers are hand-written kernels; the surrounding layers are torch (cuBLAS / cuDNN)
+stand-ins for the SpeechBrain modules, which are not installable here.  Parameter
+initialisation follows ``TransformerASR._init_params`` (xavier_normal_ on every >= 2-D parameter of the
+Transformer block, TransformerASR.py:1051-1054).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .conmamba import ConmambaEncoder
+from .fbank import Fbank
+
+# model blocks of the BASELINE.json configs
+CONFIGS = {
+    # hparams/S2S/conmamba_small.yaml:188-189,229-236 model block on the CTC recipe
+    "conmamba_small_ctc": dict(d_model=144, d_ffn=1024, num_layers=12, n_fft=400, win_length=25, n_mels=80,
+                               output_neurons=31, seed=7775),
+    # hparams/CTC/conmamba_large.yaml:153-183
+    "conmamba_large_ctc": dict(d_model=256, d_ffn=1024, num_layers=18, n_fft=512, win_length=32, n_mels=80,
+                               output_neurons=31, seed=3402),
+    # encoder of hparams/S2S/conmambamamba_large.yaml:251-287
+    "conmamba_large_s2s_encoder": dict(d_model=512, d_ffn=2048, num_layers=12, n_fft=512, win_length=32, n_mels=80,
+                                       output_neurons=5000, seed=3407),
+}
+
+
+class InputNormalization(nn.Module):
+    """Stand-in for speechbrain InputNormalization(norm_type="global") on its first batch: per-feature mean / std
+    over the valid frames of the batch."""
+
+    def forward(self, feats, wav_lens=None):
+        Bt, T, Fd = feats.shape
+        if wav_lens is None:
+            mean = feats.mean(dim=(0, 1))
+            std = feats.std(dim=(0, 1))
+        else:
+            n = torch.round(wav_lens.float() * T).clamp(min=1)
+            mask = (torch.arange(T, device=feats.device)[None, :] < n[:, None]).unsqueeze(-1).to(feats.dtype)
+            cnt = mask.sum(dim=1)
+            mean_u = (feats * mask).sum(dim=1) / cnt
+            var_u = (((feats - mean_u[:, None]) ** 2) * mask).sum(dim=1) / (cnt - 1).clamp(min=1)
+            mean, std = mean_u.mean(0), var_u.sqrt().mean(0)
+        return (feats - mean) / std.clamp(min=1e-10)
+
+
+class ConvFrontEnd(nn.Module):
+    """Stand-in for speechbrain ConvolutionFrontEnd(num_blocks=2, out_channels=(64, 32), kernel 3, stride 2)."""
+
+    def __init__(self, n_mels=80, out_channels=(64, 32)):
+        super().__init__()
+        blocks, c_in, f = [], 1, n_mels
+        self.norms = nn.ModuleList()
+        self.convs = nn.ModuleList()
+        for c_out in out_channels:
+            self.convs.append(nn.Conv2d(c_in, c_out, kernel_size=3, stride=2, padding=1))
+            f = (f - 1) // 2 + 1
+            self.norms.append(nn.LayerNorm([f, c_out]))
+            c_in = c_out
+        self.out_features = f * c_in
+
+    def forward(self, feats):
+        x = feats.unsqueeze(1)                                     # (B, 1, T, F)
+        for conv, norm in zip(self.convs, self.norms):
+            x = conv(x)                                            # (B, C, T', F')
+            x = F.leaky_relu(norm(x.permute(0, 2, 3, 1)))          # (B, T', F', C)
+            x = x.permute(0, 3, 1, 2)
+        x = x.permute(0, 2, 3, 1)                                  # (B, L, F'', C)
+        return x.reshape(x.shape[0], x.shape[1], -1)               # (B, L, 640)  (TransformerASR.py:760-762)
+
+
+class ConMambaCTC(nn.Module):
+    def __init__(self, d_model, d_ffn, num_layers, n_fft=512, win_length=32, n_mels=80, output_neurons=31,
+                 dropout=0.1, seed=None, d_state=16, expand=2, d_conv=4, bidirectional=True):
+        super().__init__()
+        self.compute_features = Fbank(sample_rate=16000, n_fft=n_fft, n_mels=n_mels, win_length=win_length)
+        self.normalize = InputNormalization()
+        self.CNN = ConvFrontEnd(n_mels)
+        self.custom_src_module = nn.Sequential(nn.Linear(self.CNN.out_features, d_model), nn.Dropout(dropout))
+        mamba_config = dict(d_state=d_state, expand=expand, d_conv=d_conv, bidirectional=bidirectional)
+        # Transformer.py:740-751: encoder activation is branchformer_activation (GELU), kernel 31, bias, non-causal
+        self.encoder = ConmambaEncoder(num_layers=num_layers, d_model=d_model, d_ffn=d_ffn, kernel_size=31,
+                                       activation=nn.GELU, bias=True, dropout=dropout, causal=False,
+                                       mamba_config=mamba_config)
+        self.ctc_lin = nn.Linear(d_model, output_neurons)
+        for p in list(self.custom_src_module.parameters()) + list(self.encoder.parameters()):
+            if p.dim() > 1:
+                nn.init.xavier_normal_(p)                          # TransformerASR.py:1051-1054
+
+    def features(self, wavs, wav_lens=None):
+        feats = self.compute_features(wavs)                        # (B, T, 80) fp32, no grad
+        return self.normalize(feats, wav_lens)
+
+    def encode(self, feats):
+        src = self.custom_src_module(self.CNN(feats))
+        out, _ = self.encoder(src)
+        return out
+
+    def forward(self, wavs, wav_lens=None):
+        """wavs: (B, n_samples) -> log-probs (B, L, output_neurons)"""
+        enc = self.encode(self.features(wavs, wav_lens))
+        return F.log_softmax(self.ctc_lin(enc), dim=-1)
+
+
+def build_model(name, **overrides):
+    cfg = dict(CONFIGS[name])
+    cfg.update(overrides)
+    seed = cfg.pop("seed", None)
+    if seed is not None:
+        torch.manual_seed(seed)
+    return ConMambaCTC(**cfg)

@@ -1,0 +1,373 @@
+"""Tensor-level launchers over the C ABI (include/conmamba_b200.h).
+
+Each function takes torch CUDA tensors, fills the POD argument block with raw pointers / element strides and
+enqueues the sm_100a kernels on torch's current stream.  Logical shapes follow the reference
+(u, delta, z: (B, D, L); variable B, C: (B, N, L)), but ANY strides are accepted - channel-last memory
+(a ``(B, L, D)`` buffer viewed through ``.transpose(1, 2)``) is the fast path.  No host synchronisation.
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import _cabi as cabi
+
+__all__ = ["scan_forward", "scan_backward", "conv_forward", "conv_backward", "conv_update", "fbank_logmel",
+           "empty_like_bdl", "num_ckpt"]
+
+
+def _require_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError("mamba_asr_b200: %s must be a CUDA tensor - the B200 kernels have no CPU fallback" % name)
+
+
+def empty_like_bdl(t, dtype=None):
+    """New (B, D, L) tensor with t's memory order (channel-last stays channel-last)."""
+    Bt, D, L = t.shape
+    dtype = dtype or t.dtype
+    if t.stride(1) == 1 and D > 1:
+        return torch.empty((Bt, L, D), dtype=dtype, device=t.device).transpose(1, 2)
+    return torch.empty((Bt, D, L), dtype=dtype, device=t.device)
+
+
+def num_ckpt(L, ndir):
+    return cabi.lib().cm_scan_num_ckpt(L, ndir)
+
+
+def _f32c(t, name):
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32 (reference keeps A, D, delta_bias in fp32, bimamba.py:200,232-233)" % name)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _fill_scan_dir(sd, d, keep, const_bc):
+    u, delta = d["u"], d["delta"]
+    sd.reverse = 1 if d.get("reverse", False) else 0
+    sd.bc_const = 1 if const_bc else 0
+    sd.u = cabi.t3(u)
+    sd.delta = cabi.t3(delta)
+    Bm, Cm = d["B"], d["C"]
+    if const_bc:
+        # (D, N) fp32 constants: the "batch" stride slot carries the channel stride
+        Bm, Cm = Bm.float().contiguous(), Cm.float().contiguous()
+        keep += [Bm, Cm]
+        sd.Bm = cabi.Tensor3(Bm.data_ptr(), Bm.stride(0), Bm.stride(1), 0)
+        sd.Cm = cabi.Tensor3(Cm.data_ptr(), Cm.stride(0), Cm.stride(1), 0)
+    else:
+        sd.Bm = cabi.t3(Bm)
+        sd.Cm = cabi.t3(Cm)
+    A = _f32c(d["A"], "A")
+    Dk = _f32c(d.get("D"), "D")
+    bias = _f32c(d.get("delta_bias"), "delta_bias")
+    keep += [A, Dk, bias]
+    sd.A = A.data_ptr()
+    sd.A_sd, sd.A_sn = A.stride(0), A.stride(1)
+    sd.Dskip = cabi.ptr(Dk)
+    sd.delta_bias = cabi.ptr(bias)
+
+
+def _check_dirs(dirs):
+    if len(dirs) not in (1, 2):
+        raise ValueError("1 or 2 scan directions")
+    u0 = dirs[0]["u"]
+    Bt, D, L = u0.shape
+    N = dirs[0]["A"].shape[1]
+    const_bc = dirs[0]["B"].dim() == 2
+    for d in dirs:
+        for k in ("u", "delta", "B", "C"):
+            _require_cuda(d[k], k)
+        if d["u"].shape != (Bt, D, L) or d["delta"].shape != (Bt, D, L):
+            raise ValueError("u / delta must be (B, D, L)")
+        if d["u"].dtype != u0.dtype or d["delta"].dtype != u0.dtype:
+            raise TypeError("u and delta must share one dtype")
+        if d["A"].shape != (D, N):
+            raise ValueError("A must be (D, N)")
+        if (d["B"].dim() == 2) != const_bc or (d["C"].dim() == 2) != const_bc:
+            raise NotImplementedError("B and C must both be input-dependent (B, N, L) or both constant (D, N)")
+        if const_bc:
+            if d["B"].shape != (D, N) or d["C"].shape != (D, N):
+                raise ValueError("constant B / C must be (D, N)")
+        else:
+            if d["B"].shape != (Bt, N, L) or d["C"].shape != (Bt, N, L):
+                raise ValueError("variable B / C must be (B, N, L)")
+        if not const_bc and (d["B"].dtype != u0.dtype or d["C"].dtype != u0.dtype):
+            raise TypeError("input-dependent B and C must have the dtype of u")
+    return Bt, D, L, N, const_bc
+
+
+def scan_forward(dirs, z=None, out_scale=1.0, delta_softplus=False, need_ckpt=False, need_last_state=False,
+                 need_out_pre=False, lanes=0):
+    """Fused selective scan forward (cm_scan_fwd).
+
+    dirs: list of 1 or 2 dicts {u, delta, A, B, C, D=None, delta_bias=None, reverse=False}.
+    Returns dict(out, out_pre, ckpt[list], last_state[list]).
+    """
+    lib = cabi.lib()
+    Bt, D, L, N, const_bc = _check_dirs(dirs)
+    u0 = dirs[0]["u"]
+    a = cabi.ScanFwdArgs()
+    a.batch, a.dim, a.seqlen, a.dstate = Bt, D, L, N
+    a.ndir = len(dirs)
+    a.dtype = cabi.dtype_code(u0.dtype)
+    a.flags = cabi.CM_FLAG_DELTA_SOFTPLUS if delta_softplus else 0
+    a.out_scale = float(out_scale)
+    a.lanes_per_channel = int(lanes) or int(os.environ.get("CM_SCAN_LANES", "0"))   # 0 = library heuristic
+    keep = []
+    ckpts, lasts = [], []
+    nck = lib.cm_scan_num_ckpt(L, len(dirs))
+    for r, d in enumerate(dirs):
+        sd = a.dir[r]
+        _fill_scan_dir(sd, d, keep, const_bc)
+        if need_ckpt:
+            ck = torch.empty((Bt, D, nck, 16), dtype=torch.float32, device=u0.device)
+            sd.ckpt = ck.data_ptr()
+            sd.ckpt_sb, sd.ckpt_sd = ck.stride(0), ck.stride(1)
+            ckpts.append(ck)
+        if need_last_state:
+            ls = torch.empty((Bt, D, N), dtype=torch.float32, device=u0.device)
+            sd.last_state = ls.data_ptr()
+            sd.ls_sb, sd.ls_sd, sd.ls_sn = ls.stride()
+            lasts.append(ls)
+    if z is not None:
+        _require_cuda(z, "z")
+        if z.shape != (Bt, D, L) or z.dtype != u0.dtype:
+            raise ValueError("z must match u in shape and dtype")
+    a.z = cabi.t3(z)
+    out = empty_like_bdl(u0)
+    a.out = cabi.t3(out)
+    out_pre = empty_like_bdl(u0) if need_out_pre else None
+    a.out_pre = cabi.t3(out_pre)
+    cabi.check(lib.cm_scan_fwd(C.byref(a), cabi.stream_ptr()), "cm_scan_fwd")
+    return dict(out=out, out_pre=out_pre, ckpt=ckpts, last_state=lasts)
+
+
+def scan_backward(dirs, ckpts, dout, z=None, out_pre=None, out_scale=1.0, delta_softplus=False, lanes=0,
+                  dz_out=None, dBC_like=None):
+    """Fused selective scan backward (cm_scan_bwd + deterministic reducers).
+
+    Returns dict(du[list], ddelta[list], dz, dB[list], dC[list], dA[list], dD[list], dbias[list]).
+    ``dz_out``: optional pre-allocated (B, D, L) view to receive dz (e.g. a slice of dxz).
+    ``dBC_like``: optional list (per direction) of (dB, dC) tensors to fill instead of allocating.
+    """
+    lib = cabi.lib()
+    Bt, D, L, N, const_bc = _check_dirs(dirs)
+    u0 = dirs[0]["u"]
+    dev = u0.device
+    a = cabi.ScanBwdArgs()
+    a.batch, a.dim, a.seqlen, a.dstate = Bt, D, L, N
+    a.ndir = len(dirs)
+    a.dtype = cabi.dtype_code(u0.dtype)
+    a.flags = cabi.CM_FLAG_DELTA_SOFTPLUS if delta_softplus else 0
+    a.out_scale = float(out_scale)
+    lpc = int(lanes) or int(os.environ.get("CM_SCAN_LANES", "0")) or lib.cm_scan_pick_lanes(Bt, D, len(dirs))
+    a.lanes_per_channel = lpc
+    slab_ch = lib.cm_scan_slab_channels(lpc)
+    n_slab = (D + slab_ch - 1) // slab_ch
+    keep = []
+    res = dict(du=[], ddelta=[], dB=[], dC=[], dA=[], dD=[], dbias=[], dz=None)
+    parts = []
+    for r, d in enumerate(dirs):
+        bd = a.dir[r]
+        _fill_scan_dir(bd.inp, d, keep, const_bc)
+        ck = ckpts[r]
+        bd.inp.ckpt = ck.data_ptr()
+        bd.inp.ckpt_sb, bd.inp.ckpt_sd = ck.stride(0), ck.stride(1)
+        du = empty_like_bdl(d["u"])
+        ddelta = empty_like_bdl(d["delta"])
+        bd.du, bd.ddelta = cabi.t3(du), cabi.t3(ddelta)
+        if const_bc:
+            bc_part = torch.empty((Bt, D, 32), dtype=torch.float32, device=dev)
+        else:
+            bc_part = torch.empty((Bt, n_slab, L, 32), dtype=torch.float32, device=dev)
+        dA_part = torch.empty((Bt, D, 16), dtype=torch.float32, device=dev)
+        dD_part = torch.empty((Bt, D), dtype=torch.float32, device=dev) if d.get("D") is not None else None
+        db_part = torch.empty((Bt, D), dtype=torch.float32, device=dev) if d.get("delta_bias") is not None else None
+        bd.dBC_part, bd.dA_part = bc_part.data_ptr(), dA_part.data_ptr()
+        bd.dD_part, bd.dbias_part = cabi.ptr(dD_part), cabi.ptr(db_part)
+        parts.append((bc_part, dA_part, dD_part, db_part))
+        res["du"].append(du)
+        res["ddelta"].append(ddelta)
+    _require_cuda(dout, "dout")
+    if dout.shape != (Bt, D, L):
+        raise ValueError("dout must be (B, D, L)")
+    if dout.dtype != u0.dtype:
+        dout = dout.to(u0.dtype)
+    a.dout = cabi.t3(dout)
+    if z is not None:
+        if out_pre is None:
+            raise ValueError("out_pre (pre-gate output saved by forward) is required when z is given")
+        dz = dz_out if dz_out is not None else empty_like_bdl(z)
+        a.z, a.out_pre, a.dz = cabi.t3(z), cabi.t3(out_pre), cabi.t3(dz)
+        res["dz"] = dz
+    st = cabi.stream_ptr()
+    cabi.check(lib.cm_scan_bwd(C.byref(a), st), "cm_scan_bwd")
+
+    for r, d in enumerate(dirs):
+        bc_part, dA_part, dD_part, db_part = parts[r]
+        dA = torch.empty((D, 16), dtype=torch.float32, device=dev)
+        cabi.check(lib.cm_reduce_rows(dA_part.data_ptr(), Bt, D * 16, dA.data_ptr(), st), "cm_reduce_rows")
+        res["dA"].append(dA[:, :N])
+        if dD_part is not None:
+            dD = torch.empty((D,), dtype=torch.float32, device=dev)
+            cabi.check(lib.cm_reduce_rows(dD_part.data_ptr(), Bt, D, dD.data_ptr(), st), "cm_reduce_rows")
+            res["dD"].append(dD)
+        else:
+            res["dD"].append(None)
+        if db_part is not None:
+            db = torch.empty((D,), dtype=torch.float32, device=dev)
+            cabi.check(lib.cm_reduce_rows(db_part.data_ptr(), Bt, D, db.data_ptr(), st), "cm_reduce_rows")
+            res["dbias"].append(db)
+        else:
+            res["dbias"].append(None)
+        if const_bc:
+            dBC = torch.empty((D, 32), dtype=torch.float32, device=dev)
+            cabi.check(lib.cm_reduce_rows(bc_part.data_ptr(), Bt, D * 32, dBC.data_ptr(), st), "cm_reduce_rows")
+            res["dB"].append(dBC[:, :N].to(d["B"].dtype))
+            res["dC"].append(dBC[:, 16:16 + N].to(d["C"].dtype))
+        else:
+            if dBC_like is not None:
+                dB, dC = dBC_like[r]
+            else:
+                dB = torch.empty_strided(d["B"].shape, _dense_strides(d["B"]), dtype=d["B"].dtype, device=dev)
+                dC = torch.empty_strided(d["C"].shape, _dense_strides(d["C"]), dtype=d["C"].dtype, device=dev)
+            cabi.check(lib.cm_reduce_dbc(bc_part.data_ptr(), Bt, n_slab, L, N, a.dtype, cabi.t3(dB), cabi.t3(dC), st),
+                       "cm_reduce_dbc")
+            res["dB"].append(dB)
+            res["dC"].append(dC)
+    return res
+
+
+def _dense_strides(t):
+    """Strides of a dense tensor with t's dimension order (views into wider buffers become compact)."""
+    order = sorted(range(t.dim()), key=lambda i: (t.stride(i), -i), reverse=True)
+    strides = [0] * t.dim()
+    acc = 1
+    for i in reversed(order):
+        strides[i] = acc
+        acc *= t.shape[i]
+    return strides
+
+
+# ------------------------------------------------------------------------------------------------------
+def _conv_common(x, dirs, silu):
+    lib = cabi.lib()
+    _require_cuda(x, "x")
+    Bt, D, L = x.shape
+    W = dirs[0]["weight"].shape[1]
+    a = cabi.ConvArgs()
+    a.batch, a.dim, a.seqlen, a.width = Bt, D, L, W
+    a.ndir = len(dirs)
+    a.dtype = cabi.dtype_code(x.dtype)
+    a.flags = cabi.CM_FLAG_SILU if silu else 0
+    a.x = cabi.t3(x)
+    keep = []
+    for r, d in enumerate(dirs):
+        w = d["weight"]
+        if w.shape != (D, W):
+            raise ValueError("conv weight must be (D, W)")
+        w = w.float().contiguous()
+        b = d.get("bias")
+        b = None if b is None else b.float().contiguous()
+        keep += [w, b]
+        cd = a.dir[r]
+        cd.anticausal = 1 if d.get("anticausal", False) else 0
+        cd.weight = w.data_ptr()
+        cd.bias = cabi.ptr(b)
+    return lib, a, keep, (Bt, D, L, W)
+
+
+def conv_forward(x, dirs, silu=True, outs=None):
+    """cm_conv_fwd.  x: (B, D, L) any strides; dirs: 1-2 dicts {weight (D, W), bias, anticausal}.
+    Returns the list of outputs (same memory order as x)."""
+    lib, a, keep, _ = _conv_common(x, dirs, silu)
+    res = []
+    for r in range(len(dirs)):
+        o = outs[r] if outs is not None else empty_like_bdl(x)
+        a.dir[r].out = cabi.t3(o)
+        res.append(o)
+    cabi.check(lib.cm_conv_fwd(C.byref(a), cabi.stream_ptr()), "cm_conv_fwd")
+    return res
+
+
+def conv_backward(x, dirs, douts, silu=True, dx_out=None):
+    """cm_conv_bwd.  Returns (dx, [dweight (D, W) fp32], [dbias (D,) fp32 or None])."""
+    lib, a, keep, (Bt, D, L, W) = _conv_common(x, dirs, silu)
+    dev = x.device
+    dx = dx_out if dx_out is not None else empty_like_bdl(x)
+    a.dx = cabi.t3(dx)
+    npart = lib.cm_conv_num_part(Bt, L)
+    parts = []
+    for r, d in enumerate(dirs):
+        g = douts[r]
+        if g.shape != x.shape:
+            raise ValueError("dout must match x")
+        if g.dtype != x.dtype:
+            g = g.to(x.dtype)
+        keep.append(g)
+        a.dir[r].out = cabi.t3(g)
+        wp = torch.empty((npart, D, W), dtype=torch.float32, device=dev)
+        bp = torch.empty((npart, D), dtype=torch.float32, device=dev) if d.get("bias") is not None else None
+        a.dir[r].dweight_part = wp.data_ptr()
+        a.dir[r].dbias_part = cabi.ptr(bp)
+        parts.append((wp, bp))
+    st = cabi.stream_ptr()
+    cabi.check(lib.cm_conv_bwd(C.byref(a), st), "cm_conv_bwd")
+    dws, dbs = [], []
+    for wp, bp in parts:
+        dw = torch.empty((D, W), dtype=torch.float32, device=dev)
+        cabi.check(lib.cm_reduce_rows(wp.data_ptr(), npart, D * W, dw.data_ptr(), st), "cm_reduce_rows")
+        dws.append(dw)
+        if bp is not None:
+            db = torch.empty((D,), dtype=torch.float32, device=dev)
+            cabi.check(lib.cm_reduce_rows(bp.data_ptr(), npart, D, db.data_ptr(), st), "cm_reduce_rows")
+            dbs.append(db)
+        else:
+            dbs.append(None)
+    return dx, dws, dbs
+
+
+def conv_update(x, conv_state, weight, bias=None, silu=False):
+    """cm_conv_update: x (B, D), conv_state (B, D, W) contiguous, updated in place; returns (B, D)."""
+    lib = cabi.lib()
+    _require_cuda(x, "x")
+    Bt, D = x.shape
+    W = weight.shape[1]
+    if not conv_state.is_contiguous() or conv_state.shape != (Bt, D, W) or conv_state.dtype != x.dtype:
+        raise ValueError("conv_state must be a contiguous (B, D, W) tensor of x's dtype")
+    x = x.contiguous()
+    w = weight.float().contiguous()
+    b = None if bias is None else bias.float().contiguous()
+    out = torch.empty_like(x)
+    cabi.check(lib.cm_conv_update(x.data_ptr(), conv_state.data_ptr(), w.data_ptr(), cabi.ptr(b), out.data_ptr(), Bt, D, W,
+                                  cabi.dtype_code(x.dtype), cabi.CM_FLAG_SILU if silu else 0, cabi.stream_ptr()),
+               "cm_conv_update")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+def fbank_logmel(stft, fbank, top_db=80.0, amin=1e-10, multiplier=10.0, db_offset=0.0):
+    """cm_fbank_logmel + cm_fbank_floor.  stft: complex64 (B, F, T) as returned by torch.stft; fbank: (F, M) fp32.
+    Returns (B, T, M) fp32 log-mel features with the per-utterance top_db floor applied."""
+    lib = cabi.lib()
+    _require_cuda(stft, "stft")
+    if stft.dtype != torch.complex64:
+        raise TypeError("stft must be complex64")
+    Bt, F, T = stft.shape
+    M = fbank.shape[1]
+    if fbank.shape[0] != F:
+        raise ValueError("fbank must be (n_bins, n_mels)")
+    fb = fbank.float().contiguous()
+    out = torch.empty((Bt, T, M), dtype=torch.float32, device=stft.device)
+    umax = torch.full((Bt,), float("-inf"), dtype=torch.float32, device=stft.device)
+    a = cabi.FbankArgs()
+    a.batch, a.frames, a.nbins, a.nmels = Bt, T, F, M
+    a.stft = stft.data_ptr()
+    a.s_b, a.s_f, a.s_t = stft.stride()
+    a.fbank, a.out, a.utt_max = fb.data_ptr(), out.data_ptr(), umax.data_ptr()
+    a.amin, a.multiplier, a.db_offset, a.top_db = amin, multiplier, db_offset, top_db
+    st = cabi.stream_ptr()
+    cabi.check(lib.cm_fbank_logmel(C.byref(a), st), "cm_fbank_logmel")
+    cabi.check(lib.cm_fbank_floor(C.byref(a), st), "cm_fbank_floor")
+    return out

@@ -1,0 +1,137 @@
+"""Channel-last Mamba inner block (conv -> x_proj -> dt_proj -> fused scan) as one autograd Function.
+
+This is the B200-native body behind ``Mamba.forward`` (both BiMamba-v2 directions in one pass) and behind the
+reference-signature wrappers in ``selective_scan_interface.py``.  It computes what the reference computes in
+``MambaInnerFnNoOutProj.forward/backward`` (modules/mamba/selective_scan_interface.py:160-294) called twice with
+a flip in between (modules/mamba/bimamba.py:223-253), but
+
+  * activations stay time-major / channel-last ``(B, L, D)``: in_proj output, x_proj input and out_proj input
+    need no transposes (the reference makes three transposing copies, :186-212), and every scan access is a
+    coalesced row segment;
+  * the two directions share one conv launch (one read of x), one scan launch (no ``flip``, one gate, one
+    output) and one launch each in backward;
+  * conv1d_out and delta are kept for backward instead of recomputed (the reference's checkpoint_lvl=1 saves
+    memory that a 180 GB part does not need to save).
+
+The dense projections are torch.matmul (cuBLAS tensor cores); everything else is the hand-written kernels.
+"""
+import torch
+
+from . import kernels as K
+
+
+def _as_bdl(t_bld):
+    """(B, L, D) memory -> logical (B, D, L) view."""
+    return t_bld.transpose(1, 2)
+
+
+class MambaInnerCL(torch.autograd.Function):
+    """y = MambaInnerCL.apply(xz, ndir, out_scale, reverse0, *params)
+
+    xz: (B, L, 2*D) with unit last stride.  ``params`` holds, per direction,
+    (conv_w (D,1,W), conv_b (D,)|None, x_proj_w (R+2N, D), dt_proj_w (D, R), A (D, N) fp32, Dskip (D,) fp32,
+    dt_bias (D,) fp32).  Direction 0 runs in time order ``reverse0`` (False = causal), direction 1 the opposite.
+    Returns y: (B, L, D) = out_scale * sum_dirs(scan) * silu(z).
+    """
+
+    NPER = 7
+
+    @staticmethod
+    def forward(ctx, xz, ndir, out_scale, reverse0, *params):
+        assert len(params) == ndir * MambaInnerCL.NPER
+        if xz.stride(-1) != 1:
+            xz = xz.contiguous()
+        Bt, L, twoD = xz.shape
+        D = twoD // 2
+        act = xz.dtype
+        need_grad = any(ctx.needs_input_grad)
+        x = _as_bdl(xz[..., :D])
+        z = _as_bdl(xz[..., D:])
+        P = [params[r * 7:(r + 1) * 7] for r in range(ndir)]
+        rev = [bool(reverse0) ^ (r == 1) for r in range(ndir)]
+        with torch.autocast("cuda", enabled=False):
+            conv_dirs = [dict(weight=p[0][:, 0, :], bias=p[1], anticausal=rev[r]) for r, p in enumerate(P)]
+            us = K.conv_forward(x, conv_dirs, silu=True)                     # logical (B, D, L), memory (B, L, D)
+            scan_dirs, x_dbls, deltas, wx, wdt = [], [], [], [], []
+            for r, p in enumerate(P):
+                xw = p[2].to(act)
+                dw = p[3].to(act)
+                R = dw.shape[1]
+                N = p[4].shape[1]
+                u_mem = us[r].transpose(1, 2)                                # (B, L, D) contiguous
+                x_dbl = torch.mm(u_mem.reshape(Bt * L, D), xw.t())           # (B*L, R+2N)
+                delta_mem = torch.mm(x_dbl[:, :R], dw.t()).view(Bt, L, D)    # (B, L, D)
+                xv = x_dbl.view(Bt, L, -1)
+                scan_dirs.append(dict(u=us[r], delta=_as_bdl(delta_mem), A=p[4],
+                                      B=_as_bdl(xv[..., R:R + N]), C=_as_bdl(xv[..., R + N:R + 2 * N]),
+                                      D=p[5], delta_bias=p[6], reverse=rev[r]))
+                x_dbls.append(x_dbl)
+                deltas.append(delta_mem)
+                wx.append(xw)
+                wdt.append(dw)
+            res = K.scan_forward(scan_dirs, z=z, out_scale=out_scale, delta_softplus=True,
+                                 need_ckpt=need_grad, need_out_pre=need_grad)
+        y = res["out"].transpose(1, 2)                                       # (B, L, D) contiguous memory
+        if need_grad:
+            ctx.ndir, ctx.out_scale, ctx.rev = ndir, out_scale, rev
+            ctx.n_us = len(us)
+            ctx.save_for_backward(xz, res["out_pre"], *us, *deltas, *x_dbls, *res["ckpt"], *wx, *wdt, *params)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        ndir, rev = ctx.ndir, ctx.rev
+        sv = ctx.saved_tensors
+        xz, out_pre = sv[0], sv[1]
+        k = 2
+        us = sv[k:k + ndir]; k += ndir
+        deltas = sv[k:k + ndir]; k += ndir
+        x_dbls = sv[k:k + ndir]; k += ndir
+        ckpts = sv[k:k + ndir]; k += ndir
+        wx = sv[k:k + ndir]; k += ndir
+        wdt = sv[k:k + ndir]; k += ndir
+        params = sv[k:]
+        P = [params[r * 7:(r + 1) * 7] for r in range(ndir)]
+        Bt, L, twoD = xz.shape
+        D = twoD // 2
+        act = xz.dtype
+        x = _as_bdl(xz[..., :D])
+        z = _as_bdl(xz[..., D:])
+        with torch.autocast("cuda", enabled=False):
+            dxz = torch.empty_like(xz)
+            scan_dirs, dx_dbls, dbc_like = [], [], []
+            for r, p in enumerate(P):
+                R = wdt[r].shape[1]
+                N = p[4].shape[1]
+                xv = x_dbls[r].view(Bt, L, -1)
+                scan_dirs.append(dict(u=us[r], delta=_as_bdl(deltas[r]), A=p[4],
+                                      B=_as_bdl(xv[..., R:R + N]), C=_as_bdl(xv[..., R + N:R + 2 * N]),
+                                      D=p[5], delta_bias=p[6], reverse=rev[r]))
+                dxd = torch.empty_like(x_dbls[r])
+                dv = dxd.view(Bt, L, -1)
+                dbc_like.append((_as_bdl(dv[..., R:R + N]), _as_bdl(dv[..., R + N:R + 2 * N])))
+                dx_dbls.append(dxd)
+            g = K.scan_backward(scan_dirs, ckpts, _as_bdl(dy), z=z, out_pre=out_pre, out_scale=ctx.out_scale,
+                                delta_softplus=True, dz_out=_as_bdl(dxz[..., D:]), dBC_like=dbc_like)
+            grads = []
+            conv_dirs, conv_douts = [], []
+            for r, p in enumerate(P):
+                R = wdt[r].shape[1]
+                u_mem = us[r].transpose(1, 2).reshape(Bt * L, D)
+                ddelta = g["ddelta"][r].transpose(1, 2).reshape(Bt * L, D)
+                du = g["du"][r].transpose(1, 2).reshape(Bt * L, D)
+                dxd = dx_dbls[r]
+                d_dtw = torch.mm(ddelta.t(), x_dbls[r][:, :R])                       # (D, R)
+                dxd[:, :R] = torch.mm(ddelta, wdt[r])                                # (B*L, R)
+                d_xw = torch.mm(dxd.t(), u_mem)                                      # (R+2N, D)
+                du.addmm_(dxd, wx[r])                                                # + x_proj back-prop (:282)
+                conv_dirs.append(dict(weight=p[0][:, 0, :], bias=p[1], anticausal=rev[r]))
+                conv_douts.append(g["du"][r])
+                grads.append([None, None, d_xw.to(p[2].dtype), d_dtw.to(p[3].dtype), g["dA"][r].to(p[4].dtype),
+                              g["dD"][r], g["dbias"][r]])
+            _, dws, dbs = K.conv_backward(x, conv_dirs, conv_douts, silu=True, dx_out=_as_bdl(dxz[..., :D]))
+            for r, p in enumerate(P):
+                grads[r][0] = dws[r].to(p[0].dtype).unsqueeze(1)
+                grads[r][1] = None if p[1] is None else dbs[r].to(p[1].dtype)
+        flat = [t for gr in grads for t in gr]
+        return (dxz, None, None, None, *flat)

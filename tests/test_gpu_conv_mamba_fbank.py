@@ -1,0 +1,252 @@
+"""GPU parity: causal conv1d kernels, the fused BiMamba-v2 block, the Fbank tail and the extension-module shims."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from cm_testutil import assert_close, channel_last, make_scan_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------------------------------------ conv
+@pytest.mark.parametrize("name", ["w4_bias", "w4_nobias", "w2_short"])
+@pytest.mark.parametrize("layout", ["tc", "cl"])
+def test_conv_matches_reference_golden(golden_dir, name, layout):
+    from mamba_asr_b200.causal_conv1d import causal_conv1d_fn
+    z = np.load(os.path.join(golden_dir, f"conv_{name}.npz"))
+    x = torch.from_numpy(z["in_x"]).cuda()
+    if layout == "cl":
+        x = channel_last(x)
+    x.requires_grad_(True)
+    w = torch.from_numpy(z["in_weight"]).cuda().requires_grad_(True)
+    b = torch.from_numpy(z["in_bias"]).cuda().requires_grad_(True) if "in_bias" in z else None
+    y = causal_conv1d_fn(x, w, b, activation="silu")
+    assert_close(y, torch.from_numpy(z["out"]), what="conv out")
+    (y * torch.from_numpy(z["cotangent"]).cuda()).sum().backward()
+    assert_close(x.grad, torch.from_numpy(z["grad_x"]), what="dx")
+    assert_close(w.grad, torch.from_numpy(z["grad_weight"]), floor="max", what="dweight")
+    if b is not None:
+        assert_close(b.grad, torch.from_numpy(z["grad_bias"]), floor="max", what="dbias")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 64, 67, 4), (1, 40, 130, 3), (3, 288, 100, 4), (2, 33, 17, 2), (2, 64, 1, 4)])
+@pytest.mark.parametrize("layout", ["tc", "cl"])
+def test_conv_bidirectional_fused(dtype, shape, layout):
+    """One launch producing causal (conv1d) and anticausal (conv1d_b on the flipped sequence) outputs, fwd + bwd."""
+    from mamba_asr_b200 import kernels as K
+    from oracle.conv_ref import causal_conv1d_oracle
+    Bt, D, L, W = shape
+    g = torch.Generator().manual_seed(L)
+    x = torch.randn(Bt, D, L, generator=g).to(dtype)
+    ws = [torch.randn(D, W, generator=g) * 0.5 for _ in range(2)]
+    bs = [torch.randn(D, generator=g) * 0.5 for _ in range(2)]
+    xc = x.clone().float().requires_grad_(True)
+    wc = [w.clone().requires_grad_(True) for w in ws]
+    bc = [b.clone().requires_grad_(True) for b in bs]
+    refs = [causal_conv1d_oracle(xc, wc[0], bc[0], "silu"), causal_conv1d_oracle(xc, wc[1], bc[1], "silu", anticausal=True)]
+    cots = [torch.randn(Bt, D, L, generator=g) for _ in range(2)]
+    (refs[0] * cots[0] + refs[1] * cots[1]).sum().backward()
+
+    xg = x.cuda()
+    if layout == "cl":
+        xg = channel_last(xg)
+    dirs = [dict(weight=ws[0].cuda(), bias=bs[0].cuda(), anticausal=False),
+            dict(weight=ws[1].cuda(), bias=bs[1].cuda(), anticausal=True)]
+    outs = K.conv_forward(xg, dirs, silu=True)
+    for r in range(2):
+        assert_close(outs[r].float(), refs[r], dtype, what=f"out[{r}]")
+    douts = [c.to(dtype).cuda() for c in cots]
+    if layout == "cl":
+        douts = [channel_last(t) for t in douts]
+    dx, dws, dbs = K.conv_backward(xg, dirs, douts, silu=True)
+    assert_close(dx.float(), xc.grad, dtype, what="dx")
+    for r in range(2):
+        assert_close(dws[r], wc[r].grad, dtype, floor="max", what=f"dw[{r}]")
+        assert_close(dbs[r], bc[r].grad, dtype, floor="max", what=f"db[{r}]")
+
+
+def test_conv_update_matches_oracle():
+    from mamba_asr_b200.causal_conv1d import causal_conv1d_update
+    from oracle.conv_ref import causal_conv1d_update_oracle
+    g = torch.Generator().manual_seed(0)
+    Bt, D, W = 3, 64, 4
+    state = torch.randn(Bt, D, W, generator=g)
+    w, b = torch.randn(D, W, generator=g), torch.randn(D, generator=g)
+    sg = state.clone().cuda()
+    for _ in range(5):
+        x = torch.randn(Bt, D, generator=g)
+        ref = causal_conv1d_update_oracle(x, state, w, b, "silu")
+        out = causal_conv1d_update(x.cuda(), sg, w.cuda(), b.cuda(), "silu")
+        assert_close(out, ref, what="update out")
+        assert torch.equal(sg.cpu(), state)
+
+
+# ------------------------------------------------------------------------------------------------ mamba block
+def _load_bimamba(golden_dir):
+    z = np.load(os.path.join(golden_dir, "bimamba_v2.npz"))
+    sd = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("p_")}
+    return z, sd
+
+
+def test_bimamba_v2_module_matches_reference_composition(golden_dir):
+    from mamba_asr_b200 import Mamba
+    z, sd = _load_bimamba(golden_dir)
+    meta = json.load(open(os.path.join(golden_dir, "mamba_state_dict.json")))
+    m = Mamba(d_model=meta["d_model"], bimamba_type="v2").cuda()
+    m.load_state_dict(sd, strict=True)
+    hidden = torch.from_numpy(z["hidden"]).cuda()
+    out = m(hidden)
+    assert_close(out, torch.from_numpy(z["out"]), what="bimamba v2 out", rtol_mul=2.0)
+    m.if_devide_out = False
+    assert_close(m(hidden), torch.from_numpy(z["out_nodivide"]), what="bimamba v2 out (sum)", rtol_mul=2.0)
+
+
+def test_bimamba_v2_gradients_match_oracle_autograd(golden_dir):
+    from mamba_asr_b200 import Mamba
+    from oracle.bimamba_ref import bimamba_v2_oracle
+    z, sd = _load_bimamba(golden_dir)
+    meta = json.load(open(os.path.join(golden_dir, "mamba_state_dict.json")))
+    m = Mamba(d_model=meta["d_model"], bimamba_type="v2").cuda()
+    m.load_state_dict(sd, strict=True)
+    hidden = torch.from_numpy(z["hidden"])
+    hc = hidden.clone().requires_grad_(True)
+    pc = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = bimamba_v2_oracle(hc, pc)
+    cot = torch.randn(ref.shape, generator=torch.Generator().manual_seed(3))
+    (ref * cot).sum().backward()
+    hg = hidden.cuda().requires_grad_(True)
+    out = m(hg)
+    (out * cot.cuda()).sum().backward()
+    assert_close(hg.grad, hc.grad, what="d hidden", rtol_mul=2.0)
+    for name, p in m.named_parameters():
+        assert p.grad is not None, name
+        assert_close(p.grad, pc[name].grad, floor="max", what=f"d {name}", rtol_mul=2.0)
+
+
+def test_bimamba_v2_bf16_autocast_within_tolerance(golden_dir):
+    """bf16 path (autocast, as precision: bf16 in the YAML) against the fp32 oracle fed the same parameters."""
+    from mamba_asr_b200 import Mamba
+    z, sd = _load_bimamba(golden_dir)
+    meta = json.load(open(os.path.join(golden_dir, "mamba_state_dict.json")))
+    m = Mamba(d_model=meta["d_model"], bimamba_type="v2").cuda()
+    m.load_state_dict(sd, strict=True)
+    hidden = torch.from_numpy(z["hidden"]).cuda()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = m(hidden)
+    assert out.dtype == torch.bfloat16
+    assert_close(out.float(), torch.from_numpy(z["out"]), torch.bfloat16, what="bf16 out")
+
+
+def test_unimamba_matches_oracle():
+    from mamba_asr_b200 import UniMamba
+    from oracle.bimamba_ref import mamba_inner_oracle
+    torch.manual_seed(5)
+    m = UniMamba(d_model=48).cuda()
+    for p in m.parameters():
+        if p.dim() > 1:
+            torch.nn.init.xavier_normal_(p)
+    hidden = torch.randn(2, 53, 48)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    xz = (sd["in_proj.weight"] @ hidden.reshape(-1, 48).t()).reshape(-1, 2, 53).transpose(0, 1)
+    y = mamba_inner_oracle(xz, sd["conv1d.weight"], sd["conv1d.bias"], sd["x_proj.weight"], sd["dt_proj.weight"],
+                           -torch.exp(sd["A_log"]), sd["D"], sd["dt_proj.bias"])
+    ref = F.linear(y.transpose(1, 2), sd["out_proj.weight"])
+    assert_close(m(hidden.cuda()), ref, what="unimamba out", rtol_mul=2.0)
+
+
+def test_reference_signature_inner_fn_time_contiguous_layout(golden_dir):
+    """mamba_inner_fn_no_out_proj with the reference's (B, 2D, L) xz view (strides (L, B*L, 1), bimamba.py:192-196)."""
+    from mamba_asr_b200.selective_scan_interface import mamba_inner_fn_no_out_proj
+    from oracle.bimamba_ref import mamba_inner_oracle
+    z, sd = _load_bimamba(golden_dir)
+    hidden = torch.from_numpy(z["hidden"])
+    Bt, L, d = hidden.shape
+    xz = (sd["in_proj.weight"] @ hidden.reshape(Bt * L, d).t()).reshape(-1, Bt, L).transpose(0, 1)
+    A = -torch.exp(sd["A_log"])
+    ref = mamba_inner_oracle(xz, sd["conv1d.weight"], sd["conv1d.bias"], sd["x_proj.weight"], sd["dt_proj.weight"], A,
+                             sd["D"], sd["dt_proj.bias"])
+    xg = (sd["in_proj.weight"].cuda() @ hidden.cuda().reshape(Bt * L, d).t()).reshape(-1, Bt, L).transpose(0, 1)
+    out = mamba_inner_fn_no_out_proj(xg, sd["conv1d.weight"].cuda(), sd["conv1d.bias"].cuda(), sd["x_proj.weight"].cuda(),
+                                     sd["dt_proj.weight"].cuda(), A.cuda(), None, None, sd["D"].cuda(),
+                                     delta_bias=sd["dt_proj.bias"].cuda(), delta_softplus=True)
+    assert out.shape == ref.shape
+    assert_close(out, ref, what="inner fn out", rtol_mul=2.0)
+
+
+# ------------------------------------------------------------------------------------------------ extension shims
+def test_extension_module_shims_follow_the_pybind_abi():
+    """compat/selective_scan_cuda + causal_conv1d_cuda: argument order / return lists of the reference call sites
+    (selective_scan_interface.py:42, 67-70, 182, 286)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "compat"))
+    import causal_conv1d_cuda
+    import selective_scan_cuda
+    from oracle.conv_ref import causal_conv1d_oracle
+    from oracle.scan_ref import selective_scan_oracle
+    ins = make_scan_inputs(2, 64, 70, 16, torch.float32, seed=9)
+    c = {k: v.cuda() for k, v in ins.items()}
+    B4, C4 = c["B"].unsqueeze(1).contiguous(), c["C"].unsqueeze(1).contiguous()
+    out, x, out_z = selective_scan_cuda.fwd(c["u"], c["delta"], c["A"], B4, C4, c["D"], c["z"], c["delta_bias"], True)
+    ref_z, last = selective_scan_oracle(ins["u"], ins["delta"], ins["A"], ins["B"], ins["C"], ins["D"], ins["z"],
+                                        ins["delta_bias"], True, return_last_state=True)
+    ref_pre = selective_scan_oracle(ins["u"], ins["delta"], ins["A"], ins["B"], ins["C"], ins["D"], None,
+                                    ins["delta_bias"], True)
+    assert_close(out_z, ref_z, what="out_z")
+    assert_close(out, ref_pre, what="out")
+    assert x.dim() == 4 and x.shape[:2] == (2, 64) and x.shape[-1] == 32
+    assert_close(x[:, :, -1, 1::2], last, what="last_state via x[:, :, -1, 1::2]")
+    dout = torch.randn_like(out_z)
+    dz = torch.empty_like(c["z"])
+    ret = selective_scan_cuda.bwd(c["u"], c["delta"], c["A"], B4, C4, c["D"], c["z"], c["delta_bias"], dout, x, out, dz,
+                                  True, True)
+    assert len(ret) == 9 and ret[7].data_ptr() == dz.data_ptr() and ret[3].shape == B4.shape
+    leaf = {k: v.clone().requires_grad_(True) for k, v in ins.items()}
+    r = selective_scan_oracle(leaf["u"], leaf["delta"], leaf["A"], leaf["B"], leaf["C"], leaf["D"], leaf["z"],
+                              leaf["delta_bias"], True)
+    (r * dout.cpu()).sum().backward()
+    assert_close(ret[0], leaf["u"].grad, what="du")
+    assert_close(ret[1], leaf["delta"].grad, what="ddelta")
+    assert_close(ret[2], leaf["A"].grad, floor="max", what="dA")
+    assert_close(ret[3][:, 0], leaf["B"].grad, floor="max", what="dB")
+    assert_close(ret[7], leaf["z"].grad, what="dz")
+    assert_close(ret[8], ref_z, what="recomputed out_z")
+
+    g = torch.Generator().manual_seed(1)
+    xx, w, b = torch.randn(2, 64, 50, generator=g), torch.randn(64, 4, generator=g), torch.randn(64, generator=g)
+    y = causal_conv1d_cuda.causal_conv1d_fwd(xx.cuda(), w.cuda(), b.cuda(), None, True)
+    assert_close(y, causal_conv1d_oracle(xx, w, b, "silu"), what="conv fwd shim")
+    dxz = torch.empty(2, 128, 50, device="cuda")
+    dx, dw, db = causal_conv1d_cuda.causal_conv1d_bwd(xx.cuda(), w.cuda(), b.cuda(), torch.ones_like(y), None,
+                                                      dxz[:, :64], True)
+    assert dx.data_ptr() == dxz.data_ptr() and dw.shape == (64, 4) and db.shape == (64,)
+
+
+# ------------------------------------------------------------------------------------------------ fbank
+@pytest.mark.parametrize("cfg", [dict(n_fft=512, win_length=32), dict(n_fft=400, win_length=25)])
+def test_fbank_matches_oracle(cfg):
+    from mamba_asr_b200 import Fbank
+    from oracle.fbank_ref import fbank_oracle
+    g = torch.Generator().manual_seed(3402)
+    wav = 0.1 * torch.randn(3, 16000 * 2 + 37, generator=g)
+    wav[1, 9000:] = 0.0                      # a padded utterance: the top_db floor must kick in
+    fb = Fbank(sample_rate=16000, n_mels=80, **cfg).cuda()
+    out = fb(wav.cuda())
+    ref = fbank_oracle(wav, n_fft=cfg["n_fft"], win_length_ms=cfg["win_length"])
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    # dB values; same STFT algorithm on a different FFT library: compare with the fp32 contract on the dB scale
+    assert_close(out, ref, floor="max", what="fbank dB")
+    assert float((out[1].max() - out[1].min()).cpu()) <= 80.0 + 1e-3
+
+
+def test_fbank_frame_count_is_bit_exact():
+    from mamba_asr_b200 import Fbank
+    from oracle.lengths_ref import fbank_frames
+    fb = Fbank(n_fft=400, n_mels=80).cuda()
+    for n in (16000, 159999, 160000, 160001, 240000):
+        assert fb(torch.zeros(1, n, device="cuda")).shape[1] == fbank_frames(n)

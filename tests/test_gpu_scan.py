@@ -1,0 +1,205 @@
+"""GPU parity of the selective-scan kernels against the oracle and the golden fixtures frozen from the reference.
+Every call goes Python wrapper -> ctypes -> C ABI (libconmamba_b200.so) -> sm_100a kernel."""
+import numpy as np
+import pytest
+import torch
+
+from cm_testutil import RTOL, assert_close, channel_last, load_scan_golden, make_scan_inputs
+
+pytestmark = pytest.mark.gpu
+
+GRAD_KEYS = ("u", "delta", "A", "B", "C", "D", "z", "delta_bias")
+SUM_KEYS = ("A", "B", "C", "D", "delta_bias")     # gradients that are sums over many positions
+
+
+def _cuda(ins, layout="tc"):
+    out = {}
+    for k, v in ins.items():
+        if v is None:
+            out[k] = None
+            continue
+        t = v.cuda()
+        if layout == "cl" and t.dim() == 3:
+            t = channel_last(t)
+        out[k] = t
+    return out
+
+
+def _fn():
+    from mamba_asr_b200.selective_scan_interface import selective_scan_fn
+    return selective_scan_fn
+
+
+@pytest.mark.parametrize("name", ["f32_full", "f32_s4d", "f32_plain4d", "f32_constBC", "bf16_full", "f32_L1"])
+@pytest.mark.parametrize("layout", ["tc", "cl"])
+def test_scan_forward_matches_reference_golden(golden_dir, name, layout):
+    z, meta, ins, dt = load_scan_golden(golden_dir, name)
+    c = _cuda(ins, layout)
+    out, last = _fn()(c["u"], c["delta"], c["A"], c["B"], c["C"], c["D"], c["z"], c["delta_bias"],
+                      delta_softplus=meta["softplus"], return_last_state=True)
+    assert out.dtype == dt and out.shape == tuple(z["out"].shape)
+    assert_close(out.float(), torch.from_numpy(z["out"]), dt, what=f"{name} out")
+    assert_close(last, torch.from_numpy(z["last_state"]), dt, what=f"{name} last_state")
+
+
+@pytest.mark.parametrize("name", ["f32_full", "f32_s4d", "f32_plain4d", "f32_L1"])
+@pytest.mark.parametrize("layout", ["tc", "cl"])
+def test_scan_backward_matches_reference_autograd(golden_dir, name, layout):
+    z, meta, ins, dt = load_scan_golden(golden_dir, name)
+    c = _cuda(ins, layout)
+    leaf = {k: (v.requires_grad_(True) if v is not None else None) for k, v in c.items()}
+    out = _fn()(leaf["u"], leaf["delta"], leaf["A"], leaf["B"], leaf["C"], leaf["D"], leaf["z"], leaf["delta_bias"],
+                delta_softplus=meta["softplus"])
+    (out * torch.from_numpy(z["cotangent"]).cuda()).sum().backward()
+    for k in GRAD_KEYS:
+        if leaf[k] is None:
+            continue
+        assert leaf[k].grad.shape == leaf[k].shape
+        assert_close(leaf[k].grad, torch.from_numpy(z["grad_" + k]), dt, floor="max" if k in SUM_KEYS else "rms",
+                     what=f"{name} grad_{k}")
+
+
+@pytest.mark.parametrize("lanes", [1, 2, 4])
+@pytest.mark.parametrize("shape", [(2, 64, 67), (1, 40, 131), (3, 96, 8), (2, 32, 9), (2, 33, 40)])
+def test_scan_lane_splits_and_ragged_shapes(lanes, shape, monkeypatch):
+    """1/2/4 lanes per channel; dims that are not multiples of the warp's channel count; L around the 8-step tile."""
+    from oracle.scan_ref import selective_scan_oracle
+    monkeypatch.setenv("CM_SCAN_LANES", str(lanes))
+    Bt, D, L = shape
+    ins = make_scan_inputs(Bt, D, L, 16, torch.float32, seed=L)
+    c = _cuda(ins, "cl")
+    lc = {k: v.clone().requires_grad_(True) for k, v in ins.items()}
+    lg = {k: v.requires_grad_(True) for k, v in c.items()}
+    ref = selective_scan_oracle(lc["u"], lc["delta"], lc["A"], lc["B"], lc["C"], lc["D"], lc["z"], lc["delta_bias"], True)
+    out = _fn()(lg["u"], lg["delta"], lg["A"], lg["B"], lg["C"], lg["D"], lg["z"], lg["delta_bias"], True)
+    assert_close(out, ref, what="out")
+    cot = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1))
+    (ref * cot).sum().backward()
+    (out * cot.cuda()).sum().backward()
+    for k in GRAD_KEYS:
+        assert_close(lg[k].grad, lc[k].grad, floor="max" if k in SUM_KEYS else "rms", what=f"grad_{k}")
+
+
+@pytest.mark.parametrize("dstate", [4, 8, 16])
+def test_scan_small_dstate(dstate):
+    from oracle.scan_ref import selective_scan_oracle
+    ins = make_scan_inputs(2, 32, 50, dstate, torch.float32, seed=3)
+    c = _cuda(ins, "cl")
+    ref = selective_scan_oracle(ins["u"], ins["delta"], ins["A"], ins["B"], ins["C"], ins["D"], ins["z"],
+                                ins["delta_bias"], True)
+    out = _fn()(c["u"], c["delta"], c["A"], c["B"], c["C"], c["D"], c["z"], c["delta_bias"], True)
+    assert_close(out, ref, what=f"dstate {dstate}")
+
+
+def test_scan_rejects_what_it_does_not_implement():
+    ins = make_scan_inputs(1, 32, 16, 32, torch.float32)
+    c = _cuda(ins)
+    with pytest.raises(NotImplementedError):
+        _fn()(c["u"], c["delta"], c["A"], c["B"], c["C"])
+    cpu = make_scan_inputs(1, 32, 16, 16, torch.float32)
+    with pytest.raises(RuntimeError):      # no CPU fallback
+        _fn()(cpu["u"], cpu["delta"], cpu["A"], cpu["B"], cpu["C"])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_bidirectional_fused_equals_flip_composition(dtype):
+    """cm_scan_fwd with ndir=2 == 0.5*out + 0.5*out_b.flip(-1) of bimamba.py:223-253 built from the oracle."""
+    from mamba_asr_b200 import kernels as K
+    from oracle.scan_ref import selective_scan_oracle
+    Bt, D, L, N = 2, 64, 77, 16
+    f = make_scan_inputs(Bt, D, L, N, dtype, seed=1)
+    bwd = make_scan_inputs(Bt, D, L, N, dtype, seed=2)
+    z = f["z"]
+    of = selective_scan_oracle(f["u"], f["delta"], f["A"], f["B"], f["C"], f["D"], z, f["delta_bias"], True)
+    fl = lambda t: t.flip(-1)
+    ob = selective_scan_oracle(fl(bwd["u"]), fl(bwd["delta"]), bwd["A"], fl(bwd["B"]), fl(bwd["C"]), bwd["D"], fl(z),
+                               bwd["delta_bias"], True)
+    ref = 0.5 * of.float() + 0.5 * fl(ob).float()
+    dirs = []
+    for src, rev in ((f, False), (bwd, True)):
+        c = _cuda(src, "cl")
+        dirs.append(dict(u=c["u"], delta=c["delta"], A=c["A"], B=c["B"], C=c["C"], D=c["D"],
+                         delta_bias=c["delta_bias"], reverse=rev))
+    res = K.scan_forward(dirs, z=channel_last(z.cuda()), out_scale=0.5, delta_softplus=True)
+    assert_close(res["out"].float(), ref, dtype, what="bidir out")
+
+
+def test_bidirectional_backward_matches_autograd_of_flip_composition():
+    from mamba_asr_b200 import kernels as K
+    from oracle.scan_ref import selective_scan_oracle
+    Bt, D, L, N = 2, 64, 45, 16
+    f = make_scan_inputs(Bt, D, L, N, torch.float32, seed=11)
+    bw = make_scan_inputs(Bt, D, L, N, torch.float32, seed=12)
+    lf = {k: v.clone().requires_grad_(True) for k, v in f.items()}
+    lb = {k: v.clone().requires_grad_(True) for k, v in bw.items() if k != "z"}
+    fl = lambda t: t.flip(-1)
+    of = selective_scan_oracle(lf["u"], lf["delta"], lf["A"], lf["B"], lf["C"], lf["D"], lf["z"], lf["delta_bias"], True)
+    ob = selective_scan_oracle(fl(lb["u"]), fl(lb["delta"]), lb["A"], fl(lb["B"]), fl(lb["C"]), lb["D"], fl(lf["z"]),
+                               lb["delta_bias"], True)
+    ref = 0.5 * of + 0.5 * fl(ob)
+    cot = torch.randn(ref.shape, generator=torch.Generator().manual_seed(5))
+    (ref * cot).sum().backward()
+
+    dirs = []
+    for src, rev in ((f, False), (bw, True)):
+        c = _cuda(src, "cl")
+        dirs.append(dict(u=c["u"], delta=c["delta"], A=c["A"], B=c["B"], C=c["C"], D=c["D"],
+                         delta_bias=c["delta_bias"], reverse=rev))
+    zc = channel_last(f["z"].cuda())
+    res = K.scan_forward(dirs, z=zc, out_scale=0.5, delta_softplus=True, need_ckpt=True, need_out_pre=True)
+    g = K.scan_backward(dirs, res["ckpt"], channel_last(cot.cuda()), z=zc, out_pre=res["out_pre"], out_scale=0.5,
+                        delta_softplus=True)
+    assert_close(g["dz"], lf["z"].grad, what="dz")
+    for r, leaf in enumerate((lf, lb)):
+        assert_close(g["du"][r], leaf["u"].grad, what=f"du[{r}]")
+        assert_close(g["ddelta"][r], leaf["delta"].grad, what=f"ddelta[{r}]")
+        assert_close(g["dB"][r], leaf["B"].grad, floor="max", what=f"dB[{r}]")
+        assert_close(g["dC"][r], leaf["C"].grad, floor="max", what=f"dC[{r}]")
+        assert_close(g["dA"][r], leaf["A"].grad, floor="max", what=f"dA[{r}]")
+        assert_close(g["dD"][r], leaf["D"].grad, floor="max", what=f"dD[{r}]")
+        assert_close(g["dbias"][r], leaf["delta_bias"].grad, floor="max", what=f"dbias[{r}]")
+
+
+def test_scan_backward_is_deterministic():
+    ins = make_scan_inputs(4, 96, 200, 16, torch.bfloat16, seed=7)
+    c = _cuda(ins, "cl")
+    grads = []
+    for _ in range(2):
+        leaf = {k: v.clone().requires_grad_(True) for k, v in c.items()}
+        out = _fn()(leaf["u"], leaf["delta"], leaf["A"], leaf["B"], leaf["C"], leaf["D"], leaf["z"], leaf["delta_bias"], True)
+        out.float().square().sum().backward()
+        grads.append({k: leaf[k].grad.clone() for k in GRAD_KEYS})
+    for k in GRAD_KEYS:
+        assert torch.equal(grads[0][k], grads[1][k]), k
+
+
+def test_full_size_properties_config3_shapes():
+    """ConMamba-large shapes (B 64, D 512, L 501, bf16): properties that need no CPU oracle pass.
+    (i) reversed scan == flip -> scan -> flip, bit for bit; (ii) fused bidirectional == the two unidirectional
+    kernels combined; (iii) the scan is linear in u when D skip and gate are fixed."""
+    from mamba_asr_b200 import kernels as K
+    Bt, D, L, N = 64, 512, 501, 16
+    f = make_scan_inputs(Bt, D, L, N, torch.bfloat16, seed=21, device="cuda")
+    b = make_scan_inputs(Bt, D, L, N, torch.bfloat16, seed=22, device="cuda")
+    cl = lambda d: {k: (channel_last(v) if v.dim() == 3 else v) for k, v in d.items()}
+    f, b = cl(f), cl(b)
+    mk = lambda s, rev, **kw: dict(u=kw.get("u", s["u"]), delta=s["delta"], A=s["A"], B=s["B"], C=s["C"], D=s["D"],
+                                   delta_bias=s["delta_bias"], reverse=rev)
+    # (i)
+    r1 = K.scan_forward([mk(b, True)], z=None, delta_softplus=True)["out"]
+    fl = lambda t: channel_last(t.flip(-1))
+    bf = {k: (fl(v) if v.dim() == 3 else v) for k, v in b.items()}
+    r2 = K.scan_forward([mk(bf, False)], z=None, delta_softplus=True)["out"].flip(-1)
+    assert torch.equal(r1, r2)
+    # (ii)
+    of = K.scan_forward([mk(f, False)], z=None, delta_softplus=True)["out"].float()
+    fused = K.scan_forward([mk(f, False), mk(b, True)], z=f["z"], out_scale=0.5, delta_softplus=True)["out"].float()
+    zf = f["z"].float()
+    comp = 0.5 * (of + r1.float()) * (zf * torch.sigmoid(zf))
+    assert_close(fused, comp, torch.bfloat16, what="fused vs separate")
+    # (iii)
+    u2 = channel_last(torch.randn_like(f["u"]))
+    o1 = K.scan_forward([mk(f, False)], delta_softplus=True)["out"].float()
+    o2 = K.scan_forward([mk(f, False, u=u2)], delta_softplus=True)["out"].float()
+    o12 = K.scan_forward([mk(f, False, u=(f["u"] + u2))], delta_softplus=True)["out"].float()
+    assert_close(o12, o1 + o2, torch.bfloat16, what="linearity in u")

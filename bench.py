@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py - ConMamba encoder audio-seconds / second (fwd+bwd) on N B200s, with the scan-kernel roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload at N = 1 (BASELINE.json configs[1]): ConMamba-small CTC encoder, forward + backward, bf16 autocast,
+batch 32 x 15 s of synthetic 16 kHz audio per GPU; weak scaling (per-GPU batch fixed, DDP gradient all-reduce
+over NCCL at N > 1).  One step = Fbank -> normalise -> conv front-end -> 12 ConMamba layers -> CTC loss -> backward.
+
+Printed JSON line (rank 0):
+  value     audio-s/s of the whole job, inputs already resident in HBM, K steps timed with CUDA events between
+            barrier + synchronize, max over ranks
+  e2e       the same step driven from pinned HOST audio: H2D copy of the waveforms and D2H read of the loss inside
+            the timed region
+  roofline  the dominant hand-written kernel (the selective scan): algorithmic bytes / launch
+            divided by its CUDA-event duration measured in the timed steps, against MEASURED_PEAKS.json
+  cpu_baseline  the reference CPU path (oracle port of selective_scan_ref + torch conv + Fbank inside the same
+            module tree) on the host cores, bounded sample
+``--impl reference`` times that CPU path alone (rank 0 only).
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+METRIC = "ConMamba encoder audio-sec/sec (fwd+bwd)"
+UNIT = "audio-sec/sec"
+
+WORKLOADS = {
+    # BASELINE.json configs[1] - the configuration the metric is quoted on for one GPU
+    "conmamba_small_ctc_fwdbwd_b32x15s": dict(model="conmamba_small_ctc", batch=32, seconds=15.0),
+    # BASELINE.json configs[2] shape (encoder fwd+bwd of the large CTC model, 64 x 20 s per GPU)
+    "conmamba_large_ctc_fwdbwd_b64x20s": dict(model="conmamba_large_ctc", batch=64, seconds=20.0),
+    # small smoke shape for debugging
+    "tiny": dict(model="conmamba_small_ctc", batch=2, seconds=2.0),
+}
+DEFAULT_WORKLOAD = "conmamba_small_ctc_fwdbwd_b32x15s"
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {}
+        for n in dir(nv):
+            if n.startswith("nvmlClocksEventReason") or n.startswith("nvmlClocksThrottleReason"):
+                v = getattr(nv, n)
+                if isinstance(v, int) and v not in (0,):
+                    names.setdefault(v, n.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", ""))
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if bit and (mask & bit) == bit and bin(bit).count("1") == 1:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=2)
+        med = statistics.median(self.samples) if self.samples else None
+        reasons = sorted(r for r in self.reasons if r not in ("GpuIdle", "None", "ApplicationsClocksSetting"))
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.samples)}
+
+
+def make_batch(model_cfg, batch, seconds, seed, device, n_classes):
+    g = torch.Generator().manual_seed(seed)
+    n = int(round(16000 * seconds))
+    wav = 0.1 * torch.randn(batch, n, generator=g)
+    tgt_len = max(1, int(3 * seconds))
+    targets = torch.randint(3, n_classes, (batch, tgt_len), generator=g)
+    return wav, targets
+
+
+def ctc_step(model, wav, targets, autocast):
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        logp = model(wav)                                       # (B, L, C)
+    Bt, L, _ = logp.shape
+    in_len = torch.full((Bt,), L, dtype=torch.long)
+    tg_len = torch.full((Bt,), targets.shape[1], dtype=torch.long)
+    loss = F.ctc_loss(logp.float().transpose(0, 1), targets, in_len, tg_len, blank=0, reduction="mean",
+                      zero_infinity=True)
+    loss.backward()
+    return loss
+
+
+def scan_algorithmic_bytes(batch, L, D, N, s, ndir, bwd):
+    """bytes per (b, d, l) position of one fused-bidirectional scan launch."""
+    if ndir == 2:
+        per = (11 + 8.0 * N / D) * s if bwd else (6 + 4.0 * N / D) * s
+    else:
+        per = (7 + 4.0 * N / D) * s if bwd else (4 + 2.0 * N / D) * s
+    return per * batch * L * D
+
+
+def conv_algorithmic_bytes(batch, L, D, s, ndir, bwd):
+    per = (4 if bwd else 3) * s if ndir == 2 else (3 if bwd else 2) * s
+    return per * batch * L * D
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_run(workload, steps, warmup, budget_s=200.0):
+    """Times the reference CPU path on a bounded sample of the workload; returns (audio-s/s, description dict)."""
+    from mamba_asr_b200.encoder import CONFIGS, build_model
+    from oracle.cpu_encoder import to_cpu_reference
+    wl = WORKLOADS[workload]
+    cfg = CONFIGS[wl["model"]]
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    model = to_cpu_reference(build_model(wl["model"]), cfg["n_fft"], cfg["n_mels"], cfg["win_length"])
+    model.train()
+    seconds = wl["seconds"]
+
+    def one(sec):
+        wav, targets = make_batch(cfg, 1, sec, 1234, "cpu", cfg["output_neurons"])
+        t0 = time.perf_counter()
+        model.zero_grad(set_to_none=True)
+        logp = model(wav)
+        L = logp.shape[1]
+        loss = F.ctc_loss(logp.float().transpose(0, 1), targets, torch.tensor([L]), torch.tensor([targets.shape[1]]),
+                          blank=0, reduction="mean", zero_infinity=True)
+        loss.backward()
+        return time.perf_counter() - t0
+
+    # pick the largest sample (1 utterance of the workload's duration, else a shorter cut) that fits the budget
+    sec = seconds
+    t_probe = one(sec)                                        # also the first warm-up step
+    total = steps + warmup
+    while t_probe * total > budget_s and sec > 1.0:
+        sec = max(1.0, sec / 2.0)
+        t_probe = one(sec)
+    for _ in range(max(0, warmup - 1)):
+        one(sec)
+    times = [one(sec) for _ in range(steps)]
+    dt = sum(times)
+    value = sec * steps / dt
+    desc = {"kind": "port", "cores": threads, "value": value, "unit": UNIT,
+            "sample": "1 utterance x %.2f s of the %s workload per step (oracle port of selective_scan_ref + torch conv + "
+                      "Fbank inside the same 12-layer module tree, fwd+bwd, fp32, %d steps, %.2f s/step)"
+                      % (sec, workload, steps, dt / steps)}
+    return value, dt / steps * 1e3, desc
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = WORKLOADS[args.workload]
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        value, ms, desc = cpu_reference_run(args.workload, args.steps, max(1, args.warmup))
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": args.workload, "note": "reference CPU path on host cores, bounded sample"},
+                "cpu_baseline": desc,
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl ours) needs a CUDA device: the product path has no CPU fallback")
+    warmup = max(3, args.warmup)
+    steps = max(1, args.steps)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from mamba_asr_b200 import kernels as K
+    from mamba_asr_b200.encoder import CONFIGS, build_model
+    cfg = CONFIGS[wl["model"]]
+    model = build_model(wl["model"]).to(dev)
+    model.train()
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])
+    n_params = sum(p.numel() for p in model.parameters())
+
+    batch, seconds = wl["batch"], wl["seconds"]
+    wav_h, tgt_h = make_batch(cfg, batch, seconds, cfg["seed"] + rank, dev, cfg["output_neurons"])
+    wav_pin, tgt_pin = wav_h.pin_memory(), tgt_h.pin_memory()
+    wav_d, tgt_d = wav_h.to(dev), tgt_h.to(dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        model.zero_grad(set_to_none=True)
+        return ctc_step(net, wav_d, tgt_d, True)
+
+    def step_e2e():
+        model.zero_grad(set_to_none=True)
+        w = wav_pin.to(dev, non_blocking=True)
+        t = tgt_pin.to(dev, non_blocking=True)
+        return float(ctc_step(net, w, t, True).item())
+
+    for _ in range(warmup):
+        step_resident()
+    barrier()
+    torch.cuda.reset_peak_memory_stats()
+
+    # ---- timed region: K steps, device events, kernel-level events for the roofline -----------------------------
+    sampler = ClockSampler(local_rank)
+    launches0 = K.LAUNCHES
+    K.start_timing()
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step_resident()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ktimes = K.stop_timing()
+    launches = K.LAUNCHES - launches0
+    elapsed_ms = e0.elapsed_time(e1)
+    peak_mem = torch.cuda.max_memory_allocated()
+    loss_val = float(loss.item())
+
+    # ---- end-to-end: host audio -> H2D -> step -> loss D2H, every step -----------------------------------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(steps):
+        step_e2e()
+    g1.record()
+    barrier()
+    e2e_ms = g0.elapsed_time(g1)
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+
+    if dist is not None:
+        t = torch.tensor([elapsed_ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, e2e_ms = float(t[0]), float(t[1])
+        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt)
+
+    audio_s = batch * seconds * world * steps
+    value = audio_s / (elapsed_ms / 1e3)
+    e2e_value = audio_s / (e2e_ms / 1e3)
+
+    if rank == 0:
+        # ---- roofline of the hand-written kernels (rank 0's launches) ----------------------------------------
+        hbm_peak, peak_src = peaks()
+        T = 1 + int(round(16000 * seconds)) // 160
+        L = (((T - 1) // 2 + 1) - 1) // 2 + 1
+        D, N, s = 2 * cfg["d_model"], 16, 2
+        alg = {
+            "cm_scan_fwd": scan_algorithmic_bytes(batch, L, D, N, s, 2, False),
+            "cm_scan_bwd": scan_algorithmic_bytes(batch, L, D, N, s, 2, True),
+            "cm_conv_fwd": conv_algorithmic_bytes(batch, L, D, s, 2, False),
+            "cm_conv_bwd": conv_algorithmic_bytes(batch, L, D, s, 2, True),
+        }
+        kern = {}
+        for name, byts in alg.items():
+            ts = ktimes.get(name, [])
+            if ts:
+                avg = sum(ts) / len(ts)
+                kern[name] = {"launches": len(ts), "avg_ms": avg, "total_ms": sum(ts), "alg_bytes": byts,
+                              "achieved_gbs": byts / (avg * 1e-3) / 1e9, "frac": byts / (avg * 1e-3) / 1e9 / hbm_peak}
+        share = {k: sum(v) for k, v in ktimes.items()}
+        dom = max((k for k in kern), key=lambda k: kern[k]["total_ms"]) if kern else None
+        roofline = None
+        if dom:
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["achieved_gbs"], "peak": hbm_peak,
+                        "unit": "GB/s", "frac": kern[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                        "alg_bytes_per_launch": kern[dom]["alg_bytes"], "avg_launch_ms": kern[dom]["avg_ms"],
+                        "note": "fp32 state update is MUFU/issue-bound before HBM (SURVEY.md 0.8); see `kernels`"}
+        cpu_desc = None
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                _, _, cpu_desc = cpu_reference_run(args.workload, args.cpu_steps, 1, budget_s=60.0)
+            except Exception as ex:                               # the baseline must never take the GPU number down
+                cpu_desc = {"kind": "port", "error": repr(ex)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": elapsed_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": args.workload, "per_gpu_batch": batch, "audio_seconds": seconds,
+                       "encoder_frames": L, "d_inner": D, "layers": cfg["num_layers"], "params": n_params,
+                       "step": "Fbank+norm+CNN+%d ConMamba layers+CTC loss, forward+backward, bf16 autocast, no optimizer"
+                               % cfg["num_layers"],
+                       "parallelism": "dp%d (DDP grad all-reduce over NCCL)" % world if world > 1 else "single GPU",
+                       "l2": "no flush: activations touched per step (peak %.2f GB allocated) exceed the 126 MB L2"
+                             % (peak_mem / 1e9)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / steps,
+                    "host_wall_ms_per_step": e2e_wall_ms / steps,
+                    "h2d_bytes_per_step": int(wav_pin.numel() * 4 + tgt_pin.numel() * 8), "d2h_bytes_per_step": 4},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roofline,
+            "kernels": kern,
+            "kernel_time_share_ms": share,
+            "cpu_baseline": cpu_desc,
+            "loss": loss_val,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -16,6 +16,38 @@ __all__ = ["scan_forward", "scan_backward", "conv_forward", "conv_backward", "co
            "empty_like_bdl", "num_ckpt"]
 
 
+# ---- launch accounting (bench.py reads these; they never change what is computed) -------------------------
+LAUNCHES = 0          # kernels launched through the C ABI since import (one per entry-point call)
+_TIMING = None        # None, or {entry point: [(start_event, end_event), ...]} while bench.py profiles a step
+
+
+def start_timing():
+    """Record a CUDA event pair around every C-ABI launch on the launching stream (used by bench.py's roofline)."""
+    global _TIMING
+    _TIMING = {}
+
+
+def stop_timing():
+    """-> {entry point: [ms per launch, ...]} ; synchronises."""
+    global _TIMING
+    t, _TIMING = _TIMING, None
+    torch.cuda.synchronize()
+    return {k: [a.elapsed_time(b) for a, b in v] for k, v in (t or {}).items()}
+
+
+def _call(name, fn, *args):
+    global LAUNCHES
+    LAUNCHES += 1
+    if _TIMING is None:
+        cabi.check(fn(*args), name)
+        return
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    cabi.check(fn(*args), name)
+    e.record()
+    _TIMING.setdefault(name, []).append((s, e))
+
+
 def _require_cuda(t, name):
     if not t.is_cuda:
         raise RuntimeError("mamba_asr_b200: %s must be a CUDA tensor - the B200 kernels have no CPU fallback" % name)
@@ -139,7 +171,7 @@ def scan_forward(dirs, z=None, out_scale=1.0, delta_softplus=False, need_ckpt=Fa
     a.out = cabi.t3(out)
     out_pre = empty_like_bdl(u0) if need_out_pre else None
     a.out_pre = cabi.t3(out_pre)
-    cabi.check(lib.cm_scan_fwd(C.byref(a), cabi.stream_ptr()), "cm_scan_fwd")
+    _call("cm_scan_fwd", lib.cm_scan_fwd, C.byref(a), cabi.stream_ptr())
     return dict(out=out, out_pre=out_pre, ckpt=ckpts, last_state=lasts)
 
 
@@ -202,28 +234,28 @@ def scan_backward(dirs, ckpts, dout, z=None, out_pre=None, out_scale=1.0, delta_
         a.z, a.out_pre, a.dz = cabi.t3(z), cabi.t3(out_pre), cabi.t3(dz)
         res["dz"] = dz
     st = cabi.stream_ptr()
-    cabi.check(lib.cm_scan_bwd(C.byref(a), st), "cm_scan_bwd")
+    _call("cm_scan_bwd", lib.cm_scan_bwd, C.byref(a), st)
 
     for r, d in enumerate(dirs):
         bc_part, dA_part, dD_part, db_part = parts[r]
         dA = torch.empty((D, 16), dtype=torch.float32, device=dev)
-        cabi.check(lib.cm_reduce_rows(dA_part.data_ptr(), Bt, D * 16, dA.data_ptr(), st), "cm_reduce_rows")
+        _call("cm_reduce_rows", lib.cm_reduce_rows, dA_part.data_ptr(), Bt, D * 16, dA.data_ptr(), st)
         res["dA"].append(dA[:, :N])
         if dD_part is not None:
             dD = torch.empty((D,), dtype=torch.float32, device=dev)
-            cabi.check(lib.cm_reduce_rows(dD_part.data_ptr(), Bt, D, dD.data_ptr(), st), "cm_reduce_rows")
+            _call("cm_reduce_rows", lib.cm_reduce_rows, dD_part.data_ptr(), Bt, D, dD.data_ptr(), st)
             res["dD"].append(dD)
         else:
             res["dD"].append(None)
         if db_part is not None:
             db = torch.empty((D,), dtype=torch.float32, device=dev)
-            cabi.check(lib.cm_reduce_rows(db_part.data_ptr(), Bt, D, db.data_ptr(), st), "cm_reduce_rows")
+            _call("cm_reduce_rows", lib.cm_reduce_rows, db_part.data_ptr(), Bt, D, db.data_ptr(), st)
             res["dbias"].append(db)
         else:
             res["dbias"].append(None)
         if const_bc:
             dBC = torch.empty((D, 32), dtype=torch.float32, device=dev)
-            cabi.check(lib.cm_reduce_rows(bc_part.data_ptr(), Bt, D * 32, dBC.data_ptr(), st), "cm_reduce_rows")
+            _call("cm_reduce_rows", lib.cm_reduce_rows, bc_part.data_ptr(), Bt, D * 32, dBC.data_ptr(), st)
             res["dB"].append(dBC[:, :N].to(d["B"].dtype))
             res["dC"].append(dBC[:, 16:16 + N].to(d["C"].dtype))
         else:
@@ -232,8 +264,7 @@ def scan_backward(dirs, ckpts, dout, z=None, out_pre=None, out_scale=1.0, delta_
             else:
                 dB = torch.empty_strided(d["B"].shape, _dense_strides(d["B"]), dtype=d["B"].dtype, device=dev)
                 dC = torch.empty_strided(d["C"].shape, _dense_strides(d["C"]), dtype=d["C"].dtype, device=dev)
-            cabi.check(lib.cm_reduce_dbc(bc_part.data_ptr(), Bt, n_slab, L, N, a.dtype, cabi.t3(dB), cabi.t3(dC), st),
-                       "cm_reduce_dbc")
+            _call("cm_reduce_dbc", lib.cm_reduce_dbc, bc_part.data_ptr(), Bt, n_slab, L, N, a.dtype, cabi.t3(dB), cabi.t3(dC), st)
             res["dB"].append(dB)
             res["dC"].append(dC)
     return res
@@ -287,7 +318,7 @@ def conv_forward(x, dirs, silu=True, outs=None):
         o = outs[r] if outs is not None else empty_like_bdl(x)
         a.dir[r].out = cabi.t3(o)
         res.append(o)
-    cabi.check(lib.cm_conv_fwd(C.byref(a), cabi.stream_ptr()), "cm_conv_fwd")
+    _call("cm_conv_fwd", lib.cm_conv_fwd, C.byref(a), cabi.stream_ptr())
     return res
 
 
@@ -313,15 +344,15 @@ def conv_backward(x, dirs, douts, silu=True, dx_out=None):
         a.dir[r].dbias_part = cabi.ptr(bp)
         parts.append((wp, bp))
     st = cabi.stream_ptr()
-    cabi.check(lib.cm_conv_bwd(C.byref(a), st), "cm_conv_bwd")
+    _call("cm_conv_bwd", lib.cm_conv_bwd, C.byref(a), st)
     dws, dbs = [], []
     for wp, bp in parts:
         dw = torch.empty((D, W), dtype=torch.float32, device=dev)
-        cabi.check(lib.cm_reduce_rows(wp.data_ptr(), npart, D * W, dw.data_ptr(), st), "cm_reduce_rows")
+        _call("cm_reduce_rows", lib.cm_reduce_rows, wp.data_ptr(), npart, D * W, dw.data_ptr(), st)
         dws.append(dw)
         if bp is not None:
             db = torch.empty((D,), dtype=torch.float32, device=dev)
-            cabi.check(lib.cm_reduce_rows(bp.data_ptr(), npart, D, db.data_ptr(), st), "cm_reduce_rows")
+            _call("cm_reduce_rows", lib.cm_reduce_rows, bp.data_ptr(), npart, D, db.data_ptr(), st)
             dbs.append(db)
         else:
             dbs.append(None)
@@ -340,9 +371,8 @@ def conv_update(x, conv_state, weight, bias=None, silu=False):
     w = weight.float().contiguous()
     b = None if bias is None else bias.float().contiguous()
     out = torch.empty_like(x)
-    cabi.check(lib.cm_conv_update(x.data_ptr(), conv_state.data_ptr(), w.data_ptr(), cabi.ptr(b), out.data_ptr(), Bt, D, W,
-                                  cabi.dtype_code(x.dtype), cabi.CM_FLAG_SILU if silu else 0, cabi.stream_ptr()),
-               "cm_conv_update")
+    _call("cm_conv_update", lib.cm_conv_update, x.data_ptr(), conv_state.data_ptr(), w.data_ptr(), cabi.ptr(b), out.data_ptr(), Bt, D, W,
+                                  cabi.dtype_code(x.dtype), cabi.CM_FLAG_SILU if silu else 0, cabi.stream_ptr())
     return out
 
 
@@ -368,6 +398,6 @@ def fbank_logmel(stft, fbank, top_db=80.0, amin=1e-10, multiplier=10.0, db_offse
     a.fbank, a.out, a.utt_max = fb.data_ptr(), out.data_ptr(), umax.data_ptr()
     a.amin, a.multiplier, a.db_offset, a.top_db = amin, multiplier, db_offset, top_db
     st = cabi.stream_ptr()
-    cabi.check(lib.cm_fbank_logmel(C.byref(a), st), "cm_fbank_logmel")
-    cabi.check(lib.cm_fbank_floor(C.byref(a), st), "cm_fbank_floor")
+    _call("cm_fbank_logmel", lib.cm_fbank_logmel, C.byref(a), st)
+    _call("cm_fbank_floor", lib.cm_fbank_floor, C.byref(a), st)
     return out

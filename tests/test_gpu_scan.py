@@ -196,7 +196,9 @@ def test_full_size_properties_config3_shapes():
     fused = K.scan_forward([mk(f, False), mk(b, True)], z=f["z"], out_scale=0.5, delta_softplus=True)["out"].float()
     zf = f["z"].float()
     comp = 0.5 * (of + r1.float()) * (zf * torch.sigmoid(zf))
-    assert_close(fused, comp, torch.bfloat16, what="fused vs separate")
+    # `comp` rounds each direction to bf16 before the add and the gate (as the reference does); the fused kernel
+    # rounds once, so the difference is bounded by bf16 eps of the PRE-gate magnitudes -> floor on max|ref|
+    assert_close(fused, comp, torch.bfloat16, floor="max", what="fused vs separate")
     # (iii)
     u2 = channel_last(torch.randn_like(f["u"]))
     o1 = K.scan_forward([mk(f, False)], delta_softplus=True)["out"].float()

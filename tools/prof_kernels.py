@@ -1,0 +1,128 @@
+#!/usr/bin/env python
+"""Kernel-level microbenchmark (run on the B200 box): times cm_scan_fwd / cm_scan_bwd / cm_conv_fwd / cm_conv_bwd
+standalone at the BASELINE.json shapes with CUDA events and prints achieved algorithmic GB/s vs the measured HBM peak.
+
+    python tools/prof_kernels.py [--cfg 2|3|4|5] [--iters 20] [--lanes 0] [--only scan_fwd,...] [--dtype bf16|f32]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mamba_asr_b200 import kernels as K  # noqa: E402
+
+CFG = {  # (Bt, D, L, R)
+    "1": (8, 288, 251, 9), "2": (32, 288, 376, 9), "3": (64, 512, 501, 16), "4": (64, 1024, 501, 32),
+    "5": (4, 512, 7501, 16), "5a": (4, 512, 1024, 16), "5b": (4, 512, 30000, 16),
+}
+
+
+def hbm_peak():
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def timeit(fn, iters, flush):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()                       # > L2 capacity: evicts the previous iteration's lines
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[0], ts[len(ts) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cfg", default="2,3")
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--lanes", default="0")
+    ap.add_argument("--only", default="scan_fwd,scan_bwd,conv_fwd,conv_bwd,scan_fwd_infer")
+    ap.add_argument("--dtype", default="bf16")
+    args = ap.parse_args()
+    dt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    s = 2 if dt == torch.bfloat16 else 4
+    peak = hbm_peak()
+    dev = "cuda"
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    only = set(args.only.split(","))
+    N = 16
+    for cfg in args.cfg.split(","):
+        Bt, D, L, R = CFG[cfg]
+        pos = Bt * D * L
+        g = torch.Generator(device=dev).manual_seed(0)
+        rn = lambda *sh: torch.randn(*sh, device=dev, generator=g)
+        cl = lambda: rn(Bt, L, D).to(dt).transpose(1, 2)
+        z = cl()
+        P = R + 2 * N
+        dirs = []
+        for rev in (False, True):
+            xdbl = rn(Bt, L, P).to(dt)
+            dirs.append(dict(u=cl(), delta=(0.5 * rn(Bt, L, D)).to(dt).transpose(1, 2), A=-torch.exp(0.3 * rn(D, N)),
+                             B=xdbl[..., R:R + N].transpose(1, 2), C=xdbl[..., R + N:].transpose(1, 2),
+                             D=torch.ones(D, device=dev), delta_bias=torch.full((D,), -4.0, device=dev), reverse=rev))
+        for lanes in [int(x) for x in args.lanes.split(",")]:
+            tag = "cfg%s B%d D%d L%d %s lanes=%d" % (cfg, Bt, D, L, args.dtype, lanes)
+            if "scan_fwd" in only:
+                f = lambda: K.scan_forward(dirs, z=z, out_scale=0.5, delta_softplus=True, need_ckpt=True,
+                                           need_out_pre=True, lanes=lanes)
+                best, med = timeit(f, args.iters, flush)
+                byts = (6 + 4.0 * N / D) * s * pos
+                print("%-40s scan_fwd(train)  best %.3f ms med %.3f ms  alg %.1f GB/s (%.1f%% of %.0f)  %.1f ps/pos"
+                      % (tag, best, med, byts / best / 1e6, 100 * byts / best / 1e6 / peak, peak, best * 1e9 / pos))
+            if "scan_fwd_infer" in only:
+                f = lambda: K.scan_forward(dirs, z=z, out_scale=0.5, delta_softplus=True, lanes=lanes)
+                best, med = timeit(f, args.iters, flush)
+                byts = (6 + 4.0 * N / D) * s * pos
+                print("%-40s scan_fwd(infer)  best %.3f ms med %.3f ms  alg %.1f GB/s (%.1f%%)"
+                      % (tag, best, med, byts / best / 1e6, 100 * byts / best / 1e6 / peak))
+            if "scan_bwd" in only:
+                res = K.scan_forward(dirs, z=z, out_scale=0.5, delta_softplus=True, need_ckpt=True, need_out_pre=True)
+                dout = cl()
+                f = lambda: K.scan_backward(dirs, res["ckpt"], dout, z=z, out_pre=res["out_pre"], out_scale=0.5,
+                                            delta_softplus=True, lanes=lanes)
+                K.start_timing()
+                for _ in range(5):
+                    f()
+                kt = K.stop_timing()
+                best = min(kt["cm_scan_bwd"])
+                byts = (11 + 8.0 * N / D) * s * pos
+                print("%-40s scan_bwd kernel  best %.3f ms              alg %.1f GB/s (%.1f%%)  %.1f ps/pos ; reducers %s"
+                      % (tag, best, byts / best / 1e6, 100 * byts / best / 1e6 / peak, best * 1e9 / pos,
+                         {k: round(min(v), 4) for k, v in kt.items() if k != "cm_scan_bwd"}))
+        x = cl()
+        cdirs = [dict(weight=rn(D, 4), bias=rn(D), anticausal=False), dict(weight=rn(D, 4), bias=rn(D), anticausal=True)]
+        tag = "cfg%s B%d D%d L%d %s" % (cfg, Bt, D, L, args.dtype)
+        if "conv_fwd" in only:
+            outs = [K.empty_like_bdl(x), K.empty_like_bdl(x)]
+            best, med = timeit(lambda: K.conv_forward(x, cdirs, silu=True, outs=outs), args.iters, flush)
+            byts = 3 * s * pos
+            print("%-40s conv_fwd         best %.3f ms med %.3f ms  alg %.1f GB/s (%.1f%%)"
+                  % (tag, best, med, byts / best / 1e6, 100 * byts / best / 1e6 / peak))
+        if "conv_bwd" in only:
+            douts = [cl(), cl()]
+            K.start_timing()
+            for _ in range(5):
+                K.conv_backward(x, cdirs, douts, silu=True)
+            kt = K.stop_timing()
+            best = min(kt["cm_conv_bwd"])
+            byts = 4 * s * pos
+            print("%-40s conv_bwd kernel  best %.3f ms              alg %.1f GB/s (%.1f%%)"
+                  % (tag, best, byts / best / 1e6, 100 * byts / best / 1e6 / peak))
+
+
+if __name__ == "__main__":
+    main()

@@ -15,8 +15,15 @@ constexpr float kLn2 = 0.6931471805599453f;
 // ---- element I/O ---------------------------------------------------------------------------------
 template <typename T>
 struct Elem;
+// ld_raw / cvt split a load from its conversion: kernels batch all ld_raw of a tile into registers first and
+// convert at the point of use, so that no ALU instruction sits between consecutive loads (a shift right after
+// each LDG serialises the loads on the scoreboard - measured: 6 long-scoreboard stalls per issued instruction).
 template <>
 struct Elem<float> {
+  using Raw = float;
+  static __device__ __forceinline__ Raw ld_raw(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ Raw ld_raw_cg(const float* p) { return __ldcg(p); }
+  static __device__ __forceinline__ float cvt(Raw r) { return r; }
   static __device__ __forceinline__ float ld(const float* p) { return __ldg(p); }
   static __device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }
   static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
@@ -24,6 +31,10 @@ struct Elem<float> {
 };
 template <>
 struct Elem<__nv_bfloat16> {
+  using Raw = unsigned short;
+  static __device__ __forceinline__ Raw ld_raw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const unsigned short*>(p)); }
+  static __device__ __forceinline__ Raw ld_raw_cg(const __nv_bfloat16* p) { return __ldcg(reinterpret_cast<const unsigned short*>(p)); }
+  static __device__ __forceinline__ float cvt(Raw r) { return __uint_as_float(static_cast<uint32_t>(r) << 16); }
   static __device__ __forceinline__ float ld(const __nv_bfloat16* p) {
     unsigned short r = __ldg(reinterpret_cast<const unsigned short*>(p));
     return __uint_as_float(static_cast<uint32_t>(r) << 16);
@@ -37,6 +48,10 @@ struct Elem<__nv_bfloat16> {
 };
 template <>
 struct Elem<__half> {
+  using Raw = unsigned short;
+  static __device__ __forceinline__ Raw ld_raw(const __half* p) { return __ldg(reinterpret_cast<const unsigned short*>(p)); }
+  static __device__ __forceinline__ Raw ld_raw_cg(const __half* p) { return __ldcg(reinterpret_cast<const unsigned short*>(p)); }
+  static __device__ __forceinline__ float cvt(Raw r) { return __half2float(__ushort_as_half(r)); }
   static __device__ __forceinline__ float ld(const __half* p) {
     unsigned short r = __ldg(reinterpret_cast<const unsigned short*>(p));
     return __half2float(__ushort_as_half(r));

@@ -80,89 +80,99 @@ __global__ void __launch_bounds__(32) scan_bwd_kernel(const cm_scan_bwd_args p) 
   }
   float dD_acc = 0.f, dbias_acc = 0.f;
 
-  const T* up = static_cast<const T*>(dp.u.ptr) + b * dp.u.sb + d * dp.u.sd;
-  const T* dlp = static_cast<const T*>(dp.delta.ptr) + b * dp.delta.sb + d * dp.delta.sd;
-  const T* zp = has_z ? static_cast<const T*>(p.z.ptr) + b * p.z.sb + d * p.z.sd : nullptr;
-  const T* prep = do_dz ? static_cast<const T*>(p.out_pre.ptr) + b * p.out_pre.sb + d * p.out_pre.sd : nullptr;
-  const T* dop = static_cast<const T*>(p.dout.ptr) + b * p.dout.sb + d * p.dout.sd;
-  T* dzp = do_dz ? static_cast<T*>(p.dz.ptr) + b * p.dz.sb + d * p.dz.sd : nullptr;
-  T* dup = static_cast<T*>(bd.du.ptr) + b * bd.du.sb + d * bd.du.sd;
-  T* ddp = static_cast<T*>(bd.ddelta.ptr) + b * bd.ddelta.sb + d * bd.ddelta.sd;
-  const T* Bp = BC_CONST ? nullptr : static_cast<const T*>(dp.Bm.ptr) + b * dp.Bm.sb;
-  const T* Cp = BC_CONST ? nullptr : static_cast<const T*>(dp.Cm.ptr) + b * dp.Cm.sb;
+  // pointers positioned at processed step 0; signed element strides per processed step
+  using Raw = typename Elem<T>::Raw;
+  const int64_t l0 = rev ? (L - 1) : 0;
+  const int sgn = rev ? -1 : 1;
+  const T* up = static_cast<const T*>(dp.u.ptr) + b * dp.u.sb + d * dp.u.sd + l0 * dp.u.sl;
+  const T* dlp = static_cast<const T*>(dp.delta.ptr) + b * dp.delta.sb + d * dp.delta.sd + l0 * dp.delta.sl;
+  const T* zp = has_z ? static_cast<const T*>(p.z.ptr) + b * p.z.sb + d * p.z.sd + l0 * p.z.sl : nullptr;
+  const T* prep = do_dz ? static_cast<const T*>(p.out_pre.ptr) + b * p.out_pre.sb + d * p.out_pre.sd + l0 * p.out_pre.sl
+                        : nullptr;
+  const T* dop = static_cast<const T*>(p.dout.ptr) + b * p.dout.sb + d * p.dout.sd + l0 * p.dout.sl;
+  T* dzp = do_dz ? static_cast<T*>(p.dz.ptr) + b * p.dz.sb + d * p.dz.sd + l0 * p.dz.sl : nullptr;
+  T* dup = static_cast<T*>(bd.du.ptr) + b * bd.du.sb + d * bd.du.sd + l0 * bd.du.sl;
+  T* ddp = static_cast<T*>(bd.ddelta.ptr) + b * bd.ddelta.sb + d * bd.ddelta.sd + l0 * bd.ddelta.sl;
+  const int su = sgn * (int)dp.u.sl, sdl = sgn * (int)dp.delta.sl, sz = sgn * (int)p.z.sl;
+  const int spre = sgn * (int)p.out_pre.sl, sdo = sgn * (int)p.dout.sl, sdz = sgn * (int)p.dz.sl;
+  const int sdu = sgn * (int)bd.du.sl, sdd = sgn * (int)bd.ddelta.sl;
   const float* ckp = dp.ckpt + b * dp.ckpt_sb + d * dp.ckpt_sd;
   float* partp = BC_CONST ? nullptr
-                          : bd.dBC_part + ((int64_t)b * gridDim.x + slab) * (int64_t)L * 32;
+                          : bd.dBC_part + ((int64_t)b * gridDim.x + slab) * (int64_t)L * 32 + l0 * 32;
+  const int spart = sgn * 32;
+
+  // B/C staging source of this lane (see the forward kernel): 8 loads per lane per 8-step tile
+  const T *bcpA = nullptr, *bcpB = nullptr;
+  int64_t bc_hiA = 0, bc_hiB = 0;
+  bool bc_okA = false, bc_tc = false;
+  int sbc = 0;
+  if (!BC_CONST) {
+    const T* Bp = static_cast<const T*>(dp.Bm.ptr) + b * dp.Bm.sb + l0 * dp.Bm.sl;
+    const T* Cp = static_cast<const T*>(dp.Cm.ptr) + b * dp.Cm.sb + l0 * dp.Cm.sl;
+    bc_tc = (dp.Bm.sl == 1 && dp.Cm.sl == 1);
+    if (bc_tc) {
+      // lane -> step k = lane & 7, state q = lane >> 3 (0..3); loads j = 0..3: B[q + 4 j], then C[q + 4 j]
+      const int q = lane >> 3, k = lane & 7;
+      bcpA = Bp + (int64_t)q * dp.Bm.sd + (int64_t)k * sgn;
+      bcpB = Cp + (int64_t)q * dp.Cm.sd + (int64_t)k * sgn;
+      bc_hiA = 4 * dp.Bm.sd;
+      bc_hiB = 4 * dp.Cm.sd;
+      sbc = sgn;
+    } else {
+      const int n = lane & 15;
+      bcpA = (lane < 16) ? (Bp + n * dp.Bm.sd) : (Cp + n * dp.Cm.sd);
+      bc_okA = n < p.dstate;
+      sbc = sgn * (int)((lane < 16) ? dp.Bm.sl : dp.Cm.sl);
+    }
+  }
 
   const int s1 = cm_first_range(L, p.ndir, dp.reverse);
 
   // ranges are walked last -> first: [s1, L) (absent for ndir == 1) then [0, s1)
+#pragma unroll 1
   for (int range = (p.ndir == 2 ? 1 : 0); range >= 0; --range) {
     const int s_begin = (range == 1) ? s1 : 0;
     const int s_end = (range == 1) ? L : s1;
     const int j0 = (range == 1) ? cm_ceil_div(s1, kTile) : 0;
     const int ntile = cm_ceil_div(s_end - s_begin, kTile);
+#pragma unroll 1
     for (int t = ntile - 1; t >= 0; --t) {
       const int s0 = s_begin + t * kTile;
+      const int nvalid = min(kTile, s_end - s0);
 
-      // ---- phase 0: loads for the tile ----------------------------------------------------------
-      float uu[kTile], xx[kTile], gg[kTile];
+      // ---- phase 0: every global load of the tile, back to back, into raw registers ------------------
+      Raw ur[kTile], dr[kTile], gr[kTile], zr[kTile], pr[kTile], bcr[kTile];
 #pragma unroll
       for (int k = 0; k < kTile; ++k) {
-        const int s = s0 + k;
-        uu[k] = 0.f; xx[k] = 0.f; gg[k] = 0.f;
-        if (s < s_end) {
-          const int64_t l = rev ? (L - 1 - s) : s;
-          uu[k] = Elem<T>::ld(up + l * dp.u.sl);
-          xx[k] = Elem<T>::ld(dlp + l * dp.delta.sl) + bias;
-          const float dov = Elem<T>::ld(dop + l * p.dout.sl) * scale;
-          if (has_z) {
-            const float zz = Elem<T>::ld(zp + l * p.z.sl);
-            const float sig = sigmoidf_fast(zz);
-            gg[k] = dov * zz * sig;
-            if (do_dz && sg == 0 && dvalid) {
-              const float ypre = Elem<T>::ld(prep + l * p.out_pre.sl);
-              Elem<T>::st(dzp + l * p.dz.sl, dov * ypre * sig * fmaf(zz, 1.f - sig, 1.f));
-            }
-          } else {
-            gg[k] = dov;
-          }
+        ur[k] = Raw(0); dr[k] = Raw(0); gr[k] = Raw(0); zr[k] = Raw(0); pr[k] = Raw(0); bcr[k] = Raw(0);
+        if (k < nvalid) {
+          const int64_t s = s0 + k;
+          ur[k] = Elem<T>::ld_raw(up + s * su);
+          dr[k] = Elem<T>::ld_raw(dlp + s * sdl);
+          gr[k] = Elem<T>::ld_raw(dop + s * sdo);
+          if (has_z) zr[k] = Elem<T>::ld_raw(zp + s * sz);
+          if (do_dz) pr[k] = Elem<T>::ld_raw(prep + s * spre);
         }
       }
       if (!BC_CONST) {
-        __syncwarp();
-        if (dp.Bm.sl == 1 && dp.Cm.sl == 1) {
-          // time-contiguous B/C: 4 lane groups x 8 steps, 8 passes over the 32 values
-          const int k = lane & 7, vq = lane >> 3;
-          const int s = s0 + k;
+        if (bc_tc) {
+          if ((lane & 7) < nvalid) {
+            const int64_t off = (int64_t)s0 * sbc;
 #pragma unroll
-          for (int pass = 0; pass < 8; ++pass) {
-            const int v = pass * 4 + vq;
-            const int n = v & 15;
-            float val = 0.f;
-            if (s < s_end && n < p.dstate) {
-              const int64_t l = rev ? (L - 1 - s) : s;
-              val = (v < 16) ? Elem<T>::ld(Bp + n * dp.Bm.sd + l) : Elem<T>::ld(Cp + n * dp.Cm.sd + l);
+            for (int j = 0; j < 4; ++j) {
+              if ((lane >> 3) + 4 * j < p.dstate) {
+                bcr[j] = Elem<T>::ld_raw(bcpA + j * bc_hiA + off);
+                bcr[4 + j] = Elem<T>::ld_raw(bcpB + j * bc_hiB + off);
+              }
             }
-            sm.bc[k][v] = val;
           }
-        } else {
-          const int n = lane & 15;
-          const T* src = (lane < 16) ? (Bp + n * dp.Bm.sd) : (Cp + n * dp.Cm.sd);
-          const int64_t sl = (lane < 16) ? dp.Bm.sl : dp.Cm.sl;
+        } else if (bc_okA) {
 #pragma unroll
-          for (int k = 0; k < kTile; ++k) {
-            const int s = s0 + k;
-            float val = 0.f;
-            if (s < s_end && n < p.dstate) val = Elem<T>::ld(src + (int64_t)(rev ? (L - 1 - s) : s) * sl);
-            sm.bc[k][lane] = val;
-          }
+          for (int k = 0; k < kTile; ++k)
+            if (k < nvalid) bcr[k] = Elem<T>::ld_raw(bcpA + (int64_t)(s0 + k) * sbc);
         }
-        __syncwarp();
       }
-
-      // ---- phase 1: recompute the tile's states from its checkpoint -------------------------------
-      float h[NS], dtv[kTile];
+      float h[NS];
       {
         const float4* src = reinterpret_cast<const float4*>(ckp + (int64_t)(j0 + t) * 16 + sg * NS);
 #pragma unroll
@@ -171,10 +181,45 @@ __global__ void __launch_bounds__(32) scan_bwd_kernel(const cm_scan_bwd_args p) 
           h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
         }
       }
+      // publish B/C to the warp
+      if (!BC_CONST) {
+        __syncwarp();
+        if (bc_tc) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            sm.bc[lane & 7][(lane >> 3) + 4 * j] = Elem<T>::cvt(bcr[j]);
+            sm.bc[lane & 7][16 + (lane >> 3) + 4 * j] = Elem<T>::cvt(bcr[4 + j]);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < kTile; ++k) sm.bc[k][lane] = Elem<T>::cvt(bcr[k]);
+        }
+        __syncwarp();
+      }
+      // per-step scalars
+      float uu[kTile], xx[kTile], gg[kTile];
+#pragma unroll
+      for (int k = 0; k < kTile; ++k) {
+        uu[k] = Elem<T>::cvt(ur[k]);
+        xx[k] = Elem<T>::cvt(dr[k]) + bias;
+        const float dov = Elem<T>::cvt(gr[k]) * scale;
+        if (has_z) {
+          const float zz = Elem<T>::cvt(zr[k]);
+          const float sig = sigmoidf_fast(zz);
+          gg[k] = dov * zz * sig;
+          if (do_dz && sg == 0 && dvalid && k < nvalid)
+            Elem<T>::st(dzp + (int64_t)(s0 + k) * sdz, dov * Elem<T>::cvt(pr[k]) * sig * fmaf(zz, 1.f - sig, 1.f));
+        } else {
+          gg[k] = dov;
+        }
+      }
+
+      // ---- phase 1: recompute the tile's states from its checkpoint -------------------------------
+      float dtv[kTile];
 #pragma unroll
       for (int k = 0; k < kTile; ++k) {
         dtv[k] = 0.f;
-        if (s0 + k < s_end) {
+        if (k < nvalid) {
           const float dt = softplus ? softplus_fwd<sizeof(T) == 4>(xx[k]) : xx[k];
           dtv[k] = dt;
           const float du_ = dt * uu[k];
@@ -196,9 +241,8 @@ __global__ void __launch_bounds__(32) scan_bwd_kernel(const cm_scan_bwd_args p) 
       // ---- phase 2: reverse sweep -----------------------------------------------------------------
 #pragma unroll
       for (int k = kTile - 1; k >= 0; --k) {
-        const int s = s0 + k;
-        if (s < s_end) {
-          const int64_t l = rev ? (L - 1 - s) : s;
+        if (k < nvalid) {
+          const int64_t s = s0 + k;
           const float dt = dtv[k], u_ = uu[k], g = gg[k];
           const float du_ = dt * u_;
           float hk[NS];
@@ -242,8 +286,8 @@ __global__ void __launch_bounds__(32) scan_bwd_kernel(const cm_scan_bwd_args p) 
           dD_acc = fmaf(g, u_, dD_acc);
           dbias_acc += ddl;
           if (sg == 0 && dvalid) {
-            Elem<T>::st(dup + l * bd.du.sl, du);
-            Elem<T>::st(ddp + l * bd.ddelta.sl, ddl);
+            Elem<T>::st(dup + s * sdu, du);
+            Elem<T>::st(ddp + s * sdd, ddl);
           }
           if (BC_CONST) {
 #pragma unroll
@@ -269,7 +313,7 @@ __global__ void __launch_bounds__(32) scan_bwd_kernel(const cm_scan_bwd_args p) 
               acc0 += sm.red[c * LPC + row0][col];
               acc1 += sm.red[(c + 1) * LPC + row0][col];
             }
-            partp[l * 32 + lane] = acc0 + acc1;
+            partp[s * spart + lane] = acc0 + acc1;
           }
         }
       }

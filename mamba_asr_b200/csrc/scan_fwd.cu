@@ -22,128 +22,127 @@
 
 namespace cm {
 
-constexpr int kGroup = CM_SCAN_CKPT_STEPS;  // steps per register-prefetched group == checkpoint period
-constexpr int kBcTile = 32;                 // steps per shared-memory B/C tile
-constexpr int kBcPitch = 36;                // floats per staged step (32 values + pad, keeps rows 16B aligned)
+constexpr int kGroup = 4;                       // steps per register-prefetched, fully unrolled group
+constexpr int kCkptGroups = CM_SCAN_CKPT_STEPS / kGroup;   // a checkpoint every 2 groups
+constexpr int kBcPitch = 36;                    // floats per staged step (16 B + 16 C + pad, rows stay 16B aligned)
 
 enum { MODE_UNI = 0, MODE_STASH = 1, MODE_COMBINE = 2 };
 
+// raw (unconverted) per-lane inputs of one group, converted at the point of use.  bc[k] is this lane's share of
+// the group's 4 x 32 B/C values (shared by the warp through shared memory).
 template <typename T>
 struct FwdGroup {
-  float u[kGroup], dl[kGroup], z[kGroup], st[kGroup];
+  typename Elem<T>::Raw u[kGroup], dl[kGroup], z[kGroup], st[kGroup], bc[kGroup];
 };
 
 template <typename T, int LPC, bool BC_CONST>
 struct FwdCtx {
   static constexpr int NS = 16 / LPC;
   static constexpr int CPW = 32 / LPC;
+  using Raw = typename Elem<T>::Raw;
 
-  // per-lane constants
-  int L, dstate, sg, lane;
-  bool rev, dvalid, softplus, has_z;
+  // per-lane state
+  int dstate, sg, lane, mode;
+  bool dvalid, softplus, has_z, bc_time_contig;
   float scale, Dsk, bias;
   float kA[NS], h[NS], Bc[NS], Cc[NS];
-  const T *up, *dlp, *zp, *Bp, *Cp;
-  int64_t u_sl, dl_sl, z_sl, B_sd, B_sl, C_sd, C_sl, o_sl, op_sl;
+  // pointers are positioned at processed step 0; the s* members are signed element strides per processed step
+  const T *up, *dlp, *zp;
+  const T *bcpA, *bcpB;             // this lane's B/C sources (see load_group)
+  int64_t bc_hiA, bc_hiB;           // time-contiguous layout: offset of the lane's second state (n + 8)
+  bool bc_okA, bc_okB;              // ... and whether n / n + 8 are real states
+  int su, sdl, sz, so, sop, sbc;
   T *outp, *outprep;
   float* ckp;  // row base of the checkpoints, or nullptr
-  float* bc;   // this warp's staging buffer
+  float* bc;   // this warp's staging buffer [kGroup][kBcPitch]
 
-  __device__ __forceinline__ int time_of(int s) const { return rev ? (L - 1 - s) : s; }
+  // Prefetch of one group: every global load of the group is issued here, back to back, into raw registers.
+  __device__ __forceinline__ void load_group(FwdGroup<T>& g, int s0, int nvalid) const {
+    const bool need_z = has_z && mode != MODE_STASH;
+    const bool need_st = mode == MODE_COMBINE;
+#pragma unroll
+    for (int k = 0; k < kGroup; ++k) {
+      const int64_t s = s0 + k;
+      g.u[k] = Raw(0); g.dl[k] = Raw(0); g.z[k] = Raw(0); g.st[k] = Raw(0); g.bc[k] = Raw(0);
+      if (k < nvalid) {
+        g.u[k] = Elem<T>::ld_raw(up + s * su);
+        g.dl[k] = Elem<T>::ld_raw(dlp + s * sdl);
+        if (need_z) g.z[k] = Elem<T>::ld_raw(zp + s * sz);
+        if (need_st) g.st[k] = Elem<T>::ld_raw_cg(outp + s * so);
+      }
+    }
+    if (!BC_CONST) {
+      if (bc_time_contig) {
+        // time-contiguous B/C (the reference's (B, 1, N, L) layout): lane -> step k = lane & 3, state q = lane >> 2;
+        // the four loads are B[q], B[q + 8], C[q], C[q + 8] at that step
+        static_assert(kGroup == 4, "lane mapping below assumes 4-step groups");
+        if ((lane & 3) < nvalid) {
+          const int64_t off = (int64_t)s0 * sbc;
+          if (bc_okA) { g.bc[0] = Elem<T>::ld_raw(bcpA + off); g.bc[2] = Elem<T>::ld_raw(bcpB + off); }
+          if (bc_okB) { g.bc[1] = Elem<T>::ld_raw(bcpA + bc_hiA + off); g.bc[3] = Elem<T>::ld_raw(bcpB + bc_hiB + off); }
+        }
+      } else if (bc_okA) {
+        // state-contiguous rows (slices of the time-major x_dbl): lane -> value v = lane, k-th load = step k
+#pragma unroll
+        for (int k = 0; k < kGroup; ++k)
+          if (k < nvalid) g.bc[k] = Elem<T>::ld_raw(bcpA + (int64_t)(s0 + k) * sbc);
+      }
+    }
+  }
 
-  __device__ __forceinline__ void stage_bc(int tile_start, int s_end) {
+  // publish the group's B/C values to the warp (fp32)
+  __device__ __forceinline__ void publish_bc(const FwdGroup<T>& g) {
     if (BC_CONST) return;
     __syncwarp();
-    if (B_sl == 1 && C_sl == 1) {
-      // time-contiguous B/C (the reference's (B, 1, N, L) layout): lanes over time
-      const int s = tile_start + lane;
-      const bool ok = s < s_end;
-      const int l = ok ? time_of(s) : 0;
-#pragma unroll 8
-      for (int v = 0; v < 32; ++v) {
-        const int n = v & 15;
-        float val = 0.f;
-        if (ok && n < dstate) val = (v < 16) ? Elem<T>::ld(Bp + n * B_sd + l) : Elem<T>::ld(Cp + n * C_sd + l);
-        bc[lane * kBcPitch + v] = val;
-      }
+    if (bc_time_contig) {
+#pragma unroll
+      for (int j = 0; j < kGroup; ++j) bc[(lane & 3) * kBcPitch + 8 * j + (lane >> 2)] = Elem<T>::cvt(g.bc[j]);
     } else {
-      // state-contiguous rows (slices of the time-major x_dbl): lanes over the 32 values of one step
-      const int n = lane & 15;
-      const T* src = (lane < 16) ? (Bp + n * B_sd) : (Cp + n * C_sd);
-      const int64_t sl = (lane < 16) ? B_sl : C_sl;
-#pragma unroll 8
-      for (int t = 0; t < kBcTile; ++t) {
-        const int s = tile_start + t;
-        float val = 0.f;
-        if (s < s_end && n < dstate) val = Elem<T>::ld(src + (int64_t)time_of(s) * sl);
-        bc[t * kBcPitch + lane] = val;
-      }
+#pragma unroll
+      for (int k = 0; k < kGroup; ++k) bc[k * kBcPitch + lane] = Elem<T>::cvt(g.bc[k]);
     }
     __syncwarp();
   }
 
-  template <int MODE>
-  __device__ __forceinline__ void load_group(FwdGroup<T>& g, int s0, int s_end) const {
+  // one recurrence step; `row` = this step's staged B/C row
+  __device__ __forceinline__ void step(Raw ur, Raw dlr, Raw zr, Raw str, int64_t s, const float* row) {
+    float Bv[NS], Cv[NS];
+    if (BC_CONST) {
 #pragma unroll
-    for (int k = 0; k < kGroup; ++k) {
-      const int s = s0 + k;
-      g.u[k] = 0.f; g.dl[k] = 0.f; g.z[k] = 0.f; g.st[k] = 0.f;
-      if (s < s_end) {
-        const int64_t l = time_of(s);
-        g.u[k] = Elem<T>::ld(up + l * u_sl);
-        g.dl[k] = Elem<T>::ld(dlp + l * dl_sl);
-        if (MODE != MODE_STASH && has_z) g.z[k] = Elem<T>::ld(zp + l * z_sl);
-        if (MODE == MODE_COMBINE) g.st[k] = Elem<T>::ld_cg(outp + l * o_sl);
+      for (int i = 0; i < NS; ++i) { Bv[i] = Bc[i]; Cv[i] = Cc[i]; }
+    } else {
+      const float4* rb = reinterpret_cast<const float4*>(row + sg * NS);
+      const float4* rc = reinterpret_cast<const float4*>(row + 16 + sg * NS);
+#pragma unroll
+      for (int i = 0; i < NS / 4; ++i) {
+        const float4 b4 = rb[i], c4 = rc[i];
+        Bv[4 * i + 0] = b4.x; Bv[4 * i + 1] = b4.y; Bv[4 * i + 2] = b4.z; Bv[4 * i + 3] = b4.w;
+        Cv[4 * i + 0] = c4.x; Cv[4 * i + 1] = c4.y; Cv[4 * i + 2] = c4.z; Cv[4 * i + 3] = c4.w;
       }
     }
-  }
-
-  template <int MODE>
-  __device__ __forceinline__ void compute_group(const FwdGroup<T>& g, int s0, int s_end, int tile_start) {
+    const float uu = Elem<T>::cvt(ur);
+    const float x = Elem<T>::cvt(dlr) + bias;
+    const float dt = softplus ? softplus_fwd<sizeof(T) == 4>(x) : x;
+    const float du = dt * uu;
+    float y0 = 0.f, y1 = 0.f;
 #pragma unroll
-    for (int k = 0; k < kGroup; ++k) {
-      const int s = s0 + k;
-      if (s < s_end) {
-        float Bv[NS], Cv[NS];
-        if (BC_CONST) {
-#pragma unroll
-          for (int i = 0; i < NS; ++i) { Bv[i] = Bc[i]; Cv[i] = Cc[i]; }
-        } else {
-          const float4* row = reinterpret_cast<const float4*>(bc + (s - tile_start) * kBcPitch + sg * NS);
-          const float4* rowc = reinterpret_cast<const float4*>(bc + (s - tile_start) * kBcPitch + 16 + sg * NS);
-#pragma unroll
-          for (int i = 0; i < NS / 4; ++i) {
-            const float4 b4 = row[i], c4 = rowc[i];
-            Bv[4 * i + 0] = b4.x; Bv[4 * i + 1] = b4.y; Bv[4 * i + 2] = b4.z; Bv[4 * i + 3] = b4.w;
-            Cv[4 * i + 0] = c4.x; Cv[4 * i + 1] = c4.y; Cv[4 * i + 2] = c4.z; Cv[4 * i + 3] = c4.w;
-          }
-        }
-        const float uu = g.u[k];
-        const float x = g.dl[k] + bias;
-        const float dt = softplus ? softplus_fwd<sizeof(T) == 4>(x) : x;
-        const float du = dt * uu;
-        float y0 = 0.f, y1 = 0.f;
-#pragma unroll
-        for (int i = 0; i < NS; ++i) {
-          const float a = ex2(dt * kA[i]);
-          h[i] = fmaf(a, h[i], du * Bv[i]);
-          if (i & 1) y1 = fmaf(Cv[i], h[i], y1); else y0 = fmaf(Cv[i], h[i], y0);
-        }
-        float y = y0 + y1;
-        if (LPC >= 2) y += __shfl_xor_sync(0xffffffffu, y, 1);
-        if (LPC >= 4) y += __shfl_xor_sync(0xffffffffu, y, 2);
-        y = fmaf(Dsk, uu, y);
-        const int64_t l = time_of(s);
-        if (MODE == MODE_STASH) {
-          if (sg == 0 && dvalid) Elem<T>::st(outp + l * o_sl, y);
-        } else {
-          float tot = (MODE == MODE_COMBINE) ? (y + g.st[k]) : y;
-          if (sg == 0 && dvalid) {
-            if (outprep) Elem<T>::st(outprep + l * op_sl, tot);
-            if (has_z) { const float zz = g.z[k]; tot *= zz * sigmoidf_fast(zz); }
-            Elem<T>::st(outp + l * o_sl, tot * scale);
-          }
-        }
+    for (int i = 0; i < NS; ++i) {
+      const float a = ex2(dt * kA[i]);
+      h[i] = fmaf(a, h[i], du * Bv[i]);
+      if (i & 1) y1 = fmaf(Cv[i], h[i], y1); else y0 = fmaf(Cv[i], h[i], y0);
+    }
+    float y = y0 + y1;
+    if (LPC >= 2) y += __shfl_xor_sync(0xffffffffu, y, 1);
+    if (LPC >= 4) y += __shfl_xor_sync(0xffffffffu, y, 2);
+    y = fmaf(Dsk, uu, y);
+    if (mode == MODE_STASH) {
+      if (sg == 0 && dvalid) Elem<T>::st(outp + s * so, y);
+    } else {
+      float tot = (mode == MODE_COMBINE) ? (y + Elem<T>::cvt(str)) : y;
+      if (sg == 0 && dvalid) {
+        if (outprep) Elem<T>::st(outprep + s * sop, tot);
+        if (has_z) { const float zz = Elem<T>::cvt(zr); tot *= zz * sigmoidf_fast(zz); }
+        Elem<T>::st(outp + s * so, tot * scale);
       }
     }
   }
@@ -156,29 +155,30 @@ struct FwdCtx {
     }
   }
 
-  // Processes steps [s_begin, s_end) in groups of kGroup; checkpoint index of the first group is j0.
-  template <int MODE>
+  // Processes steps [s_begin, s_end) in groups of kGroup.  While group g computes (fully unrolled, branch-free),
+  // every load of group g+1 - u, delta, z, stash and the B/C rows - is already in flight.
   __device__ __forceinline__ void run_range(int s_begin, int s_end, int j0) {
     if (s_begin >= s_end) return;
-    FwdGroup<T> ga, gb;
-    load_group<MODE>(ga, s_begin, s_end);
-    int j = j0;
-    for (int s0 = s_begin; s0 < s_end; s0 += 2 * kGroup) {
-      // ---- group A
-      int tile_start = s_begin + ((s0 - s_begin) / kBcTile) * kBcTile;
-      if (s0 == tile_start) stage_bc(tile_start, s_end);
-      load_group<MODE>(gb, s0 + kGroup, s_end);
-      save_ckpt(j++);
-      compute_group<MODE>(ga, s0, s_end, tile_start);
-      // ---- group B
-      const int s1 = s0 + kGroup;
-      if (s1 < s_end) {
-        tile_start = s_begin + ((s1 - s_begin) / kBcTile) * kBcTile;
-        if (s1 == tile_start) stage_bc(tile_start, s_end);
-        load_group<MODE>(ga, s1 + kGroup, s_end);
-        save_ckpt(j++);
-        compute_group<MODE>(gb, s1, s_end, tile_start);
+    const int n = s_end - s_begin;
+    const int ngroup = (n + kGroup - 1) / kGroup;
+    FwdGroup<T> cur, nxt;
+    load_group(cur, s_begin, min(kGroup, n));
+#pragma unroll 1
+    for (int g = 0; g < ngroup; ++g) {
+      const int s0 = s_begin + g * kGroup;
+      const int nvalid = min(kGroup, s_end - s0);
+      publish_bc(cur);
+      load_group(nxt, s0 + kGroup, max(0, min(kGroup, s_end - s0 - kGroup)));
+      if ((g % kCkptGroups) == 0) save_ckpt(j0 + g / kCkptGroups);
+      if (nvalid == kGroup) {
+#pragma unroll
+        for (int k = 0; k < kGroup; ++k) step(cur.u[k], cur.dl[k], cur.z[k], cur.st[k], s0 + k, bc + k * kBcPitch);
+      } else {
+#pragma unroll
+        for (int k = 0; k < kGroup - 1; ++k)
+          if (k < nvalid) step(cur.u[k], cur.dl[k], cur.z[k], cur.st[k], s0 + k, bc + k * kBcPitch);
       }
+      cur = nxt;
     }
   }
 };
@@ -187,7 +187,7 @@ template <typename T, int LPC, bool BC_CONST>
 __global__ void __launch_bounds__(64) scan_fwd_kernel(const cm_scan_fwd_args p) {
   using Ctx = FwdCtx<T, LPC, BC_CONST>;
   constexpr int NS = Ctx::NS, CPW = Ctx::CPW;
-  __shared__ __align__(16) float bc_smem[2][kBcTile * kBcPitch];
+  __shared__ __align__(16) float bc_smem[2][kGroup * kBcPitch];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -195,13 +195,12 @@ __global__ void __launch_bounds__(64) scan_fwd_kernel(const cm_scan_fwd_args p) 
   const int b = blockIdx.y;
   const int cl = lane / LPC;
   int d = blockIdx.x * CPW + cl;
+  const int L = p.seqlen;
 
   Ctx c;
-  c.L = p.seqlen;
   c.dstate = p.dstate;
   c.sg = lane % LPC;
   c.lane = lane;
-  c.rev = dp.reverse != 0;
   c.dvalid = d < p.dim;
   if (!c.dvalid) d = p.dim - 1;
   c.softplus = (p.flags & CM_FLAG_DELTA_SOFTPLUS) != 0;
@@ -221,35 +220,57 @@ __global__ void __launch_bounds__(64) scan_fwd_kernel(const cm_scan_fwd_args p) 
       c.Cc[i] = __ldg(static_cast<const float*>(dp.Cm.ptr) + d * dp.Cm.sb + n * dp.Cm.sd);
     }
   }
-  c.up = static_cast<const T*>(dp.u.ptr) + b * dp.u.sb + d * dp.u.sd;
-  c.u_sl = dp.u.sl;
-  c.dlp = static_cast<const T*>(dp.delta.ptr) + b * dp.delta.sb + d * dp.delta.sd;
-  c.dl_sl = dp.delta.sl;
-  c.zp = c.has_z ? static_cast<const T*>(p.z.ptr) + b * p.z.sb + d * p.z.sd : nullptr;
-  c.z_sl = p.z.sl;
+  // step-0 positions and signed per-step strides (descending time = negative stride)
+  const int64_t l0 = (dp.reverse != 0) ? (L - 1) : 0;
+  const int sgn = (dp.reverse != 0) ? -1 : 1;
+  c.up = static_cast<const T*>(dp.u.ptr) + b * dp.u.sb + d * dp.u.sd + l0 * dp.u.sl;
+  c.su = sgn * (int)dp.u.sl;
+  c.dlp = static_cast<const T*>(dp.delta.ptr) + b * dp.delta.sb + d * dp.delta.sd + l0 * dp.delta.sl;
+  c.sdl = sgn * (int)dp.delta.sl;
+  c.zp = c.has_z ? static_cast<const T*>(p.z.ptr) + b * p.z.sb + d * p.z.sd + l0 * p.z.sl : nullptr;
+  c.sz = sgn * (int)p.z.sl;
+  c.bcpA = nullptr; c.bcpB = nullptr;
+  c.bc_hiA = 0; c.bc_hiB = 0;
+  c.bc_okA = false; c.bc_okB = false;
+  c.sbc = 0;
+  c.bc_time_contig = false;
   if (!BC_CONST) {
-    c.Bp = static_cast<const T*>(dp.Bm.ptr) + b * dp.Bm.sb;
-    c.Cp = static_cast<const T*>(dp.Cm.ptr) + b * dp.Cm.sb;
-  } else {
-    c.Bp = nullptr;
-    c.Cp = nullptr;
+    const T* Bp = static_cast<const T*>(dp.Bm.ptr) + b * dp.Bm.sb + l0 * dp.Bm.sl;
+    const T* Cp = static_cast<const T*>(dp.Cm.ptr) + b * dp.Cm.sb + l0 * dp.Cm.sl;
+    c.bc_time_contig = (dp.Bm.sl == 1 && dp.Cm.sl == 1);
+    if (c.bc_time_contig) {
+      const int q = lane >> 2, k = lane & 3;
+      c.bcpA = Bp + (int64_t)q * dp.Bm.sd + (int64_t)k * sgn;
+      c.bcpB = Cp + (int64_t)q * dp.Cm.sd + (int64_t)k * sgn;
+      c.bc_hiA = 8 * dp.Bm.sd;
+      c.bc_hiB = 8 * dp.Cm.sd;
+      c.bc_okA = q < p.dstate;
+      c.bc_okB = q + 8 < p.dstate;
+      c.sbc = sgn;
+    } else {
+      const int n = lane & 15;
+      c.bcpA = (lane < 16) ? (Bp + n * dp.Bm.sd) : (Cp + n * dp.Cm.sd);
+      c.bc_okA = n < p.dstate;
+      c.sbc = sgn * (int)((lane < 16) ? dp.Bm.sl : dp.Cm.sl);
+    }
   }
-  c.B_sd = dp.Bm.sd; c.B_sl = dp.Bm.sl; c.C_sd = dp.Cm.sd; c.C_sl = dp.Cm.sl;
-  c.outp = static_cast<T*>(p.out.ptr) + b * p.out.sb + d * p.out.sd;
-  c.o_sl = p.out.sl;
-  c.outprep = p.out_pre.ptr ? static_cast<T*>(p.out_pre.ptr) + b * p.out_pre.sb + d * p.out_pre.sd : nullptr;
-  c.op_sl = p.out_pre.sl;
+  c.outp = static_cast<T*>(p.out.ptr) + b * p.out.sb + d * p.out.sd + l0 * p.out.sl;
+  c.so = sgn * (int)p.out.sl;
+  c.outprep = p.out_pre.ptr ? static_cast<T*>(p.out_pre.ptr) + b * p.out_pre.sb + d * p.out_pre.sd + l0 * p.out_pre.sl
+                            : nullptr;
+  c.sop = sgn * (int)p.out_pre.sl;
   c.ckp = dp.ckpt ? dp.ckpt + b * dp.ckpt_sb + d * dp.ckpt_sd : nullptr;
   c.bc = bc_smem[warp];
 
-  const int L = p.seqlen;
-  if (p.ndir == 1) {
-    c.template run_range<MODE_UNI>(0, L, 0);
-  } else {
-    const int s1 = cm_first_range(L, 2, dp.reverse);
-    c.template run_range<MODE_STASH>(0, s1, 0);
-    __syncthreads();  // partner's stash for the other half is now visible (same CTA, ld.global.cg)
-    c.template run_range<MODE_COMBINE>(s1, L, cm_ceil_div(s1, kGroup));
+  // One copy of the range body in the instruction stream (it must stay within the instruction cache): the
+  // bidirectional launch runs it twice with a CTA barrier in between.
+  const int s1 = cm_first_range(L, p.ndir, dp.reverse);
+  const int nrange = (p.ndir == 2) ? 2 : 1;
+#pragma unroll 1
+  for (int range = 0; range < nrange; ++range) {
+    if (range == 1) __syncthreads();  // partner's stash for the other half is now visible (same CTA, ld.global.cg)
+    c.mode = (p.ndir == 1) ? MODE_UNI : (range == 0 ? MODE_STASH : MODE_COMBINE);
+    c.run_range(range == 0 ? 0 : s1, range == 0 ? s1 : L, range == 0 ? 0 : cm_ceil_div(s1, CM_SCAN_CKPT_STEPS));
   }
 
   if (dp.last_state != nullptr && c.dvalid) {

@@ -10,7 +10,7 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libconmamba_b200.so")
+LIB_PATH = os.environ.get("CM_LIB_PATH") or os.path.join(_PKG, "lib", "libconmamba_b200.so")   # env: tuning experiments
 
 CM_F32, CM_BF16, CM_F16 = 0, 1, 2
 CM_ERR_BAD_ARG, CM_ERR_UNSUPPORTED = -1, -2

@@ -55,7 +55,8 @@ def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = _nvcc()
     headers = _headers()
-    flags = " ".join(NVCC_FLAGS)
+    extra = os.environ.get("CM_NVCC_EXTRA", "").split()      # tuning experiments, e.g. -DCM_FWD_MINB=8
+    flags = " ".join(NVCC_FLAGS + extra)
 
     def compile_one(src):
         path = os.path.join(CSRC, src)
@@ -64,7 +65,7 @@ def build(force=False, verbose=False):
         dg = _digest([path] + headers, flags)
         if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dg:
             return obj, False
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))

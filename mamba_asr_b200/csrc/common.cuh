@@ -12,6 +12,20 @@ namespace cm {
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
+// 16-bit global loads that land zero-extended in a full 32-bit register.  The C++ route (unsigned short -> uint32_t)
+// makes the compiler mask the value right after the LDG (LOP3 0xffff), which stalls the warp on every load and
+// defeats the register prefetch; PTX allows a destination wider than the access type.
+__device__ __forceinline__ uint32_t ld16_nc(const void* p) {
+  uint32_t v;
+  asm("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld16_cg(const void* p) {
+  uint32_t v;
+  asm volatile("ld.global.cg.u16 %0, [%1];" : "=r"(v) : "l"(p));   // coherent at L2: reads the partner warp's stash
+  return v;
+}
+
 // ---- element I/O ---------------------------------------------------------------------------------
 template <typename T>
 struct Elem;
@@ -31,10 +45,10 @@ struct Elem<float> {
 };
 template <>
 struct Elem<__nv_bfloat16> {
-  using Raw = unsigned short;
-  static __device__ __forceinline__ Raw ld_raw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const unsigned short*>(p)); }
-  static __device__ __forceinline__ Raw ld_raw_cg(const __nv_bfloat16* p) { return __ldcg(reinterpret_cast<const unsigned short*>(p)); }
-  static __device__ __forceinline__ float cvt(Raw r) { return __uint_as_float(static_cast<uint32_t>(r) << 16); }
+  using Raw = uint32_t;   // zero-extended 16 bits in a full register (a 16-bit Raw makes ptxas pack pairs with PRMT)
+  static __device__ __forceinline__ Raw ld_raw(const __nv_bfloat16* p) { return ld16_nc(p); }
+  static __device__ __forceinline__ Raw ld_raw_cg(const __nv_bfloat16* p) { return ld16_cg(p); }
+  static __device__ __forceinline__ float cvt(Raw r) { return __uint_as_float(r << 16); }
   static __device__ __forceinline__ float ld(const __nv_bfloat16* p) {
     unsigned short r = __ldg(reinterpret_cast<const unsigned short*>(p));
     return __uint_as_float(static_cast<uint32_t>(r) << 16);
@@ -48,10 +62,10 @@ struct Elem<__nv_bfloat16> {
 };
 template <>
 struct Elem<__half> {
-  using Raw = unsigned short;
-  static __device__ __forceinline__ Raw ld_raw(const __half* p) { return __ldg(reinterpret_cast<const unsigned short*>(p)); }
-  static __device__ __forceinline__ Raw ld_raw_cg(const __half* p) { return __ldcg(reinterpret_cast<const unsigned short*>(p)); }
-  static __device__ __forceinline__ float cvt(Raw r) { return __half2float(__ushort_as_half(r)); }
+  using Raw = uint32_t;
+  static __device__ __forceinline__ Raw ld_raw(const __half* p) { return ld16_nc(p); }
+  static __device__ __forceinline__ Raw ld_raw_cg(const __half* p) { return ld16_cg(p); }
+  static __device__ __forceinline__ float cvt(Raw r) { return __half2float(__ushort_as_half(static_cast<unsigned short>(r))); }
   static __device__ __forceinline__ float ld(const __half* p) {
     unsigned short r = __ldg(reinterpret_cast<const unsigned short*>(p));
     return __half2float(__ushort_as_half(r));
@@ -89,30 +103,62 @@ __device__ __forceinline__ float sigmoidf_fast(float x) { return rcp(1.0f + ex2(
 // instantiations use the two-MUFU form.  *sig receives d softplus / dx = sigmoid(x).
 template <bool PRECISE>
 __device__ __forceinline__ float softplus_fwd(float x) {
-  if (x > 20.0f) return x;
+  // branch-free: both forms are evaluated and selected
   const float e = ex2(x * kLog2e);
   float r = kLn2 * lg2(1.0f + e);
   if (PRECISE) {
-    if (e < 0.25f) {
-      // log1p(e) = e - e^2/2 + e^3/3 - ... ; |e| < 1/4, 11 terms: truncation < 1e-8 relative
-      float p = -1.0f / 12.0f;
-      p = fmaf(p, e, 1.0f / 11.0f);
-      p = fmaf(p, e, -1.0f / 10.0f);
-      p = fmaf(p, e, 1.0f / 9.0f);
-      p = fmaf(p, e, -1.0f / 8.0f);
-      p = fmaf(p, e, 1.0f / 7.0f);
-      p = fmaf(p, e, -1.0f / 6.0f);
-      p = fmaf(p, e, 1.0f / 5.0f);
-      p = fmaf(p, e, -1.0f / 4.0f);
-      p = fmaf(p, e, 1.0f / 3.0f);
-      p = fmaf(p, e, -1.0f / 2.0f);
-      p = fmaf(p, e, 1.0f);
-      r = p * e;
-    }
+    // log1p(e) = e - e^2/2 + e^3/3 - ... ; used for e < 1/4 (11 terms: truncation < 1e-8 relative), where the
+    // lg2.approx absolute error would dominate a small result
+    float p = -1.0f / 12.0f;
+    p = fmaf(p, e, 1.0f / 11.0f);
+    p = fmaf(p, e, -1.0f / 10.0f);
+    p = fmaf(p, e, 1.0f / 9.0f);
+    p = fmaf(p, e, -1.0f / 8.0f);
+    p = fmaf(p, e, 1.0f / 7.0f);
+    p = fmaf(p, e, -1.0f / 6.0f);
+    p = fmaf(p, e, 1.0f / 5.0f);
+    p = fmaf(p, e, -1.0f / 4.0f);
+    p = fmaf(p, e, 1.0f / 3.0f);
+    p = fmaf(p, e, -1.0f / 2.0f);
+    p = fmaf(p, e, 1.0f);
+    r = (e < 0.25f) ? p * e : r;
   }
-  return r;
+  return (x > 20.0f) ? x : r;
 }
 __device__ __forceinline__ float softplus_grad(float x) { return x > 20.0f ? 1.0f : sigmoidf_fast(x); }
+
+// sigmoid for 16-bit outputs: one MUFU (tanh.approx, |rel err| ~2^-11) instead of ex2 + rcp
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <bool PRECISE>
+__device__ __forceinline__ float sigmoid_sel(float x) {
+  if (PRECISE) return sigmoidf_fast(x);
+  return fmaf(tanh_approx(0.5f * x), 0.5f, 0.5f);
+}
+
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 lanes per issue slot) ---------------
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; "
+      "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd; }"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd; }"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd; }"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 

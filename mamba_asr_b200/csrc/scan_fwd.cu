@@ -42,50 +42,68 @@ struct FwdCtx {
   using Raw = typename Elem<T>::Raw;
 
   // per-lane state
-  int dstate, sg, lane, mode;
+  int dstate, sg, lane, mode, seqlen;
   bool dvalid, softplus, has_z, bc_time_contig;
   float scale, Dsk, bias;
-  float kA[NS], h[NS], Bc[NS], Cc[NS];
-  // pointers are positioned at processed step 0; the s* members are signed element strides per processed step
-  const T *up, *dlp, *zp;
-  const T *bcpA, *bcpB;             // this lane's B/C sources (see load_group)
-  int64_t bc_hiA, bc_hiB;           // time-contiguous layout: offset of the lane's second state (n + 8)
-  bool bc_okA, bc_okB;              // ... and whether n / n + 8 are real states
+  float2 kA2[NS / 2], h2[NS / 2];   // state pairs for FFMA2 / FMUL2
+  float Bc[NS], Cc[NS];
+  // byte pointers positioned at processed step 0; the s* members are signed BYTE strides per processed step, so an
+  // address is one IMAD.WIDE (stride * step + base)
+  const char *up, *dlp, *zp;
+  const char* bcpA;                 // this lane's B/C source (see load_group)
+  bool bc_okA;                      // ... and whether it is a real state
+  const cm_scan_dir* dirp;          // kernel parameter block of this direction (slow paths re-derive from it)
+  int bidx;
+  bool stash_mode, pre_ok, st_ok;   // per-range output predicates (see run_range)
   int su, sdl, sz, so, sop, sbc;
-  T *outp, *outprep;
+  char *outp, *outprep;
   float* ckp;  // row base of the checkpoints, or nullptr
   float* bc;   // this warp's staging buffer [kGroup][kBcPitch]
 
+  static __device__ __forceinline__ const T* at(const char* base, int stride_bytes, int s) {
+    return reinterpret_cast<const T*>(base + (int64_t)stride_bytes * (int64_t)s);
+  }
+  static __device__ __forceinline__ T* at(char* base, int stride_bytes, int s) {
+    return reinterpret_cast<T*>(base + (int64_t)stride_bytes * (int64_t)s);
+  }
+
   // Prefetch of one group: every global load of the group is issued here, back to back, into raw registers.
+  // FULL: all kGroup steps exist (no predicates in the instruction stream of the steady state).
+  template <bool FULL>
   __device__ __forceinline__ void load_group(FwdGroup<T>& g, int s0, int nvalid) const {
     const bool need_z = has_z && mode != MODE_STASH;
     const bool need_st = mode == MODE_COMBINE;
 #pragma unroll
     for (int k = 0; k < kGroup; ++k) {
-      const int64_t s = s0 + k;
+      const int s = s0 + k;
       g.u[k] = Raw(0); g.dl[k] = Raw(0); g.z[k] = Raw(0); g.st[k] = Raw(0); g.bc[k] = Raw(0);
-      if (k < nvalid) {
-        g.u[k] = Elem<T>::ld_raw(up + s * su);
-        g.dl[k] = Elem<T>::ld_raw(dlp + s * sdl);
-        if (need_z) g.z[k] = Elem<T>::ld_raw(zp + s * sz);
-        if (need_st) g.st[k] = Elem<T>::ld_raw_cg(outp + s * so);
+      if (FULL || k < nvalid) {
+        g.u[k] = Elem<T>::ld_raw(at(up, su, s));
+        g.dl[k] = Elem<T>::ld_raw(at(dlp, sdl, s));
+        if (need_z) g.z[k] = Elem<T>::ld_raw(at(zp, sz, s));
+        if (need_st) g.st[k] = Elem<T>::ld_raw_cg(at(outp, so, s));
       }
     }
     if (!BC_CONST) {
       if (bc_time_contig) {
-        // time-contiguous B/C (the reference's (B, 1, N, L) layout): lane -> step k = lane & 3, state q = lane >> 2;
-        // the four loads are B[q], B[q + 8], C[q], C[q + 8] at that step
+        // time-contiguous B/C (the reference's (B, 1, N, L) layout; compatibility path): lane -> step k = lane & 3,
+        // state q = lane >> 2; the four loads are B[q], B[q + 8], C[q], C[q + 8] at that step.  Addresses are
+        // re-derived from the parameter block to keep the hot path's register footprint small.
         static_assert(kGroup == 4, "lane mapping below assumes 4-step groups");
-        if ((lane & 3) < nvalid) {
-          const int64_t off = (int64_t)s0 * sbc;
-          if (bc_okA) { g.bc[0] = Elem<T>::ld_raw(bcpA + off); g.bc[2] = Elem<T>::ld_raw(bcpB + off); }
-          if (bc_okB) { g.bc[1] = Elem<T>::ld_raw(bcpA + bc_hiA + off); g.bc[3] = Elem<T>::ld_raw(bcpB + bc_hiB + off); }
+        if (FULL || (lane & 3) < nvalid) {
+          const cm_scan_dir& dp = *dirp;
+          const int q = lane >> 2;
+          const int64_t t = dp.reverse ? (int64_t)(seqlen - 1 - (s0 + (lane & 3))) : (int64_t)(s0 + (lane & 3));
+          const T* Bq = static_cast<const T*>(dp.Bm.ptr) + bidx * dp.Bm.sb + q * dp.Bm.sd + t;
+          const T* Cq = static_cast<const T*>(dp.Cm.ptr) + bidx * dp.Cm.sb + q * dp.Cm.sd + t;
+          if (q < dstate) { g.bc[0] = Elem<T>::ld_raw(Bq); g.bc[2] = Elem<T>::ld_raw(Cq); }
+          if (q + 8 < dstate) { g.bc[1] = Elem<T>::ld_raw(Bq + 8 * dp.Bm.sd); g.bc[3] = Elem<T>::ld_raw(Cq + 8 * dp.Cm.sd); }
         }
       } else if (bc_okA) {
         // state-contiguous rows (slices of the time-major x_dbl): lane -> value v = lane, k-th load = step k
 #pragma unroll
         for (int k = 0; k < kGroup; ++k)
-          if (k < nvalid) g.bc[k] = Elem<T>::ld_raw(bcpA + (int64_t)(s0 + k) * sbc);
+          if (FULL || k < nvalid) g.bc[k] = Elem<T>::ld_raw(at(bcpA, sbc, s0 + k));
       }
     }
   }
@@ -104,87 +122,126 @@ struct FwdCtx {
     __syncwarp();
   }
 
-  // one recurrence step; `row` = this step's staged B/C row
-  __device__ __forceinline__ void step(Raw ur, Raw dlr, Raw zr, Raw str, int64_t s, const float* row) {
-    float Bv[NS], Cv[NS];
-    if (BC_CONST) {
-#pragma unroll
-      for (int i = 0; i < NS; ++i) { Bv[i] = Bc[i]; Cv[i] = Cc[i]; }
-    } else {
-      const float4* rb = reinterpret_cast<const float4*>(row + sg * NS);
-      const float4* rc = reinterpret_cast<const float4*>(row + 16 + sg * NS);
-#pragma unroll
-      for (int i = 0; i < NS / 4; ++i) {
-        const float4 b4 = rb[i], c4 = rc[i];
-        Bv[4 * i + 0] = b4.x; Bv[4 * i + 1] = b4.y; Bv[4 * i + 2] = b4.z; Bv[4 * i + 3] = b4.w;
-        Cv[4 * i + 0] = c4.x; Cv[4 * i + 1] = c4.y; Cv[4 * i + 2] = c4.z; Cv[4 * i + 3] = c4.w;
-      }
-    }
+  // one recurrence step; `row` = this step's staged B/C row.  State update on fp32 pairs:
+  //   x2 = dt*kA ; a2 = ex2(x2) ; h2 = a2*h2 + (dt*u)*B2 ; y2 += C2*h2      -> 2 FMUL2 + 2 FFMA2 + 2 MUFU per pair
+  __device__ __forceinline__ void step(Raw ur, Raw dlr, Raw zr, Raw str, int s, const float* row) {
     const float uu = Elem<T>::cvt(ur);
     const float x = Elem<T>::cvt(dlr) + bias;
     const float dt = softplus ? softplus_fwd<sizeof(T) == 4>(x) : x;
     const float du = dt * uu;
-    float y0 = 0.f, y1 = 0.f;
+    const float2 dt2 = make_float2(dt, dt), du2 = make_float2(du, du);
+    // pass 1: state update (needs B); pass 2: output contraction (needs C).  Two passes keep only one of the two
+    // 16-float operand rows live at a time.
+    {
+      float2 B2[NS / 2];
+      if (BC_CONST) {
 #pragma unroll
-    for (int i = 0; i < NS; ++i) {
-      const float a = ex2(dt * kA[i]);
-      h[i] = fmaf(a, h[i], du * Bv[i]);
-      if (i & 1) y1 = fmaf(Cv[i], h[i], y1); else y0 = fmaf(Cv[i], h[i], y0);
+        for (int i = 0; i < NS / 2; ++i) B2[i] = make_float2(Bc[2 * i], Bc[2 * i + 1]);
+      } else {
+        const float4* rb = reinterpret_cast<const float4*>(row + sg * NS);
+#pragma unroll
+        for (int i = 0; i < NS / 4; ++i) {
+          const float4 b4 = rb[i];
+          B2[2 * i] = make_float2(b4.x, b4.y); B2[2 * i + 1] = make_float2(b4.z, b4.w);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NS / 2; ++i) {
+        const float2 x2 = fmul2(dt2, kA2[i]);
+        const float2 a2 = make_float2(ex2(x2.x), ex2(x2.y));
+        h2[i] = ffma2(a2, h2[i], fmul2(du2, B2[i]));
+      }
     }
-    float y = y0 + y1;
+    float2 ya = make_float2(0.f, 0.f), yb = make_float2(0.f, 0.f);
+    {
+      float2 C2[NS / 2];
+      if (BC_CONST) {
+#pragma unroll
+        for (int i = 0; i < NS / 2; ++i) C2[i] = make_float2(Cc[2 * i], Cc[2 * i + 1]);
+      } else {
+        const float4* rc = reinterpret_cast<const float4*>(row + 16 + sg * NS);
+#pragma unroll
+        for (int i = 0; i < NS / 4; ++i) {
+          const float4 c4 = rc[i];
+          C2[2 * i] = make_float2(c4.x, c4.y); C2[2 * i + 1] = make_float2(c4.z, c4.w);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NS / 2; ++i) {
+        if (i & 1) yb = ffma2(C2[i], h2[i], yb); else ya = ffma2(C2[i], h2[i], ya);
+      }
+    }
+    const float2 ys = fadd2(ya, yb);
+    float y = ys.x + ys.y;
     if (LPC >= 2) y += __shfl_xor_sync(0xffffffffu, y, 1);
     if (LPC >= 4) y += __shfl_xor_sync(0xffffffffu, y, 2);
     y = fmaf(Dsk, uu, y);
-    if (mode == MODE_STASH) {
-      if (sg == 0 && dvalid) Elem<T>::st(outp + s * so, y);
-    } else {
-      float tot = (mode == MODE_COMBINE) ? (y + Elem<T>::cvt(str)) : y;
-      if (sg == 0 && dvalid) {
-        if (outprep) Elem<T>::st(outprep + s * sop, tot);
-        if (has_z) { const float zz = Elem<T>::cvt(zr); tot *= zz * sigmoidf_fast(zz); }
-        Elem<T>::st(outp + s * so, tot * scale);
-      }
-    }
+    // branch-free output: first-half steps stash the raw y, the others write the gated sum (stash is 0 and the
+    // gate input is 0 whenever they do not apply)
+    const float tot = y + Elem<T>::cvt(str);
+    const float zz = Elem<T>::cvt(zr);
+    const float gate = has_z ? zz * sigmoid_sel<sizeof(T) == 4>(zz) : 1.f;
+    const float val = stash_mode ? y : tot * gate * scale;
+    if (pre_ok) Elem<T>::st(at(outprep, sop, s), tot);
+    if (st_ok) Elem<T>::st(at(outp, so, s), val);
   }
 
   __device__ __forceinline__ void save_ckpt(int j) const {
     if (ckp != nullptr && dvalid) {
       float4* dst = reinterpret_cast<float4*>(ckp + (int64_t)j * 16 + sg * NS);
 #pragma unroll
-      for (int i = 0; i < NS / 4; ++i) dst[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+      for (int i = 0; i < NS / 4; ++i) dst[i] = make_float4(h2[2 * i].x, h2[2 * i].y, h2[2 * i + 1].x, h2[2 * i + 1].y);
     }
   }
 
   // Processes steps [s_begin, s_end) in groups of kGroup.  While group g computes (fully unrolled, branch-free),
   // every load of group g+1 - u, delta, z, stash and the B/C rows - is already in flight.
+  __device__ __forceinline__ void do_group(const FwdGroup<T>& cur, FwdGroup<T>& nxt, int g, int s_begin, int s_end,
+                                           int nfull, int j0) {
+    const int s0 = s_begin + g * kGroup;
+    publish_bc(cur);
+    if (g + 1 < nfull) load_group<true>(nxt, s0 + kGroup, kGroup);
+    else load_group<false>(nxt, s0 + kGroup, max(0, s_end - s0 - kGroup));
+    if ((g % kCkptGroups) == 0) save_ckpt(j0 + g / kCkptGroups);
+    if (g < nfull) {
+#pragma unroll
+      for (int k = 0; k < kGroup; ++k) {
+        step(cur.u[k], cur.dl[k], cur.z[k], cur.st[k], s0 + k, bc + k * kBcPitch);
+#ifdef CM_FWD_STEP_FENCE
+        asm volatile("" ::: "memory");   // keep the B/C LDS of later steps from being hoisted (register pressure)
+#endif
+      }
+    } else {
+      const int nvalid = s_end - s0;
+#pragma unroll
+      for (int k = 0; k < kGroup - 1; ++k)
+        if (k < nvalid) step(cur.u[k], cur.dl[k], cur.z[k], cur.st[k], s0 + k, bc + k * kBcPitch);
+    }
+  }
+
   __device__ __forceinline__ void run_range(int s_begin, int s_end, int j0) {
     if (s_begin >= s_end) return;
+    stash_mode = mode == MODE_STASH;
+    st_ok = (sg == 0) && dvalid;
+    pre_ok = st_ok && !stash_mode && outprep != nullptr;
     const int n = s_end - s_begin;
     const int ngroup = (n + kGroup - 1) / kGroup;
-    FwdGroup<T> cur, nxt;
-    load_group(cur, s_begin, min(kGroup, n));
+    const int nfull = n / kGroup;
+    FwdGroup<T> ga, gb;     // ping-pong prefetch buffers (no register copies between groups)
+    if (nfull > 0) load_group<true>(ga, s_begin, kGroup); else load_group<false>(ga, s_begin, n);
 #pragma unroll 1
-    for (int g = 0; g < ngroup; ++g) {
-      const int s0 = s_begin + g * kGroup;
-      const int nvalid = min(kGroup, s_end - s0);
-      publish_bc(cur);
-      load_group(nxt, s0 + kGroup, max(0, min(kGroup, s_end - s0 - kGroup)));
-      if ((g % kCkptGroups) == 0) save_ckpt(j0 + g / kCkptGroups);
-      if (nvalid == kGroup) {
-#pragma unroll
-        for (int k = 0; k < kGroup; ++k) step(cur.u[k], cur.dl[k], cur.z[k], cur.st[k], s0 + k, bc + k * kBcPitch);
-      } else {
-#pragma unroll
-        for (int k = 0; k < kGroup - 1; ++k)
-          if (k < nvalid) step(cur.u[k], cur.dl[k], cur.z[k], cur.st[k], s0 + k, bc + k * kBcPitch);
-      }
-      cur = nxt;
+    for (int g = 0; g < ngroup; g += 2) {
+      do_group(ga, gb, g, s_begin, s_end, nfull, j0);
+      if (g + 1 < ngroup) do_group(gb, ga, g + 1, s_begin, s_end, nfull, j0);
     }
   }
 };
 
+#ifndef CM_FWD_MINB
+#define CM_FWD_MINB 8   // <= 128 registers: 8 two-warp CTAs per SM, so e.g. 64 x 512 channels x 2 directions is one wave
+#endif
 template <typename T, int LPC, bool BC_CONST>
-__global__ void __launch_bounds__(64) scan_fwd_kernel(const cm_scan_fwd_args p) {
+__global__ void __launch_bounds__(64, CM_FWD_MINB) scan_fwd_kernel(const __grid_constant__ cm_scan_fwd_args p) {
   using Ctx = FwdCtx<T, LPC, BC_CONST>;
   constexpr int NS = Ctx::NS, CPW = Ctx::CPW;
   __shared__ __align__(16) float bc_smem[2][kGroup * kBcPitch];
@@ -211,8 +268,9 @@ __global__ void __launch_bounds__(64) scan_fwd_kernel(const cm_scan_fwd_args p) 
 #pragma unroll
   for (int i = 0; i < NS; ++i) {
     const int n = c.sg * NS + i;
-    c.kA[i] = (n < p.dstate) ? __ldg(dp.A + d * dp.A_sd + n * dp.A_sn) * kLog2e : 0.f;
-    c.h[i] = 0.f;
+    const float ka = (n < p.dstate) ? __ldg(dp.A + d * dp.A_sd + n * dp.A_sn) * kLog2e : 0.f;
+    if (i & 1) c.kA2[i / 2].y = ka; else c.kA2[i / 2].x = ka;
+    if (i & 1) c.h2[i / 2].y = 0.f; else c.h2[i / 2].x = 0.f;
     c.Bc[i] = 0.f;
     c.Cc[i] = 0.f;
     if (BC_CONST && n < p.dstate) {
@@ -220,45 +278,40 @@ __global__ void __launch_bounds__(64) scan_fwd_kernel(const cm_scan_fwd_args p) 
       c.Cc[i] = __ldg(static_cast<const float*>(dp.Cm.ptr) + d * dp.Cm.sb + n * dp.Cm.sd);
     }
   }
-  // step-0 positions and signed per-step strides (descending time = negative stride)
+  // step-0 positions and signed per-step BYTE strides (descending time = negative stride)
   const int64_t l0 = (dp.reverse != 0) ? (L - 1) : 0;
   const int sgn = (dp.reverse != 0) ? -1 : 1;
-  c.up = static_cast<const T*>(dp.u.ptr) + b * dp.u.sb + d * dp.u.sd + l0 * dp.u.sl;
-  c.su = sgn * (int)dp.u.sl;
-  c.dlp = static_cast<const T*>(dp.delta.ptr) + b * dp.delta.sb + d * dp.delta.sd + l0 * dp.delta.sl;
-  c.sdl = sgn * (int)dp.delta.sl;
-  c.zp = c.has_z ? static_cast<const T*>(p.z.ptr) + b * p.z.sb + d * p.z.sd + l0 * p.z.sl : nullptr;
-  c.sz = sgn * (int)p.z.sl;
-  c.bcpA = nullptr; c.bcpB = nullptr;
-  c.bc_hiA = 0; c.bc_hiB = 0;
-  c.bc_okA = false; c.bc_okB = false;
+  constexpr int ES = (int)sizeof(T);
+  auto cptr = [](const void* base, int64_t elems) { return static_cast<const char*>(base) + elems * ES; };
+  c.up = cptr(dp.u.ptr, b * dp.u.sb + d * dp.u.sd + l0 * dp.u.sl);
+  c.su = sgn * ES * (int)dp.u.sl;
+  c.dlp = cptr(dp.delta.ptr, b * dp.delta.sb + d * dp.delta.sd + l0 * dp.delta.sl);
+  c.sdl = sgn * ES * (int)dp.delta.sl;
+  c.zp = c.has_z ? cptr(p.z.ptr, b * p.z.sb + d * p.z.sd + l0 * p.z.sl) : nullptr;
+  c.sz = sgn * ES * (int)p.z.sl;
+  c.bcpA = nullptr;
+  c.bc_okA = false;
   c.sbc = 0;
   c.bc_time_contig = false;
+  c.dirp = &dp;
+  c.bidx = b;
+  c.seqlen = L;
   if (!BC_CONST) {
-    const T* Bp = static_cast<const T*>(dp.Bm.ptr) + b * dp.Bm.sb + l0 * dp.Bm.sl;
-    const T* Cp = static_cast<const T*>(dp.Cm.ptr) + b * dp.Cm.sb + l0 * dp.Cm.sl;
+    const int64_t Boff = b * dp.Bm.sb + l0 * dp.Bm.sl, Coff = b * dp.Cm.sb + l0 * dp.Cm.sl;
     c.bc_time_contig = (dp.Bm.sl == 1 && dp.Cm.sl == 1);
-    if (c.bc_time_contig) {
-      const int q = lane >> 2, k = lane & 3;
-      c.bcpA = Bp + (int64_t)q * dp.Bm.sd + (int64_t)k * sgn;
-      c.bcpB = Cp + (int64_t)q * dp.Cm.sd + (int64_t)k * sgn;
-      c.bc_hiA = 8 * dp.Bm.sd;
-      c.bc_hiB = 8 * dp.Cm.sd;
-      c.bc_okA = q < p.dstate;
-      c.bc_okB = q + 8 < p.dstate;
-      c.sbc = sgn;
-    } else {
+    if (!c.bc_time_contig) {
       const int n = lane & 15;
-      c.bcpA = (lane < 16) ? (Bp + n * dp.Bm.sd) : (Cp + n * dp.Cm.sd);
+      c.bcpA = (lane < 16) ? cptr(dp.Bm.ptr, Boff + n * dp.Bm.sd) : cptr(dp.Cm.ptr, Coff + n * dp.Cm.sd);
       c.bc_okA = n < p.dstate;
-      c.sbc = sgn * (int)((lane < 16) ? dp.Bm.sl : dp.Cm.sl);
+      c.sbc = sgn * ES * (int)((lane < 16) ? dp.Bm.sl : dp.Cm.sl);
     }
   }
-  c.outp = static_cast<T*>(p.out.ptr) + b * p.out.sb + d * p.out.sd + l0 * p.out.sl;
-  c.so = sgn * (int)p.out.sl;
-  c.outprep = p.out_pre.ptr ? static_cast<T*>(p.out_pre.ptr) + b * p.out_pre.sb + d * p.out_pre.sd + l0 * p.out_pre.sl
-                            : nullptr;
-  c.sop = sgn * (int)p.out_pre.sl;
+  c.outp = const_cast<char*>(cptr(p.out.ptr, b * p.out.sb + d * p.out.sd + l0 * p.out.sl));
+  c.so = sgn * ES * (int)p.out.sl;
+  c.outprep = p.out_pre.ptr
+                  ? const_cast<char*>(cptr(p.out_pre.ptr, b * p.out_pre.sb + d * p.out_pre.sd + l0 * p.out_pre.sl))
+                  : nullptr;
+  c.sop = sgn * ES * (int)p.out_pre.sl;
   c.ckp = dp.ckpt ? dp.ckpt + b * dp.ckpt_sb + d * dp.ckpt_sd : nullptr;
   c.bc = bc_smem[warp];
 
@@ -278,7 +331,7 @@ __global__ void __launch_bounds__(64) scan_fwd_kernel(const cm_scan_fwd_args p) 
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
       const int n = c.sg * NS + i;
-      if (n < p.dstate) ls[n * dp.ls_sn] = c.h[i];
+      if (n < p.dstate) ls[n * dp.ls_sn] = (i & 1) ? c.h2[i / 2].y : c.h2[i / 2].x;
     }
   }
 }

@@ -200,6 +200,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-steps", type=int, default=2)
     args = ap.parse_args()
 
@@ -253,41 +254,72 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
+    def step_eager(w, t):
         model.zero_grad(set_to_none=True)
-        return ctc_step(net, wav_d, tgt_d, True)
+        return ctc_step(net, w, t, True)
 
-    def step_e2e():
-        model.zero_grad(set_to_none=True)
-        w = wav_pin.to(dev, non_blocking=True)
-        t = tgt_pin.to(dev, non_blocking=True)
-        return float(ctc_step(net, w, t, True).item())
+    # One CUDA graph for forward + CTC loss + backward (the step is host-launch-bound otherwise); eager fallback if
+    # the capture is refused (e.g. a collective that cannot be captured).
+    graph_note = "eager launches (--no-graph)"
+    step_fn = step_eager
+    launches_per_step = None
+    if not args.no_graph:
+        try:
+            # forward graph + backward graph of the whole model (wav -> log-probs); the CTC loss between them stays
+            # eager because its length tensors live on the host
+            from mamba_asr_b200.graphs import graph_module
+            l0 = K.LAUNCHES
+            gnet = graph_module(net, (wav_d,), warmup=3)
+            launches_per_step = (K.LAUNCHES - l0) // 4          # 3 warm-ups + 1 capture
+
+            def step_graphed(w, t):
+                model.zero_grad(set_to_none=True)
+                return ctc_step(gnet, w, t, True)
+            step_graphed(wav_d, tgt_d)
+            torch.cuda.synchronize()
+            step_fn = step_graphed
+            graph_note = "model forward and backward replayed as CUDA graphs (CTC loss eager in between)"
+        except Exception as ex:
+            torch.cuda.synchronize()
+            graph_note = "eager launches (graph capture refused: %s)" % (repr(ex)[:160])
+            step_fn = step_eager
 
     for _ in range(warmup):
-        step_resident()
+        step_fn(wav_d, tgt_d)
     barrier()
     torch.cuda.reset_peak_memory_stats()
 
-    # ---- timed region: K steps, device events, kernel-level events for the roofline -----------------------------
+    # ---- timed region: K steps, device events -------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     launches0 = K.LAUNCHES
-    K.start_timing()
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        loss = step_resident()
+        loss = step_fn(wav_d, tgt_d)
     e1.record()
     barrier()
     clocks = sampler.stop()
-    ktimes = K.stop_timing()
-    launches = K.LAUNCHES - launches0
+    launches = (K.LAUNCHES - launches0) if launches_per_step is None else launches_per_step * steps
     elapsed_ms = e0.elapsed_time(e1)
     peak_mem = torch.cuda.max_memory_allocated()
     loss_val = float(loss.item())
 
-    # ---- end-to-end: host audio -> H2D -> step -> loss D2H, every step -----------------------------------------
+    # ---- per-kernel CUDA events for the roofline: the same step, launched eagerly right after the timed region ------
+    for _ in range(2):
+        step_eager(wav_d, tgt_d)
+    K.start_timing()
+    for _ in range(3):
+        step_eager(wav_d, tgt_d)
+    ktimes = K.stop_timing()
+
+    # ---- end-to-end: pinned host audio -> H2D -> step -> loss D2H, every step ---------------------------------
+    def step_e2e():
+        wav_d.copy_(wav_pin, non_blocking=True)              # host -> device copy of this step's inputs
+        tgt_d.copy_(tgt_pin, non_blocking=True)
+        return float(step_fn(wav_d, tgt_d).item())           # device -> host read of the loss
+
     for _ in range(2):
         step_e2e()
     barrier()
@@ -355,6 +387,9 @@ def main():
                        "step": "Fbank+norm+CNN+%d ConMamba layers+CTC loss, forward+backward, bf16 autocast, no optimizer"
                                % cfg["num_layers"],
                        "parallelism": "dp%d (DDP grad all-reduce over NCCL)" % world if world > 1 else "single GPU",
+                       "launch": graph_note,
+                       "roofline_timing": "per-kernel CUDA events from 3 eager launches of the same step right after "
+                                          "the timed region (kernels inside a graph replay cannot carry events)",
                        "l2": "no flush: activations touched per step (peak %.2f GB allocated) exceed the 126 MB L2"
                              % (peak_mem / 1e9)},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / steps,

@@ -141,6 +141,14 @@ int cm_reduce_dbc(const float* part, int32_t batch, int32_t n_slab, int32_t seql
                   int32_t dtype, cm_tensor3 dB, cm_tensor3 dC, void* stream);
 /* out[c] = sum_r part[r*cols + c]   (fp32; deterministic order) - dA, dD, d(delta_bias), conv dweight/dbias */
 int cm_reduce_rows(const float* part, int64_t rows, int64_t cols, float* out, void* stream);
+/* the same for up to CM_REDUCE_MAX_JOBS independent (part, rows, cols, out) jobs in ONE launch */
+#define CM_REDUCE_MAX_JOBS 8
+typedef struct {
+  const float* part;
+  float* out;
+  int64_t rows, cols;
+} cm_reduce_job;
+int cm_reduce_multi(const cm_reduce_job* jobs, int32_t njobs, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Depthwise causal conv1d (+ SiLU).  Replaces causal_conv1d_cuda.causal_conv1d_fwd / _bwd of
@@ -207,7 +215,7 @@ int cm_fbank_floor(const cm_fbank_args* args, void* stream);
 /* library identification: returns CM_ABI_VERSION; writes the compiled-for arch (e.g. 100) to *sm_arch if non-NULL */
 int cm_version(int32_t* sm_arch);
 /* sizeof() of the argument structs, for binding self-checks: 0 cm_tensor3, 1 cm_scan_dir, 2 cm_scan_fwd_args,
- * 3 cm_scan_bwd_dir, 4 cm_scan_bwd_args, 5 cm_conv_dir, 6 cm_conv_args, 7 cm_fbank_args */
+ * 3 cm_scan_bwd_dir, 4 cm_scan_bwd_args, 5 cm_conv_dir, 6 cm_conv_args, 7 cm_fbank_args, 8 cm_reduce_job */
 int cm_abi_sizeof(int32_t which);
 
 #ifdef __cplusplus

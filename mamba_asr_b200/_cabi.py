@@ -22,8 +22,9 @@ CM_ABI_VERSION = 1
 EXPORTS = (
     "cm_version", "cm_scan_num_ckpt", "cm_scan_slab_channels", "cm_scan_pick_lanes", "cm_scan_fwd", "cm_scan_bwd",
     "cm_reduce_dbc", "cm_reduce_rows", "cm_conv_fwd", "cm_conv_num_part", "cm_conv_bwd", "cm_conv_update",
-    "cm_fbank_logmel", "cm_fbank_floor", "cm_abi_sizeof",
+    "cm_fbank_logmel", "cm_fbank_floor", "cm_abi_sizeof", "cm_reduce_multi",
 )
+CM_REDUCE_MAX_JOBS = 8
 
 _DTYPES = {torch.float32: CM_F32, torch.bfloat16: CM_BF16, torch.float16: CM_F16}
 
@@ -96,7 +97,11 @@ class FbankArgs(C.Structure):
     ]
 
 
-ABI_STRUCTS = (Tensor3, ScanDir, ScanFwdArgs, ScanBwdDir, ScanBwdArgs, ConvDir, ConvArgs, FbankArgs)
+class ReduceJob(C.Structure):
+    _fields_ = [("part", C.c_void_p), ("out", C.c_void_p), ("rows", C.c_int64), ("cols", C.c_int64)]
+
+
+ABI_STRUCTS = (Tensor3, ScanDir, ScanFwdArgs, ScanBwdDir, ScanBwdArgs, ConvDir, ConvArgs, FbankArgs, ReduceJob)
 
 _lib = None
 
@@ -129,6 +134,7 @@ def lib():
         L.cm_fbank_logmel.argtypes = [C.POINTER(FbankArgs), C.c_void_p]
         L.cm_fbank_floor.argtypes = [C.POINTER(FbankArgs), C.c_void_p]
         L.cm_abi_sizeof.argtypes = [C.c_int32]
+        L.cm_reduce_multi.argtypes = [C.POINTER(ReduceJob), C.c_int32, C.c_void_p]
         if L.cm_version(None) != CM_ABI_VERSION:
             raise RuntimeError("mamba_asr_b200: %s has a different ABI version; rebuild it" % LIB_PATH)
         for i, st in enumerate(ABI_STRUCTS):

@@ -43,6 +43,16 @@ __device__ __forceinline__ void load_row(const float* src, float (&dst)[NS]) {
   }
 }
 
+template <int NP>
+__device__ __forceinline__ void load_row2(const float* src, float2 (&dst)[NP]) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int i = 0; i < NP / 2; ++i) {
+    const float4 v = s4[i];
+    dst[2 * i] = make_float2(v.x, v.y); dst[2 * i + 1] = make_float2(v.z, v.w);
+  }
+}
+
 template <typename T, int LPC, bool BC_CONST>
 __global__ void __launch_bounds__(32) scan_bwd_kernel(const cm_scan_bwd_args p) {
   constexpr int NS = 16 / LPC, CPW = 32 / LPC;
@@ -67,12 +77,16 @@ __global__ void __launch_bounds__(32) scan_bwd_kernel(const cm_scan_bwd_args p) 
   const float Dsk = dp.Dskip ? __ldg(dp.Dskip + d) : 0.f;
   const float bias = dp.delta_bias ? __ldg(dp.delta_bias + d) : 0.f;
 
-  float kA[NS], mu[NS], dA[NS], Bc[NS], Cc[NS], dBacc[NS], dCacc[NS];
+  constexpr int NP = NS / 2;   // state pairs (FFMA2 / FMUL2)
+  float2 kA2[NP], mu2[NP], dA2[NP];
+  float Bc[NS], Cc[NS], dBacc[NS], dCacc[NS];
 #pragma unroll
   for (int i = 0; i < NS; ++i) {
     const int n = sg * NS + i;
-    kA[i] = (n < p.dstate) ? __ldg(dp.A + d * dp.A_sd + n * dp.A_sn) * kLog2e : 0.f;
-    mu[i] = 0.f; dA[i] = 0.f; Bc[i] = 0.f; Cc[i] = 0.f; dBacc[i] = 0.f; dCacc[i] = 0.f;
+    const float ka = (n < p.dstate) ? __ldg(dp.A + d * dp.A_sd + n * dp.A_sn) * kLog2e : 0.f;
+    if (i & 1) { kA2[i / 2].y = ka; mu2[i / 2].y = 0.f; dA2[i / 2].y = 0.f; }
+    else { kA2[i / 2].x = ka; mu2[i / 2].x = 0.f; dA2[i / 2].x = 0.f; }
+    Bc[i] = 0.f; Cc[i] = 0.f; dBacc[i] = 0.f; dCacc[i] = 0.f;
     if (BC_CONST && n < p.dstate) {
       Bc[i] = __ldg(static_cast<const float*>(dp.Bm.ptr) + d * dp.Bm.sb + n * dp.Bm.sd);   // constants are fp32
       Cc[i] = __ldg(static_cast<const float*>(dp.Cm.ptr) + d * dp.Cm.sb + n * dp.Cm.sd);
@@ -172,13 +186,13 @@ __global__ void __launch_bounds__(32) scan_bwd_kernel(const cm_scan_bwd_args p) 
             if (k < nvalid) bcr[k] = Elem<T>::ld_raw(bcpA + (int64_t)(s0 + k) * sbc);
         }
       }
-      float h[NS];
+      float2 h2[NP];
       {
         const float4* src = reinterpret_cast<const float4*>(ckp + (int64_t)(j0 + t) * 16 + sg * NS);
 #pragma unroll
         for (int i = 0; i < NS / 4; ++i) {
           const float4 v = __ldg(src + i);
-          h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
+          h2[2 * i] = make_float2(v.x, v.y); h2[2 * i + 1] = make_float2(v.z, v.w);
         }
       }
       // publish B/C to the warp
@@ -214,7 +228,7 @@ __global__ void __launch_bounds__(32) scan_bwd_kernel(const cm_scan_bwd_args p) 
         }
       }
 
-      // ---- phase 1: recompute the tile's states from its checkpoint -------------------------------
+      // ---- phase 1: recompute the tile's states from its checkpoint (fp32 pairs: FMUL2 / FFMA2) ------
       float dtv[kTile];
 #pragma unroll
       for (int k = 0; k < kTile; ++k) {
@@ -223,18 +237,23 @@ __global__ void __launch_bounds__(32) scan_bwd_kernel(const cm_scan_bwd_args p) 
           const float dt = softplus ? softplus_fwd<sizeof(T) == 4>(xx[k]) : xx[k];
           dtv[k] = dt;
           const float du_ = dt * uu[k];
-          float Bv[NS];
+          const float2 dt2 = make_float2(dt, dt), du2 = make_float2(du_, du_);
+          float2 B2[NP];
           if (BC_CONST) {
 #pragma unroll
-            for (int i = 0; i < NS; ++i) Bv[i] = Bc[i];
+            for (int i = 0; i < NP; ++i) B2[i] = make_float2(Bc[2 * i], Bc[2 * i + 1]);
           } else {
-            load_row<NS>(&sm.bc[k][sg * NS], Bv);
+            load_row2<NP>(&sm.bc[k][sg * NS], B2);
           }
 #pragma unroll
-          for (int i = 0; i < NS; ++i) h[i] = fmaf(ex2(dt * kA[i]), h[i], du_ * Bv[i]);
+          for (int i = 0; i < NP; ++i) {
+            const float2 x2 = fmul2(dt2, kA2[i]);
+            const float2 a2 = make_float2(ex2(x2.x), ex2(x2.y));
+            h2[i] = ffma2(a2, h2[i], fmul2(du2, B2[i]));
+          }
 #pragma unroll
           for (int i = 0; i < NS / 4; ++i)
-            sm.h[k][i][lane] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+            sm.h[k][i][lane] = make_float4(h2[2 * i].x, h2[2 * i].y, h2[2 * i + 1].x, h2[2 * i + 1].y);
         }
       }
 
@@ -245,33 +264,39 @@ __global__ void __launch_bounds__(32) scan_bwd_kernel(const cm_scan_bwd_args p) 
           const int64_t s = s0 + k;
           const float dt = dtv[k], u_ = uu[k], g = gg[k];
           const float du_ = dt * u_;
-          float hk[NS];
+          const float2 dt2 = make_float2(dt, dt), du2 = make_float2(du_, du_), g2 = make_float2(g, g);
+          const float2 ndu2 = make_float2(-du_, -du_);
+          float2 hk2[NP], B2[NP], C2[NP], dB2[NP], dC2[NP];
 #pragma unroll
           for (int i = 0; i < NS / 4; ++i) {
             const float4 v = sm.h[k][i][lane];
-            hk[4 * i] = v.x; hk[4 * i + 1] = v.y; hk[4 * i + 2] = v.z; hk[4 * i + 3] = v.w;
+            hk2[2 * i] = make_float2(v.x, v.y); hk2[2 * i + 1] = make_float2(v.z, v.w);
           }
-          float sLB = 0.f, sWA = 0.f;
-          float dBv[NS], dCv[NS], Bv[NS], Cv[NS];
           if (BC_CONST) {
 #pragma unroll
-            for (int i = 0; i < NS; ++i) { Bv[i] = Bc[i]; Cv[i] = Cc[i]; }
+            for (int i = 0; i < NP; ++i) {
+              B2[i] = make_float2(Bc[2 * i], Bc[2 * i + 1]);
+              C2[i] = make_float2(Cc[2 * i], Cc[2 * i + 1]);
+            }
           } else {
-            load_row<NS>(&sm.bc[k][sg * NS], Bv);
-            load_row<NS>(&sm.bc[k][16 + sg * NS], Cv);
+            load_row2<NP>(&sm.bc[k][sg * NS], B2);
+            load_row2<NP>(&sm.bc[k][16 + sg * NS], C2);
           }
+          float2 sLB2 = make_float2(0.f, 0.f), sWA2 = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int i = 0; i < NS; ++i) {
-            const float lam = fmaf(g, Cv[i], mu[i]);
-            dCv[i] = g * hk[i];
-            dBv[i] = lam * du_;
-            sLB = fmaf(lam, Bv[i], sLB);
-            const float hp = fmaf(-du_, Bv[i], hk[i]);   // = a * h_{s-1}
-            const float w = lam * hp;
-            sWA = fmaf(w, kA[i], sWA);
-            dA[i] = fmaf(w, dt, dA[i]);
-            mu[i] = ex2(dt * kA[i]) * lam;
+          for (int i = 0; i < NP; ++i) {
+            const float2 lam = ffma2(g2, C2[i], mu2[i]);          // lambda = g*C + mu
+            dC2[i] = fmul2(g2, hk2[i]);
+            dB2[i] = fmul2(lam, du2);
+            sLB2 = ffma2(lam, B2[i], sLB2);
+            const float2 hp = ffma2(ndu2, B2[i], hk2[i]);         // = a * h_{s-1}
+            const float2 w = fmul2(lam, hp);
+            sWA2 = ffma2(w, kA2[i], sWA2);
+            dA2[i] = ffma2(w, dt2, dA2[i]);
+            const float2 x2 = fmul2(dt2, kA2[i]);
+            mu2[i] = fmul2(make_float2(ex2(x2.x), ex2(x2.y)), lam);
           }
+          float sLB = sLB2.x + sLB2.y, sWA = sWA2.x + sWA2.y;
           if (LPC >= 2) {
             sLB += __shfl_xor_sync(0xffffffffu, sLB, 1);
             sWA += __shfl_xor_sync(0xffffffffu, sWA, 1);
@@ -291,17 +316,20 @@ __global__ void __launch_bounds__(32) scan_bwd_kernel(const cm_scan_bwd_args p) 
           }
           if (BC_CONST) {
 #pragma unroll
-            for (int i = 0; i < NS; ++i) { dBacc[i] += dBv[i]; dCacc[i] += dCv[i]; }
+            for (int i = 0; i < NP; ++i) {
+              dBacc[2 * i] += dB2[i].x; dBacc[2 * i + 1] += dB2[i].y;
+              dCacc[2 * i] += dC2[i].x; dCacc[2 * i + 1] += dC2[i].y;
+            }
           } else {
             // cross-channel reduce of the 32 per-step values
             __syncwarp();
             float4* dst = reinterpret_cast<float4*>(&sm.red[lane][0]);
+            const float keep = dvalid ? 1.f : 0.f;
 #pragma unroll
             for (int i = 0; i < NS / 4; ++i) {
-              dst[i] = dvalid ? make_float4(dBv[4 * i], dBv[4 * i + 1], dBv[4 * i + 2], dBv[4 * i + 3])
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
-              dst[NS / 4 + i] = dvalid ? make_float4(dCv[4 * i], dCv[4 * i + 1], dCv[4 * i + 2], dCv[4 * i + 3])
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+              dst[i] = make_float4(keep * dB2[2 * i].x, keep * dB2[2 * i].y, keep * dB2[2 * i + 1].x, keep * dB2[2 * i + 1].y);
+              dst[NS / 4 + i] =
+                  make_float4(keep * dC2[2 * i].x, keep * dC2[2 * i].y, keep * dC2[2 * i + 1].x, keep * dC2[2 * i + 1].y);
             }
             __syncwarp();
             const int n = lane & 15;
@@ -323,7 +351,7 @@ __global__ void __launch_bounds__(32) scan_bwd_kernel(const cm_scan_bwd_args p) 
   if (dvalid) {
     const int64_t row = (int64_t)b * p.dim + d;
 #pragma unroll
-    for (int i = 0; i < NS; ++i) bd.dA_part[row * 16 + sg * NS + i] = dA[i];
+    for (int i = 0; i < NS; ++i) bd.dA_part[row * 16 + sg * NS + i] = (i & 1) ? dA2[i / 2].y : dA2[i / 2].x;
     if (sg == 0) {
       if (bd.dD_part) bd.dD_part[row] = dD_acc;
       if (bd.dbias_part) bd.dbias_part[row] = dbias_acc;
@@ -384,7 +412,48 @@ __global__ void reduce_rows_kernel(const float* __restrict__ part, int64_t rows,
   out[c] = acc;
 }
 
+// Up to CM_REDUCE_MAX_JOBS column-sum jobs in one launch.  blockIdx.y = job; a CTA of 32 x 8 threads owns 32 columns,
+// its 8 warps stride over the rows and combine through shared memory in a fixed order (deterministic).
+struct ReduceJobs {
+  cm_reduce_job j[CM_REDUCE_MAX_JOBS];
+};
+__global__ void __launch_bounds__(256) reduce_multi_kernel(const ReduceJobs jobs) {
+  __shared__ float sm[8][33];
+  const cm_reduce_job& job = jobs.j[blockIdx.y];
+  const int64_t c = (int64_t)blockIdx.x * 32 + threadIdx.x;
+  if ((int64_t)blockIdx.x * 32 >= job.cols) return;      // CTA-uniform
+  float acc = 0.f;
+  if (c < job.cols) {
+    const float* src = job.part + c;
+    for (int64_t r = threadIdx.y; r < job.rows; r += 8) acc += __ldg(src + r * job.cols);
+  }
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < job.cols) {
+    float t = sm[0][threadIdx.x];
+#pragma unroll
+    for (int y = 1; y < 8; ++y) t += sm[y][threadIdx.x];
+    job.out[c] = t;
+  }
+}
+
 }  // namespace cm
+
+extern "C" int cm_reduce_multi(const cm_reduce_job* jobs, int32_t njobs, void* stream) {
+  if (jobs == nullptr || njobs <= 0 || njobs > CM_REDUCE_MAX_JOBS) return CM_ERR_BAD_ARG;
+  cm::ReduceJobs rj;
+  int64_t maxcols = 0;
+  for (int i = 0; i < njobs; ++i) {
+    if (!jobs[i].part || !jobs[i].out || jobs[i].rows <= 0 || jobs[i].cols <= 0) return CM_ERR_BAD_ARG;
+    rj.j[i] = jobs[i];
+    if (jobs[i].cols > maxcols) maxcols = jobs[i].cols;
+  }
+  for (int i = njobs; i < CM_REDUCE_MAX_JOBS; ++i) rj.j[i] = jobs[0];
+  const dim3 grid((unsigned)((maxcols + 31) / 32), njobs);
+  cm::reduce_multi_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(rj);
+  CM_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int cm_scan_bwd(const cm_scan_bwd_args* args, void* stream) {
   if (args == nullptr) return CM_ERR_BAD_ARG;

@@ -48,6 +48,20 @@ def _call(name, fn, *args):
     _TIMING.setdefault(name, []).append((s, e))
 
 
+def reduce_many(jobs):
+    """cm_reduce_multi: jobs = [(part (rows, cols) fp32 contiguous, out (cols,) fp32)], batched 8 per launch."""
+    lib = cabi.lib()
+    st = cabi.stream_ptr()
+    for i in range(0, len(jobs), cabi.CM_REDUCE_MAX_JOBS):
+        chunk = jobs[i:i + cabi.CM_REDUCE_MAX_JOBS]
+        arr = (cabi.ReduceJob * len(chunk))()
+        for k, (part, out) in enumerate(chunk):
+            rows = part.shape[0]
+            arr[k].part, arr[k].out = part.data_ptr(), out.data_ptr()
+            arr[k].rows, arr[k].cols = rows, part.numel() // rows
+        _call("cm_reduce_multi", lib.cm_reduce_multi, arr, len(chunk), st)
+
+
 def _require_cuda(t, name):
     if not t.is_cuda:
         raise RuntimeError("mamba_asr_b200: %s must be a CUDA tensor - the B200 kernels have no CPU fallback" % name)
@@ -236,26 +250,31 @@ def scan_backward(dirs, ckpts, dout, z=None, out_pre=None, out_scale=1.0, delta_
     st = cabi.stream_ptr()
     _call("cm_scan_bwd", lib.cm_scan_bwd, C.byref(a), st)
 
+    jobs = []
+    outs = []
     for r, d in enumerate(dirs):
         bc_part, dA_part, dD_part, db_part = parts[r]
         dA = torch.empty((D, 16), dtype=torch.float32, device=dev)
-        _call("cm_reduce_rows", lib.cm_reduce_rows, dA_part.data_ptr(), Bt, D * 16, dA.data_ptr(), st)
-        res["dA"].append(dA[:, :N])
+        jobs.append((dA_part, dA))
+        dD = db = dBC = None
         if dD_part is not None:
             dD = torch.empty((D,), dtype=torch.float32, device=dev)
-            _call("cm_reduce_rows", lib.cm_reduce_rows, dD_part.data_ptr(), Bt, D, dD.data_ptr(), st)
-            res["dD"].append(dD)
-        else:
-            res["dD"].append(None)
+            jobs.append((dD_part, dD))
         if db_part is not None:
             db = torch.empty((D,), dtype=torch.float32, device=dev)
-            _call("cm_reduce_rows", lib.cm_reduce_rows, db_part.data_ptr(), Bt, D, db.data_ptr(), st)
-            res["dbias"].append(db)
-        else:
-            res["dbias"].append(None)
+            jobs.append((db_part, db))
         if const_bc:
             dBC = torch.empty((D, 32), dtype=torch.float32, device=dev)
-            _call("cm_reduce_rows", lib.cm_reduce_rows, bc_part.data_ptr(), Bt, D * 32, dBC.data_ptr(), st)
+            jobs.append((bc_part, dBC))
+        outs.append((dA, dD, db, dBC))
+    reduce_many(jobs)
+    for r, d in enumerate(dirs):
+        bc_part = parts[r][0]
+        dA, dD, db, dBC = outs[r]
+        res["dA"].append(dA[:, :N])
+        res["dD"].append(dD)
+        res["dbias"].append(db)
+        if const_bc:
             res["dB"].append(dBC[:, :N].to(d["B"].dtype))
             res["dC"].append(dBC[:, 16:16 + N].to(d["C"].dtype))
         else:
@@ -345,17 +364,18 @@ def conv_backward(x, dirs, douts, silu=True, dx_out=None):
         parts.append((wp, bp))
     st = cabi.stream_ptr()
     _call("cm_conv_bwd", lib.cm_conv_bwd, C.byref(a), st)
-    dws, dbs = [], []
+    dws, dbs, jobs = [], [], []
     for wp, bp in parts:
         dw = torch.empty((D, W), dtype=torch.float32, device=dev)
-        _call("cm_reduce_rows", lib.cm_reduce_rows, wp.data_ptr(), npart, D * W, dw.data_ptr(), st)
+        jobs.append((wp, dw))
         dws.append(dw)
         if bp is not None:
             db = torch.empty((D,), dtype=torch.float32, device=dev)
-            _call("cm_reduce_rows", lib.cm_reduce_rows, bp.data_ptr(), npart, D, db.data_ptr(), st)
+            jobs.append((bp, db))
             dbs.append(db)
         else:
             dbs.append(None)
+    reduce_many(jobs)
     return dx, dws, dbs
 
 

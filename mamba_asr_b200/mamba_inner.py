@@ -20,6 +20,20 @@ import torch
 from . import kernels as K
 
 
+def _aligned_proj_weights(x_proj_w, dt_proj_w, R, N, act):
+    """x_proj rows reordered to [B (N) | C (N) | dt (R) | zero pad] and dt_proj's K padded with zero columns so that
+    both GEMMs have 8-element-aligned leading dimensions (tensor-core kernels instead of the align1 fallbacks at
+    R = 9) and every B/C row of x_dbl starts on a 16-byte boundary.  The pad columns of x_dbl are exact zeros."""
+    Rp = (R + 7) // 8 * 8
+    xw = x_proj_w.to(act)
+    dw = dt_proj_w.to(act)
+    parts = [xw[R:R + 2 * N], xw[:R]]
+    if Rp != R:
+        parts.append(xw.new_zeros((Rp - R, xw.shape[1])))
+        dw = torch.cat([dw, dw.new_zeros((dw.shape[0], Rp - R))], dim=1)
+    return torch.cat(parts, dim=0), dw
+
+
 def _as_bdl(t_bld):
     """(B, L, D) memory -> logical (B, D, L) view."""
     return t_bld.transpose(1, 2)
@@ -54,16 +68,16 @@ class MambaInnerCL(torch.autograd.Function):
             us = K.conv_forward(x, conv_dirs, silu=True)                     # logical (B, D, L), memory (B, L, D)
             scan_dirs, x_dbls, deltas, wx, wdt = [], [], [], [], []
             for r, p in enumerate(P):
-                xw = p[2].to(act)
-                dw = p[3].to(act)
-                R = dw.shape[1]
+                R = p[3].shape[1]
                 N = p[4].shape[1]
+                xw, dw = _aligned_proj_weights(p[2], p[3], R, N, act)        # rows [B | C | dt | 0-pad], K padded
+                Rp = dw.shape[1]
                 u_mem = us[r].transpose(1, 2)                                # (B, L, D) contiguous
-                x_dbl = torch.mm(u_mem.reshape(Bt * L, D), xw.t())           # (B*L, R+2N)
-                delta_mem = torch.mm(x_dbl[:, :R], dw.t()).view(Bt, L, D)    # (B, L, D)
+                x_dbl = torch.mm(u_mem.reshape(Bt * L, D), xw.t())           # (B*L, 2N + Rp), 16-byte-aligned rows
+                delta_mem = torch.mm(x_dbl[:, 2 * N:], dw.t()).view(Bt, L, D)
                 xv = x_dbl.view(Bt, L, -1)
                 scan_dirs.append(dict(u=us[r], delta=_as_bdl(delta_mem), A=p[4],
-                                      B=_as_bdl(xv[..., R:R + N]), C=_as_bdl(xv[..., R + N:R + 2 * N]),
+                                      B=_as_bdl(xv[..., :N]), C=_as_bdl(xv[..., N:2 * N]),
                                       D=p[5], delta_bias=p[6], reverse=rev[r]))
                 x_dbls.append(x_dbl)
                 deltas.append(delta_mem)
@@ -101,29 +115,30 @@ class MambaInnerCL(torch.autograd.Function):
             dxz = torch.empty_like(xz)
             scan_dirs, dx_dbls, dbc_like = [], [], []
             for r, p in enumerate(P):
-                R = wdt[r].shape[1]
                 N = p[4].shape[1]
                 xv = x_dbls[r].view(Bt, L, -1)
                 scan_dirs.append(dict(u=us[r], delta=_as_bdl(deltas[r]), A=p[4],
-                                      B=_as_bdl(xv[..., R:R + N]), C=_as_bdl(xv[..., R + N:R + 2 * N]),
+                                      B=_as_bdl(xv[..., :N]), C=_as_bdl(xv[..., N:2 * N]),
                                       D=p[5], delta_bias=p[6], reverse=rev[r]))
                 dxd = torch.empty_like(x_dbls[r])
                 dv = dxd.view(Bt, L, -1)
-                dbc_like.append((_as_bdl(dv[..., R:R + N]), _as_bdl(dv[..., R + N:R + 2 * N])))
+                dbc_like.append((_as_bdl(dv[..., :N]), _as_bdl(dv[..., N:2 * N])))
                 dx_dbls.append(dxd)
             g = K.scan_backward(scan_dirs, ckpts, _as_bdl(dy), z=z, out_pre=out_pre, out_scale=ctx.out_scale,
                                 delta_softplus=True, dz_out=_as_bdl(dxz[..., D:]), dBC_like=dbc_like)
             grads = []
             conv_dirs, conv_douts = [], []
             for r, p in enumerate(P):
-                R = wdt[r].shape[1]
+                R = p[3].shape[1]
+                N = p[4].shape[1]
                 u_mem = us[r].transpose(1, 2).reshape(Bt * L, D)
                 ddelta = g["ddelta"][r].transpose(1, 2).reshape(Bt * L, D)
                 du = g["du"][r].transpose(1, 2).reshape(Bt * L, D)
                 dxd = dx_dbls[r]
-                d_dtw = torch.mm(ddelta.t(), x_dbls[r][:, :R])                       # (D, R)
-                dxd[:, :R] = torch.mm(ddelta, wdt[r])                                # (B*L, R)
-                d_xw = torch.mm(dxd.t(), u_mem)                                      # (R+2N, D)
+                d_dtw = torch.mm(ddelta.t(), x_dbls[r][:, 2 * N:])[:, :R]            # (D, R)
+                dxd[:, 2 * N:] = torch.mm(ddelta, wdt[r])                            # (B*L, Rp); pad columns get 0
+                d_xw_perm = torch.mm(dxd.t(), u_mem)                                 # (2N + Rp, D)
+                d_xw = torch.cat([d_xw_perm[2 * N:2 * N + R], d_xw_perm[:2 * N]], dim=0)   # back to [dt | B | C] rows
                 du.addmm_(dxd, wx[r])                                                # + x_proj back-prop (:282)
                 conv_dirs.append(dict(weight=p[0][:, 0, :], bias=p[1], anticausal=rev[r]))
                 conv_douts.append(g["du"][r])

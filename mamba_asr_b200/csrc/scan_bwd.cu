@@ -17,6 +17,8 @@
 // cm_reduce_dbc() sums over slabs in a fixed order: deterministic, no atomics.
 // dA, dD, d(delta_bias) are per-row register sums written once per (batch, channel) and reduced over batch
 // by cm_reduce_rows().
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cm {
@@ -455,6 +457,10 @@ extern "C" int cm_reduce_multi(const cm_reduce_job* jobs, int32_t njobs, void* s
   return 0;
 }
 
+namespace cm {
+int scan_bwd_try_channel_last(const cm_scan_bwd_args& a, int lpc, cudaStream_t st, int* rc);   // scan_bwd_cl.cu
+}
+
 extern "C" int cm_scan_bwd(const cm_scan_bwd_args* args, void* stream) {
   if (args == nullptr) return CM_ERR_BAD_ARG;
   const cm_scan_bwd_args& a = *args;
@@ -477,6 +483,10 @@ extern "C" int cm_scan_bwd(const cm_scan_bwd_args* args, void* stream) {
   if (lpc != 1 && lpc != 2 && lpc != 4) return CM_ERR_BAD_ARG;
   const bool bcc = a.dir[0].in.bc_const != 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (getenv("CM_SCAN_GENERIC") == nullptr) {   // env switch only for A/B measurements of the two kernels
+    int rc = 0;
+    if (cm::scan_bwd_try_channel_last(a, lpc, st, &rc)) return rc;
+  }
   switch (a.dtype) {
     case CM_F32: return cm::launch_bwd_t<float>(a, lpc, bcc, st);
     case CM_BF16: return cm::launch_bwd_t<__nv_bfloat16>(a, lpc, bcc, st);

@@ -12,6 +12,9 @@
 // Generic kernels (any strides, e.g. the reference's time-contiguous (B, D, L)): lanes along time, halo re-reads
 // served by L1.  Weight/bias gradients are reduced in-CTA and written as per-(batch, 64-step chunk) partial rows
 // that cm_reduce_rows() sums in a fixed order (no atomics, deterministic).
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cm {
@@ -39,12 +42,18 @@ template <> __device__ __forceinline__ uint32_t float_to_bits<__half>(float f) {
   return __half_as_ushort(__float2half_rn(f));
 }
 
-// VEC adjacent elements <-> fp32 registers through one aligned load/store
+// VEC adjacent elements <-> fp32 registers through one aligned load/store.  ld_raw / cvt are split so that a kernel can
+// issue all of a tile's loads back to back and unpack afterwards (an unpack right behind each load serialises them).
 template <typename T, int VEC>
 struct VecIO {
   using Raw = typename RawVec<sizeof(T) * VEC>::type;
-  static __device__ __forceinline__ void ld(const T* p, float (&o)[VEC]) {
-    const Raw r = __ldg(reinterpret_cast<const Raw*>(p));
+  static __device__ __forceinline__ Raw ld_raw(const T* p) { return __ldg(reinterpret_cast<const Raw*>(p)); }
+  static __device__ __forceinline__ Raw zero() {
+    Raw r;
+    memset(&r, 0, sizeof(Raw));
+    return r;
+  }
+  static __device__ __forceinline__ void cvt(const Raw& r, float (&o)[VEC]) {
     if constexpr (sizeof(T) == 4) {
       const float* f = reinterpret_cast<const float*>(&r);
 #pragma unroll
@@ -55,6 +64,7 @@ struct VecIO {
       for (int i = 0; i < VEC; ++i) o[i] = bits_to_float<T>(h[i]);
     }
   }
+  static __device__ __forceinline__ void ld(const T* p, float (&o)[VEC]) { cvt(ld_raw(p), o); }
   static __device__ __forceinline__ void st(T* p, const float (&v)[VEC]) {
     Raw r;
     if constexpr (sizeof(T) == 4) {
@@ -70,9 +80,12 @@ struct VecIO {
   }
 };
 
-__device__ __forceinline__ float silu_f(float s) { return s * sigmoidf_fast(s); }
+// PRECISE (fp32 I/O): ex2 + rcp sigmoid; 16-bit I/O: one MUFU.TANH (error far below the output rounding)
+template <bool PRECISE>
+__device__ __forceinline__ float silu_f(float s) { return s * sigmoid_sel<PRECISE>(s); }
+template <bool PRECISE>
 __device__ __forceinline__ float silu_grad(float s) {
-  const float sig = sigmoidf_fast(s);
+  const float sig = sigmoid_sel<PRECISE>(s);
   return sig * fmaf(s, 1.f - sig, 1.f);
 }
 
@@ -105,18 +118,17 @@ __global__ void __launch_bounds__(32 * kTY) conv_fwd_cl_kernel(const cm_conv_arg
   const int b = blockIdx.z;
   const bool silu = (p.flags & CM_FLAG_SILU) != 0;
 
-  float xw[kTL + 6][VEC];
+  using VIO = VecIO<T, VEC>;
+  typename VIO::Raw xr[kTL + 6];
   const T* xp = static_cast<const T*>(p.x.ptr) + b * p.x.sb + d0;
 #pragma unroll
-  for (int i = 0; i < kTL + 6; ++i) {
+  for (int i = 0; i < kTL + 6; ++i) {          // all 22 row loads in flight before the first unpack
     const int l = l0 - 3 + i;
-    if (l >= 0 && l < L) {
-      VecIO<T, VEC>::ld(xp + (int64_t)l * p.x.sl, xw[i]);
-    } else {
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) xw[i][v] = 0.f;
-    }
+    xr[i] = (l >= 0 && l < L) ? VIO::ld_raw(xp + (int64_t)l * p.x.sl) : VIO::zero();
   }
+  float xw[kTL + 6][VEC];
+#pragma unroll
+  for (int i = 0; i < kTL + 6; ++i) VIO::cvt(xr[i], xw[i]);
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     if (r < p.ndir) {
@@ -135,7 +147,7 @@ __global__ void __launch_bounds__(32 * kTY) conv_fwd_cl_kernel(const cm_conv_arg
             float acc = tp.b[v];
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc = fmaf(tp.w[v][j], anti ? xw[i + 6 - j][v] : xw[i + j][v], acc);
-            o[v] = silu ? silu_f(acc) : acc;
+            o[v] = silu ? silu_f<sizeof(T) == 4>(acc) : acc;
           }
           VecIO<T, VEC>::st(op + (int64_t)l * dr.out.sl, o);
         }
@@ -158,30 +170,41 @@ __global__ void __launch_bounds__(32 * kTY) conv_bwd_cl_kernel(const cm_conv_arg
   const bool silu = (p.flags & CM_FLAG_SILU) != 0;
   const int dsafe = (d0 < p.dim) ? d0 : 0;
 
-  float xw[kTL + 6][VEC];
-  float dxa[kTL][VEC];
+  using VIO = VecIO<T, VEC>;
+  // every global load of the thread is issued first: x window (22 rows) and both upstream-gradient windows (19 rows)
+  typename VIO::Raw xr[kTL + 6], gr[2][kTL + 6];
 #pragma unroll
-  for (int i = 0; i < kTL; ++i)
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) dxa[i][v] = 0.f;
+  for (int i = 0; i < kTL + 6; ++i) { xr[i] = VIO::zero(); gr[0][i] = VIO::zero(); gr[1][i] = VIO::zero(); }
   if (active) {
     const T* xp = static_cast<const T*>(p.x.ptr) + b * p.x.sb + d0;
 #pragma unroll
     for (int i = 0; i < kTL + 6; ++i) {
       const int l = l0 - 3 + i;
-      if (l >= 0 && l < L) {
-        VecIO<T, VEC>::ld(xp + (int64_t)l * p.x.sl, xw[i]);
-      } else {
+      if (l >= 0 && l < L) xr[i] = VIO::ld_raw(xp + (int64_t)l * p.x.sl);
+    }
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) xw[i][v] = 0.f;
+    for (int r = 0; r < 2; ++r) {
+      if (r < p.ndir) {
+        const cm_conv_dir& dr = p.dir[r];
+        const bool anti = dr.anticausal != 0;
+        const T* gp = static_cast<const T*>(dr.out.ptr) + b * dr.out.sb + d0;
+#pragma unroll
+        for (int q = 0; q < kTL + 6; ++q) {
+          const bool need = anti ? (q < kTL + 3) : (q >= 3);
+          const int lq = l0 - 3 + q;
+          if (need && lq >= 0 && lq < L) gr[r][q] = VIO::ld_raw(gp + (int64_t)lq * dr.out.sl);
+        }
       }
     }
-  } else {
-#pragma unroll
-    for (int i = 0; i < kTL + 6; ++i)
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) xw[i][v] = 0.f;
   }
+  float xw[kTL + 6][VEC];
+  float dxa[kTL][VEC];
+#pragma unroll
+  for (int i = 0; i < kTL + 6; ++i) VIO::cvt(xr[i], xw[i]);
+#pragma unroll
+  for (int i = 0; i < kTL; ++i)
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) dxa[i][v] = 0.f;
 
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -198,7 +221,6 @@ __global__ void __launch_bounds__(32 * kTY) conv_bwd_cl_kernel(const cm_conv_arg
         for (int j = 0; j < 4; ++j) dw[v][j] = 0.f;
       }
       if (active) {
-        const T* gp = static_cast<const T*>(dr.out.ptr) + b * dr.out.sb + d0;
         // positions lq = l0 - 3 + q whose upstream gradient reaches this thread's dx rows:
         //   causal:     l' in [l0, l0 + TL + 3)   -> q in [3, TL + 6)
         //   anticausal: l' in [l0 - 3, l0 + TL)   -> q in [0, TL + 3)
@@ -208,7 +230,7 @@ __global__ void __launch_bounds__(32 * kTY) conv_bwd_cl_kernel(const cm_conv_arg
           const int lq = l0 - 3 + q;
           if (need && lq >= 0 && lq < L) {
             float go[VEC];
-            VecIO<T, VEC>::ld(gp + (int64_t)lq * dr.out.sl, go);
+            VIO::cvt(gr[r][q], go);
             const bool own = (q >= 3) && (q < kTL + 3);   // lq in [l0, l0 + TL)
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
@@ -222,7 +244,7 @@ __global__ void __launch_bounds__(32 * kTY) conv_bwd_cl_kernel(const cm_conv_arg
                   const float xv = (xi >= 0 && xi < kTL + 6) ? xw[xi][v] : 0.f;
                   s = fmaf(tp.w[v][j], xv, s);
                 }
-                g *= silu_grad(s);
+                g *= silu_grad<sizeof(T) == 4>(s);
               }
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -306,7 +328,7 @@ __global__ void __launch_bounds__(128) conv_fwd_generic_kernel(const cm_conv_arg
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc = fmaf(tp.w[0][j], dr.anticausal ? xv[6 - j] : xv[j], acc);
     Elem<T>::st(static_cast<T*>(dr.out.ptr) + b * dr.out.sb + d * dr.out.sd + (int64_t)l * dr.out.sl,
-                silu ? silu_f(acc) : acc);
+                silu ? silu_f<sizeof(T) == 4>(acc) : acc);
   }
 }
 
@@ -344,7 +366,7 @@ __global__ void __launch_bounds__(kChunk) conv_bwd_generic_kernel(const cm_conv_
               const int off = anti ? (o + 3 - j) : (o - 3 + j);   // input time relative to l
               s = fmaf(tp.w[0][j], xv[6 + off], s);
             }
-            g *= silu_grad(s);
+            g *= silu_grad<sizeof(T) == 4>(s);
           }
           dx = fmaf(tp.w[0][3 - oo], g, dx);
           if (oo == 0) {   // own position: weight / bias gradients
@@ -399,7 +421,7 @@ __global__ void conv_update_kernel(const T* __restrict__ x, T* __restrict__ stat
     Elem<T>::st(st + k, v);
     acc = fmaf(__ldg(w + (int64_t)d * W + k), v, acc);
   }
-  Elem<T>::st(out + idx, (flags & CM_FLAG_SILU) ? silu_f(acc) : acc);
+  Elem<T>::st(out + idx, (flags & CM_FLAG_SILU) ? silu_f<sizeof(T) == 4>(acc) : acc);
 }
 
 // ---- host dispatch ---------------------------------------------------------------------------------
@@ -412,7 +434,8 @@ static int pick_vec(const cm_conv_args& a, bool bwd) {
   if (bwd && a.dx.sd != 1) return 0;
   for (int r = 0; r < a.ndir; ++r)
     if (a.dir[r].out.sd != 1) return 0;
-  const int maxv = bwd ? 2 : 4;
+  int maxv = 2;   // measured on B200: 2 channels per thread (88 registers, 5+ CTAs/SM) beats 4 (154 registers)
+  if (const char* e = getenv("CM_CONV_VEC")) maxv = std::max(1, std::min(maxv, atoi(e)));   // tuning experiments
   for (int vec = maxv; vec >= 1; vec >>= 1) {
     const size_t bytes = sizeof(T) * vec;
     if (bytes > 16) continue;

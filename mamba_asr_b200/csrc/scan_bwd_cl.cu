@@ -132,9 +132,9 @@ __global__ void __launch_bounds__(32) scan_bwd_cl_kernel(const __grid_constant__
   T* dzp = do_dz ? static_cast<T*>(p.dz.ptr) + b * p.dz.sb + d * p.dz.sd + l0 * p.dz.sl : nullptr;
   T* dup = static_cast<T*>(bd.du.ptr) + b * bd.du.sb + d * bd.du.sd + l0 * bd.du.sl;
   T* ddp = static_cast<T*>(bd.ddelta.ptr) + b * bd.ddelta.sb + d * bd.ddelta.sd + l0 * bd.ddelta.sl;
-  const int64_t sdz = sgn * p.dz.sl, sdu = sgn * bd.du.sl, sdd = sgn * bd.ddelta.sl;
+  const int sdz = (int)(sgn * p.dz.sl), sdu = (int)(sgn * bd.du.sl), sdd = (int)(sgn * bd.ddelta.sl);
   float* partp = bd.dBC_part + ((int64_t)b * gridDim.x + slab) * (int64_t)L * 32 + l0 * 32;
-  const int64_t spart = sgn * 32;
+  const int spart = (int)sgn * 32;
 
   const int s1 = cm_first_range(L, p.ndir, dp.reverse);
   // flat tile index over both ranges, walked from the last tile to the first
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(32) scan_bwd_cl_kernel(const __grid_constant__
           const float sig = sigmoidf_fast(zz);
           gg[k] = dov * zz * sig;
           if (do_dz && sg == 0)
-            Elem<T>::st(dzp + (int64_t)(s0 + k) * sdz, dov * ldsf<T>(S.pre[k][cl]) * sig * fmaf(zz, 1.f - sig, 1.f));
+            Elem<T>::st(dzp + (int64_t)(s0 + k) * (int64_t)sdz, dov * ldsf<T>(S.pre[k][cl]) * sig * fmaf(zz, 1.f - sig, 1.f));
         } else {
           gg[k] = dov;
         }
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(32) scan_bwd_cl_kernel(const __grid_constant__
 #pragma unroll
     for (int k = kTileC - 1; k >= 0; --k) {
       if (k < nvalid) {
-        const int64_t s = s0 + k;
+        const int s = s0 + k;
         const float dt = dtv[k], u_ = uu[k], g = gg[k];
         const float du_ = dt * u_;
         const float2 dt2 = make_float2(dt, dt), du2 = make_float2(du_, du_), g2 = make_float2(g, g);
@@ -304,8 +304,8 @@ __global__ void __launch_bounds__(32) scan_bwd_cl_kernel(const __grid_constant__
         dD_acc = fmaf(g, u_, dD_acc);
         dbias_acc += ddl;
         if (sg == 0) {
-          Elem<T>::st(dup + s * sdu, du);
-          Elem<T>::st(ddp + s * sdd, ddl);
+          Elem<T>::st(dup + (int64_t)s * sdu, du);
+          Elem<T>::st(ddp + (int64_t)s * sdd, ddl);
         }
         // cross-channel reduce of the 32 per-step values
         __syncwarp();
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(32) scan_bwd_cl_kernel(const __grid_constant__
           acc0 += sm.red[c * LPC + row0][col];
           acc1 += sm.red[(c + 1) * LPC + row0][col];
         }
-        partp[s * spart + lane] = acc0 + acc1;
+        partp[(int64_t)s * spart + lane] = acc0 + acc1;
       }
     }
     __syncwarp();   // all lanes done with this stage before it is refilled two tiles later

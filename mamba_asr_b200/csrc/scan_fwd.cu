@@ -18,6 +18,8 @@
 //
 // Every CM_SCAN_CKPT_STEPS processed steps the warp saves its fp32 state (64 B per lane, contiguous) so the
 // backward kernel can recompute states tile by tile without dividing by the decay.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cm {
@@ -386,6 +388,10 @@ static int check_dir(const cm_scan_dir& d) {
   return 0;
 }
 
+namespace cm {
+int scan_fwd_try_channel_last(const cm_scan_fwd_args& a, int lpc, cudaStream_t st, int* rc);   // scan_fwd_cl.cu
+}
+
 extern "C" int cm_scan_fwd(const cm_scan_fwd_args* args, void* stream) {
   if (args == nullptr) return CM_ERR_BAD_ARG;
   const cm_scan_fwd_args& a = *args;
@@ -405,6 +411,10 @@ extern "C" int cm_scan_fwd(const cm_scan_fwd_args* args, void* stream) {
   if (lpc != 1 && lpc != 2 && lpc != 4) return CM_ERR_BAD_ARG;
   const bool bcc = a.dir[0].bc_const != 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (getenv("CM_SCAN_GENERIC") == nullptr) {   // env switch only for A/B measurements of the two kernels
+    int rc = 0;
+    if (cm::scan_fwd_try_channel_last(a, lpc, st, &rc)) return rc;
+  }
   switch (a.dtype) {
     case CM_F32: return cm::launch_fwd_t<float>(a, lpc, bcc, st);
     case CM_BF16: return cm::launch_fwd_t<__nv_bfloat16>(a, lpc, bcc, st);

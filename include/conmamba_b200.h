@@ -104,6 +104,8 @@ int cm_scan_num_ckpt(int32_t seqlen, int32_t ndir);
 int cm_scan_slab_channels(int32_t lanes_per_channel);
 /* the lanes_per_channel the library would pick for this problem when the caller passes 0 */
 int cm_scan_pick_lanes(int32_t batch, int32_t dim, int32_t ndir);
+/* the same for cm_scan_bwd (its register / shared-memory footprint favours 2 lanes per channel) */
+int cm_scan_pick_lanes_bwd(int32_t batch, int32_t dim, int32_t ndir);
 
 int cm_scan_fwd(const cm_scan_fwd_args* args, void* stream);
 

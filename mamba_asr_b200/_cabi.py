@@ -20,7 +20,8 @@ CM_SCAN_CKPT_STEPS = 8
 CM_ABI_VERSION = 1
 
 EXPORTS = (
-    "cm_version", "cm_scan_num_ckpt", "cm_scan_slab_channels", "cm_scan_pick_lanes", "cm_scan_fwd", "cm_scan_bwd",
+    "cm_version", "cm_scan_num_ckpt", "cm_scan_slab_channels", "cm_scan_pick_lanes", "cm_scan_pick_lanes_bwd", "cm_scan_fwd",
+    "cm_scan_bwd",
     "cm_reduce_dbc", "cm_reduce_rows", "cm_conv_fwd", "cm_conv_num_part", "cm_conv_bwd", "cm_conv_update",
     "cm_fbank_logmel", "cm_fbank_floor", "cm_abi_sizeof", "cm_reduce_multi",
 )
@@ -121,6 +122,7 @@ def lib():
         L.cm_scan_num_ckpt.argtypes = [C.c_int32, C.c_int32]
         L.cm_scan_slab_channels.argtypes = [C.c_int32]
         L.cm_scan_pick_lanes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+        L.cm_scan_pick_lanes_bwd.argtypes = [C.c_int32, C.c_int32, C.c_int32]
         L.cm_scan_fwd.argtypes = [C.POINTER(ScanFwdArgs), C.c_void_p]
         L.cm_scan_bwd.argtypes = [C.POINTER(ScanBwdArgs), C.c_void_p]
         L.cm_reduce_dbc.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, Tensor3, Tensor3,

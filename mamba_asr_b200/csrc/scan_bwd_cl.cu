@@ -9,6 +9,8 @@
 //
 // Shared memory per warp (bf16, LPC = 1): 2 stages x (5 x 512 B activations + 512 B B|C rows + 2 KB checkpoint)
 // + 16 KB recomputed states + 1.1 KB fp32 B/C rows + 4.5 KB reduce scratch = 32 KB.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace cm {
@@ -75,8 +77,13 @@ __device__ __forceinline__ float ldsf<__nv_bfloat16>(const __nv_bfloat16& v) { r
 template <>
 __device__ __forceinline__ float ldsf<__half>(const __half& v) { return __half2float(v); }
 
+#ifdef CM_BWD_CAP
+#define CM_BWD_LB __launch_bounds__(32, (LPC == 1 ? 7 : (LPC == 2 ? 12 : 16)))
+#else
+#define CM_BWD_LB __launch_bounds__(32)
+#endif
 template <typename T, int LPC>
-__global__ void __launch_bounds__(32) scan_bwd_cl_kernel(const __grid_constant__ cm_scan_bwd_args p) {
+__global__ void CM_BWD_LB scan_bwd_cl_kernel(const __grid_constant__ cm_scan_bwd_args p) {
   constexpr int NS = 16 / LPC, CPW = 32 / LPC, NP = NS / 2;
   constexpr int ES = (int)sizeof(T);
   constexpr int ROWB = CPW * ES;          // bytes of one staged activation row
@@ -135,6 +142,12 @@ __global__ void __launch_bounds__(32) scan_bwd_cl_kernel(const __grid_constant__
   const int sdz = (int)(sgn * p.dz.sl), sdu = (int)(sgn * bd.du.sl), sdd = (int)(sgn * bd.ddelta.sl);
   float* partp = bd.dBC_part + ((int64_t)b * gridDim.x + slab) * (int64_t)L * 32 + l0 * 32;
   const int spart = (int)sgn * 32;
+
+  // Pin the per-step scalars in registers (ptxas otherwise re-derives them from the parameter block per step).
+  float scale_r = scale, Dsk_r = Dsk, bias_r = bias;
+  int sdz_r = sdz, sdu_r = sdu, sdd_r = sdd, spart_r = spart;
+  asm volatile("" : "+l"(dzp), "+l"(dup), "+l"(ddp), "+l"(partp), "+r"(sdz_r), "+r"(sdu_r), "+r"(sdd_r), "+r"(spart_r),
+               "+f"(scale_r), "+f"(Dsk_r), "+f"(bias_r));
 
   const int s1 = cm_first_range(L, p.ndir, dp.reverse);
   // flat tile index over both ranges, walked from the last tile to the first
@@ -197,130 +210,157 @@ __global__ void __launch_bounds__(32) scan_bwd_cl_kernel(const __grid_constant__
     __syncwarp();
     const typename Smem::Stage& S = sm.st[t & 1];
 
-    // fp32 B/C rows for the tile
-    {
+    auto tile_body = [&](auto full_tag) {
+      constexpr bool FULL = decltype(full_tag)::value;   // all 8 steps exist: no per-step predicates
+      // fp32 B/C rows for the tile
+      {
 #pragma unroll
-      for (int k = 0; k < kTileC; ++k) sm.bcf[k][lane] = (k < nvalid) ? ldsf<T>(S.bc[k][lane]) : 0.f;
-    }
-    // per-step scalars of this lane's channel
-    float uu[kTileC], xx[kTileC], gg[kTileC];
-#pragma unroll
-    for (int k = 0; k < kTileC; ++k) {
-      uu[k] = 0.f; xx[k] = 0.f; gg[k] = 0.f;
-      if (k < nvalid) {
-        uu[k] = ldsf<T>(S.u[k][cl]);
-        xx[k] = ldsf<T>(S.dl[k][cl]) + bias;
-        const float dov = ldsf<T>(S.go[k][cl]) * scale;
-        if (has_z) {
-          const float zz = ldsf<T>(S.z[k][cl]);
-          const float sig = sigmoidf_fast(zz);
-          gg[k] = dov * zz * sig;
-          if (do_dz && sg == 0)
-            Elem<T>::st(dzp + (int64_t)(s0 + k) * (int64_t)sdz, dov * ldsf<T>(S.pre[k][cl]) * sig * fmaf(zz, 1.f - sig, 1.f));
-        } else {
-          gg[k] = dov;
-        }
+        for (int k = 0; k < kTileC; ++k) sm.bcf[k][lane] = (FULL || k < nvalid) ? ldsf<T>(S.bc[k][lane]) : 0.f;
       }
-    }
-    float2 h2[NP];
-    lds_row2<NP>(&S.ck[cl][sg * NS], h2);
-    __syncwarp();   // bcf visible
-
-    // ---- phase 1: recompute the tile's states from its checkpoint ------------------------------------
-    float dtv[kTileC];
+      // per-step scalars of this lane's channel
+      float uu[kTileC], xx[kTileC], gg[kTileC];
 #pragma unroll
-    for (int k = 0; k < kTileC; ++k) {
-      dtv[k] = 0.f;
-      if (k < nvalid) {
-        const float dt = softplus ? softplus_fwd<sizeof(T) == 4>(xx[k]) : xx[k];
-        dtv[k] = dt;
-        const float du_ = dt * uu[k];
-        const float2 dt2 = make_float2(dt, dt), du2 = make_float2(du_, du_);
-        float2 B2[NP];
-        lds_row2<NP>(&sm.bcf[k][sg * NS], B2);
-#pragma unroll
-        for (int i = 0; i < NP; ++i) {
-          const float2 x2 = fmul2(dt2, kA2[i]);
-          const float2 a2 = make_float2(ex2(x2.x), ex2(x2.y));
-          h2[i] = ffma2(a2, h2[i], fmul2(du2, B2[i]));
-        }
-#pragma unroll
-        for (int i = 0; i < NS / 4; ++i)
-          sm.h[k][i][lane] = make_float4(h2[2 * i].x, h2[2 * i].y, h2[2 * i + 1].x, h2[2 * i + 1].y);
-      }
-    }
-
-    // ---- phase 2: reverse sweep ---------------------------------------------------------------------
-#pragma unroll
-    for (int k = kTileC - 1; k >= 0; --k) {
-      if (k < nvalid) {
-        const int s = s0 + k;
-        const float dt = dtv[k], u_ = uu[k], g = gg[k];
-        const float du_ = dt * u_;
-        const float2 dt2 = make_float2(dt, dt), du2 = make_float2(du_, du_), g2 = make_float2(g, g);
-        const float2 ndu2 = make_float2(-du_, -du_);
-        __syncwarp();   // previous step's readers of sm.red are done
-        float4* red = reinterpret_cast<float4*>(&sm.red[lane][0]);
-        float2 sLB2 = make_float2(0.f, 0.f), sWA2 = make_float2(0.f, 0.f);
-        // four states (two fp32 pairs) at a time: operands come in as LDS.128, dB / dC leave as STS.128
-#pragma unroll
-        for (int q = 0; q < NS / 4; ++q) {
-          const float4 hv = sm.h[k][q][lane];
-          const float4 bv = *reinterpret_cast<const float4*>(&sm.bcf[k][sg * NS + 4 * q]);
-          const float4 cv = *reinterpret_cast<const float4*>(&sm.bcf[k][16 + sg * NS + 4 * q]);
-          float2 dBq[2], dCq[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int i = 2 * q + e;
-            const float2 hk = e ? make_float2(hv.z, hv.w) : make_float2(hv.x, hv.y);
-            const float2 Bq = e ? make_float2(bv.z, bv.w) : make_float2(bv.x, bv.y);
-            const float2 Cq = e ? make_float2(cv.z, cv.w) : make_float2(cv.x, cv.y);
-            const float2 lam = ffma2(g2, Cq, mu2[i]);           // lambda = g*C + mu
-            dCq[e] = fmul2(g2, hk);
-            dBq[e] = fmul2(lam, du2);
-            sLB2 = ffma2(lam, Bq, sLB2);
-            const float2 hp = ffma2(ndu2, Bq, hk);              // = a * h_{s-1}
-            const float2 w = fmul2(lam, hp);
-            sWA2 = ffma2(w, kA2[i], sWA2);
-            dA2[i] = ffma2(w, dt2, dA2[i]);
-            const float2 x2 = fmul2(dt2, kA2[i]);
-            mu2[i] = fmul2(make_float2(ex2(x2.x), ex2(x2.y)), lam);
+      for (int k = 0; k < kTileC; ++k) {
+        uu[k] = 0.f; xx[k] = 0.f; gg[k] = 0.f;
+        if (FULL || k < nvalid) {
+          uu[k] = ldsf<T>(S.u[k][cl]);
+          xx[k] = ldsf<T>(S.dl[k][cl]) + bias_r;
+          const float dov = ldsf<T>(S.go[k][cl]) * scale_r;
+          if (has_z) {
+            const float zz = ldsf<T>(S.z[k][cl]);
+            const float sig = sigmoidf_fast(zz);
+            gg[k] = dov * zz * sig;
+            if (do_dz && sg == 0)
+              Elem<T>::st(dzp + (int64_t)(s0 + k) * sdz_r, dov * ldsf<T>(S.pre[k][cl]) * sig * fmaf(zz, 1.f - sig, 1.f));
+          } else {
+            gg[k] = dov;
           }
-          red[q] = make_float4(dBq[0].x, dBq[0].y, dBq[1].x, dBq[1].y);
-          red[NS / 4 + q] = make_float4(dCq[0].x, dCq[0].y, dCq[1].x, dCq[1].y);
         }
-        float sLB = sLB2.x + sLB2.y, sWA = sWA2.x + sWA2.y;
-        if (LPC >= 2) {
-          sLB += __shfl_xor_sync(0xffffffffu, sLB, 1);
-          sWA += __shfl_xor_sync(0xffffffffu, sWA, 1);
-        }
-        if (LPC >= 4) {
-          sLB += __shfl_xor_sync(0xffffffffu, sLB, 2);
-          sWA += __shfl_xor_sync(0xffffffffu, sWA, 2);
-        }
-        const float du = fmaf(g, Dsk, dt * sLB);
-        const float ddt = fmaf(u_, sLB, kLn2 * sWA);
-        const float ddl = softplus ? ddt * softplus_grad(xx[k]) : ddt;
-        dD_acc = fmaf(g, u_, dD_acc);
-        dbias_acc += ddl;
-        if (sg == 0) {
-          Elem<T>::st(dup + (int64_t)s * sdu, du);
-          Elem<T>::st(ddp + (int64_t)s * sdd, ddl);
-        }
-        // cross-channel reduce of the 32 per-step values
-        __syncwarp();
-        const int n = lane & 15;
-        const int col = ((lane < 16) ? 0 : NS) + (n % NS);
-        const int row0 = n / NS;
-        float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-        for (int c = 0; c < CPW; c += 2) {
-          acc0 += sm.red[c * LPC + row0][col];
-          acc1 += sm.red[(c + 1) * LPC + row0][col];
-        }
-        partp[(int64_t)s * spart + lane] = acc0 + acc1;
       }
-    }
+      float2 h2[NP];
+      lds_row2<NP>(&S.ck[cl][sg * NS], h2);
+      __syncwarp();   // bcf visible
+
+      // ---- phase 1: recompute the tile's states from its checkpoint ------------------------------------
+      float dtv[kTileC];
+#pragma unroll
+      for (int k = 0; k < kTileC; ++k) {
+        dtv[k] = 0.f;
+        if (FULL || k < nvalid) {
+          const float dt = softplus ? softplus_fwd<sizeof(T) == 4>(xx[k]) : xx[k];
+          dtv[k] = dt;
+          const float du_ = dt * uu[k];
+          const float2 dt2 = make_float2(dt, dt), du2 = make_float2(du_, du_);
+          float2 B2[NP];
+          lds_row2<NP>(&sm.bcf[k][sg * NS], B2);
+#pragma unroll
+          for (int i = 0; i < NP; ++i) {
+            const float2 x2 = fmul2(dt2, kA2[i]);
+            const float2 a2 = make_float2(ex2(x2.x), ex2(x2.y));
+            h2[i] = ffma2(a2, h2[i], fmul2(du2, B2[i]));
+          }
+#pragma unroll
+          for (int i = 0; i < NS / 4; ++i)
+            sm.h[k][i][lane] = make_float4(h2[2 * i].x, h2[2 * i].y, h2[2 * i + 1].x, h2[2 * i + 1].y);
+        }
+      }
+
+      // ---- phase 2: reverse sweep ---------------------------------------------------------------------
+#pragma unroll
+      for (int k = kTileC - 1; k >= 0; --k) {
+        if (FULL || k < nvalid) {
+          const int s = s0 + k;
+          const float dt = dtv[k], u_ = uu[k], g = gg[k];
+          const float du_ = dt * u_;
+          const float2 dt2 = make_float2(dt, dt), du2 = make_float2(du_, du_), g2 = make_float2(g, g);
+          const float2 ndu2 = make_float2(-du_, -du_);
+          __syncwarp();   // previous step's readers of sm.red are done
+          float4* red = reinterpret_cast<float4*>(&sm.red[lane][0]);
+          float2 sLB2 = make_float2(0.f, 0.f), sWA2 = make_float2(0.f, 0.f);
+          // four states (two fp32 pairs) at a time: operands come in as LDS.128, dB / dC leave as STS.128
+#pragma unroll
+          for (int q = 0; q < NS / 4; ++q) {
+            const float4 hv = sm.h[k][q][lane];
+            const float4 bv = *reinterpret_cast<const float4*>(&sm.bcf[k][sg * NS + 4 * q]);
+            const float4 cv = *reinterpret_cast<const float4*>(&sm.bcf[k][16 + sg * NS + 4 * q]);
+            float2 dBq[2], dCq[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int i = 2 * q + e;
+              const float2 hk = e ? make_float2(hv.z, hv.w) : make_float2(hv.x, hv.y);
+              const float2 Bq = e ? make_float2(bv.z, bv.w) : make_float2(bv.x, bv.y);
+              const float2 Cq = e ? make_float2(cv.z, cv.w) : make_float2(cv.x, cv.y);
+              const float2 lam = ffma2(g2, Cq, mu2[i]);           // lambda = g*C + mu
+              dCq[e] = fmul2(g2, hk);
+              dBq[e] = fmul2(lam, du2);
+              sLB2 = ffma2(lam, Bq, sLB2);
+              const float2 hp = ffma2(ndu2, Bq, hk);              // = a * h_{s-1}
+              const float2 w = fmul2(lam, hp);
+              sWA2 = ffma2(w, kA2[i], sWA2);
+              dA2[i] = ffma2(w, dt2, dA2[i]);
+              const float2 x2 = fmul2(dt2, kA2[i]);
+              mu2[i] = fmul2(make_float2(ex2(x2.x), ex2(x2.y)), lam);
+            }
+            red[q] = make_float4(dBq[0].x, dBq[0].y, dBq[1].x, dBq[1].y);
+            red[NS / 4 + q] = make_float4(dCq[0].x, dCq[0].y, dCq[1].x, dCq[1].y);
+          }
+          float sLB = sLB2.x + sLB2.y, sWA = sWA2.x + sWA2.y;
+          if (LPC >= 2) {
+            sLB += __shfl_xor_sync(0xffffffffu, sLB, 1);
+            sWA += __shfl_xor_sync(0xffffffffu, sWA, 1);
+          }
+          if (LPC >= 4) {
+            sLB += __shfl_xor_sync(0xffffffffu, sLB, 2);
+            sWA += __shfl_xor_sync(0xffffffffu, sWA, 2);
+          }
+          const float du = fmaf(g, Dsk_r, dt * sLB);
+          const float ddt = fmaf(u_, sLB, kLn2 * sWA);
+          const float ddl = softplus ? ddt * softplus_grad(xx[k]) : ddt;
+          dD_acc = fmaf(g, u_, dD_acc);
+          dbias_acc += ddl;
+          if (sg == 0) {
+            Elem<T>::st(dup + (int64_t)s * sdu_r, du);
+            Elem<T>::st(ddp + (int64_t)s * sdd_r, ddl);
+          }
+          // cross-channel reduce of the 32 per-step values
+          __syncwarp();
+          if (LPC == 1) {
+            // lane -> (quad q = lane & 7 of the 32 values, row group rg = lane >> 3): 8 LDS.128 + packed adds, then two
+            // shuffle rounds fold the 4 row groups; lanes 0..7 store one coalesced 128-byte row
+            const int q = lane & 7, rg = lane >> 3;
+            float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 v = *reinterpret_cast<const float4*>(&sm.red[rg + 4 * i][4 * q]);
+              a0 = fadd2(a0, make_float2(v.x, v.y));
+              a1 = fadd2(a1, make_float2(v.z, v.w));
+            }
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+              a0.x += __shfl_xor_sync(0xffffffffu, a0.x, o); a0.y += __shfl_xor_sync(0xffffffffu, a0.y, o);
+              a1.x += __shfl_xor_sync(0xffffffffu, a1.x, o); a1.y += __shfl_xor_sync(0xffffffffu, a1.y, o);
+            }
+            if (lane < 8) *reinterpret_cast<float4*>(partp + (int64_t)s * spart_r + 4 * q) = make_float4(a0.x, a0.y, a1.x, a1.y);
+          } else {
+            const int n = lane & 15;
+            const int col = ((lane < 16) ? 0 : NS) + (n % NS);
+            const int row0 = n / NS;
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < CPW; c += 2) {
+              acc0 += sm.red[c * LPC + row0][col];
+              acc1 += sm.red[(c + 1) * LPC + row0][col];
+            }
+            partp[(int64_t)s * spart_r + lane] = acc0 + acc1;
+          }
+        }
+      }
+    };
+#ifdef CM_BWD_FULLSPLIT
+    if (nvalid == kTileC) tile_body(std::true_type{}); else tile_body(std::false_type{});
+#else
+    tile_body(std::false_type{});
+#endif
     __syncwarp();   // all lanes done with this stage before it is refilled two tiles later
   }
 

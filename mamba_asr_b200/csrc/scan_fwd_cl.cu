@@ -9,6 +9,8 @@
 // Requirements (checked by the launcher, which otherwise falls back to scan_fwd.cu): unit channel stride and
 // 16-byte aligned rows for u, delta, z, out, B, C; dim a multiple of the warp's channel count; dstate == 16;
 // input-dependent B/C.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace cm {
@@ -59,8 +61,11 @@ struct FwdClSmem {
 
 enum { FM_UNI = 0, FM_STASH = 1, FM_COMBINE = 2 };
 
+#ifndef CM_FWDCL_MINB
+#define CM_FWDCL_MINB 7
+#endif
 template <typename T, int LPC>
-__global__ void __launch_bounds__(64, 8) scan_fwd_cl_kernel(const __grid_constant__ cm_scan_fwd_args p) {
+__global__ void __launch_bounds__(64, CM_FWDCL_MINB) scan_fwd_cl_kernel(const __grid_constant__ cm_scan_fwd_args p) {
   constexpr int NS = 16 / LPC, CPW = 32 / LPC, NP = NS / 2;
   constexpr int ES = (int)sizeof(T);
   constexpr int ROWB = CPW * ES;
@@ -103,6 +108,11 @@ __global__ void __launch_bounds__(64, 8) scan_fwd_cl_kernel(const __grid_constan
   T* prep = p.out_pre.ptr ? static_cast<T*>(p.out_pre.ptr) + b * p.out_pre.sb + d * p.out_pre.sd + l0 * p.out_pre.sl : nullptr;
   const int so_e = (int)(sgn * p.out.sl), sp_e = (int)(sgn * p.out_pre.sl);   // 32-bit: one IMAD.WIDE per address
   float* ckp = dp.ckpt ? dp.ckpt + b * dp.ckpt_sb + d * dp.ckpt_sd : nullptr;
+  // Pin the per-step scalars in registers: without this ptxas re-derives them from the parameter block inside the
+  // step loop (S2R tid -> warp -> LDC p.dir[warp]...), ~25 extra integer instructions per step.
+  float scale_r = scale, Dsk_r = Dsk, bias_r = bias;
+  int so_r = so_e, sp_r = sp_e;
+  asm volatile("" : "+l"(outp), "+l"(prep), "+r"(so_r), "+r"(sp_r), "+f"(scale_r), "+f"(Dsk_r), "+f"(bias_r));
 
   const int s1 = cm_first_range(L, p.ndir, dp.reverse);
   const int nrange = (p.ndir == 2) ? 2 : 1;
@@ -166,63 +176,67 @@ __global__ void __launch_bounds__(64, 8) scan_fwd_cl_kernel(const __grid_constan
         for (int i = 0; i < NS / 4; ++i) dst[i] = make_float4(h2[2 * i].x, h2[2 * i].y, h2[2 * i + 1].x, h2[2 * i + 1].y);
       }
       __syncwarp();
+      auto group_body = [&](auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;   // all kGrp steps exist: no per-step predicates
       // ---- pre-phase: per-step scalars of the whole group (four independent softplus / gate chains interleave)
-      float uu[kGrp], dtv[kGrp], stv[kGrp], gatev[kGrp];
+        float uu[kGrp], dtv[kGrp], stv[kGrp], gatev[kGrp];
 #pragma unroll
-      for (int k = 0; k < kGrp; ++k) {
-        uu[k] = sld<T>(S.u[k][cl]);
-        const float x = sld<T>(S.dl[k][cl]) + bias;
-        dtv[k] = softplus ? softplus_fwd<sizeof(T) == 4>(x) : x;
-        stv[k] = need_st ? sld<T>(S.st[k][cl]) : 0.f;
-        gatev[k] = 1.f;
-        if (need_z) { const float zz = sld<T>(S.z[k][cl]); gatev[k] = zz * sigmoid_sel<sizeof(T) == 4>(zz); }
-      }
-      // ---- recurrence: each step is written in pipeline order - operand rows, all exponent arguments, all 16 MUFU,
-      // all input products, then the state updates and the output contraction - so that no instruction sits right
-      // behind the MUFU / LDS result it consumes
-#pragma unroll
-      for (int k = 0; k < kGrp; ++k) {
-        if (k < nvalid) {
-          const float dt = dtv[k], du = dt * uu[k];
-          const float2 dt2 = make_float2(dt, dt), du2 = make_float2(du, du);
-          float4 b4[NS / 4], c4[NS / 4];
-          const float4* rb = reinterpret_cast<const float4*>(&bcf[k][sg * NS]);
-          const float4* rc = reinterpret_cast<const float4*>(&bcf[k][16 + sg * NS]);
-#pragma unroll
-          for (int q = 0; q < NS / 4; ++q) b4[q] = rb[q];
-          float2 a2[NP];
-#pragma unroll
-          for (int i = 0; i < NP; ++i) a2[i] = fmul2(dt2, kA2[i]);
-#pragma unroll
-          for (int q = 0; q < NS / 4; ++q) c4[q] = rc[q];
-#pragma unroll
-          for (int i = 0; i < NP; ++i) a2[i] = make_float2(ex2(a2[i].x), ex2(a2[i].y));
-          float2 ub[NP];
-#pragma unroll
-          for (int q = 0; q < NS / 4; ++q) {
-            ub[2 * q] = fmul2(du2, make_float2(b4[q].x, b4[q].y));
-            ub[2 * q + 1] = fmul2(du2, make_float2(b4[q].z, b4[q].w));
-          }
-#pragma unroll
-          for (int i = 0; i < NP; ++i) h2[i] = ffma2(a2[i], h2[i], ub[i]);
-          float2 ya = make_float2(0.f, 0.f), yb = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int q = 0; q < NS / 4; ++q) {
-            ya = ffma2(make_float2(c4[q].x, c4[q].y), h2[2 * q], ya);
-            yb = ffma2(make_float2(c4[q].z, c4[q].w), h2[2 * q + 1], yb);
-          }
-          const float2 ys = fadd2(ya, yb);
-          float y = ys.x + ys.y;
-          if (LPC >= 2) y += __shfl_xor_sync(0xffffffffu, y, 1);
-          if (LPC >= 4) y += __shfl_xor_sync(0xffffffffu, y, 2);
-          y = fmaf(Dsk, uu[k], y);
-          const float tot = y + stv[k];
-          const float val = stash_mode ? y : tot * gatev[k] * scale;
-          const int s = s0 + k;
-          if (pre_ok) Elem<T>::st(prep + (int64_t)s * sp_e, tot);
-          if (sg == 0) Elem<T>::st(outp + (int64_t)s * so_e, val);
+        for (int k = 0; k < kGrp; ++k) {
+          uu[k] = sld<T>(S.u[k][cl]);
+          const float x = sld<T>(S.dl[k][cl]) + bias_r;
+          dtv[k] = softplus ? softplus_fwd<sizeof(T) == 4>(x) : x;
+          stv[k] = need_st ? sld<T>(S.st[k][cl]) : 0.f;
+          gatev[k] = 1.f;
+          if (need_z) { const float zz = sld<T>(S.z[k][cl]); gatev[k] = zz * sigmoid_sel<sizeof(T) == 4>(zz); }
         }
-      }
+        // ---- recurrence: each step is written in pipeline order - operand rows, all exponent arguments, all 16 MUFU,
+        // all input products, then the state updates and the output contraction - so that no instruction sits right
+        // behind the MUFU / LDS result it consumes
+#pragma unroll
+        for (int k = 0; k < kGrp; ++k) {
+          if (FULL || k < nvalid) {
+            const float dt = dtv[k], du = dt * uu[k];
+            const float2 dt2 = make_float2(dt, dt), du2 = make_float2(du, du);
+            float4 b4[NS / 4], c4[NS / 4];
+            const float4* rb = reinterpret_cast<const float4*>(&bcf[k][sg * NS]);
+            const float4* rc = reinterpret_cast<const float4*>(&bcf[k][16 + sg * NS]);
+#pragma unroll
+            for (int q = 0; q < NS / 4; ++q) b4[q] = rb[q];
+            float2 a2[NP];
+#pragma unroll
+            for (int i = 0; i < NP; ++i) a2[i] = fmul2(dt2, kA2[i]);
+#pragma unroll
+            for (int q = 0; q < NS / 4; ++q) c4[q] = rc[q];
+#pragma unroll
+            for (int i = 0; i < NP; ++i) a2[i] = make_float2(ex2(a2[i].x), ex2(a2[i].y));
+            float2 ub[NP];
+#pragma unroll
+            for (int q = 0; q < NS / 4; ++q) {
+              ub[2 * q] = fmul2(du2, make_float2(b4[q].x, b4[q].y));
+              ub[2 * q + 1] = fmul2(du2, make_float2(b4[q].z, b4[q].w));
+            }
+#pragma unroll
+            for (int i = 0; i < NP; ++i) h2[i] = ffma2(a2[i], h2[i], ub[i]);
+            float2 ya = make_float2(0.f, 0.f), yb = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < NS / 4; ++q) {
+              ya = ffma2(make_float2(c4[q].x, c4[q].y), h2[2 * q], ya);
+              yb = ffma2(make_float2(c4[q].z, c4[q].w), h2[2 * q + 1], yb);
+            }
+            const float2 ys = fadd2(ya, yb);
+            float y = ys.x + ys.y;
+            if (LPC >= 2) y += __shfl_xor_sync(0xffffffffu, y, 1);
+            if (LPC >= 4) y += __shfl_xor_sync(0xffffffffu, y, 2);
+            y = fmaf(Dsk_r, uu[k], y);
+            const float tot = y + stv[k];
+            const float val = stash_mode ? y : tot * gatev[k] * scale_r;
+            const int s = s0 + k;
+            if (pre_ok) Elem<T>::st(prep + (int64_t)s * sp_r, tot);
+            if (sg == 0) Elem<T>::st(outp + (int64_t)s * so_r, val);
+          }
+        }
+      };
+      if (nvalid == kGrp) group_body(std::true_type{}); else group_body(std::false_type{});
       __syncwarp();   // stage g % kStages is refilled by the next iteration's issue
     }
     cpa_wait<0>();

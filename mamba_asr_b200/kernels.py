@@ -207,7 +207,7 @@ def scan_backward(dirs, ckpts, dout, z=None, out_pre=None, out_scale=1.0, delta_
     a.dtype = cabi.dtype_code(u0.dtype)
     a.flags = cabi.CM_FLAG_DELTA_SOFTPLUS if delta_softplus else 0
     a.out_scale = float(out_scale)
-    lpc = int(lanes) or int(os.environ.get("CM_SCAN_LANES", "0")) or lib.cm_scan_pick_lanes(Bt, D, len(dirs))
+    lpc = int(lanes) or int(os.environ.get("CM_SCAN_LANES", "0")) or lib.cm_scan_pick_lanes_bwd(Bt, D, len(dirs))
     a.lanes_per_channel = lpc
     slab_ch = lib.cm_scan_slab_channels(lpc)
     n_slab = (D + slab_ch - 1) // slab_ch

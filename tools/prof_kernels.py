@@ -67,12 +67,12 @@ def main():
         rn = lambda *sh: torch.randn(*sh, device=dev, generator=g)
         cl = lambda: rn(Bt, L, D).to(dt).transpose(1, 2)
         z = cl()
-        P = R + 2 * N
+        P = 2 * N + (R + 7) // 8 * 8                  # the module's aligned x_dbl layout: [B | C | dt | pad]
         dirs = []
         for rev in (False, True):
             xdbl = rn(Bt, L, P).to(dt)
             dirs.append(dict(u=cl(), delta=(0.5 * rn(Bt, L, D)).to(dt).transpose(1, 2), A=-torch.exp(0.3 * rn(D, N)),
-                             B=xdbl[..., R:R + N].transpose(1, 2), C=xdbl[..., R + N:].transpose(1, 2),
+                             B=xdbl[..., :N].transpose(1, 2), C=xdbl[..., N:2 * N].transpose(1, 2),
                              D=torch.ones(D, device=dev), delta_bias=torch.full((D,), -4.0, device=dev), reverse=rev))
         for lanes in [int(x) for x in args.lanes.split(",")]:
             tag = "cfg%s B%d D%d L%d %s lanes=%d" % (cfg, Bt, D, L, args.dtype, lanes)

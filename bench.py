@@ -200,7 +200,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--graph", action="store_true", help="replay model forward/backward as CUDA graphs (measured slower than eager: the step is GPU-bound, not launch-bound)")
+    ap.add_argument("--no-graph", action="store_true", help="(default) launch every kernel eagerly")
     ap.add_argument("--cpu-steps", type=int, default=2)
     args = ap.parse_args()
 
@@ -260,10 +261,10 @@ def main():
 
     # One CUDA graph for forward + CTC loss + backward (the step is host-launch-bound otherwise); eager fallback if
     # the capture is refused (e.g. a collective that cannot be captured).
-    graph_note = "eager launches (--no-graph)"
+    graph_note = "eager launches"
     step_fn = step_eager
     launches_per_step = None
-    if not args.no_graph:
+    if args.graph and not args.no_graph:
         try:
             # forward graph + backward graph of the whole model (wav -> log-probs); the CTC loss between them stays
             # eager because its length tensors live on the host

@@ -151,3 +151,18 @@ def test_bench_reference_arm_prints_the_contract_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "audio-sec/sec"
+
+
+def test_product_length_and_mask_integers_are_bit_exact_with_the_oracle():
+    from mamba_asr_b200 import lengths as P
+    from oracle import lengths_ref as O
+    for n in (16000, 159999, 160000, 240000, 320000, 4800000):
+        assert P.fbank_frames(n) == O.fbank_frames(n)
+        assert P.encoder_frames(P.fbank_frames(n)) == O.encoder_frames(O.fbank_frames(n))
+    g = torch.Generator().manual_seed(0)
+    for L in (1, 2, 251, 376, 501, 7501):
+        wl = torch.cat([torch.linspace(0.5, 1.0, 64), torch.rand(64, generator=g).clamp(min=0.01), torch.tensor([1.0])])
+        a, b = P.abs_lengths(wl, L), O.abs_lengths(wl, L)
+        assert torch.equal(a, b) and np.array_equal(a.numpy(), O.abs_lengths_numpy(wl.numpy(), L))
+        assert torch.equal(P.key_padding_mask(wl, L), O.key_padding_mask(wl, L))
+    assert float(P.abs_lengths(torch.tensor([0.5]), 501)) == 250.0      # half-to-even

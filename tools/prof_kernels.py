@@ -16,7 +16,8 @@ from mamba_asr_b200 import kernels as K  # noqa: E402
 
 CFG = {  # (Bt, D, L, R)
     "1": (8, 288, 251, 9), "2": (32, 288, 376, 9), "3": (64, 512, 501, 16), "4": (64, 1024, 501, 32),
-    "5": (4, 512, 7501, 16), "5a": (4, 512, 1024, 16), "5b": (4, 512, 30000, 16),
+    "5": (4, 512, 7501, 16), "5_1k": (4, 512, 1024, 16), "5_2k": (4, 512, 2048, 16), "5_4k": (4, 512, 4096, 16),
+    "5_8k": (4, 512, 8192, 16), "5_16k": (4, 512, 16384, 16), "5_30k": (4, 512, 30001, 16),
 }
 
 

@@ -407,14 +407,16 @@ extern "C" int cm_scan_fwd(const cm_scan_fwd_args* args, void* stream) {
     if (a.dir[0].bc_const != a.dir[1].bc_const) return CM_ERR_UNSUPPORTED;
   }
   int lpc = a.lanes_per_channel;
-  if (lpc == 0) lpc = cm_scan_pick_lanes(a.batch, a.dim, a.ndir);
-  if (lpc != 1 && lpc != 2 && lpc != 4) return CM_ERR_BAD_ARG;
+  if (lpc != 0 && lpc != 1 && lpc != 2 && lpc != 4) return CM_ERR_BAD_ARG;
   const bool bcc = a.dir[0].bc_const != 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (getenv("CM_SCAN_GENERIC") == nullptr) {   // env switch only for A/B measurements of the two kernels
+    // The cp.async-staged kernel is fastest with ONE lane per channel at every measured shape (32 x 288 ... 64 x 1024
+    // channels, L 376 ... 30 k): splitting a channel over lanes duplicates the per-step scalar work.
     int rc = 0;
-    if (cm::scan_fwd_try_channel_last(a, lpc, st, &rc)) return rc;
+    if (cm::scan_fwd_try_channel_last(a, lpc == 0 ? 1 : lpc, st, &rc)) return rc;
   }
+  if (lpc == 0) lpc = cm_scan_pick_lanes(a.batch, a.dim, a.ndir);
   switch (a.dtype) {
     case CM_F32: return cm::launch_fwd_t<float>(a, lpc, bcc, st);
     case CM_BF16: return cm::launch_fwd_t<__nv_bfloat16>(a, lpc, bcc, st);

@@ -214,10 +214,38 @@ typedef struct {
 int cm_fbank_logmel(const cm_fbank_args* args, void* stream);
 int cm_fbank_floor(const cm_fbank_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * LayerNorm over the last dimension (the six LayerNorms around each Mamba block,
+ * reference modules/Conmamba.py:595-621, 638-649).  y = (x - mean) * rstd * gamma + beta, statistics in fp32.
+ * dy / y share y_dtype; dx has x_dtype.  Backward writes cm_layernorm_num_part(rows) partial rows of dgamma / dbeta
+ * (fp32, [n_part][cols]) to be summed with cm_reduce_multi.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t rows;
+  int32_t cols;             /* <= 1024 */
+  int32_t x_dtype, y_dtype;
+  float eps;
+  const void* x;  int64_t x_stride;      /* row strides in elements; unit column stride */
+  void* y;        int64_t y_stride;      /* forward output */
+  const float* gamma;                    /* (cols) fp32 or NULL */
+  const float* beta;                     /* (cols) fp32 or NULL */
+  float* mean;                           /* (rows) fp32: written by forward, read by backward */
+  float* rstd;                           /* (rows) fp32 */
+  const void* dy; int64_t dy_stride;     /* backward: grad of y */
+  void* dx;       int64_t dx_stride;     /* backward: grad of x */
+  float* dgamma_part;
+  float* dbeta_part;
+} cm_layernorm_args;
+
+int cm_layernorm_num_part(int64_t rows);
+int cm_layernorm_fwd(const cm_layernorm_args* args, void* stream);
+int cm_layernorm_bwd(const cm_layernorm_args* args, void* stream);
+
 /* library identification: returns CM_ABI_VERSION; writes the compiled-for arch (e.g. 100) to *sm_arch if non-NULL */
 int cm_version(int32_t* sm_arch);
 /* sizeof() of the argument structs, for binding self-checks: 0 cm_tensor3, 1 cm_scan_dir, 2 cm_scan_fwd_args,
- * 3 cm_scan_bwd_dir, 4 cm_scan_bwd_args, 5 cm_conv_dir, 6 cm_conv_args, 7 cm_fbank_args, 8 cm_reduce_job */
+ * 3 cm_scan_bwd_dir, 4 cm_scan_bwd_args, 5 cm_conv_dir, 6 cm_conv_args, 7 cm_fbank_args, 8 cm_reduce_job,
+ * 9 cm_layernorm_args */
 int cm_abi_sizeof(int32_t which);
 
 #ifdef __cplusplus

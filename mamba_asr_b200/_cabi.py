@@ -23,7 +23,8 @@ EXPORTS = (
     "cm_version", "cm_scan_num_ckpt", "cm_scan_slab_channels", "cm_scan_pick_lanes", "cm_scan_pick_lanes_bwd", "cm_scan_fwd",
     "cm_scan_bwd",
     "cm_reduce_dbc", "cm_reduce_rows", "cm_conv_fwd", "cm_conv_num_part", "cm_conv_bwd", "cm_conv_update",
-    "cm_fbank_logmel", "cm_fbank_floor", "cm_abi_sizeof", "cm_reduce_multi",
+    "cm_fbank_logmel", "cm_fbank_floor", "cm_abi_sizeof", "cm_reduce_multi", "cm_layernorm_num_part", "cm_layernorm_fwd",
+    "cm_layernorm_bwd",
 )
 CM_REDUCE_MAX_JOBS = 8
 
@@ -102,7 +103,18 @@ class ReduceJob(C.Structure):
     _fields_ = [("part", C.c_void_p), ("out", C.c_void_p), ("rows", C.c_int64), ("cols", C.c_int64)]
 
 
-ABI_STRUCTS = (Tensor3, ScanDir, ScanFwdArgs, ScanBwdDir, ScanBwdArgs, ConvDir, ConvArgs, FbankArgs, ReduceJob)
+class LayerNormArgs(C.Structure):
+    _fields_ = [
+        ("rows", C.c_int64), ("cols", C.c_int32), ("x_dtype", C.c_int32), ("y_dtype", C.c_int32), ("eps", C.c_float),
+        ("x", C.c_void_p), ("x_stride", C.c_int64), ("y", C.c_void_p), ("y_stride", C.c_int64),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("mean", C.c_void_p), ("rstd", C.c_void_p),
+        ("dy", C.c_void_p), ("dy_stride", C.c_int64), ("dx", C.c_void_p), ("dx_stride", C.c_int64),
+        ("dgamma_part", C.c_void_p), ("dbeta_part", C.c_void_p),
+    ]
+
+
+ABI_STRUCTS = (Tensor3, ScanDir, ScanFwdArgs, ScanBwdDir, ScanBwdArgs, ConvDir, ConvArgs, FbankArgs, ReduceJob,
+               LayerNormArgs)
 
 _lib = None
 
@@ -137,6 +149,9 @@ def lib():
         L.cm_fbank_floor.argtypes = [C.POINTER(FbankArgs), C.c_void_p]
         L.cm_abi_sizeof.argtypes = [C.c_int32]
         L.cm_reduce_multi.argtypes = [C.POINTER(ReduceJob), C.c_int32, C.c_void_p]
+        L.cm_layernorm_num_part.argtypes = [C.c_int64]
+        L.cm_layernorm_fwd.argtypes = [C.POINTER(LayerNormArgs), C.c_void_p]
+        L.cm_layernorm_bwd.argtypes = [C.POINTER(LayerNormArgs), C.c_void_p]
         if L.cm_version(None) != CM_ABI_VERSION:
             raise RuntimeError("mamba_asr_b200: %s has a different ABI version; rebuild it" % LIB_PATH)
         for i, st in enumerate(ABI_STRUCTS):

@@ -390,6 +390,7 @@ static int check_dir(const cm_scan_dir& d) {
 
 namespace cm {
 int scan_fwd_try_channel_last(const cm_scan_fwd_args& a, int lpc, cudaStream_t st, int* rc);   // scan_fwd_cl.cu
+int scan_fwd_try_state_parallel(const cm_scan_fwd_args& a, cudaStream_t st, int* rc);            // scan_fwd_sp.cu
 }
 
 extern "C" int cm_scan_fwd(const cm_scan_fwd_args* args, void* stream) {
@@ -410,6 +411,11 @@ extern "C" int cm_scan_fwd(const cm_scan_fwd_args* args, void* stream) {
   if (lpc != 0 && lpc != 1 && lpc != 2 && lpc != 4) return CM_ERR_BAD_ARG;
   const bool bcc = a.dir[0].bc_const != 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (getenv("CM_SCAN_GENERIC") == nullptr && getenv("CM_SCAN_NO_SP") == nullptr && a.lanes_per_channel == 0) {
+    // state-parallel kernel (lane = state): the default whenever the layout is channel-last
+    int rc = 0;
+    if (cm::scan_fwd_try_state_parallel(a, st, &rc)) return rc;
+  }
   if (getenv("CM_SCAN_GENERIC") == nullptr) {   // env switch only for A/B measurements of the two kernels
     // The cp.async-staged kernel is fastest with ONE lane per channel at every measured shape (32 x 288 ... 64 x 1024
     // channels, L 376 ... 30 k): splitting a channel over lanes duplicates the per-step scalar work.

@@ -46,6 +46,20 @@ def timeit(fn, iters, flush):
     return ts[0], ts[len(ts) // 2]
 
 
+def timek(fn, name, iters, flush):
+    """kernel-only time: event pair around the C-ABI launch (kernels._call), L2 flushed before every launch"""
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        K.start_timing()
+        fn()
+        ts += K.stop_timing()[name]
+    ts.sort()
+    return ts[0], ts[len(ts) // 2]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cfg", default="2,3")
@@ -80,13 +94,13 @@ def main():
             if "scan_fwd" in only:
                 f = lambda: K.scan_forward(dirs, z=z, out_scale=0.5, delta_softplus=True, need_ckpt=True,
                                            need_out_pre=True, lanes=lanes)
-                best, med = timeit(f, args.iters, flush)
+                best, med = timek(f, "cm_scan_fwd", args.iters, flush)
                 byts = (6 + 4.0 * N / D) * s * pos
                 print("%-40s scan_fwd(train)  best %.3f ms med %.3f ms  alg %.1f GB/s (%.1f%% of %.0f)  %.1f ps/pos"
                       % (tag, best, med, byts / best / 1e6, 100 * byts / best / 1e6 / peak, peak, best * 1e9 / pos))
             if "scan_fwd_infer" in only:
                 f = lambda: K.scan_forward(dirs, z=z, out_scale=0.5, delta_softplus=True, lanes=lanes)
-                best, med = timeit(f, args.iters, flush)
+                best, med = timek(f, "cm_scan_fwd", args.iters, flush)
                 byts = (6 + 4.0 * N / D) * s * pos
                 print("%-40s scan_fwd(infer)  best %.3f ms med %.3f ms  alg %.1f GB/s (%.1f%%)"
                       % (tag, best, med, byts / best / 1e6, 100 * byts / best / 1e6 / peak))

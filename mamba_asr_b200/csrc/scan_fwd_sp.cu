@@ -1,458 +1,425 @@
-// Selective-scan forward, state-parallel channel-last kernel for sm_100a ("sp" path).
+// Selective-scan forward, state-parallel channel-last kernel for sm_100a ("sp" path) - the default forward kernel.
 //
 // Mathematics, bidirectional stash/combine protocol and checkpoint contract are those of scan_fwd.cu (see its header;
 // reference semantics: modules/mamba/selective_scan_interface.py:106-157 and modules/mamba/bimamba.py:223-253).
 // What differs is the mapping of work to lanes.  scan_fwd.cu / scan_fwd_cl.cu give one lane a whole channel (16 states
-// in registers); that is op-optimal but leaves batch*dim*ndir/32 warps - 576 warps for 32 x 288 channels, fewer than
-// the 592 SM sub-partitions of a B200 - and every step pays the per-channel scalar work (softplus, gate, conversions,
-// predicates) at 1/32 lane efficiency in front of a latency-exposed recurrence.
+// in registers): op-optimal, but only batch*dim*ndir/32 warps exist - 576 for 32 x 288 channels, fewer than the 592 SM
+// sub-partitions of a B200 - and the per-channel scalar work (softplus, gate, conversions, predicates) runs in front
+// of a latency-exposed recurrence at 1/32 lane efficiency.
 //
-// Here a LANE OWNS ONE STATE n of CPL adjacent channels: a warp = 2 half-warps x 16 states = 2*CPL channels, so there
-// are 16/CPL times more warps, and the time loop of a lane is the bare recurrence
-//     LDS (dt,du)  LDS (B_n,C_n)  FMUL2  MUFU.EX2 x CPL  FMUL2  FFMA2  FMUL2  STS
-// - about 9 issue slots per 16 MUFU cycles for CPL = 2: the XU pipe (16 ex2/clk/SM) is the binding unit, as it must be
-// for this op on B200.  Everything that is per (step, channel) rather than per (step, channel,
-// state) is done by the same threads in vectorised phases around the recurrence, one TILE of kT steps at a time:
-//   pre-phase : each thread converts ONE (step, channel-pair): raw loads (issued a whole tile ahead, straight into
-//               registers), softplus, dt*u  -> fp32 (dt, du) rows in shared memory; B/C rows -> fp32 (B_n, C_n) pairs
-//   recurrence: writes the products C_n*h_n to a padded shared tile
-//   epilogue  : the thread that converted a (step, channel-pair) sums its 16 products (LDS.128, conflict-free), adds
-//               D*u, stashes / combines with the partner direction / gates, and stores 2 channels with one access.
-// The two time directions of a channel block share a CTA (one 128-thread group each, private named barriers) and meet
-// in the middle exactly like scan_fwd.cu: range 0 stashes pre-gate sums in `out`, one __syncthreads(), range 1 reads the
-// partner's stash back (L2), adds, gates once, writes the final value and `out_pre`.
+// Here a LANE OWNS FOUR STATES (4m..4m+3) OF TWO ADJACENT CHANNELS: 4 lanes cover a channel pair, a warp 8 pairs, and
+// the kernel is WARP-SPECIALISED.  Per time direction a CTA (32 channels) runs
+//   2 recurrence warps: the bare time loop on packed fp32 pairs, per step
+//        LDS.128 (dt0,dt1,du0,du1)  2 LDS.128 (B[4], C[4])  4 FMUL2  8 MUFU.EX2  4 FMUL2  4 FFMA2  FMUL2 3 FFMA2  STS.64
+//      = 28 issue slots per 64 XU cycles, then a warp-local reduction of the 4 partial sums of each (step, pair);
+//   2 IO warps: raw global loads issued a whole tile ahead straight into registers, softplus, dt*u -> fp32
+//      (dt0,dt1,du0,du1) rows and fp32 B/C rows in a 2-tile shared ring; epilogue: D*u skip term, stash / combine with
+//      the partner direction / gate, 2 channels per store.
+// The roles meet only through mbarriers (full/empty pairs on the operand ring and on the y ring), so the recurrence
+// warps never see a global-memory latency.  WHY 4 x 2: measured with ncu, the binding unit of the 2-states-x-2-channels
+// variant was neither the MUFU pipe (45 %) nor issue (42 %) but the LSU data pipe (l1tex__data_pipe_lsu_wavefronts
+// 90 %): every state update needs its operands delivered to registers through the 128 B/clk shared-memory pipe,
+// 12/S + 8/C bytes per update for S states x C channels per lane (dt,du,y per channel; B,C per state).  2x2 = 10 B,
+// 4x2 = 7 B, which puts the pipe at 18 updates/clk/SM against the MUFU pipe's 16.
+// The two time directions of a channel block share a CTA and meet in the middle exactly like scan_fwd.cu: range 0
+// stashes pre-gate sums in `out`, one __syncthreads(), range 1 reads the partner's stash back (L2), adds, gates once,
+// writes the final value and `out_pre`.
 //
 // Requirements (else the launcher falls through to the other kernels): unit channel stride, dstate == 16, variable
-// B/C with unit state stride, dim a multiple of the CTA's channel count, pair/quad-aligned rows.
+// B/C with unit state stride, dim a multiple of 32, pair/quad-aligned rows, 32-bit byte strides per step.
+#include <climits>
 #include <cstdlib>
-#include <type_traits>
 
-#include "common.cuh"
+#include "sp_common.cuh"
 
 namespace cm {
 namespace sp {
 
-constexpr int kT = 16;          // steps per tile
-constexpr int kNW = 4;          // warps per direction group
-constexpr int kGT = kNW * 32;   // threads per direction group
-
-template <int CPL>
-struct Cfg {
-  static constexpr int CH = kNW * 2 * CPL;        // channels per CTA
-  static constexpr int NG = CH / CPL;             // channel groups per CTA (= lanes' channel blocks) = 2*kNW
-  static constexpr int PROW = 16 * CPL + 4;       // padded row of the product tile (floats)
-  static constexpr int NPAIR = CH / 2;            // channel pairs per step
-  static constexpr int UPT = kT * NPAIR / kGT;    // (step, pair) units per thread
-  static constexpr int KSTRIDE = kGT / NPAIR;     // step distance between a thread's units
-  static_assert(kT * NPAIR % kGT == 0 && UPT >= 1, "tile must divide over the group");
+// kernel-side view of one direction: byte pointers at (batch 0, channel 0, PROCESSED step 0) and signed byte strides
+// per processed step, so that every address is one IMAD.WIDE with a constant-bank stride
+struct FwdDir {
+  const char *u, *dl, *B, *C, *z;
+  char *out, *pre;
+  int64_t u_sb, dl_sb, b_sb, c_sb, z_sb, out_sb, pre_sb;   // batch strides (bytes)
+  int32_t u_ss, dl_ss, b_ss, c_ss, z_ss, out_ss, pre_ss;   // bytes per processed step
+  int32_t s1;                                              // length of the first range (cm_first_range)
+  const float* A;
+  int64_t A_sd, A_sn;
+  const float *Dskip, *bias;
+  float* ckpt;
+  int64_t ckpt_sb, ckpt_sd;
+  float* last;
+  int64_t ls_sb, ls_sd, ls_sn;
+};
+struct FwdParams {
+  int32_t L;
+  uint32_t flags;
+  float scale;
+  int32_t pad;
+  FwdDir dir[2];
 };
 
-template <int CPL>
-struct DirSmem {
-  using C = Cfg<CPL>;
-  float dd[2][kT][C::NG][2 * CPL];   // per channel group: dt[CPL] then du[CPL]
-  float2 bc[2][kT][16];              // (B_n, C_n)
-  float p[kT][C::NG][C::PROW];       // products C_n*h_n: element [n*CPL + j]
-};
+#ifndef CM_FWDSP_IO
+#define CM_FWDSP_IO 64
+#endif
+constexpr int kIO = CM_FWDSP_IO; // IO threads per direction (2 or 4 warps)
+constexpr int kNBC = 128 / kIO;  // B/C quarter rows per IO thread and tile
+constexpr int kIU = kT * kNP / kIO;   // (step, pair) units per IO thread and tile (4)
+constexpr int kIKS = kIO / kNP;       // step distance between an IO thread's units (4)
 
-// ---- paired element I/O ------------------------------------------------------------------------------------------
-template <typename T> struct Pair;
-template <> struct Pair<float> {
-  using Raw = float2;
-  static __device__ __forceinline__ Raw ld_nc(const void* p) {
-    Raw r; asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p)); return r;
-  }
-  static __device__ __forceinline__ Raw ld_cg(const void* p) {
-    Raw r; asm volatile("ld.global.cg.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p)); return r;
-  }
-  static __device__ __forceinline__ Raw zero() { return make_float2(0.f, 0.f); }
-  static __device__ __forceinline__ float2 cvt(Raw r) { return r; }
-  static __device__ __forceinline__ void st(void* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+struct FwdSmem {
+  float4 dd[2][kT][kNP];      // (dt0, dt1, du0, du1) of a channel pair            [ring of 2 tiles]
+  float bc[2][kT][32];        // B[0..15] | C[0..15]
+  float p[kNW][kT][8][8];     // warp-private partial products of the tile in flight: [pair in warp][2*lane_in_pair + channel]
+  float2 y[2][kT][kNP];       // sum over states of C*h per (step, channel pair)     [ring of 2 tiles]
+  uint64_t in_full[2], in_empty[2], p_full[2], p_empty[2];   // p_* guard the y ring
 };
-template <> struct Pair<__nv_bfloat16> {
-  using Raw = uint32_t;
-  static __device__ __forceinline__ Raw ld_nc(const void* p) {
-    Raw r; asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(r) : "l"(p)); return r;
-  }
-  static __device__ __forceinline__ Raw ld_cg(const void* p) {
-    Raw r; asm volatile("ld.global.cg.b32 %0, [%1];" : "=r"(r) : "l"(p)); return r;
-  }
-  static __device__ __forceinline__ Raw zero() { return 0u; }
-  static __device__ __forceinline__ float2 cvt(Raw r) {
-    return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u));
-  }
-  static __device__ __forceinline__ void st(void* p, float2 v) {
-    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y);
-  }
-};
-template <> struct Pair<__half> {
-  using Raw = uint32_t;
-  static __device__ __forceinline__ Raw ld_nc(const void* p) {
-    Raw r; asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(r) : "l"(p)); return r;
-  }
-  static __device__ __forceinline__ Raw ld_cg(const void* p) {
-    Raw r; asm volatile("ld.global.cg.b32 %0, [%1];" : "=r"(r) : "l"(p)); return r;
-  }
-  static __device__ __forceinline__ Raw zero() { return 0u; }
-  static __device__ __forceinline__ float2 cvt(Raw r) {
-    return __half22float2(*reinterpret_cast<const __half2*>(&r));
-  }
-  static __device__ __forceinline__ void st(void* p, float2 v) {
-    *reinterpret_cast<__half2*>(p) = __floats2half2_rn(v.x, v.y);
-  }
-};
-
-// four consecutive elements (one quarter of a B or C row)
-template <typename T> struct Quad;
-template <> struct Quad<float> {
-  using Raw = float4;
-  static __device__ __forceinline__ Raw ld_nc(const void* p) {
-    Raw r;
-    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-  }
-  static __device__ __forceinline__ Raw zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
-  static __device__ __forceinline__ void cvt(Raw r, float* o) { o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w; }
-};
-template <> struct Quad<__nv_bfloat16> {
-  using Raw = uint2;
-  static __device__ __forceinline__ Raw ld_nc(const void* p) {
-    Raw r;
-    asm volatile("ld.global.nc.v2.b32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
-    return r;
-  }
-  static __device__ __forceinline__ Raw zero() { return make_uint2(0u, 0u); }
-  static __device__ __forceinline__ void cvt(Raw r, float* o) {
-    o[0] = __uint_as_float(r.x << 16); o[1] = __uint_as_float(r.x & 0xffff0000u);
-    o[2] = __uint_as_float(r.y << 16); o[3] = __uint_as_float(r.y & 0xffff0000u);
-  }
-};
-template <> struct Quad<__half> {
-  using Raw = uint2;
-  static __device__ __forceinline__ Raw ld_nc(const void* p) {
-    Raw r;
-    asm volatile("ld.global.nc.v2.b32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
-    return r;
-  }
-  static __device__ __forceinline__ Raw zero() { return make_uint2(0u, 0u); }
-  static __device__ __forceinline__ void cvt(Raw r, float* o) {
-    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
-    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
-    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
-  }
-};
-
-// private barrier of a direction group (immediate ids: a register id would make ptxas reserve all 16 barriers)
-__device__ __forceinline__ void group_bar(int grp) {
-  if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(kGT) : "memory");
-  else asm volatile("bar.sync 2, %0;" ::"n"(kGT) : "memory");
-}
 
 enum { FM_UNI = 0, FM_STASH = 1, FM_COMBINE = 2 };
 
 #ifndef CM_FWDSP_MINB
-#define CM_FWDSP_MINB 3
+#define CM_FWDSP_MINB 2
 #endif
-constexpr int kSub = 4;   // steps per software-pipelined sub-block of the recurrence
+#ifndef CM_FWDSP_SUB
+#define CM_FWDSP_SUB 2
+#endif
+constexpr int kSub = CM_FWDSP_SUB;   // steps per software-pipelined sub-block of the recurrence
 
-// One direction group (128 threads) of a CTA.  DIR is a template parameter so that every p.dir[DIR] field is a
-// constant-bank operand (no indexed LDC, no registers spent on strides).
-template <typename T, int CPL, int NDIR, int DIR>
-__device__ __forceinline__ void run_dir(const cm_scan_fwd_args& p, DirSmem<CPL>& S, const int gt) {
-  using C = Cfg<CPL>;
+// ---- mbarrier primitives (shared::cta) ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "MBAR_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra MBAR_DONE;\n\t"
+      "bra MBAR_WAIT;\n\t"
+      "MBAR_DONE:\n\t}"
+      ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+// order-pinned shared load / ex2 (volatile: ptxas keeps volatile asm statements in program order)
+__device__ __forceinline__ float4 lds128v(const void* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+__device__ __forceinline__ float ex2v(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// one arrival per warp, after the warp's own shared-memory accesses are ordered
+__device__ __forceinline__ void warp_arrive(uint64_t* b, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(b);
+}
+
+// Tile counter `it` runs over BOTH ranges of a direction; ring slot = it & 1, use count of a slot = it >> 1.
+//   in_full[slot]  : IO warps  -> recurrence warps   (dd/bc of tile `it` are in shared memory)
+//   in_empty[slot] : recurrence -> IO                 (tile `it` has been consumed; slot may be refilled with it+2)
+//   p_full[slot]   : recurrence -> IO                 (y of tile `it` is complete)
+//   p_empty[slot]  : IO -> recurrence                 (y of tile `it` has been consumed; slot free for it+2)
+// The 8 partial products of a (step, channel pair) come from the 8 lanes of ONE warp, so the recurrence warps reduce
+// them themselves after the tile (warp-private buffer, __syncwarp only) - the XU-bound warps have the issue slots.
+
+template <int NDIR>
+__device__ __forceinline__ void range_of(const FwdDir& d, int L, int range, int* s_begin, int* s_end) {
+  *s_begin = range == 0 ? 0 : d.s1;
+  *s_end = (NDIR == 1 || range == 1) ? L : d.s1;
+  if (NDIR == 1) *s_begin = 0;
+}
+
+// ---- recurrence warps (2 per direction): lane = states 4m..4m+3 of channel pair pr -------------------------------
+template <typename T, int NDIR, int DIR>
+__device__ __forceinline__ void scan_role(const FwdParams& P, FwdSmem& S, const int gt) {
+  const FwdDir& d = P.dir[DIR];
+  const int warp = gt >> 5, lane = gt & 31;
+  const int b = blockIdx.y;
+  const int c_base = blockIdx.x * kCH;
+  const int g = lane >> 2, m = lane & 3;
+  const int pr = warp * 8 + g;
+  const int c0 = c_base + 2 * pr;
+  float2 kA[4], h[4];   // [state 4m + j] ; .x channel c0, .y channel c0 + 1
+  {
+    const float* A0 = d.A + (int64_t)c0 * d.A_sd;
+    const float* A1 = A0 + d.A_sd;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      kA[j] = make_float2(__ldg(A0 + (4 * m + j) * d.A_sn) * kLog2e, __ldg(A1 + (4 * m + j) * d.A_sn) * kLog2e);
+      h[j] = make_float2(0.f, 0.f);
+    }
+  }
+  float* ckp = d.ckpt ? d.ckpt + b * d.ckpt_sb + (int64_t)c0 * d.ckpt_sd + 4 * m : nullptr;
+  int it = 0;
+#pragma unroll 1
+  for (int range = 0; range < NDIR; ++range) {
+    if (NDIR == 2 && range == 1) __syncthreads();   // partner's stash of the other half is complete
+    int s_begin, s_end;
+    range_of<NDIR>(d, P.L, range, &s_begin, &s_end);
+    int jck = range == 0 ? 0 : cm_ceil_div(d.s1, CM_SCAN_CKPT_STEPS);   // next checkpoint slot
+    const int nst = s_end - s_begin;
+    const int ntile = nst > 0 ? cm_ceil_div(nst, kT) : 0;
+#pragma unroll 1
+    for (int t = 0; t < ntile; ++t, ++it) {
+      const int slot = it & 1;
+      const uint32_t par = (it >> 1) & 1;
+      const int nvalid = nst - t * kT;    // steps of this tile inside the range (may exceed kT)
+      mbar_wait(&S.in_full[slot], par);
+      if (it >= 2) mbar_wait(&S.p_empty[slot], par ^ 1);
+      const float4* ddb = &S.dd[slot][0][pr];
+      const float* bcb = &S.bc[slot][0][4 * m];
+      float* pb = &S.p[warp][0][g][2 * m];
+      float4 ddr[kSub], br[kSub], cr[kSub];
+      auto lds_sub = [&](int sb) {
+#pragma unroll
+        for (int i = 0; i < kSub; ++i) {
+          ddr[i] = ddb[(sb * kSub + i) * kNP];
+          br[i] = *reinterpret_cast<const float4*>(bcb + (sb * kSub + i) * 32);
+          cr[i] = *reinterpret_cast<const float4*>(bcb + (sb * kSub + i) * 32 + 16);
+        }
+      };
+      lds_sub(0);
+#pragma unroll
+      for (int sb = 0; sb < kT / kSub; ++sb) {
+        if (((sb * kSub) % CM_SCAN_CKPT_STEPS) == 0) {
+          if (ckp != nullptr && sb * kSub < nvalid) {
+            float* dst = ckp + (int64_t)jck * 16;
+            *reinterpret_cast<float4*>(dst) = make_float4(h[0].x, h[1].x, h[2].x, h[3].x);
+            *reinterpret_cast<float4*>(dst + d.ckpt_sd) = make_float4(h[0].y, h[1].y, h[2].y, h[3].y);
+          }
+          ++jck;
+        }
+        float2 a[kSub][4], ub[kSub][4];
+        float4 cc[kSub];
+#pragma unroll
+        for (int i = 0; i < kSub; ++i) {
+          const float2 dt = make_float2(ddr[i].x, ddr[i].y), du = make_float2(ddr[i].z, ddr[i].w);
+          const float bb[4] = {br[i].x, br[i].y, br[i].z, br[i].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            a[i][j] = fmul2(dt, kA[j]);
+            ub[i][j] = fmul2(du, make_float2(bb[j], bb[j]));
+          }
+          cc[i] = cr[i];
+        }
+        if (sb + 1 < kT / kSub) lds_sub(sb + 1);
+#pragma unroll
+        for (int i = 0; i < kSub; ++i) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) a[i][j] = make_float2(ex2(a[i][j].x), ex2(a[i][j].y));
+        }
+#pragma unroll
+        for (int i = 0; i < kSub; ++i) {
+          const float c4[4] = {cc[i].x, cc[i].y, cc[i].z, cc[i].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) h[j] = ffma2(a[i][j], h[j], ub[i][j]);
+          float2 pp = fmul2(make_float2(c4[0], c4[0]), h[0]);
+#pragma unroll
+          for (int j = 1; j < 4; ++j) pp = ffma2(make_float2(c4[j], c4[j]), h[j], pp);
+          *reinterpret_cast<float2*>(pb + (sb * kSub + i) * 64) = pp;
+        }
+      }
+      __syncwarp();
+      // reduce this warp's 128 (step, pair) rows of 8 floats (4 lanes x 2 channels): lane -> rows lane + 32 j.  The two
+      // 16-byte halves are read in an order that depends on the row, which keeps the LDS.128 conflict-free.
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = lane + 32 * j;
+        const float4* row = reinterpret_cast<const float4*>(&S.p[warp][0][0][0] + r * 8);
+        const int sw = (r >> 2) & 1;
+        const float4 v0 = row[sw], v1 = row[sw ^ 1];
+        const float2 acc = fadd2(fadd2(make_float2(v0.x, v0.y), make_float2(v0.z, v0.w)),
+                                 fadd2(make_float2(v1.x, v1.y), make_float2(v1.z, v1.w)));
+        S.y[slot][r >> 3][warp * 8 + (r & 7)] = acc;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&S.in_empty[slot]);
+        mbar_arrive(&S.p_full[slot]);
+      }
+    }
+  }
+  if (d.last != nullptr) {
+    float* ls = d.last + b * d.ls_sb + (int64_t)c0 * d.ls_sd + 4 * m * d.ls_sn;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      ls[j * d.ls_sn] = h[j].x;
+      ls[d.ls_sd + j * d.ls_sn] = h[j].y;
+    }
+  }
+}
+
+// ---- IO warps (2 per direction): thread = channel pair cp at steps k0 + 4i of every tile ----------------------------
+template <typename T, int NDIR, int DIR>
+__device__ __forceinline__ void io_role(const FwdParams& P, FwdSmem& S, const int io) {
   using P2 = Pair<T>;
   using Q4 = Quad<T>;
   constexpr int ES = (int)sizeof(T);
   constexpr bool PRECISE = sizeof(T) == 4;
-  const cm_scan_dir& dp = p.dir[DIR];
-  const int warp = gt >> 5, lane = gt & 31;
+  const FwdDir& d = P.dir[DIR];
+  const int lane = io & 31;
   const int b = blockIdx.y;
-  const int c_base = blockIdx.x * C::CH;
-  const int L = p.seqlen;
-  const bool rev = dp.reverse != 0;
-  const bool softplus = (p.flags & CM_FLAG_DELTA_SOFTPLUS) != 0;
-  const bool has_z = p.z.ptr != nullptr;
-
-  // ---- recurrence identity: state n of channel group g
-  const int hw = lane >> 4, n = lane & 15;
-  const int g = warp * 2 + hw;
-  const int cs = c_base + g * CPL;
-  float kA[CPL], h[CPL];
-#pragma unroll
-  for (int j = 0; j < CPL; ++j) {
-    kA[j] = __ldg(dp.A + (int64_t)(cs + j) * dp.A_sd + n * dp.A_sn) * kLog2e;
-    h[j] = 0.f;
-  }
-  float* ckp = dp.ckpt ? dp.ckpt + b * dp.ckpt_sb + (int64_t)cs * dp.ckpt_sd + n : nullptr;
-
-  // ---- unit identity (pre-phase and epilogue): channel pair cp at steps k0 + i*KSTRIDE of every tile
-  const int cp = gt % C::NPAIR, k0 = gt / C::NPAIR;
+  const int c_base = blockIdx.x * kCH;
+  const bool softplus = (P.flags & CM_FLAG_DELTA_SOFTPLUS) != 0;
+  const bool has_z = d.z != nullptr;
+  const int cp = io & (kNP - 1), k0 = io / kNP;
   const int cu = c_base + 2 * cp;
-  float bias[2], Dsk[2];
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    bias[j] = dp.delta_bias ? __ldg(dp.delta_bias + cu + j) : 0.f;
-    Dsk[j] = dp.Dskip ? __ldg(dp.Dskip + cu + j) : 0.f;
-  }
-  const int64_t sgn = rev ? -1 : 1, l0 = rev ? (L - 1) : 0;
-  // byte pointer of this thread's first unit at processed step s
-  auto at = [&](const cm_tensor3& t, int s) {
-    return static_cast<char*>(t.ptr) + (b * t.sb + (int64_t)cu * t.sd + (l0 + sgn * s) * t.sl) * ES;
-  };
-  // B/C quarter rows: thread (row kq, part) of the tile
-  const int kq = gt >> 3, part = gt & 7, q4 = (part & 3) * 4;
-  const cm_tensor3& bct = (part < 4) ? dp.Bm : dp.Cm;
+  float2 bias = make_float2(0.f, 0.f), Dsk = make_float2(0.f, 0.f);
+  if (d.bias) bias = make_float2(__ldg(d.bias + cu), __ldg(d.bias + cu + 1));
+  if (d.Dskip) Dsk = make_float2(__ldg(d.Dskip + cu), __ldg(d.Dskip + cu + 1));
+  const char* pu = d.u + b * d.u_sb + cu * ES;
+  const char* pdl = d.dl + b * d.dl_sb + cu * ES;
+  const char* pz = has_z ? d.z + b * d.z_sb + cu * ES : nullptr;
+  char* po = d.out + b * d.out_sb + cu * ES;
+  char* ppre = d.pre ? d.pre + b * d.pre_sb + cu * ES : nullptr;
+  // B/C quarter rows: rows kq + j*kIO/8 of the tile, quarter `part`
+  const int kq = io >> 3, part = io & 7, isC = part >> 2, q4 = (part & 3) * 4;
+  const char* pbc = (isC ? d.C + b * d.c_sb : d.B + b * d.b_sb) + q4 * ES;
+  const int bc_ss = isC ? d.c_ss : d.b_ss;
+  const int bc_dst = isC * 16 + q4;   // floats: row = B[0..15] | C[0..15]
 
-  typename P2::Raw ru[C::UPT], rdl[C::UPT];
-  typename Q4::Raw rbc;
-  float2 uu[C::UPT];
-
-  const int s1 = cm_first_range(L, NDIR, dp.reverse);
+  typename P2::Raw ru[kIU], rdl[kIU], uprev[kIU], rz[kIU], rst[kIU];
+  typename Q4::Raw rbc[kNBC];
+  int it = 0;
 #pragma unroll 1
   for (int range = 0; range < NDIR; ++range) {
     if (NDIR == 2 && range == 1) __syncthreads();   // partner's stash of the other half is complete
     const int mode = (NDIR == 1) ? FM_UNI : (range == 0 ? FM_STASH : FM_COMBINE);
-    const int s_begin = range == 0 ? 0 : s1, s_end = range == 0 ? s1 : L;
-    int jck = range == 0 ? 0 : cm_ceil_div(s1, CM_SCAN_CKPT_STEPS);   // next checkpoint slot
+    int s_begin, s_end;
+    range_of<NDIR>(d, P.L, range, &s_begin, &s_end);
     const int nst = s_end - s_begin;
-    if (nst <= 0) continue;
-    const int ntile = cm_ceil_div(nst, kT);
+    const int ntile = nst > 0 ? cm_ceil_div(nst, kT) : 0;
     const bool need_z = has_z && mode != FM_STASH;
     const bool need_st = mode == FM_COMBINE;
 
-    // advancing pointers: *_n = the tile being prefetched, *_c = the tile being finished
-    const char* pu_n = at(dp.u, s_begin + k0);
-    const char* pdl_n = at(dp.delta, s_begin + k0);
-    const char* pbc_n = static_cast<const char*>(bct.ptr) + (b * bct.sb + (l0 + sgn * (s_begin + kq)) * bct.sl + q4) * ES;
-    const char* pz_c = has_z ? at(p.z, s_begin + k0) : nullptr;
-    char* po_c = at(p.out, s_begin + k0);
-    char* ppre_c = p.out_pre.ptr ? at(p.out_pre, s_begin + k0) : nullptr;
-    int rem_n = nst - k0;       // > i*KSTRIDE  <=> unit i of the prefetched tile exists
-    int remq_n = nst - kq;      // > 0 <=> B/C row of the prefetched tile exists
-
-    auto load_raw = [&]() {
+    auto load_raw = [&](int sb0) {
 #pragma unroll
-      for (int i = 0; i < C::UPT; ++i) {
-        if (rem_n > i * C::KSTRIDE) {
-          ru[i] = P2::ld_nc(pu_n + (int64_t)i * C::KSTRIDE * sgn * dp.u.sl * ES);
-          rdl[i] = P2::ld_nc(pdl_n + (int64_t)i * C::KSTRIDE * sgn * dp.delta.sl * ES);
+      for (int i = 0; i < kIU; ++i) {
+        const int s = sb0 + k0 + i * kIKS;
+        if (s < s_end) {
+          ru[i] = P2::ld_nc(pu + (int64_t)s * d.u_ss);
+          rdl[i] = P2::ld_nc(pdl + (int64_t)s * d.dl_ss);
         } else {
           ru[i] = P2::zero();
           rdl[i] = P2::zero();
         }
       }
-      rbc = (remq_n > 0) ? Q4::ld_nc(pbc_n) : Q4::zero();
-    };
-    auto advance_n = [&]() {
-      pu_n += (int64_t)kT * sgn * dp.u.sl * ES;
-      pdl_n += (int64_t)kT * sgn * dp.delta.sl * ES;
-      pbc_n += (int64_t)kT * sgn * bct.sl * ES;
-      rem_n -= kT;
-      remq_n -= kT;
-    };
-    // converts the raw registers (loaded with the `rem` in force at load time, passed here as remv)
-    auto convert_store = [&](int buf, int remv) {
 #pragma unroll
-      for (int i = 0; i < C::UPT; ++i) {
-        const int k = k0 + i * C::KSTRIDE;
-        const bool valid = remv > i * C::KSTRIDE;
+      for (int j = 0; j < kNBC; ++j) {
+        const int s = sb0 + kq + (kIO / 8) * j;
+        rbc[j] = (s < s_end) ? Q4::ld_nc(pbc + (int64_t)s * bc_ss) : Q4::zero();
+      }
+    };
+    auto convert_store = [&](int sb0, int slot) {
+#pragma unroll
+      for (int i = 0; i < kIU; ++i) {
+        const int k = k0 + i * kIKS;
         const float2 u2 = P2::cvt(ru[i]);
-        const float2 d2 = P2::cvt(rdl[i]);
-        float dt0 = d2.x + bias[0], dt1 = d2.y + bias[1];
-        if (softplus) { dt0 = softplus_fwd<PRECISE>(dt0); dt1 = softplus_fwd<PRECISE>(dt1); }
-        if (!valid) { dt0 = 0.f; dt1 = 0.f; }   // a = 1, input 0: the state passes through a missing step unchanged
-        uu[i] = u2;
-        float* row = &S.dd[buf][k][(2 * cp) / CPL][0];
-        if constexpr (CPL == 2) {
-          *reinterpret_cast<float4*>(row) = make_float4(dt0, dt1, dt0 * u2.x, dt1 * u2.y);
-        } else {
-          const int j = (2 * cp) % CPL;
-          *reinterpret_cast<float2*>(row + j) = make_float2(dt0, dt1);
-          *reinterpret_cast<float2*>(row + CPL + j) = make_float2(dt0 * u2.x, dt1 * u2.y);
-        }
+        float2 dt = fadd2(P2::cvt(rdl[i]), bias);
+        if (softplus) { dt.x = softplus_fwd<PRECISE>(dt.x); dt.y = softplus_fwd<PRECISE>(dt.y); }
+        if (sb0 + k >= s_end) dt = make_float2(0.f, 0.f);   // a = 1, input 0: a missing step leaves the state unchanged
+        const float2 du = fmul2(dt, u2);
+        S.dd[slot][k][cp] = make_float4(dt.x, dt.y, du.x, du.y);
       }
-      float v[4];
-      Q4::cvt(rbc, v);
-      float* dst = reinterpret_cast<float*>(&S.bc[buf][kq][q4]) + (part >> 2);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) dst[2 * i] = v[i];
+      for (int j = 0; j < kNBC; ++j) {
+        float v[4];
+        Q4::cvt(rbc[j], v);
+        *reinterpret_cast<float4*>(&S.bc[slot][kq + (kIO / 8) * j][bc_dst]) = make_float4(v[0], v[1], v[2], v[3]);
+      }
     };
-
-    load_raw();
-    convert_store(0, rem_n);
-    advance_n();
-    group_bar(DIR);
-
-    int rem_c = nst - k0;       // validity of the tile being finished
-#pragma unroll 1
-    for (int t = 0; t < ntile; ++t) {
-      const int buf = t & 1;
-      load_raw();               // tile t+1 (all-zero beyond the range)
-      // epilogue operands of this tile, in flight during the recurrence
-      typename P2::Raw rz[C::UPT], rst[C::UPT];
+    // epilogue operands (gate, partner's stash) of the tile starting at sb0
+    auto load_epi = [&](int sb0) {
 #pragma unroll
-      for (int i = 0; i < C::UPT; ++i) {
-        const bool v = rem_c > i * C::KSTRIDE;
-        rz[i] = (need_z && v) ? P2::ld_nc(pz_c + (int64_t)i * C::KSTRIDE * sgn * p.z.sl * ES) : P2::zero();
-        rst[i] = (need_st && v) ? P2::ld_cg(po_c + (int64_t)i * C::KSTRIDE * sgn * p.out.sl * ES) : P2::zero();
+      for (int i = 0; i < kIU; ++i) {
+        const int s = sb0 + k0 + i * kIKS;
+        const bool v = s < s_end;
+        rz[i] = (need_z && v) ? P2::ld_nc(pz + (int64_t)s * d.z_ss) : P2::zero();
+        rst[i] = (need_st && v) ? P2::ld_cg(po + (int64_t)s * d.out_ss) : P2::zero();
       }
-
-      // ---- recurrence over the tile: sub-blocks of kSub steps, operands of the next sub-block loaded while the
-      // dependent chain of the current one runs.  Missing steps of a last partial tile carry dt = 0 (identity).
-      const int nvalid = nst - t * kT;    // steps of this tile inside the range (may exceed kT)
-      {
-        const float* ddb = &S.dd[buf][0][g][0];
-        const float2* bcb = &S.bc[buf][0][n];
-        float* pb = &S.p[0][g][n * CPL];
-        constexpr int DDS = C::NG * 2 * CPL;      // floats per step in dd
-        constexpr int PS = C::NG * C::PROW;       // floats per step in p
-        float ddr[kSub][2 * CPL];
-        float2 bcr[kSub];
-        auto lds_sub = [&](int sb) {
+    };
+    // finishes tile (sb0, ring counter itf): skip term, stash / combine / gate, store
+    auto epilogue = [&](int sb0, int itf) {
+      const int slot = itf & 1;
+      mbar_wait(&S.p_full[slot], (itf >> 1) & 1);
+      float2 yv[kIU];
 #pragma unroll
-          for (int i = 0; i < kSub; ++i) {
-            const float* src = ddb + (sb * kSub + i) * DDS;
-            if constexpr (CPL == 2) {
-              const float4 v = *reinterpret_cast<const float4*>(src);
-              ddr[i][0] = v.x; ddr[i][1] = v.y; ddr[i][2] = v.z; ddr[i][3] = v.w;
-            } else {
-              const float4 v = *reinterpret_cast<const float4*>(src);
-              const float4 w = *reinterpret_cast<const float4*>(src + 4);
-              ddr[i][0] = v.x; ddr[i][1] = v.y; ddr[i][2] = v.z; ddr[i][3] = v.w;
-              ddr[i][4] = w.x; ddr[i][5] = w.y; ddr[i][6] = w.z; ddr[i][7] = w.w;
-            }
-            bcr[i] = bcb[(sb * kSub + i) * 16];
-          }
-        };
-        lds_sub(0);
+      for (int i = 0; i < kIU; ++i) yv[i] = S.y[slot][k0 + i * kIKS][cp];
+      warp_arrive(&S.p_empty[slot], lane);
 #pragma unroll
-        for (int sb = 0; sb < kT / kSub; ++sb) {
-          if (((sb * kSub) % CM_SCAN_CKPT_STEPS) == 0) {
-            if (ckp != nullptr && sb * kSub < nvalid) {
-              float* dst = ckp + (int64_t)jck * 16;
-#pragma unroll
-              for (int j = 0; j < CPL; ++j) dst[j * dp.ckpt_sd] = h[j];
-            }
-            ++jck;
-          }
-          // exponent arguments, decays and input products of the whole sub-block
-          float a[kSub][CPL], ub[kSub][CPL], cc[kSub];
-#pragma unroll
-          for (int i = 0; i < kSub; ++i) {
-#pragma unroll
-            for (int j = 0; j < CPL; j += 2) {
-              const float2 x = fmul2(make_float2(ddr[i][j], ddr[i][j + 1]), make_float2(kA[j], kA[j + 1]));
-              a[i][j] = x.x; a[i][j + 1] = x.y;
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < kSub; ++i) {
-#pragma unroll
-            for (int j = 0; j < CPL; ++j) a[i][j] = ex2(a[i][j]);
-          }
-#pragma unroll
-          for (int i = 0; i < kSub; ++i) {
-#pragma unroll
-            for (int j = 0; j < CPL; j += 2) {
-              const float2 w = fmul2(make_float2(ddr[i][CPL + j], ddr[i][CPL + j + 1]), make_float2(bcr[i].x, bcr[i].x));
-              ub[i][j] = w.x; ub[i][j + 1] = w.y;
-            }
-            cc[i] = bcr[i].y;
-          }
-          if (sb + 1 < kT / kSub) lds_sub(sb + 1);
-          // the dependent chain
-#pragma unroll
-          for (int i = 0; i < kSub; ++i) {
-            float pv[CPL];
-#pragma unroll
-            for (int j = 0; j < CPL; j += 2) {
-              const float2 hn = ffma2(make_float2(a[i][j], a[i][j + 1]), make_float2(h[j], h[j + 1]),
-                                      make_float2(ub[i][j], ub[i][j + 1]));
-              h[j] = hn.x; h[j + 1] = hn.y;
-              const float2 pp = fmul2(make_float2(cc[i], cc[i]), hn);
-              pv[j] = pp.x; pv[j + 1] = pp.y;
-            }
-            float* pr = pb + (sb * kSub + i) * PS;
-            if constexpr (CPL == 2) *reinterpret_cast<float2*>(pr) = make_float2(pv[0], pv[1]);
-            else *reinterpret_cast<float4*>(pr) = make_float4(pv[0], pv[1], pv[2], pv[3]);
-          }
-        }
-        // slots are counted per EXISTING checkpoint: undo the count of a slot whose step lies beyond the range
-        if (nvalid <= CM_SCAN_CKPT_STEPS) --jck;
-      }
-      group_bar(DIR);
-
-      // ---- epilogue: one (step, channel pair) per unit
-#pragma unroll
-      for (int i = 0; i < C::UPT; ++i) {
-        const int k = k0 + i * C::KSTRIDE;
-        float2 y;
-        {
-          // row of channel group (2cp)/CPL; this pair's products sit at [n*CPL + jj], jj = (2cp)%CPL + {0,1}
-          const float* row = &S.p[k][(2 * cp) / CPL][(2 * cp) % CPL];
-          float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-          if constexpr (CPL == 2) {
-            const float4* r = reinterpret_cast<const float4*>(row);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 v = r[q];
-              acc0 = fadd2(acc0, make_float2(v.x, v.y));
-              acc1 = fadd2(acc1, make_float2(v.z, v.w));
-            }
-          } else {
-#pragma unroll
-            for (int nn = 0; nn < 16; nn += 2) {
-              acc0 = fadd2(acc0, *reinterpret_cast<const float2*>(row + nn * CPL));
-              acc1 = fadd2(acc1, *reinterpret_cast<const float2*>(row + (nn + 1) * CPL));
-            }
-          }
-          y = fadd2(acc0, acc1);
-        }
-        y.x = fmaf(Dsk[0], uu[i].x, y.x);
-        y.y = fmaf(Dsk[1], uu[i].y, y.y);
-        if (rem_c > i * C::KSTRIDE) {
-          char* po = po_c + (int64_t)i * C::KSTRIDE * sgn * p.out.sl * ES;
+      for (int i = 0; i < kIU; ++i) {
+        const int s = sb0 + k0 + i * kIKS;
+        const float2 y = ffma2(Dsk, P2::cvt(uprev[i]), yv[i]);
+        if (s < s_end) {
+          char* dsto = po + (int64_t)s * d.out_ss;
           if (mode == FM_STASH) {
-            P2::st(po, y);
+            P2::st(dsto, y);
           } else {
-            const float2 stv = P2::cvt(rst[i]);
-            const float2 tot = make_float2(y.x + stv.x, y.y + stv.y);
-            float2 val = make_float2(tot.x * p.out_scale, tot.y * p.out_scale);
+            const float2 tot = fadd2(y, P2::cvt(rst[i]));
+            float2 val = fmul2(tot, make_float2(P.scale, P.scale));
             if (need_z) {
               const float2 zz = P2::cvt(rz[i]);
               val.x *= zz.x * sigmoid_sel<PRECISE>(zz.x);
               val.y *= zz.y * sigmoid_sel<PRECISE>(zz.y);
             }
-            if (ppre_c != nullptr) P2::st(ppre_c + (int64_t)i * C::KSTRIDE * sgn * p.out_pre.sl * ES, tot);
-            P2::st(po, val);
+            if (ppre != nullptr) P2::st(ppre + (int64_t)s * d.pre_ss, tot);
+            P2::st(dsto, val);
           }
         }
       }
-      // advance the finished-tile pointers
-      if (has_z) pz_c += (int64_t)kT * sgn * p.z.sl * ES;
-      po_c += (int64_t)kT * sgn * p.out.sl * ES;
-      if (ppre_c != nullptr) ppre_c += (int64_t)kT * sgn * p.out_pre.sl * ES;
-      rem_c -= kT;
-      convert_store(buf ^ 1, rem_n);   // tile t+1 (zeros past the end: harmless, never consumed)
-      advance_n();
-      group_bar(DIR);
-    }
-  }
+    };
 
-  if (dp.last_state != nullptr) {
-    float* ls = dp.last_state + b * dp.ls_sb + (int64_t)cs * dp.ls_sd + n * dp.ls_sn;
+    // every global load is issued one full iteration before its use
+    if (ntile > 0) load_raw(s_begin);
+#pragma unroll 1
+    for (int t = 0; t < ntile; ++t, ++it) {
+      const int slot = it & 1;
+      const int sb0 = s_begin + t * kT;
+      if (it >= 2) mbar_wait(&S.in_empty[slot], ((it >> 1) & 1) ^ 1);
+      convert_store(sb0, slot);
+      warp_arrive(&S.in_full[slot], lane);
+      typename P2::Raw ucur[kIU];
 #pragma unroll
-    for (int j = 0; j < CPL; ++j) ls[j * dp.ls_sd] = h[j];
+      for (int i = 0; i < kIU; ++i) ucur[i] = ru[i];
+      if (t + 1 < ntile) load_raw(sb0 + kT);
+      if (t > 0) epilogue(sb0 - kT, it - 1);      // uses uprev, rz, rst of tile t-1
+      load_epi(sb0);
+#pragma unroll
+      for (int i = 0; i < kIU; ++i) uprev[i] = ucur[i];
+    }
+    if (ntile > 0) epilogue(s_begin + (ntile - 1) * kT, it - 1);
   }
 }
 
-template <typename T, int CPL, int NDIR>
-__global__ void __launch_bounds__(NDIR* kGT, CM_FWDSP_MINB) scan_fwd_sp_kernel(const __grid_constant__ cm_scan_fwd_args p) {
+template <typename T, int NDIR>
+__global__ void __launch_bounds__(NDIR*(kGT + kIO), CM_FWDSP_MINB) scan_fwd_sp_kernel(const __grid_constant__ FwdParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  DirSmem<CPL>* S = reinterpret_cast<DirSmem<CPL>*>(smem_raw);
+  FwdSmem* S = reinterpret_cast<FwdSmem*>(smem_raw);
   const int tid = threadIdx.x;
-  if (NDIR == 1 || tid < kGT) run_dir<T, CPL, NDIR, 0>(p, S[0], tid);
-  else run_dir<T, CPL, NDIR, 1>(p, S[1], tid - kGT);
+  if (tid < NDIR) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&S[tid].in_full[i], kIO / 32);
+      mbar_init(&S[tid].in_empty[i], kNW);
+      mbar_init(&S[tid].p_full[i], kNW);
+      mbar_init(&S[tid].p_empty[i], kIO / 32);
+    }
+  }
+  __syncthreads();
+  // thread layout: [recurrence dir 0 | recurrence dir 1 | IO dir 0 | IO dir 1]
+  if (tid < NDIR * kGT) {
+    if (NDIR == 1 || tid < kGT) scan_role<T, NDIR, 0>(P, S[0], tid);
+    else scan_role<T, NDIR, 1>(P, S[1], tid - kGT);
+  } else {
+    const int io = tid - NDIR * kGT;
+    if (NDIR == 1 || io < kIO) io_role<T, NDIR, 0>(P, S[0], io);
+    else io_role<T, NDIR, 1>(P, S[1], io - kIO);
+  }
 }
 
 template <typename T>
@@ -463,66 +430,82 @@ static bool t_ok(const cm_tensor3& t, int64_t quantum) {
 }
 
 template <typename T>
-static bool fwd_sp_ok(const cm_scan_fwd_args& a, int cpl) {
-  const int ch = kNW * 2 * cpl;
-  if (a.dstate != 16 || a.dim % ch != 0) return false;
+static bool build_params(const cm_scan_fwd_args& a, FwdParams* P) {
+  constexpr int ES = (int)sizeof(T);
+  if (a.dstate != 16 || a.dim % kCH != 0) return false;
   if (!t_ok<T>(a.out, 2)) return false;
   if (a.z.ptr != nullptr && !t_ok<T>(a.z, 2)) return false;
   if (a.out_pre.ptr != nullptr && !t_ok<T>(a.out_pre, 2)) return false;
+  P->L = a.seqlen;
+  P->flags = a.flags;
+  P->scale = a.out_scale;
+  P->pad = 0;
   for (int r = 0; r < a.ndir; ++r) {
-    const cm_scan_dir& d = a.dir[r];
-    if (d.bc_const) return false;
-    if (!t_ok<T>(d.u, 2) || !t_ok<T>(d.delta, 2) || !t_ok<T>(d.Bm, 4) || !t_ok<T>(d.Cm, 4)) return false;
+    const cm_scan_dir& s = a.dir[r];
+    FwdDir& d = P->dir[r];
+    if (s.bc_const) return false;
+    if (!t_ok<T>(s.u, 2) || !t_ok<T>(s.delta, 2) || !t_ok<T>(s.Bm, 4) || !t_ok<T>(s.Cm, 4)) return false;
+    if (s.ckpt != nullptr && ((reinterpret_cast<uintptr_t>(s.ckpt) & 15) != 0 || (s.ckpt_sb % 4) != 0 || (s.ckpt_sd % 4) != 0))
+      return false;   // checkpoints are written as float4
+    const bool rev = s.reverse != 0;
+    const int64_t l0 = rev ? a.seqlen - 1 : 0;
+    auto bp = [&](const cm_tensor3& t) { return static_cast<char*>(t.ptr) + l0 * t.sl * ES; };
+    bool ok = true;
+    ok &= step_stride(s.u.sl, ES, rev, a.seqlen, &d.u_ss);
+    ok &= step_stride(s.delta.sl, ES, rev, a.seqlen, &d.dl_ss);
+    ok &= step_stride(s.Bm.sl, ES, rev, a.seqlen, &d.b_ss);
+    ok &= step_stride(s.Cm.sl, ES, rev, a.seqlen, &d.c_ss);
+    ok &= step_stride(a.out.sl, ES, rev, a.seqlen, &d.out_ss);
+    d.z_ss = d.pre_ss = 0;
+    if (a.z.ptr) ok &= step_stride(a.z.sl, ES, rev, a.seqlen, &d.z_ss);
+    if (a.out_pre.ptr) ok &= step_stride(a.out_pre.sl, ES, rev, a.seqlen, &d.pre_ss);
+    if (!ok) return false;
+    d.u = bp(s.u); d.dl = bp(s.delta); d.B = bp(s.Bm); d.C = bp(s.Cm);
+    d.z = a.z.ptr ? bp(a.z) : nullptr;
+    d.out = bp(a.out);
+    d.pre = a.out_pre.ptr ? bp(a.out_pre) : nullptr;
+    d.u_sb = s.u.sb * ES; d.dl_sb = s.delta.sb * ES; d.b_sb = s.Bm.sb * ES; d.c_sb = s.Cm.sb * ES;
+    d.z_sb = a.z.sb * ES; d.out_sb = a.out.sb * ES; d.pre_sb = a.out_pre.sb * ES;
+    d.s1 = cm_first_range(a.seqlen, a.ndir, s.reverse);
+    d.A = s.A; d.A_sd = s.A_sd; d.A_sn = s.A_sn;
+    d.Dskip = s.Dskip; d.bias = s.delta_bias;
+    d.ckpt = s.ckpt; d.ckpt_sb = s.ckpt_sb; d.ckpt_sd = s.ckpt_sd;
+    d.last = s.last_state; d.ls_sb = s.ls_sb; d.ls_sd = s.ls_sd; d.ls_sn = s.ls_sn;
   }
   return true;
 }
 
-template <typename T, int CPL, int NDIR>
-static int launch_one(const cm_scan_fwd_args& a, cudaStream_t st) {
-  const size_t smem = sizeof(DirSmem<CPL>) * NDIR;
-  auto kern = scan_fwd_sp_kernel<T, CPL, NDIR>;
+template <typename T, int NDIR>
+static int launch_one(const FwdParams& P, const cm_scan_fwd_args& a, cudaStream_t st) {
+  const size_t smem = sizeof(FwdSmem) * NDIR;
+  auto kern = scan_fwd_sp_kernel<T, NDIR>;
   static bool attr_done = false;   // idempotent attribute; a benign race sets it twice
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  kern<<<dim3(a.dim / Cfg<CPL>::CH, a.batch), NDIR * kGT, smem, st>>>(a);
+  kern<<<dim3(a.dim / kCH, a.batch), NDIR * (kGT + kIO), smem, st>>>(P);
   CM_LAUNCH_CHECK();
   return 0;
 }
 
 template <typename T>
-static int launch_t(const cm_scan_fwd_args& a, int cpl, cudaStream_t st) {
-  if (a.ndir == 2) {
-    if (cpl == 2) return launch_one<T, 2, 2>(a, st);
-    return launch_one<T, 4, 2>(a, st);
-  }
-  if (cpl == 2) return launch_one<T, 2, 1>(a, st);
-  return launch_one<T, 4, 1>(a, st);
+static int try_t(const cm_scan_fwd_args& a, cudaStream_t st, int* rc) {
+  FwdParams P;
+  if (!build_params<T>(a, &P)) return 0;
+  *rc = (a.ndir == 2) ? launch_one<T, 2>(P, a, st) : launch_one<T, 1>(P, a, st);
+  return 1;
 }
 
 }  // namespace sp
 
 // returns 1 if launched (result in *rc), 0 if the state-parallel path does not apply
 int scan_fwd_try_state_parallel(const cm_scan_fwd_args& a, cudaStream_t st, int* rc) {
-  int cpl = 2;
-  if (const char* e = getenv("CM_SP_CPL")) cpl = atoi(e);   // A/B measurements only
-  if (cpl != 2 && cpl != 4) cpl = 2;
-  while (cpl > 2 && a.dim % (sp::kNW * 2 * cpl) != 0) cpl >>= 1;
   switch (a.dtype) {
-    case CM_F32:
-      if (!sp::fwd_sp_ok<float>(a, cpl)) return 0;
-      *rc = sp::launch_t<float>(a, cpl, st);
-      return 1;
-    case CM_BF16:
-      if (!sp::fwd_sp_ok<__nv_bfloat16>(a, cpl)) return 0;
-      *rc = sp::launch_t<__nv_bfloat16>(a, cpl, st);
-      return 1;
-    default:
-      if (!sp::fwd_sp_ok<__half>(a, cpl)) return 0;
-      *rc = sp::launch_t<__half>(a, cpl, st);
-      return 1;
+    case CM_F32: return sp::try_t<float>(a, st, rc);
+    case CM_BF16: return sp::try_t<__nv_bfloat16>(a, st, rc);
+    default: return sp::try_t<__half>(a, st, rc);
   }
 }
 

@@ -459,14 +459,16 @@ extern "C" int cm_reduce_multi(const cm_reduce_job* jobs, int32_t njobs, void* s
 
 namespace cm {
 int scan_bwd_try_channel_last(const cm_scan_bwd_args& a, int lpc, cudaStream_t st, int* rc);   // scan_bwd_cl.cu
+int scan_bwd_try_state_parallel(const cm_scan_bwd_args& a, cudaStream_t st, int* rc);            // scan_bwd_sp.cu
 }
 
 extern "C" int cm_scan_pick_lanes_bwd(int32_t batch, int32_t dim, int32_t ndir) {
-  // Measured on B200 (tools/prof_kernels.py): with one lane per channel the backward kernel holds 16 states, 16
-  // adjoints and 16 dA sums per lane (230+ registers, 32 KB shared memory per warp -> 7 warps / SM); two lanes per
-  // channel run 12 warps / SM and are 10-15 % faster from 32 x 288 up to 64 x 1024 channels.
-  const int fwd = cm_scan_pick_lanes(batch, dim, ndir);
-  return fwd < 2 ? 2 : fwd;
+  // The default backward kernel (scan_bwd_sp.cu) reduces dB/dC over 32-channel slabs = cm_scan_slab_channels(1).
+  // Callers size the partial tensor from this value; when the state-parallel kernel does not apply (strided layout,
+  // dim % 32 != 0, constant B/C) the lane-per-channel kernels run with the same slab width.  (Measured on B200: for
+  // those kernels 2 lanes per channel are 10-15 % faster; pass lanes_per_channel = 2 explicitly to get that.)
+  (void)batch; (void)dim; (void)ndir;
+  return 1;
 }
 
 extern "C" int cm_scan_bwd(const cm_scan_bwd_args* args, void* stream) {
@@ -491,6 +493,10 @@ extern "C" int cm_scan_bwd(const cm_scan_bwd_args* args, void* stream) {
   if (lpc != 1 && lpc != 2 && lpc != 4) return CM_ERR_BAD_ARG;
   const bool bcc = a.dir[0].in.bc_const != 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (getenv("CM_SCAN_GENERIC") == nullptr && getenv("CM_SCAN_NO_SP") == nullptr && lpc == 1) {
+    int rc = 0;
+    if (cm::scan_bwd_try_state_parallel(a, st, &rc)) return rc;
+  }
   if (getenv("CM_SCAN_GENERIC") == nullptr) {   // env switch only for A/B measurements of the two kernels
     int rc = 0;
     if (cm::scan_bwd_try_channel_last(a, lpc, st, &rc)) return rc;

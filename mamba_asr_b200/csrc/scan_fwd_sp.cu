@@ -78,10 +78,10 @@ struct FwdSmem {
 enum { FM_UNI = 0, FM_STASH = 1, FM_COMBINE = 2 };
 
 #ifndef CM_FWDSP_MINB
-#define CM_FWDSP_MINB 2
+#define CM_FWDSP_MINB 3
 #endif
 #ifndef CM_FWDSP_SUB
-#define CM_FWDSP_SUB 2
+#define CM_FWDSP_SUB 1
 #endif
 constexpr int kSub = CM_FWDSP_SUB;   // steps per software-pipelined sub-block of the recurrence
 

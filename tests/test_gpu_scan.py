@@ -248,3 +248,75 @@ def test_state_parallel_forward_matches_oracle(cpl, dtype, shape, monkeypatch):
     for r in range(2):
         assert_close(bi["ckpt"][r][:, :, :nck2], bi_o["ckpt"][r][:, :, :nck2], dtype, floor="max", what="sp ckpt bidir")
     assert_close(bi["out_pre"].float(), bi_o["out_pre"].float(), dtype, floor="max", what="sp out_pre")
+
+
+def _bidir_backward_case(Bt, D, L, dtype, seed):
+    from mamba_asr_b200 import kernels as K
+    N = 16
+    f = make_scan_inputs(Bt, D, L, N, dtype, seed=seed)
+    bw = make_scan_inputs(Bt, D, L, N, dtype, seed=seed + 1)
+    dirs = []
+    for src, rev in ((f, False), (bw, True)):
+        c = _cuda(src, "cl")
+        dirs.append(dict(u=c["u"], delta=c["delta"], A=c["A"], B=c["B"], C=c["C"], D=c["D"],
+                         delta_bias=c["delta_bias"], reverse=rev))
+    zc = channel_last(f["z"].cuda())
+    cot = torch.randn((Bt, D, L), generator=torch.Generator().manual_seed(seed + 2)).to(dtype)
+    return K, f, bw, dirs, zc, cot
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 45), (1, 32, 8), (2, 32, 9), (1, 32, 1), (2, 64, 17), (1, 96, 67), (2, 32, 16)])
+def test_state_parallel_backward_matches_autograd(shape):
+    """scan_bwd_sp.cu (the default channel-last backward): every gradient of the fused bidirectional block and of a
+    unidirectional scan against autograd through the oracle, fp32, over ragged lengths and tile boundaries."""
+    from oracle.scan_ref import selective_scan_oracle
+    Bt, D, L = shape
+    K, f, bw, dirs, zc, cot = _bidir_backward_case(Bt, D, L, torch.float32, seed=41)
+    lf = {k: v.clone().requires_grad_(True) for k, v in f.items()}
+    lb = {k: v.clone().requires_grad_(True) for k, v in bw.items() if k != "z"}
+    fl = lambda t: t.flip(-1)
+    of = selective_scan_oracle(lf["u"], lf["delta"], lf["A"], lf["B"], lf["C"], lf["D"], lf["z"], lf["delta_bias"], True)
+    ob = selective_scan_oracle(fl(lb["u"]), fl(lb["delta"]), lb["A"], fl(lb["B"]), fl(lb["C"]), lb["D"], fl(lf["z"]),
+                               lb["delta_bias"], True)
+    ((0.5 * of + 0.5 * fl(ob)) * cot).sum().backward()
+    res = K.scan_forward(dirs, z=zc, out_scale=0.5, delta_softplus=True, need_ckpt=True, need_out_pre=True)
+    g = K.scan_backward(dirs, res["ckpt"], channel_last(cot.cuda()), z=zc, out_pre=res["out_pre"], out_scale=0.5,
+                        delta_softplus=True)
+    assert_close(g["dz"], lf["z"].grad, what="dz")
+    for r, leaf in enumerate((lf, lb)):
+        assert_close(g["du"][r], leaf["u"].grad, what=f"du[{r}]")
+        assert_close(g["ddelta"][r], leaf["delta"].grad, what=f"ddelta[{r}]")
+        assert_close(g["dB"][r], leaf["B"].grad, floor="max", what=f"dB[{r}]")
+        assert_close(g["dC"][r], leaf["C"].grad, floor="max", what=f"dC[{r}]")
+        assert_close(g["dA"][r], leaf["A"].grad, floor="max", what=f"dA[{r}]")
+        assert_close(g["dD"][r], leaf["D"].grad, floor="max", what=f"dD[{r}]")
+        assert_close(g["dbias"][r], leaf["delta_bias"].grad, floor="max", what=f"dbias[{r}]")
+    # unidirectional, no gate, no softplus
+    lu = {k: v.clone().requires_grad_(True) for k, v in f.items() if k != "z"}
+    ou = selective_scan_oracle(lu["u"], lu["delta"], lu["A"], lu["B"], lu["C"], lu["D"], None, lu["delta_bias"], False)
+    (ou * cot).sum().backward()
+    r1 = K.scan_forward(dirs[:1], delta_softplus=False, need_ckpt=True)
+    g1 = K.scan_backward(dirs[:1], r1["ckpt"], channel_last(cot.cuda()), delta_softplus=False)
+    assert_close(g1["du"][0], lu["u"].grad, what="uni du")
+    assert_close(g1["ddelta"][0], lu["delta"].grad, what="uni ddelta")
+    assert_close(g1["dB"][0], lu["B"].grad, floor="max", what="uni dB")
+    assert_close(g1["dC"][0], lu["C"].grad, floor="max", what="uni dC")
+    if L > 1:   # L == 1: dA is exactly 0 in the reference (h_{-1} = 0); the kernel's a*h_{-1} = h_0 - du*B leaves rounding noise
+        assert_close(g1["dA"][0], lu["A"].grad, floor="max", what="uni dA")
+
+
+def test_state_parallel_backward_bf16_matches_lane_per_channel_kernel(monkeypatch):
+    """bf16 I/O: the two backward kernels see the same rounded inputs; they must agree to bf16 rounding of the outputs."""
+    K, f, bw, dirs, zc, cot = _bidir_backward_case(3, 96, 203, torch.bfloat16, seed=51)
+    res = K.scan_forward(dirs, z=zc, out_scale=0.5, delta_softplus=True, need_ckpt=True, need_out_pre=True)
+    run = lambda: K.scan_backward(dirs, res["ckpt"], channel_last(cot.cuda()), z=zc, out_pre=res["out_pre"], out_scale=0.5,
+                                  delta_softplus=True)
+    g_sp = run()
+    monkeypatch.setenv("CM_SCAN_NO_SP", "1")
+    g_old = run()
+    assert_close(g_sp["dz"].float(), g_old["dz"].float(), torch.bfloat16, what="dz")
+    for r in range(2):
+        for key in ("du", "ddelta"):
+            assert_close(g_sp[key][r].float(), g_old[key][r].float(), torch.bfloat16, what=f"{key}[{r}]")
+        for key in ("dB", "dC", "dA", "dD", "dbias"):
+            assert_close(g_sp[key][r].float(), g_old[key][r].float(), torch.bfloat16, floor="max", what=f"{key}[{r}]")

@@ -30,12 +30,16 @@ namespace spb {
 using namespace cm::sp;
 
 #ifndef CM_BWDSP_MINB
-#define CM_BWDSP_MINB 3
+#define CM_BWDSP_MINB 4
 #endif
 #ifndef CM_BWDSP_UNROLL
 #define CM_BWDSP_UNROLL 2
 #endif
 constexpr int kUnr = CM_BWDSP_UNROLL;
+#ifndef CM_BWDSP_HREG
+#define CM_BWDSP_HREG 4
+#endif
+constexpr int kHR = CM_BWDSP_HREG;        // last kHR steps of a tile keep their recomputed states in registers, the rest in smem
 constexpr int kTB = CM_SCAN_CKPT_STEPS;   // steps per tile (8)
 constexpr int kIO = 64;                   // IO threads (2 warps)
 constexpr int kIU = kTB * kNP / kIO;      // (step, pair) units per IO thread and tile (2)
@@ -71,7 +75,7 @@ struct BwdSmem {
   float4 dd[2][kTB][kNP];        // (dt0, dt1, du0, du1)                              [operand ring, 2 tiles]
   float2 dy[2][kTB][kNP];        // gated output gradient of the pair
   float bc[2][kTB][32];          // B[0..15] | C[0..15]
-  float4 hs[kNW][kTB][2][32];    // recomputed states of the tile in flight (warp-private): [channel][lane]
+  float4 hs[kNW][kTB - kHR > 0 ? kTB - kHR : 1][2][32];   // recomputed states of the first steps of the tile in flight
   float4 pb[kNW][kTB][2][8][4];  // per-lane dB[4] (0) and dC[4] (1)                 (warp-private)
   float4 pr[kNW][kTB][8][4];     // per-lane (r1_0, r1_1, r2_0, r2_1)                (warp-private)
   float4 r[2][kTB][kNP];         // sums over states                                 [result ring, 2 tiles]
@@ -149,7 +153,6 @@ __device__ __forceinline__ void scan_role(const BwdParams& P, BwdSmem& S, const 
   const float* ckp = d.ckpt + b * d.ckpt_sb + (int64_t)c0 * d.ckpt_sd + 4 * m;
   const TileSeq seq(P.L, P.ndir, d.s1);
   const int ntot = seq.total();
-  float4 (*hs)[2][32] = S.hs[warp];
 
   int sb0, s_end, cslot;
   float4 ck0, ck1;
@@ -172,8 +175,11 @@ __device__ __forceinline__ void scan_role(const BwdParams& P, BwdSmem& S, const 
     const float4* ddb = &S.dd[slot][0][pr];
     const float2* dyb = &S.dy[slot][0][pr];
     const float* bcb = &S.bc[slot][0][4 * m];
-    // ---- forward: recompute and park the states of the tile
-#pragma unroll kUnr
+    // ---- forward: recompute the states of the tile.  The history of the last kHR steps stays in registers, the first
+    // steps are parked in shared memory (all 8 in shared memory cost 16 of the 86 LSU wavefronts per warp-step that bound
+    // the first version of this kernel; all 8 in registers spill)
+    float2 hist[kHR > 0 ? kHR : 1][4];
+#pragma unroll
     for (int k = 0; k < kTB; ++k) {
       const float4 dd = ddb[k * kNP];
       const float4 bb = *reinterpret_cast<const float4*>(bcb + k * 32);
@@ -185,20 +191,34 @@ __device__ __forceinline__ void scan_role(const BwdParams& P, BwdSmem& S, const 
         const float2 a = make_float2(ex2(x.x), ex2(x.y));
         h[j] = ffma2(a, h[j], fmul2(du, make_float2(b4[j], b4[j])));
       }
-      hs[k][0][lane] = make_float4(h[0].x, h[1].x, h[2].x, h[3].x);
-      hs[k][1][lane] = make_float4(h[0].y, h[1].y, h[2].y, h[3].y);
+      if (k >= kTB - kHR) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hist[k - (kTB - kHR)][j] = h[j];
+      } else {
+        S.hs[warp][k][0][lane] = make_float4(h[0].x, h[1].x, h[2].x, h[3].x);
+        S.hs[warp][k][1][lane] = make_float4(h[0].y, h[1].y, h[2].y, h[3].y);
+      }
     }
     // ---- reverse sweep
-#pragma unroll kUnr
+#pragma unroll
     for (int k = kTB - 1; k >= 0; --k) {
+      if ((k % kUnr) == kUnr - 1) asm volatile("" ::: "memory");   // scheduling fence: bounds how far ptxas hoists the
+                                                                  // operand loads of later steps (register pressure)
       const float4 dd = ddb[k * kNP];
       const float2 dy = dyb[k * kNP];
       const float4 bb = *reinterpret_cast<const float4*>(bcb + k * 32);
       const float4 cc = *reinterpret_cast<const float4*>(bcb + k * 32 + 16);
-      const float4 hx = hs[k][0][lane], hy = hs[k][1][lane];
       const float2 dt = make_float2(dd.x, dd.y), du = make_float2(dd.z, dd.w);
       const float b4[4] = {bb.x, bb.y, bb.z, bb.w}, c4[4] = {cc.x, cc.y, cc.z, cc.w};
-      const float2 hk[4] = {make_float2(hx.x, hy.x), make_float2(hx.y, hy.y), make_float2(hx.z, hy.z), make_float2(hx.w, hy.w)};
+      float2 hk[4];
+      if (k >= kTB - kHR) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hk[j] = hist[k - (kTB - kHR)][j];
+      } else {
+        const float4 hx = S.hs[warp][k][0][lane], hy = S.hs[warp][k][1][lane];
+        hk[0] = make_float2(hx.x, hy.x); hk[1] = make_float2(hx.y, hy.y);
+        hk[2] = make_float2(hx.z, hy.z); hk[3] = make_float2(hx.w, hy.w);
+      }
       float dBv[4], dCv[4];
       float2 r1 = make_float2(0.f, 0.f), r2 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -229,23 +249,28 @@ __device__ __forceinline__ void scan_role(const BwdParams& P, BwdSmem& S, const 
     for (int jj = 0; jj < 2; ++jj) {
       const int ui = lane + 32 * jj;          // = k * 8 + g
       const float4* src = &S.pr[warp][0][0][0] + ui * 4;
-      const float4 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3];
-      S.r[slot][ui >> 3][warp * 8 + (ui & 7)] =
-          make_float4((v0.x + v1.x) + (v2.x + v3.x), (v0.y + v1.y) + (v2.y + v3.y), (v0.z + v1.z) + (v2.z + v3.z),
-                      (v0.w + v1.w) + (v2.w + v3.w));
+      const int rot = ui >> 1;                // lanes 64 B apart: a rotated start keeps the 8 lanes of a phase on 8 bank groups
+      const float4 v0 = src[rot & 3], v1 = src[(rot + 1) & 3], v2 = src[(rot + 2) & 3], v3 = src[(rot + 3) & 3];
+      const float2 s0 = fadd2(fadd2(make_float2(v0.x, v0.y), make_float2(v1.x, v1.y)),
+                              fadd2(make_float2(v2.x, v2.y), make_float2(v3.x, v3.y)));
+      const float2 s1 = fadd2(fadd2(make_float2(v0.z, v0.w), make_float2(v1.z, v1.w)),
+                              fadd2(make_float2(v2.z, v2.w), make_float2(v3.z, v3.w)));
+      S.r[slot][ui >> 3][warp * 8 + (ui & 7)] = make_float4(s0.x, s0.y, s1.x, s1.y);
     }
     // (step, lane-in-pair, dB|dC) -> sum over the warp's 8 pairs: 64 float4 outputs, 2 per lane
 #pragma unroll
     for (int jj = 0; jj < 2; ++jj) {
       const int oi = lane + 32 * jj;          // = k * 8 + mm * 2 + which
       const int k = oi >> 3, mm = (oi >> 1) & 3, which = oi & 1;
-      float4 acc = S.pb[warp][k][which][0][mm];
+      // the dB and dC lanes of a phase start on different halves of the 8 pairs (bank groups 4*gg + mm)
+      float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int gg = 1; gg < 8; ++gg) {
-        const float4 v = S.pb[warp][k][which][gg][mm];
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      for (int gg = 0; gg < 8; ++gg) {
+        const float4 v = S.pb[warp][k][which][gg ^ which][mm];
+        a0 = fadd2(a0, make_float2(v.x, v.y));
+        a1 = fadd2(a1, make_float2(v.z, v.w));
       }
-      *reinterpret_cast<float4*>(&S.bcw[slot][warp][k][which * 16 + 4 * mm]) = acc;
+      *reinterpret_cast<float4*>(&S.bcw[slot][warp][k][which * 16 + 4 * mm]) = make_float4(a0.x, a0.y, a1.x, a1.y);
     }
     __syncwarp();
     if (lane == 0) {

@@ -20,6 +20,7 @@ import torch.nn as nn
 
 from .bimamba import Mamba as BiMamba
 from .bimamba import UniMamba as Mamba
+from .layernorm import FusedLayerNorm
 
 LAYER_NORM_EPS = 1e-6        # reference ConMambaConstants.LAYER_NORM_EPS (Conmamba.py:687)
 FFN_RESIDUAL_SCALE = 0.5     # reference ConMambaConstants.FFN_RESIDUAL_SCALE (Conmamba.py:638,649)
@@ -39,9 +40,9 @@ class Swish(nn.Module):
 class LayerNorm(nn.Module):
     """speechbrain.nnet.normalization.LayerNorm over the last dimension (parameters under ``.norm``)."""
 
-    def __init__(self, input_size, eps=1e-05, elementwise_affine=True):
+    def __init__(self, input_size, eps=1e-05, elementwise_affine=True, keep_dtype=False):
         super().__init__()
-        self.norm = nn.LayerNorm(input_size, eps=eps, elementwise_affine=elementwise_affine)
+        self.norm = FusedLayerNorm(input_size, eps=eps, elementwise_affine=elementwise_affine, keep_dtype=keep_dtype)
 
     def forward(self, x):
         return self.norm(x)
@@ -70,12 +71,12 @@ class ConvolutionModule(nn.Module):
         self.dilation = dilation
         full = (kernel_size - 1) * 2 ** (dilation - 1)
         self.padding = full if causal else full // 2
-        self.layer_norm = nn.LayerNorm(input_size)
+        self.layer_norm = FusedLayerNorm(input_size)
         self.bottleneck = nn.Sequential(nn.Conv1d(input_size, 2 * input_size, kernel_size=1, stride=1, bias=bias),
                                         nn.GLU(dim=1))
         self.conv = nn.Conv1d(input_size, input_size, kernel_size=kernel_size, stride=1, padding=self.padding,
                               dilation=dilation, groups=input_size, bias=bias)
-        self.after_conv = nn.Sequential(nn.LayerNorm(input_size), activation(), nn.Linear(input_size, input_size, bias=bias),
+        self.after_conv = nn.Sequential(FusedLayerNorm(input_size), activation(), nn.Linear(input_size, input_size, bias=bias),
                                         nn.Dropout(dropout))
 
     def forward(self, x, mask: Optional[torch.Tensor] = None, dynchunktrain_config=None):
@@ -110,16 +111,16 @@ class ConmambaEncoderLayer(nn.Module):
         super().__init__()
         self.mamba = _make_mixer(d_model, mamba_config, bidirectional_ok=not causal)
         self.convolution_module = ConvolutionModule(d_model, kernel_size, bias, activation, dropout, causal=causal)
-        self.ffn_module1 = nn.Sequential(nn.LayerNorm(d_model),
+        self.ffn_module1 = nn.Sequential(FusedLayerNorm(d_model),
                                          PositionalwiseFeedForward(d_ffn=d_ffn, input_size=d_model, dropout=dropout,
                                                                    activation=activation),
                                          nn.Dropout(dropout))
-        self.ffn_module2 = nn.Sequential(nn.LayerNorm(d_model),
+        self.ffn_module2 = nn.Sequential(FusedLayerNorm(d_model),
                                          PositionalwiseFeedForward(d_ffn=d_ffn, input_size=d_model, dropout=dropout,
                                                                    activation=activation),
                                          nn.Dropout(dropout))
         self.norm1 = LayerNorm(d_model)
-        self.norm2 = LayerNorm(d_model)
+        self.norm2 = LayerNorm(d_model, keep_dtype=True)      # its output is the residual stream of the next layer
         self.drop = nn.Dropout(dropout)
 
     def forward(self, x, src_mask: Optional[torch.Tensor] = None, src_key_padding_mask: Optional[torch.Tensor] = None,
@@ -145,7 +146,7 @@ class ConmambaEncoder(nn.Module):
             ConmambaEncoderLayer(d_model=d_model, d_ffn=d_ffn, dropout=dropout, activation=activation,
                                  kernel_size=kernel_size, bias=bias, causal=causal, mamba_config=mamba_config)
             for _ in range(num_layers)])
-        self.norm = LayerNorm(d_model, eps=LAYER_NORM_EPS)
+        self.norm = LayerNorm(d_model, eps=LAYER_NORM_EPS, keep_dtype=True)
 
     def forward(self, src, src_mask: Optional[torch.Tensor] = None, src_key_padding_mask: Optional[torch.Tensor] = None,
                 pos_embs: Optional[torch.Tensor] = None, dynchunktrain_config=None):

@@ -421,3 +421,56 @@ def fbank_logmel(stft, fbank, top_db=80.0, amin=1e-10, multiplier=10.0, db_offse
     _call("cm_fbank_logmel", lib.cm_fbank_logmel, C.byref(a), st)
     _call("cm_fbank_floor", lib.cm_fbank_floor, C.byref(a), st)
     return out
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+def layernorm_forward(x2d, weight, bias, eps, out_dtype):
+    """cm_layernorm_fwd over the rows of a (rows, C) CUDA tensor with unit column stride.
+    Returns (y (rows, C) in out_dtype, mean (rows,) fp32, rstd (rows,) fp32)."""
+    lib = cabi.lib()
+    _require_cuda(x2d, "x")
+    rows, Cn = x2d.shape
+    if x2d.stride(1) != 1:
+        raise ValueError("layernorm: the normalised dimension must be contiguous")
+    y = torch.empty((rows, Cn), dtype=out_dtype, device=x2d.device)
+    mean = torch.empty((rows,), dtype=torch.float32, device=x2d.device)
+    rstd = torch.empty((rows,), dtype=torch.float32, device=x2d.device)
+    a = cabi.LayerNormArgs()
+    a.rows, a.cols = rows, Cn
+    a.x_dtype, a.y_dtype = cabi.dtype_code(x2d.dtype), cabi.dtype_code(out_dtype)
+    a.eps = float(eps)
+    a.x, a.x_stride = x2d.data_ptr(), x2d.stride(0)
+    a.y, a.y_stride = y.data_ptr(), y.stride(0)
+    a.gamma, a.beta = cabi.ptr(weight), cabi.ptr(bias)
+    a.mean, a.rstd = mean.data_ptr(), rstd.data_ptr()
+    _call("cm_layernorm_fwd", lib.cm_layernorm_fwd, C.byref(a), cabi.stream_ptr())
+    return y, mean, rstd
+
+
+def layernorm_backward(x2d, dy2d, weight, mean, rstd, need_wgrad=True):
+    """cm_layernorm_bwd + deterministic reduction of the per-CTA dgamma / dbeta partial rows.
+    Returns (dx in x's dtype, dgamma fp32 (C,), dbeta fp32 (C,))."""
+    lib = cabi.lib()
+    rows, Cn = x2d.shape
+    if dy2d.stride(1) != 1:
+        dy2d = dy2d.contiguous()
+    dx = torch.empty((rows, Cn), dtype=x2d.dtype, device=x2d.device)
+    n_part = lib.cm_layernorm_num_part(rows)
+    dg_part = torch.empty((n_part, Cn), dtype=torch.float32, device=x2d.device)
+    db_part = torch.empty((n_part, Cn), dtype=torch.float32, device=x2d.device)
+    a = cabi.LayerNormArgs()
+    a.rows, a.cols = rows, Cn
+    a.x_dtype, a.y_dtype = cabi.dtype_code(x2d.dtype), cabi.dtype_code(dy2d.dtype)
+    a.x, a.x_stride = x2d.data_ptr(), x2d.stride(0)
+    a.gamma = cabi.ptr(weight)
+    a.mean, a.rstd = mean.data_ptr(), rstd.data_ptr()
+    a.dy, a.dy_stride = dy2d.data_ptr(), dy2d.stride(0)
+    a.dx, a.dx_stride = dx.data_ptr(), dx.stride(0)
+    a.dgamma_part, a.dbeta_part = dg_part.data_ptr(), db_part.data_ptr()
+    _call("cm_layernorm_bwd", lib.cm_layernorm_bwd, C.byref(a), cabi.stream_ptr())
+    if not need_wgrad:
+        return dx, None, None
+    dg = torch.empty((Cn,), dtype=torch.float32, device=x2d.device)
+    db = torch.empty((Cn,), dtype=torch.float32, device=x2d.device)
+    reduce_many([(dg_part, dg), (db_part, db)])
+    return dx, dg, db

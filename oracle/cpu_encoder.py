@@ -38,7 +38,11 @@ class OracleFbank(nn.Module):
 
 def to_cpu_reference(model, n_fft, n_mels, win_length_ms):
     """In-place: swap the sm_100a mixers / Fbank of a ``ConMambaCTC`` (built on CPU) for the oracle versions."""
+    from mamba_asr_b200.layernorm import FusedLayerNorm
     for layer in model.encoder.layers:
         layer.mamba = OracleBiMamba(layer.mamba)
+    for mod in model.modules():                  # the sm_100a LayerNorm has no CPU path: torch's own op on the CPU arm
+        if isinstance(mod, FusedLayerNorm):
+            mod.__class__ = nn.LayerNorm
     model.compute_features = OracleFbank(n_fft, n_mels, win_length_ms)
     return model

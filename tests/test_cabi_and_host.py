@@ -66,7 +66,9 @@ def test_checkpoint_and_partial_counts_follow_the_documented_formulas(lib):
         assert lib.cm_conv_num_part(3, L) == 3 * -(-L // 64)
     assert [lib.cm_scan_slab_channels(x) for x in (1, 2, 4)] == [32, 16, 8]
     assert lib.cm_scan_pick_lanes(64, 512, 2) == 1 and lib.cm_scan_pick_lanes(4, 512, 2) == 4
-    assert lib.cm_scan_pick_lanes_bwd(64, 512, 2) == 2 and lib.cm_scan_pick_lanes_bwd(4, 512, 2) == 4
+    # backward: 32-channel dB/dC slabs (the state-parallel kernel's CTA width) at every shape
+    assert lib.cm_scan_pick_lanes_bwd(64, 512, 2) == 1 and lib.cm_scan_pick_lanes_bwd(4, 512, 2) == 1
+    assert lib.cm_layernorm_num_part(8) == 1 and lib.cm_layernorm_num_part(10 ** 6) == 148 * 4
 
 
 def test_mamba_module_keeps_reference_state_dict_layout(golden_dir):

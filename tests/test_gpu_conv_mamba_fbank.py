@@ -250,3 +250,49 @@ def test_fbank_frame_count_is_bit_exact():
     fb = Fbank(n_fft=400, n_mels=80).cuda()
     for n in (16000, 159999, 160000, 160001, 240000):
         assert fb(torch.zeros(1, n, device="cuda")).shape[1] == fbank_frames(n)
+
+
+@pytest.mark.parametrize("shape", [(4, 37, 144), (2, 501, 256), (3, 5, 33), (1, 1, 512), (2, 9, 1024)])
+@pytest.mark.parametrize("dtypes", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16),
+                                    (torch.float32, torch.bfloat16), (torch.bfloat16, torch.float32)])
+def test_layernorm_matches_torch_fp32_reference(shape, dtypes):
+    """cm_layernorm_fwd / cm_layernorm_bwd against F.layer_norm evaluated in fp32 on the same (rounded) inputs:
+    output, dx, dgamma, dbeta.  Tolerance: fp32 1e-4, bf16 2e-2 (BASELINE.json)."""
+    import torch.nn.functional as F
+    from mamba_asr_b200.layernorm import layer_norm
+    xd, yd = dtypes
+    g = torch.Generator().manual_seed(3)
+    Cn = shape[-1]
+    x = (torch.randn(*shape, generator=g) * 2 + 0.5).to(xd).cuda()
+    w = (1 + 0.1 * torch.randn(Cn, generator=g)).cuda()
+    b = (0.1 * torch.randn(Cn, generator=g)).cuda()
+    cot = torch.randn(*shape, generator=g).to(yd).cuda()
+    xr = x.float().clone().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.layer_norm(xr, (Cn,), wr, br, 1e-5)
+    (ref * cot.float()).sum().backward()
+    xk = x.clone().requires_grad_(True)
+    wk, bk = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    out = layer_norm(xk, wk, bk, 1e-5, out_dtype=yd)
+    assert out.dtype == yd and out.shape == x.shape
+    (out.float() * cot.float()).sum().backward()
+    assert_close(out.float(), ref, yd, what="ln out")
+    assert xk.grad.dtype == xd
+    assert_close(xk.grad.float(), xr.grad, xd, what="ln dx")
+    tol_dt = torch.float32 if (xd == torch.float32 and yd == torch.float32) else torch.bfloat16
+    assert_close(wk.grad, wr.grad, tol_dt, floor="max", what="ln dgamma")
+    assert_close(bk.grad, br.grad, tol_dt, floor="max", what="ln dbeta")
+
+
+def test_layernorm_module_follows_autocast_and_has_no_cpu_path():
+    from mamba_asr_b200.layernorm import FusedLayerNorm
+    ln = FusedLayerNorm(144).cuda()
+    keep = FusedLayerNorm(144, keep_dtype=True).cuda()
+    x = torch.randn(2, 7, 144, device="cuda")
+    assert ln(x).dtype == torch.float32
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        assert ln(x).dtype == torch.bfloat16
+        assert keep(x.bfloat16()).dtype == torch.float32      # torch's autocast rule for layer_norm
+    assert sorted(ln.state_dict().keys()) == ["bias", "weight"]
+    with pytest.raises(RuntimeError):
+        FusedLayerNorm(144)(torch.randn(2, 144))

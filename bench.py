@@ -242,7 +242,9 @@ def main():
     model.train()
     net = model
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])
+        from mamba_asr_b200.dist_utils import allreduce_gradients
+        for p_ in model.parameters():                          # identical replicas: rank 0's initialisation
+            dist.broadcast(p_.data, 0)
     n_params = sum(p.numel() for p in model.parameters())
 
     batch, seconds = wl["batch"], wl["seconds"]
@@ -261,9 +263,12 @@ def main():
         model.zero_grad(set_to_none=True)
         cur, net.forward = net.forward, eager_forward
         try:
-            return ctc_step(net, w, t, True)
+            loss = ctc_step(net, w, t, True)
         finally:
             net.forward = cur
+        if world > 1:
+            allreduce_gradients(model.parameters(), world)     # NCCL over NVLink: the step's only collective
+        return loss
 
     # One CUDA graph for forward + CTC loss + backward (the step is host-launch-bound otherwise); eager fallback if
     # the capture is refused (e.g. a collective that cannot be captured).
@@ -284,7 +289,10 @@ def main():
 
             def step_graphed(w, t):
                 model.zero_grad(set_to_none=True)
-                return ctc_step(gnet, w, t, True)
+                loss = ctc_step(gnet, w, t, True)
+                if world > 1:
+                    allreduce_gradients(model.parameters(), world)
+                return loss
             step_graphed(wav_d, tgt_d)
             torch.cuda.synchronize()
             step_fn = step_graphed
@@ -396,7 +404,7 @@ def main():
                        "encoder_frames": L, "d_inner": D, "layers": cfg["num_layers"], "params": n_params,
                        "step": "Fbank+norm+CNN+%d ConMamba layers+CTC loss, forward+backward, bf16 autocast, no optimizer"
                                % cfg["num_layers"],
-                       "parallelism": "dp%d (DDP grad all-reduce over NCCL)" % world if world > 1 else "single GPU",
+                       "parallelism": "dp%d (utterance sharding; one flat NCCL gradient all-reduce per step)" % world if world > 1 else "single GPU",
                        "launch": graph_note,
                        "roofline_timing": "per-kernel CUDA events from 3 eager launches of the same step right after "
                                           "the timed region (kernels inside a graph replay cannot carry events)",

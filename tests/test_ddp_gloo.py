@@ -1,6 +1,6 @@
 """World-size-2 gloo test (CPU) of the data-parallel host logic bench.py uses at N > 1: utterances are sharded by
-rank (no data-path collective), gradients are all-reduced by DDP, and the reduced gradient equals the gradient of the
-same global batch on one process.  The CPU arm swaps the sm_100a mixers for the oracle (tests may use oracle/)."""
+rank (no data-path collective), gradients are averaged by ONE flat all-reduce (mamba_asr_b200.dist_utils), and the
+reduced gradient equals the gradient of the same global batch on one process.  The CPU arm swaps the sm_100a mixers for the oracle (tests may use oracle/)."""
 import os
 import socket
 
@@ -46,19 +46,12 @@ def _worker(rank, world, port, q):
     # InputNormalization uses batch statistics: give every rank the same statistics by normalising features outside
     feats = model.features(wav)[shard]
 
-    class Tail(torch.nn.Module):                               # the part of the model that has parameters
-        def __init__(self, m):
-            super().__init__()
-            self.m = m
-
-        def forward(self, f):
-            return F.log_softmax(self.m.ctc_lin(self.m.encode(f)), dim=-1)
-
-    ddp = torch.nn.parallel.DistributedDataParallel(Tail(model))
-    out = ddp(feats)
+    from mamba_asr_b200.dist_utils import allreduce_gradients
+    out = F.log_softmax(model.ctc_lin(model.encode(feats)), dim=-1)
     loss = F.ctc_loss(out.transpose(0, 1), tgt[shard], torch.full((2,), out.shape[1]), torch.full((2,), 3), blank=0,
                       reduction="sum", zero_infinity=True)
-    loss.backward()                                            # DDP all-reduces (averages) the gradients over gloo
+    loss.backward()
+    allreduce_gradients(model.parameters(), world)             # one flat all-reduce over gloo, averaged
     grads = [p.grad.clone() * world for p in model.parameters() if p.grad is not None]
     t = torch.tensor([float(loss.detach())])
     dist.all_reduce(t)

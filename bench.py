@@ -61,6 +61,16 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(entry, workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `entry` at this workload's shape, from the committed
+    `ncu --set full` capture (profiles/r01_traffic.json, written by tools/ncu_traffic.py); None if not captured."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        return d.get("%s@%s" % (entry, workload))
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
 
@@ -387,7 +397,7 @@ def main():
         roofline = None
         if dom:
             roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["achieved_gbs"], "peak": hbm_peak,
-                        "unit": "GB/s", "frac": kern[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                        "unit": "GB/s", "frac": kern[dom]["frac"], "traffic": ncu_traffic(dom, args.workload), "peak_source": peak_src,
                         "alg_bytes_per_launch": kern[dom]["alg_bytes"], "avg_launch_ms": kern[dom]["avg_ms"],
                         "note": "fp32 state update is MUFU/issue-bound before HBM (SURVEY.md 0.8); see `kernels`"}
         cpu_desc = None

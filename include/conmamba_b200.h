@@ -241,11 +241,39 @@ int cm_layernorm_num_part(int64_t rows);
 int cm_layernorm_fwd(const cm_layernorm_args* args, void* stream);
 int cm_layernorm_bwd(const cm_layernorm_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Depthwise conv1d over time (the kernel_size = 31 convolution of the ConMamba
+ * convolution module, reference modules/Conmamba.py:281-290, nn.Conv1d(C, C, K, padding, groups=C)).
+ *   y[b,l,c] = bias[c] + sum_k weight[c,k] * x[b, l - pad_left + k, c]      (zero outside [0, L))
+ * pad_left = (K-1)/2 for "same" padding, K-1 for the causal variant.  K in {3, 7, 15, 31}.
+ * Backward-data is the same entry point with flip = 1, pad_left' = K-1-pad_left, bias = NULL, x = grad of y.
+ * cm_dwconv_bwd_weight writes cm_dwconv_num_part() partial rows: dweight_part [n_part][dim][K], dbias_part
+ * [n_part][dim] (fp32); sum them with cm_reduce_multi.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch, dim, seqlen, ksize;
+  int32_t pad_left;
+  int32_t dtype;
+  int32_t flip;             /* 1: use weight[c][K-1-k] (backward-data) */
+  int32_t reserved;
+  cm_tensor3 x;             /* (batch, dim, time) input (forward) / grad of y (backward-data) */
+  cm_tensor3 y;             /* output (forward) / grad of x (backward-data) */
+  const float* weight;      /* (dim, K) fp32 contiguous */
+  const float* bias;        /* (dim) fp32 or NULL */
+  cm_tensor3 dy;            /* backward-weight: grad of y */
+  float* dweight_part;      /* backward-weight outputs */
+  float* dbias_part;        /* or NULL */
+} cm_dwconv_args;
+
+int cm_dwconv_num_part(int32_t batch, int32_t seqlen, int32_t ksize);
+int cm_dwconv_fwd(const cm_dwconv_args* args, void* stream);
+int cm_dwconv_bwd_weight(const cm_dwconv_args* args, void* stream);
+
 /* library identification: returns CM_ABI_VERSION; writes the compiled-for arch (e.g. 100) to *sm_arch if non-NULL */
 int cm_version(int32_t* sm_arch);
 /* sizeof() of the argument structs, for binding self-checks: 0 cm_tensor3, 1 cm_scan_dir, 2 cm_scan_fwd_args,
  * 3 cm_scan_bwd_dir, 4 cm_scan_bwd_args, 5 cm_conv_dir, 6 cm_conv_args, 7 cm_fbank_args, 8 cm_reduce_job,
- * 9 cm_layernorm_args */
+ * 9 cm_layernorm_args, 10 cm_dwconv_args */
 int cm_abi_sizeof(int32_t which);
 
 #ifdef __cplusplus

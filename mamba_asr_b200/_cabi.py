@@ -24,7 +24,7 @@ EXPORTS = (
     "cm_scan_bwd",
     "cm_reduce_dbc", "cm_reduce_rows", "cm_conv_fwd", "cm_conv_num_part", "cm_conv_bwd", "cm_conv_update",
     "cm_fbank_logmel", "cm_fbank_floor", "cm_abi_sizeof", "cm_reduce_multi", "cm_layernorm_num_part", "cm_layernorm_fwd",
-    "cm_layernorm_bwd",
+    "cm_layernorm_bwd", "cm_dwconv_num_part", "cm_dwconv_fwd", "cm_dwconv_bwd_weight",
 )
 CM_REDUCE_MAX_JOBS = 8
 
@@ -113,8 +113,17 @@ class LayerNormArgs(C.Structure):
     ]
 
 
+class DwConvArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("dim", C.c_int32), ("seqlen", C.c_int32), ("ksize", C.c_int32),
+        ("pad_left", C.c_int32), ("dtype", C.c_int32), ("flip", C.c_int32), ("reserved", C.c_int32),
+        ("x", Tensor3), ("y", Tensor3), ("weight", C.c_void_p), ("bias", C.c_void_p), ("dy", Tensor3),
+        ("dweight_part", C.c_void_p), ("dbias_part", C.c_void_p),
+    ]
+
+
 ABI_STRUCTS = (Tensor3, ScanDir, ScanFwdArgs, ScanBwdDir, ScanBwdArgs, ConvDir, ConvArgs, FbankArgs, ReduceJob,
-               LayerNormArgs)
+               LayerNormArgs, DwConvArgs)
 
 _lib = None
 
@@ -152,6 +161,9 @@ def lib():
         L.cm_layernorm_num_part.argtypes = [C.c_int64]
         L.cm_layernorm_fwd.argtypes = [C.POINTER(LayerNormArgs), C.c_void_p]
         L.cm_layernorm_bwd.argtypes = [C.POINTER(LayerNormArgs), C.c_void_p]
+        L.cm_dwconv_num_part.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+        L.cm_dwconv_fwd.argtypes = [C.POINTER(DwConvArgs), C.c_void_p]
+        L.cm_dwconv_bwd_weight.argtypes = [C.POINTER(DwConvArgs), C.c_void_p]
         if L.cm_version(None) != CM_ABI_VERSION:
             raise RuntimeError("mamba_asr_b200: %s has a different ABI version; rebuild it" % LIB_PATH)
         for i, st in enumerate(ABI_STRUCTS):

@@ -17,9 +17,12 @@ from typing import Optional
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from .bimamba import Mamba as BiMamba
 from .bimamba import UniMamba as Mamba
+from .dwconv import depthwise_conv1d
+from .kernels import DWCONV_KSIZES
 from .layernorm import FusedLayerNorm
 
 LAYER_NORM_EPS = 1e-6        # reference ConMambaConstants.LAYER_NORM_EPS (Conmamba.py:687)
@@ -78,11 +81,22 @@ class ConvolutionModule(nn.Module):
                               dilation=dilation, groups=input_size, bias=bias)
         self.after_conv = nn.Sequential(FusedLayerNorm(input_size), activation(), nn.Linear(input_size, input_size, bias=bias),
                                         nn.Dropout(dropout))
+        # channel-last evaluation on the sm_100a depthwise kernel (no transposes); the CPU reference arm
+        # (oracle/cpu_encoder.py) clears the flag and gets the reference's own torch op chain below
+        self.use_kernel = dilation == 1 and kernel_size in DWCONV_KSIZES
 
     def forward(self, x, mask: Optional[torch.Tensor] = None, dynchunktrain_config=None):
         if dynchunktrain_config is not None:
             raise NotImplementedError("Dynamic Chunk Training convolution is never enabled by the ConMamba encoder "
                                       "(TransformerASR.py:783-788 passes no config)")
+        if self.use_kernel:
+            pw = self.bottleneck[0]                                   # pointwise conv = Linear over channel-last rows
+            out = F.glu(F.linear(self.layer_norm(x), pw.weight.squeeze(-1), pw.bias), dim=-1)
+            out = depthwise_conv1d(out, self.conv.weight, self.conv.bias, pad_left=self.padding)
+            out = self.after_conv(out)
+            if mask is not None:
+                out.masked_fill_(mask, 0.0)
+            return out
         out = self.layer_norm(x).transpose(1, 2)
         out = self.conv(self.bottleneck(out))
         if self.causal:

@@ -1,0 +1,192 @@
+// Depthwise conv1d over time, channel-last, for sm_100a: the k = 31 convolution of the ConMamba convolution module
+// (reference modules/Conmamba.py:281-290: nn.Conv1d(C, C, kernel_size, padding, groups=C)).
+//
+//   y[b, l, c] = bias[c] + sum_k w[c, k] * x[b, l - pad_left + k, c]            (zero outside [0, L))
+//
+// torch evaluates it on (B, C, L) tensors through conv_depthwise2d kernels - measured on B200 at 64 x 501 x 256: 179 us
+// forward, 211 us backward-data, 396 us backward-weight per layer, plus the two transposes around it; the op itself is
+// 254 MFMA and 33 MB per layer (7 us of FP32 issue, 5 us of HBM).
+//
+// Layout: a lane owns ONE channel (a warp row is 32 consecutive channels: coalesced in the channel-last activations),
+// keeps the K taps and a K-deep sliding window of the input in registers and walks a slab of time steps; the loop is
+// unrolled by K so that the window rotation is register renaming.  One new row per output, K FFMA per output.
+//   forward / backward-data : the same kernel (backward-data = taps flipped, pad_left' = K-1-pad_left, no bias)
+//   backward-weight         : dw[c,k] += dy[l] * x[l - pad_left + k]  with the same window; 4 warps of a CTA are summed in
+//                             shared memory and each CTA writes one partial row (fixed-order reduction by cm_reduce_multi:
+//                             deterministic, no atomics)
+// Roof: HBM / FP32 issue (balanced).  Algorithmic bytes per position: 2s forward, 2s backward-data, 2s backward-weight.
+#include "common.cuh"
+
+namespace cm {
+
+constexpr int kDwWarps = 4;
+
+template <int K> struct DwCfg {
+  static constexpr int NCH = (64 + K - 1) / K;   // chunks of K outputs per warp slab
+  static constexpr int TW = NCH * K;             // outputs per warp slab
+};
+
+template <typename T, int K>
+__global__ void __launch_bounds__(32 * kDwWarps) dwconv_fwd_kernel(const cm_dwconv_args p) {
+  constexpr int TW = DwCfg<K>::TW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const bool act = c < p.dim;
+  const int b = blockIdx.z;
+  const int t0 = (blockIdx.y * kDwWarps + warp) * TW;
+  const int L = p.seqlen;
+  if (t0 >= L) return;
+  const int cc = act ? c : 0;
+  float w[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) w[k] = act ? __ldg(p.weight + (int64_t)cc * K + (p.flip ? K - 1 - k : k)) : 0.f;
+  const float bias = (act && p.bias != nullptr) ? __ldg(p.bias + cc) : 0.f;
+  const T* xp = static_cast<const T*>(p.x.ptr) + b * p.x.sb + cc * p.x.sd;
+  T* yp = static_cast<T*>(p.y.ptr) + b * p.y.sb + cc * p.y.sd;
+  const int64_t xsl = p.x.sl, ysl = p.y.sl;
+  const int pad = p.pad_left;
+  auto ldx = [&](int r) -> float { return (act && r >= 0 && r < L) ? Elem<T>::ld(xp + r * xsl) : 0.f; };
+  float win[K];
+#pragma unroll
+  for (int i = 0; i < K - 1; ++i) win[i] = ldx(t0 - pad + i);
+  win[K - 1] = 0.f;
+#pragma unroll 1
+  for (int o = 0; o < TW; o += K) {
+    if (t0 + o >= L) break;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const int l = t0 + o + j;
+      win[(K - 1 + j) % K] = ldx(l - pad + K - 1);
+      float acc = bias;
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc = fmaf(w[k], win[(j + k) % K], acc);
+      if (act && l < L) Elem<T>::st(yp + l * ysl, acc);
+    }
+  }
+}
+
+template <typename T, int K>
+__global__ void __launch_bounds__(32 * kDwWarps) dwconv_bwd_weight_kernel(const cm_dwconv_args p) {
+  constexpr int TW = DwCfg<K>::TW;
+  __shared__ float red[kDwWarps][K + 1][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const bool act = c < p.dim;
+  const int b = blockIdx.z;
+  const int t0 = (blockIdx.y * kDwWarps + warp) * TW;
+  const int L = p.seqlen;
+  const int cc = act ? c : 0;
+  const T* xp = static_cast<const T*>(p.x.ptr) + b * p.x.sb + cc * p.x.sd;
+  const T* gp = static_cast<const T*>(p.dy.ptr) + b * p.dy.sb + cc * p.dy.sd;
+  const int64_t xsl = p.x.sl, gsl = p.dy.sl;
+  const int pad = p.pad_left;
+  float dw[K], db = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) dw[k] = 0.f;
+  if (t0 < L) {
+    auto ldx = [&](int r) -> float { return (act && r >= 0 && r < L) ? Elem<T>::ld(xp + r * xsl) : 0.f; };
+    float win[K];
+#pragma unroll
+    for (int i = 0; i < K - 1; ++i) win[i] = ldx(t0 - pad + i);
+    win[K - 1] = 0.f;
+#pragma unroll 1
+    for (int o = 0; o < TW; o += K) {
+      if (t0 + o >= L) break;
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const int l = t0 + o + j;
+        win[(K - 1 + j) % K] = ldx(l - pad + K - 1);
+        const float g = (act && l < L) ? Elem<T>::ld(gp + l * gsl) : 0.f;
+        db += g;
+#pragma unroll
+        for (int k = 0; k < K; ++k) dw[k] = fmaf(g, win[(j + k) % K], dw[k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) red[warp][k][lane] = dw[k];
+  red[warp][K][lane] = db;
+  __syncthreads();
+  // fixed-order sum over the CTA's warps; one partial row per CTA
+  const int64_t part = (int64_t)blockIdx.z * gridDim.y + blockIdx.y;
+  for (int i = threadIdx.x; i < (K + 1) * 32; i += blockDim.x) {
+    const int k = i / 32, ln = i % 32;
+    const int ch = blockIdx.x * 32 + ln;
+    if (ch >= p.dim) continue;
+    float a = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < kDwWarps; ++wv) a += red[wv][k][ln];
+    if (k < K) p.dweight_part[(part * p.dim + ch) * K + k] = a;
+    else if (p.dbias_part != nullptr) p.dbias_part[part * p.dim + ch] = a;
+  }
+}
+
+template <typename T, int K>
+static int dw_launch(const cm_dwconv_args& a, bool wgrad, cudaStream_t st) {
+  constexpr int TW = DwCfg<K>::TW;
+  const dim3 grid(cm_ceil_div(a.dim, 32), cm_ceil_div(a.seqlen, kDwWarps * TW), a.batch);
+  if (wgrad) dwconv_bwd_weight_kernel<T, K><<<grid, 32 * kDwWarps, 0, st>>>(a);
+  else dwconv_fwd_kernel<T, K><<<grid, 32 * kDwWarps, 0, st>>>(a);
+  CM_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+static int dw_dispatch(const cm_dwconv_args& a, bool wgrad, cudaStream_t st) {
+  switch (a.ksize) {
+    case 3: return dw_launch<T, 3>(a, wgrad, st);
+    case 7: return dw_launch<T, 7>(a, wgrad, st);
+    case 15: return dw_launch<T, 15>(a, wgrad, st);
+    case 31: return dw_launch<T, 31>(a, wgrad, st);
+    default: return CM_ERR_UNSUPPORTED;
+  }
+}
+
+static int dw_slab(int ksize) {
+  switch (ksize) {
+    case 3: return DwCfg<3>::TW;
+    case 7: return DwCfg<7>::TW;
+    case 15: return DwCfg<15>::TW;
+    case 31: return DwCfg<31>::TW;
+    default: return 0;
+  }
+}
+
+}  // namespace cm
+
+extern "C" int cm_dwconv_num_part(int32_t batch, int32_t seqlen, int32_t ksize) {
+  const int tw = cm::dw_slab(ksize);
+  if (batch <= 0 || seqlen <= 0 || tw == 0) return CM_ERR_BAD_ARG;
+  return batch * cm_ceil_div(seqlen, cm::kDwWarps * tw);
+}
+
+static int dw_check(const cm_dwconv_args* a) {
+  if (a == nullptr || a->batch <= 0 || a->dim <= 0 || a->seqlen <= 0 || a->x.ptr == nullptr) return CM_ERR_BAD_ARG;
+  if (!cm::dtype_ok(a->dtype)) return CM_ERR_BAD_ARG;
+  if (a->batch > 65535) return CM_ERR_UNSUPPORTED;
+  if (cm::dw_slab(a->ksize) == 0) return CM_ERR_UNSUPPORTED;
+  if (a->pad_left < 0 || a->pad_left >= a->ksize) return CM_ERR_BAD_ARG;
+  return 0;
+}
+
+extern "C" int cm_dwconv_fwd(const cm_dwconv_args* a, void* stream) {
+  if (int e = dw_check(a)) return e;
+  if (a->y.ptr == nullptr || a->weight == nullptr) return CM_ERR_BAD_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (a->dtype) {
+    case CM_F32: return cm::dw_dispatch<float>(*a, false, st);
+    case CM_BF16: return cm::dw_dispatch<__nv_bfloat16>(*a, false, st);
+    default: return cm::dw_dispatch<__half>(*a, false, st);
+  }
+}
+
+extern "C" int cm_dwconv_bwd_weight(const cm_dwconv_args* a, void* stream) {
+  if (int e = dw_check(a)) return e;
+  if (a->dy.ptr == nullptr || a->dweight_part == nullptr) return CM_ERR_BAD_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (a->dtype) {
+    case CM_F32: return cm::dw_dispatch<float>(*a, true, st);
+    case CM_BF16: return cm::dw_dispatch<__nv_bfloat16>(*a, true, st);
+    default: return cm::dw_dispatch<__half>(*a, true, st);
+  }
+}

@@ -149,6 +149,7 @@ extern "C" int cm_abi_sizeof(int32_t which) {
     case 7: return (int)sizeof(cm_fbank_args);
     case 8: return (int)sizeof(cm_reduce_job);
     case 9: return (int)sizeof(cm_layernorm_args);
+    case 10: return (int)sizeof(cm_dwconv_args);
     default: return CM_ERR_BAD_ARG;
   }
 }

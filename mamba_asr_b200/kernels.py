@@ -474,3 +474,56 @@ def layernorm_backward(x2d, dy2d, weight, mean, rstd, need_wgrad=True):
     db = torch.empty((Cn,), dtype=torch.float32, device=x2d.device)
     reduce_many([(dg_part, dg), (db_part, db)])
     return dx, dg, db
+
+
+# ------------------------------------------------------------------------------------------------ depthwise conv1d
+DWCONV_KSIZES = (3, 7, 15, 31)
+
+
+def _dwconv_args(x_blc, ksize, pad_left):
+    _require_cuda(x_blc, "x")
+    if x_blc.dim() != 3:
+        raise ValueError("dwconv: x must be (batch, time, channels)")
+    if ksize not in DWCONV_KSIZES:
+        raise NotImplementedError("dwconv: kernel_size must be one of %s" % (DWCONV_KSIZES,))
+    Bt, L, Cn = x_blc.shape
+    a = cabi.DwConvArgs()
+    a.batch, a.dim, a.seqlen, a.ksize = Bt, Cn, L, ksize
+    a.pad_left = int(pad_left)
+    a.dtype = cabi.dtype_code(x_blc.dtype)
+    return a
+
+
+def dwconv_forward(x_blc, weight_ck, bias, pad_left, flip=False):
+    """cm_dwconv_fwd on a channel-last (B, L, C) tensor; weight (C, K) fp32, bias (C,) fp32 or None.
+    flip=True evaluates the backward-data form (taps reversed; pass pad_left' = K-1-pad_left, bias None)."""
+    lib = cabi.lib()
+    Cn, K = weight_ck.shape
+    a = _dwconv_args(x_blc, K, pad_left)
+    y = torch.empty(x_blc.shape, dtype=x_blc.dtype, device=x_blc.device)
+    a.flip = 1 if flip else 0
+    a.x, a.y = cabi.t3(x_blc, "bld"), cabi.t3(y, "bld")
+    a.weight, a.bias = weight_ck.data_ptr(), cabi.ptr(bias)
+    _call("cm_dwconv_fwd", lib.cm_dwconv_fwd, C.byref(a), cabi.stream_ptr())
+    return y
+
+
+def dwconv_backward_weight(x_blc, dy_blc, ksize, pad_left, need_bias=True):
+    """cm_dwconv_bwd_weight + deterministic reduction: returns (dweight (C, K) fp32, dbias (C,) fp32 or None)."""
+    lib = cabi.lib()
+    Bt, L, Cn = x_blc.shape
+    a = _dwconv_args(x_blc, ksize, pad_left)
+    n_part = lib.cm_dwconv_num_part(Bt, L, ksize)
+    dw_part = torch.empty((n_part, Cn * ksize), dtype=torch.float32, device=x_blc.device)
+    db_part = torch.empty((n_part, Cn), dtype=torch.float32, device=x_blc.device) if need_bias else None
+    a.x, a.dy = cabi.t3(x_blc, "bld"), cabi.t3(dy_blc, "bld")
+    a.dweight_part, a.dbias_part = dw_part.data_ptr(), cabi.ptr(db_part)
+    _call("cm_dwconv_bwd_weight", lib.cm_dwconv_bwd_weight, C.byref(a), cabi.stream_ptr())
+    dw = torch.empty((Cn * ksize,), dtype=torch.float32, device=x_blc.device)
+    jobs = [(dw_part, dw)]
+    db = None
+    if need_bias:
+        db = torch.empty((Cn,), dtype=torch.float32, device=x_blc.device)
+        jobs.append((db_part, db))
+    reduce_many(jobs)
+    return dw.view(Cn, ksize), db

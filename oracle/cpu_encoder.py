@@ -44,5 +44,7 @@ def to_cpu_reference(model, n_fft, n_mels, win_length_ms):
     for mod in model.modules():                  # the sm_100a LayerNorm has no CPU path: torch's own op on the CPU arm
         if isinstance(mod, FusedLayerNorm):
             mod.__class__ = nn.LayerNorm
+        if hasattr(mod, "use_kernel"):           # ConvolutionModule: the reference's transpose -> nn.Conv1d chain
+            mod.use_kernel = False
     model.compute_features = OracleFbank(n_fft, n_mels, win_length_ms)
     return model

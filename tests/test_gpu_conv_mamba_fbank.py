@@ -296,3 +296,51 @@ def test_layernorm_module_follows_autocast_and_has_no_cpu_path():
     assert sorted(ln.state_dict().keys()) == ["bias", "weight"]
     with pytest.raises(RuntimeError):
         FusedLayerNorm(144)(torch.randn(2, 144))
+
+
+@pytest.mark.parametrize("ksize,causal", [(31, False), (31, True), (15, False), (7, False), (3, True)])
+@pytest.mark.parametrize("shape", [(2, 501, 256), (3, 67, 144), (1, 5, 33), (2, 94, 64)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_depthwise_conv1d_matches_torch_conv1d(ksize, causal, shape, dtype):
+    """cm_dwconv_fwd / cm_dwconv_bwd_weight against the reference's own op (nn.Conv1d(C, C, K, padding, groups=C),
+    modules/Conmamba.py:281-290) evaluated in fp32 on the same (rounded) inputs: y, dx, dweight, dbias."""
+    from mamba_asr_b200.dwconv import depthwise_conv1d
+    Bt, L, Cn = shape
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(Bt, L, Cn, generator=g).to(dtype).cuda()
+    w = (torch.randn(Cn, 1, ksize, generator=g) / ksize ** 0.5).cuda()
+    b = (0.1 * torch.randn(Cn, generator=g)).cuda()
+    cot = torch.randn(Bt, L, Cn, generator=g).to(dtype).cuda()
+    pad = ksize - 1 if causal else (ksize - 1) // 2
+    xr = x.float().clone().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.conv1d(xr.transpose(1, 2), wr, br, padding=pad, groups=Cn)
+    ref = (ref[..., :-pad] if causal else ref).transpose(1, 2)
+    (ref * cot.float()).sum().backward()
+    xk = x.clone().requires_grad_(True)
+    wk, bk = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    out = depthwise_conv1d(xk, wk, bk, pad_left=pad)
+    assert out.shape == x.shape and out.dtype == dtype
+    (out.float() * cot.float()).sum().backward()
+    assert_close(out.float(), ref, dtype, what="dwconv y")
+    assert_close(xk.grad.float(), xr.grad, dtype, what="dwconv dx")
+    assert_close(wk.grad, wr.grad, dtype, floor="max", what="dwconv dweight")
+    assert_close(bk.grad, br.grad, dtype, floor="max", what="dwconv dbias")
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_convolution_module_kernel_path_equals_reference_op_chain(causal, monkeypatch):
+    """ConvolutionModule on the channel-last kernels == the reference's transpose -> Conv1d -> GLU -> Conv1d chain."""
+    from mamba_asr_b200.conmamba import ConvolutionModule
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)    # the reference chain's cuDNN convs in true fp32
+    torch.manual_seed(4)
+    m = ConvolutionModule(64, kernel_size=31, causal=causal).cuda().eval()
+    x = torch.randn(2, 77, 64, device="cuda")
+    assert m.use_kernel
+    y_k = m(x)
+    m.use_kernel = False
+    for mod in m.modules():                      # the reference chain uses torch's LayerNorm
+        if type(mod).__name__ == "FusedLayerNorm":
+            mod.__class__ = torch.nn.LayerNorm
+    y_t = m(x)
+    assert_close(y_k, y_t, what="conv module")

@@ -419,22 +419,32 @@ __global__ void reduce_rows_kernel(const float* __restrict__ part, int64_t rows,
 struct ReduceJobs {
   cm_reduce_job j[CM_REDUCE_MAX_JOBS];
 };
-__global__ void __launch_bounds__(256) reduce_multi_kernel(const ReduceJobs jobs) {
-  __shared__ float sm[8][33];
+constexpr int kRmWarps = 16;
+__global__ void __launch_bounds__(32 * kRmWarps) reduce_multi_kernel(const ReduceJobs jobs) {
+  __shared__ float sm[kRmWarps][33];
   const cm_reduce_job& job = jobs.j[blockIdx.y];
   const int64_t c = (int64_t)blockIdx.x * 32 + threadIdx.x;
   if ((int64_t)blockIdx.x * 32 >= job.cols) return;      // CTA-uniform
-  float acc = 0.f;
+  // four independent running sums per thread (rows ty, ty+16, ...: round-robin), combined in a fixed order: the loads
+  // of a thread are in flight together instead of one L2 round trip per row
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   if (c < job.cols) {
     const float* src = job.part + c;
-    for (int64_t r = threadIdx.y; r < job.rows; r += 8) acc += __ldg(src + r * job.cols);
+    const int64_t rows = job.rows, cols = job.cols;
+    int64_t r = threadIdx.y;
+    for (; r + 3 * kRmWarps < rows; r += 4 * kRmWarps) {
+      const float v0 = __ldg(src + r * cols), v1 = __ldg(src + (r + kRmWarps) * cols);
+      const float v2 = __ldg(src + (r + 2 * kRmWarps) * cols), v3 = __ldg(src + (r + 3 * kRmWarps) * cols);
+      a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+    }
+    for (; r < rows; r += kRmWarps) a0 += __ldg(src + r * cols);
   }
-  sm[threadIdx.y][threadIdx.x] = acc;
+  sm[threadIdx.y][threadIdx.x] = (a0 + a1) + (a2 + a3);
   __syncthreads();
   if (threadIdx.y == 0 && c < job.cols) {
     float t = sm[0][threadIdx.x];
 #pragma unroll
-    for (int y = 1; y < 8; ++y) t += sm[y][threadIdx.x];
+    for (int y = 1; y < kRmWarps; ++y) t += sm[y][threadIdx.x];
     job.out[c] = t;
   }
 }
@@ -452,7 +462,7 @@ extern "C" int cm_reduce_multi(const cm_reduce_job* jobs, int32_t njobs, void* s
   }
   for (int i = njobs; i < CM_REDUCE_MAX_JOBS; ++i) rj.j[i] = jobs[0];
   const dim3 grid((unsigned)((maxcols + 31) / 32), njobs);
-  cm::reduce_multi_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(rj);
+  cm::reduce_multi_kernel<<<grid, dim3(32, cm::kRmWarps), 0, static_cast<cudaStream_t>(stream)>>>(rj);
   CM_LAUNCH_CHECK();
   return 0;
 }

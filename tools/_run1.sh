@@ -1,13 +1,9 @@
-timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -8 > gpurun_out/pytest.log
+timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -4 > gpurun_out/pytest.log
 cat gpurun_out/pytest.log
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench9.log 2> gpurun_out/bench9.err; python - <<EOF2
+for wl in conmamba_small_ctc_fwdbwd_b32x15s conmamba_large_ctc_fwdbwd_b64x20s; do
+timeout 900 python bench.py --steps 8 --warmup 3 --workload $wl --no-cpu-baseline > gpurun_out/bench_x.log 2> gpurun_out/bench_x.err; python - <<EOF2
 import json
-l=[x for x in open("gpurun_out/bench9.log") if x.startswith("{")]
-d=json.loads(l[-1]); print({k:d[k] for k in ("value","ms_per_step","e2e","gpu_launches","loss")}); print(d["roofline"])
+l=[x for x in open("gpurun_out/bench_x.log") if x.startswith("{")]
+d=json.loads(l[-1]); print({k:d[k] for k in ("value","ms_per_step","gpu_launches","loss")}); print({k:round(v/3,3) for k,v in d["kernel_time_share_ms"].items()})
 EOF2
-tail -2 gpurun_out/bench9.err | cut -c1-200
-timeout 900 python bench.py --steps 5 --warmup 3 --workload conmamba_large_ctc_fwdbwd_b64x20s --no-cpu-baseline > gpurun_out/bench_large.log 2> gpurun_out/bench_large.err; python - <<EOF2
-import json
-l=[x for x in open("gpurun_out/bench_large.log") if x.startswith("{")]
-d=json.loads(l[-1]); print({k:d[k] for k in ("value","ms_per_step","e2e","gpu_launches","loss")}); print(d["kernel_time_share_ms"])
-EOF2
+done

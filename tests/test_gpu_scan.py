@@ -320,3 +320,60 @@ def test_state_parallel_backward_bf16_matches_lane_per_channel_kernel(monkeypatc
             assert_close(g_sp[key][r].float(), g_old[key][r].float(), torch.bfloat16, what=f"{key}[{r}]")
         for key in ("dB", "dC", "dA", "dD", "dbias"):
             assert_close(g_sp[key][r].float(), g_old[key][r].float(), torch.bfloat16, floor="max", what=f"{key}[{r}]")
+
+
+def test_full_size_backward_properties_config3_shapes(monkeypatch):
+    """ConMamba-large shapes (B 64, D 512, L 501, bf16), backward: (i) two launches are bit-identical (fixed-order sums,
+    no atomics); (ii) the state-parallel kernel and the lane-per-channel kernel agree on every gradient; (iii) the
+    gradients are linear in the output cotangent."""
+    from mamba_asr_b200 import kernels as K
+    Bt, D, L, N = 64, 512, 501, 16
+    f = make_scan_inputs(Bt, D, L, N, torch.bfloat16, seed=61, device="cuda")
+    b = make_scan_inputs(Bt, D, L, N, torch.bfloat16, seed=62, device="cuda")
+    cl = lambda d: {k: (channel_last(v) if v.dim() == 3 else v) for k, v in d.items()}
+    f, b = cl(f), cl(b)
+    dirs = [dict(u=s["u"], delta=s["delta"], A=s["A"], B=s["B"], C=s["C"], D=s["D"], delta_bias=s["delta_bias"], reverse=rev)
+            for s, rev in ((f, False), (b, True))]
+    res = K.scan_forward(dirs, z=f["z"], out_scale=0.5, delta_softplus=True, need_ckpt=True, need_out_pre=True)
+    g1 = channel_last(torch.randn(Bt, D, L, device="cuda").bfloat16())
+    g2 = channel_last(torch.randn(Bt, D, L, device="cuda").bfloat16())
+    run = lambda g: K.scan_backward(dirs, res["ckpt"], g, z=f["z"], out_pre=res["out_pre"], out_scale=0.5, delta_softplus=True)
+    a1, a1b, a2, a12 = run(g1), run(g1), run(g2), run(g1 + g2)
+    keys_t, keys_p = ("du", "ddelta", "dB", "dC"), ("dA", "dD", "dbias")
+    assert torch.equal(a1["dz"], a1b["dz"])
+    for r in range(2):
+        for k in keys_t + keys_p:
+            assert torch.equal(a1[k][r], a1b[k][r]), (k, r)                      # (i)
+    for r in range(2):                                                            # (iii)
+        for k in keys_t:
+            assert_close(a12[k][r].float(), a1[k][r].float() + a2[k][r].float(), torch.bfloat16, floor="max", what=f"lin {k}[{r}]")
+        for k in keys_p:
+            assert_close(a12[k][r], a1[k][r] + a2[k][r], torch.bfloat16, floor="max", what=f"lin {k}[{r}]")
+    monkeypatch.setenv("CM_SCAN_NO_SP", "1")                                      # (ii)
+    o1 = run(g1)
+    assert_close(a1["dz"].float(), o1["dz"].float(), torch.bfloat16, floor="max", what="dz vs lane-per-channel")
+    for r in range(2):
+        for k in keys_t:
+            assert_close(a1[k][r].float(), o1[k][r].float(), torch.bfloat16, floor="max", what=f"{k}[{r}] vs lane-per-channel")
+        for k in keys_p:
+            assert_close(a1[k][r], o1[k][r], torch.bfloat16, floor="max", what=f"{k}[{r}] vs lane-per-channel")
+
+
+def test_long_sequence_forward_matches_lane_per_channel_kernel(monkeypatch):
+    """BASELINE config 5 shape class (batch 4, D 512, L 7501, bf16 and fp32): the state-parallel forward against the
+    lane-per-channel kernel (both pinned to the oracle at small sizes)."""
+    from mamba_asr_b200 import kernels as K
+    for dtype in (torch.bfloat16, torch.float32):
+        Bt, D, L, N = 4, 512, 7501, 16
+        f = make_scan_inputs(Bt, D, L, N, dtype, seed=71, device="cuda")
+        b = make_scan_inputs(Bt, D, L, N, dtype, seed=72, device="cuda")
+        cl = lambda d: {k: (channel_last(v) if v.dim() == 3 else v) for k, v in d.items()}
+        f, b = cl(f), cl(b)
+        dirs = [dict(u=s["u"], delta=s["delta"], A=s["A"], B=s["B"], C=s["C"], D=s["D"], delta_bias=s["delta_bias"], reverse=rev)
+                for s, rev in ((f, False), (b, True))]
+        run = lambda: K.scan_forward(dirs, z=f["z"], out_scale=0.5, delta_softplus=True)["out"].float()
+        monkeypatch.delenv("CM_SCAN_NO_SP", raising=False)
+        o_sp = run()
+        monkeypatch.setenv("CM_SCAN_NO_SP", "1")
+        o_old = run()
+        assert_close(o_sp, o_old, dtype, floor="max", what=f"long forward {dtype}")

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CM_ABI_VERSION 1
+#define CM_ABI_VERSION 2
 
 /* element type of activations (u, delta, z, B, C, x, out, and their gradients) */
 enum { CM_F32 = 0, CM_BF16 = 1, CM_F16 = 2 };
@@ -96,6 +96,8 @@ typedef struct {
   cm_tensor3 z;             /* gate, shared by both directions; ptr NULL = none */
   cm_tensor3 out;           /* gated output */
   cm_tensor3 out_pre;       /* optional pre-gate sum over directions (saved for backward when z is given) */
+  void* workspace;          /* optional device scratch (16-byte aligned) of cm_scan_fwd_workspace_bytes() bytes: lets an */
+  int64_t workspace_bytes;  /* inference launch on few long sequences run as parallel time windows; NULL / 0 = never   */
 } cm_scan_fwd_args;
 
 /* number of fp32 [16] checkpoints per (batch, channel, direction) row that forward writes and backward reads */
@@ -107,6 +109,10 @@ int cm_scan_pick_lanes(int32_t batch, int32_t dim, int32_t ndir);
 /* the same for cm_scan_bwd (its register / shared-memory footprint favours 2 lanes per channel) */
 int cm_scan_pick_lanes_bwd(int32_t batch, int32_t dim, int32_t ndir);
 
+/* Scratch bytes with which cm_scan_fwd would split THIS launch into time windows (chunk-parallel scan: per-window
+ * summaries, a serial combine over windows, then every window from its incoming state), or 0 when the whole-sequence
+ * launch already fills the GPU or checkpoints are requested.  The library never allocates: the caller provides it. */
+int64_t cm_scan_fwd_workspace_bytes(const cm_scan_fwd_args* args);
 int cm_scan_fwd(const cm_scan_fwd_args* args, void* stream);
 
 typedef struct {

@@ -17,14 +17,14 @@ CM_ERR_BAD_ARG, CM_ERR_UNSUPPORTED = -1, -2
 CM_FLAG_DELTA_SOFTPLUS = 1
 CM_FLAG_SILU = 1
 CM_SCAN_CKPT_STEPS = 8
-CM_ABI_VERSION = 1
+CM_ABI_VERSION = 2
 
 EXPORTS = (
     "cm_version", "cm_scan_num_ckpt", "cm_scan_slab_channels", "cm_scan_pick_lanes", "cm_scan_pick_lanes_bwd", "cm_scan_fwd",
     "cm_scan_bwd",
     "cm_reduce_dbc", "cm_reduce_rows", "cm_conv_fwd", "cm_conv_num_part", "cm_conv_bwd", "cm_conv_update",
     "cm_fbank_logmel", "cm_fbank_floor", "cm_abi_sizeof", "cm_reduce_multi", "cm_layernorm_num_part", "cm_layernorm_fwd",
-    "cm_layernorm_bwd", "cm_dwconv_num_part", "cm_dwconv_fwd", "cm_dwconv_bwd_weight",
+    "cm_layernorm_bwd", "cm_scan_fwd_workspace_bytes", "cm_dwconv_num_part", "cm_dwconv_fwd", "cm_dwconv_bwd_weight",
 )
 CM_REDUCE_MAX_JOBS = 8
 
@@ -53,6 +53,7 @@ class ScanFwdArgs(C.Structure):
         ("lanes_per_channel", C.c_int32), ("reserved", C.c_int32),
         ("dir", ScanDir * 2),
         ("z", Tensor3), ("out", Tensor3), ("out_pre", Tensor3),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
     ]
 
 
@@ -158,6 +159,8 @@ def lib():
         L.cm_fbank_floor.argtypes = [C.POINTER(FbankArgs), C.c_void_p]
         L.cm_abi_sizeof.argtypes = [C.c_int32]
         L.cm_reduce_multi.argtypes = [C.POINTER(ReduceJob), C.c_int32, C.c_void_p]
+        L.cm_scan_fwd_workspace_bytes.argtypes = [C.POINTER(ScanFwdArgs)]
+        L.cm_scan_fwd_workspace_bytes.restype = C.c_int64
         L.cm_layernorm_num_part.argtypes = [C.c_int64]
         L.cm_layernorm_fwd.argtypes = [C.POINTER(LayerNormArgs), C.c_void_p]
         L.cm_layernorm_bwd.argtypes = [C.POINTER(LayerNormArgs), C.c_void_p]

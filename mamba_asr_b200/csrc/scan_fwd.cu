@@ -391,6 +391,14 @@ static int check_dir(const cm_scan_dir& d) {
 namespace cm {
 int scan_fwd_try_channel_last(const cm_scan_fwd_args& a, int lpc, cudaStream_t st, int* rc);   // scan_fwd_cl.cu
 int scan_fwd_try_state_parallel(const cm_scan_fwd_args& a, cudaStream_t st, int* rc);            // scan_fwd_sp.cu
+int64_t scan_fwd_sp_workspace_bytes(const cm_scan_fwd_args& a);                                  // scan_fwd_sp.cu
+}
+
+extern "C" int64_t cm_scan_fwd_workspace_bytes(const cm_scan_fwd_args* args) {
+  if (args == nullptr || args->batch <= 0 || args->dim <= 0 || args->seqlen <= 0) return 0;
+  if (args->ndir != 1 && args->ndir != 2) return 0;
+  if (args->lanes_per_channel != 0 || getenv("CM_SCAN_GENERIC") != nullptr || getenv("CM_SCAN_NO_SP") != nullptr) return 0;
+  return cm::scan_fwd_sp_workspace_bytes(*args);
 }
 
 extern "C" int cm_scan_fwd(const cm_scan_fwd_args* args, void* stream) {

@@ -43,6 +43,7 @@ struct FwdDir {
   int64_t u_sb, dl_sb, b_sb, c_sb, z_sb, out_sb, pre_sb;   // batch strides (bytes)
   int32_t u_ss, dl_ss, b_ss, c_ss, z_ss, out_ss, pre_ss;   // bytes per processed step
   int32_t s1;                                              // length of the first range (cm_first_range)
+  int32_t reverse, pad0;
   const float* A;
   int64_t A_sd, A_sn;
   const float *Dskip, *bias;
@@ -55,7 +56,12 @@ struct FwdParams {
   int32_t L;
   uint32_t flags;
   float scale;
-  int32_t pad;
+  int32_t dim;
+  // time windows (small-batch long sequences): grid.z = window; W == 0: one window = the whole sequence
+  int32_t W, nwin, summary, ndir;
+  float* ws_state;     // [batch][ndir][nwin][dim][16]: pass 1 writes each window's end state from zero, the combine kernel
+                       // turns it in place into the window's INCOMING state, pass 2 starts from it
+  float* ws_sumdt;     // [batch][ndir][nwin][dim]: sum of Delta over the window (decay of the window = exp(A * sum))
   FwdDir dir[2];
 };
 
@@ -128,11 +134,24 @@ __device__ __forceinline__ void warp_arrive(uint64_t* b, int lane) {
 // The 8 partial products of a (step, channel pair) come from the 8 lanes of ONE warp, so the recurrence warps reduce
 // them themselves after the tile (warp-private buffer, __syncwarp only) - the XU-bound warps have the issue slots.
 
+// Processed-step ranges of this CTA's window for one direction: range 0 = [lo, mid), range 1 = [mid, hi).  In a
+// bidirectional launch the ascending direction first covers the first half of the window's time span and the descending
+// one the second half (stash), then each finishes the other half (combine).  Summary launches have a single range.
 template <int NDIR>
-__device__ __forceinline__ void range_of(const FwdDir& d, int L, int range, int* s_begin, int* s_end) {
-  *s_begin = range == 0 ? 0 : d.s1;
-  *s_end = (NDIR == 1 || range == 1) ? L : d.s1;
-  if (NDIR == 1) *s_begin = 0;
+__device__ __forceinline__ void window_ranges(const FwdParams& P, const FwdDir& d, int* lo, int* mid, int* hi) {
+  const int L = P.L;
+  if (P.W == 0) {
+    *lo = 0; *hi = L; *mid = (NDIR == 2) ? d.s1 : L;
+    return;
+  }
+  const int t0 = blockIdx.z * P.W, t1 = min(t0 + P.W, L), n = t1 - t0;
+  const int first = (NDIR == 2 && !P.summary) ? (d.reverse ? n - cm_mid(n) : cm_mid(n)) : n;
+  *lo = d.reverse ? L - t1 : t0;
+  *hi = d.reverse ? L - t0 : t1;
+  *mid = *lo + first;
+}
+__device__ __forceinline__ int64_t ws_row(const FwdParams& P, int b, int dir, int w) {
+  return ((int64_t)b * P.ndir + dir) * P.nwin + w;
 }
 
 // ---- recurrence warps (2 per direction): lane = states 4m..4m+3 of channel pair pr -------------------------------
@@ -156,13 +175,20 @@ __device__ __forceinline__ void scan_role(const FwdParams& P, FwdSmem& S, const 
     }
   }
   float* ckp = d.ckpt ? d.ckpt + b * d.ckpt_sb + (int64_t)c0 * d.ckpt_sd + 4 * m : nullptr;
+  const bool summary = P.summary != 0;
+  float* wsp = P.ws_state ? P.ws_state + (ws_row(P, b, DIR, blockIdx.z) * P.dim + c0) * 16 + 4 * m : nullptr;
+  if (wsp != nullptr && !summary) {               // pass 2 of a windowed launch: the window's incoming state
+    const float4 v0 = *reinterpret_cast<const float4*>(wsp), v1 = *reinterpret_cast<const float4*>(wsp + 16);
+    h[0] = make_float2(v0.x, v1.x); h[1] = make_float2(v0.y, v1.y); h[2] = make_float2(v0.z, v1.z); h[3] = make_float2(v0.w, v1.w);
+  }
+  int s_lo, s_mid, s_hi;
+  window_ranges<NDIR>(P, d, &s_lo, &s_mid, &s_hi);
   int it = 0;
 #pragma unroll 1
   for (int range = 0; range < NDIR; ++range) {
     if (NDIR == 2 && range == 1) __syncthreads();   // partner's stash of the other half is complete
-    int s_begin, s_end;
-    range_of<NDIR>(d, P.L, range, &s_begin, &s_end);
-    int jck = range == 0 ? 0 : cm_ceil_div(d.s1, CM_SCAN_CKPT_STEPS);   // next checkpoint slot
+    const int s_begin = range == 0 ? s_lo : s_mid, s_end = (NDIR == 1 || range == 1) ? s_hi : s_mid;
+    int jck = range == 0 ? 0 : cm_ceil_div(d.s1, CM_SCAN_CKPT_STEPS);   // next checkpoint slot (unwindowed launches only)
     const int nst = s_end - s_begin;
     const int ntile = nst > 0 ? cm_ceil_div(nst, kT) : 0;
 #pragma unroll 1
@@ -171,7 +197,7 @@ __device__ __forceinline__ void scan_role(const FwdParams& P, FwdSmem& S, const 
       const uint32_t par = (it >> 1) & 1;
       const int nvalid = nst - t * kT;    // steps of this tile inside the range (may exceed kT)
       mbar_wait(&S.in_full[slot], par);
-      if (it >= 2) mbar_wait(&S.p_empty[slot], par ^ 1);
+      if (it >= 2 && !summary) mbar_wait(&S.p_empty[slot], par ^ 1);
       const float4* ddb = &S.dd[slot][0][pr];
       const float* bcb = &S.bc[slot][0][4 * m];
       float* pb = &S.p[warp][0][g][2 * m];
@@ -219,13 +245,19 @@ __device__ __forceinline__ void scan_role(const FwdParams& P, FwdSmem& S, const 
           const float c4[4] = {cc[i].x, cc[i].y, cc[i].z, cc[i].w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) h[j] = ffma2(a[i][j], h[j], ub[i][j]);
-          float2 pp = fmul2(make_float2(c4[0], c4[0]), h[0]);
+          if (!summary) {
+            float2 pp = fmul2(make_float2(c4[0], c4[0]), h[0]);
 #pragma unroll
-          for (int j = 1; j < 4; ++j) pp = ffma2(make_float2(c4[j], c4[j]), h[j], pp);
-          *reinterpret_cast<float2*>(pb + (sb * kSub + i) * 64) = pp;
+            for (int j = 1; j < 4; ++j) pp = ffma2(make_float2(c4[j], c4[j]), h[j], pp);
+            *reinterpret_cast<float2*>(pb + (sb * kSub + i) * 64) = pp;
+          }
         }
       }
       __syncwarp();
+      if (summary) {                                // state-only pass: nothing to hand to the IO warps
+        if (lane == 0) mbar_arrive(&S.in_empty[slot]);
+        continue;
+      }
       // reduce this warp's 128 (step, pair) rows of 8 floats (4 lanes x 2 channels): lane -> rows lane + 32 j.  The two
       // 16-byte halves are read in an order that depends on the row, which keeps the LDS.128 conflict-free.
 #pragma unroll
@@ -245,7 +277,13 @@ __device__ __forceinline__ void scan_role(const FwdParams& P, FwdSmem& S, const 
       }
     }
   }
-  if (d.last != nullptr) {
+  if (summary) {                                  // pass 1: end state of the window started from zero
+    *reinterpret_cast<float4*>(wsp) = make_float4(h[0].x, h[1].x, h[2].x, h[3].x);
+    *reinterpret_cast<float4*>(wsp + 16) = make_float4(h[0].y, h[1].y, h[2].y, h[3].y);
+    return;
+  }
+  const bool final_window = P.W == 0 || blockIdx.z == (d.reverse ? 0 : P.nwin - 1);
+  if (d.last != nullptr && final_window) {
     float* ls = d.last + b * d.ls_sb + (int64_t)c0 * d.ls_sd + 4 * m * d.ls_sn;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -286,13 +324,16 @@ __device__ __forceinline__ void io_role(const FwdParams& P, FwdSmem& S, const in
 
   typename P2::Raw ru[kIU], rdl[kIU], uprev[kIU], rz[kIU], rst[kIU];
   typename Q4::Raw rbc[kNBC];
+  const bool summary = P.summary != 0;
+  float2 sumdt = make_float2(0.f, 0.f);
+  int s_lo, s_mid, s_hi;
+  window_ranges<NDIR>(P, d, &s_lo, &s_mid, &s_hi);
   int it = 0;
 #pragma unroll 1
   for (int range = 0; range < NDIR; ++range) {
     if (NDIR == 2 && range == 1) __syncthreads();   // partner's stash of the other half is complete
     const int mode = (NDIR == 1) ? FM_UNI : (range == 0 ? FM_STASH : FM_COMBINE);
-    int s_begin, s_end;
-    range_of<NDIR>(d, P.L, range, &s_begin, &s_end);
+    const int s_begin = range == 0 ? s_lo : s_mid, s_end = (NDIR == 1 || range == 1) ? s_hi : s_mid;
     const int nst = s_end - s_begin;
     const int ntile = nst > 0 ? cm_ceil_div(nst, kT) : 0;
     const bool need_z = has_z && mode != FM_STASH;
@@ -324,6 +365,7 @@ __device__ __forceinline__ void io_role(const FwdParams& P, FwdSmem& S, const in
         float2 dt = fadd2(P2::cvt(rdl[i]), bias);
         if (softplus) { dt.x = softplus_fwd<PRECISE>(dt.x); dt.y = softplus_fwd<PRECISE>(dt.y); }
         if (sb0 + k >= s_end) dt = make_float2(0.f, 0.f);   // a = 1, input 0: a missing step leaves the state unchanged
+        sumdt = fadd2(sumdt, dt);
         const float2 du = fmul2(dt, u2);
         S.dd[slot][k][cp] = make_float4(dt.x, dt.y, du.x, du.y);
       }
@@ -388,12 +430,29 @@ __device__ __forceinline__ void io_role(const FwdParams& P, FwdSmem& S, const in
 #pragma unroll
       for (int i = 0; i < kIU; ++i) ucur[i] = ru[i];
       if (t + 1 < ntile) load_raw(sb0 + kT);
-      if (t > 0) epilogue(sb0 - kT, it - 1);      // uses uprev, rz, rst of tile t-1
-      load_epi(sb0);
+      if (!summary) {
+        if (t > 0) epilogue(sb0 - kT, it - 1);      // uses uprev, rz, rst of tile t-1
+        load_epi(sb0);
+      }
 #pragma unroll
       for (int i = 0; i < kIU; ++i) uprev[i] = ucur[i];
     }
-    if (ntile > 0) epilogue(s_begin + (ntile - 1) * kT, it - 1);
+    if (ntile > 0 && !summary) epilogue(s_begin + (ntile - 1) * kT, it - 1);
+  }
+  if (summary) {
+    // sum of Delta over the window per channel: the kIKS threads that share a channel pair combine through shared memory
+    // (the y ring is idle in this pass; the recurrence warps never touch it)
+    float2* scratch = &S.y[0][0][0];
+    if (DIR == 0) asm volatile("bar.sync 1, %0;" ::"n"(kIO) : "memory"); else asm volatile("bar.sync 2, %0;" ::"n"(kIO) : "memory");
+    scratch[io] = sumdt;
+    if (DIR == 0) asm volatile("bar.sync 1, %0;" ::"n"(kIO) : "memory"); else asm volatile("bar.sync 2, %0;" ::"n"(kIO) : "memory");
+    if (io < kNP) {
+      float2 a = scratch[io];
+#pragma unroll
+      for (int q = 1; q < kIKS; ++q) a = fadd2(a, scratch[io + q * kNP]);
+      float* dst = P.ws_sumdt + ws_row(P, b, DIR, blockIdx.z) * P.dim + c_base + 2 * io;
+      dst[0] = a.x; dst[1] = a.y;
+    }
   }
 }
 
@@ -439,10 +498,13 @@ static bool build_params(const cm_scan_fwd_args& a, FwdParams* P) {
   P->L = a.seqlen;
   P->flags = a.flags;
   P->scale = a.out_scale;
-  P->pad = 0;
+  P->dim = a.dim;
+  P->W = 0; P->nwin = 1; P->summary = 0; P->ndir = a.ndir;
+  P->ws_state = nullptr; P->ws_sumdt = nullptr;
   for (int r = 0; r < a.ndir; ++r) {
     const cm_scan_dir& s = a.dir[r];
     FwdDir& d = P->dir[r];
+    d.reverse = s.reverse != 0; d.pad0 = 0;
     if (s.bc_const) return false;
     if (!t_ok<T>(s.u, 2) || !t_ok<T>(s.delta, 2) || !t_ok<T>(s.Bm, 4) || !t_ok<T>(s.Cm, 4)) return false;
     if (s.ckpt != nullptr && ((reinterpret_cast<uintptr_t>(s.ckpt) & 15) != 0 || (s.ckpt_sb % 4) != 0 || (s.ckpt_sd % 4) != 0))
@@ -475,6 +537,55 @@ static bool build_params(const cm_scan_fwd_args& a, FwdParams* P) {
   return true;
 }
 
+// Serial pass over the windows of a row: turns each window's end-state-from-zero into its incoming state, in place.
+__global__ void __launch_bounds__(256) window_combine_kernel(const FwdParams P, int batch) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)batch * P.ndir * P.dim * 16;
+  if (idx >= total) return;
+  const int n = (int)(idx & 15);
+  const int c = (int)((idx >> 4) % P.dim);
+  const int dir = (int)((idx / (16 * (int64_t)P.dim)) % P.ndir);
+  const int b = (int)(idx / (16 * (int64_t)P.dim * P.ndir));
+  const FwdDir& d = P.dir[dir];
+  const float kA = __ldg(d.A + (int64_t)c * d.A_sd + n * d.A_sn) * kLog2e;
+  float h = 0.f;
+  for (int i = 0; i < P.nwin; ++i) {
+    const int w = d.reverse ? P.nwin - 1 - i : i;        // processing order of the direction
+    const int64_t row = ws_row(P, b, dir, w);
+    float* sp_ = P.ws_state + (row * P.dim + c) * 16 + n;
+    const float end0 = *sp_;
+    const float sd = P.ws_sumdt[row * P.dim + c];
+    *sp_ = h;
+    h = fmaf(ex2(kA * sd), h, end0);
+  }
+}
+
+// Windows over time pay the recurrence twice but multiply the number of CTAs: worth it when a whole-sequence launch
+// leaves most SMs idle (inference on a few long utterances, BASELINE config 5).  Training launches (checkpoints) are
+// never windowed: the backward kernel walks whole sequences.
+static int plan_windows(const cm_scan_fwd_args& a, int* W) {
+  *W = 0;
+  for (int r = 0; r < a.ndir; ++r)
+    if (a.dir[r].ckpt != nullptr) return 1;
+  if (getenv("CM_SCAN_NO_WINDOWS") != nullptr) return 1;
+  const int64_t ctas = (int64_t)(a.dim / kCH) * a.batch;
+  const int64_t slots = 148 * 3;
+  if (ctas * 2 > slots || a.seqlen < 1024) return 1;
+  int want = (int)((slots + ctas - 1) / ctas);
+  if (const char* e = getenv("CM_SCAN_WINDOWS")) want = atoi(e);   // A/B measurements
+  if (want < 2) return 1;
+  int w = (a.seqlen + want - 1) / want;
+  w = (w + 63) / 64 * 64;
+  if (w < 256) w = 256;
+  const int nwin = (a.seqlen + w - 1) / w;
+  if (nwin < 2) return 1;
+  *W = w;
+  return nwin;
+}
+static int64_t window_bytes(const cm_scan_fwd_args& a, int nwin) {
+  return (int64_t)a.batch * a.ndir * nwin * a.dim * (16 + 1) * (int64_t)sizeof(float);
+}
+
 template <typename T, int NDIR>
 static int launch_one(const FwdParams& P, const cm_scan_fwd_args& a, cudaStream_t st) {
   const size_t smem = sizeof(FwdSmem) * NDIR;
@@ -485,7 +596,7 @@ static int launch_one(const FwdParams& P, const cm_scan_fwd_args& a, cudaStream_
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  kern<<<dim3(a.dim / kCH, a.batch), NDIR * (kGT + kIO), smem, st>>>(P);
+  kern<<<dim3(a.dim / kCH, a.batch, P.nwin), NDIR * (kGT + kIO), smem, st>>>(P);
   CM_LAUNCH_CHECK();
   return 0;
 }
@@ -494,11 +605,33 @@ template <typename T>
 static int try_t(const cm_scan_fwd_args& a, cudaStream_t st, int* rc) {
   FwdParams P;
   if (!build_params<T>(a, &P)) return 0;
+  int W = 0;
+  const int nwin = plan_windows(a, &W);
+  if (nwin > 1 && a.workspace != nullptr && a.workspace_bytes >= window_bytes(a, nwin) &&
+      (reinterpret_cast<uintptr_t>(a.workspace) & 15) == 0) {
+    P.W = W; P.nwin = nwin;
+    P.ws_state = static_cast<float*>(a.workspace);
+    P.ws_sumdt = P.ws_state + (int64_t)a.batch * a.ndir * nwin * a.dim * 16;
+    P.summary = 1;
+    *rc = (a.ndir == 2) ? launch_one<T, 2>(P, a, st) : launch_one<T, 1>(P, a, st);
+    if (*rc) return 1;
+    const int64_t total = (int64_t)a.batch * a.ndir * a.dim * 16;
+    window_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P, a.batch);
+    P.summary = 0;
+  }
   *rc = (a.ndir == 2) ? launch_one<T, 2>(P, a, st) : launch_one<T, 1>(P, a, st);
   return 1;
 }
 
 }  // namespace sp
+
+// bytes of caller-provided workspace that let cm_scan_fwd split this launch into time windows (0: not useful)
+int64_t scan_fwd_sp_workspace_bytes(const cm_scan_fwd_args& a) {
+  if (a.dstate != 16 || a.dim % sp::kCH != 0) return 0;
+  int W = 0;
+  const int nwin = sp::plan_windows(a, &W);
+  return nwin > 1 ? sp::window_bytes(a, nwin) : 0;
+}
 
 // returns 1 if launched (result in *rc), 0 if the state-parallel path does not apply
 int scan_fwd_try_state_parallel(const cm_scan_fwd_args& a, cudaStream_t st, int* rc) {

@@ -185,6 +185,11 @@ def scan_forward(dirs, z=None, out_scale=1.0, delta_softplus=False, need_ckpt=Fa
     a.out = cabi.t3(out)
     out_pre = empty_like_bdl(u0) if need_out_pre else None
     a.out_pre = cabi.t3(out_pre)
+    ws_bytes = lib.cm_scan_fwd_workspace_bytes(C.byref(a))   # > 0: few long sequences, no checkpoints -> time windows
+    if ws_bytes > 0:
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=u0.device)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws_bytes
+        keep.append(ws)
     _call("cm_scan_fwd", lib.cm_scan_fwd, C.byref(a), cabi.stream_ptr())
     return dict(out=out, out_pre=out_pre, ckpt=ckpts, last_state=lasts)
 

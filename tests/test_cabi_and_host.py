@@ -24,7 +24,7 @@ def lib():
 def _declared_entry_points():
     src = open(os.path.join(ROOT, "include", "conmamba_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"^\s*int\s+(cm_\w+)\s*\(", src, flags=re.M)))
+    return sorted(set(re.findall(r"^\s*(?:int|int64_t)\s+(cm_\w+)\s*\(", src, flags=re.M)))
 
 
 def test_library_exports_every_declared_symbol(lib):

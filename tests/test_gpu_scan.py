@@ -377,3 +377,40 @@ def test_long_sequence_forward_matches_lane_per_channel_kernel(monkeypatch):
         monkeypatch.setenv("CM_SCAN_NO_SP", "1")
         o_old = run()
         assert_close(o_sp, o_old, dtype, floor="max", what=f"long forward {dtype}")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape,windows", [((2, 32, 1500), 3), ((1, 64, 2049), 5), ((2, 32, 1024), 4)])
+def test_time_windowed_forward_equals_whole_sequence_launch(dtype, shape, windows, monkeypatch):
+    """Chunk-parallel launch (per-window summaries -> serial combine -> windows from their incoming states) against the
+    whole-sequence launch of the same kernel and against the oracle: bidirectional fused, unidirectional + last state."""
+    from mamba_asr_b200 import kernels as K
+    from oracle.scan_ref import selective_scan_oracle
+    Bt, D, L = shape
+    N = 16
+    f = make_scan_inputs(Bt, D, L, N, dtype, seed=81)
+    bw = make_scan_inputs(Bt, D, L, N, dtype, seed=82)
+    dirs = []
+    for src, rev in ((f, False), (bw, True)):
+        c = _cuda(src, "cl")
+        dirs.append(dict(u=c["u"], delta=c["delta"], A=c["A"], B=c["B"], C=c["C"], D=c["D"],
+                         delta_bias=c["delta_bias"], reverse=rev))
+    zc = channel_last(f["z"].cuda())
+    monkeypatch.setenv("CM_SCAN_NO_WINDOWS", "1")
+    whole_bi = K.scan_forward(dirs, z=zc, out_scale=0.5, delta_softplus=True)["out"].float()
+    whole_uni = K.scan_forward(dirs[1:], z=zc, delta_softplus=True, need_last_state=True)
+    monkeypatch.delenv("CM_SCAN_NO_WINDOWS")
+    monkeypatch.setenv("CM_SCAN_WINDOWS", str(windows))
+    win_bi = K.scan_forward(dirs, z=zc, out_scale=0.5, delta_softplus=True)["out"].float()
+    win_uni = K.scan_forward(dirs[1:], z=zc, delta_softplus=True, need_last_state=True)
+    assert_close(win_bi, whole_bi, dtype, floor="max", what="windowed bidir vs whole")
+    assert_close(win_uni["out"].float(), whole_uni["out"].float(), dtype, floor="max", what="windowed uni vs whole")
+    assert_close(win_uni["last_state"][0], whole_uni["last_state"][0], dtype, floor="max", what="windowed last state")
+    fl = lambda t: t.flip(-1)
+    of = selective_scan_oracle(f["u"], f["delta"], f["A"], f["B"], f["C"], f["D"], f["z"], f["delta_bias"], True)
+    ob = selective_scan_oracle(fl(bw["u"]), fl(bw["delta"]), bw["A"], fl(bw["B"]), fl(bw["C"]), bw["D"], fl(f["z"]),
+                               bw["delta_bias"], True)
+    # the oracle composition rounds each direction to the I/O dtype before the add (bimamba.py:250-253): for bf16 the
+    # floor is the magnitude of the summands
+    assert_close(win_bi, 0.5 * of.float() + 0.5 * fl(ob).float(), dtype, floor="rms" if dtype == torch.float32 else "max",
+                 what="windowed bidir vs oracle")

@@ -1,2 +1,9 @@
-timeout 900 python -m pytest tests/test_gpu_scan.py -q -m gpu -x 2>&1 | tail -6
-for nw in 1 0; do if [ $nw = 1 ]; then export CM_SCAN_NO_WINDOWS=1; else unset CM_SCAN_NO_WINDOWS; fi; echo "NO_WINDOWS=$nw"; timeout 300 python tools/prof_kernels.py --cfg 5_1k,5_4k,5,5_30k --only scan_fwd_infer 2>&1 | grep scan_fwd; done
+timeout 900 python -m pytest tests/test_gpu_conv_mamba_fbank.py -q -m gpu 2>&1 | tail -3
+for wl in conmamba_small_ctc_fwdbwd_b32x15s conmamba_large_ctc_fwdbwd_b64x20s; do
+timeout 900 python bench.py --steps 8 --warmup 3 --workload $wl --no-cpu-baseline > gpurun_out/bench_x.log 2> gpurun_out/bench_x.err; python - <<EOF2
+import json
+l=[x for x in open("gpurun_out/bench_x.log") if x.startswith("{")]
+d=json.loads(l[-1]); print({k:d[k] for k in ("value","ms_per_step","gpu_launches","loss")})
+EOF2
+done
+timeout 600 python tools/step_profile.py --workload conmamba_large_ctc_fwdbwd_b64x20s --top 40 2>&1 | tee gpurun_out/step_profile_large2.log | tail -42

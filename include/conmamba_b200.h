@@ -275,6 +275,15 @@ int cm_dwconv_num_part(int32_t batch, int32_t seqlen, int32_t ksize);
 int cm_dwconv_fwd(const cm_dwconv_args* args, void* stream);
 int cm_dwconv_bwd_weight(const cm_dwconv_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Column sums of a (rows, cols) matrix = bias gradient of a Linear / pointwise conv (SURVEY.md section 8(f) rank 2;
+ * the six biased Linear layers around each Mamba block, reference modules/Conmamba.py:595-621).
+ * Writes cm_colsum_num_part(rows) partial rows part[n_part][cols] (fp32); sum them with cm_reduce_multi.
+ * cols and row_stride must be even (pair accesses): CM_ERR_UNSUPPORTED otherwise.
+ * ---------------------------------------------------------------------------------------------------- */
+int cm_colsum_num_part(int64_t rows);
+int cm_colsum(const void* x, int64_t rows, int32_t cols, int64_t row_stride, int32_t dtype, float* part, void* stream);
+
 /* library identification: returns CM_ABI_VERSION; writes the compiled-for arch (e.g. 100) to *sm_arch if non-NULL */
 int cm_version(int32_t* sm_arch);
 /* sizeof() of the argument structs, for binding self-checks: 0 cm_tensor3, 1 cm_scan_dir, 2 cm_scan_fwd_args,

@@ -24,7 +24,7 @@ EXPORTS = (
     "cm_scan_bwd",
     "cm_reduce_dbc", "cm_reduce_rows", "cm_conv_fwd", "cm_conv_num_part", "cm_conv_bwd", "cm_conv_update",
     "cm_fbank_logmel", "cm_fbank_floor", "cm_abi_sizeof", "cm_reduce_multi", "cm_layernorm_num_part", "cm_layernorm_fwd",
-    "cm_layernorm_bwd", "cm_scan_fwd_workspace_bytes", "cm_dwconv_num_part", "cm_dwconv_fwd", "cm_dwconv_bwd_weight",
+    "cm_layernorm_bwd", "cm_scan_fwd_workspace_bytes", "cm_dwconv_num_part", "cm_dwconv_fwd", "cm_dwconv_bwd_weight", "cm_colsum_num_part", "cm_colsum",
 )
 CM_REDUCE_MAX_JOBS = 8
 
@@ -164,6 +164,8 @@ def lib():
         L.cm_layernorm_num_part.argtypes = [C.c_int64]
         L.cm_layernorm_fwd.argtypes = [C.POINTER(LayerNormArgs), C.c_void_p]
         L.cm_layernorm_bwd.argtypes = [C.POINTER(LayerNormArgs), C.c_void_p]
+        L.cm_colsum_num_part.argtypes = [C.c_int64]
+        L.cm_colsum.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
         L.cm_dwconv_num_part.argtypes = [C.c_int32, C.c_int32, C.c_int32]
         L.cm_dwconv_fwd.argtypes = [C.POINTER(DwConvArgs), C.c_void_p]
         L.cm_dwconv_bwd_weight.argtypes = [C.POINTER(DwConvArgs), C.c_void_p]

@@ -24,6 +24,7 @@ from .bimamba import UniMamba as Mamba
 from .dwconv import depthwise_conv1d
 from .kernels import DWCONV_KSIZES
 from .layernorm import FusedLayerNorm
+from .linear import BiasGradLinear, linear as _linear
 
 LAYER_NORM_EPS = 1e-6        # reference ConMambaConstants.LAYER_NORM_EPS (Conmamba.py:687)
 FFN_RESIDUAL_SCALE = 0.5     # reference ConMambaConstants.FFN_RESIDUAL_SCALE (Conmamba.py:638,649)
@@ -56,8 +57,8 @@ class PositionalwiseFeedForward(nn.Module):
 
     def __init__(self, d_ffn, input_size, dropout=0.0, activation=nn.ReLU):
         super().__init__()
-        self.ffn = nn.Sequential(nn.Linear(input_size, d_ffn), activation(), nn.Dropout(dropout),
-                                 nn.Linear(d_ffn, input_size))
+        self.ffn = nn.Sequential(BiasGradLinear(input_size, d_ffn), activation(), nn.Dropout(dropout),
+                                 BiasGradLinear(d_ffn, input_size))
 
     def forward(self, x):
         return self.ffn(x)
@@ -79,7 +80,7 @@ class ConvolutionModule(nn.Module):
                                         nn.GLU(dim=1))
         self.conv = nn.Conv1d(input_size, input_size, kernel_size=kernel_size, stride=1, padding=self.padding,
                               dilation=dilation, groups=input_size, bias=bias)
-        self.after_conv = nn.Sequential(FusedLayerNorm(input_size), activation(), nn.Linear(input_size, input_size, bias=bias),
+        self.after_conv = nn.Sequential(FusedLayerNorm(input_size), activation(), BiasGradLinear(input_size, input_size, bias=bias),
                                         nn.Dropout(dropout))
         # channel-last evaluation on the sm_100a depthwise kernel (no transposes); the CPU reference arm
         # (oracle/cpu_encoder.py) clears the flag and gets the reference's own torch op chain below
@@ -91,7 +92,7 @@ class ConvolutionModule(nn.Module):
                                       "(TransformerASR.py:783-788 passes no config)")
         if self.use_kernel:
             pw = self.bottleneck[0]                                   # pointwise conv = Linear over channel-last rows
-            out = F.glu(F.linear(self.layer_norm(x), pw.weight.squeeze(-1), pw.bias), dim=-1)
+            out = F.glu(_linear(self.layer_norm(x), pw.weight.squeeze(-1), pw.bias), dim=-1)
             out = depthwise_conv1d(out, self.conv.weight, self.conv.bias, pad_left=self.padding)
             out = self.after_conv(out)
             if mask is not None:

@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .linear import BiasGradLinear
 from .conmamba import ConmambaEncoder
 from .fbank import Fbank
 
@@ -85,13 +86,13 @@ class ConMambaCTC(nn.Module):
         self.compute_features = Fbank(sample_rate=16000, n_fft=n_fft, n_mels=n_mels, win_length=win_length)
         self.normalize = InputNormalization()
         self.CNN = ConvFrontEnd(n_mels)
-        self.custom_src_module = nn.Sequential(nn.Linear(self.CNN.out_features, d_model), nn.Dropout(dropout))
+        self.custom_src_module = nn.Sequential(BiasGradLinear(self.CNN.out_features, d_model), nn.Dropout(dropout))
         mamba_config = dict(d_state=d_state, expand=expand, d_conv=d_conv, bidirectional=bidirectional)
         # Transformer.py:740-751: encoder activation is branchformer_activation (GELU), kernel 31, bias, non-causal
         self.encoder = ConmambaEncoder(num_layers=num_layers, d_model=d_model, d_ffn=d_ffn, kernel_size=31,
                                        activation=nn.GELU, bias=True, dropout=dropout, causal=False,
                                        mamba_config=mamba_config)
-        self.ctc_lin = nn.Linear(d_model, output_neurons)
+        self.ctc_lin = BiasGradLinear(d_model, output_neurons)
         for p in list(self.custom_src_module.parameters()) + list(self.encoder.parameters()):
             if p.dim() > 1:
                 nn.init.xavier_normal_(p)                          # TransformerASR.py:1051-1054

@@ -532,3 +532,21 @@ def dwconv_backward_weight(x_blc, dy_blc, ksize, pad_left, need_bias=True):
         jobs.append((db_part, db))
     reduce_many(jobs)
     return dw.view(Cn, ksize), db
+
+
+# ------------------------------------------------------------------------------------------------ column sums (bias grads)
+def colsum(x2d):
+    """fp32 column sums of a (rows, cols) CUDA matrix with unit column stride (cm_colsum + fixed-order reduction).
+    Returns None when the shape is outside the kernel's envelope (odd cols / stride): the caller uses torch.sum."""
+    lib = cabi.lib()
+    _require_cuda(x2d, "x")
+    rows, cols = x2d.shape
+    if x2d.stride(1) != 1 or (cols & 1) or (x2d.stride(0) & 1) or x2d.data_ptr() % (2 * x2d.element_size()):
+        return None
+    n_part = lib.cm_colsum_num_part(rows)
+    part = torch.empty((n_part, cols), dtype=torch.float32, device=x2d.device)
+    _call("cm_colsum", lib.cm_colsum, x2d.data_ptr(), rows, cols, x2d.stride(0), cabi.dtype_code(x2d.dtype), part.data_ptr(),
+          cabi.stream_ptr())
+    out = torch.empty((cols,), dtype=torch.float32, device=x2d.device)
+    reduce_many([(part, out)])
+    return out

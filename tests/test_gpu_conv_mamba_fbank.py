@@ -344,3 +344,29 @@ def test_convolution_module_kernel_path_equals_reference_op_chain(causal, monkey
             mod.__class__ = torch.nn.LayerNorm
     y_t = m(x)
     assert_close(y_k, y_t, what="conv module")
+
+
+@pytest.mark.parametrize("shape", [(3, 501, 256, 1024), (2, 37, 144, 576), (1, 5, 32, 10), (4, 9, 64, 11)])
+@pytest.mark.parametrize("autocast", [False, True])
+def test_bias_grad_linear_matches_nn_linear(shape, autocast):
+    """BiasGradLinear (cm_colsum for db, cuBLAS for the rest) against nn.Linear: output and every gradient, fp32 and
+    under bf16 autocast; odd output widths take torch's own reduction."""
+    from mamba_asr_b200.linear import BiasGradLinear
+    Bt, L, cin, cout = shape
+    torch.manual_seed(5)
+    ref = torch.nn.Linear(cin, cout).cuda()
+    mine = BiasGradLinear(cin, cout).cuda()
+    mine.load_state_dict(ref.state_dict())
+    x = torch.randn(Bt, L, cin, device="cuda")
+    cot = torch.randn(Bt, L, cout, device="cuda")
+    outs = []
+    for m in (ref, mine):
+        xi = x.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            y = m(xi)
+        (y.float() * cot).sum().backward()
+        outs.append((y.float(), xi.grad, m.weight.grad, m.bias.grad))
+    dt = torch.bfloat16 if autocast else torch.float32
+    for a, b, nm in zip(outs[1], outs[0], ("y", "dx", "dw", "db")):
+        assert a.dtype == b.dtype
+        assert_close(a.float(), b.float(), dt, floor="max", what="linear " + nm)

@@ -179,6 +179,13 @@ __device__ __forceinline__ void scan_role(const BwdParams& P, BwdSmem& S, const 
     // steps are parked in shared memory (all 8 in shared memory cost 16 of the 86 LSU wavefronts per warp-step that bound
     // the first version of this kernel; all 8 in registers spill)
     float2 hist[kHR > 0 ? kHR : 1][4];
+#ifdef CM_ABL_NO_FWD
+#pragma unroll
+    for (int k = 0; k < kHR; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) hist[k][j] = h[j];
+    if (mu[1].x == 123.456f)
+#endif
 #pragma unroll
     for (int k = 0; k < kTB; ++k) {
       const float4 dd = ddb[k * kNP];
@@ -237,12 +244,26 @@ __device__ __forceinline__ void scan_role(const BwdParams& P, BwdSmem& S, const 
         r2 = ffma2(q, kA[j], r2);
         mu[j] = fmul2(a, lam);
       }
+#ifdef CM_ABL_NO_PB
+      if (dBv[0] == 123.456f)
+#endif
       S.pb[warp][k][0][g][m] = make_float4(dBv[0], dBv[1], dBv[2], dBv[3]);
+#ifdef CM_ABL_NO_PB
+      if (dCv[0] == 123.456f)
+#endif
       S.pb[warp][k][1][g][m] = make_float4(dCv[0], dCv[1], dCv[2], dCv[3]);
+#ifdef CM_ABL_NO_PB
+      if (r1.x == 123.456f)
+#endif
       S.pr[warp][k][g][m] = make_float4(r1.x, r1.y, r2.x, r2.y);
     }
     __syncwarp();
     if (i >= 2) mbar_wait(&S.out_empty[slot], par ^ 1);
+#ifdef CM_ABL_NO_PB
+    if (mu[0].x == 123.456f) {
+#else
+    {
+#endif
     // ---- warp-local reductions
     // (step, pair) -> sum over the pair's 4 lanes of (r1, r2): 64 units, 2 per lane
 #pragma unroll
@@ -271,6 +292,7 @@ __device__ __forceinline__ void scan_role(const BwdParams& P, BwdSmem& S, const 
         a1 = fadd2(a1, make_float2(v.z, v.w));
       }
       *reinterpret_cast<float4*>(&S.bcw[slot][warp][k][which * 16 + 4 * mm]) = make_float4(a0.x, a0.y, a1.x, a1.y);
+    }
     }
     __syncwarp();
     if (lane == 0) {

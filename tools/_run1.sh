@@ -1,2 +1,2 @@
-timeout 900 python -m pytest tests/test_gpu_scan.py -q -m gpu -x 2>&1 | tail -4
-timeout 300 python tools/prof_kernels.py --cfg 2,3,4,5_4k --only scan_bwd 2>&1 | grep scan_bwd | cut -c1-125
+timeout 600 python -m pytest tests/test_gpu_conv_mamba_fbank.py -q -m gpu -k "layernorm" 2>&1 | tail -3
+timeout 300 python tools/prof_kernels.py --cfg 2,3 --only aux 2>&1 | grep "ln_"

@@ -118,6 +118,35 @@ def main():
                 print("%-40s scan_bwd kernel  best %.3f ms              alg %.1f GB/s (%.1f%%)  %.1f ps/pos ; reducers %s"
                       % (tag, best, byts / best / 1e6, 100 * byts / best / 1e6 / peak, best * 1e9 / pos,
                          {k: round(min(v), 4) for k, v in kt.items() if k != "cm_scan_bwd"}))
+        tag = "cfg%s B%d D%d L%d %s" % (cfg, Bt, D, L, args.dtype)
+        if "aux" in only:
+            # LayerNorm / depthwise conv / column sums at the layer's (rows, d_model) shape
+            d_model = D // 2
+            rows = Bt * L
+            for xdt, ydt in ((torch.float32, dt), (dt, dt)):
+                xs_, ys_ = (4 if xdt == torch.float32 else 2), (4 if ydt == torch.float32 else 2)
+                xx = rn(rows, d_model).to(xdt)
+                w, bb = torch.ones(d_model, device=dev), torch.zeros(d_model, device=dev)
+                best, med = timek(lambda: K.layernorm_forward(xx, w, bb, 1e-5, ydt), "cm_layernorm_fwd", args.iters, flush)
+                byts = rows * d_model * (xs_ + ys_)
+                print("%-40s ln_fwd %s->%s  best %.4f ms  alg %.1f GB/s (%.1f%%)" % (tag, xdt, ydt, best, byts / best / 1e6, 100 * byts / best / 1e6 / peak))
+                y, mean, rstd = K.layernorm_forward(xx, w, bb, 1e-5, ydt)
+                dy = rn(rows, d_model).to(ydt)
+                best, med = timek(lambda: K.layernorm_backward(xx, dy, w, mean, rstd), "cm_layernorm_bwd", args.iters, flush)
+                byts = rows * d_model * (2 * xs_ + ys_)
+                print("%-40s ln_bwd %s  best %.4f ms  alg %.1f GB/s (%.1f%%)" % (tag, xdt, best, byts / best / 1e6, 100 * byts / best / 1e6 / peak))
+            xc = rn(Bt, L, d_model).to(dt)
+            wc, bc_ = rn(d_model, 31), rn(d_model)
+            best, med = timek(lambda: K.dwconv_forward(xc, wc, bc_, 15), "cm_dwconv_fwd", args.iters, flush)
+            byts = 2 * s * rows * d_model
+            print("%-40s dwconv_fwd k31  best %.4f ms  alg %.1f GB/s (%.1f%%)" % (tag, best, byts / best / 1e6, 100 * byts / best / 1e6 / peak))
+            dyc = rn(Bt, L, d_model).to(dt)
+            best, med = timek(lambda: K.dwconv_backward_weight(xc, dyc, 31, 15), "cm_dwconv_bwd_weight", args.iters, flush)
+            print("%-40s dwconv_bwdw k31 best %.4f ms  alg %.1f GB/s (%.1f%%)" % (tag, best, byts / best / 1e6, 100 * byts / best / 1e6 / peak))
+            dff = rn(rows, 4 * d_model).to(dt)
+            best, med = timek(lambda: K.colsum(dff), "cm_colsum", args.iters, flush)
+            byts = s * rows * 4 * d_model
+            print("%-40s colsum 4d       best %.4f ms  alg %.1f GB/s (%.1f%%)" % (tag, best, byts / best / 1e6, 100 * byts / best / 1e6 / peak))
         x = cl()
         cdirs = [dict(weight=rn(D, 4), bias=rn(D), anticausal=False), dict(weight=rn(D, 4), bias=rn(D), anticausal=True)]
         tag = "cfg%s B%d D%d L%d %s" % (cfg, Bt, D, L, args.dtype)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CM_ABI_VERSION 2
+#define CM_ABI_VERSION 3
 
 /* element type of activations (u, delta, z, B, C, x, out, and their gradients) */
 enum { CM_F32 = 0, CM_BF16 = 1, CM_F16 = 2 };
@@ -195,6 +195,30 @@ int cm_conv_bwd(const cm_conv_args* args, void* stream);
  * rolls conv_state (batch, dim, width) left by one, appends x (batch, dim), returns act(bias + <state, w>) */
 int cm_conv_update(const void* x, void* conv_state, const float* weight, const float* bias, void* out,
                    int32_t batch, int32_t dim, int32_t width, int32_t dtype, uint32_t flags, void* stream);
+
+/* single-token selective-state update for incremental decoding.  Replaces `selective_state_update` of mamba-ssm
+ * 1.1.3.post1 (reference call site modules/mamba/bimamba.py:354-356; the torch fallback the reference runs without it is
+ * bimamba.py:345-352):  dt = softplus(dt + dt_bias); state = state*exp(dt*A) + (dt*B)*x  (in place);
+ * out = (<state, C> + D*x) * silu(z). */
+typedef struct {
+  int32_t batch, dim, dstate;
+  int32_t dtype;            /* CM_* of x, dt, z, Bm, Cm, out */
+  int32_t state_dtype;      /* CM_* of state */
+  uint32_t flags;           /* CM_FLAG_DELTA_SOFTPLUS */
+  void* state;              /* (batch, dim, dstate) contiguous, updated in place */
+  const void* x;            /* (batch, dim), unit channel stride, row stride x_sb elements */
+  const void* dt;           /* (batch, dim) */
+  const void* z;            /* (batch, dim) or NULL */
+  const void* Bm;           /* (batch, dstate) */
+  const void* Cm;           /* (batch, dstate) */
+  void* out;                /* (batch, dim) */
+  int64_t x_sb, dt_sb, z_sb, b_sb, c_sb, out_sb;
+  const float* A;           /* (dim, dstate) fp32 contiguous */
+  const float* Dskip;       /* (dim) fp32 or NULL */
+  const float* dt_bias;     /* (dim) fp32 or NULL */
+} cm_ssm_step_args;
+
+int cm_ssm_step(const cm_ssm_step_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Fbank tail.  Replaces the torch op chain behind speechbrain.lobes.features.Fbank after the STFT

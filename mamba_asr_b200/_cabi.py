@@ -17,7 +17,7 @@ CM_ERR_BAD_ARG, CM_ERR_UNSUPPORTED = -1, -2
 CM_FLAG_DELTA_SOFTPLUS = 1
 CM_FLAG_SILU = 1
 CM_SCAN_CKPT_STEPS = 8
-CM_ABI_VERSION = 2
+CM_ABI_VERSION = 3
 
 EXPORTS = (
     "cm_version", "cm_scan_num_ckpt", "cm_scan_slab_channels", "cm_scan_pick_lanes", "cm_scan_pick_lanes_bwd", "cm_scan_fwd",
@@ -25,6 +25,7 @@ EXPORTS = (
     "cm_reduce_dbc", "cm_reduce_rows", "cm_conv_fwd", "cm_conv_num_part", "cm_conv_bwd", "cm_conv_update",
     "cm_fbank_logmel", "cm_fbank_floor", "cm_abi_sizeof", "cm_reduce_multi", "cm_layernorm_num_part", "cm_layernorm_fwd",
     "cm_layernorm_bwd", "cm_scan_fwd_workspace_bytes", "cm_dwconv_num_part", "cm_dwconv_fwd", "cm_dwconv_bwd_weight", "cm_colsum_num_part", "cm_colsum",
+    "cm_ssm_step",
 )
 CM_REDUCE_MAX_JOBS = 8
 
@@ -123,11 +124,21 @@ class DwConvArgs(C.Structure):
     ]
 
 
-ABI_STRUCTS = (Tensor3, ScanDir, ScanFwdArgs, ScanBwdDir, ScanBwdArgs, ConvDir, ConvArgs, FbankArgs, ReduceJob,
-               LayerNormArgs, DwConvArgs)
-
 _lib = None
 
+
+class SsmStepArgs(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("dim", C.c_int32), ("dstate", C.c_int32), ("dtype", C.c_int32),
+                ("state_dtype", C.c_int32), ("flags", C.c_uint32),
+                ("state", C.c_void_p), ("x", C.c_void_p), ("dt", C.c_void_p), ("z", C.c_void_p), ("Bm", C.c_void_p),
+                ("Cm", C.c_void_p), ("out", C.c_void_p),
+                ("x_sb", C.c_int64), ("dt_sb", C.c_int64), ("z_sb", C.c_int64), ("b_sb", C.c_int64), ("c_sb", C.c_int64),
+                ("out_sb", C.c_int64),
+                ("A", C.c_void_p), ("Dskip", C.c_void_p), ("dt_bias", C.c_void_p)]
+
+
+ABI_STRUCTS = (Tensor3, ScanDir, ScanFwdArgs, ScanBwdDir, ScanBwdArgs, ConvDir, ConvArgs, FbankArgs, ReduceJob,
+               LayerNormArgs, DwConvArgs, SsmStepArgs)
 
 def lib():
     """The loaded shared library; raises (never falls back) when it is absent or stale."""
@@ -169,6 +180,7 @@ def lib():
         L.cm_dwconv_num_part.argtypes = [C.c_int32, C.c_int32, C.c_int32]
         L.cm_dwconv_fwd.argtypes = [C.POINTER(DwConvArgs), C.c_void_p]
         L.cm_dwconv_bwd_weight.argtypes = [C.POINTER(DwConvArgs), C.c_void_p]
+        L.cm_ssm_step.argtypes = [C.POINTER(SsmStepArgs), C.c_void_p]
         if L.cm_version(None) != CM_ABI_VERSION:
             raise RuntimeError("mamba_asr_b200: %s has a different ABI version; rebuild it" % LIB_PATH)
         for i, st in enumerate(ABI_STRUCTS):

@@ -9,7 +9,9 @@ Parameter names, shapes, dtypes, creation order and the ``_no_weight_decay`` / `
 reference (pinned by tests/golden/mamba_state_dict.json), so checkpoints load either way.
 
 Forward is one fused path: in_proj GEMM -> ``MambaInnerCL`` (fused bidirectional conv + scan kernels,
-channel-last, no flips) -> out_proj GEMM.  There is no slow path and no CPU path.
+channel-last, no flips) -> out_proj GEMM.  Incremental decoding (``inference_params``, ``step``,
+``allocate_inference_cache``; reference bimamba.py:320-414) runs on the single-token kernels cm_conv_update and
+cm_ssm_step.  There is no slow path and no CPU path.
 """
 import math
 
@@ -17,7 +19,9 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .mamba_inner import MambaInnerCL
+from .causal_conv1d import causal_conv1d_update
+from .mamba_inner import MambaInnerCL, inner_forward
+from .selective_state_update import selective_state_update
 
 
 def _s4d_real_log(d_inner, d_state, device):
@@ -87,19 +91,66 @@ class _MambaBase(nn.Module):
         return (g("conv1d").weight, g("conv1d").bias, g("x_proj").weight, g("dt_proj").weight, A, Dk.float(),
                 g("dt_proj").bias.float())
 
-    def _check(self, hidden_states, inference_params):
-        if inference_params is not None:
-            raise NotImplementedError(
-                "incremental decoding (inference_params / step) is not part of the ConMamba training or "
-                "evaluation path: the reference trainers never pass it (SURVEY.md section 2.1 row 2)")
+    def _check(self, hidden_states):
         if not hidden_states.is_cuda:
             raise RuntimeError("mamba_asr_b200.Mamba runs on CUDA only (sm_100a kernels, no CPU fallback)")
 
+    # ---- incremental decoding (reference bimamba.py:176-186, 320-414; same code in mamba_ssm.Mamba) ----------------
+    def _cached(self, hidden_states, inference_params):
+        """The reference's inference_params protocol: a single-token ``step`` once ``seqlen_offset > 0``, else a
+        prefill that leaves the conv window and the last SSM state in the cache (bimamba.py:183-186, 277, 314-316).
+        As in the reference, a bidirectional module decodes with its forward-direction parameters only."""
+        conv_state, ssm_state = self._get_states_from_cache(inference_params, hidden_states.shape[0])
+        if inference_params.seqlen_offset > 0:
+            out, _, _ = self.step(hidden_states, conv_state, ssm_state)
+            return out
+        with torch.no_grad():
+            xz = F.linear(hidden_states, self.in_proj.weight, self.in_proj.bias)          # (B, L, 2D)
+            L, D = xz.shape[1], self.d_inner
+            W = self.d_conv
+            xt = xz[..., :D].transpose(1, 2)                                              # logical (B, D, L)
+            conv_state.copy_(F.pad(xt, (W - L, 0)))                                       # bimamba.py:277
+            y, _, _, last = inner_forward(xz, 1, 1.0, False, self._dir_params(""), need_last_state=True)
+            ssm_state.copy_(last[0])                                                      # bimamba.py:314-316
+            return F.linear(y, self.out_proj.weight, self.out_proj.bias)
+
     def step(self, hidden_states, conv_state, ssm_state):
-        raise NotImplementedError("single-token step is outside the ConMamba hot path (never called by the trainers)")
+        """One token: hidden_states (B, 1, d_model); conv_state (B, D, W) and ssm_state (B, D, N) updated in place.
+        Reference bimamba.py:320-365 with both optional kernels present (the sm_100a ones)."""
+        self._check(hidden_states)
+        assert hidden_states.shape[1] == 1, "Only support decoding with 1 token at a time for now"
+        xz = self.in_proj(hidden_states.squeeze(1))                                       # (B, 2D)
+        x, z = xz.chunk(2, dim=-1)
+        x = causal_conv1d_update(x.to(conv_state.dtype), conv_state, self.conv1d.weight[:, 0, :], self.conv1d.bias,
+                                 self.activation).to(xz.dtype)
+        x_db = self.x_proj(x)                                                             # (B, R + 2N)
+        dt, Bm, Cm = torch.split(x_db, [self.dt_rank, self.d_state, self.d_state], dim=-1)
+        dt = F.linear(dt, self.dt_proj.weight)                                            # (B, D); bias joins in-kernel
+        A = -torch.exp(self.A_log.float())
+        y = selective_state_update(ssm_state, x, dt, A, Bm, Cm, self.D, z=z, dt_bias=self.dt_proj.bias,
+                                   dt_softplus=True)
+        out = self.out_proj(y)
+        return out.unsqueeze(1), conv_state, ssm_state
 
     def allocate_inference_cache(self, batch_size, max_seqlen, dtype=None, **kwargs):
-        raise NotImplementedError("inference cache is outside the ConMamba hot path (never called by the trainers)")
+        device = self.out_proj.weight.device
+        conv_dtype = self.conv1d.weight.dtype if dtype is None else dtype
+        conv_state = torch.zeros(batch_size, self.d_model * self.expand, self.d_conv, device=device, dtype=conv_dtype)
+        ssm_dtype = self.dt_proj.weight.dtype if dtype is None else dtype
+        ssm_state = torch.zeros(batch_size, self.d_model * self.expand, self.d_state, device=device, dtype=ssm_dtype)
+        return conv_state, ssm_state
+
+    def _get_states_from_cache(self, inference_params, batch_size, initialize_states=False):
+        assert self.layer_idx is not None
+        if self.layer_idx not in inference_params.key_value_memory_dict:
+            conv_state, ssm_state = self.allocate_inference_cache(batch_size, 0)
+            inference_params.key_value_memory_dict[self.layer_idx] = (conv_state, ssm_state)
+        else:
+            conv_state, ssm_state = inference_params.key_value_memory_dict[self.layer_idx]
+            if initialize_states:
+                conv_state.zero_()
+                ssm_state.zero_()
+        return conv_state, ssm_state
 
 
 class Mamba(_MambaBase):
@@ -121,7 +172,9 @@ class Mamba(_MambaBase):
 
     def forward(self, hidden_states, inference_params=None):
         """hidden_states: (B, L, d_model) -> (B, L, d_model)"""
-        self._check(hidden_states, inference_params)
+        self._check(hidden_states)
+        if inference_params is not None:
+            return self._cached(hidden_states, inference_params)
         xz = F.linear(hidden_states, self.in_proj.weight, self.in_proj.bias)              # (B, L, 2D), time-major
         scale = 0.5 if self.if_devide_out else 1.0                                        # bimamba.py:250-253
         y = MambaInnerCL.apply(xz, 2, scale, False, *self._dir_params(""), *self._dir_params("_b"))
@@ -142,7 +195,9 @@ class UniMamba(_MambaBase):
                     conv_bias, bias, use_fast_path, layer_idx, device, dtype, bidirectional=False)
 
     def forward(self, hidden_states, inference_params=None):
-        self._check(hidden_states, inference_params)
+        self._check(hidden_states)
+        if inference_params is not None:
+            return self._cached(hidden_states, inference_params)
         xz = F.linear(hidden_states, self.in_proj.weight, self.in_proj.bias)
         y = MambaInnerCL.apply(xz, 1, 1.0, False, *self._dir_params(""))
         return F.linear(y, self.out_proj.weight, self.out_proj.bias)

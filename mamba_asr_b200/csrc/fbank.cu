@@ -150,6 +150,7 @@ extern "C" int cm_abi_sizeof(int32_t which) {
     case 8: return (int)sizeof(cm_reduce_job);
     case 9: return (int)sizeof(cm_layernorm_args);
     case 10: return (int)sizeof(cm_dwconv_args);
+    case 11: return (int)sizeof(cm_ssm_step_args);
     default: return CM_ERR_BAD_ARG;
   }
 }

@@ -402,6 +402,46 @@ def conv_update(x, conv_state, weight, bias=None, silu=False):
 
 
 # ------------------------------------------------------------------------------------------------------
+def ssm_step(state, x, dt, A, Bm, Cm, D=None, z=None, dt_bias=None, dt_softplus=False):
+    """cm_ssm_step: one decoding token.  state (B, D, N) contiguous, updated in place; x, dt, z (B, D); Bm, Cm (B, N);
+    A (D, N); D, dt_bias (D,).  Returns out (B, D) = (<state, C> + D*x) * silu(z)."""
+    lib = cabi.lib()
+    _require_cuda(x, "x")
+    _require_cuda(state, "state")
+    Bt, Dm = x.shape
+    N = A.shape[-1]
+    if state.shape != (Bt, Dm, N) or not state.is_contiguous():
+        raise ValueError("ssm_state must be a contiguous (B, D, N) tensor")
+    if A.shape != (Dm, N) or Bm.shape != (Bt, N) or Cm.shape != (Bt, N) or dt.shape != (Bt, Dm):
+        raise ValueError("ssm_step: shapes must be x, dt (B, D); A (D, N); B, C (B, N)")
+    act = x.dtype
+
+    def row(t, name):
+        if t.dtype != act:
+            t = t.to(act)
+        if t.stride(-1) != 1:
+            t = t.contiguous()
+        return t
+
+    x, dt, Bm, Cm = row(x, "x"), row(dt, "dt"), row(Bm, "B"), row(Cm, "C")
+    z = None if z is None else row(z, "z")
+    Af = _f32c(A.float(), "A")
+    Df = None if D is None else _f32c(D.float(), "D")
+    bf = None if dt_bias is None else _f32c(dt_bias.float(), "dt_bias")
+    out = torch.empty((Bt, Dm), dtype=act, device=x.device)
+    a = cabi.SsmStepArgs()
+    a.batch, a.dim, a.dstate = Bt, Dm, N
+    a.dtype, a.state_dtype = cabi.dtype_code(act), cabi.dtype_code(state.dtype)
+    a.flags = cabi.CM_FLAG_DELTA_SOFTPLUS if dt_softplus else 0
+    a.state, a.x, a.dt, a.z = state.data_ptr(), x.data_ptr(), dt.data_ptr(), cabi.ptr(z)
+    a.Bm, a.Cm, a.out = Bm.data_ptr(), Cm.data_ptr(), out.data_ptr()
+    a.x_sb, a.dt_sb, a.z_sb = x.stride(0), dt.stride(0), (0 if z is None else z.stride(0))
+    a.b_sb, a.c_sb, a.out_sb = Bm.stride(0), Cm.stride(0), out.stride(0)
+    a.A, a.Dskip, a.dt_bias = Af.data_ptr(), cabi.ptr(Df), cabi.ptr(bf)
+    _call("cm_ssm_step", lib.cm_ssm_step, C.byref(a), cabi.stream_ptr())
+    return out
+
+
 def fbank_logmel(stft, fbank, top_db=80.0, amin=1e-10, multiplier=10.0, db_offset=0.0):
     """cm_fbank_logmel + cm_fbank_floor.  stft: complex64 (B, F, T) as returned by torch.stft; fbank: (F, M) fp32.
     Returns (B, T, M) fp32 log-mel features with the per-utterance top_db floor applied."""

@@ -51,6 +51,47 @@ def _wgrad(a, b, nsplit):
     return torch.bmm(a3.transpose(1, 2), b3).sum(0)
 
 
+def inner_forward(xz, ndir, out_scale, reverse0, params, need_grad=False, need_last_state=False):
+    """conv -> x_proj -> dt_proj -> fused scan on channel-last buffers.  Returns (y (B, L, D), tensors to save for
+    backward or None, per-direction time order, per-direction last states (B, D, N) fp32 or [])."""
+    assert len(params) == ndir * MambaInnerCL.NPER
+    if xz.stride(-1) != 1:
+        xz = xz.contiguous()
+    Bt, L, twoD = xz.shape
+    D = twoD // 2
+    act = xz.dtype
+    x = _as_bdl(xz[..., :D])
+    z = _as_bdl(xz[..., D:])
+    P = [params[r * 7:(r + 1) * 7] for r in range(ndir)]
+    rev = [bool(reverse0) ^ (r == 1) for r in range(ndir)]
+    with torch.autocast("cuda", enabled=False):
+        conv_dirs = [dict(weight=p[0][:, 0, :], bias=p[1], anticausal=rev[r]) for r, p in enumerate(P)]
+        us = K.conv_forward(x, conv_dirs, silu=True)                     # logical (B, D, L), memory (B, L, D)
+        scan_dirs, x_dbls, deltas, wx, wdt = [], [], [], [], []
+        for r, p in enumerate(P):
+            R = p[3].shape[1]
+            N = p[4].shape[1]
+            xw, dw = _aligned_proj_weights(p[2], p[3], R, N, act)        # rows [B | C | dt | 0-pad], K padded
+            u_mem = us[r].transpose(1, 2)                                # (B, L, D) contiguous
+            x_dbl = torch.mm(u_mem.reshape(Bt * L, D), xw.t())           # (B*L, 2N + Rp), 16-byte-aligned rows
+            delta_mem = torch.mm(x_dbl[:, 2 * N:], dw.t()).view(Bt, L, D)
+            xv = x_dbl.view(Bt, L, -1)
+            scan_dirs.append(dict(u=us[r], delta=_as_bdl(delta_mem), A=p[4],
+                                  B=_as_bdl(xv[..., :N]), C=_as_bdl(xv[..., N:2 * N]),
+                                  D=p[5], delta_bias=p[6], reverse=rev[r]))
+            x_dbls.append(x_dbl)
+            deltas.append(delta_mem)
+            wx.append(xw)
+            wdt.append(dw)
+        res = K.scan_forward(scan_dirs, z=z, out_scale=out_scale, delta_softplus=True,
+                             need_ckpt=need_grad, need_out_pre=need_grad, need_last_state=need_last_state)
+    y = res["out"].transpose(1, 2)                                       # (B, L, D) contiguous memory
+    saved = None
+    if need_grad:
+        saved = (xz, res["out_pre"], *us, *deltas, *x_dbls, *res["ckpt"], *wx, *wdt, *params)
+    return y, saved, rev, res["last_state"]
+
+
 class MambaInnerCL(torch.autograd.Function):
     """y = MambaInnerCL.apply(xz, ndir, out_scale, reverse0, *params)
 
@@ -64,44 +105,11 @@ class MambaInnerCL(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, xz, ndir, out_scale, reverse0, *params):
-        assert len(params) == ndir * MambaInnerCL.NPER
-        if xz.stride(-1) != 1:
-            xz = xz.contiguous()
-        Bt, L, twoD = xz.shape
-        D = twoD // 2
-        act = xz.dtype
         need_grad = any(ctx.needs_input_grad)
-        x = _as_bdl(xz[..., :D])
-        z = _as_bdl(xz[..., D:])
-        P = [params[r * 7:(r + 1) * 7] for r in range(ndir)]
-        rev = [bool(reverse0) ^ (r == 1) for r in range(ndir)]
-        with torch.autocast("cuda", enabled=False):
-            conv_dirs = [dict(weight=p[0][:, 0, :], bias=p[1], anticausal=rev[r]) for r, p in enumerate(P)]
-            us = K.conv_forward(x, conv_dirs, silu=True)                     # logical (B, D, L), memory (B, L, D)
-            scan_dirs, x_dbls, deltas, wx, wdt = [], [], [], [], []
-            for r, p in enumerate(P):
-                R = p[3].shape[1]
-                N = p[4].shape[1]
-                xw, dw = _aligned_proj_weights(p[2], p[3], R, N, act)        # rows [B | C | dt | 0-pad], K padded
-                Rp = dw.shape[1]
-                u_mem = us[r].transpose(1, 2)                                # (B, L, D) contiguous
-                x_dbl = torch.mm(u_mem.reshape(Bt * L, D), xw.t())           # (B*L, 2N + Rp), 16-byte-aligned rows
-                delta_mem = torch.mm(x_dbl[:, 2 * N:], dw.t()).view(Bt, L, D)
-                xv = x_dbl.view(Bt, L, -1)
-                scan_dirs.append(dict(u=us[r], delta=_as_bdl(delta_mem), A=p[4],
-                                      B=_as_bdl(xv[..., :N]), C=_as_bdl(xv[..., N:2 * N]),
-                                      D=p[5], delta_bias=p[6], reverse=rev[r]))
-                x_dbls.append(x_dbl)
-                deltas.append(delta_mem)
-                wx.append(xw)
-                wdt.append(dw)
-            res = K.scan_forward(scan_dirs, z=z, out_scale=out_scale, delta_softplus=True,
-                                 need_ckpt=need_grad, need_out_pre=need_grad)
-        y = res["out"].transpose(1, 2)                                       # (B, L, D) contiguous memory
+        y, saved, rev, _ = inner_forward(xz, ndir, out_scale, reverse0, params, need_grad=need_grad)
         if need_grad:
             ctx.ndir, ctx.out_scale, ctx.rev = ndir, out_scale, rev
-            ctx.n_us = len(us)
-            ctx.save_for_backward(xz, res["out_pre"], *us, *deltas, *x_dbls, *res["ckpt"], *wx, *wdt, *params)
+            ctx.save_for_backward(*saved)
         return y
 
     @staticmethod

@@ -15,6 +15,8 @@ then freezes
   conv_*.npz      the reference's torch conv fallback  act(conv1d(x)[..., :L])  (bimamba.py:83-91, 278-279)
                   with autograd gradients
   bimamba_v2.npz  the v2 composition written with the reference's own pieces and flips (bimamba.py:223-253)
+  mamba_step.npz  prefill + single-token ``step`` outputs and cache states of the reference ``Mamba``
+                  (bimamba.py:176-186, 320-414)
   mamba_state_dict.json   parameter names / shapes / dtypes / tagged attrs of the reference
                   ``Mamba(d_model, bimamba_type="v2")`` constructor (bimamba.py:40-174)
 
@@ -167,9 +169,60 @@ def bimamba_case(ssi, bim, seed=11, Bt=2, L=37, d_model=32):
     print("wrote bimamba_v2, mamba_state_dict.json")
 
 
+def step_case(ssi, bim, seed=21, Bt=3, L=9, T=5, d_model=32):
+    """Incremental decoding through the reference's own ``Mamba`` (bimamba.py:176-186, 320-414): a prefill of L tokens
+    with ``inference_params`` (the slow path, bimamba.py:274-316, with ``selective_scan_fn`` bound to the reference's
+    ``selective_scan_ref`` because the CUDA extension is absent), then T single-token ``step`` calls on the torch
+    fallbacks of bimamba.py:328-333 and :350-357.  Also T steps from zero states (no prefill)."""
+    torch.manual_seed(seed)
+    m = bim.Mamba(d_model=d_model, d_state=16, d_conv=4, expand=2, bimamba_type="v2", layer_idx=0)
+    for p in m.parameters():
+        if p.dim() > 1:
+            nn.init.xavier_normal_(p)
+    with torch.no_grad():
+        m.D.copy_(torch.randn(m.D.shape))
+        m.A_log.copy_(m.A_log + 0.3 * torch.randn(m.A_log.shape))
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    bim.selective_scan_fn = ssi.selective_scan_ref            # same signature (selective_scan_interface.py:82,91)
+    assert bim.causal_conv1d_fn is None and bim.causal_conv1d_update is None and bim.selective_state_update is None
+
+    class InferenceParams:                                    # mamba_ssm.utils.generation.InferenceParams fields used
+        def __init__(self):
+            self.seqlen_offset = 0
+            self.key_value_memory_dict = {}
+
+    prompt = torch.randn(Bt, L, d_model)
+    tokens = torch.randn(Bt, T, d_model)
+    rec = {"p_" + k: t2n(v) for k, v in sd.items()}
+    with torch.no_grad():
+        ip = InferenceParams()
+        out_prefill = m(prompt, inference_params=ip)
+        conv0, ssm0 = [t.clone() for t in ip.key_value_memory_dict[0]]
+        outs = []
+        for t in range(T):
+            ip.seqlen_offset = L + t
+            outs.append(m(tokens[:, t:t + 1], inference_params=ip))
+        conv1, ssm1 = ip.key_value_memory_dict[0]
+        rec.update(prompt=t2n(prompt), tokens=t2n(tokens), out_prefill=t2n(out_prefill),
+                   conv_after_prefill=t2n(conv0), ssm_after_prefill=t2n(ssm0),
+                   out_steps=t2n(torch.cat(outs, dim=1)), conv_final=t2n(conv1), ssm_final=t2n(ssm1))
+        # steps from a zero cache
+        cs, ss = m.allocate_inference_cache(Bt, 0)
+        outs = []
+        for t in range(T):
+            o, cs, ss = m.step(tokens[:, t:t + 1], cs, ss)
+            outs.append(o)
+        rec.update(out_steps_zero=t2n(torch.cat(outs, dim=1)), conv_zero_final=t2n(cs), ssm_zero_final=t2n(ss))
+    np.savez_compressed(os.path.join(HERE, "mamba_step.npz"), **rec)
+    print("wrote mamba_step")
+
+
 def main():
     torch.set_num_threads(1)          # fixed reduction order
     ssi, bim = import_reference()
+    if "--only-step" in sys.argv:
+        step_case(ssi, bim)
+        return
     f32, bf16 = torch.float32, torch.bfloat16
     scan_case(ssi, "f32_full", 1, 2, 32, 67, 16, f32, 3, True, True, True, True, "xavier", True)
     scan_case(ssi, "f32_s4d", 2, 2, 32, 131, 16, f32, 3, True, True, True, True, "s4d", True)
@@ -181,6 +234,7 @@ def main():
     conv_case("w4_nobias", 8, 1, 32, 5, 4, False)
     conv_case("w2_short", 9, 2, 32, 3, 2, True)
     bimamba_case(ssi, bim)
+    step_case(ssi, bim)
 
 
 if __name__ == "__main__":

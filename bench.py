@@ -43,8 +43,12 @@ WORKLOADS = {
     "conmamba_small_ctc_fwdbwd_b32x15s": dict(model="conmamba_small_ctc", batch=32, seconds=15.0),
     # BASELINE.json configs[2] shape (encoder fwd+bwd of the large CTC model, 64 x 20 s per GPU)
     "conmamba_large_ctc_fwdbwd_b64x20s": dict(model="conmamba_large_ctc", batch=64, seconds=20.0),
-    # small smoke shape for debugging
+    # BASELINE.json configs[3] shape: ConMambaMamba-large S2S (12 ConMamba encoder + 6 Mamba decoder layers, d_model 512,
+    # vocab 5000) training step, 64 x 20 s per GPU, 3 target tokens per audio second
+    "conmambamamba_large_s2s_fwdbwd_b64x20s": dict(model="conmambamamba_large_s2s", batch=64, seconds=20.0),
+    # small smoke shapes for debugging
     "tiny": dict(model="conmamba_small_ctc", batch=2, seconds=2.0),
+    "tiny_s2s": dict(model="conmambamamba_large_s2s", batch=2, seconds=2.0),
 }
 DEFAULT_WORKLOAD = "conmamba_small_ctc_fwdbwd_b32x15s"
 
@@ -132,14 +136,35 @@ def make_batch(model_cfg, batch, seconds, seed, device, n_classes):
     return wav, targets
 
 
-def ctc_step(model, wav, targets, autocast):
-    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
-        logp = model(wav)                                       # (B, L, C)
+def ctc_loss_of(logp, targets):
     Bt, L, _ = logp.shape
     in_len = torch.full((Bt,), L, dtype=torch.long)
     tg_len = torch.full((Bt,), targets.shape[1], dtype=torch.long)
-    loss = F.ctc_loss(logp.float().transpose(0, 1), targets, in_len, tg_len, blank=0, reduction="mean",
+    return F.ctc_loss(logp.float().transpose(0, 1), targets, in_len, tg_len, blank=0, reduction="mean",
                       zero_infinity=True)
+
+
+def step_loss(model, wav, targets, autocast):
+    """CTC recipe (train_CTC.py:285-302).  S2S recipe (train_S2S.py:344-361, 518-530): ctc_weight * CTC on the encoder +
+    (1 - ctc_weight) * label-smoothed KL on the decoder, decoder input = <bos> + targets, decoder target = targets + <eos>."""
+    is_s2s = hasattr(model, "decoder")
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        if is_s2s:
+            bos = torch.cat([torch.ones_like(targets[:, :1]), targets], dim=1)
+            p_ctc, p_seq = model(wav, bos)
+        else:
+            logp = model(wav)                                       # (B, L, C)
+    if is_s2s:
+        from mamba_asr_b200.encoder import kldiv_loss
+        eos = torch.cat([targets, torch.full_like(targets[:, :1], 2)], dim=1)
+        loss = 0.3 * ctc_loss_of(p_ctc, targets) + 0.7 * kldiv_loss(p_seq.float(), eos, label_smoothing=0.1)
+    else:
+        loss = ctc_loss_of(logp, targets)
+    return loss
+
+
+def ctc_step(model, wav, targets, autocast):
+    loss = step_loss(model, wav, targets, autocast)
     loss.backward()
     return loss
 
@@ -175,11 +200,7 @@ def cpu_reference_run(workload, steps, warmup, budget_s=200.0):
         wav, targets = make_batch(cfg, 1, sec, 1234, "cpu", cfg["output_neurons"])
         t0 = time.perf_counter()
         model.zero_grad(set_to_none=True)
-        logp = model(wav)
-        L = logp.shape[1]
-        loss = F.ctc_loss(logp.float().transpose(0, 1), targets, torch.tensor([L]), torch.tensor([targets.shape[1]]),
-                          blank=0, reduction="mean", zero_infinity=True)
-        loss.backward()
+        step_loss(model, wav, targets, False).backward()
         return time.perf_counter() - t0
 
     # pick the largest sample (1 utterance of the workload's duration, else a shorter cut) that fits the budget
@@ -256,6 +277,7 @@ def main():
         for p_ in model.parameters():                          # identical replicas: rank 0's initialisation
             dist.broadcast(p_.data, 0)
     n_params = sum(p.numel() for p in model.parameters())
+    is_s2s = hasattr(model, "decoder")
 
     batch, seconds = wl["batch"], wl["seconds"]
     wav_h, tgt_h = make_batch(cfg, batch, seconds, cfg["seed"] + rank, dev, cfg["output_neurons"])
@@ -294,7 +316,8 @@ def main():
             # capture under the same autocast policy the step runs with (weight-cast caching off: the cached casts of a
             # warm-up iteration would otherwise be baked out of the graph)
             with torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False):
-                gnet = graph_module(net, (wav_d,), warmup=3)
+                sample = (wav_d,) if not is_s2s else (wav_d, torch.cat([torch.ones_like(tgt_d[:, :1]), tgt_d], dim=1))
+                gnet = graph_module(net, sample, warmup=3)
             launches_per_step = (K.LAUNCHES - l0) // 4          # 3 warm-ups + 1 capture
 
             def step_graphed(w, t):
@@ -394,6 +417,8 @@ def main():
                               "achieved_gbs": byts / (avg * 1e-3) / 1e9, "frac": byts / (avg * 1e-3) / 1e9 / hbm_peak}
         share = {k: sum(v) for k, v in ktimes.items()}
         dom = max((k for k in kern), key=lambda k: kern[k]["total_ms"]) if kern else None
+        if is_s2s:      # the decoder's unidirectional launches share the entry-point names: no single shape to quote
+            dom, kern = None, {}
         roofline = None
         if dom:
             roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["achieved_gbs"], "peak": hbm_peak,

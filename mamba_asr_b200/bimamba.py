@@ -194,10 +194,14 @@ class UniMamba(_MambaBase):
         self._build(d_model, d_state, d_conv, expand, dt_rank, dt_min, dt_max, dt_init, dt_scale, dt_init_floor,
                     conv_bias, bias, use_fast_path, layer_idx, device, dtype, bidirectional=False)
 
-    def forward(self, hidden_states, inference_params=None):
+    def forward(self, hidden_states, inference_params=None, keep_last=None):
+        """``keep_last=S`` (extension, default off): project only the last S positions through out_proj - what the
+        decoder's cross-Mamba keeps of its scan over [memory ; tgt] (reference modules/Conmamba.py:934)."""
         self._check(hidden_states)
         if inference_params is not None:
             return self._cached(hidden_states, inference_params)
         xz = F.linear(hidden_states, self.in_proj.weight, self.in_proj.bias)
         y = MambaInnerCL.apply(xz, 1, 1.0, False, *self._dir_params(""))
+        if keep_last is not None:
+            y = y[:, -keep_last:]
         return F.linear(y, self.out_proj.weight, self.out_proj.bias)

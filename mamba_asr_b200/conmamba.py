@@ -199,7 +199,8 @@ class MambaDecoderLayer(nn.Module):
             tgt = self.norm1(tgt)
         t = self.norm2(tgt) if pre else tgt
         # causal scan over [memory ; tgt]: every target position sees the whole encoder output first
-        cross = self.cross_mamba(torch.cat([memory, t], dim=1))[:, -t.shape[1]:]
+        # (Conmamba.py:934); only the target rows go through out_proj
+        cross = self.cross_mamba(torch.cat([memory, t], dim=1), keep_last=t.shape[1])
         tgt = tgt + self.dropout2(cross)
         if not pre:
             tgt = self.norm2(tgt)

@@ -17,8 +17,10 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+import math
+
 from .linear import BiasGradLinear
-from .conmamba import ConmambaEncoder
+from .conmamba import ConmambaEncoder, MambaDecoder
 from .fbank import Fbank
 
 # model blocks of the BASELINE.json configs
@@ -32,6 +34,9 @@ CONFIGS = {
     # encoder of hparams/S2S/conmambamamba_large.yaml:251-287
     "conmamba_large_s2s_encoder": dict(d_model=512, d_ffn=2048, num_layers=12, n_fft=512, win_length=32, n_mels=80,
                                        output_neurons=5000, seed=3407),
+    # hparams/S2S/conmambamamba_large.yaml:251-315: 12 ConMamba encoder layers + 6 Mamba decoder layers, d_model 512
+    "conmambamamba_large_s2s": dict(d_model=512, d_ffn=2048, num_layers=12, num_decoder_layers=6, n_fft=512,
+                                    win_length=32, n_mels=80, output_neurons=5000, seed=3407),
 }
 
 
@@ -112,10 +117,84 @@ class ConMambaCTC(nn.Module):
         return F.log_softmax(self.ctc_lin(enc), dim=-1)
 
 
+class NormalizedEmbedding(nn.Module):
+    """speechbrain NormalizedEmbedding (TransformerASR.py:738-740): token embedding scaled by sqrt(d_model)."""
+
+    def __init__(self, d_model, vocab):
+        super().__init__()
+        self.emb = nn.Embedding(vocab, d_model, padding_idx=0)
+        self.d_model = d_model
+
+    def forward(self, x):
+        return self.emb(x) * math.sqrt(self.d_model)
+
+
+class PositionalEncoding(nn.Module):
+    """speechbrain fixed sinusoidal PositionalEncoding, added to the decoder input (TransformerASR.py:794)."""
+
+    def __init__(self, d_model, max_len=2500):
+        super().__init__()
+        pe = torch.zeros(max_len, d_model)
+        pos = torch.arange(0, max_len).unsqueeze(1).float()
+        den = torch.exp(torch.arange(0, d_model, 2).float() * -(math.log(10000.0) / d_model))
+        pe[:, 0::2] = torch.sin(pos * den)
+        pe[:, 1::2] = torch.cos(pos * den)
+        self.register_buffer("pe", pe.unsqueeze(0), persistent=False)
+
+    def forward(self, x):
+        return self.pe[:, :x.size(1)].clone().detach()
+
+
+def kldiv_loss(log_probs, targets, label_smoothing=0.1, pad_idx=0):
+    """speechbrain.nnet.losses.kldiv_loss as the S2S recipe uses it (hparams/S2S/conmambamamba_large.yaml:414-415):
+    KL divergence to the label-smoothed target distribution (smoothing mass spread over the other n_class - 1 tokens),
+    padding positions masked, summed and divided by the batch size."""
+    bz, _, n_class = log_probs.shape
+    lp = log_probs.reshape(-1, n_class)
+    tg = targets.reshape(-1).long()
+    with torch.no_grad():
+        dist = torch.full_like(lp, label_smoothing / (n_class - 1))
+        ignore = tg == pad_idx
+        dist.scatter_(1, tg.masked_fill(ignore, 0).unsqueeze(1), 1.0 - label_smoothing)
+    loss = F.kl_div(lp, dist, reduction="none").masked_fill(ignore.unsqueeze(1), 0.0)
+    return loss.sum() / bz
+
+
+class ConMambaS2S(ConMambaCTC):
+    """ConMamba encoder + Mamba decoder of ``train_S2S.py`` (compute_forward :344-361) with the objects
+    ``hparams/S2S/conmambamamba_large.yaml:300-340`` builds: TransformerASR(encoder_module=conmamba,
+    decoder_module=mamba, normalize_before=True) -> (enc_out, dec_out) -> ctc_lin / seq_lin -> log_softmax."""
+
+    def __init__(self, d_model, d_ffn, num_layers, num_decoder_layers=6, output_neurons=5000, dropout=0.1, d_state=16,
+                 expand=2, d_conv=4, **kw):
+        super().__init__(d_model, d_ffn, num_layers, output_neurons=output_neurons, dropout=dropout, d_state=d_state,
+                         expand=expand, d_conv=d_conv, **kw)
+        self.custom_tgt_module = NormalizedEmbedding(d_model, output_neurons)
+        self.positional_encoding_decoder = PositionalEncoding(d_model)
+        mamba_config = dict(d_state=d_state, expand=expand, d_conv=d_conv, bidirectional=True)
+        # TransformerASR.py:703-712: decoder activation nn.GELU from the YAML, normalize_before=True
+        self.decoder = MambaDecoder(num_layers=num_decoder_layers, d_model=d_model, d_ffn=d_ffn, activation=nn.GELU,
+                                    dropout=dropout, normalize_before=True, mamba_config=mamba_config)
+        self.seq_lin = BiasGradLinear(d_model, output_neurons)
+        for p in list(self.custom_tgt_module.parameters()) + list(self.decoder.parameters()):
+            if p.dim() > 1:
+                nn.init.xavier_normal_(p)                          # TransformerASR.py:1051-1054
+
+    def forward(self, wavs, tokens_bos, wav_lens=None):
+        """wavs (B, n_samples), tokens_bos (B, S) -> (p_ctc (B, L, V), p_seq (B, S, V)) log-probabilities"""
+        enc = self.encode(self.features(wavs, wav_lens))
+        tgt = self.custom_tgt_module(tokens_bos)
+        tgt = tgt + self.positional_encoding_decoder(tgt)
+        dec, _, _ = self.decoder(tgt, enc)
+        return F.log_softmax(self.ctc_lin(enc), dim=-1), F.log_softmax(self.seq_lin(dec), dim=-1)
+
+
 def build_model(name, **overrides):
     cfg = dict(CONFIGS[name])
     cfg.update(overrides)
     seed = cfg.pop("seed", None)
     if seed is not None:
         torch.manual_seed(seed)
+    if "num_decoder_layers" in cfg:
+        return ConMambaS2S(**cfg)
     return ConMambaCTC(**cfg)

@@ -26,6 +26,26 @@ class OracleBiMamba(nn.Module):
         return bimamba_v2_oracle(hidden, p, if_devide_out=self.if_devide_out)
 
 
+class OracleUniMamba(nn.Module):
+    """Causal mixer (``mamba_ssm.Mamba`` as the decoder uses it, reference modules/Conmamba.py:854-862) on the CPU oracle:
+    in_proj -> MambaInnerFn body (selective_scan_interface.py:297-370) -> out_proj."""
+
+    def __init__(self, mamba):
+        super().__init__()
+        self.inner = mamba
+
+    def forward(self, hidden, inference_params=None, keep_last=None):
+        import torch.nn.functional as F
+        from .bimamba_ref import mamba_inner_oracle
+        p = dict(self.inner.named_parameters())
+        Bt, L, d = hidden.shape
+        xz = (p["in_proj.weight"] @ hidden.reshape(Bt * L, d).t()).reshape(-1, Bt, L).transpose(0, 1)
+        y = mamba_inner_oracle(xz, p["conv1d.weight"], p["conv1d.bias"], p["x_proj.weight"], p["dt_proj.weight"],
+                               -torch.exp(p["A_log"].float()), p["D"].float(), p["dt_proj.bias"].float())
+        out = F.linear(y.transpose(1, 2), p["out_proj.weight"], None)
+        return out if keep_last is None else out[:, -keep_last:]
+
+
 class OracleFbank(nn.Module):
     def __init__(self, n_fft, n_mels, win_length_ms):
         super().__init__()
@@ -37,10 +57,16 @@ class OracleFbank(nn.Module):
 
 
 def to_cpu_reference(model, n_fft, n_mels, win_length_ms):
-    """In-place: swap the sm_100a mixers / Fbank of a ``ConMambaCTC`` (built on CPU) for the oracle versions."""
+    """In-place: swap the sm_100a mixers / Fbank of a ``ConMambaCTC`` / ``ConMambaS2S`` (built on CPU) for the oracle
+    versions."""
+    from mamba_asr_b200.bimamba import Mamba as BiMamba, UniMamba
     from mamba_asr_b200.layernorm import FusedLayerNorm
-    for layer in model.encoder.layers:
-        layer.mamba = OracleBiMamba(layer.mamba)
+    for parent in list(model.modules()):
+        for name, child in list(parent.named_children()):
+            if isinstance(child, BiMamba):
+                setattr(parent, name, OracleBiMamba(child))
+            elif isinstance(child, UniMamba):
+                setattr(parent, name, OracleUniMamba(child))
     for mod in model.modules():                  # the sm_100a LayerNorm has no CPU path: torch's own op on the CPU arm
         if isinstance(mod, FusedLayerNorm):
             mod.__class__ = nn.LayerNorm

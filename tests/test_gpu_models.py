@@ -1,0 +1,118 @@
+"""GPU parity of the layer / model shells around the hot path:
+the same module tree evaluated (a) on the sm_100a kernels and (b) on the CPU reference path of oracle/cpu_encoder.py
+(selective_scan_ref + torch conv composed as bimamba.py:223-253, the reference's transpose -> nn.Conv1d convolution
+module, nn.LayerNorm, the Fbank restatement)."""
+import copy
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from cm_testutil import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32_library_ops():
+    """The shells' torch ops (cuDNN front-end convs, cuBLAS GEMMs) default to TF32 for fp32 inputs; the parity check
+    needs them at fp32 so that what is compared is the hand-written kernels."""
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _pair(name, **over):
+    from mamba_asr_b200.encoder import CONFIGS, build_model
+    from oracle.cpu_encoder import to_cpu_reference
+    cfg = CONFIGS[name]
+    gpu = build_model(name, dropout=0.0, **over)
+    with torch.no_grad():                      # leave the init point where D = 1 and A = -(1..N) exactly
+        for n, p in gpu.named_parameters():
+            if n.endswith(".D") or n.endswith(".D_b") or "A_log" in n or "A_b_log" in n:
+                p.add_(0.2 * torch.randn(p.shape, generator=torch.Generator().manual_seed(len(n))))
+    cpu = to_cpu_reference(copy.deepcopy(gpu), cfg["n_fft"], cfg["n_mels"], cfg["win_length"])
+    return gpu.cuda(), cpu
+
+
+def _grads_close(gpu, cpu, skip=()):
+    ref = dict(cpu.named_parameters())
+    n = 0
+    for name, p in gpu.named_parameters():
+        rname = name
+        for cand in (name, name.replace(".mamba.", ".mamba.inner."), name.replace(".self_mamba.", ".self_mamba.inner."),
+                     name.replace(".cross_mamba.", ".cross_mamba.inner.")):
+            if cand in ref:
+                rname = cand
+                break
+        g = ref[rname].grad
+        assert p.grad is not None and g is not None, name
+        assert_close(p.grad, g, floor="max", what="d " + name, rtol_mul=5.0)
+        n += 1
+    assert n == len(ref)
+
+
+def test_ctc_encoder_stack_forward_backward_matches_cpu_reference():
+    gpu, cpu = _pair("conmamba_small_ctc", d_model=32, d_ffn=64, num_layers=2)
+    g = torch.Generator().manual_seed(1)
+    wav = 0.1 * torch.randn(3, 12000, generator=g)
+    tgt = torch.randint(1, 31, (3, 6), generator=g)
+
+    def loss_of(model, w):
+        logp = model(w)
+        L = logp.shape[1]
+        return logp, F.ctc_loss(logp.transpose(0, 1), tgt, torch.full((3,), L), torch.full((3,), 6), blank=0,
+                                reduction="mean")
+    lp_c, loss_c = loss_of(cpu, wav)
+    loss_c.backward()
+    lp_g, loss_g = loss_of(gpu, wav.cuda())
+    loss_g.backward()
+    assert lp_g.shape == lp_c.shape
+    assert_close(lp_g, lp_c, floor="max", what="log-probs", rtol_mul=5.0)
+    assert abs(float(loss_g) - float(loss_c)) <= 1e-4 * abs(float(loss_c))
+    _grads_close(gpu, cpu)
+
+
+def test_s2s_encoder_decoder_forward_backward_matches_cpu_reference():
+    from mamba_asr_b200.encoder import kldiv_loss
+    gpu, cpu = _pair("conmambamamba_large_s2s", d_model=32, d_ffn=64, num_layers=1, num_decoder_layers=2,
+                     output_neurons=40)
+    g = torch.Generator().manual_seed(2)
+    wav = 0.1 * torch.randn(2, 9000, generator=g)
+    bos = torch.randint(3, 40, (2, 7), generator=g)
+    bos[:, 0] = 1
+    eos = torch.cat([bos[:, 1:], torch.full((2, 1), 2)], dim=1)
+    eos[1, -2:] = 0                                        # padding positions are masked out of the loss
+
+    def loss_of(model, w, b, e):
+        p_ctc, p_seq = model(w, b)
+        return p_ctc, p_seq, kldiv_loss(p_seq, e, label_smoothing=0.1) + 0.3 * p_ctc[..., 0].mean()
+    pc_c, ps_c, loss_c = loss_of(cpu, wav, bos, eos)
+    loss_c.backward()
+    pc_g, ps_g, loss_g = loss_of(gpu, wav.cuda(), bos.cuda(), eos.cuda())
+    loss_g.backward()
+    assert_close(pc_g, pc_c, floor="max", what="p_ctc", rtol_mul=5.0)
+    assert_close(ps_g, ps_c, floor="max", what="p_seq", rtol_mul=5.0)
+    assert abs(float(loss_g) - float(loss_c)) <= 1e-4 * abs(float(loss_c))
+    _grads_close(gpu, cpu)
+
+
+def test_config1_small_encoder_forward_bf16_against_cpu_reference():
+    """BASELINE.json configs[0]: ConMamba-small CTC encoder forward, batch 8 x 10 s, reference path on CPU (fp32) next
+    to the bf16-autocast GPU forward.  Tolerance: bf16 rtol 2e-2 of the log-prob range, accumulated over 12 layers."""
+    gpu, cpu = _pair("conmamba_small_ctc")
+    gpu.eval(), cpu.eval()
+    wav = 0.1 * torch.randn(8, 160000, generator=torch.Generator().manual_seed(7775))
+    with torch.no_grad():
+        ref = cpu(wav)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = gpu(wav.cuda())
+        out32 = gpu(wav.cuda())
+    assert out.shape == ref.shape == (8, 251, 31)
+    assert_close(out32, ref, floor="max", what="fp32 log-probs", rtol_mul=10.0)
+    err = (out.float().cpu() - ref).abs()
+    assert float(err.mean()) <= 2e-2 * float(ref.abs().max()), float(err.mean())
+    assert float(err.max()) <= 0.15 * float(ref.abs().max()), float(err.max())
+    assert float((out.float().cpu().argmax(-1) == ref.argmax(-1)).float().mean()) > 0.9

@@ -24,7 +24,7 @@ def main():
     dev = torch.device("cuda:0")
     model = build_model(wl["model"]).to(dev).train()
     wav, targets = bench.make_batch(cfg, wl["batch"], wl["seconds"], 1234, dev, cfg["output_neurons"])
-    wav = wav.to(dev)
+    wav, targets = wav.to(dev), targets.to(dev)
     for _ in range(3):
         model.zero_grad(set_to_none=True)
         bench.ctc_step(model, wav, targets, True)

@@ -234,6 +234,7 @@ def main():
     ap.add_argument("--graph", action="store_true", help="(default) replay the model forward / backward as CUDA graphs: the eager step is host-launch-bound (2.4 k launches, 41 ms wall for 30 ms of kernels on B200)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly")
     ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--no-param-cache", action="store_true", help="per-use autocast-style parameter casts (A/B)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -271,6 +272,8 @@ def main():
     cfg = CONFIGS[wl["model"]]
     model = build_model(wl["model"]).to(dev)
     model.train()
+    if not args.no_param_cache:
+        model.enable_param_cache()          # bf16 parameter copies refreshed by one multi-tensor copy per step
     net = model
     if world > 1:
         from mamba_asr_b200.dist_utils import allreduce_gradients

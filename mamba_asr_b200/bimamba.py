@@ -20,6 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .causal_conv1d import causal_conv1d_update
+from .linear import linear
 from .mamba_inner import MambaInnerCL, inner_forward
 from .selective_state_update import selective_state_update
 
@@ -175,10 +176,10 @@ class Mamba(_MambaBase):
         self._check(hidden_states)
         if inference_params is not None:
             return self._cached(hidden_states, inference_params)
-        xz = F.linear(hidden_states, self.in_proj.weight, self.in_proj.bias)              # (B, L, 2D), time-major
+        xz = linear(hidden_states, self.in_proj.weight, self.in_proj.bias)                # (B, L, 2D), time-major
         scale = 0.5 if self.if_devide_out else 1.0                                        # bimamba.py:250-253
         y = MambaInnerCL.apply(xz, 2, scale, False, *self._dir_params(""), *self._dir_params("_b"))
-        out = F.linear(y, self.out_proj.weight, self.out_proj.bias)
+        out = linear(y, self.out_proj.weight, self.out_proj.bias)
         if self.init_layer_scale is not None:
             out = out * self.gamma
         return out
@@ -200,8 +201,8 @@ class UniMamba(_MambaBase):
         self._check(hidden_states)
         if inference_params is not None:
             return self._cached(hidden_states, inference_params)
-        xz = F.linear(hidden_states, self.in_proj.weight, self.in_proj.bias)
+        xz = linear(hidden_states, self.in_proj.weight, self.in_proj.bias)
         y = MambaInnerCL.apply(xz, 1, 1.0, False, *self._dir_params(""))
         if keep_last is not None:
             y = y[:, -keep_last:]
-        return F.linear(y, self.out_proj.weight, self.out_proj.bias)
+        return linear(y, self.out_proj.weight, self.out_proj.bias)

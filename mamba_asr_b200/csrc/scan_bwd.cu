@@ -419,27 +419,37 @@ __global__ void reduce_rows_kernel(const float* __restrict__ part, int64_t rows,
 struct ReduceJobs {
   cm_reduce_job j[CM_REDUCE_MAX_JOBS];
 };
-constexpr int kRmWarps = 16;
+constexpr int kRmWarps = 32;
+constexpr int kRmFly = 8;     // independent loads in flight per thread
 __global__ void __launch_bounds__(32 * kRmWarps) reduce_multi_kernel(const ReduceJobs jobs) {
   __shared__ float sm[kRmWarps][33];
   const cm_reduce_job& job = jobs.j[blockIdx.y];
   const int64_t c = (int64_t)blockIdx.x * 32 + threadIdx.x;
   if ((int64_t)blockIdx.x * 32 >= job.cols) return;      // CTA-uniform
-  // four independent running sums per thread (rows ty, ty+16, ...: round-robin), combined in a fixed order: the loads
-  // of a thread are in flight together instead of one L2 round trip per row
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  // kRmFly independent running sums per thread (rows ty, ty + 32, ...: round-robin), combined in a fixed order: the
+  // loads of a thread are in flight together instead of one L2 round trip per row.  The kernel is pure latency (a few
+  // hundred partial rows of a few hundred columns): 592 rows = 3 round trips per thread.
+  float acc[kRmFly];
+#pragma unroll
+  for (int i = 0; i < kRmFly; ++i) acc[i] = 0.f;
   if (c < job.cols) {
     const float* src = job.part + c;
     const int64_t rows = job.rows, cols = job.cols;
     int64_t r = threadIdx.y;
-    for (; r + 3 * kRmWarps < rows; r += 4 * kRmWarps) {
-      const float v0 = __ldg(src + r * cols), v1 = __ldg(src + (r + kRmWarps) * cols);
-      const float v2 = __ldg(src + (r + 2 * kRmWarps) * cols), v3 = __ldg(src + (r + 3 * kRmWarps) * cols);
-      a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+    for (; r + (kRmFly - 1) * kRmWarps < rows; r += kRmFly * kRmWarps) {
+      float v[kRmFly];
+#pragma unroll
+      for (int i = 0; i < kRmFly; ++i) v[i] = __ldg(src + (r + i * kRmWarps) * cols);
+#pragma unroll
+      for (int i = 0; i < kRmFly; ++i) acc[i] += v[i];
     }
-    for (; r < rows; r += kRmWarps) a0 += __ldg(src + r * cols);
+    float v[kRmFly];
+#pragma unroll
+    for (int i = 0; i < kRmFly; ++i) v[i] = (r + i * kRmWarps < rows) ? __ldg(src + (r + i * kRmWarps) * cols) : 0.f;
+#pragma unroll
+    for (int i = 0; i < kRmFly; ++i) acc[i] += v[i];
   }
-  sm[threadIdx.y][threadIdx.x] = (a0 + a1) + (a2 + a3);
+  sm[threadIdx.y][threadIdx.x] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
   __syncthreads();
   if (threadIdx.y == 0 && c < job.cols) {
     float t = sm[0][threadIdx.x];

@@ -19,7 +19,7 @@ import torch.nn.functional as F
 
 import math
 
-from .linear import BiasGradLinear
+from .linear import BiasGradLinear, ParamCache, set_param_cache
 from .conmamba import ConmambaEncoder, MambaDecoder
 from .fbank import Fbank
 
@@ -102,6 +102,20 @@ class ConMambaCTC(nn.Module):
             if p.dim() > 1:
                 nn.init.xavier_normal_(p)                          # TransformerASR.py:1051-1054
 
+    def enable_param_cache(self, dtype=torch.bfloat16):
+        """Keep bf16 copies of all parameters in one flat buffer, refreshed by one multi-tensor copy at the start of every
+        autocast forward (linear.ParamCache): removes the per-parameter cast kernels of bf16 autocast training.  Call
+        after the model is on its device."""
+        self._param_cache = ParamCache(self, dtype)
+        set_param_cache(self._param_cache)
+        return self
+
+    def _refresh_param_cache(self):
+        c = getattr(self, "_param_cache", None)
+        if c is not None and torch.is_autocast_enabled("cuda") and torch.is_grad_enabled():
+            set_param_cache(c)
+            c.refresh()
+
     def features(self, wavs, wav_lens=None):
         feats = self.compute_features(wavs)                        # (B, T, 80) fp32, no grad
         return self.normalize(feats, wav_lens)
@@ -113,6 +127,7 @@ class ConMambaCTC(nn.Module):
 
     def forward(self, wavs, wav_lens=None):
         """wavs: (B, n_samples) -> log-probs (B, L, output_neurons)"""
+        self._refresh_param_cache()
         enc = self.encode(self.features(wavs, wav_lens))
         return F.log_softmax(self.ctc_lin(enc), dim=-1)
 
@@ -182,6 +197,7 @@ class ConMambaS2S(ConMambaCTC):
 
     def forward(self, wavs, tokens_bos, wav_lens=None):
         """wavs (B, n_samples), tokens_bos (B, S) -> (p_ctc (B, L, V), p_seq (B, S, V)) log-probabilities"""
+        self._refresh_param_cache()
         enc = self.encode(self.features(wavs, wav_lens))
         tgt = self.custom_tgt_module(tokens_bos)
         tgt = tgt + self.positional_encoding_decoder(tgt)

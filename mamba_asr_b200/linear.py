@@ -1,9 +1,15 @@
-"""``nn.Linear`` whose bias gradient is reduced by the sm_100a column-sum kernel (cm_colsum).
+"""Linear layers of the shell around the hot path: cuBLAS GEMMs with the non-GEMM work on sm_100a kernels or removed.
 
-The GEMMs stay cuBLAS (forward, dx, dW - exactly what torch's own Linear backward launches); only ``db = dy.sum(rows)``
-changes: torch's generic reduce_kernel ran at 1-1.5 TB/s for these (rows ~ 10^4, cols 256-1024) matrices on B200 and
-cost 5.3 of 69 ms of the ConMamba-large step.  ``BiasGradLinear`` subclasses ``nn.Linear`` (same parameters, same
-``state_dict``); on CPU tensors it is plain ``F.linear`` (the CPU reference arm never sees the kernel).
+* bias gradient: ``db = dy.sum(rows)`` on the streaming column-sum kernel (cm_colsum) instead of torch's generic
+  reduce_kernel (1-1.5 TB/s for rows ~ 10^4, cols 256-1024 on B200; 5.3 of 69 ms of the ConMamba-large step);
+* low-precision parameter copies: under bf16 autocast every use of a weight costs a cast kernel forward and a cast of
+  its gradient backward (750 launches = 10 % of the ConMamba-small step on B200).  ``ParamCache`` keeps bf16 copies of
+  all parameters of a model in one flat buffer, refreshed by ONE multi-tensor copy per step, and the weight-gradient
+  GEMMs write fp32 directly (``torch.mm(..., out_dtype=float32)``), so no per-parameter cast kernel remains.
+
+The GEMMs stay cuBLAS (forward, dx, dW - what torch's own Linear backward launches).  ``BiasGradLinear`` subclasses
+``nn.Linear`` (same parameters, same ``state_dict``); on CPU tensors it is plain ``F.linear`` (the CPU reference arm never
+sees the kernels).
 """
 import torch
 import torch.nn as nn
@@ -12,38 +18,95 @@ import torch.nn.functional as F
 from . import kernels as K
 
 
+class ParamCache:
+    """bf16 (autocast dtype) copies of a module tree's fp32 parameters in one flat buffer.
+
+    ``refresh()`` is one ``torch._foreach_copy_`` (a multi-tensor kernel) - call it once per step before the forward
+    (the model shells in ``encoder.py`` do, inside the captured graph).  ``get(p)`` returns the copy of parameter ``p`` or
+    None.  Only consulted under CUDA autocast; gradients always flow to the fp32 parameters."""
+
+    def __init__(self, module, dtype=torch.bfloat16):
+        self.params = [p for p in module.parameters() if p.is_cuda and p.dtype == torch.float32]
+        self.dtype = dtype
+        offs, n = [], 0
+        for p in self.params:
+            offs.append(n)
+            n += (p.numel() + 7) // 8 * 8                      # 16-byte aligned views (TMA / vector loads downstream)
+        dev = self.params[0].device if self.params else None
+        self.flat = torch.zeros(n, dtype=dtype, device=dev)
+        self.views = [self.flat[o:o + p.numel()].view(p.shape) for o, p in zip(offs, self.params)]
+        self.map = {id(p): v for p, v in zip(self.params, self.views)}
+
+    def refresh(self):
+        with torch.no_grad():
+            torch._foreach_copy_(self.views, self.params)
+
+    def get(self, p, dtype):
+        return self.map.get(id(p)) if dtype == self.dtype else None
+
+
+_ACTIVE = None
+
+
+def set_param_cache(cache):
+    """Install (or clear, with None) the cache ``linear`` consults."""
+    global _ACTIVE
+    _ACTIVE = cache
+
+
+def cached_param(p, dtype):
+    """The cached low-precision copy of ``p`` (no autograd link) or None."""
+    return _ACTIVE.get(p, dtype) if (_ACTIVE is not None and p is not None) else None
+
+
 class _LinearFn(torch.autograd.Function):
+    """y = x @ w^T + b with explicit low-precision operands: ``w_lp`` / ``b_lp`` are the forward operands (cached copies
+    or ``weight`` / ``bias`` themselves), gradients are returned for ``weight`` / ``bias`` in THEIR dtype."""
+
     @staticmethod
-    def forward(ctx, x, weight, bias):
-        ctx.save_for_backward(x, weight)
-        ctx.bias_dtype = bias.dtype
-        return F.linear(x, weight, bias)
+    def forward(ctx, x, weight, bias, w_lp, b_lp):
+        ctx.save_for_backward(x, w_lp)
+        ctx.w_dtype = weight.dtype
+        ctx.b_dtype = None if bias is None else bias.dtype
+        return F.linear(x, w_lp, b_lp)
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight = ctx.saved_tensors
+        x, w_lp = ctx.saved_tensors
         dy2 = dy.reshape(-1, dy.shape[-1])
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = torch.matmul(dy, weight)
+            dx = torch.matmul(dy, w_lp)
         if ctx.needs_input_grad[1]:
-            dw = torch.mm(dy2.t(), x.reshape(-1, x.shape[-1]))
-        if ctx.needs_input_grad[2]:
+            x2 = x.reshape(-1, x.shape[-1])
+            if ctx.w_dtype == torch.float32 and dy2.dtype != torch.float32:
+                dw = torch.mm(dy2.t(), x2, out_dtype=torch.float32)      # fp32 straight out of the GEMM: no cast kernel
+            else:
+                dw = torch.mm(dy2.t(), x2).to(ctx.w_dtype)
+        if ctx.b_dtype is not None and ctx.needs_input_grad[2]:
             s = K.colsum(dy2 if dy2.stride(-1) == 1 else dy2.contiguous())
-            db = (s if s is not None else dy2.sum(0)).to(ctx.bias_dtype)
-        return dx, dw, db
+            db = (s if s is not None else dy2.sum(0)).to(ctx.b_dtype)
+        return dx, dw, db, None, None
 
 
 def linear(x, weight, bias=None):
-    """F.linear with the bias gradient on the sm_100a kernel (CUDA tensors with a bias that needs grad); F.linear otherwise."""
-    if bias is None or not x.is_cuda or not (torch.is_grad_enabled() and bias.requires_grad):
+    """F.linear for CUDA training: bias gradient on cm_colsum, parameter casts from the ``ParamCache`` when one is
+    installed, fp32 weight gradients straight from the GEMM.  Plain F.linear on CPU or without grad."""
+    if not x.is_cuda or not torch.is_grad_enabled() or not (weight.requires_grad or (bias is not None and bias.requires_grad)):
         return F.linear(x, weight, bias)
-    if torch.is_autocast_enabled("cuda"):          # the casts autocast would insert, visible to autograd
+    if torch.is_autocast_enabled("cuda"):          # the casts autocast would insert
         dt = torch.get_autocast_dtype("cuda")
-        x, weight, bias = x.to(dt), weight.to(dt), bias.to(dt)
+        w_lp = cached_param(weight, dt)
+        b_lp = cached_param(bias, dt)
+        if w_lp is None:
+            w_lp = weight.detach().to(dt)
+        if bias is not None and b_lp is None:
+            b_lp = bias.detach().to(dt)
         with torch.autocast("cuda", enabled=False):
-            return _LinearFn.apply(x, weight, bias)
-    return _LinearFn.apply(x, weight, bias)
+            return _LinearFn.apply(x.to(dt), weight, bias, w_lp, b_lp)
+    if bias is None:
+        return F.linear(x, weight, bias)
+    return _LinearFn.apply(x, weight, bias, weight.detach(), bias.detach())
 
 
 class BiasGradLinear(nn.Linear):

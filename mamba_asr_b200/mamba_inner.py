@@ -18,6 +18,7 @@ The dense projections are torch.matmul (cuBLAS tensor cores); everything else is
 import torch
 
 from . import kernels as K
+from .linear import cached_param
 
 
 def _aligned_proj_weights(x_proj_w, dt_proj_w, R, N, act):
@@ -25,8 +26,10 @@ def _aligned_proj_weights(x_proj_w, dt_proj_w, R, N, act):
     both GEMMs have 8-element-aligned leading dimensions (tensor-core kernels instead of the align1 fallbacks at
     R = 9) and every B/C row of x_dbl starts on a 16-byte boundary.  The pad columns of x_dbl are exact zeros."""
     Rp = (R + 7) // 8 * 8
-    xw = x_proj_w.to(act)
-    dw = dt_proj_w.to(act)
+    xw = cached_param(x_proj_w, act)              # per-step bf16 copies (linear.ParamCache) when installed
+    dw = cached_param(dt_proj_w, act)
+    xw = x_proj_w.to(act) if xw is None else xw
+    dw = dt_proj_w.to(act) if dw is None else dw
     parts = [xw[R:R + 2 * N], xw[:R]]
     if Rp != R:
         parts.append(xw.new_zeros((Rp - R, xw.shape[1])))
@@ -44,11 +47,12 @@ def _wgrad(a, b, nsplit):
     one bmm over `nsplit` row blocks plus a sum.  As a single GEMM cuBLAS picks a serial-K sm_75 CUTLASS kernel for these
     shapes on B200 (85 us per call at K = 32064, measured); split over the batch it is a 64-way parallel reduction."""
     Kr = a.shape[0]
+    od = {} if a.dtype == torch.float32 else {"out_dtype": torch.float32}   # fp32 straight out of the GEMM
     if nsplit <= 1 or Kr % nsplit != 0:
-        return torch.mm(a.t(), b)
+        return torch.mm(a.t(), b, **od)
     a3 = a.unflatten(0, (nsplit, Kr // nsplit))
     b3 = b.unflatten(0, (nsplit, Kr // nsplit))
-    return torch.bmm(a3.transpose(1, 2), b3).sum(0)
+    return torch.bmm(a3.transpose(1, 2), b3, **od).sum(0)
 
 
 def inner_forward(xz, ndir, out_scale, reverse0, params, need_grad=False, need_last_state=False):

@@ -116,3 +116,44 @@ def test_config1_small_encoder_forward_bf16_against_cpu_reference():
     assert float(err.mean()) <= 2e-2 * float(ref.abs().max()), float(err.mean())
     assert float(err.max()) <= 0.15 * float(ref.abs().max()), float(err.max())
     assert float((out.float().cpu().argmax(-1) == ref.argmax(-1)).float().mean()) > 0.9
+
+
+def test_param_cache_step_equals_per_use_casts():
+    """bf16 autocast training step with the flat bf16 parameter cache (one multi-tensor copy per step, fp32 weight
+    gradients straight from the GEMMs) against the same step with per-use casts: same loss, gradients within bf16
+    rounding of each other; and the cache follows parameter updates."""
+    from mamba_asr_b200.encoder import build_model
+    from mamba_asr_b200.linear import set_param_cache
+    g = torch.Generator().manual_seed(3)
+    wav = (0.1 * torch.randn(2, 16000, generator=g)).cuda()
+    tgt = torch.randint(1, 31, (2, 5), generator=g)
+
+    def run(model):
+        model.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logp = model(wav)
+        L = logp.shape[1]
+        loss = F.ctc_loss(logp.float().transpose(0, 1), tgt, torch.full((2,), L), torch.full((2,), 5), blank=0)
+        loss.backward()
+        return float(loss.detach()), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    model = build_model("conmamba_small_ctc", d_model=64, d_ffn=128, num_layers=2, dropout=0.0).cuda()
+    try:
+        set_param_cache(None)
+        loss0, g0 = run(model)
+        model.enable_param_cache()
+        loss1, g1 = run(model)
+        assert abs(loss1 - loss0) <= 2e-2 * abs(loss0)
+        assert g0.keys() == g1.keys()
+        for n in g0:
+            assert g1[n].dtype == g0[n].dtype == torch.float32
+            assert_close(g1[n], g0[n], torch.bfloat16, floor="max", what="d " + n, rtol_mul=2.0)
+        with torch.no_grad():
+            for p in model.parameters():
+                p.mul_(0.5)
+        loss2, _ = run(model)
+        set_param_cache(None)
+        model._param_cache = None
+        loss3, _ = run(model)
+        assert abs(loss2 - loss3) <= 2e-2 * abs(loss3) and abs(loss2 - loss1) > 1e-3
+    finally:
+        set_param_cache(None)

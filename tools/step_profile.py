@@ -23,6 +23,7 @@ def main():
     cfg = CONFIGS[wl["model"]]
     dev = torch.device("cuda:0")
     model = build_model(wl["model"]).to(dev).train()
+    model.enable_param_cache()
     wav, targets = bench.make_batch(cfg, wl["batch"], wl["seconds"], 1234, dev, cfg["output_neurons"])
     wav, targets = wav.to(dev), targets.to(dev)
     for _ in range(3):

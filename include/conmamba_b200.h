@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CM_ABI_VERSION 3
+#define CM_ABI_VERSION 4
 
 /* element type of activations (u, delta, z, B, C, x, out, and their gradients) */
 enum { CM_F32 = 0, CM_BF16 = 1, CM_F16 = 2 };
@@ -272,6 +272,44 @@ int cm_layernorm_fwd(const cm_layernorm_args* args, void* stream);
 int cm_layernorm_bwd(const cm_layernorm_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
+ * Residual add + dropout + LayerNorm in one pass (reference modules/Conmamba.py:638-649:
+ * every sub-block of a ConMamba layer ends in  s = a + alpha * dropout(b)  and the next starts with  y = LayerNorm(s)).
+ *   forward : s = a + alpha * keep/(1-p) * b ; y = (s - mean) * rstd * gamma + beta ; writes s, y, mean, rstd, mask
+ *   backward: t = LayerNorm'(dy; s) + ds ; da = t ; db = alpha * keep/(1-p) * t ; dgamma / dbeta partial rows
+ *             (cm_layernorm_num_part(rows) rows each, summed by cm_reduce_multi)
+ * a, s, ds, da share a_dtype; b, db share b_dtype; y, dy share y_dtype.  Supported (a, b, y): (f32, bf16, bf16),
+ * (f32, bf16, f32), (f32, f32, f32), (bf16, bf16, bf16), (bf16, bf16, f32); cols even and <= 1024, even strides.
+ * The keep mask is a counter-based hash of (*seed, call_id, element index), stored as one byte per element.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t rows;
+  int32_t cols;
+  int32_t a_dtype, b_dtype, y_dtype;
+  float eps, alpha, p_drop;       /* p_drop in [0, 1); the mask pointer decides whether dropout is applied */
+  uint32_t call_id;               /* distinguishes call sites that share a seed */
+  int32_t reserved;
+  const int64_t* seed;            /* device scalar (read at kernel time: graph replays see host-side advances) or NULL */
+  const void* a;  int64_t a_stride;
+  const void* b;  int64_t b_stride;   /* NULL: s = a */
+  void* s;        int64_t s_stride;   /* forward: output (may be NULL if the caller never needs s); backward: input */
+  void* y;        int64_t y_stride;
+  uint8_t* mask;                      /* (rows, cols) contiguous; NULL = no dropout */
+  const float* gamma;
+  const float* beta;
+  float* mean;
+  float* rstd;
+  const void* dy; int64_t dy_stride;
+  const void* ds; int64_t ds_stride;  /* gradient reaching s from its other consumers, or NULL */
+  void* da;       int64_t da_stride;
+  void* db;       int64_t db_stride;  /* NULL when b was NULL */
+  float* dgamma_part;
+  float* dbeta_part;
+} cm_add_ln_args;
+
+int cm_add_ln_fwd(const cm_add_ln_args* args, void* stream);
+int cm_add_ln_bwd(const cm_add_ln_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
  * Depthwise conv1d over time (the kernel_size = 31 convolution of the ConMamba
  * convolution module, reference modules/Conmamba.py:281-290, nn.Conv1d(C, C, K, padding, groups=C)).
  *   y[b,l,c] = bias[c] + sum_k weight[c,k] * x[b, l - pad_left + k, c]      (zero outside [0, L))
@@ -312,7 +350,7 @@ int cm_colsum(const void* x, int64_t rows, int32_t cols, int64_t row_stride, int
 int cm_version(int32_t* sm_arch);
 /* sizeof() of the argument structs, for binding self-checks: 0 cm_tensor3, 1 cm_scan_dir, 2 cm_scan_fwd_args,
  * 3 cm_scan_bwd_dir, 4 cm_scan_bwd_args, 5 cm_conv_dir, 6 cm_conv_args, 7 cm_fbank_args, 8 cm_reduce_job,
- * 9 cm_layernorm_args, 10 cm_dwconv_args */
+ * 9 cm_layernorm_args, 10 cm_dwconv_args, 11 cm_ssm_step_args, 12 cm_add_ln_args */
 int cm_abi_sizeof(int32_t which);
 
 #ifdef __cplusplus

@@ -17,7 +17,7 @@ CM_ERR_BAD_ARG, CM_ERR_UNSUPPORTED = -1, -2
 CM_FLAG_DELTA_SOFTPLUS = 1
 CM_FLAG_SILU = 1
 CM_SCAN_CKPT_STEPS = 8
-CM_ABI_VERSION = 3
+CM_ABI_VERSION = 4
 
 EXPORTS = (
     "cm_version", "cm_scan_num_ckpt", "cm_scan_slab_channels", "cm_scan_pick_lanes", "cm_scan_pick_lanes_bwd", "cm_scan_fwd",
@@ -25,7 +25,7 @@ EXPORTS = (
     "cm_reduce_dbc", "cm_reduce_rows", "cm_conv_fwd", "cm_conv_num_part", "cm_conv_bwd", "cm_conv_update",
     "cm_fbank_logmel", "cm_fbank_floor", "cm_abi_sizeof", "cm_reduce_multi", "cm_layernorm_num_part", "cm_layernorm_fwd",
     "cm_layernorm_bwd", "cm_scan_fwd_workspace_bytes", "cm_dwconv_num_part", "cm_dwconv_fwd", "cm_dwconv_bwd_weight", "cm_colsum_num_part", "cm_colsum",
-    "cm_ssm_step",
+    "cm_ssm_step", "cm_add_ln_fwd", "cm_add_ln_bwd",
 )
 CM_REDUCE_MAX_JOBS = 8
 
@@ -137,8 +137,21 @@ class SsmStepArgs(C.Structure):
                 ("A", C.c_void_p), ("Dskip", C.c_void_p), ("dt_bias", C.c_void_p)]
 
 
+class AddLnArgs(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("cols", C.c_int32), ("a_dtype", C.c_int32), ("b_dtype", C.c_int32),
+                ("y_dtype", C.c_int32), ("eps", C.c_float), ("alpha", C.c_float), ("p_drop", C.c_float),
+                ("call_id", C.c_uint32), ("reserved", C.c_int32), ("seed", C.c_void_p),
+                ("a", C.c_void_p), ("a_stride", C.c_int64), ("b", C.c_void_p), ("b_stride", C.c_int64),
+                ("s", C.c_void_p), ("s_stride", C.c_int64), ("y", C.c_void_p), ("y_stride", C.c_int64),
+                ("mask", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("mean", C.c_void_p),
+                ("rstd", C.c_void_p),
+                ("dy", C.c_void_p), ("dy_stride", C.c_int64), ("ds", C.c_void_p), ("ds_stride", C.c_int64),
+                ("da", C.c_void_p), ("da_stride", C.c_int64), ("db", C.c_void_p), ("db_stride", C.c_int64),
+                ("dgamma_part", C.c_void_p), ("dbeta_part", C.c_void_p)]
+
+
 ABI_STRUCTS = (Tensor3, ScanDir, ScanFwdArgs, ScanBwdDir, ScanBwdArgs, ConvDir, ConvArgs, FbankArgs, ReduceJob,
-               LayerNormArgs, DwConvArgs, SsmStepArgs)
+               LayerNormArgs, DwConvArgs, SsmStepArgs, AddLnArgs)
 
 def lib():
     """The loaded shared library; raises (never falls back) when it is absent or stale."""
@@ -181,6 +194,8 @@ def lib():
         L.cm_dwconv_fwd.argtypes = [C.POINTER(DwConvArgs), C.c_void_p]
         L.cm_dwconv_bwd_weight.argtypes = [C.POINTER(DwConvArgs), C.c_void_p]
         L.cm_ssm_step.argtypes = [C.POINTER(SsmStepArgs), C.c_void_p]
+        L.cm_add_ln_fwd.argtypes = [C.POINTER(AddLnArgs), C.c_void_p]
+        L.cm_add_ln_bwd.argtypes = [C.POINTER(AddLnArgs), C.c_void_p]
         if L.cm_version(None) != CM_ABI_VERSION:
             raise RuntimeError("mamba_asr_b200: %s has a different ABI version; rebuild it" % LIB_PATH)
         for i, st in enumerate(ABI_STRUCTS):

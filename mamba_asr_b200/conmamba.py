@@ -13,6 +13,7 @@ with reference checkpoints).  The SpeechBrain building blocks the reference impo
 SpeechBrain's parameter names; they stay cuBLAS / cuDNN work and are not part of the hand-written kernel scope
 (SURVEY.md section 2.1 row 3).  The Mamba mixers are the fused sm_100a ones from ``bimamba.py``.
 """
+import os
 from typing import Optional
 
 import torch
@@ -23,7 +24,7 @@ from .bimamba import Mamba as BiMamba
 from .bimamba import UniMamba as Mamba
 from .dwconv import depthwise_conv1d
 from .kernels import DWCONV_KSIZES
-from .layernorm import FusedLayerNorm
+from .layernorm import FusedLayerNorm, add_dropout_layer_norm
 from .linear import BiasGradLinear, linear as _linear
 
 LAYER_NORM_EPS = 1e-6        # reference ConMambaConstants.LAYER_NORM_EPS (Conmamba.py:687)
@@ -91,10 +92,7 @@ class ConvolutionModule(nn.Module):
             raise NotImplementedError("Dynamic Chunk Training convolution is never enabled by the ConMamba encoder "
                                       "(TransformerASR.py:783-788 passes no config)")
         if self.use_kernel:
-            pw = self.bottleneck[0]                                   # pointwise conv = Linear over channel-last rows
-            out = F.glu(_linear(self.layer_norm(x), pw.weight.squeeze(-1), pw.bias), dim=-1)
-            out = depthwise_conv1d(out, self.conv.weight, self.conv.bias, pad_left=self.padding)
-            out = self.after_conv(out)
+            out = self.body(self.layer_norm(x))
             if mask is not None:
                 out.masked_fill_(mask, 0.0)
             return out
@@ -106,6 +104,19 @@ class ConvolutionModule(nn.Module):
         if mask is not None:
             out.masked_fill_(mask, 0.0)
         return out
+
+
+def _conv_body(self, normed, final_dropout=True):
+    """Everything of the kernel path after ``layer_norm`` (channel-last, no transposes); ``final_dropout=False`` leaves the
+    trailing Dropout to the caller (the encoder layer fuses it into the next add + LayerNorm)."""
+    pw = self.bottleneck[0]                                           # pointwise conv = Linear over channel-last rows
+    out = F.glu(_linear(normed, pw.weight.squeeze(-1), pw.bias), dim=-1)
+    out = depthwise_conv1d(out, self.conv.weight, self.conv.bias, pad_left=self.padding)
+    out = self.after_conv[2](self.after_conv[1](self.after_conv[0](out)))
+    return self.after_conv[3](out) if final_dropout else out
+
+
+ConvolutionModule.body = _conv_body
 
 
 def _make_mixer(d_model, mamba_config, bidirectional_ok):
@@ -137,12 +148,26 @@ class ConmambaEncoderLayer(nn.Module):
         self.norm1 = LayerNorm(d_model)
         self.norm2 = LayerNorm(d_model, keep_dtype=True)      # its output is the residual stream of the next layer
         self.drop = nn.Dropout(dropout)
+        self.fuse_add_norm = os.environ.get("CM_NO_FUSE_ADD_NORM") is None   # evaluation strategy only (A/B switch)
 
     def forward(self, x, src_mask: Optional[torch.Tensor] = None, src_key_padding_mask: Optional[torch.Tensor] = None,
                 pos_embs: torch.Tensor = None, dynchunktrain_config=None):
         # The reference builds a conv mask from src_key_padding_mask and then discards it (Conmamba.py:631-635):
         # padding is never masked inside ConMamba.  Reproduced, not "fixed".
         conv_mask = None
+        cm = self.convolution_module
+        if x.is_cuda and cm.use_kernel and dynchunktrain_config is None and self.fuse_add_norm:
+            # Same arithmetic with every "residual add (+ dropout, + 0.5 scale) -> next LayerNorm" pair evaluated by one
+            # sm_100a kernel (cm_add_ln_*); sub-module structure and state_dict are untouched.
+            tr = self.training
+            f1 = self.ffn_module1[1](self.ffn_module1[0](x))
+            x, h = add_dropout_layer_norm(x, f1, self.norm1.norm, FFN_RESIDUAL_SCALE, self.ffn_module1[2].p, tr)
+            x, c_in = add_dropout_layer_norm(x, self.mamba(h), cm.layer_norm, 1.0, 0.0, tr)
+            c_out = cm.body(c_in, final_dropout=False)
+            x, f_in = add_dropout_layer_norm(x, c_out, self.ffn_module2[0], 1.0, cm.after_conv[3].p, tr)
+            f2 = self.ffn_module2[1](f_in)
+            _, out = add_dropout_layer_norm(x, f2, self.norm2.norm, FFN_RESIDUAL_SCALE, self.ffn_module2[2].p, tr)
+            return out
         x = x + FFN_RESIDUAL_SCALE * self.ffn_module1(x)
         skip = x
         x = self.norm1(x)

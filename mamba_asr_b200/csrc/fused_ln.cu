@@ -1,0 +1,290 @@
+// Residual add + dropout + LayerNorm in one pass, forward and backward, for sm_100a.
+//
+// SURVEY.md section 8(f) rank 2 ("fusable LN+residual", reference modules/Conmamba.py:638-649).  Every sub-block of a
+// ConMamba layer ends in   s = a + alpha * dropout(b)   and the next one starts with   y = LayerNorm(s)
+// (ffn_module1 -> norm1, mamba + skip -> convolution_module.layer_norm, conv module -> ffn_module2[0], ffn_module2 ->
+// norm2).  As separate torch kernels that is dropout (read b, write b', write mask), scale, add (read a, read b', write
+// s) and the norm (read s, write y): 25 bytes per element at fp32 residual / bf16 branch; fused it is 13 (read a, b; write
+// s, y, mask), and backward likewise folds the norm's dx, the residual gradient, the dropout mask and alpha into one pass
+// that also produces the dgamma / dbeta partial rows.
+//
+// Layout and method are those of layernorm.cu's pair-vectorised kernels: one warp owns two rows at a time, a lane owns
+// column pairs lane + 32 i, statistics by warp shuffles in fp32.  The dropout mask comes from a counter-based hash of
+// (seed, call id, element index): no RNG state in the kernel, a fresh mask per call site and per step (the seed is read
+// from device memory, so a CUDA-graph replay sees the value the host advanced before it); the mask is stored (1 byte per
+// element) and re-read by backward.  Roof: HBM.
+#include "common.cuh"
+
+namespace cm {
+
+constexpr int kFlWarps = 8;
+
+template <typename T> struct Fl2;
+template <> struct Fl2<float> {
+  static __device__ __forceinline__ float2 ld(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+  static __device__ __forceinline__ void st(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+};
+template <> struct Fl2<__nv_bfloat16> {
+  static __device__ __forceinline__ float2 ld(const __nv_bfloat16* p) {
+    const uint32_t r = __ldg(reinterpret_cast<const uint32_t*>(p));
+    return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u));
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, float2 v) {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y);
+  }
+};
+
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {   // "lowbias32" integer finaliser
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t drop_key(const int64_t* seed, uint32_t call_id) {
+  const uint64_t s = seed ? static_cast<uint64_t>(*seed) : 0x243F6A8885A308D3ull;
+  return mix32(static_cast<uint32_t>(s) ^ mix32(static_cast<uint32_t>(s >> 32) + call_id * 0x9E3779B9u + 0x85EBCA6Bu));
+}
+// two 16-bit uniform samples for the column pair `pi` of `row`
+__device__ __forceinline__ uint32_t drop_bits(uint32_t key, int64_t row, int np, int pi) {
+  const uint64_t idx = static_cast<uint64_t>(row) * np + pi;
+  return mix32((static_cast<uint32_t>(idx) * 0x9E3779B9u) ^ key ^ mix32(static_cast<uint32_t>(idx >> 32) + 0x68E31DA4u));
+}
+
+template <typename Ta, typename Tb, typename Ty, int NPP>
+__global__ void __launch_bounds__(32 * kFlWarps) add_ln_fwd_kernel(const cm_add_ln_args A) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row0 = ((int64_t)blockIdx.x * kFlWarps + (threadIdx.x >> 5)) * 2;
+  if (row0 >= A.rows) return;
+  const bool two = row0 + 1 < A.rows;
+  const int C = A.cols, np = C >> 1;
+  const Ta* a = static_cast<const Ta*>(A.a);
+  const Tb* b = static_cast<const Tb*>(A.b);
+  const bool drop = A.mask != nullptr;
+  const uint32_t thr = drop ? (uint32_t)(A.p_drop * 65536.0f) : 0u;
+  const float keep_scale = drop ? A.alpha / (1.0f - A.p_drop) : A.alpha;
+  const uint32_t key = drop ? drop_key(A.seed, A.call_id) : 0u;
+  float2 v[2][NPP];
+  float s[2] = {0.f, 0.f};
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int64_t row = row0 + (two ? r : 0);
+#pragma unroll
+    for (int i = 0; i < NPP; ++i) {
+      const int pi = lane + 32 * i;
+      float2 t = make_float2(0.f, 0.f);
+      if (pi < np) {
+        t = Fl2<Ta>::ld(a + row * A.a_stride + 2 * pi);
+        if (b != nullptr) {
+          const float2 bv = Fl2<Tb>::ld(b + row * A.b_stride + 2 * pi);
+          float kx = keep_scale, ky = keep_scale;
+          if (drop) {
+            const uint32_t h = drop_bits(key, row, np, pi);
+            const bool k0 = (h & 0xffffu) >= thr, k1 = (h >> 16) >= thr;
+            kx = k0 ? keep_scale : 0.f; ky = k1 ? keep_scale : 0.f;
+            if (r == 0 || two)
+              *reinterpret_cast<uchar2*>(A.mask + row * (int64_t)C + 2 * pi) = make_uchar2(k0 ? 1 : 0, k1 ? 1 : 0);
+          }
+          t.x = fmaf(kx, bv.x, t.x); t.y = fmaf(ky, bv.y, t.y);
+        }
+        if (A.s != nullptr && (r == 0 || two)) Fl2<Ta>::st(static_cast<Ta*>(A.s) + row * A.s_stride + 2 * pi, t);
+        // the statistics are taken from the value as the residual stream stores it (what backward re-reads)
+        if (sizeof(Ta) == 2) t = make_float2(Elem<Ta>::round(t.x), Elem<Ta>::round(t.y));
+      }
+      v[r][i] = t;
+      s[r] += t.x + t.y;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s[0] += __shfl_xor_sync(0xffffffffu, s[0], o);
+    s[1] += __shfl_xor_sync(0xffffffffu, s[1], o);
+  }
+  const float invC = 1.f / (float)C;
+  float mu[2] = {s[0] * invC, s[1] * invC}, q[2] = {0.f, 0.f};
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int i = 0; i < NPP; ++i) {
+      const int pi = lane + 32 * i;
+      if (pi < np) {
+        const float d0 = v[r][i].x - mu[r], d1 = v[r][i].y - mu[r];
+        q[r] = fmaf(d0, d0, fmaf(d1, d1, q[r]));
+      }
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    q[0] += __shfl_xor_sync(0xffffffffu, q[0], o);
+    q[1] += __shfl_xor_sync(0xffffffffu, q[1], o);
+  }
+  const float rs[2] = {rsqrtf(q[0] * invC + A.eps), rsqrtf(q[1] * invC + A.eps)};
+  Ty* y = static_cast<Ty*>(A.y);
+#pragma unroll
+  for (int i = 0; i < NPP; ++i) {
+    const int pi = lane + 32 * i;
+    if (pi < np) {
+      const float2 g = A.gamma ? __ldg(reinterpret_cast<const float2*>(A.gamma + 2 * pi)) : make_float2(1.f, 1.f);
+      const float2 bb = A.beta ? __ldg(reinterpret_cast<const float2*>(A.beta + 2 * pi)) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        if (r == 1 && !two) break;
+        Fl2<Ty>::st(y + (row0 + r) * A.y_stride + 2 * pi,
+                    make_float2(fmaf((v[r][i].x - mu[r]) * rs[r], g.x, bb.x), fmaf((v[r][i].y - mu[r]) * rs[r], g.y, bb.y)));
+      }
+    }
+  }
+  if (lane == 0) {
+    A.mean[row0] = mu[0]; A.rstd[row0] = rs[0];
+    if (two) { A.mean[row0 + 1] = mu[1]; A.rstd[row0 + 1] = rs[1]; }
+  }
+}
+
+// backward: total = LayerNorm-backward(dy; s) + ds ;  da = total ;  db = alpha * mask / (1 - p) * total
+// One row per warp iteration, every load of the row (s, dy, ds, mask) issued before the first use: with the residual
+// gradient and the mask fetched after the row reductions the kernel paid two memory round trips per row (measured 68 us
+// for 32064 x 256 = 2.0 TB/s); two rows in flight per warp with all loads up front need 150 registers (1 CTA / SM).
+// Measured at 32064 x 256 (fp32 residual, bf16 branch): 4 CTAs / SM (64 registers, 24 B spilled) 46 us, 2 CTAs 48 us,
+// 3 CTAs 59 us.
+#ifndef CM_FL_BWD_MINB
+#define CM_FL_BWD_MINB 4
+#endif
+template <typename Ta, typename Tb, typename Ty, int NPP>
+__global__ void __launch_bounds__(32 * kFlWarps, (NPP <= 4 ? CM_FL_BWD_MINB : 1)) add_ln_bwd_kernel(const cm_add_ln_args A) {
+  __shared__ float2 red[kFlWarps][32 * NPP + 1];   // reused for dgamma, then dbeta
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int C = A.cols, np = C >> 1;
+  const Ta* sx = static_cast<const Ta*>(A.s);
+  const Ty* dy = static_cast<const Ty*>(A.dy);
+  const Ta* ds = static_cast<const Ta*>(A.ds);
+  Ta* da = static_cast<Ta*>(A.da);
+  Tb* db_out = static_cast<Tb*>(A.db);
+  const bool drop = A.mask != nullptr;
+  const float keep_scale = drop ? A.alpha / (1.0f - A.p_drop) : A.alpha;
+  float2 g[NPP], dg[NPP], db[NPP];
+#pragma unroll
+  for (int i = 0; i < NPP; ++i) {
+    const int pi = lane + 32 * i;
+    g[i] = (A.gamma && pi < np) ? __ldg(reinterpret_cast<const float2*>(A.gamma + 2 * pi)) : make_float2(1.f, 1.f);
+    dg[i] = make_float2(0.f, 0.f); db[i] = make_float2(0.f, 0.f);
+  }
+  const float invC = 1.f / (float)C;
+  const int64_t rstep = (int64_t)gridDim.x * kFlWarps;
+  for (int64_t row = (int64_t)blockIdx.x * kFlWarps + warp; row < A.rows; row += rstep) {
+    float2 xh[NPP], gy[NPP], e[NPP];
+    unsigned short mk[NPP];
+    const float mu = __ldg(A.mean + row), rs = __ldg(A.rstd + row);
+#pragma unroll
+    for (int i = 0; i < NPP; ++i) {
+      const int pi = lane + 32 * i;
+      const bool in = pi < np;
+      xh[i] = in ? Fl2<Ta>::ld(sx + row * A.s_stride + 2 * pi) : make_float2(0.f, 0.f);
+      gy[i] = in ? Fl2<Ty>::ld(dy + row * A.dy_stride + 2 * pi) : make_float2(0.f, 0.f);
+      e[i] = (ds != nullptr && in) ? Fl2<Ta>::ld(ds + row * A.ds_stride + 2 * pi) : make_float2(0.f, 0.f);
+      mk[i] = (drop && in) ? __ldg(reinterpret_cast<const unsigned short*>(A.mask + row * (int64_t)C + 2 * pi))
+                           : (unsigned short)0x0101;
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPP; ++i) {
+      const int pi = lane + 32 * i;
+      const float2 dv = gy[i];
+      const float2 h = (pi < np) ? make_float2((xh[i].x - mu) * rs, (xh[i].y - mu) * rs) : make_float2(0.f, 0.f);
+      xh[i] = h;
+      gy[i] = make_float2(dv.x * g[i].x, dv.y * g[i].y);
+      dg[i].x = fmaf(dv.x, h.x, dg[i].x); dg[i].y = fmaf(dv.y, h.y, dg[i].y);
+      db[i].x += dv.x; db[i].y += dv.y;
+      s1 += gy[i].x + gy[i].y;
+      s2 = fmaf(gy[i].x, h.x, fmaf(gy[i].y, h.y, s2));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float m1 = s1 * invC, m2 = s2 * invC;
+#pragma unroll
+    for (int i = 0; i < NPP; ++i) {
+      const int pi = lane + 32 * i;
+      if (pi < np) {
+        const float2 t = make_float2(fmaf(rs, gy[i].x - m1 - xh[i].x * m2, e[i].x), fmaf(rs, gy[i].y - m1 - xh[i].y * m2, e[i].y));
+        Fl2<Ta>::st(da + row * A.da_stride + 2 * pi, t);
+        if (db_out != nullptr) {
+          const float kx = (mk[i] & 0x00ffu) ? keep_scale : 0.f, ky = (mk[i] & 0xff00u) ? keep_scale : 0.f;
+          Fl2<Tb>::st(db_out + row * A.db_stride + 2 * pi, make_float2(kx * t.x, ky * t.y));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass) __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NPP; ++i) red[warp][lane + 32 * i] = pass ? db[i] : dg[i];
+    __syncthreads();
+    float* dst = pass ? A.dbeta_part : A.dgamma_part;
+    for (int pi = threadIdx.x; pi < np; pi += blockDim.x) {
+      float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int w = 0; w < kFlWarps; ++w) { acc.x += red[w][pi].x; acc.y += red[w][pi].y; }
+      *reinterpret_cast<float2*>(dst + (int64_t)blockIdx.x * C + 2 * pi) = acc;
+    }
+  }
+}
+
+static bool al(const void* p, size_t n) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % n) == 0; }
+
+template <typename Ta, typename Tb, typename Ty>
+static int add_ln_launch(const cm_add_ln_args& a, bool bwd, cudaStream_t st) {
+  const int C = a.cols;
+  if (!bwd) {
+    const unsigned grid = (unsigned)((a.rows + 2 * kFlWarps - 1) / (2 * kFlWarps));
+#define FL_F(N) add_ln_fwd_kernel<Ta, Tb, Ty, N><<<grid, 32 * kFlWarps, 0, st>>>(a)
+    if (C <= 192) FL_F(3); else if (C <= 256) FL_F(4); else if (C <= 512) FL_F(8); else FL_F(16);
+#undef FL_F
+  } else {
+    const int nblk = cm_layernorm_num_part(a.rows);
+#define FL_B(N) add_ln_bwd_kernel<Ta, Tb, Ty, N><<<nblk, 32 * kFlWarps, 0, st>>>(a)
+    if (C <= 192) FL_B(3); else if (C <= 256) FL_B(4); else if (C <= 512) FL_B(8); else FL_B(16);
+#undef FL_B
+  }
+  CM_LAUNCH_CHECK();
+  return 0;
+}
+
+static int add_ln_dispatch(const cm_add_ln_args& a, bool bwd, cudaStream_t st) {
+#define GO(TA, TB, TY) return add_ln_launch<TA, TB, TY>(a, bwd, st)
+  const int bd = a.b ? a.b_dtype : (a.db ? a.b_dtype : a.a_dtype == CM_F32 ? CM_F32 : CM_BF16);
+  if (a.a_dtype == CM_F32 && bd == CM_BF16 && a.y_dtype == CM_BF16) GO(float, __nv_bfloat16, __nv_bfloat16);
+  if (a.a_dtype == CM_F32 && bd == CM_BF16 && a.y_dtype == CM_F32) GO(float, __nv_bfloat16, float);
+  if (a.a_dtype == CM_F32 && bd == CM_F32 && a.y_dtype == CM_F32) GO(float, float, float);
+  if (a.a_dtype == CM_BF16 && bd == CM_BF16 && a.y_dtype == CM_BF16) GO(__nv_bfloat16, __nv_bfloat16, __nv_bfloat16);
+  if (a.a_dtype == CM_BF16 && bd == CM_BF16 && a.y_dtype == CM_F32) GO(__nv_bfloat16, __nv_bfloat16, float);
+#undef GO
+  return CM_ERR_UNSUPPORTED;
+}
+
+}  // namespace cm
+
+static int add_ln_common_ok(const cm_add_ln_args* a) {
+  if (!a || a->rows <= 0 || a->cols <= 0 || !a->mean || !a->rstd) return CM_ERR_BAD_ARG;
+  if (a->cols > 1024 || (a->cols & 1)) return CM_ERR_UNSUPPORTED;
+  if (a->p_drop < 0.f || a->p_drop >= 1.f) return CM_ERR_BAD_ARG;
+  if (!cm::al(a->gamma, 8) || !cm::al(a->beta, 8) || !cm::al(a->mask, 2)) return CM_ERR_UNSUPPORTED;
+  return 0;
+}
+
+extern "C" int cm_add_ln_fwd(const cm_add_ln_args* a, void* stream) {
+  if (int rc = add_ln_common_ok(a)) return rc;
+  if (!a->a || !a->y) return CM_ERR_BAD_ARG;
+  if (a->mask != nullptr && (a->b == nullptr || a->p_drop <= 0.f)) return CM_ERR_BAD_ARG;
+  if (!cm::al(a->a, 8) || !cm::al(a->b, 4) || !cm::al(a->s, 8) || !cm::al(a->y, 4)) return CM_ERR_UNSUPPORTED;
+  if ((a->a_stride | a->b_stride | a->s_stride | a->y_stride) & 1) return CM_ERR_UNSUPPORTED;
+  return cm::add_ln_dispatch(*a, false, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int cm_add_ln_bwd(const cm_add_ln_args* a, void* stream) {
+  if (int rc = add_ln_common_ok(a)) return rc;
+  if (!a->s || !a->dy || !a->da || !a->dgamma_part || !a->dbeta_part) return CM_ERR_BAD_ARG;
+  if (!cm::al(a->s, 8) || !cm::al(a->dy, 4) || !cm::al(a->ds, 8) || !cm::al(a->da, 8) || !cm::al(a->db, 4) ||
+      !cm::al(a->dgamma_part, 8) || !cm::al(a->dbeta_part, 8))
+    return CM_ERR_UNSUPPORTED;
+  if ((a->s_stride | a->dy_stride | a->ds_stride | a->da_stride | a->db_stride) & 1) return CM_ERR_UNSUPPORTED;
+  return cm::add_ln_dispatch(*a, true, static_cast<cudaStream_t>(stream));
+}

@@ -521,6 +521,97 @@ def layernorm_backward(x2d, dy2d, weight, mean, rstd, need_wgrad=True):
     return dx, dg, db
 
 
+# ------------------------------------------------------------------------------------------------ add + dropout + LayerNorm
+ADD_LN_COMBOS = {(torch.float32, torch.bfloat16, torch.bfloat16), (torch.float32, torch.bfloat16, torch.float32),
+                 (torch.float32, torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16, torch.bfloat16),
+                 (torch.bfloat16, torch.bfloat16, torch.float32)}
+
+
+def add_ln_supported(a2d, b2d, out_dtype):
+    """True when cm_add_ln_* implements this (dtype, shape, alignment) combination."""
+    rows, Cn = a2d.shape
+    bd = a2d.dtype if b2d is None else b2d.dtype
+    if b2d is None and a2d.dtype == torch.float32 and out_dtype == torch.bfloat16:
+        bd = torch.bfloat16
+    if (a2d.dtype, bd, out_dtype) not in ADD_LN_COMBOS or Cn % 2 or Cn > 1024:
+        return False
+    for t in (a2d, b2d):
+        if t is not None and (t.stride(1) != 1 or t.stride(0) % 2 or t.data_ptr() % 8):
+            return False
+    return True
+
+
+def add_ln_forward(a2d, b2d, weight, bias, eps, alpha, p_drop, seed, call_id, out_dtype, need_s=True):
+    """cm_add_ln_fwd: s = a + alpha * dropout_p(b); y = LayerNorm(s).  a2d (rows, C); b2d (rows, C) or None; seed: int64
+    CUDA scalar tensor or None.  Returns (s, y, mean, rstd, mask); mask is None when p_drop == 0."""
+    lib = cabi.lib()
+    _require_cuda(a2d, "a")
+    rows, Cn = a2d.shape
+    dev = a2d.device
+    s = torch.empty((rows, Cn), dtype=a2d.dtype, device=dev) if (need_s or b2d is not None) else None
+    y = torch.empty((rows, Cn), dtype=out_dtype, device=dev)
+    mean = torch.empty((rows,), dtype=torch.float32, device=dev)
+    rstd = torch.empty((rows,), dtype=torch.float32, device=dev)
+    mask = torch.empty((rows, Cn), dtype=torch.uint8, device=dev) if (p_drop > 0.0 and b2d is not None) else None
+    a = cabi.AddLnArgs()
+    a.rows, a.cols = rows, Cn
+    a.a_dtype, a.y_dtype = cabi.dtype_code(a2d.dtype), cabi.dtype_code(out_dtype)
+    a.b_dtype = cabi.dtype_code(b2d.dtype) if b2d is not None else a.a_dtype
+    a.eps, a.alpha, a.p_drop = float(eps), float(alpha), float(p_drop if mask is not None else 0.0)
+    a.call_id = int(call_id) & 0xffffffff
+    a.seed = cabi.ptr(seed)
+    a.a, a.a_stride = a2d.data_ptr(), a2d.stride(0)
+    if b2d is not None:
+        a.b, a.b_stride = b2d.data_ptr(), b2d.stride(0)
+    if s is not None:
+        a.s, a.s_stride = s.data_ptr(), s.stride(0)
+    a.y, a.y_stride = y.data_ptr(), y.stride(0)
+    a.mask = cabi.ptr(mask)
+    a.gamma, a.beta = cabi.ptr(weight), cabi.ptr(bias)
+    a.mean, a.rstd = mean.data_ptr(), rstd.data_ptr()
+    _call("cm_add_ln_fwd", lib.cm_add_ln_fwd, C.byref(a), cabi.stream_ptr())
+    return s, y, mean, rstd, mask
+
+
+def add_ln_backward(s2d, dy2d, ds2d, weight, mean, rstd, mask, alpha, p_drop, b_dtype, need_db=True, need_wgrad=True):
+    """cm_add_ln_bwd + deterministic reduction of the dgamma / dbeta partial rows.
+    Returns (da in s's dtype, db in b_dtype or None, dgamma fp32 (C,), dbeta fp32 (C,))."""
+    lib = cabi.lib()
+    rows, Cn = s2d.shape
+    dev = s2d.device
+    if dy2d.stride(1) != 1 or dy2d.stride(0) % 2:
+        dy2d = dy2d.contiguous()
+    if ds2d is not None and (ds2d.stride(1) != 1 or ds2d.stride(0) % 2 or ds2d.dtype != s2d.dtype):
+        ds2d = ds2d.to(s2d.dtype).contiguous()
+    da = torch.empty((rows, Cn), dtype=s2d.dtype, device=dev)
+    db = torch.empty((rows, Cn), dtype=b_dtype, device=dev) if need_db else None
+    n_part = lib.cm_layernorm_num_part(rows)
+    dg_part = torch.empty((n_part, Cn), dtype=torch.float32, device=dev)
+    db_part = torch.empty((n_part, Cn), dtype=torch.float32, device=dev)
+    a = cabi.AddLnArgs()
+    a.rows, a.cols = rows, Cn
+    a.a_dtype, a.b_dtype, a.y_dtype = cabi.dtype_code(s2d.dtype), cabi.dtype_code(b_dtype), cabi.dtype_code(dy2d.dtype)
+    a.alpha, a.p_drop = float(alpha), float(p_drop if mask is not None else 0.0)
+    a.s, a.s_stride = s2d.data_ptr(), s2d.stride(0)
+    a.mask = cabi.ptr(mask)
+    a.gamma = cabi.ptr(weight)
+    a.mean, a.rstd = mean.data_ptr(), rstd.data_ptr()
+    a.dy, a.dy_stride = dy2d.data_ptr(), dy2d.stride(0)
+    if ds2d is not None:
+        a.ds, a.ds_stride = ds2d.data_ptr(), ds2d.stride(0)
+    a.da, a.da_stride = da.data_ptr(), da.stride(0)
+    if db is not None:
+        a.db, a.db_stride = db.data_ptr(), db.stride(0)
+    a.dgamma_part, a.dbeta_part = dg_part.data_ptr(), db_part.data_ptr()
+    _call("cm_add_ln_bwd", lib.cm_add_ln_bwd, C.byref(a), cabi.stream_ptr())
+    if not need_wgrad:
+        return da, db, None, None
+    dg = torch.empty((Cn,), dtype=torch.float32, device=dev)
+    dbt = torch.empty((Cn,), dtype=torch.float32, device=dev)
+    reduce_many([(dg_part, dg), (db_part, dbt)])
+    return da, db, dg, dbt
+
+
 # ------------------------------------------------------------------------------------------------ depthwise conv1d
 DWCONV_KSIZES = (3, 7, 15, 31)
 

@@ -70,3 +70,91 @@ class FusedLayerNorm(nn.LayerNorm):
         if self.keep_dtype:
             out_dtype = torch.float32 if torch.is_autocast_enabled("cuda") else x.dtype
         return layer_norm(x, self.weight, self.bias, self.eps, out_dtype=out_dtype)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# residual add + dropout + LayerNorm in one pass (cm_add_ln_fwd / cm_add_ln_bwd)
+class DropoutSeed:
+    """Device-resident seed of the fused dropout masks.  Every call site gets its own ``call_id`` (a host counter); the
+    int64 device scalar is advanced once per step by ``advance()`` - an in-place add that a captured CUDA graph replays,
+    so each replay draws fresh masks although the call ids are baked into the graph."""
+
+    _state = {}
+    _calls = 0
+
+    @classmethod
+    def tensor(cls, device):
+        key = (device.type, device.index)
+        t = cls._state.get(key)
+        if t is None:
+            t = torch.full((1,), torch.initial_seed() & 0x7fffffffffffffff, dtype=torch.int64, device=device)
+            cls._state[key] = t
+        return t
+
+    @classmethod
+    def advance(cls, device):
+        cls.tensor(device).add_(0x9E3779B97F4A7C15 & 0x7fffffffffffffff)
+
+    @classmethod
+    def next_call_id(cls):
+        cls._calls += 1
+        return cls._calls
+
+
+class _AddDropoutLayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, weight, bias, eps, alpha, p_drop, out_dtype):
+        Cn = a.shape[-1]
+        a2 = a.reshape(-1, Cn)
+        b2 = None if b is None else b.reshape(-1, Cn)
+        seed = DropoutSeed.tensor(a.device) if p_drop > 0.0 else None
+        s, y, mean, rstd, mask = K.add_ln_forward(a2, b2, weight, bias, eps, alpha, p_drop, seed,
+                                                  DropoutSeed.next_call_id(), out_dtype)
+        ctx.save_for_backward(s, weight, mean, rstd, mask)
+        ctx.shape = a.shape
+        ctx.alpha, ctx.p_drop = alpha, p_drop
+        ctx.b_dtype = None if b is None else b.dtype
+        ctx.has_bias = bias is not None
+        return s.view(a.shape), y.view(a.shape)
+
+    @staticmethod
+    def backward(ctx, ds, dy):
+        s, weight, mean, rstd, mask = ctx.saved_tensors
+        Cn = s.shape[1]
+        if dy is None:
+            dy = torch.zeros(ctx.shape, dtype=s.dtype, device=s.device)
+        need_w = weight is not None and (ctx.needs_input_grad[2] or ctx.needs_input_grad[3])
+        da, db, dg, dbt = K.add_ln_backward(s, dy.reshape(-1, Cn), None if ds is None else ds.reshape(-1, Cn), weight,
+                                            mean, rstd, mask, ctx.alpha, ctx.p_drop, ctx.b_dtype or s.dtype,
+                                            need_db=ctx.b_dtype is not None, need_wgrad=need_w)
+        return (da.view(ctx.shape), None if db is None else db.view(ctx.shape),
+                dg.to(weight.dtype) if (need_w and ctx.needs_input_grad[2]) else None,
+                dbt.to(weight.dtype) if (need_w and ctx.has_bias and ctx.needs_input_grad[3]) else None,
+                None, None, None, None)
+
+
+def add_dropout_layer_norm(a, b, norm, alpha=1.0, p_drop=0.0, training=True):
+    """(s, y) with  s = a + alpha * dropout(b, p_drop)  and  y = norm(s)  for a ``FusedLayerNorm`` ``norm`` - one kernel
+    forward, one backward (cm_add_ln_*) when the combination is implemented, else the separate ops.  ``b`` may be None
+    (s = a)."""
+    p = float(p_drop) if training else 0.0
+    out_dtype = None
+    if norm.keep_dtype:
+        out_dtype = torch.float32 if torch.is_autocast_enabled("cuda") else a.dtype
+    elif torch.is_autocast_enabled("cuda"):
+        out_dtype = torch.get_autocast_dtype("cuda")
+    else:
+        out_dtype = a.dtype
+    Cn = a.shape[-1]
+    ok = (b is not None and a.is_cuda and a.is_contiguous() and b.is_contiguous() and b.shape == a.shape
+          and K.add_ln_supported(a.reshape(-1, Cn), b.reshape(-1, Cn), out_dtype))
+    if not ok:
+        if b is None:
+            s = a
+        else:
+            s = a + alpha * (torch.nn.functional.dropout(b, p, training=True) if p > 0 else b)
+        return s, norm(s)
+    w = norm.weight if norm.weight is None or norm.weight.dtype == torch.float32 else norm.weight.float()
+    bb = norm.bias if norm.bias is None or norm.bias.dtype == torch.float32 else norm.bias.float()
+    with torch.autocast("cuda", enabled=False):
+        return _AddDropoutLayerNormFn.apply(a, b, w, bb, norm.eps, float(alpha), p, out_dtype)

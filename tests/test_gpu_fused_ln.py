@@ -1,0 +1,123 @@
+"""GPU parity of the fused residual-add + dropout + LayerNorm kernels (cm_add_ln_fwd / cm_add_ln_bwd) against the plain
+torch fp32 composition  s = a + alpha * dropout(b) ; y = layer_norm(s)  (reference modules/Conmamba.py:638-649)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from cm_testutil import assert_close
+
+pytestmark = pytest.mark.gpu
+
+COMBOS = [(torch.float32, torch.bfloat16, torch.bfloat16), (torch.float32, torch.bfloat16, torch.float32),
+          (torch.float32, torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16, torch.bfloat16),
+          (torch.bfloat16, torch.bfloat16, torch.float32)]
+
+
+def _inputs(shape, ta, tb, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randn(*shape, generator=g).to(ta)
+    b = torch.randn(*shape, generator=g).to(tb)
+    C = shape[-1]
+    w, bias = 1.0 + 0.2 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    cs, cy = torch.randn(*shape, generator=g), torch.randn(*shape, generator=g)
+    return a, b, w, bias, cs, cy
+
+
+@pytest.mark.parametrize("combo", COMBOS)
+@pytest.mark.parametrize("shape", [(3, 37, 144), (2, 501, 256), (1, 1, 512), (5, 3, 34), (2, 9, 1024)])
+@pytest.mark.parametrize("use_s", [True, False])
+def test_add_layer_norm_no_dropout_matches_torch(combo, shape, use_s):
+    from mamba_asr_b200.layernorm import FusedLayerNorm, add_dropout_layer_norm
+    ta, tb, ty = combo
+    a, b, w, bias, cs, cy = _inputs(shape, ta, tb)
+    C = shape[-1]
+    alpha = 0.5
+    # fp32 reference on the rounded inputs; s is rounded to a's dtype before the norm, as the residual stream stores it
+    ar, br = a.float().clone().requires_grad_(True), b.float().clone().requires_grad_(True)
+    wr, biasr = w.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    s_ref = ar + alpha * br
+    s_st = s_ref + (s_ref.detach().to(ta).float() - s_ref.detach())          # straight-through rounding
+    y_ref = F.layer_norm(s_st, (C,), wr, biasr, 1e-5)
+    loss = (y_ref * cy).sum() + ((s_ref * cs).sum() if use_s else 0.0)
+    loss.backward()
+
+    norm = FusedLayerNorm(C).cuda()
+    norm.keep_dtype = ty == torch.float32
+    with torch.no_grad():
+        norm.weight.copy_(w)
+        norm.bias.copy_(bias)
+    ag, bg = a.detach().cuda().requires_grad_(True), b.detach().cuda().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(tb == torch.bfloat16)):
+        s, y = add_dropout_layer_norm(ag, bg, norm, alpha=alpha, p_drop=0.0, training=True)
+    assert s.dtype == ta and y.dtype == ty, (s.dtype, y.dtype)
+    lg = (y.float() * cy.cuda()).sum() + ((s.float() * cs.cuda()).sum() if use_s else 0.0)
+    lg.backward()
+    assert_close(s.float(), s_ref.detach().to(ta).float(), ta, what="s")
+    assert_close(y.float(), y_ref, ty, what="y")
+    lo = torch.bfloat16 if torch.bfloat16 in combo else torch.float32
+    assert_close(ag.grad.float(), ar.grad, ta if ta == torch.bfloat16 else lo, floor="max", what="da")
+    assert_close(bg.grad.float(), br.grad, lo, floor="max", what="db")
+    assert_close(norm.weight.grad, wr.grad, lo, floor="max", what="dgamma")
+    assert_close(norm.bias.grad, biasr.grad, lo, floor="max", what="dbeta")
+
+
+@pytest.mark.parametrize("combo", [COMBOS[0], COMBOS[2], COMBOS[3]])
+def test_fused_dropout_mask_statistics_and_gradient(combo):
+    from mamba_asr_b200 import kernels as K
+    from mamba_asr_b200.layernorm import DropoutSeed
+    ta, tb, ty = combo
+    rows, C, p, alpha = 4096, 256, 0.1, 0.5
+    a, b, w, bias, cs, cy = _inputs((rows, C), ta, tb, seed=1)
+    a, b, w, bias = a.cuda(), b.cuda(), w.cuda(), bias.cuda()
+    seed = DropoutSeed.tensor(a.device)
+    s, y, mean, rstd, mask = K.add_ln_forward(a, b, w, bias, 1e-5, alpha, p, seed, 7, ty)
+    keep = mask.float()
+    assert set(mask.unique().tolist()) <= {0, 1}
+    assert abs(float(keep.mean()) - (1 - p)) < 3e-3                               # 1M samples: sigma = 3e-4
+    assert float(keep.mean(0).min()) > 0.85 and float(keep.mean(1).min()) > 0.75    # no dead rows / columns
+    s_ref = a.float() + alpha / (1 - p) * keep * b.float()
+    assert_close(s.float(), s_ref.to(ta).float(), ta, what="s with dropout")
+    y_ref = F.layer_norm(s_ref.to(ta).float(), (C,), w, bias, 1e-5)
+    assert_close(y.float(), y_ref, ty, what="y with dropout")
+    # same (seed, call id) -> same mask; another call id or an advanced seed -> a different one
+    m2 = K.add_ln_forward(a, b, w, bias, 1e-5, alpha, p, seed, 7, ty)[4]
+    m3 = K.add_ln_forward(a, b, w, bias, 1e-5, alpha, p, seed, 8, ty)[4]
+    assert torch.equal(mask, m2) and not torch.equal(mask, m3)
+    assert abs(float((mask == m3).float().mean()) - (p * p + (1 - p) ** 2)) < 5e-3  # independent masks
+    DropoutSeed.advance(a.device)
+    m4 = K.add_ln_forward(a, b, w, bias, 1e-5, alpha, p, seed, 7, ty)[4]
+    assert not torch.equal(mask, m4)
+    # backward: db = alpha / (1 - p) * keep * da
+    dy = cy.cuda().to(ty)
+    ds = cs.cuda().to(ta)
+    da, db, dg, dbt = K.add_ln_backward(s, dy, ds, w, mean, rstd, mask, alpha, p, tb)
+    assert_close(db.float(), (alpha / (1 - p)) * keep * da.float(), tb, floor="max", what="db vs mask * da")
+    sr = s.float().requires_grad_(True)
+    (F.layer_norm(sr, (C,), w, bias, 1e-5) * dy.float()).sum().backward()
+    assert_close(da.float(), sr.grad + ds.float(), ta, floor="max", what="da")
+
+
+def test_encoder_layer_fused_path_equals_unfused_ops():
+    """The layer with the fused add+norm kernels against the same layer on the separate ops (dropout off), fp32 and
+    bf16 autocast, forward and backward."""
+    from mamba_asr_b200.conmamba import ConmambaEncoderLayer
+    torch.manual_seed(0)
+    layer = ConmambaEncoderLayer(d_model=64, d_ffn=128, activation=torch.nn.GELU, dropout=0.0,
+                                 mamba_config=dict(d_state=16, expand=2, d_conv=4, bidirectional=True)).cuda()
+    x = torch.randn(2, 45, 64, device="cuda")
+    cot = torch.randn(2, 45, 64, device="cuda")
+    for autocast in (False, True):
+        outs, grads = [], []
+        for fused in (True, False):
+            layer.fuse_add_norm = fused
+            layer.zero_grad(set_to_none=True)
+            xi = x.clone().requires_grad_(True)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                o = layer(xi)
+            (o.float() * cot).sum().backward()
+            outs.append(o.float())
+            grads.append([xi.grad] + [p.grad.clone() for p in layer.parameters()])
+        dt = torch.bfloat16 if autocast else torch.float32
+        assert_close(outs[0], outs[1], dt, what="layer out (autocast=%s)" % autocast)
+        for g0, g1 in zip(grads[0], grads[1]):
+            assert_close(g0, g1, dt, floor="max", what="layer grads (autocast=%s)" % autocast, rtol_mul=2.0)

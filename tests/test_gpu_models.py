@@ -71,7 +71,7 @@ def test_ctc_encoder_stack_forward_backward_matches_cpu_reference():
     loss_g.backward()
     assert lp_g.shape == lp_c.shape
     assert_close(lp_g, lp_c, floor="max", what="log-probs", rtol_mul=5.0)
-    assert abs(float(loss_g) - float(loss_c)) <= 1e-4 * abs(float(loss_c))
+    assert abs(float(loss_g.detach()) - float(loss_c.detach())) <= 1e-4 * abs(float(loss_c.detach()))
     _grads_close(gpu, cpu)
 
 
@@ -95,7 +95,7 @@ def test_s2s_encoder_decoder_forward_backward_matches_cpu_reference():
     loss_g.backward()
     assert_close(pc_g, pc_c, floor="max", what="p_ctc", rtol_mul=5.0)
     assert_close(ps_g, ps_c, floor="max", what="p_seq", rtol_mul=5.0)
-    assert abs(float(loss_g) - float(loss_c)) <= 1e-4 * abs(float(loss_c))
+    assert abs(float(loss_g.detach()) - float(loss_c.detach())) <= 1e-4 * abs(float(loss_c.detach()))
     _grads_close(gpu, cpu)
 
 

@@ -135,6 +135,18 @@ def main():
                 best, med = timek(lambda: K.layernorm_backward(xx, dy, w, mean, rstd), "cm_layernorm_bwd", args.iters, flush)
                 byts = rows * d_model * (2 * xs_ + ys_)
                 print("%-40s ln_bwd %s  best %.4f ms  alg %.1f GB/s (%.1f%%)" % (tag, xdt, best, byts / best / 1e6, 100 * byts / best / 1e6 / peak))
+            # fused residual add + dropout + LayerNorm (fp32 residual, bf16 branch, bf16 out)
+            a32, bb16 = rn(rows, d_model), rn(rows, d_model).to(dt)
+            seed = torch.zeros(1, dtype=torch.int64, device=dev)
+            w, bb = torch.ones(d_model, device=dev), torch.zeros(d_model, device=dev)
+            best, med = timek(lambda: K.add_ln_forward(a32, bb16, w, bb, 1e-5, 0.5, 0.1, seed, 1, dt), "cm_add_ln_fwd", args.iters, flush)
+            byts = rows * d_model * (4 + s + 4 + s + 1)
+            print("%-40s add_ln_fwd      best %.4f ms  alg %.1f GB/s (%.1f%%)" % (tag, best, byts / best / 1e6, 100 * byts / best / 1e6 / peak))
+            sv, yv, mean, rstd, mask = K.add_ln_forward(a32, bb16, w, bb, 1e-5, 0.5, 0.1, seed, 1, dt)
+            dyv, dsv = rn(rows, d_model).to(dt), rn(rows, d_model)
+            best, med = timek(lambda: K.add_ln_backward(sv, dyv, dsv, w, mean, rstd, mask, 0.5, 0.1, dt), "cm_add_ln_bwd", args.iters, flush)
+            byts = rows * d_model * (4 + s + 4 + 1 + 4 + s)
+            print("%-40s add_ln_bwd      best %.4f ms  alg %.1f GB/s (%.1f%%)" % (tag, best, byts / best / 1e6, 100 * byts / best / 1e6 / peak))
             xc = rn(Bt, L, d_model).to(dt)
             wc, bc_ = rn(d_model, 31), rn(d_model)
             best, med = timek(lambda: K.dwconv_forward(xc, wc, bc_, 15), "cm_dwconv_fwd", args.iters, flush)

@@ -111,7 +111,7 @@ class ClockSampler:
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.01)
 
     def start(self):
         if self.nv is not None:

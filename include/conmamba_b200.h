@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CM_ABI_VERSION 4
+#define CM_ABI_VERSION 5
 
 /* element type of activations (u, delta, z, B, C, x, out, and their gradients) */
 enum { CM_F32 = 0, CM_BF16 = 1, CM_F16 = 2 };
@@ -308,6 +308,18 @@ typedef struct {
 
 int cm_add_ln_fwd(const cm_add_ln_args* args, void* stream);
 int cm_add_ln_bwd(const cm_add_ln_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * GELU (exact, erf) + dropout in one pass over a flat tensor (the activation and the
+ * Dropout between the two Linears of speechbrain's PositionalwiseFeedForward, reference modules/Conmamba.py:595-621).
+ *   forward : y = keep/(1-p) * gelu(x), mask (1 byte per element, NULL = no dropout) written for backward
+ *   backward: dx = keep/(1-p) * gelu'(x) * dy
+ * n must be a multiple of 8, pointers 16-byte aligned (mask 8).  Mask = hash of (*seed, call_id, element index).
+ * ---------------------------------------------------------------------------------------------------- */
+int cm_gelu_dropout_fwd(const void* x, void* y, uint8_t* mask, int64_t n, int32_t dtype, float p_drop,
+                        const int64_t* seed, uint32_t call_id, void* stream);
+int cm_gelu_dropout_bwd(const void* x, const void* dy, const uint8_t* mask, void* dx, int64_t n, int32_t dtype,
+                        float p_drop, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Depthwise conv1d over time (the kernel_size = 31 convolution of the ConMamba

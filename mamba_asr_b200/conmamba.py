@@ -24,7 +24,7 @@ from .bimamba import Mamba as BiMamba
 from .bimamba import UniMamba as Mamba
 from .dwconv import depthwise_conv1d
 from .kernels import DWCONV_KSIZES
-from .layernorm import FusedLayerNorm, add_dropout_layer_norm
+from .layernorm import FusedLayerNorm, add_dropout_layer_norm, gelu_dropout
 from .linear import BiasGradLinear, linear as _linear
 
 LAYER_NORM_EPS = 1e-6        # reference ConMambaConstants.LAYER_NORM_EPS (Conmamba.py:687)
@@ -62,6 +62,10 @@ class PositionalwiseFeedForward(nn.Module):
                                  BiasGradLinear(d_ffn, input_size))
 
     def forward(self, x):
+        act, drop = self.ffn[1], self.ffn[2]
+        if x.is_cuda and type(act) is nn.GELU and act.approximate == "none" and os.environ.get("CM_NO_FUSE_GELU") is None:
+            # Linear -> [GELU + Dropout: one sm_100a kernel] -> Linear
+            return self.ffn[3](gelu_dropout(self.ffn[0](x), drop.p, self.training))
         return self.ffn(x)
 
 

@@ -1,0 +1,180 @@
+// GELU (exact, erf) + dropout in one pass, forward and backward, for sm_100a.
+//
+// the position-wise feed-forward modules of a ConMamba layer are
+// Linear -> activation -> Dropout -> Linear (speechbrain PositionalwiseFeedForward; reference modules/Conmamba.py:595-621
+// with activation = GELU from Transformer.py:740-751), the FLOP majority of the layer.  As torch ops the
+// activation and the dropout are two passes over the (rows, d_ffn) tensor forward (9 bytes per element at bf16) and two
+// backward (11 bytes); fused they are one each (5 and 7 bytes).  Eight elements per thread (one 16-byte access at 16-bit
+// types), grid-stride over the flat tensor.  Dropout mask: the counter-based hash of fused_ln.cu, stored as one byte per
+// element for backward.  Roof: HBM.
+#include "common.cuh"
+
+namespace cm {
+
+__device__ __forceinline__ uint32_t act_mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t act_key(const int64_t* seed, uint32_t call_id) {
+  const uint64_t s = seed ? static_cast<uint64_t>(*seed) : 0x243F6A8885A308D3ull;
+  return act_mix32(static_cast<uint32_t>(s) ^ act_mix32(static_cast<uint32_t>(s >> 32) + call_id * 0x9E3779B9u + 0x85EBCA6Bu));
+}
+
+template <typename T> struct Vec8;
+template <> struct Vec8<float> {
+  static __device__ __forceinline__ void ld(const float* p, float* o) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float* v) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <> struct Vec8<__nv_bfloat16> {
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float* o) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { o[2 * i] = __uint_as_float(w[i] << 16); o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float* v) {
+    uint4 r;
+    __nv_bfloat162 t;
+    t = __floats2bfloat162_rn(v[0], v[1]); r.x = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(v[2], v[3]); r.y = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(v[4], v[5]); r.z = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(v[6], v[7]); r.w = *reinterpret_cast<uint32_t*>(&t);
+    *reinterpret_cast<uint4*>(p) = r;
+  }
+};
+template <> struct Vec8<__half> {
+  static __device__ __forceinline__ void ld(const __half* p, float* o) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      o[2 * i] = f.x; o[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void st(__half* p, const float* v) {
+    uint4 r;
+    __half2 t;
+    t = __floats2half2_rn(v[0], v[1]); r.x = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2half2_rn(v[2], v[3]); r.y = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2half2_rn(v[4], v[5]); r.z = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2half2_rn(v[6], v[7]); r.w = *reinterpret_cast<uint32_t*>(&t);
+    *reinterpret_cast<uint4*>(p) = r;
+  }
+};
+
+constexpr float kInvSqrt2 = 0.7071067811865476f;
+constexpr float kInvSqrt2Pi = 0.3989422804014327f;
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * kInvSqrt2)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  return 0.5f * (1.0f + erff(x * kInvSqrt2)) + x * kInvSqrt2Pi * __expf(-0.5f * x * x);
+}
+
+// keep bits of 8 consecutive elements starting at flat index 8 * v: two hashes, 16-bit samples
+__device__ __forceinline__ uint32_t keep8(uint32_t key, int64_t v, uint32_t thr) {
+  uint32_t bits = 0;
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    const uint64_t idx = static_cast<uint64_t>(v) * 4 + h;
+    const uint32_t r = act_mix32((static_cast<uint32_t>(idx) * 0x9E3779B9u) ^ key ^ act_mix32(static_cast<uint32_t>(idx >> 32) + 0x68E31DA4u));
+    bits |= ((r & 0xffffu) >= thr ? 1u : 0u) << (2 * h);
+    bits |= ((r >> 16) >= thr ? 1u : 0u) << (2 * h + 1);
+  }
+  return bits;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gelu_dropout_fwd_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                               uint8_t* __restrict__ mask, int64_t n8, float p,
+                                                               const int64_t* __restrict__ seed, uint32_t call_id) {
+  const bool drop = mask != nullptr;
+  const uint32_t thr = drop ? (uint32_t)(p * 65536.0f) : 0u;
+  const float scale = drop ? 1.0f / (1.0f - p) : 1.0f;
+  const uint32_t key = drop ? act_key(seed, call_id) : 0u;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n8; v += (int64_t)gridDim.x * blockDim.x) {
+    float a[8];
+    Vec8<T>::ld(x + 8 * v, a);
+    const uint32_t kb = drop ? keep8(key, v, thr) : 0xffu;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = ((kb >> i) & 1u) ? scale * gelu_f(a[i]) : 0.f;
+    Vec8<T>::st(y + 8 * v, a);
+    if (drop) {
+      uint2 m;
+      m.x = (kb & 1u) | ((kb & 2u) << 7) | ((kb & 4u) << 14) | ((kb & 8u) << 21);
+      m.y = ((kb >> 4) & 1u) | (((kb >> 4) & 2u) << 7) | (((kb >> 4) & 4u) << 14) | (((kb >> 4) & 8u) << 21);
+      *reinterpret_cast<uint2*>(mask + 8 * v) = m;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gelu_dropout_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                                               const uint8_t* __restrict__ mask, T* __restrict__ dx,
+                                                               int64_t n8, float p) {
+  const bool drop = mask != nullptr;
+  const float scale = drop ? 1.0f / (1.0f - p) : 1.0f;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n8; v += (int64_t)gridDim.x * blockDim.x) {
+    float a[8], g[8];
+    Vec8<T>::ld(x + 8 * v, a);
+    Vec8<T>::ld(dy + 8 * v, g);
+    uint2 m = make_uint2(0x01010101u, 0x01010101u);
+    if (drop) m = __ldg(reinterpret_cast<const uint2*>(mask + 8 * v));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t w = i < 4 ? m.x : m.y;
+      const bool k = (w >> (8 * (i & 3))) & 0xffu;
+      a[i] = k ? scale * g[i] * gelu_grad_f(a[i]) : 0.f;
+    }
+    Vec8<T>::st(dx + 8 * v, a);
+  }
+}
+
+static unsigned act_grid(int64_t n8) {
+  const int64_t need = (n8 + 255) / 256;
+  const int64_t cap = 148 * 8;
+  return (unsigned)(need < cap ? (need < 1 ? 1 : need) : cap);
+}
+
+}  // namespace cm
+
+static bool act_al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int cm_gelu_dropout_fwd(const void* x, void* y, uint8_t* mask, int64_t n, int32_t dtype, float p_drop,
+                                   const int64_t* seed, uint32_t call_id, void* stream) {
+  if (!x || !y || n <= 0 || !cm::dtype_ok(dtype) || p_drop < 0.f || p_drop >= 1.f) return CM_ERR_BAD_ARG;
+  if ((n & 7) || !act_al16(x) || !act_al16(y) || (mask && (reinterpret_cast<uintptr_t>(mask) & 7))) return CM_ERR_UNSUPPORTED;
+  if (mask && p_drop <= 0.f) return CM_ERR_BAD_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n8 = n >> 3;
+  const unsigned grid = cm::act_grid(n8);
+  switch (dtype) {
+    case CM_F32: cm::gelu_dropout_fwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), static_cast<float*>(y), mask, n8, p_drop, seed, call_id); break;
+    case CM_BF16: cm::gelu_dropout_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), mask, n8, p_drop, seed, call_id); break;
+    default: cm::gelu_dropout_fwd_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), static_cast<__half*>(y), mask, n8, p_drop, seed, call_id); break;
+  }
+  CM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cm_gelu_dropout_bwd(const void* x, const void* dy, const uint8_t* mask, void* dx, int64_t n, int32_t dtype,
+                                   float p_drop, void* stream) {
+  if (!x || !dy || !dx || n <= 0 || !cm::dtype_ok(dtype) || p_drop < 0.f || p_drop >= 1.f) return CM_ERR_BAD_ARG;
+  if ((n & 7) || !act_al16(x) || !act_al16(dy) || !act_al16(dx) || (mask && (reinterpret_cast<uintptr_t>(mask) & 7)))
+    return CM_ERR_UNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n8 = n >> 3;
+  const unsigned grid = cm::act_grid(n8);
+  switch (dtype) {
+    case CM_F32: cm::gelu_dropout_bwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), static_cast<const float*>(dy), mask, static_cast<float*>(dx), n8, p_drop); break;
+    case CM_BF16: cm::gelu_dropout_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), mask, static_cast<__nv_bfloat16*>(dx), n8, p_drop); break;
+    default: cm::gelu_dropout_bwd_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), static_cast<const __half*>(dy), mask, static_cast<__half*>(dx), n8, p_drop); break;
+  }
+  CM_LAUNCH_CHECK();
+  return 0;
+}

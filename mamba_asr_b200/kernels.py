@@ -612,6 +612,33 @@ def add_ln_backward(s2d, dy2d, ds2d, weight, mean, rstd, mask, alpha, p_drop, b_
     return da, db, dg, dbt
 
 
+# ------------------------------------------------------------------------------------------------ GELU + dropout
+def gelu_dropout_supported(x):
+    return x.is_cuda and x.is_contiguous() and x.numel() % 8 == 0 and x.data_ptr() % 16 == 0 and \
+        x.dtype in (torch.float32, torch.bfloat16, torch.float16)
+
+
+def gelu_dropout_forward(x, p_drop, seed, call_id):
+    """cm_gelu_dropout_fwd on a contiguous tensor: returns (y, mask) with mask None when p_drop == 0."""
+    lib = cabi.lib()
+    _require_cuda(x, "x")
+    y = torch.empty_like(x)
+    mask = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if p_drop > 0.0 else None
+    _call("cm_gelu_dropout_fwd", lib.cm_gelu_dropout_fwd, x.data_ptr(), y.data_ptr(), cabi.ptr(mask), x.numel(),
+          cabi.dtype_code(x.dtype), float(p_drop), cabi.ptr(seed), int(call_id) & 0xffffffff, cabi.stream_ptr())
+    return y, mask
+
+
+def gelu_dropout_backward(x, dy, mask, p_drop):
+    lib = cabi.lib()
+    if not dy.is_contiguous() or dy.dtype != x.dtype:
+        dy = dy.to(x.dtype).contiguous()
+    dx = torch.empty_like(x)
+    _call("cm_gelu_dropout_bwd", lib.cm_gelu_dropout_bwd, x.data_ptr(), dy.data_ptr(), cabi.ptr(mask), dx.data_ptr(),
+          x.numel(), cabi.dtype_code(x.dtype), float(p_drop if mask is not None else 0.0), cabi.stream_ptr())
+    return dx
+
+
 # ------------------------------------------------------------------------------------------------ depthwise conv1d
 DWCONV_KSIZES = (3, 7, 15, 31)
 

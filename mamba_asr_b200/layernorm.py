@@ -158,3 +158,30 @@ def add_dropout_layer_norm(a, b, norm, alpha=1.0, p_drop=0.0, training=True):
     bb = norm.bias if norm.bias is None or norm.bias.dtype == torch.float32 else norm.bias.float()
     with torch.autocast("cuda", enabled=False):
         return _AddDropoutLayerNormFn.apply(a, b, w, bb, norm.eps, float(alpha), p, out_dtype)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GELU + dropout in one pass (cm_gelu_dropout_fwd / cm_gelu_dropout_bwd)
+class _GeluDropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p_drop):
+        seed = DropoutSeed.tensor(x.device) if p_drop > 0.0 else None
+        y, mask = K.gelu_dropout_forward(x, p_drop, seed, DropoutSeed.next_call_id())
+        ctx.save_for_backward(x, mask)
+        ctx.p_drop = p_drop
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mask = ctx.saved_tensors
+        return K.gelu_dropout_backward(x, dy, mask, ctx.p_drop), None
+
+
+def gelu_dropout(x, p_drop=0.0, training=True):
+    """dropout(gelu(x)) (exact erf GELU, as ``nn.GELU()``) - one sm_100a kernel forward and one backward on CUDA tensors
+    the kernel supports, the two torch ops otherwise."""
+    p = float(p_drop) if training else 0.0
+    if not K.gelu_dropout_supported(x):
+        y = torch.nn.functional.gelu(x)
+        return torch.nn.functional.dropout(y, p, training=True) if p > 0 else y
+    return _GeluDropoutFn.apply(x, p)

@@ -121,3 +121,31 @@ def test_encoder_layer_fused_path_equals_unfused_ops():
         assert_close(outs[0], outs[1], dt, what="layer out (autocast=%s)" % autocast)
         for g0, g1 in zip(grads[0], grads[1]):
             assert_close(g0, g1, dt, floor="max", what="layer grads (autocast=%s)" % autocast, rtol_mul=2.0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(3, 37, 1024), (2, 5, 8), (1, 501, 576)])
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_gelu_dropout_matches_torch(dtype, shape, p):
+    from mamba_asr_b200 import kernels as K
+    from mamba_asr_b200.layernorm import DropoutSeed, gelu_dropout
+    g = torch.Generator().manual_seed(5)
+    x = (2.0 * torch.randn(*shape, generator=g)).to(dtype)
+    cot = torch.randn(*shape, generator=g).to(dtype)
+    xg = x.cuda().requires_grad_(True)
+    y = gelu_dropout(xg, p, training=True)
+    assert y.dtype == dtype
+    y.backward(cot.cuda())
+    xr = x.float().clone().requires_grad_(True)
+    yr = F.gelu(xr)
+    if p > 0:
+        keep = (y != 0) | (yr.detach().cuda() == 0)          # the mask, read off the output
+        frac = float(keep.float().mean())
+        if x.numel() > 10000:
+            assert abs(frac - (1 - p)) < 0.01, frac
+        yr = yr * keep.cpu().float() / (1 - p)
+    (yr * cot.float()).sum().backward()
+    assert_close(y.float(), yr, dtype, what="gelu_dropout out")
+    assert_close(xg.grad.float(), xr.grad, dtype, floor="max", what="gelu_dropout dx")
+    # eval mode: no dropout
+    assert_close(gelu_dropout(x.cuda(), 0.5, training=False).float(), F.gelu(x.float()), dtype, what="eval")

@@ -78,7 +78,11 @@ class ConvFrontEnd(nn.Module):
         # channels-last memory throughout: the (B, T', F', C) view the LayerNorm wants is then the conv output's own
         # memory order, and cuDNN's bf16 kernels take NHWC directly (as NCHW the two blocks cost four nchwToNhwc kernels
         # and five permute copies per step - 3 ms of the 61 ms ConMamba-large step on B200)
-        x = feats.unsqueeze(1).contiguous(memory_format=torch.channels_last)    # (B, 1, T, F)
+        feats = feats.contiguous()
+        Bt, T, Fd = feats.shape
+        # (B, 1, T, F) with explicit NHWC strides: with one channel the default strides are ambiguous and torch resolves
+        # the ambiguity to NCHW, which makes cuDNN convert the 64-channel output back and forth
+        x = feats.as_strided((Bt, 1, T, Fd), (T * Fd, 1, Fd, 1))
         for conv, norm in zip(self.convs, self.norms):
             x = F.conv2d(x, conv.weight.contiguous(memory_format=torch.channels_last), conv.bias, conv.stride,
                          conv.padding)                             # (B, C, T', F'), NHWC memory

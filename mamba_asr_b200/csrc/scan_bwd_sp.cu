@@ -130,9 +130,13 @@ struct TileSeq {
 };
 
 // ---- recurrence warps ------------------------------------------------------------------------------------------------
-template <int DIR>
-__device__ __forceinline__ void scan_role(const BwdParams& P, BwdSmem& S, const int gt) {
-  const BwdDir& d = P.dir[DIR];
+#ifndef CM_BWDSP_RTDIR
+#define CM_BWDSP_RTDIR 1
+#endif
+// The direction is a run-time value here (the role touches five fields of BwdDir, all before the time loop): as a template
+// parameter the kernel carried two copies of the 8-step-unrolled recompute + reverse sweep.
+__device__ __forceinline__ void scan_role(const BwdParams& P, BwdSmem& S, const int gt, const int dir) {
+  const BwdDir& d = P.dir[dir];
   const int warp = gt >> 5, lane = gt & 31;
   const int b = blockIdx.y;
   const int c_base = blockIdx.x * kCH;
@@ -307,8 +311,13 @@ __device__ __forceinline__ void scan_role(const BwdParams& P, BwdSmem& S, const 
 }
 
 // ---- IO warps ----------------------------------------------------------------------------------------------------------
-template <typename T, int DIR>
-__device__ __forceinline__ void io_role(const BwdParams& P, BwdSmem& S, const int io) {
+// The IO role reads its BwdDir fields inside the loops (constant-bank operands); with a run-time direction they move to
+// registers / indexed constant loads and the kernel is 3 % slower (measured), so this role stays templated in effect.
+#ifndef CM_BWDSP_RTDIR_IO
+#define CM_BWDSP_RTDIR_IO 0
+#endif
+template <typename T>
+__device__ __forceinline__ void io_role(const BwdParams& P, BwdSmem& S, const int io, const int DIR) {
   using P2 = Pair<T>;
   using Q4 = Quad<T>;
   constexpr int ES = (int)sizeof(T);
@@ -479,10 +488,18 @@ __global__ void __launch_bounds__(kGT + kIO, CM_BWDSP_MINB) scan_bwd_sp_kernel(c
     }
   }
   __syncthreads();
-  if (blockIdx.z == 0) {
-    if (tid < kGT) scan_role<0>(P, S, tid); else io_role<T, 0>(P, S, tid - kGT);
+  if (tid < kGT) {
+#if CM_BWDSP_RTDIR
+    scan_role(P, S, tid, blockIdx.z);
+#else
+    if (blockIdx.z == 0) scan_role(P, S, tid, 0); else scan_role(P, S, tid, 1);
+#endif
   } else {
-    if (tid < kGT) scan_role<1>(P, S, tid); else io_role<T, 1>(P, S, tid - kGT);
+#if CM_BWDSP_RTDIR_IO
+    io_role<T>(P, S, tid - kGT, blockIdx.z);
+#else
+    if (blockIdx.z == 0) io_role<T>(P, S, tid - kGT, 0); else io_role<T>(P, S, tid - kGT, 1);
+#endif
   }
 }
 

@@ -155,8 +155,13 @@ __device__ __forceinline__ int64_t ws_row(const FwdParams& P, int b, int dir, in
 }
 
 // ---- recurrence warps (2 per direction): lane = states 4m..4m+3 of channel pair pr -------------------------------
-template <typename T, int NDIR, int DIR>
-__device__ __forceinline__ void scan_role(const FwdParams& P, FwdSmem& S, const int gt) {
+#ifndef CM_FWDSP_RTDIR
+#define CM_FWDSP_RTDIR 1
+#endif
+// The direction is a run-time value for this role (it reads a handful of FwdDir fields, all before the time loop): as a
+// template parameter a bidirectional CTA kept two copies of the unrolled 16-step recurrence live in the instruction cache.
+template <typename T, int NDIR>
+__device__ __forceinline__ void scan_role(const FwdParams& P, FwdSmem& S, const int gt, const int DIR) {
   const FwdDir& d = P.dir[DIR];
   const int warp = gt >> 5, lane = gt & 31;
   const int b = blockIdx.y;
@@ -294,8 +299,11 @@ __device__ __forceinline__ void scan_role(const FwdParams& P, FwdSmem& S, const 
 }
 
 // ---- IO warps (2 per direction): thread = channel pair cp at steps k0 + 4i of every tile ----------------------------
-template <typename T, int NDIR, int DIR>
-__device__ __forceinline__ void io_role(const FwdParams& P, FwdSmem& S, const int io) {
+#ifndef CM_FWDSP_RTDIR_IO
+#define CM_FWDSP_RTDIR_IO 0
+#endif
+template <typename T, int NDIR>
+__device__ __forceinline__ void io_role(const FwdParams& P, FwdSmem& S, const int io, const int DIR) {
   using P2 = Pair<T>;
   using Q4 = Quad<T>;
   constexpr int ES = (int)sizeof(T);
@@ -472,12 +480,22 @@ __global__ void __launch_bounds__(NDIR*(kGT + kIO), CM_FWDSP_MINB) scan_fwd_sp_k
   __syncthreads();
   // thread layout: [recurrence dir 0 | recurrence dir 1 | IO dir 0 | IO dir 1]
   if (tid < NDIR * kGT) {
-    if (NDIR == 1 || tid < kGT) scan_role<T, NDIR, 0>(P, S[0], tid);
-    else scan_role<T, NDIR, 1>(P, S[1], tid - kGT);
+#if CM_FWDSP_RTDIR
+    const int dir = (NDIR == 2 && tid >= kGT) ? 1 : 0;
+    scan_role<T, NDIR>(P, S[dir], tid - dir * kGT, dir);
+#else
+    if (NDIR == 1 || tid < kGT) scan_role<T, NDIR>(P, S[0], tid, 0);
+    else scan_role<T, NDIR>(P, S[1], tid - kGT, 1);
+#endif
   } else {
     const int io = tid - NDIR * kGT;
-    if (NDIR == 1 || io < kIO) io_role<T, NDIR, 0>(P, S[0], io);
-    else io_role<T, NDIR, 1>(P, S[1], io - kIO);
+#if CM_FWDSP_RTDIR_IO
+    const int dir = (NDIR == 2 && io >= kIO) ? 1 : 0;
+    io_role<T, NDIR>(P, S[dir], io - dir * kIO, dir);
+#else
+    if (NDIR == 1 || io < kIO) io_role<T, NDIR>(P, S[0], io, 0);
+    else io_role<T, NDIR>(P, S[1], io - kIO, 1);
+#endif
   }
 }
 

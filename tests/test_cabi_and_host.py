@@ -168,3 +168,72 @@ def test_product_length_and_mask_integers_are_bit_exact_with_the_oracle():
         assert torch.equal(a, b) and np.array_equal(a.numpy(), O.abs_lengths_numpy(wl.numpy(), L))
         assert torch.equal(P.key_padding_mask(wl, L), O.key_padding_mask(wl, L))
     assert float(P.abs_lengths(torch.tensor([0.5]), 501)) == 250.0      # half-to-even
+
+
+def test_kldiv_loss_matches_a_hand_computed_label_smoothed_kl():
+    """The S2S recipe's sequence loss (hparams/S2S/conmambamamba_large.yaml:414-415): KL to the label-smoothed target
+    distribution, padding masked, sum / batch."""
+    import math
+    import torch
+    from mamba_asr_b200.encoder import kldiv_loss
+    torch.manual_seed(0)
+    Bt, S, V, eps = 2, 3, 7, 0.1
+    logp = torch.log_softmax(torch.randn(Bt, S, V), dim=-1)
+    tgt = torch.tensor([[3, 5, 0], [1, 0, 0]])
+    total = 0.0
+    for b in range(Bt):
+        for s_ in range(S):
+            t = int(tgt[b, s_])
+            if t == 0:
+                continue
+            for v in range(V):
+                q = 1 - eps if v == t else eps / (V - 1)
+                total += q * (math.log(q) - float(logp[b, s_, v]))
+    assert abs(float(kldiv_loss(logp, tgt, label_smoothing=eps)) - total / Bt) < 1e-5
+
+
+def test_s2s_model_runs_on_the_cpu_reference_path_and_backpropagates():
+    """ConMambaS2S (encoder + Mamba decoder) swapped onto the CPU oracle mixers: shapes, finite loss, a gradient on every
+    parameter - the path bench.py --impl reference times for the S2S workload."""
+    import torch
+    from mamba_asr_b200.encoder import CONFIGS, build_model, kldiv_loss
+    from oracle.cpu_encoder import to_cpu_reference
+    cfg = CONFIGS["conmambamamba_large_s2s"]
+    m = build_model("conmambamamba_large_s2s", d_model=32, d_ffn=64, num_layers=1, num_decoder_layers=1,
+                    output_neurons=20, dropout=0.0)
+    m = to_cpu_reference(m, cfg["n_fft"], cfg["n_mels"], cfg["win_length"])
+    wav = 0.1 * torch.randn(2, 6400)
+    bos = torch.tensor([[1, 4, 5, 6], [1, 7, 8, 9]])
+    p_ctc, p_seq = m(wav, bos)
+    assert p_ctc.shape == (2, 11, 20) and p_seq.shape == (2, 4, 20)
+    loss = kldiv_loss(p_seq, torch.tensor([[4, 5, 6, 2], [7, 8, 9, 2]])) + p_ctc[..., 0].mean()
+    loss.backward()
+    assert torch.isfinite(loss)
+    missing = [n for n, p in m.named_parameters() if p.requires_grad and p.grad is None]
+    assert not missing, missing
+
+
+def test_decode_api_mirrors_the_reference_and_refuses_cpu():
+    """step / allocate_inference_cache / _get_states_from_cache exist with the reference's signatures
+    (modules/mamba/bimamba.py:320, 367, 381) and the product path has no CPU fallback for them."""
+    import inspect
+    import pytest
+    import torch
+    from mamba_asr_b200 import Mamba, UniMamba
+    for cls in (Mamba, UniMamba):
+        assert list(inspect.signature(cls.step).parameters)[1:] == ["hidden_states", "conv_state", "ssm_state"]
+        assert list(inspect.signature(cls.allocate_inference_cache).parameters)[1:4] == ["batch_size", "max_seqlen", "dtype"]
+    m = UniMamba(d_model=16, layer_idx=2)
+    cs, ss = m.allocate_inference_cache(3, 0)
+    assert cs.shape == (3, 32, 4) and ss.shape == (3, 32, 16) and cs.dtype == torch.float32
+
+    class IP:
+        seqlen_offset = 0
+        key_value_memory_dict = {}
+    ip = IP()
+    a, b = m._get_states_from_cache(ip, 3)
+    assert ip.key_value_memory_dict[2][0] is a and a.shape == cs.shape
+    with pytest.raises(RuntimeError):
+        m.step(torch.zeros(3, 1, 16), cs, ss)
+    with pytest.raises(AssertionError):
+        UniMamba(d_model=16)._get_states_from_cache(IP(), 1)       # layer_idx is required, as in the reference

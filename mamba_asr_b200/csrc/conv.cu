@@ -19,8 +19,14 @@
 
 namespace cm {
 
-constexpr int kTL = 16;        // time steps per thread (channel-last kernels)
-constexpr int kTY = 4;         // threadIdx.y: time chunks per CTA  -> 64 steps per CTA
+#ifndef CM_CONV_TL
+#define CM_CONV_TL 16
+#endif
+#ifndef CM_CONV_TY
+#define CM_CONV_TY 4
+#endif
+constexpr int kTL = CM_CONV_TL;   // time steps per thread (channel-last kernels)
+constexpr int kTY = CM_CONV_TY;   // threadIdx.y: time chunks per CTA  -> kTL * kTY = 64 steps per CTA
 constexpr int kChunk = kTL * kTY;
 
 template <int BYTES> struct RawVec;

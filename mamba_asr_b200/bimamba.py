@@ -25,6 +25,16 @@ from .mamba_inner import MambaInnerCL, inner_forward
 from .selective_state_update import selective_state_update
 
 
+def _inner(xz, ndir, scale, params):
+    """The fused conv + scan block: through autograd when a gradient can be asked for, else the inference launch - no
+    state checkpoints, no saved pre-gate sums, and the chunk-parallel scan over time windows for few long sequences.
+    (Inside ``Function.forward`` grad mode is always off and ``needs_input_grad`` is true for parameters even under
+    ``torch.no_grad()``, so the distinction has to be made here.)"""
+    if torch.is_grad_enabled():
+        return MambaInnerCL.apply(xz, ndir, scale, False, *params)
+    return inner_forward(xz, ndir, scale, False, params, need_grad=False)[0]
+
+
 def _s4d_real_log(d_inner, d_state, device):
     # reference bimamba.py:123-129: A = repeat(arange(1, N+1), "n -> d n"); A_log = log(A), kept in fp32
     a = torch.arange(1, d_state + 1, dtype=torch.float32, device=device)
@@ -178,7 +188,7 @@ class Mamba(_MambaBase):
             return self._cached(hidden_states, inference_params)
         xz = linear(hidden_states, self.in_proj.weight, self.in_proj.bias)                # (B, L, 2D), time-major
         scale = 0.5 if self.if_devide_out else 1.0                                        # bimamba.py:250-253
-        y = MambaInnerCL.apply(xz, 2, scale, False, *self._dir_params(""), *self._dir_params("_b"))
+        y = _inner(xz, 2, scale, (*self._dir_params(""), *self._dir_params("_b")))
         out = linear(y, self.out_proj.weight, self.out_proj.bias)
         if self.init_layer_scale is not None:
             out = out * self.gamma
@@ -202,7 +212,7 @@ class UniMamba(_MambaBase):
         if inference_params is not None:
             return self._cached(hidden_states, inference_params)
         xz = linear(hidden_states, self.in_proj.weight, self.in_proj.bias)
-        y = MambaInnerCL.apply(xz, 1, 1.0, False, *self._dir_params(""))
+        y = _inner(xz, 1, 1.0, self._dir_params(""))
         if keep_last is not None:
             y = y[:, -keep_last:]
         return linear(y, self.out_proj.weight, self.out_proj.bias)

@@ -147,6 +147,16 @@ def main():
             best, med = timek(lambda: K.add_ln_backward(sv, dyv, dsv, w, mean, rstd, mask, 0.5, 0.1, dt), "cm_add_ln_bwd", args.iters, flush)
             byts = rows * d_model * (4 + s + 4 + 1 + 4 + s)
             print("%-40s add_ln_bwd      best %.4f ms  alg %.1f GB/s (%.1f%%)" % (tag, best, byts / best / 1e6, 100 * byts / best / 1e6 / peak))
+            # single-token decoding at the decoder width of this config (state (B, D, 16) fp32)
+            st_ = rn(Bt, D, N)
+            xs1, dts1, zs1 = rn(Bt, D).to(dt), rn(Bt, D).to(dt), rn(Bt, D).to(dt)
+            Bs1, Cs1 = rn(Bt, N).to(dt), rn(Bt, N).to(dt)
+            As1 = -torch.exp(0.3 * rn(D, N))
+            Ds1, bs1 = torch.ones(D, device=dev), torch.full((D,), -4.0, device=dev)
+            best, med = timek(lambda: K.ssm_step(st_, xs1, dts1, As1, Bs1, Cs1, Ds1, z=zs1, dt_bias=bs1, dt_softplus=True),
+                              "cm_ssm_step", args.iters, flush)
+            byts = 2 * Bt * D * N * 4
+            print("%-40s ssm_step (B=%d, D=%d) best %.4f ms  alg %.1f GB/s (%.1f%%)" % (tag, Bt, D, best, byts / best / 1e6, 100 * byts / best / 1e6 / peak))
             xc = rn(Bt, L, d_model).to(dt)
             wc, bc_ = rn(d_model, 31), rn(d_model)
             best, med = timek(lambda: K.dwconv_forward(xc, wc, bc_, 15), "cm_dwconv_fwd", args.iters, flush)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CM_ABI_VERSION 5
+#define CM_ABI_VERSION 6
 
 /* element type of activations (u, delta, z, B, C, x, out, and their gradients) */
 enum { CM_F32 = 0, CM_BF16 = 1, CM_F16 = 2 };
@@ -320,6 +320,18 @@ int cm_gelu_dropout_fwd(const void* x, void* y, uint8_t* mask, int64_t n, int32_
                         const int64_t* seed, uint32_t call_id, void* stream);
 int cm_gelu_dropout_bwd(const void* x, const void* dy, const uint8_t* mask, void* dx, int64_t n, int32_t dtype,
                         float p_drop, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Tall-skinny weight-gradient GEMM  C[M, N] = sum_r A[r, m] * B[r, n]  (A^T B): the gradients of the Mamba block's skinny
+ * projections, d dt_proj.weight = ddelta^T x_dbl[:, :R] and d x_proj.weight = dx_dbl^T conv1d_out (reference
+ * modules/mamba/selective_scan_interface.py:277-283), whose reduction dimension is batch * L.
+ * A (rows, M) and B (rows, N) are 16-bit row-major with leading dimensions lda, ldb (elements, multiples of 8; 16-byte
+ * aligned bases); M a multiple of 8, N a multiple of 8 and <= 64.  Writes cm_tsmm_num_part(rows, M) partial blocks
+ * part[chunk][M][N] (fp32); sum them with cm_reduce_multi (rows = chunks, cols = M * N).
+ * ---------------------------------------------------------------------------------------------------- */
+int cm_tsmm_num_part(int64_t rows, int32_t M);
+int cm_tsmm(const void* A, int64_t lda, const void* B, int64_t ldb, float* part, int64_t rows, int32_t M, int32_t N,
+            int32_t dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Depthwise conv1d over time (the kernel_size = 31 convolution of the ConMamba

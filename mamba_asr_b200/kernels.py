@@ -639,6 +639,36 @@ def gelu_dropout_backward(x, dy, mask, p_drop):
     return dx
 
 
+# ------------------------------------------------------------------------------------------------ tall-skinny A^T B
+def tsmm_supported(a2d, b2d):
+    """cm_tsmm computes a2d^T @ b2d for 16-bit row-major operands with b2d at most 64 columns wide."""
+    if not (a2d.is_cuda and a2d.dtype in (torch.bfloat16, torch.float16) and b2d.dtype == a2d.dtype):
+        return False
+    if a2d.dim() != 2 or b2d.dim() != 2 or a2d.shape[0] != b2d.shape[0] or a2d.shape[0] == 0:
+        return False
+    M, N = a2d.shape[1], b2d.shape[1]
+    if N > 64 or N % 8 or M % 8 or a2d.stride(1) != 1 or b2d.stride(1) != 1:
+        return False
+    return a2d.stride(0) % 8 == 0 and b2d.stride(0) % 8 == 0 and a2d.data_ptr() % 16 == 0 and b2d.data_ptr() % 16 == 0
+
+
+def tsmm(a2d, b2d):
+    """a2d^T @ b2d -> (M, N) fp32 through cm_tsmm (tensor-core partial blocks per 256-row chunk) and the deterministic
+    reducer.  a2d (rows, M), b2d (rows, N <= 64), 16-bit, unit column stride."""
+    lib = cabi.lib()
+    rows, M = a2d.shape
+    N = b2d.shape[1]
+    n_part = lib.cm_tsmm_num_part(rows, M)
+    part = torch.empty((n_part, M * N), dtype=torch.float32, device=a2d.device)
+    _call("cm_tsmm", lib.cm_tsmm, a2d.data_ptr(), a2d.stride(0), b2d.data_ptr(), b2d.stride(0), part.data_ptr(), rows, M, N,
+          cabi.dtype_code(a2d.dtype), cabi.stream_ptr())
+    if n_part == 1:
+        return part.view(M, N)
+    out = torch.empty((M * N,), dtype=torch.float32, device=a2d.device)
+    reduce_many([(part, out)])
+    return out.view(M, N)
+
+
 # ------------------------------------------------------------------------------------------------ depthwise conv1d
 DWCONV_KSIZES = (3, 7, 15, 31)
 

@@ -15,6 +15,8 @@ a flip in between (modules/mamba/bimamba.py:223-253), but
 
 The dense projections are torch.matmul (cuBLAS tensor cores); everything else is the hand-written kernels.
 """
+import os
+
 import torch
 
 from . import kernels as K
@@ -42,10 +44,19 @@ def _as_bdl(t_bld):
     return t_bld.transpose(1, 2)
 
 
+_USE_TSMM = os.environ.get("CM_TSMM") is not None     # opt-in until the re-tuned kernel is verified on the GPU
+
+
 def _wgrad(a, b, nsplit):
-    """a^T @ b for tall-skinny operands (a: (K, M), b: (K, N), K = batch * L in the tens of thousands, M or N <= 64):
-    one bmm over `nsplit` row blocks plus a sum.  As a single GEMM cuBLAS picks a serial-K sm_75 CUTLASS kernel for these
-    shapes on B200 (85 us per call at K = 32064, measured); split over the batch it is a 64-way parallel reduction."""
+    """a^T @ b for tall-skinny operands (a: (K, M), b: (K, N), K = batch * L in the tens of thousands, M or N <= 64), fp32.
+    16-bit operands go to the sm_100a kernel cm_tsmm (tensor-core partial blocks per row chunk + the deterministic
+    reducer); otherwise one bmm over `nsplit` row blocks plus a sum (as a single GEMM cuBLAS picks a serial-K sm_75 CUTLASS
+    kernel for these shapes on B200: 85 us per call at K = 32064, measured)."""
+    if _USE_TSMM and os.environ.get("CM_NO_TSMM") is None:
+        if K.tsmm_supported(a, b):
+            return K.tsmm(a, b)
+        if K.tsmm_supported(b, a):
+            return K.tsmm(b, a).t()
     Kr = a.shape[0]
     od = {} if a.dtype == torch.float32 else {"out_dtype": torch.float32}   # fp32 straight out of the GEMM
     if nsplit <= 1 or Kr % nsplit != 0:

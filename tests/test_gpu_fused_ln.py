@@ -149,3 +149,44 @@ def test_gelu_dropout_matches_torch(dtype, shape, p):
     assert_close(xg.grad.float(), xr.grad, dtype, floor="max", what="gelu_dropout dx")
     # eval mode: no dropout
     assert_close(gelu_dropout(x.cuda(), 0.5, training=False).float(), F.gelu(x.float()), dtype, what="eval")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(12032, 288, 16), (32064, 512, 48), (501, 64, 8), (1, 8, 8), (1000, 1024, 64),
+                                   (257, 72, 40), (256, 96, 24)])
+def test_tall_skinny_weight_gradient_gemm_matches_fp32_reference(dtype, shape):
+    """cm_tsmm (A^T B over batch * L rows; the x_proj / dt_proj weight gradients of
+    selective_scan_interface.py:277-283) against an fp64 product of the same 16-bit inputs; strided B as in the module."""
+    from mamba_asr_b200 import kernels as K
+    rows, M, N = shape
+    g = torch.Generator().manual_seed(rows + M + N)
+    a = torch.randn(rows, M, generator=g).to(dtype).cuda()
+    wide = torch.randn(rows, N + 32, generator=g).to(dtype).cuda()
+    b = wide[:, 32:]                                              # leading dimension N + 32, base offset 64 bytes
+    assert K.tsmm_supported(a, b)
+    out = K.tsmm(a, b)
+    ref = (a.double().t() @ b.double()).float()
+    assert out.shape == (M, N) and out.dtype == torch.float32
+    assert_close(out, ref, torch.float32, floor="max", what="tsmm", rtol_mul=2.0)
+    out2 = K.tsmm(a, b)
+    assert torch.equal(out, out2)                                  # deterministic
+
+
+def test_mamba_weight_gradients_same_with_and_without_tsmm(monkeypatch):
+    from mamba_asr_b200 import Mamba
+    from mamba_asr_b200 import mamba_inner
+    monkeypatch.setattr(mamba_inner, "_USE_TSMM", True)
+    torch.manual_seed(1)
+    m = Mamba(d_model=64, bimamba_type="v2").cuda()
+    x = torch.randn(3, 70, 64, device="cuda")
+    grads = []
+    for off in (False, True):
+        if off:
+            monkeypatch.setenv("CM_NO_TSMM", "1")
+        m.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = m(x)
+        y.float().square().mean().backward()
+        grads.append({n: p.grad.clone() for n, p in m.named_parameters()})
+    for n in grads[0]:
+        assert_close(grads[0][n], grads[1][n], torch.bfloat16, floor="max", what="d " + n)

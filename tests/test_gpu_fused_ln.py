@@ -176,6 +176,7 @@ def test_mamba_weight_gradients_same_with_and_without_tsmm(monkeypatch):
     from mamba_asr_b200 import Mamba
     from mamba_asr_b200 import mamba_inner
     monkeypatch.setattr(mamba_inner, "_USE_TSMM", True)
+    monkeypatch.setattr(mamba_inner, "_TSMM_MAX_ELEMS", 1 << 40)
     torch.manual_seed(1)
     m = Mamba(d_model=64, bimamba_type="v2").cuda()
     x = torch.randn(3, 70, 64, device="cuda")

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CM_ABI_VERSION 6
+#define CM_ABI_VERSION 7
 
 /* element type of activations (u, delta, z, B, C, x, out, and their gradients) */
 enum { CM_F32 = 0, CM_BF16 = 1, CM_F16 = 2 };
@@ -370,11 +370,42 @@ int cm_dwconv_bwd_weight(const cm_dwconv_args* args, void* stream);
 int cm_colsum_num_part(int64_t rows);
 int cm_colsum(const void* x, int64_t rows, int32_t cols, int64_t row_stride, int32_t dtype, float* part, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Wide-row LayerNorm + LeakyReLU in one pass (the two conv blocks of the reference's
+ * ConvolutionFrontEnd, hparams/CTC/conmamba_large.yaml:187-199 - conv 3x3 stride 2 -> LayerNorm([F', C]) -> LeakyReLU;
+ * rows of F'*C = 2560 and 640 elements at the BASELINE shapes).
+ *   forward : y = leaky_relu((x - mean) * rstd * gamma + beta, slope)     statistics in fp32; slope = 1: plain LayerNorm
+ *   backward: dx, and cm_ln_act_num_part(rows, cols) partial rows of dgamma / dbeta ([n_part][cols] fp32, summed with
+ *             cm_reduce_multi); the pre-activation sign is recomputed from x, mean, rstd.
+ * x, y, dy, dx are dense (rows, cols) matrices of one dtype; cols a multiple of 4, <= 2560; 16-byte aligned bases.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t rows;
+  int32_t cols;
+  int32_t dtype;
+  float eps;
+  float slope;              /* LeakyReLU negative slope (torch default 0.01) */
+  const void* x;
+  void* y;                  /* forward output */
+  const float* gamma;       /* (cols) fp32 */
+  const float* beta;        /* (cols) fp32 */
+  float* mean;              /* (rows) fp32: written by forward, read by backward */
+  float* rstd;              /* (rows) fp32 */
+  const void* dy;           /* backward: grad of y */
+  void* dx;                 /* backward: grad of x */
+  float* dgamma_part;
+  float* dbeta_part;
+} cm_ln_act_args;
+
+int cm_ln_act_num_part(int64_t rows, int32_t cols);
+int cm_ln_act_fwd(const cm_ln_act_args* args, void* stream);
+int cm_ln_act_bwd(const cm_ln_act_args* args, void* stream);
+
 /* library identification: returns CM_ABI_VERSION; writes the compiled-for arch (e.g. 100) to *sm_arch if non-NULL */
 int cm_version(int32_t* sm_arch);
 /* sizeof() of the argument structs, for binding self-checks: 0 cm_tensor3, 1 cm_scan_dir, 2 cm_scan_fwd_args,
  * 3 cm_scan_bwd_dir, 4 cm_scan_bwd_args, 5 cm_conv_dir, 6 cm_conv_args, 7 cm_fbank_args, 8 cm_reduce_job,
- * 9 cm_layernorm_args, 10 cm_dwconv_args, 11 cm_ssm_step_args, 12 cm_add_ln_args */
+ * 9 cm_layernorm_args, 10 cm_dwconv_args, 11 cm_ssm_step_args, 12 cm_add_ln_args, 13 cm_ln_act_args */
 int cm_abi_sizeof(int32_t which);
 
 #ifdef __cplusplus

@@ -17,7 +17,7 @@ CM_ERR_BAD_ARG, CM_ERR_UNSUPPORTED = -1, -2
 CM_FLAG_DELTA_SOFTPLUS = 1
 CM_FLAG_SILU = 1
 CM_SCAN_CKPT_STEPS = 8
-CM_ABI_VERSION = 6
+CM_ABI_VERSION = 7
 
 EXPORTS = (
     "cm_version", "cm_scan_num_ckpt", "cm_scan_slab_channels", "cm_scan_pick_lanes", "cm_scan_pick_lanes_bwd", "cm_scan_fwd",
@@ -26,6 +26,7 @@ EXPORTS = (
     "cm_fbank_logmel", "cm_fbank_floor", "cm_abi_sizeof", "cm_reduce_multi", "cm_layernorm_num_part", "cm_layernorm_fwd",
     "cm_layernorm_bwd", "cm_scan_fwd_workspace_bytes", "cm_dwconv_num_part", "cm_dwconv_fwd", "cm_dwconv_bwd_weight", "cm_colsum_num_part", "cm_colsum",
     "cm_ssm_step", "cm_add_ln_fwd", "cm_add_ln_bwd", "cm_gelu_dropout_fwd", "cm_gelu_dropout_bwd", "cm_tsmm_num_part", "cm_tsmm",
+    "cm_ln_act_num_part", "cm_ln_act_fwd", "cm_ln_act_bwd",
 )
 CM_REDUCE_MAX_JOBS = 8
 
@@ -150,8 +151,15 @@ class AddLnArgs(C.Structure):
                 ("dgamma_part", C.c_void_p), ("dbeta_part", C.c_void_p)]
 
 
+class LnActArgs(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("cols", C.c_int32), ("dtype", C.c_int32), ("eps", C.c_float), ("slope", C.c_float),
+                ("x", C.c_void_p), ("y", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("mean", C.c_void_p),
+                ("rstd", C.c_void_p), ("dy", C.c_void_p), ("dx", C.c_void_p), ("dgamma_part", C.c_void_p),
+                ("dbeta_part", C.c_void_p)]
+
+
 ABI_STRUCTS = (Tensor3, ScanDir, ScanFwdArgs, ScanBwdDir, ScanBwdArgs, ConvDir, ConvArgs, FbankArgs, ReduceJob,
-               LayerNormArgs, DwConvArgs, SsmStepArgs, AddLnArgs)
+               LayerNormArgs, DwConvArgs, SsmStepArgs, AddLnArgs, LnActArgs)
 
 def lib():
     """The loaded shared library; raises (never falls back) when it is absent or stale."""
@@ -203,6 +211,9 @@ def lib():
         L.cm_tsmm_num_part.argtypes = [C.c_int64, C.c_int32]
         L.cm_tsmm.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                               C.c_void_p]
+        L.cm_ln_act_num_part.argtypes = [C.c_int64, C.c_int32]
+        L.cm_ln_act_fwd.argtypes = [C.POINTER(LnActArgs), C.c_void_p]
+        L.cm_ln_act_bwd.argtypes = [C.POINTER(LnActArgs), C.c_void_p]
         if L.cm_version(None) != CM_ABI_VERSION:
             raise RuntimeError("mamba_asr_b200: %s has a different ABI version; rebuild it" % LIB_PATH)
         for i, st in enumerate(ABI_STRUCTS):

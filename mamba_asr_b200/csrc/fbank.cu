@@ -152,6 +152,7 @@ extern "C" int cm_abi_sizeof(int32_t which) {
     case 10: return (int)sizeof(cm_dwconv_args);
     case 11: return (int)sizeof(cm_ssm_step_args);
     case 12: return (int)sizeof(cm_add_ln_args);
+    case 13: return (int)sizeof(cm_ln_act_args);
     default: return CM_ERR_BAD_ARG;
   }
 }

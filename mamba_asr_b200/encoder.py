@@ -18,7 +18,9 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 import math
+import os
 
+from .layernorm import layer_norm_leaky_relu
 from .linear import BiasGradLinear, ParamCache, set_param_cache
 from .conmamba import ConmambaEncoder, MambaDecoder
 from .fbank import Fbank
@@ -73,6 +75,9 @@ class ConvFrontEnd(nn.Module):
             self.norms.append(nn.LayerNorm([f, c_out]))
             c_in = c_out
         self.out_features = f * c_in
+        # LayerNorm([F', C]) + LeakyReLU of each block on the fused sm_100a kernel (cm_ln_act_*); the CPU reference arm
+        # (oracle/cpu_encoder.py) clears the flag and gets the two torch ops
+        self.use_kernel = True
 
     def forward(self, feats):
         # channels-last memory throughout: the (B, T', F', C) view the LayerNorm wants is then the conv output's own
@@ -86,7 +91,11 @@ class ConvFrontEnd(nn.Module):
         for conv, norm in zip(self.convs, self.norms):
             x = F.conv2d(x, conv.weight.contiguous(memory_format=torch.channels_last), conv.bias, conv.stride,
                          conv.padding)                             # (B, C, T', F'), NHWC memory
-            x = F.leaky_relu(norm(x.permute(0, 2, 3, 1)))          # (B, T', F', C)
+            x = x.permute(0, 2, 3, 1)                              # (B, T', F', C), contiguous
+            if self.use_kernel and os.environ.get("CM_NO_FUSE_FRONTEND_LN") is None:
+                x = layer_norm_leaky_relu(x, norm)
+            else:
+                x = F.leaky_relu(norm(x))
             x = x.permute(0, 3, 1, 2)
         x = x.permute(0, 2, 3, 1)                                  # (B, L, F'', C)
         return x.reshape(x.shape[0], x.shape[1], -1)               # (B, L, 640)  (TransformerASR.py:760-762)

@@ -521,6 +521,66 @@ def layernorm_backward(x2d, dy2d, weight, mean, rstd, need_wgrad=True):
     return dx, dg, db
 
 
+# ------------------------------------------------------------------------------------------------ wide LayerNorm + LeakyReLU
+LN_ACT_MAX_COLS = 2560
+
+
+def ln_act_supported(x2d):
+    """cm_ln_act_* envelope: dense (rows, C) CUDA matrix, C a multiple of 4 and <= 2560, 16-byte aligned."""
+    return (x2d.is_cuda and x2d.dim() == 2 and x2d.is_contiguous() and x2d.dtype in cabi._DTYPES
+            and x2d.shape[1] % 4 == 0 and 0 < x2d.shape[1] <= LN_ACT_MAX_COLS and x2d.shape[0] > 0
+            and x2d.data_ptr() % 16 == 0)
+
+
+def _ln_act_args(x2d, weight, bias, eps, slope, mean, rstd):
+    a = cabi.LnActArgs()
+    a.rows, a.cols = x2d.shape
+    a.dtype = cabi.dtype_code(x2d.dtype)
+    a.eps, a.slope = float(eps), float(slope)
+    a.x = x2d.data_ptr()
+    a.gamma, a.beta = _f32c(weight, "weight").data_ptr(), _f32c(bias, "bias").data_ptr()
+    a.mean, a.rstd = mean.data_ptr(), rstd.data_ptr()
+    return a
+
+
+def ln_act_forward(x2d, weight, bias, eps, slope):
+    """cm_ln_act_fwd: y = leaky_relu(layer_norm(x), slope) over the rows of a dense (rows, C) matrix, y in x's dtype.
+    Returns (y, mean (rows,) fp32, rstd (rows,) fp32)."""
+    lib = cabi.lib()
+    _require_cuda(x2d, "x")
+    rows = x2d.shape[0]
+    y = torch.empty_like(x2d)
+    mean = torch.empty((rows,), dtype=torch.float32, device=x2d.device)
+    rstd = torch.empty((rows,), dtype=torch.float32, device=x2d.device)
+    a = _ln_act_args(x2d, weight, bias, eps, slope, mean, rstd)
+    a.y = y.data_ptr()
+    _call("cm_ln_act_fwd", lib.cm_ln_act_fwd, C.byref(a), cabi.stream_ptr())
+    return y, mean, rstd
+
+
+def ln_act_backward(x2d, dy2d, weight, bias, mean, rstd, slope, need_wgrad=True):
+    """cm_ln_act_bwd + deterministic reduction of the per-CTA dgamma / dbeta partial rows.
+    Returns (dx in x's dtype, dgamma fp32 (C,), dbeta fp32 (C,))."""
+    lib = cabi.lib()
+    rows, Cn = x2d.shape
+    if dy2d.dtype != x2d.dtype or not dy2d.is_contiguous():
+        dy2d = dy2d.to(x2d.dtype).contiguous()
+    dx = torch.empty_like(x2d)
+    n_part = lib.cm_ln_act_num_part(rows, Cn)
+    dg_part = torch.empty((n_part, Cn), dtype=torch.float32, device=x2d.device)
+    db_part = torch.empty((n_part, Cn), dtype=torch.float32, device=x2d.device)
+    a = _ln_act_args(x2d, weight, bias, 0.0, slope, mean, rstd)
+    a.dy, a.dx = dy2d.data_ptr(), dx.data_ptr()
+    a.dgamma_part, a.dbeta_part = dg_part.data_ptr(), db_part.data_ptr()
+    _call("cm_ln_act_bwd", lib.cm_ln_act_bwd, C.byref(a), cabi.stream_ptr())
+    if not need_wgrad:
+        return dx, None, None
+    dg = torch.empty((Cn,), dtype=torch.float32, device=x2d.device)
+    db = torch.empty((Cn,), dtype=torch.float32, device=x2d.device)
+    reduce_many([(dg_part, dg), (db_part, db)])
+    return dx, dg, db
+
+
 # ------------------------------------------------------------------------------------------------ add + dropout + LayerNorm
 ADD_LN_COMBOS = {(torch.float32, torch.bfloat16, torch.bfloat16), (torch.float32, torch.bfloat16, torch.float32),
                  (torch.float32, torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16, torch.bfloat16),

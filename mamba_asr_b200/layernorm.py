@@ -73,6 +73,51 @@ class FusedLayerNorm(nn.LayerNorm):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# LayerNorm over several trailing dimensions + LeakyReLU in one pass (cm_ln_act_fwd / cm_ln_act_bwd): the conv blocks of
+# the CNN front-end (reference hparams/CTC/conmamba_large.yaml:187-199)
+class _LayerNormActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, slope, n_norm):
+        x2 = x.reshape(-1, n_norm)
+        w, b = weight.reshape(-1), bias.reshape(-1)
+        y, mean, rstd = K.ln_act_forward(x2, w, b, eps, slope)
+        ctx.save_for_backward(x2, w, b, mean, rstd)
+        ctx.slope = slope
+        ctx.w_shape = weight.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, b, mean, rstd = ctx.saved_tensors
+        need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        dx, dg, db = K.ln_act_backward(x2, dy.reshape(-1, x2.shape[1]), w, b, mean, rstd, ctx.slope, need_wgrad=need_w)
+        return (dx.view(dy.shape), dg.view(ctx.w_shape) if ctx.needs_input_grad[1] else None,
+                db.view(ctx.w_shape) if ctx.needs_input_grad[2] else None, None, None, None)
+
+
+def layer_norm_leaky_relu(x, norm, negative_slope=0.01):
+    """``leaky_relu(norm(x))`` for an affine ``nn.LayerNorm`` over any number of trailing dimensions, as ONE sm_100a
+    kernel forward and one backward.  The result keeps x's dtype (under bf16 autocast torch computes LayerNorm and
+    LeakyReLU in fp32 and the consumer casts back to bf16: the same single rounding).  No CPU path."""
+    if not x.is_cuda:
+        raise RuntimeError("mamba_asr_b200.layer_norm_leaky_relu runs on the sm_100a kernel only (no CPU fallback)")
+    n_norm = 1
+    for d in norm.normalized_shape:
+        n_norm *= d
+    if tuple(x.shape[-len(norm.normalized_shape):]) != tuple(norm.normalized_shape):
+        raise ValueError("layer_norm_leaky_relu: trailing dimensions %s do not match normalized_shape %s"
+                         % (tuple(x.shape), tuple(norm.normalized_shape)))
+    if norm.weight is None or norm.bias is None:
+        raise NotImplementedError("layer_norm_leaky_relu needs an affine LayerNorm with bias")
+    xc = x if x.is_contiguous() else x.contiguous()
+    if not K.ln_act_supported(xc.reshape(-1, n_norm)):
+        raise NotImplementedError("layer_norm_leaky_relu: rows of %d elements are outside the kernel envelope "
+                                  "(multiple of 4, <= %d)" % (n_norm, K.LN_ACT_MAX_COLS))
+    with torch.autocast("cuda", enabled=False):
+        return _LayerNormActFn.apply(xc, norm.weight.float(), norm.bias.float(), norm.eps, float(negative_slope), n_norm)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # residual add + dropout + LayerNorm in one pass (cm_add_ln_fwd / cm_add_ln_bwd)
 class DropoutSeed:
     """Device-resident seed of the fused dropout masks.  Every call site gets its own ``call_id`` (a host counter); the

@@ -191,3 +191,89 @@ def test_mamba_weight_gradients_same_with_and_without_tsmm(monkeypatch):
         grads.append({n: p.grad.clone() for n, p in m.named_parameters()})
     for n in grads[0]:
         assert_close(grads[0][n], grads[1][n], torch.bfloat16, floor="max", what="d " + n)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# wide-row LayerNorm + LeakyReLU (cm_ln_act_fwd / cm_ln_act_bwd): the conv blocks of the CNN front-end
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32, torch.float16])
+@pytest.mark.parametrize("shape", [(2, 37, 40, 64), (3, 19, 20, 32), (1, 1, 1, 4), (5, 3, 9, 12), (2, 7, 10, 128),
+                                   (1, 530, 20, 32), (1, 700, 40, 64)])
+def test_layer_norm_leaky_relu_matches_torch(dtype, shape):
+    """leaky_relu(LayerNorm([F, C])(x)) and all three gradients against the torch fp32 composition on the same rounded
+    inputs (rows of 4 .. 2560 elements: every thread-group width of the kernel, ragged last row block, > 1 wave)."""
+    from mamba_asr_b200.layernorm import layer_norm_leaky_relu
+    g = torch.Generator().manual_seed(sum(shape))
+    Fd, Cc = shape[-2:]
+    x = torch.randn(*shape, generator=g).to(dtype)
+    w, b = 1.0 + 0.2 * torch.randn(Fd, Cc, generator=g), 0.1 * torch.randn(Fd, Cc, generator=g)
+    cy = torch.randn(*shape, generator=g).to(dtype)
+
+    xr = x.float().clone().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    pre = F.layer_norm(xr, (Fd, Cc), wr, br, 1e-5)
+    y_ref = F.leaky_relu(pre)
+    (y_ref * cy.float()).sum().backward()
+
+    norm = torch.nn.LayerNorm([Fd, Cc]).cuda()
+    with torch.no_grad():
+        norm.weight.copy_(w)
+        norm.bias.copy_(b)
+    xg = x.cuda().requires_grad_(True)
+    y = layer_norm_leaky_relu(xg, norm)
+    assert y.dtype == dtype and y.shape == xg.shape
+    (y.float() * cy.cuda().float()).sum().backward()
+    assert_close(y.float(), y_ref, dtype, what="y")
+    # an element whose pre-activation is within rounding of zero may take the other LeakyReLU branch: not compared
+    safe = (pre.detach().abs() > 1e-5).float()
+    assert float(safe.mean()) > 0.99
+    assert_close(xg.grad.float().cpu() * safe, xr.grad * safe, dtype, floor="max", what="dx")
+    assert xg.grad.dtype == dtype
+    assert_close(norm.weight.grad, wr.grad, dtype, floor="max", what="dgamma", rtol_mul=2.0)
+    assert_close(norm.bias.grad, br.grad, dtype, floor="max", what="dbeta", rtol_mul=2.0)
+    # deterministic (fixed-order partial sums, no atomics)
+    xg2 = x.cuda().requires_grad_(True)
+    norm.zero_grad()
+    (layer_norm_leaky_relu(xg2, norm).float() * cy.cuda().float()).sum().backward()
+    assert torch.equal(xg2.grad, xg.grad)
+
+
+def test_layer_norm_leaky_relu_refuses_what_the_kernel_does_not_cover():
+    from mamba_asr_b200.layernorm import layer_norm_leaky_relu
+    norm = torch.nn.LayerNorm([3, 2]).cuda()                      # 6 elements: not a multiple of 4
+    with pytest.raises(NotImplementedError):
+        layer_norm_leaky_relu(torch.randn(2, 3, 2, device="cuda"), norm)
+    wide = torch.nn.LayerNorm([41, 64]).cuda()                    # 2624 > 2560
+    with pytest.raises(NotImplementedError):
+        layer_norm_leaky_relu(torch.randn(2, 41, 64, device="cuda"), wide)
+    with pytest.raises(RuntimeError):
+        layer_norm_leaky_relu(torch.randn(2, 4, 4), torch.nn.LayerNorm([4, 4]))   # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("autocast", [False, True])
+def test_conv_front_end_same_with_and_without_the_fused_norm(autocast, monkeypatch):
+    """ConvFrontEnd (2 x [conv 3x3 stride 2, LayerNorm([F', C]), LeakyReLU]) on the fused kernel against the same module
+    on the two torch ops: output and every parameter gradient."""
+    from mamba_asr_b200.encoder import ConvFrontEnd
+    # fp32 case in true fp32: a TF32 second conv turns 1e-7 differences of the norm output into 5e-4 ones (input rounding)
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    torch.manual_seed(3)
+    fe = ConvFrontEnd(80).cuda()
+    with torch.no_grad():
+        for n in fe.norms:
+            n.weight.add_(0.1 * torch.randn_like(n.weight))
+            n.bias.add_(0.1 * torch.randn_like(n.bias))
+    feats = torch.randn(3, 203, 80, device="cuda")
+    cy = torch.randn(3, 51, fe.out_features, device="cuda")
+    res = []
+    for fused in (True, False):
+        fe.use_kernel = fused
+        fe.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            out = fe(feats)
+        (out.float() * cy).sum().backward()
+        res.append((out.float().detach(), [p.grad.clone() for p in fe.parameters()]))
+    dt = torch.bfloat16 if autocast else torch.float32
+    assert res[0][0].shape == (3, 51, fe.out_features)
+    assert_close(res[0][0], res[1][0], dt, what="front-end output")
+    for (name, _), ga, gb in zip(fe.named_parameters(), res[0][1], res[1][1]):
+        assert_close(ga, gb, dt, floor="max", what="d " + name, rtol_mul=4.0)

@@ -119,6 +119,23 @@ def main():
                       % (tag, best, byts / best / 1e6, 100 * byts / best / 1e6 / peak, best * 1e9 / pos,
                          {k: round(min(v), 4) for k, v in kt.items() if k != "cm_scan_bwd"}))
         tag = "cfg%s B%d D%d L%d %s" % (cfg, Bt, D, L, args.dtype)
+        if "ln_act" in only:
+            # wide-row LayerNorm + LeakyReLU at the two conv blocks of the CNN front-end of this config
+            T = {2: 1501, 3: 2001, 4: 2001}.get(int(cfg), 4 * L)
+            T1 = (T - 1) // 2 + 1
+            for rows_, cols_ in ((Bt * T1, 40 * 64), (Bt * L, 20 * 32)):
+                xx = rn(rows_, cols_).to(dt)
+                w, bb = torch.ones(cols_, device=dev), torch.zeros(cols_, device=dev)
+                best, med = timek(lambda: K.ln_act_forward(xx, w, bb, 1e-5, 0.01), "cm_ln_act_fwd", args.iters, flush)
+                byts = rows_ * cols_ * 2 * s
+                print("%-40s ln_act_fwd %dx%d  best %.4f ms med %.4f  alg %.1f GB/s (%.1f%%)"
+                      % (tag, rows_, cols_, best, med, byts / best / 1e6, 100 * byts / best / 1e6 / peak))
+                y, mean, rstd = K.ln_act_forward(xx, w, bb, 1e-5, 0.01)
+                dy = rn(rows_, cols_).to(dt)
+                best, med = timek(lambda: K.ln_act_backward(xx, dy, w, bb, mean, rstd, 0.01), "cm_ln_act_bwd", args.iters, flush)
+                byts = rows_ * cols_ * 3 * s
+                print("%-40s ln_act_bwd %dx%d  best %.4f ms med %.4f  alg %.1f GB/s (%.1f%%)"
+                      % (tag, rows_, cols_, best, med, byts / best / 1e6, 100 * byts / best / 1e6 / peak))
         if "aux" in only:
             # LayerNorm / depthwise conv / column sums at the layer's (rows, d_model) shape
             d_model = D // 2

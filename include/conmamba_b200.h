@@ -374,17 +374,25 @@ int cm_colsum(const void* x, int64_t rows, int32_t cols, int64_t row_stride, int
  * Wide-row LayerNorm + LeakyReLU in one pass (the two conv blocks of the reference's
  * ConvolutionFrontEnd, hparams/CTC/conmamba_large.yaml:187-199 - conv 3x3 stride 2 -> LayerNorm([F', C]) -> LeakyReLU;
  * rows of F'*C = 2560 and 640 elements at the BASELINE shapes).
- *   forward : y = leaky_relu((x - mean) * rstd * gamma + beta, slope)     statistics in fp32; slope = 1: plain LayerNorm
- *   backward: dx, and cm_ln_act_num_part(rows, cols) partial rows of dgamma / dbeta ([n_part][cols] fp32, summed with
- *             cm_reduce_multi); the pre-activation sign is recomputed from x, mean, rstd.
- * x, y, dy, dx are dense (rows, cols) matrices of one dtype; cols a multiple of 4, <= 2560; 16-byte aligned bases.
+ * and the LayerNorm -> activation after the depthwise conv of the ConMamba convolution module, modules/Conmamba.py:292-301).
+ *   x' = x + pre_bias[col % pre_bias_n]                                   (pre_bias NULL: x' = x)
+ *   forward : y = act((x' - mean) * rstd * gamma + beta)                  statistics of x' in fp32
+ *             act = LeakyReLU(slope) (slope = 1: plain LayerNorm) or exact (erf) GELU
+ *   backward: dx (= grad of x'), and cm_ln_act_num_part(rows, cols) partial rows of dgamma / dbeta ([n_part][cols] fp32,
+ *             summed with cm_reduce_multi); the pre-activation is recomputed from x, mean, rstd.
+ * x, y, dy, dx are dense (rows, cols) matrices of one dtype; cols a multiple of 4, <= 2560; 16-byte aligned bases;
+ * pre_bias_n a multiple of 4 that divides cols.
  * ---------------------------------------------------------------------------------------------------- */
+enum { CM_LN_ACT_LEAKY_RELU = 0, CM_LN_ACT_GELU = 1 };
 typedef struct {
   int64_t rows;
   int32_t cols;
   int32_t dtype;
   float eps;
   float slope;              /* LeakyReLU negative slope (torch default 0.01) */
+  int32_t act;              /* CM_LN_ACT_* */
+  int32_t pre_bias_n;       /* period of pre_bias in columns */
+  const float* pre_bias;    /* (pre_bias_n) fp32 or NULL */
   const void* x;
   void* y;                  /* forward output */
   const float* gamma;       /* (cols) fp32 */

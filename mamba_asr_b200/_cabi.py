@@ -18,6 +18,7 @@ CM_FLAG_DELTA_SOFTPLUS = 1
 CM_FLAG_SILU = 1
 CM_SCAN_CKPT_STEPS = 8
 CM_ABI_VERSION = 7
+CM_LN_ACT_LEAKY_RELU, CM_LN_ACT_GELU = 0, 1
 
 EXPORTS = (
     "cm_version", "cm_scan_num_ckpt", "cm_scan_slab_channels", "cm_scan_pick_lanes", "cm_scan_pick_lanes_bwd", "cm_scan_fwd",
@@ -153,6 +154,7 @@ class AddLnArgs(C.Structure):
 
 class LnActArgs(C.Structure):
     _fields_ = [("rows", C.c_int64), ("cols", C.c_int32), ("dtype", C.c_int32), ("eps", C.c_float), ("slope", C.c_float),
+                ("act", C.c_int32), ("pre_bias_n", C.c_int32), ("pre_bias", C.c_void_p),
                 ("x", C.c_void_p), ("y", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("mean", C.c_void_p),
                 ("rstd", C.c_void_p), ("dy", C.c_void_p), ("dx", C.c_void_p), ("dgamma_part", C.c_void_p),
                 ("dbeta_part", C.c_void_p)]

@@ -24,7 +24,7 @@ from .bimamba import Mamba as BiMamba
 from .bimamba import UniMamba as Mamba
 from .dwconv import depthwise_conv1d
 from .kernels import DWCONV_KSIZES
-from .layernorm import FusedLayerNorm, add_dropout_layer_norm, gelu_dropout
+from .layernorm import FusedLayerNorm, add_dropout_layer_norm, gelu_dropout, layer_norm_act
 from .linear import BiasGradLinear, linear as _linear
 
 LAYER_NORM_EPS = 1e-6        # reference ConMambaConstants.LAYER_NORM_EPS (Conmamba.py:687)
@@ -116,7 +116,13 @@ def _conv_body(self, normed, final_dropout=True):
     pw = self.bottleneck[0]                                           # pointwise conv = Linear over channel-last rows
     out = F.glu(_linear(normed, pw.weight.squeeze(-1), pw.bias), dim=-1)
     out = depthwise_conv1d(out, self.conv.weight, self.conv.bias, pad_left=self.padding)
-    out = self.after_conv[2](self.after_conv[1](self.after_conv[0](out)))
+    norm, act = self.after_conv[0], self.after_conv[1]
+    if (type(act) is nn.GELU and act.approximate == "none" and norm.normalized_shape[0] % 4 == 0
+            and os.environ.get("CM_NO_FUSE_LN_GELU") is None):
+        out = layer_norm_act(out, norm, "gelu")                       # LayerNorm -> GELU: one sm_100a kernel each way
+    else:
+        out = act(norm(out))
+    out = self.after_conv[2](out)
     return self.after_conv[3](out) if final_dropout else out
 
 

@@ -139,6 +139,38 @@ __device__ __forceinline__ float sigmoid_sel(float x) {
   return fmaf(tanh_approx(0.5f * x), 0.5f, 0.5f);
 }
 
+// ---- exact (erf) GELU ------------------------------------------------------------------------------
+constexpr float kInvSqrt2 = 0.7071067811865476f;
+constexpr float kInvSqrt2Pi = 0.3989422804014327f;
+// Phi(x) = 0.5 * (1 + erf(x / sqrt 2)) and phi(x) = exp(-x^2/2) / sqrt(2 pi) from ONE ex2: erf by Abramowitz-Stegun 7.1.26
+// (|error| <= 1.5e-7, the fp32 resolution of 1 + erf), 1 - erf(|y|) = poly(t) * exp(-y^2), t = 1 / (1 + p |y|).
+// libdevice's erff costs ~25 instructions per element and made the fused kernel issue-bound (82 % issue-slot utilisation
+// in profiles/r01_fused_addln_gelu_cfg3_ncu.txt); this form is 2 MUFU + 10 FMA-pipe instructions and shares the
+// exponential with the derivative.
+__device__ __forceinline__ void gelu_parts(float x, float* Phi, float* phi) {
+  const float y = fabsf(x) * kInvSqrt2;
+  const float e = ex2(-y * y * kLog2e);                 // exp(-x^2 / 2)
+  const float t = rcp(fmaf(0.3275911f, y, 1.0f));
+  float p = 1.061405429f;
+  p = fmaf(p, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float q = 0.5f * p * t * e;                     // 0.5 * erfc(|y|) = Phi(-|x|)
+  *Phi = x >= 0.f ? 1.0f - q : q;
+  *phi = kInvSqrt2Pi * e;
+}
+__device__ __forceinline__ float gelu_f(float x) {
+  float P, d;
+  gelu_parts(x, &P, &d);
+  return x * P;
+}
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  float P, d;
+  gelu_parts(x, &P, &d);
+  return fmaf(x, d, P);
+}
+
 // ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 lanes per issue slot) ---------------
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   float2 d;

@@ -1,4 +1,5 @@
-// Wide-row LayerNorm + LeakyReLU for the CNN front-end (cm_ln_act_fwd / cm_ln_act_bwd), sm_100a.
+// LayerNorm + activation in one pass (cm_ln_act_fwd / cm_ln_act_bwd), sm_100a: the wide rows of the CNN front-end
+// (LeakyReLU, conv bias folded in) and the LayerNorm -> GELU of the ConMamba convolution module.
 //
 // SURVEY.md section 8(f) rank 2 ("SpeechBrain-free layer shell"): the reference's ConvolutionFrontEnd normalises every
 // conv block's output over (freq, channel) - LayerNorm([F', C]) = rows of 2560 and 640 elements at the BASELINE shapes -
@@ -69,9 +70,24 @@ __device__ __forceinline__ float2 group_sum(float2 v, float2 (*red)[kThreads / 3
   return s;
 }
 
-template <typename T, int G>
+// activation of the normalised value and its derivative
+template <int ACT> __device__ __forceinline__ float act_fwd(float t, float slope) {
+  if (ACT == CM_LN_ACT_GELU) return gelu_f(t);
+  return t > 0.f ? t : t * slope;
+}
+template <int ACT> __device__ __forceinline__ float act_bwd(float t, float dy, float slope) {
+  if (ACT == CM_LN_ACT_GELU) return dy * gelu_grad_f(t);
+  return t > 0.f ? dy : dy * slope;
+}
+// bias added to x before the statistics (the conv bias of the front-end blocks): period pbn columns, pbn % 4 == 0
+__device__ __forceinline__ float4 pre_bias4(const float* pb, int pbn, int q, bool ok) {
+  return (pb != nullptr && ok) ? __ldg(reinterpret_cast<const float4*>(pb + (4 * q) % pbn)) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+template <typename T, int G, int ACT>
 __global__ void __launch_bounds__(kThreads) ln_act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              const float* __restrict__ pre_bias, int pbn,
                                                               float* __restrict__ mean, float* __restrict__ rstd,
                                                               int64_t rows, int cols, float eps, float slope) {
   constexpr int RPC = kThreads / G;
@@ -87,6 +103,9 @@ __global__ void __launch_bounds__(kThreads) ln_act_fwd_kernel(const T* __restric
     gm[i] = q < nq ? __ldg(reinterpret_cast<const float4*>(gamma) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
     bt[i] = q < nq ? __ldg(reinterpret_cast<const float4*>(beta) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  float4 pbv[kNQ];
+#pragma unroll
+  for (int i = 0; i < kNQ; ++i) pbv[i] = pre_bias4(pre_bias, pbn, gl + i * G, gl + i * G < nq);
   const int64_t nblk = (rows + RPC - 1) / RPC;
   int par = 0;
   for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
@@ -104,6 +123,8 @@ __global__ void __launch_bounds__(kThreads) ln_act_fwd_kernel(const T* __restric
 #pragma unroll
     for (int i = 0; i < kNQ; ++i) {
       Quad<T>::cvt(raw[i], v[i]);
+      const float4 pb = pbv[i];
+      v[i][0] += pb.x; v[i][1] += pb.y; v[i][2] += pb.z; v[i][3] += pb.w;
       s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
     }
     const float mu = group_sum<G>(make_float2(s, 0.f), red, par).x * inv_n;
@@ -129,8 +150,7 @@ __global__ void __launch_bounds__(kThreads) ln_act_fwd_kernel(const T* __restric
           float o[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float t = fmaf(v[i][e] * rs, g4[e], b4[e]);
-            o[e] = t > 0.f ? t : t * slope;
+            o[e] = act_fwd<ACT>(fmaf(v[i][e] * rs, g4[e], b4[e]), slope);
           }
           st4<T>(py + (int64_t)q * 4 * ES, o);
         }
@@ -143,10 +163,12 @@ __global__ void __launch_bounds__(kThreads) ln_act_fwd_kernel(const T* __restric
   }
 }
 
-template <typename T, int G>
+template <typename T, int G, int ACT>
 __global__ void __launch_bounds__(kThreads, 4) ln_act_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                                  T* __restrict__ dx, const float* __restrict__ gamma,
-                                                                 const float* __restrict__ beta, const float* __restrict__ mean,
+                                                                 const float* __restrict__ beta,
+                                                                 const float* __restrict__ pre_bias, int pbn,
+                                                                 const float* __restrict__ mean,
                                                                  const float* __restrict__ rstd, float* __restrict__ dg_part,
                                                                  float* __restrict__ db_part, int64_t rows, int cols,
                                                                  float slope) {
@@ -192,11 +214,13 @@ __global__ void __launch_bounds__(kThreads, 4) ln_act_bwd_kernel(const T* __rest
       float xv[4], dv[4];
       Quad<T>::cvt(rx[i], xv);
       Quad<T>::cvt(rdy[i], dv);
+      const float4 pb = pre_bias4(pre_bias, pbn, q, rv && qv);
+      xv[0] += pb.x; xv[1] += pb.y; xv[2] += pb.z; xv[3] += pb.w;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float h = (xv[e] - mu) * rs;
         const float pre = fmaf(h, g4[e], b4[e]);
-        const float gg = pre > 0.f ? dv[e] : dv[e] * slope;   // zero for padding quads / rows (dy loaded as 0)
+        const float gg = act_bwd<ACT>(pre, dv[e], slope);     // zero for padding quads / rows (dy loaded as 0)
         dg[i][e] = fmaf(gg, h, dg[i][e]);
         db[i][e] += gg;
         const float d = gg * g4[e];
@@ -276,7 +300,14 @@ static int bwd_grid(int64_t rows, int cols) {
 }
 
 static bool args_ok(const cm_ln_act_args* a) {
-  return a && a->x && a->gamma && a->beta && a->mean && a->rstd && a->rows > 0 && a->cols > 0;
+  return a && a->x && a->gamma && a->beta && a->mean && a->rstd && a->rows > 0 && a->cols > 0 &&
+         (a->act == CM_LN_ACT_LEAKY_RELU || a->act == CM_LN_ACT_GELU);
+}
+// pre-norm bias: absent, or a period that is a multiple of 4 dividing cols, 16-byte aligned
+static bool pre_bias_ok(const cm_ln_act_args* a) {
+  if (a->pre_bias == nullptr) return true;
+  return a->pre_bias_n > 0 && (a->pre_bias_n & 3) == 0 && a->cols % a->pre_bias_n == 0 &&
+         (reinterpret_cast<uintptr_t>(a->pre_bias) & 15) == 0;
 }
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -284,14 +315,21 @@ template <typename T>
 static int fwd_t(const cm_ln_act_args* a, cudaStream_t st) {
   const int64_t nblk = row_blocks(a->rows, a->cols), cap = (int64_t)sm_count() * 8;
   const int grid = (int)(nblk < cap ? nblk : cap);
-#define CM_LNA_FWD(G)                                                                                                     \
-  ln_act_fwd_kernel<T, G><<<grid, kThreads, 0, st>>>(static_cast<const T*>(a->x), static_cast<T*>(a->y), a->gamma, a->beta, \
-                                                     a->mean, a->rstd, a->rows, a->cols, a->eps, a->slope)
+#define CM_LNA_FWD(G, ACT)                                                                                                  \
+  ln_act_fwd_kernel<T, G, ACT><<<grid, kThreads, 0, st>>>(static_cast<const T*>(a->x), static_cast<T*>(a->y), a->gamma,       \
+                                                          a->beta, a->pre_bias, a->pre_bias_n, a->mean, a->rstd, a->rows,   \
+                                                          a->cols, a->eps, a->slope)
+#define CM_LNA_FWD_G(G)                                                         \
+  do {                                                                          \
+    if (a->act == CM_LN_ACT_GELU) CM_LNA_FWD(G, CM_LN_ACT_GELU);                \
+    else CM_LNA_FWD(G, CM_LN_ACT_LEAKY_RELU);                                   \
+  } while (0)
   switch (group_size(a->cols)) {
-    case 32: CM_LNA_FWD(32); break;
-    case 64: CM_LNA_FWD(64); break;
-    default: CM_LNA_FWD(128); break;
+    case 32: CM_LNA_FWD_G(32); break;
+    case 64: CM_LNA_FWD_G(64); break;
+    default: CM_LNA_FWD_G(128); break;
   }
+#undef CM_LNA_FWD_G
 #undef CM_LNA_FWD
   CM_LAUNCH_CHECK();
   return 0;
@@ -300,15 +338,22 @@ static int fwd_t(const cm_ln_act_args* a, cudaStream_t st) {
 template <typename T>
 static int bwd_t(const cm_ln_act_args* a, cudaStream_t st) {
   const int grid = bwd_grid(a->rows, a->cols);
-#define CM_LNA_BWD(G)                                                                                                       \
-  ln_act_bwd_kernel<T, G><<<grid, kThreads, 0, st>>>(static_cast<const T*>(a->x), static_cast<const T*>(a->dy),              \
-                                                     static_cast<T*>(a->dx), a->gamma, a->beta, a->mean, a->rstd,            \
-                                                     a->dgamma_part, a->dbeta_part, a->rows, a->cols, a->slope)
+#define CM_LNA_BWD(G, ACT)                                                                                                  \
+  ln_act_bwd_kernel<T, G, ACT><<<grid, kThreads, 0, st>>>(static_cast<const T*>(a->x), static_cast<const T*>(a->dy),          \
+                                                          static_cast<T*>(a->dx), a->gamma, a->beta, a->pre_bias,            \
+                                                          a->pre_bias_n, a->mean, a->rstd, a->dgamma_part, a->dbeta_part,   \
+                                                          a->rows, a->cols, a->slope)
+#define CM_LNA_BWD_G(G)                                                         \
+  do {                                                                          \
+    if (a->act == CM_LN_ACT_GELU) CM_LNA_BWD(G, CM_LN_ACT_GELU);                \
+    else CM_LNA_BWD(G, CM_LN_ACT_LEAKY_RELU);                                   \
+  } while (0)
   switch (group_size(a->cols)) {
-    case 32: CM_LNA_BWD(32); break;
-    case 64: CM_LNA_BWD(64); break;
-    default: CM_LNA_BWD(128); break;
+    case 32: CM_LNA_BWD_G(32); break;
+    case 64: CM_LNA_BWD_G(64); break;
+    default: CM_LNA_BWD_G(128); break;
   }
+#undef CM_LNA_BWD_G
 #undef CM_LNA_BWD
   CM_LAUNCH_CHECK();
   return 0;
@@ -324,7 +369,7 @@ extern "C" int cm_ln_act_num_part(int64_t rows, int32_t cols) {
 
 extern "C" int cm_ln_act_fwd(const cm_ln_act_args* a, void* stream) {
   if (!cm::lna::args_ok(a) || !a->y) return CM_ERR_BAD_ARG;
-  if (a->cols > cm::lna::kMaxCols || (a->cols & 3) != 0 || !cm::dtype_ok(a->dtype)) return CM_ERR_UNSUPPORTED;
+  if (a->cols > cm::lna::kMaxCols || (a->cols & 3) != 0 || !cm::dtype_ok(a->dtype) || !cm::lna::pre_bias_ok(a)) return CM_ERR_UNSUPPORTED;
   if (!cm::lna::aligned16(a->x) || !cm::lna::aligned16(a->y) || !cm::lna::aligned16(a->gamma) || !cm::lna::aligned16(a->beta))
     return CM_ERR_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -337,7 +382,7 @@ extern "C" int cm_ln_act_fwd(const cm_ln_act_args* a, void* stream) {
 
 extern "C" int cm_ln_act_bwd(const cm_ln_act_args* a, void* stream) {
   if (!cm::lna::args_ok(a) || !a->dy || !a->dx || !a->dgamma_part || !a->dbeta_part) return CM_ERR_BAD_ARG;
-  if (a->cols > cm::lna::kMaxCols || (a->cols & 3) != 0 || !cm::dtype_ok(a->dtype)) return CM_ERR_UNSUPPORTED;
+  if (a->cols > cm::lna::kMaxCols || (a->cols & 3) != 0 || !cm::dtype_ok(a->dtype) || !cm::lna::pre_bias_ok(a)) return CM_ERR_UNSUPPORTED;
   if (!cm::lna::aligned16(a->x) || !cm::lna::aligned16(a->dy) || !cm::lna::aligned16(a->dx) || !cm::lna::aligned16(a->gamma) ||
       !cm::lna::aligned16(a->beta) || !cm::lna::aligned16(a->dgamma_part) || !cm::lna::aligned16(a->dbeta_part))
     return CM_ERR_UNSUPPORTED;

@@ -88,12 +88,15 @@ class ConvFrontEnd(nn.Module):
         # (B, 1, T, F) with explicit NHWC strides: with one channel the default strides are ambiguous and torch resolves
         # the ambiguity to NCHW, which makes cuDNN convert the 64-channel output back and forth
         x = feats.as_strided((Bt, 1, T, Fd), (T * Fd, 1, Fd, 1))
+        fused = self.use_kernel and os.environ.get("CM_NO_FUSE_FRONTEND_LN") is None
         for conv, norm in zip(self.convs, self.norms):
-            x = F.conv2d(x, conv.weight.contiguous(memory_format=torch.channels_last), conv.bias, conv.stride,
-                         conv.padding)                             # (B, C, T', F'), NHWC memory
+            # fused: the conv bias is added inside the norm kernel (as a separate torch add it is one more pass over the
+            # largest activation of the step)
+            x = F.conv2d(x, conv.weight.contiguous(memory_format=torch.channels_last), None if fused else conv.bias,
+                         conv.stride, conv.padding)                # (B, C, T', F'), NHWC memory
             x = x.permute(0, 2, 3, 1)                              # (B, T', F', C), contiguous
-            if self.use_kernel and os.environ.get("CM_NO_FUSE_FRONTEND_LN") is None:
-                x = layer_norm_leaky_relu(x, norm)
+            if fused:
+                x = layer_norm_leaky_relu(x, norm, pre_bias=conv.bias)
             else:
                 x = F.leaky_relu(norm(x))
             x = x.permute(0, 3, 1, 2)

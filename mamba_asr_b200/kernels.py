@@ -532,19 +532,30 @@ def ln_act_supported(x2d):
             and x2d.data_ptr() % 16 == 0)
 
 
-def _ln_act_args(x2d, weight, bias, eps, slope, mean, rstd):
+LN_ACTS = {"leaky_relu": cabi.CM_LN_ACT_LEAKY_RELU, "gelu": cabi.CM_LN_ACT_GELU}
+
+
+def _ln_act_args(x2d, weight, bias, eps, slope, mean, rstd, act, pre_bias):
     a = cabi.LnActArgs()
     a.rows, a.cols = x2d.shape
     a.dtype = cabi.dtype_code(x2d.dtype)
     a.eps, a.slope = float(eps), float(slope)
+    a.act = LN_ACTS[act]
+    if pre_bias is not None:
+        pre_bias = _f32c(pre_bias, "pre_bias")
+        n = pre_bias.numel()
+        if n % 4 != 0 or x2d.shape[1] % n != 0 or pre_bias.data_ptr() % 16 != 0:
+            raise NotImplementedError("ln_act: pre_bias needs a length that is a multiple of 4 and divides the row length")
+        a.pre_bias, a.pre_bias_n = pre_bias.data_ptr(), n
     a.x = x2d.data_ptr()
     a.gamma, a.beta = _f32c(weight, "weight").data_ptr(), _f32c(bias, "bias").data_ptr()
     a.mean, a.rstd = mean.data_ptr(), rstd.data_ptr()
     return a
 
 
-def ln_act_forward(x2d, weight, bias, eps, slope):
-    """cm_ln_act_fwd: y = leaky_relu(layer_norm(x), slope) over the rows of a dense (rows, C) matrix, y in x's dtype.
+def ln_act_forward(x2d, weight, bias, eps, slope=0.01, act="leaky_relu", pre_bias=None):
+    """cm_ln_act_fwd: y = act(layer_norm(x + pre_bias)) over the rows of a dense (rows, C) matrix, y in x's dtype;
+    act = "leaky_relu" (negative slope `slope`) or "gelu" (exact); pre_bias (n,) fp32 repeats every n columns.
     Returns (y, mean (rows,) fp32, rstd (rows,) fp32)."""
     lib = cabi.lib()
     _require_cuda(x2d, "x")
@@ -552,15 +563,15 @@ def ln_act_forward(x2d, weight, bias, eps, slope):
     y = torch.empty_like(x2d)
     mean = torch.empty((rows,), dtype=torch.float32, device=x2d.device)
     rstd = torch.empty((rows,), dtype=torch.float32, device=x2d.device)
-    a = _ln_act_args(x2d, weight, bias, eps, slope, mean, rstd)
+    a = _ln_act_args(x2d, weight, bias, eps, slope, mean, rstd, act, pre_bias)
     a.y = y.data_ptr()
     _call("cm_ln_act_fwd", lib.cm_ln_act_fwd, C.byref(a), cabi.stream_ptr())
     return y, mean, rstd
 
 
-def ln_act_backward(x2d, dy2d, weight, bias, mean, rstd, slope, need_wgrad=True):
+def ln_act_backward(x2d, dy2d, weight, bias, mean, rstd, slope=0.01, act="leaky_relu", pre_bias=None, need_wgrad=True):
     """cm_ln_act_bwd + deterministic reduction of the per-CTA dgamma / dbeta partial rows.
-    Returns (dx in x's dtype, dgamma fp32 (C,), dbeta fp32 (C,))."""
+    Returns (dx in x's dtype (= the gradient of x + pre_bias), dgamma fp32 (C,), dbeta fp32 (C,))."""
     lib = cabi.lib()
     rows, Cn = x2d.shape
     if dy2d.dtype != x2d.dtype or not dy2d.is_contiguous():
@@ -569,7 +580,7 @@ def ln_act_backward(x2d, dy2d, weight, bias, mean, rstd, slope, need_wgrad=True)
     n_part = lib.cm_ln_act_num_part(rows, Cn)
     dg_part = torch.empty((n_part, Cn), dtype=torch.float32, device=x2d.device)
     db_part = torch.empty((n_part, Cn), dtype=torch.float32, device=x2d.device)
-    a = _ln_act_args(x2d, weight, bias, 0.0, slope, mean, rstd)
+    a = _ln_act_args(x2d, weight, bias, 0.0, slope, mean, rstd, act, pre_bias)
     a.dy, a.dx = dy2d.data_ptr(), dx.data_ptr()
     a.dgamma_part, a.dbeta_part = dg_part.data_ptr(), db_part.data_ptr()
     _call("cm_ln_act_bwd", lib.cm_ln_act_bwd, C.byref(a), cabi.stream_ptr())

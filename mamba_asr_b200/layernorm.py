@@ -73,48 +73,67 @@ class FusedLayerNorm(nn.LayerNorm):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# LayerNorm over several trailing dimensions + LeakyReLU in one pass (cm_ln_act_fwd / cm_ln_act_bwd): the conv blocks of
-# the CNN front-end (reference hparams/CTC/conmamba_large.yaml:187-199)
+# LayerNorm over several trailing dimensions + activation in one pass (cm_ln_act_fwd / cm_ln_act_bwd): the conv blocks of
+# the CNN front-end (reference hparams/CTC/conmamba_large.yaml:187-199; LeakyReLU, conv bias folded in) and the
+# LayerNorm -> activation after the depthwise conv of the convolution module (reference modules/Conmamba.py:292-301)
 class _LayerNormActFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, slope, n_norm):
+    def forward(ctx, x, weight, bias, pre_bias, eps, slope, act, n_norm):
         x2 = x.reshape(-1, n_norm)
         w, b = weight.reshape(-1), bias.reshape(-1)
-        y, mean, rstd = K.ln_act_forward(x2, w, b, eps, slope)
-        ctx.save_for_backward(x2, w, b, mean, rstd)
-        ctx.slope = slope
+        y, mean, rstd = K.ln_act_forward(x2, w, b, eps, slope, act, pre_bias)
+        ctx.save_for_backward(x2, w, b, pre_bias, mean, rstd)
+        ctx.slope, ctx.act = slope, act
         ctx.w_shape = weight.shape
         return y.view(x.shape)
 
     @staticmethod
     def backward(ctx, dy):
-        x2, w, b, mean, rstd = ctx.saved_tensors
+        x2, w, b, pre_bias, mean, rstd = ctx.saved_tensors
         need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
-        dx, dg, db = K.ln_act_backward(x2, dy.reshape(-1, x2.shape[1]), w, b, mean, rstd, ctx.slope, need_wgrad=need_w)
+        dx, dg, db = K.ln_act_backward(x2, dy.reshape(-1, x2.shape[1]), w, b, mean, rstd, ctx.slope, ctx.act, pre_bias,
+                                       need_wgrad=need_w)
+        dpb = None
+        if pre_bias is not None and ctx.needs_input_grad[3]:
+            cs = K.colsum(dx)                                     # (n_norm,) fp32, fixed-order sums
+            if cs is None:
+                cs = dx.float().sum(0)
+            dpb = cs.view(-1, pre_bias.numel()).sum(0)
         return (dx.view(dy.shape), dg.view(ctx.w_shape) if ctx.needs_input_grad[1] else None,
-                db.view(ctx.w_shape) if ctx.needs_input_grad[2] else None, None, None, None)
+                db.view(ctx.w_shape) if ctx.needs_input_grad[2] else None, dpb, None, None, None, None)
 
 
-def layer_norm_leaky_relu(x, norm, negative_slope=0.01):
-    """``leaky_relu(norm(x))`` for an affine ``nn.LayerNorm`` over any number of trailing dimensions, as ONE sm_100a
-    kernel forward and one backward.  The result keeps x's dtype (under bf16 autocast torch computes LayerNorm and
-    LeakyReLU in fp32 and the consumer casts back to bf16: the same single rounding).  No CPU path."""
+def layer_norm_act(x, norm, act="leaky_relu", negative_slope=0.01, pre_bias=None):
+    """``act(norm(x + pre_bias))`` for an affine ``nn.LayerNorm`` over any number of trailing dimensions as ONE sm_100a
+    kernel forward and one backward; ``act`` is "leaky_relu" or "gelu" (exact).  ``pre_bias`` (n,) is added along the
+    last dimension before the statistics (n = the last dimension: the bias of the conv that produced x).  The result
+    keeps x's dtype (under bf16 autocast torch computes LayerNorm and the activation in fp32 and the consumer casts back
+    to bf16: the same single rounding).  No CPU path."""
     if not x.is_cuda:
-        raise RuntimeError("mamba_asr_b200.layer_norm_leaky_relu runs on the sm_100a kernel only (no CPU fallback)")
+        raise RuntimeError("mamba_asr_b200.layer_norm_act runs on the sm_100a kernel only (no CPU fallback)")
     n_norm = 1
     for d in norm.normalized_shape:
         n_norm *= d
     if tuple(x.shape[-len(norm.normalized_shape):]) != tuple(norm.normalized_shape):
-        raise ValueError("layer_norm_leaky_relu: trailing dimensions %s do not match normalized_shape %s"
+        raise ValueError("layer_norm_act: trailing dimensions %s do not match normalized_shape %s"
                          % (tuple(x.shape), tuple(norm.normalized_shape)))
     if norm.weight is None or norm.bias is None:
-        raise NotImplementedError("layer_norm_leaky_relu needs an affine LayerNorm with bias")
+        raise NotImplementedError("layer_norm_act needs an affine LayerNorm with bias")
+    if pre_bias is not None and pre_bias.numel() != x.shape[-1]:
+        raise ValueError("layer_norm_act: pre_bias must have the length of the last dimension")
     xc = x if x.is_contiguous() else x.contiguous()
-    if not K.ln_act_supported(xc.reshape(-1, n_norm)):
-        raise NotImplementedError("layer_norm_leaky_relu: rows of %d elements are outside the kernel envelope "
+    if not K.ln_act_supported(xc.reshape(-1, n_norm)) or (pre_bias is not None and pre_bias.numel() % 4 != 0):
+        raise NotImplementedError("layer_norm_act: rows of %d elements are outside the kernel envelope "
                                   "(multiple of 4, <= %d)" % (n_norm, K.LN_ACT_MAX_COLS))
     with torch.autocast("cuda", enabled=False):
-        return _LayerNormActFn.apply(xc, norm.weight.float(), norm.bias.float(), norm.eps, float(negative_slope), n_norm)
+        return _LayerNormActFn.apply(xc, norm.weight.float(), norm.bias.float(),
+                                     None if pre_bias is None else pre_bias.float(), norm.eps, float(negative_slope), act,
+                                     n_norm)
+
+
+def layer_norm_leaky_relu(x, norm, negative_slope=0.01, pre_bias=None):
+    """``leaky_relu(norm(x + pre_bias))``: see ``layer_norm_act``."""
+    return layer_norm_act(x, norm, "leaky_relu", negative_slope, pre_bias)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -198,20 +198,27 @@ def test_mamba_weight_gradients_same_with_and_without_tsmm(monkeypatch):
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32, torch.float16])
 @pytest.mark.parametrize("shape", [(2, 37, 40, 64), (3, 19, 20, 32), (1, 1, 1, 4), (5, 3, 9, 12), (2, 7, 10, 128),
                                    (1, 530, 20, 32), (1, 700, 40, 64)])
-def test_layer_norm_leaky_relu_matches_torch(dtype, shape):
-    """leaky_relu(LayerNorm([F, C])(x)) and all three gradients against the torch fp32 composition on the same rounded
+@pytest.mark.parametrize("act", ["leaky_relu", "gelu"])
+@pytest.mark.parametrize("with_pre_bias", [False, True])
+def test_layer_norm_leaky_relu_matches_torch(dtype, shape, act, with_pre_bias):
+    """act(LayerNorm([F, C])(x + pre_bias)) and all gradients against the torch fp32 composition on the same rounded
     inputs (rows of 4 .. 2560 elements: every thread-group width of the kernel, ragged last row block, > 1 wave)."""
-    from mamba_asr_b200.layernorm import layer_norm_leaky_relu
+    from mamba_asr_b200.layernorm import layer_norm_act
+    layer_norm_leaky_relu = lambda x_, n_: layer_norm_act(x_, n_, act, 0.01, pbg)
     g = torch.Generator().manual_seed(sum(shape))
     Fd, Cc = shape[-2:]
     x = torch.randn(*shape, generator=g).to(dtype)
     w, b = 1.0 + 0.2 * torch.randn(Fd, Cc, generator=g), 0.1 * torch.randn(Fd, Cc, generator=g)
     cy = torch.randn(*shape, generator=g).to(dtype)
 
+    pb = 0.5 * torch.randn(Cc, generator=g)
+    pbr = pb.clone().requires_grad_(True)
+    pbg = pb.cuda().requires_grad_(True) if with_pre_bias else None
+
     xr = x.float().clone().requires_grad_(True)
     wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
-    pre = F.layer_norm(xr, (Fd, Cc), wr, br, 1e-5)
-    y_ref = F.leaky_relu(pre)
+    pre = F.layer_norm(xr + pbr if with_pre_bias else xr, (Fd, Cc), wr, br, 1e-5)
+    y_ref = F.leaky_relu(pre) if act == "leaky_relu" else F.gelu(pre)
     (y_ref * cy.float()).sum().backward()
 
     norm = torch.nn.LayerNorm([Fd, Cc]).cuda()
@@ -224,17 +231,20 @@ def test_layer_norm_leaky_relu_matches_torch(dtype, shape):
     (y.float() * cy.cuda().float()).sum().backward()
     assert_close(y.float(), y_ref, dtype, what="y")
     # an element whose pre-activation is within rounding of zero may take the other LeakyReLU branch: not compared
-    safe = (pre.detach().abs() > 1e-5).float()
+    safe = (pre.detach().abs() > 1e-5).float() if act == "leaky_relu" else torch.ones_like(pre)
     assert float(safe.mean()) > 0.99
+    if with_pre_bias:
+        assert_close(pbg.grad, pbr.grad, dtype, floor="max", what="d pre_bias", rtol_mul=2.0)
     assert_close(xg.grad.float().cpu() * safe, xr.grad * safe, dtype, floor="max", what="dx")
     assert xg.grad.dtype == dtype
     assert_close(norm.weight.grad, wr.grad, dtype, floor="max", what="dgamma", rtol_mul=2.0)
     assert_close(norm.bias.grad, br.grad, dtype, floor="max", what="dbeta", rtol_mul=2.0)
     # deterministic (fixed-order partial sums, no atomics)
     xg2 = x.cuda().requires_grad_(True)
+    g1 = norm.weight.grad.clone()
     norm.zero_grad()
     (layer_norm_leaky_relu(xg2, norm).float() * cy.cuda().float()).sum().backward()
-    assert torch.equal(xg2.grad, xg.grad)
+    assert torch.equal(xg2.grad, xg.grad) and torch.equal(norm.weight.grad, g1)
 
 
 def test_layer_norm_leaky_relu_refuses_what_the_kernel_does_not_cover():
@@ -276,4 +286,39 @@ def test_conv_front_end_same_with_and_without_the_fused_norm(autocast, monkeypat
     assert res[0][0].shape == (3, 51, fe.out_features)
     assert_close(res[0][0], res[1][0], dt, what="front-end output")
     for (name, _), ga, gb in zip(fe.named_parameters(), res[0][1], res[1][1]):
+        if autocast:
+            # the fused path adds the conv bias in fp32, cuDNN rounds x + bias to bf16 first: pre-activations within
+            # ~1e-2 of zero take the other LeakyReLU branch (a 0.99 * dy step in single terms of the sums), so the
+            # bf16 gradients are compared in norm rather than element by element
+            rel = float((ga - gb).norm() / gb.norm())
+            assert rel < 0.05, (name, rel)
+        else:
+            assert_close(ga, gb, dt, floor="max", what="d " + name, rtol_mul=4.0)
+
+
+@pytest.mark.parametrize("autocast", [False, True])
+def test_convolution_module_same_with_and_without_the_fused_norm_gelu(autocast, monkeypatch):
+    """ConvolutionModule (reference modules/Conmamba.py:182-454) with LayerNorm -> GELU after the depthwise conv on
+    cm_ln_act_* against the separate cm_layernorm + torch GELU evaluation: output and every parameter gradient."""
+    from mamba_asr_b200.conmamba import ConvolutionModule
+    torch.manual_seed(5)
+    m = ConvolutionModule(144, kernel_size=31, activation=torch.nn.GELU, dropout=0.0).cuda()
+    x = torch.randn(3, 77, 144, device="cuda")
+    cy = torch.randn(3, 77, 144, device="cuda")
+    res = []
+    for fused in (True, False):
+        if fused:
+            monkeypatch.delenv("CM_NO_FUSE_LN_GELU", raising=False)
+        else:
+            monkeypatch.setenv("CM_NO_FUSE_LN_GELU", "1")
+        m.zero_grad()
+        xg = x.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            out = m(xg)
+        (out.float() * cy).sum().backward()
+        res.append((out.float().detach(), xg.grad.clone(), [p.grad.clone() for p in m.parameters()]))
+    dt = torch.bfloat16 if autocast else torch.float32
+    assert_close(res[0][0], res[1][0], dt, what="conv module output")
+    assert_close(res[0][1], res[1][1], dt, floor="max", what="conv module dx", rtol_mul=2.0)
+    for (name, _), ga, gb in zip(m.named_parameters(), res[0][2], res[1][2]):
         assert_close(ga, gb, dt, floor="max", what="d " + name, rtol_mul=4.0)

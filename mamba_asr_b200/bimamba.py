@@ -14,6 +14,7 @@ channel-last, no flips) -> out_proj GEMM.  Incremental decoding (``inference_par
 cm_ssm_step.  There is no slow path and no CPU path.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -98,7 +99,8 @@ class _MambaBase(nn.Module):
         g = lambda n: getattr(self, n + suffix)
         A_log = self.A_b_log if suffix else self.A_log
         Dk = self.D_b if suffix else self.D
-        A = -torch.exp(A_log.float())                                                   # bimamba.py:200,222
+        pre = getattr(self, "_A_pre", None)                                             # set by `precomputed_A`
+        A = pre[suffix] if pre is not None else -torch.exp(A_log.float())               # bimamba.py:200,222
         return (g("conv1d").weight, g("conv1d").bias, g("x_proj").weight, g("dt_proj").weight, A, Dk.float(),
                 g("dt_proj").bias.float())
 
@@ -162,6 +164,59 @@ class _MambaBase(nn.Module):
                 conv_state.zero_()
                 ssm_state.zero_()
         return conv_state, ssm_state
+
+
+class _NegExpMany(torch.autograd.Function):
+    """A_i = -exp(A_log_i) for a list of parameters with multi-tensor kernels: two launches forward, one backward
+    (dA_log_i = dA_i * A_i) instead of four small elementwise kernels per direction and layer."""
+
+    @staticmethod
+    def forward(ctx, *a_logs):
+        outs = torch._foreach_exp([a.float() for a in a_logs])
+        torch._foreach_neg_(outs)
+        ctx.save_for_backward(*outs)
+        ctx.set_materialize_grads(False)        # blocks that did not run in this forward get no gradient
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        As = ctx.saved_tensors
+        idx = [i for i, g in enumerate(grads) if g is not None]
+        prods = torch._foreach_mul([grads[i] for i in idx], [As[i] for i in idx]) if idx else []
+        out = [None] * len(As)
+        for i, pr in zip(idx, prods):
+            out[i] = pr
+        return tuple(out)
+
+
+class precomputed_A:
+    """Context manager for a model forward: evaluates ``A = -exp(A_log)`` (reference bimamba.py:200,222) of every Mamba
+    block under ``root`` at once and hands the results to the blocks for the duration of the forward pass.  The values
+    are recomputed from the current parameters on every entry, so this is an evaluation strategy only."""
+
+    def __init__(self, root):
+        self.mods = [m for m in root.modules() if isinstance(m, _MambaBase)]
+
+    def __enter__(self):
+        logs, slots = [], []
+        for m in self.mods:
+            logs.append(m.A_log)
+            slots.append((m, ""))
+            if hasattr(m, "A_b_log"):
+                logs.append(m.A_b_log)
+                slots.append((m, "_b"))
+        if logs and logs[0].is_cuda and os.environ.get("CM_NO_BATCHED_A") is None:
+            As = _NegExpMany.apply(*logs)
+            for m in self.mods:
+                m._A_pre = {}
+            for (m, suffix), A in zip(slots, As):
+                m._A_pre[suffix] = A
+        return self
+
+    def __exit__(self, *exc):
+        for m in self.mods:
+            m._A_pre = None
+        return False
 
 
 class Mamba(_MambaBase):

@@ -22,6 +22,7 @@ import os
 
 from .layernorm import layer_norm_leaky_relu
 from .linear import BiasGradLinear, ParamCache, set_param_cache
+from .bimamba import precomputed_A
 from .conmamba import ConmambaEncoder, MambaDecoder
 from .fbank import Fbank
 
@@ -148,7 +149,8 @@ class ConMambaCTC(nn.Module):
     def forward(self, wavs, wav_lens=None):
         """wavs: (B, n_samples) -> log-probs (B, L, output_neurons)"""
         self._refresh_param_cache()
-        enc = self.encode(self.features(wavs, wav_lens))
+        with precomputed_A(self):
+            enc = self.encode(self.features(wavs, wav_lens))
         return F.log_softmax(self.ctc_lin(enc), dim=-1)
 
 
@@ -218,10 +220,11 @@ class ConMambaS2S(ConMambaCTC):
     def forward(self, wavs, tokens_bos, wav_lens=None):
         """wavs (B, n_samples), tokens_bos (B, S) -> (p_ctc (B, L, V), p_seq (B, S, V)) log-probabilities"""
         self._refresh_param_cache()
-        enc = self.encode(self.features(wavs, wav_lens))
-        tgt = self.custom_tgt_module(tokens_bos)
-        tgt = tgt + self.positional_encoding_decoder(tgt)
-        dec, _, _ = self.decoder(tgt, enc)
+        with precomputed_A(self):
+            enc = self.encode(self.features(wavs, wav_lens))
+            tgt = self.custom_tgt_module(tokens_bos)
+            tgt = tgt + self.positional_encoding_decoder(tgt)
+            dec, _, _ = self.decoder(tgt, enc)
         return F.log_softmax(self.ctc_lin(enc), dim=-1), F.log_softmax(self.seq_lin(dec), dim=-1)
 
 

@@ -237,3 +237,21 @@ def test_decode_api_mirrors_the_reference_and_refuses_cpu():
         m.step(torch.zeros(3, 1, 16), cs, ss)
     with pytest.raises(AssertionError):
         UniMamba(d_model=16)._get_states_from_cache(IP(), 1)       # layer_idx is required, as in the reference
+
+
+def test_batched_neg_exp_matches_the_per_block_evaluation():
+    """precomputed_A evaluates A = -exp(A_log) (reference bimamba.py:200,222) for all blocks with multi-tensor kernels;
+    values and gradients must equal the per-block expression, unused outputs get no gradient."""
+    import torch
+    from mamba_asr_b200.bimamba import _NegExpMany
+    torch.manual_seed(0)
+    logs = [torch.randn(6, 16, requires_grad=True) for _ in range(3)]
+    outs = _NegExpMany.apply(*logs)
+    (outs[0].sum() * 2 + outs[2].pow(2).sum()).backward()
+    refs = [x.detach().clone().requires_grad_(True) for x in logs]
+    ro = [-torch.exp(x) for x in refs]
+    (ro[0].sum() * 2 + ro[2].pow(2).sum()).backward()
+    for o, r in zip(outs, ro):
+        assert torch.equal(o, r)
+    assert torch.allclose(logs[0].grad, refs[0].grad) and torch.allclose(logs[2].grad, refs[2].grad)
+    assert logs[1].grad is None

@@ -11,6 +11,8 @@ The GEMMs stay cuBLAS (forward, dx, dW - what torch's own Linear backward launch
 ``nn.Linear`` (same parameters, same ``state_dict``); on CPU tensors it is plain ``F.linear`` (the CPU reference arm never
 sees the kernels).
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -59,6 +61,35 @@ def cached_param(p, dtype):
     return _ACTIVE.get(p, dtype) if (_ACTIVE is not None and p is not None) else None
 
 
+def _wgrad_nsplit(rows, M, N):
+    """Row blocks for the split-K weight-gradient GEMM (measured on B200, tools/prof_wgrad.py, profiles/r01_wgrad_variants_
+    session4.txt): as ONE GEMM with K = batch * L in the tens of thousands cuBLAS runs these shapes at 110-440 TFLOP/s
+    (30.7 us for 12032 x 1024 x 144); a bmm over 4-16 row blocks plus the fixed-order sum of the fp32 partial products takes
+    19.5 us, and is the more accurate evaluation."""
+    if os.environ.get("CM_NO_WGRAD_SPLIT") is not None:
+        return 1
+    if rows >= 24000 and M * N <= (1 << 17):
+        want = 16
+    elif rows * max(M, N) <= (1 << 24) and M * N >= (1 << 17):
+        want = 4
+    else:
+        want = 8
+    while want > 1 and rows % want != 0:
+        want //= 2
+    return want if rows >= 4096 else 1
+
+
+def _wgrad_f32(dy2, x2):
+    """dy2^T @ x2 with fp32 output for 16-bit operands (rows, M) and (rows, N): deterministic split-K (see above)."""
+    rows = dy2.shape[0]
+    ns = _wgrad_nsplit(rows, dy2.shape[1], x2.shape[1])
+    if ns <= 1:
+        return torch.mm(dy2.t(), x2, out_dtype=torch.float32)          # fp32 straight out of the GEMM: no cast kernel
+    d3 = dy2.reshape(ns, rows // ns, dy2.shape[1])
+    x3 = x2.reshape(ns, rows // ns, x2.shape[1])
+    return torch.bmm(d3.transpose(1, 2), x3, out_dtype=torch.float32).sum(0)
+
+
 class _LinearFn(torch.autograd.Function):
     """y = x @ w^T + b with explicit low-precision operands: ``w_lp`` / ``b_lp`` are the forward operands (cached copies
     or ``weight`` / ``bias`` themselves), gradients are returned for ``weight`` / ``bias`` in THEIR dtype."""
@@ -80,7 +111,7 @@ class _LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             x2 = x.reshape(-1, x.shape[-1])
             if ctx.w_dtype == torch.float32 and dy2.dtype != torch.float32:
-                dw = torch.mm(dy2.t(), x2, out_dtype=torch.float32)      # fp32 straight out of the GEMM: no cast kernel
+                dw = _wgrad_f32(dy2, x2)
             else:
                 dw = torch.mm(dy2.t(), x2).to(ctx.w_dtype)
         if ctx.b_dtype is not None and ctx.needs_input_grad[2]:

@@ -346,11 +346,13 @@ def test_convolution_module_kernel_path_equals_reference_op_chain(causal, monkey
     assert_close(y_k, y_t, what="conv module")
 
 
-@pytest.mark.parametrize("shape", [(3, 501, 256, 1024), (2, 37, 144, 576), (1, 5, 32, 10), (4, 9, 64, 11)])
+@pytest.mark.parametrize("shape", [(3, 501, 256, 1024), (2, 37, 144, 576), (1, 5, 32, 10), (4, 9, 64, 11),
+                                   (32, 376, 144, 1024), (32, 376, 1024, 144), (64, 501, 256, 256), (5, 1002, 64, 48)])
 @pytest.mark.parametrize("autocast", [False, True])
 def test_bias_grad_linear_matches_nn_linear(shape, autocast):
     """BiasGradLinear (cm_colsum for db, cuBLAS for the rest) against nn.Linear: output and every gradient, fp32 and
-    under bf16 autocast; odd output widths take torch's own reduction."""
+    under bf16 autocast; odd output widths take torch's own reduction; the long-row shapes take the split-K weight
+    gradient (4, 8, 16 row blocks and a row count that only divides by 2)."""
     from mamba_asr_b200.linear import BiasGradLinear
     Bt, L, cin, cout = shape
     torch.manual_seed(5)

@@ -117,9 +117,12 @@ def _conv_body(self, normed, final_dropout=True):
     out = F.glu(_linear(normed, pw.weight.squeeze(-1), pw.bias), dim=-1)
     out = depthwise_conv1d(out, self.conv.weight, self.conv.bias, pad_left=self.padding)
     norm, act = self.after_conv[0], self.after_conv[1]
-    if (type(act) is nn.GELU and act.approximate == "none" and norm.normalized_shape[0] % 4 == 0
-            and os.environ.get("CM_NO_FUSE_LN_GELU") is None):
-        out = layer_norm_act(out, norm, "gelu")                       # LayerNorm -> GELU: one sm_100a kernel each way
+    # LayerNorm -> GELU as one cm_ln_act kernel each way is opt-in (CM_FUSE_LN_GELU=1): at these narrow rows (144 / 256
+    # columns, one warp per row) it measured 16.1 vs 12.9 us backward at 12032 x 144 and 36.6 vs 36.0 us at 32064 x 256
+    # against cm_layernorm + torch's GELU (gpurun_out/s4d_step_*.log) - the wide front-end rows are where it pays
+    if (os.environ.get("CM_FUSE_LN_GELU") is not None and type(act) is nn.GELU and act.approximate == "none"
+            and norm.normalized_shape[0] % 4 == 0):
+        out = layer_norm_act(out, norm, "gelu")
     else:
         out = act(norm(out))
     out = self.after_conv[2](out)

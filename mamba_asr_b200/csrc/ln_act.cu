@@ -311,28 +311,44 @@ static bool pre_bias_ok(const cm_ln_act_args* a) {
 }
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <typename T>
-static int fwd_t(const cm_ln_act_args* a, cudaStream_t st) {
-  const int64_t nblk = row_blocks(a->rows, a->cols), cap = (int64_t)sm_count() * 8;
-  const int grid = (int)(nblk < cap ? nblk : cap);
-#define CM_LNA_FWD(G, ACT)                                                                                                  \
-  ln_act_fwd_kernel<T, G, ACT><<<grid, kThreads, 0, st>>>(static_cast<const T*>(a->x), static_cast<T*>(a->y), a->gamma,       \
-                                                          a->beta, a->pre_bias, a->pre_bias_n, a->mean, a->rstd, a->rows,   \
-                                                          a->cols, a->eps, a->slope)
-#define CM_LNA_FWD_G(G)                                                         \
-  do {                                                                          \
-    if (a->act == CM_LN_ACT_GELU) CM_LNA_FWD(G, CM_LN_ACT_GELU);                \
-    else CM_LNA_FWD(G, CM_LN_ACT_LEAKY_RELU);                                   \
-  } while (0)
-  switch (group_size(a->cols)) {
-    case 32: CM_LNA_FWD_G(32); break;
-    case 64: CM_LNA_FWD_G(64); break;
-    default: CM_LNA_FWD_G(128); break;
+// persistent grid = one wave: SMs x resident CTAs of this instantiation (ncu on the first version: 1184 CTAs at 5 resident
+// per SM = 1.6 waves, profiles/r01_ln_act_fwd_cfg3_ncu.txt)
+template <typename KernelT>
+static int one_wave(KernelT kern, int* cached) {
+  if (*cached == 0) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0) != cudaSuccess || per_sm <= 0) {
+      (void)cudaGetLastError();
+      per_sm = 4;
+    }
+    *cached = per_sm * sm_count();
   }
-#undef CM_LNA_FWD_G
-#undef CM_LNA_FWD
+  return *cached;
+}
+
+template <typename T, int G, int ACT>
+static int fwd_launch(const cm_ln_act_args* a, cudaStream_t st) {
+  static int wave = 0;   // idempotent; a benign race computes it twice
+  auto kern = ln_act_fwd_kernel<T, G, ACT>;
+  const int64_t nblk = row_blocks(a->rows, a->cols), cap = one_wave(kern, &wave);
+  const int grid = (int)(nblk < cap ? nblk : cap);
+  kern<<<grid, kThreads, 0, st>>>(static_cast<const T*>(a->x), static_cast<T*>(a->y), a->gamma, a->beta, a->pre_bias,
+                                  a->pre_bias_n, a->mean, a->rstd, a->rows, a->cols, a->eps, a->slope);
   CM_LAUNCH_CHECK();
   return 0;
+}
+
+template <typename T>
+static int fwd_t(const cm_ln_act_args* a, cudaStream_t st) {
+#define CM_LNA_FWD_G(G)                                                                        \
+  return a->act == CM_LN_ACT_GELU ? fwd_launch<T, G, CM_LN_ACT_GELU>(a, st)                    \
+                                  : fwd_launch<T, G, CM_LN_ACT_LEAKY_RELU>(a, st)
+  switch (group_size(a->cols)) {
+    case 32: CM_LNA_FWD_G(32);
+    case 64: CM_LNA_FWD_G(64);
+    default: CM_LNA_FWD_G(128);
+  }
+#undef CM_LNA_FWD_G
 }
 
 template <typename T>

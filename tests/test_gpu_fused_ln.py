@@ -299,7 +299,8 @@ def test_conv_front_end_same_with_and_without_the_fused_norm(autocast, monkeypat
 @pytest.mark.parametrize("autocast", [False, True])
 def test_convolution_module_same_with_and_without_the_fused_norm_gelu(autocast, monkeypatch):
     """ConvolutionModule (reference modules/Conmamba.py:182-454) with LayerNorm -> GELU after the depthwise conv on
-    cm_ln_act_* against the separate cm_layernorm + torch GELU evaluation: output and every parameter gradient."""
+    cm_ln_act_* (opt-in, CM_FUSE_LN_GELU=1) against the default cm_layernorm + torch GELU evaluation: output and every
+    parameter gradient."""
     from mamba_asr_b200.conmamba import ConvolutionModule
     torch.manual_seed(5)
     m = ConvolutionModule(144, kernel_size=31, activation=torch.nn.GELU, dropout=0.0).cuda()
@@ -308,9 +309,9 @@ def test_convolution_module_same_with_and_without_the_fused_norm_gelu(autocast, 
     res = []
     for fused in (True, False):
         if fused:
-            monkeypatch.delenv("CM_NO_FUSE_LN_GELU", raising=False)
+            monkeypatch.setenv("CM_FUSE_LN_GELU", "1")
         else:
-            monkeypatch.setenv("CM_NO_FUSE_LN_GELU", "1")
+            monkeypatch.delenv("CM_FUSE_LN_GELU", raising=False)
         m.zero_grad()
         xg = x.clone().requires_grad_(True)
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):

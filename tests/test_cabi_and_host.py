@@ -255,3 +255,50 @@ def test_batched_neg_exp_matches_the_per_block_evaluation():
         assert torch.equal(o, r)
     assert torch.allclose(logs[0].grad, refs[0].grad) and torch.allclose(logs[2].grad, refs[2].grad)
     assert logs[1].grad is None
+
+
+def test_ln_act_entry_points_validate_arguments_without_a_gpu(lib):
+    """cm_ln_act_* (include/conmamba_b200.h): null / empty -> BAD_ARG; rows outside the envelope (not a multiple of 4,
+    > 2560 columns, a pre-norm bias whose period does not divide the row, unaligned base) -> UNSUPPORTED; partial-row
+    count = one wave of the backward kernel, at least 1."""
+    from mamba_asr_b200 import _cabi
+    a = _cabi.LnActArgs()
+    assert lib.cm_ln_act_fwd(ctypes.byref(a), None) == _cabi.CM_ERR_BAD_ARG
+    assert lib.cm_ln_act_bwd(ctypes.byref(a), None) == _cabi.CM_ERR_BAD_ARG
+    a.rows, a.cols, a.dtype, a.act = 4, 640, _cabi.CM_BF16, _cabi.CM_LN_ACT_LEAKY_RELU
+    a.x = a.y = a.gamma = a.beta = a.mean = a.rstd = 4096        # non-null, 16-byte aligned (never dereferenced here)
+    a.act = 7
+    assert lib.cm_ln_act_fwd(ctypes.byref(a), None) == _cabi.CM_ERR_BAD_ARG          # unknown activation
+    a.act = _cabi.CM_LN_ACT_GELU
+    for bad_cols in (6, 2564, 4096):
+        a.cols = bad_cols
+        assert lib.cm_ln_act_fwd(ctypes.byref(a), None) == _cabi.CM_ERR_UNSUPPORTED
+    a.cols = 640
+    a.pre_bias, a.pre_bias_n = 4096, 48                            # 640 % 48 != 0
+    assert lib.cm_ln_act_fwd(ctypes.byref(a), None) == _cabi.CM_ERR_UNSUPPORTED
+    a.pre_bias_n = 6                                               # not a multiple of 4
+    assert lib.cm_ln_act_fwd(ctypes.byref(a), None) == _cabi.CM_ERR_UNSUPPORTED
+    a.pre_bias, a.pre_bias_n = None, 0
+    a.x = 4098                                                     # unaligned base
+    assert lib.cm_ln_act_fwd(ctypes.byref(a), None) == _cabi.CM_ERR_UNSUPPORTED
+    a.x = 4096
+    assert lib.cm_ln_act_bwd(ctypes.byref(a), None) == _cabi.CM_ERR_BAD_ARG          # dy / dx / partials missing
+    assert lib.cm_ln_act_num_part(0, 640) == 1
+    assert lib.cm_ln_act_num_part(10, 640) == 3                    # 4 rows per CTA at <= 640 columns
+    assert lib.cm_ln_act_num_part(10, 2560) == 10                  # one row per CTA at 2560 columns
+    assert lib.cm_ln_act_num_part(10 ** 6, 2560) == 148 * 4
+
+
+def test_split_k_weight_gradient_row_blocks(monkeypatch):
+    """linear._wgrad_nsplit: the measured choices at the BASELINE shapes (profiles/r01_wgrad_variants_session4.txt), row
+    counts that do not divide fall back to a smaller power of two, short inputs and the A/B switch to one GEMM."""
+    from mamba_asr_b200.linear import _wgrad_nsplit
+    monkeypatch.delenv("CM_NO_WGRAD_SPLIT", raising=False)
+    assert _wgrad_nsplit(12032, 1024, 144) == 4 and _wgrad_nsplit(12032, 144, 1024) == 4      # small FFN
+    assert _wgrad_nsplit(12032, 576, 144) == 8 and _wgrad_nsplit(12032, 144, 144) == 8
+    assert _wgrad_nsplit(32064, 1024, 256) == 8 and _wgrad_nsplit(32064, 256, 1024) == 8      # large FFN
+    assert _wgrad_nsplit(32064, 256, 512) == 16 and _wgrad_nsplit(32064, 256, 256) == 16
+    assert _wgrad_nsplit(5010, 64, 48) == 2                        # 5010 = 2 * 2505
+    assert _wgrad_nsplit(5011, 64, 48) == 1 and _wgrad_nsplit(1503, 256, 1024) == 1
+    monkeypatch.setenv("CM_NO_WGRAD_SPLIT", "1")
+    assert _wgrad_nsplit(12032, 1024, 144) == 1

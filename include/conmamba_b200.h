@@ -371,10 +371,10 @@ int cm_colsum_num_part(int64_t rows);
 int cm_colsum(const void* x, int64_t rows, int32_t cols, int64_t row_stride, int32_t dtype, float* part, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
- * Wide-row LayerNorm + LeakyReLU in one pass (the two conv blocks of the reference's
- * ConvolutionFrontEnd, hparams/CTC/conmamba_large.yaml:187-199 - conv 3x3 stride 2 -> LayerNorm([F', C]) -> LeakyReLU;
- * rows of F'*C = 2560 and 640 elements at the BASELINE shapes).
- * and the LayerNorm -> activation after the depthwise conv of the ConMamba convolution module, modules/Conmamba.py:292-301).
+ * LayerNorm + activation in one pass: the two conv blocks of the reference's
+ * ConvolutionFrontEnd (hparams/CTC/conmamba_large.yaml:187-194: conv 3x3 stride 2 -> LayerNorm([F', C]) -> LeakyReLU; rows
+ * of F'*C = 2560 and 640 elements at the BASELINE shapes, the conv bias folded in as pre_bias), and the LayerNorm ->
+ * activation after the depthwise conv of the ConMamba convolution module (modules/Conmamba.py:297-303).
  *   x' = x + pre_bias[col % pre_bias_n]                                   (pre_bias NULL: x' = x)
  *   forward : y = act((x' - mean) * rstd * gamma + beta)                  statistics of x' in fp32
  *             act = LeakyReLU(slope) (slope = 1: plain LayerNorm) or exact (erf) GELU

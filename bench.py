@@ -1,21 +1,27 @@
 #!/usr/bin/env python
-"""bench.py - ConMamba encoder audio-seconds / second (fwd+bwd) on N B200s, with the scan-kernel roofline.
+"""bench.py - ConMamba encoder audio-seconds / second on N B200s, with the scan-kernel roofline.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--sweep-L]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-Workload at N = 1 (BASELINE.json configs[1]): ConMamba-small CTC encoder, forward + backward, bf16 autocast,
-batch 32 x 15 s of synthetic 16 kHz audio per GPU; weak scaling (per-GPU batch fixed, DDP gradient all-reduce
-over NCCL at N > 1).  One step = Fbank -> normalise -> conv front-end -> 12 ConMamba layers -> CTC loss -> backward.
+Default workload (BASELINE.json configs[2], the configuration the metric and the target are quoted on): ConMamba-large
+CTC training step, bf16 autocast, batch 64 x 20 s of synthetic 16 kHz audio PER GPU; weak scaling (DDP gradient all-reduce
+over NCCL at N > 1).  One step = Fbank -> normalise -> conv front-end -> 18 ConMamba layers -> CTC loss -> backward ->
+gradient clipping + AdamW + Noam learning rate (hparams/CTC/conmamba_large.yaml:91-99, 244-252; train_CTC.py:716-717).
+Other workloads (--workload): configs[0] forward only (8 x 10 s, small), configs[1] (small, 32 x 15 s, fwd+bwd),
+configs[3] (S2S large), configs[4] (4 x 300 s inference; --sweep-L adds the kernel-level scan sweep over L = 1k..30k).
 
 Printed JSON line (rank 0):
   value     audio-s/s of the whole job, inputs already resident in HBM, K steps timed with CUDA events between
             barrier + synchronize, max over ranks
   e2e       the same step driven from pinned HOST audio: H2D copy of every step's waveforms (issued on a copy stream,
             double-buffered, overlapping the previous step) and D2H read of every step's loss inside the timed region
-  roofline  the dominant hand-written kernel (the selective scan): algorithmic bytes / launch
-            divided by its CUDA-event duration measured in the timed steps, against MEASURED_PEAKS.json
+  roofline  the dominant hand-written kernel (the selective scan): algorithmic bytes / launch divided by
+            its average CUDA-event duration, against MEASURED_PEAKS.json.  The timed steps are CUDA-graph replays, whose
+            kernels cannot carry events: the events come from 3 EAGER launches of the same step run right after the
+            timed region (`config.roofline_timing` says so in the line itself); launches are grouped by (entry point,
+            shape) so a model with several scan shapes (S2S) still quotes one kernel at one shape
   cpu_baseline  the reference CPU path (oracle port of selective_scan_ref + torch conv + Fbank inside the same
             module tree) on the host cores, bounded sample
 ``--impl reference`` times that CPU path alone (rank 0 only).
@@ -38,19 +44,28 @@ import torch.nn.functional as F  # noqa: E402
 METRIC = "ConMamba encoder audio-sec/sec (fwd+bwd)"
 UNIT = "audio-sec/sec"
 
+# mode: "train" = forward + loss + backward + optimizer ; "fwd" = forward + loss under no_grad (evaluation / inference)
 WORKLOADS = {
-    # BASELINE.json configs[1] - the configuration the metric is quoted on for one GPU
-    "conmamba_small_ctc_fwdbwd_b32x15s": dict(model="conmamba_small_ctc", batch=32, seconds=15.0),
-    # BASELINE.json configs[2] shape (encoder fwd+bwd of the large CTC model, 64 x 20 s per GPU)
-    "conmamba_large_ctc_fwdbwd_b64x20s": dict(model="conmamba_large_ctc", batch=64, seconds=20.0),
+    # BASELINE.json configs[0]: ConMamba-small CTC encoder forward, 8 x 10 s (the reference's own CPU-runnable case)
+    "conmamba_small_ctc_fwd_b8x10s": dict(model="conmamba_small_ctc", batch=8, seconds=10.0, mode="fwd"),
+    # BASELINE.json configs[1]: ConMamba-small CTC encoder fwd+bwd, 32 x 15 s on one GPU
+    "conmamba_small_ctc_fwdbwd_b32x15s": dict(model="conmamba_small_ctc", batch=32, seconds=15.0, mode="train"),
+    # BASELINE.json configs[2] - the configuration the metric and the target are quoted on: ConMamba-large CTC training
+    # step, 64 x 20 s per GPU, data-parallel at 1/2/4/8 GPUs
+    "conmamba_large_ctc_fwdbwd_b64x20s": dict(model="conmamba_large_ctc", batch=64, seconds=20.0, mode="train"),
     # BASELINE.json configs[3] shape: ConMambaMamba-large S2S (12 ConMamba encoder + 6 Mamba decoder layers, d_model 512,
     # vocab 5000) training step, 64 x 20 s per GPU, 3 target tokens per audio second
-    "conmambamamba_large_s2s_fwdbwd_b64x20s": dict(model="conmambamamba_large_s2s", batch=64, seconds=20.0),
+    "conmambamamba_large_s2s_fwdbwd_b64x20s": dict(model="conmambamamba_large_s2s", batch=64, seconds=20.0, mode="train"),
+    # BASELINE.json configs[4]: long-form ConMamba-large encoder inference, 4 x 300 s (7501 encoder frames)
+    "conmamba_large_ctc_infer_b4x300s": dict(model="conmamba_large_ctc", batch=4, seconds=300.0, mode="fwd"),
     # small smoke shapes for debugging
-    "tiny": dict(model="conmamba_small_ctc", batch=2, seconds=2.0),
-    "tiny_s2s": dict(model="conmambamamba_large_s2s", batch=2, seconds=2.0),
+    "tiny": dict(model="conmamba_small_ctc", batch=2, seconds=2.0, mode="train"),
+    "tiny_fwd": dict(model="conmamba_small_ctc", batch=2, seconds=2.0, mode="fwd"),
+    "tiny_s2s": dict(model="conmambamamba_large_s2s", batch=2, seconds=2.0, mode="train"),
 }
-DEFAULT_WORKLOAD = "conmamba_small_ctc_fwdbwd_b32x15s"
+DEFAULT_WORKLOAD = "conmamba_large_ctc_fwdbwd_b64x20s"
+# optimizer of the training workloads (hparams/CTC/conmamba_large.yaml:91-99, 244-252): AdamW, Noam schedule, clipping
+OPT = dict(lr=1e-3, betas=(0.9, 0.98), eps=1e-9, weight_decay=5e-4, max_grad_norm=5.0, n_warmup_steps=7500)
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -144,10 +159,11 @@ def ctc_loss_of(logp, targets):
                       zero_infinity=True)
 
 
-def step_loss(model, wav, targets, autocast):
+def step_loss(model, wav, targets, autocast, is_s2s=None):
     """CTC recipe (train_CTC.py:285-302).  S2S recipe (train_S2S.py:344-361, 518-530): ctc_weight * CTC on the encoder +
     (1 - ctc_weight) * label-smoothed KL on the decoder, decoder input = <bos> + targets, decoder target = targets + <eos>."""
-    is_s2s = hasattr(model, "decoder")
+    if is_s2s is None:
+        is_s2s = hasattr(model, "decoder")
     with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
         if is_s2s:
             bos = torch.cat([torch.ones_like(targets[:, :1]), targets], dim=1)
@@ -163,10 +179,31 @@ def step_loss(model, wav, targets, autocast):
     return loss
 
 
-def ctc_step(model, wav, targets, autocast):
-    loss = step_loss(model, wav, targets, autocast)
+def ctc_step(model, wav, targets, autocast, train=True, is_s2s=None):
+    if not train:                       # evaluation / inference workloads: forward + loss, no gradients
+        with torch.no_grad():
+            return step_loss(model, wav, targets, autocast, is_s2s)
+    loss = step_loss(model, wav, targets, autocast, is_s2s)
     loss.backward()
     return loss
+
+
+def config_block(workload, world):
+    """The part of `config` that names the workload - identical in the GPU arm and in the reference arm."""
+    from mamba_asr_b200.encoder import CONFIGS
+    wl = WORKLOADS[workload]
+    cfg = CONFIGS[wl["model"]]
+    T = 1 + int(round(16000 * wl["seconds"])) // 160
+    L = (((T - 1) // 2 + 1) - 1) // 2 + 1
+    layers = "%d" % cfg["num_layers"] + ("+%d decoder" % cfg["num_decoder_layers"] if "num_decoder_layers" in cfg else "")
+    if wl["mode"] == "train":
+        step = ("Fbank+norm+CNN+%s ConMamba layers+loss, forward+backward, bf16 autocast, clip %.1f + AdamW + Noam"
+                % (layers, OPT["max_grad_norm"]))
+    else:
+        step = "Fbank+norm+CNN+%s ConMamba layers+loss, forward only (no_grad), bf16 autocast" % layers
+    return {"workload": workload, "per_gpu_batch": wl["batch"], "audio_seconds": wl["seconds"], "encoder_frames": L,
+            "d_inner": 2 * cfg["d_model"], "layers": cfg["num_layers"], "mode": wl["mode"], "step": step,
+            "parallelism": ("dp%d (utterance sharding; gradient all-reduce over NCCL)" % world) if world > 1 else "single GPU"}
 
 
 def scan_algorithmic_bytes(batch, L, D, N, s, ndir, bwd):
@@ -193,14 +230,24 @@ def cpu_reference_run(workload, steps, warmup, budget_s=200.0):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     model = to_cpu_reference(build_model(wl["model"]), cfg["n_fft"], cfg["n_mels"], cfg["win_length"])
-    model.train()
+    train = wl["mode"] == "train"
+    model.train(train)
     seconds = wl["seconds"]
+    opt = None
+    if train:
+        from mamba_asr_b200.trainer import TrainStep
+        opt = TrainStep(model, **OPT)
 
     def one(sec):
         wav, targets = make_batch(cfg, 1, sec, 1234, "cpu", cfg["output_neurons"])
         t0 = time.perf_counter()
-        model.zero_grad(set_to_none=True)
-        step_loss(model, wav, targets, False).backward()
+        if train:
+            model.zero_grad(set_to_none=True)
+            step_loss(model, wav, targets, False).backward()
+            opt.step()
+        else:
+            with torch.no_grad():
+                step_loss(model, wav, targets, False)
         return time.perf_counter() - t0
 
     # pick the largest sample (1 utterance of the workload's duration, else a shorter cut) that fits the budget
@@ -216,10 +263,50 @@ def cpu_reference_run(workload, steps, warmup, budget_s=200.0):
     dt = sum(times)
     value = sec * steps / dt
     desc = {"kind": "port", "cores": threads, "value": value, "unit": UNIT,
-            "sample": "1 utterance x %.2f s of the %s workload per step (oracle port of selective_scan_ref + torch conv + "
-                      "Fbank inside the same 12-layer module tree, fwd+bwd, fp32, %d steps, %.2f s/step)"
-                      % (sec, workload, steps, dt / steps)}
+            "sample": "1 utterance x %.2f s of the %s workload per step (the workload's batch is %d such utterances; audio-s/s "
+                      "does not depend on the batch on the CPU path): oracle port of selective_scan_ref + torch conv + Fbank "
+                      "inside the same %d-layer module tree, %s, fp32, %d steps, %.2f s/step"
+                      % (sec, workload, wl["batch"], cfg["num_layers"],
+                         "fwd+bwd+optimizer" if train else "forward only", steps, dt / steps)}
     return value, dt / steps * 1e3, desc
+
+
+# ------------------------------------------------------------------------------------------------ scan sweep (config 5)
+def scan_length_sweep(dev, peak, lengths=(1024, 2048, 4096, 8192, 16384, 30001), iters=10):
+    """BASELINE.json configs[4] kernel-level part: the fused bidirectional scan forward (inference launch: no
+    checkpoints, chunk-parallel over time windows when that helps) at batch 4 x D 512 for L = 1k .. 30k, bf16 and fp32;
+    algorithmic GB/s against the measured HBM peak.  L2 is flushed before every launch."""
+    from mamba_asr_b200 import kernels as K
+    Bt, D, N = 4, 512, 16
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    out = []
+    for dt, s in ((torch.bfloat16, 2), (torch.float32, 4)):
+        for L in lengths:
+            g = torch.Generator(device=dev).manual_seed(L)
+            rn = lambda *sh: torch.randn(*sh, device=dev, generator=g)
+            cl = lambda: rn(Bt, L, D).to(dt).transpose(1, 2)
+            z = cl()
+            dirs = []
+            for rev in (False, True):
+                xdbl = rn(Bt, L, 2 * N + 16).to(dt)
+                dirs.append(dict(u=cl(), delta=(0.5 * rn(Bt, L, D)).to(dt).transpose(1, 2), A=-torch.exp(0.3 * rn(D, N)),
+                                 B=xdbl[..., :N].transpose(1, 2), C=xdbl[..., N:2 * N].transpose(1, 2),
+                                 D=torch.ones(D, device=dev), delta_bias=torch.full((D,), -4.0, device=dev), reverse=rev))
+            f = lambda: K.scan_forward(dirs, z=z, out_scale=0.5, delta_softplus=True)
+            for _ in range(3):
+                f()
+            ts = []
+            for _ in range(iters):
+                flush.zero_()
+                K.start_timing()
+                f()
+                ts += K.stop_timing()["cm_scan_fwd"]
+            ts.sort()
+            byts = scan_algorithmic_bytes(Bt, L, D, N, s, 2, False)
+            med = ts[len(ts) // 2]
+            out.append({"dtype": "bf16" if s == 2 else "f32", "L": L, "ms": med, "alg_bytes": byts,
+                        "achieved_gbs": byts / (med * 1e-3) / 1e9, "frac": byts / (med * 1e-3) / 1e9 / peak})
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ main
@@ -235,21 +322,25 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-param-cache", action="store_true", help="per-use autocast-style parameter casts (A/B)")
+    ap.add_argument("--no-optimizer", action="store_true", help="training workloads: stop after backward (A/B)")
+    ap.add_argument("--sweep-L", action="store_true", help="add the kernel-level scan sweep over L = 1k..30k (configs[4]) "
+                                                           "to the JSON line as `scan_sweep`")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = WORKLOADS[args.workload]
+    train = wl["mode"] == "train"
 
     if args.impl == "reference":
         if rank != 0:
             return 0
         value, ms, desc = cpu_reference_run(args.workload, args.steps, max(1, args.warmup))
-        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        line = {"impl": "reference", "metric": METRIC if train else METRIC.replace("(fwd+bwd)", "(fwd)"), "value": value, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": args.workload, "note": "reference CPU path on host cores, bounded sample"},
+                "config": config_block(args.workload, max(1, args.gpus)),
                 "cpu_baseline": desc,
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -269,18 +360,20 @@ def main():
 
     from mamba_asr_b200 import kernels as K
     from mamba_asr_b200.encoder import CONFIGS, build_model
+    from mamba_asr_b200.trainer import TrainStep
     cfg = CONFIGS[wl["model"]]
     model = build_model(wl["model"]).to(dev)
-    model.train()
+    model.train(train)
     if not args.no_param_cache:
         model.enable_param_cache()          # bf16 parameter copies refreshed by one multi-tensor copy per step
     net = model
-    if world > 1:
+    if world > 1 and train:
         from mamba_asr_b200.dist_utils import allreduce_gradients
         for p_ in model.parameters():                          # identical replicas: rank 0's initialisation
             dist.broadcast(p_.data, 0)
     n_params = sum(p.numel() for p in model.parameters())
     is_s2s = hasattr(model, "decoder")
+    opt = TrainStep(model, **OPT) if (train and not args.no_optimizer) else None
 
     batch, seconds = wl["batch"], wl["seconds"]
     wav_h, tgt_h = make_batch(cfg, batch, seconds, cfg["seed"] + rank, dev, cfg["output_neurons"])
@@ -294,45 +387,62 @@ def main():
 
     eager_forward = net.forward      # torch.cuda.make_graphed_callables swaps net.forward for the graph replay
 
+    def finish_step():
+        """what follows backward in a training step: the step's only collective, then the optimizer"""
+        if world > 1:
+            allreduce_gradients(model.parameters(), world)     # NCCL over NVLink
+        if opt is not None:
+            opt.step()
+
     def step_eager(w, t):
+        if not train:
+            return ctc_step(net, w, t, True, train=False)
         model.zero_grad(set_to_none=True)
         cur, net.forward = net.forward, eager_forward
         try:
             loss = ctc_step(net, w, t, True)
         finally:
             net.forward = cur
-        if world > 1:
-            allreduce_gradients(model.parameters(), world)     # NCCL over NVLink: the step's only collective
+        finish_step()
         return loss
 
-    # One CUDA graph for forward + CTC loss + backward (the step is host-launch-bound otherwise); eager fallback if
-    # the capture is refused (e.g. a collective that cannot be captured).
+    # CUDA graphs: the eager step is host-launch-bound.  Training: forward graph + backward graph of the whole model
+    # (torch.cuda.make_graphed_callables); the CTC loss between them stays eager because its length tensors live on the
+    # host.  Forward-only workloads: one graph of the model forward.  Eager fallback if the capture is refused.
     graph_note = "eager launches"
     step_fn = step_eager
     launches_per_step = None
     if not args.no_graph:
         try:
-            # forward graph + backward graph of the whole model (wav -> log-probs); the CTC loss between them stays
-            # eager because its length tensors live on the host
-            from mamba_asr_b200.graphs import graph_module
+            from mamba_asr_b200.graphs import graph_forward, graph_module
             l0 = K.LAUNCHES
-            # capture under the same autocast policy the step runs with (weight-cast caching off: the cached casts of a
-            # warm-up iteration would otherwise be baked out of the graph)
-            with torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False):
-                sample = (wav_d,) if not is_s2s else (wav_d, torch.cat([torch.ones_like(tgt_d[:, :1]), tgt_d], dim=1))
-                gnet = graph_module(net, sample, warmup=3)
-            launches_per_step = (K.LAUNCHES - l0) // 4          # 3 warm-ups + 1 capture
+            sample = (wav_d,) if not is_s2s else (wav_d, torch.cat([torch.ones_like(tgt_d[:, :1]), tgt_d], dim=1))
+            if train:
+                # capture under the same autocast policy the step runs with (weight-cast caching off: the cached casts
+                # of a warm-up iteration would otherwise be baked out of the graph)
+                with torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False):
+                    gnet = graph_module(net, sample, warmup=3)
+                launches_per_step = (K.LAUNCHES - l0) // 4          # 3 warm-ups + 1 capture
 
-            def step_graphed(w, t):
-                model.zero_grad(set_to_none=True)
-                loss = ctc_step(gnet, w, t, True)
-                if world > 1:
-                    allreduce_gradients(model.parameters(), world)
-                return loss
+                def step_graphed(w, t):
+                    model.zero_grad(set_to_none=True)
+                    loss = ctc_step(gnet, w, t, True)
+                    finish_step()
+                    return loss
+                graph_note = "model forward and backward replayed as CUDA graphs (loss, collective and optimizer eager)"
+            else:
+                def fwd_only(*xs):
+                    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False):
+                        return net(*xs)
+                grun = graph_forward(fwd_only, [x.clone() for x in sample], warmup=3)
+                launches_per_step = (K.LAUNCHES - l0) // 4
+
+                def step_graphed(w, t):
+                    return ctc_step(grun, w, t, True, train=False, is_s2s=is_s2s)
+                graph_note = "model forward replayed as one CUDA graph (loss eager)"
             step_graphed(wav_d, tgt_d)
             torch.cuda.synchronize()
             step_fn = step_graphed
-            graph_note = "model forward and backward replayed as CUDA graphs (CTC loss eager in between)"
         except Exception as ex:
             torch.cuda.synchronize()
             graph_note = "eager launches (graph capture refused: %s)" % (repr(ex)[:160])
@@ -366,7 +476,7 @@ def main():
     K.start_timing()
     for _ in range(3):
         step_eager(wav_d, tgt_d)
-    ktimes = K.stop_timing()
+    ktimes = K.stop_timing(by_shape=True)
 
     # ---- end-to-end: pinned host audio -> H2D -> step -> loss D2H, every step ---------------------------------
     # Every step's inputs come from pinned host memory and its loss goes back to the host, all inside the timed region.
@@ -428,33 +538,29 @@ def main():
     e2e_value = audio_s / (e2e_ms / 1e3)
 
     if rank == 0:
-        # ---- roofline of the hand-written kernels (rank 0's launches) ----------------------------------------
+        # ---- roofline of the hand-written kernels (rank 0's launches), grouped by (entry point, launch shape) ----------
         hbm_peak, peak_src = peaks()
-        T = 1 + int(round(16000 * seconds)) // 160
-        L = (((T - 1) // 2 + 1) - 1) // 2 + 1
-        D, N, s = 2 * cfg["d_model"], 16, 2
-        alg = {
-            "cm_scan_fwd": scan_algorithmic_bytes(batch, L, D, N, s, 2, False),
-            "cm_scan_bwd": scan_algorithmic_bytes(batch, L, D, N, s, 2, True),
-            "cm_conv_fwd": conv_algorithmic_bytes(batch, L, D, s, 2, False),
-            "cm_conv_bwd": conv_algorithmic_bytes(batch, L, D, s, 2, True),
-        }
-        kern = {}
-        for name, byts in alg.items():
-            ts = ktimes.get(name, [])
-            if ts:
+        N, s = 16, 2
+        alg_of = {"cm_scan_fwd": lambda b, d, l, nd: scan_algorithmic_bytes(b, l, d, N, s, nd, False),
+                  "cm_scan_bwd": lambda b, d, l, nd: scan_algorithmic_bytes(b, l, d, N, s, nd, True),
+                  "cm_conv_fwd": lambda b, d, l, nd: conv_algorithmic_bytes(b, l, d, s, nd, False),
+                  "cm_conv_bwd": lambda b, d, l, nd: conv_algorithmic_bytes(b, l, d, s, nd, True)}
+        kern, share = {}, {}
+        for (name, tag), ts in ktimes.items():
+            share[name] = share.get(name, 0.0) + sum(ts)
+            if name in alg_of and tag is not None and ts:
+                byts = alg_of[name](*tag)
                 avg = sum(ts) / len(ts)
-                kern[name] = {"launches": len(ts), "avg_ms": avg, "total_ms": sum(ts), "alg_bytes": byts,
-                              "achieved_gbs": byts / (avg * 1e-3) / 1e9, "frac": byts / (avg * 1e-3) / 1e9 / hbm_peak}
-        share = {k: sum(v) for k, v in ktimes.items()}
-        dom = max((k for k in kern), key=lambda k: kern[k]["total_ms"]) if kern else None
-        if is_s2s:      # the decoder's unidirectional launches share the entry-point names: no single shape to quote
-            dom, kern = None, {}
+                kern["%s@B%d_D%d_L%d_dirs%d" % ((name,) + tuple(tag))] = {
+                    "entry": name, "launches": len(ts), "avg_ms": avg, "total_ms": sum(ts), "alg_bytes": byts,
+                    "achieved_gbs": byts / (avg * 1e-3) / 1e9, "frac": byts / (avg * 1e-3) / 1e9 / hbm_peak}
+        dom = max(kern, key=lambda k: kern[k]["total_ms"]) if kern else None
         roofline = None
         if dom:
             roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["achieved_gbs"], "peak": hbm_peak,
-                        "unit": "GB/s", "frac": kern[dom]["frac"], "traffic": ncu_traffic(dom, args.workload), "peak_source": peak_src,
-                        "alg_bytes_per_launch": kern[dom]["alg_bytes"], "avg_launch_ms": kern[dom]["avg_ms"],
+                        "unit": "GB/s", "frac": kern[dom]["frac"], "traffic": ncu_traffic(kern[dom]["entry"], args.workload),
+                        "peak_source": peak_src, "alg_bytes_per_launch": kern[dom]["alg_bytes"],
+                        "avg_launch_ms": kern[dom]["avg_ms"],
                         "note": "fp32 state update is MUFU/issue-bound before HBM (SURVEY.md 0.8); see `kernels`"}
         cpu_desc = None
         if not args.no_cpu_baseline and world == 1:
@@ -462,20 +568,20 @@ def main():
                 _, _, cpu_desc = cpu_reference_run(args.workload, args.cpu_steps, 1, budget_s=60.0)
             except Exception as ex:                               # the baseline must never take the GPU number down
                 cpu_desc = {"kind": "port", "error": repr(ex)}
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": elapsed_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": args.workload, "per_gpu_batch": batch, "audio_seconds": seconds,
-                       "encoder_frames": L, "d_inner": D, "layers": cfg["num_layers"], "params": n_params,
-                       "step": "Fbank+norm+CNN+%d ConMamba layers+CTC loss, forward+backward, bf16 autocast, no optimizer"
-                               % cfg["num_layers"],
-                       "parallelism": "dp%d (utterance sharding; one flat NCCL gradient all-reduce per step)" % world if world > 1 else "single GPU",
-                       "launch": graph_note,
+        config = config_block(args.workload, world)
+        config.update({"params": n_params, "launch": graph_note,
+                       "optimizer": ("torch AdamW (fused) + clip_grad_norm_ + Noam lr, inside the timed step" if opt is not None
+                                     else ("none (forward-only workload)" if not train else "disabled (--no-optimizer)")),
                        "roofline_timing": "per-kernel CUDA events from 3 eager launches of the same step right after "
                                           "the timed region (kernels inside a graph replay cannot carry events)",
                        "l2": "no flush: activations touched per step (peak %.2f GB allocated) exceed the 126 MB L2"
-                             % (peak_mem / 1e9)},
+                             % (peak_mem / 1e9)})
+        line = {
+            "metric": METRIC if train else METRIC.replace("(fwd+bwd)", "(fwd)"), "value": value, "unit": UNIT,
+            "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": elapsed_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": config,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / steps,
                     "host_wall_ms_per_step": e2e_wall_ms / steps,
                     "h2d_bytes_per_step": int(wav_pin.numel() * 4 + tgt_pin.numel() * 8), "d2h_bytes_per_step": 4,
@@ -488,6 +594,8 @@ def main():
             "cpu_baseline": cpu_desc,
             "loss": loss_val,
         }
+        if args.sweep_L:
+            line["scan_sweep"] = scan_length_sweep(dev, hbm_peak)
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

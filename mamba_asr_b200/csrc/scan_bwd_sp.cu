@@ -577,11 +577,9 @@ static int try_t(const cm_scan_bwd_args& a, cudaStream_t st, int* rc) {
   if (!build_params<T>(a, &P)) return 0;
   const size_t smem = sizeof(BwdSmem);
   auto kern = scan_bwd_sp_kernel<T>;
-  static bool attr_done = false;   // idempotent attribute; a benign race sets it twice
-  if (!attr_done) {
+  {   // per-device attribute: set on every launch (see scan_fwd_sp.cu)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { *rc = (int)e; return 1; }
-    attr_done = true;
   }
   kern<<<dim3(a.dim / kCH, a.batch, a.ndir), kGT + kIO, smem, st>>>(P);
   cudaError_t e = cudaGetLastError();

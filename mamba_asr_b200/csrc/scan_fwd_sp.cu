@@ -608,12 +608,10 @@ template <typename T, int NDIR>
 static int launch_one(const FwdParams& P, const cm_scan_fwd_args& a, cudaStream_t st) {
   const size_t smem = sizeof(FwdSmem) * NDIR;
   auto kern = scan_fwd_sp_kernel<T, NDIR>;
-  static bool attr_done = false;   // idempotent attribute; a benign race sets it twice
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    attr_done = true;
-  }
+  // per-device attribute, set on every launch (a host-side table lookup): a process-wide "done" flag would leave the
+  // second GPU of a multi-device process at the 48 KB default
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
   kern<<<dim3(a.dim / kCH, a.batch, P.nwin), NDIR * (kGT + kIO), smem, st>>>(P);
   CM_LAUNCH_CHECK();
   return 0;
@@ -635,6 +633,10 @@ static int try_t(const cm_scan_fwd_args& a, cudaStream_t st, int* rc) {
     if (*rc) return 1;
     const int64_t total = (int64_t)a.batch * a.ndir * a.dim * 16;
     window_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P, a.batch);
+    {
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) { *rc = (int)e; return 1; }
+    }
     P.summary = 0;
   }
   *rc = (a.ndir == 2) ? launch_one<T, 2>(P, a, st) : launch_one<T, 1>(P, a, st);

@@ -156,11 +156,9 @@ static int tsmm_launch_nt(const void* A, int64_t lda, const void* B, int64_t ldb
   const dim3 grid((M + kTsBM - 1) / kTsBM, (unsigned)((rows + kc - 1) / kc));
   const size_t smem = 2 * sizeof(T) * kTsKS * (kTsAPad + 8 * NT + 8);
   auto kern = tsmm_kernel<T, NT>;
-  static bool attr_done = false;   // idempotent attribute; a benign race sets it twice
-  if (!attr_done) {
+  {   // per-device attribute: set on every launch (a process-wide flag would miss the second GPU of a process)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
   }
   kern<<<grid, 128, smem, st>>>(static_cast<const T*>(A), lda, static_cast<const T*>(B), ldb, part, rows, M, kc);
   CM_LAUNCH_CHECK();

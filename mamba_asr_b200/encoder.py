@@ -20,7 +20,7 @@ import torch.nn.functional as F
 import math
 import os
 
-from .layernorm import layer_norm_leaky_relu
+from .layernorm import DropoutSeed, layer_norm_leaky_relu
 from .linear import BiasGradLinear, ParamCache, set_param_cache
 from .bimamba import precomputed_A
 from .conmamba import ConmambaEncoder, MambaDecoder
@@ -133,9 +133,15 @@ class ConMambaCTC(nn.Module):
 
     def _refresh_param_cache(self):
         c = getattr(self, "_param_cache", None)
-        if c is not None and torch.is_autocast_enabled("cuda") and torch.is_grad_enabled():
+        if c is not None and torch.is_autocast_enabled("cuda"):      # training and evaluation alike: never a stale copy
             set_param_cache(c)
             c.refresh()
+
+    def _advance_dropout_seed(self, device):
+        """Fresh masks for the fused dropout kernels on every forward: an in-place add on the device seed, so a captured
+        CUDA graph replays it (call ids and the seed POINTER are baked into the graph, the seed VALUE is not)."""
+        if self.training and device.type == "cuda":
+            DropoutSeed.advance(device)
 
     def features(self, wavs, wav_lens=None):
         feats = self.compute_features(wavs)                        # (B, T, 80) fp32, no grad
@@ -149,6 +155,7 @@ class ConMambaCTC(nn.Module):
     def forward(self, wavs, wav_lens=None):
         """wavs: (B, n_samples) -> log-probs (B, L, output_neurons)"""
         self._refresh_param_cache()
+        self._advance_dropout_seed(wavs.device)
         with precomputed_A(self):
             enc = self.encode(self.features(wavs, wav_lens))
         return F.log_softmax(self.ctc_lin(enc), dim=-1)
@@ -220,6 +227,7 @@ class ConMambaS2S(ConMambaCTC):
     def forward(self, wavs, tokens_bos, wav_lens=None):
         """wavs (B, n_samples), tokens_bos (B, S) -> (p_ctc (B, L, V), p_seq (B, S, V)) log-probabilities"""
         self._refresh_param_cache()
+        self._advance_dropout_seed(wavs.device)
         with precomputed_A(self):
             enc = self.encode(self.features(wavs, wav_lens))
             tgt = self.custom_tgt_module(tokens_bos)

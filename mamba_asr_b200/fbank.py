@@ -68,4 +68,4 @@ class Fbank(nn.Module):
             stft = torch.stft(wav.float(), self.n_fft, self.hop_length, self.win_length, self.window.to(wav.device),
                               center=True, pad_mode="constant", normalized=False, onesided=True,
                               return_complex=True)                                     # (B, F, T) complex64
-            return K.fbank_logmel(stft, self.fbank_matrix, self.top_db, self.amin, self.multiplier, self.db_offset)
+            return K.fbank_logmel(stft, self.fbank_matrix.to(wav.device), self.top_db, self.amin, self.multiplier, self.db_offset)

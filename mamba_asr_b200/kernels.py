@@ -27,15 +27,21 @@ def start_timing():
     _TIMING = {}
 
 
-def stop_timing():
-    """-> {entry point: [ms per launch, ...]} ; synchronises."""
+def stop_timing(by_shape=False):
+    """-> {entry point: [ms per launch, ...]} ; synchronises.  ``by_shape=True`` keys the scan / conv launches by
+    (entry point, (batch, dim, seqlen, ndir)) instead, so a model that launches one entry point at several shapes (the
+    S2S decoder's unidirectional scans next to the encoder's bidirectional ones) can quote one kernel at one shape."""
     global _TIMING
     t, _TIMING = _TIMING, None
     torch.cuda.synchronize()
-    return {k: [a.elapsed_time(b) for a, b in v] for k, v in (t or {}).items()}
+    out = {}
+    for (name, tag), v in (t or {}).items():
+        key = (name, tag) if by_shape else name
+        out.setdefault(key, []).extend(a.elapsed_time(b) for a, b in v)
+    return out
 
 
-def _call(name, fn, *args):
+def _call(name, fn, *args, tag=None):
     global LAUNCHES
     LAUNCHES += 1
     if _TIMING is None:
@@ -45,7 +51,7 @@ def _call(name, fn, *args):
     s.record()
     cabi.check(fn(*args), name)
     e.record()
-    _TIMING.setdefault(name, []).append((s, e))
+    _TIMING.setdefault((name, tag), []).append((s, e))
 
 
 def reduce_many(jobs):
@@ -62,9 +68,19 @@ def reduce_many(jobs):
         _call("cm_reduce_multi", lib.cm_reduce_multi, arr, len(chunk), st)
 
 
-def _require_cuda(t, name):
+def _require_cuda(t, name, like=None):
     if not t.is_cuda:
         raise RuntimeError("mamba_asr_b200: %s must be a CUDA tensor - the B200 kernels have no CPU fallback" % name)
+    if like is not None and t.device != like.device:
+        raise RuntimeError("mamba_asr_b200: %s is on %s but the launch runs on %s" % (name, t.device, like.device))
+
+
+def _same_device(like, **tensors):
+    """Every (non-None) parameter / buffer of a launch must live on the device of its activations: a host or foreign-device
+    pointer would otherwise reach the kernel and fault the context instead of raising here."""
+    for name, t in tensors.items():
+        if t is not None:
+            _require_cuda(t, name, like)
 
 
 def empty_like_bdl(t, dtype=None):
@@ -107,6 +123,7 @@ def _fill_scan_dir(sd, d, keep, const_bc):
     A = _f32c(d["A"], "A")
     Dk = _f32c(d.get("D"), "D")
     bias = _f32c(d.get("delta_bias"), "delta_bias")
+    _same_device(u, A=A, D=Dk, delta_bias=bias, B=Bm, C=Cm, delta=delta)
     keep += [A, Dk, bias]
     sd.A = A.data_ptr()
     sd.A_sd, sd.A_sn = A.stride(0), A.stride(1)
@@ -190,7 +207,7 @@ def scan_forward(dirs, z=None, out_scale=1.0, delta_softplus=False, need_ckpt=Fa
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=u0.device)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws_bytes
         keep.append(ws)
-    _call("cm_scan_fwd", lib.cm_scan_fwd, C.byref(a), cabi.stream_ptr())
+    _call("cm_scan_fwd", lib.cm_scan_fwd, C.byref(a), cabi.stream_ptr(), tag=(Bt, D, L, len(dirs)))
     return dict(out=out, out_pre=out_pre, ckpt=ckpts, last_state=lasts)
 
 
@@ -253,7 +270,7 @@ def scan_backward(dirs, ckpts, dout, z=None, out_pre=None, out_scale=1.0, delta_
         a.z, a.out_pre, a.dz = cabi.t3(z), cabi.t3(out_pre), cabi.t3(dz)
         res["dz"] = dz
     st = cabi.stream_ptr()
-    _call("cm_scan_bwd", lib.cm_scan_bwd, C.byref(a), st)
+    _call("cm_scan_bwd", lib.cm_scan_bwd, C.byref(a), st, tag=(Bt, D, L, len(dirs)))
 
     jobs = []
     outs = []
@@ -322,6 +339,7 @@ def _conv_common(x, dirs, silu):
         w = d["weight"]
         if w.shape != (D, W):
             raise ValueError("conv weight must be (D, W)")
+        _same_device(x, conv_weight=w, conv_bias=d.get("bias"))
         w = w.float().contiguous()
         b = d.get("bias")
         b = None if b is None else b.float().contiguous()
@@ -342,7 +360,7 @@ def conv_forward(x, dirs, silu=True, outs=None):
         o = outs[r] if outs is not None else empty_like_bdl(x)
         a.dir[r].out = cabi.t3(o)
         res.append(o)
-    _call("cm_conv_fwd", lib.cm_conv_fwd, C.byref(a), cabi.stream_ptr())
+    _call("cm_conv_fwd", lib.cm_conv_fwd, C.byref(a), cabi.stream_ptr(), tag=(a.batch, a.dim, a.seqlen, len(dirs)))
     return res
 
 
@@ -368,7 +386,7 @@ def conv_backward(x, dirs, douts, silu=True, dx_out=None):
         a.dir[r].dbias_part = cabi.ptr(bp)
         parts.append((wp, bp))
     st = cabi.stream_ptr()
-    _call("cm_conv_bwd", lib.cm_conv_bwd, C.byref(a), st)
+    _call("cm_conv_bwd", lib.cm_conv_bwd, C.byref(a), st, tag=(Bt, D, L, len(dirs)))
     dws, dbs, jobs = [], [], []
     for wp, bp in parts:
         dw = torch.empty((D, W), dtype=torch.float32, device=dev)
@@ -453,6 +471,7 @@ def fbank_logmel(stft, fbank, top_db=80.0, amin=1e-10, multiplier=10.0, db_offse
     M = fbank.shape[1]
     if fbank.shape[0] != F:
         raise ValueError("fbank must be (n_bins, n_mels)")
+    _same_device(stft, fbank=fbank)
     fb = fbank.float().contiguous()
     out = torch.empty((Bt, T, M), dtype=torch.float32, device=stft.device)
     umax = torch.full((Bt,), float("-inf"), dtype=torch.float32, device=stft.device)
@@ -477,6 +496,7 @@ def layernorm_forward(x2d, weight, bias, eps, out_dtype):
     rows, Cn = x2d.shape
     if x2d.stride(1) != 1:
         raise ValueError("layernorm: the normalised dimension must be contiguous")
+    _same_device(x2d, weight=weight, bias=bias)
     y = torch.empty((rows, Cn), dtype=out_dtype, device=x2d.device)
     mean = torch.empty((rows,), dtype=torch.float32, device=x2d.device)
     rstd = torch.empty((rows,), dtype=torch.float32, device=x2d.device)
@@ -536,6 +556,7 @@ LN_ACTS = {"leaky_relu": cabi.CM_LN_ACT_LEAKY_RELU, "gelu": cabi.CM_LN_ACT_GELU}
 
 
 def _ln_act_args(x2d, weight, bias, eps, slope, mean, rstd, act, pre_bias):
+    _same_device(x2d, weight=weight, bias=bias, pre_bias=pre_bias)
     a = cabi.LnActArgs()
     a.rows, a.cols = x2d.shape
     a.dtype = cabi.dtype_code(x2d.dtype)
@@ -624,6 +645,7 @@ def add_ln_forward(a2d, b2d, weight, bias, eps, alpha, p_drop, seed, call_id, ou
     mean = torch.empty((rows,), dtype=torch.float32, device=dev)
     rstd = torch.empty((rows,), dtype=torch.float32, device=dev)
     mask = torch.empty((rows, Cn), dtype=torch.uint8, device=dev) if (p_drop > 0.0 and b2d is not None) else None
+    _same_device(a2d, b=b2d, weight=weight, bias=bias, seed=seed)
     a = cabi.AddLnArgs()
     a.rows, a.cols = rows, Cn
     a.a_dtype, a.y_dtype = cabi.dtype_code(a2d.dtype), cabi.dtype_code(out_dtype)
@@ -763,6 +785,7 @@ def dwconv_forward(x_blc, weight_ck, bias, pad_left, flip=False):
     flip=True evaluates the backward-data form (taps reversed; pass pad_left' = K-1-pad_left, bias None)."""
     lib = cabi.lib()
     Cn, K = weight_ck.shape
+    _same_device(x_blc, weight=weight_ck, bias=bias)
     a = _dwconv_args(x_blc, K, pad_left)
     y = torch.empty(x_blc.shape, dtype=x_blc.dtype, device=x_blc.device)
     a.flip = 1 if flip else 0

@@ -37,14 +37,25 @@ class ParamCache:
         dev = self.params[0].device if self.params else None
         self.flat = torch.zeros(n, dtype=dtype, device=dev)
         self.views = [self.flat[o:o + p.numel()].view(p.shape) for o, p in zip(offs, self.params)]
-        self.map = {id(p): v for p, v in zip(self.params, self.views)}
+        self.index = {id(p): i for i, p in enumerate(self.params)}
+        self.versions = [-1] * len(self.params)                # parameter versions the copies were taken at
+        self.refresh()
 
     def refresh(self):
         with torch.no_grad():
             torch._foreach_copy_(self.views, self.params)
+        self.versions = [p._version for p in self.params]
 
     def get(self, p, dtype):
-        return self.map.get(id(p)) if dtype == self.dtype else None
+        """The copy of ``p``, or None when there is none or when ``p`` has been written (optimizer step, load_state_dict,
+        in-place init) since the last ``refresh()`` - a stale copy is never handed out; the caller then casts ``p`` itself.
+        (A captured CUDA graph replays the refresh kernel itself, so the host-side version check only guards eager use.)"""
+        if dtype != self.dtype:
+            return None
+        i = self.index.get(id(p))
+        if i is None or self.versions[i] != p._version:
+            return None
+        return self.views[i]
 
 
 _ACTIVE = None

@@ -5,7 +5,8 @@ same return conventions, backed by the sm_100a kernels (no CPU fallback; CUDA te
   mamba_inner_fn_no_out_proj reference :632-638 (MambaInnerFnNoOutProj :160-294)
   mamba_inner_fn             reference :611-618 (MambaInnerFn :297-439)
   bimamba_inner_fn           reference :621-629 (BiMambaInnerFn :442-608, the shared-weight "v1" form)
-  selective_scan_ref / mamba_inner_ref  are NOT here: the CPU reference lives in ``oracle/`` (test infrastructure).
+  selective_scan_ref / mamba_inner_ref / bimamba_inner_ref (reference :91, :641, :678) are importable names that RAISE:
+  the CPU reference lives in ``oracle/`` (test infrastructure); the product package has no CPU path.
 
 Differences that are deliberate and invisible to callers:
   * inputs are consumed through their strides - nothing is ``.contiguous()``-copied (reference :24-35);
@@ -150,3 +151,21 @@ def bimamba_inner_fn(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_w
     y = y_f + fl(y_b)
     return F.linear(y.transpose(1, 2), out_proj_weight.to(act),
                     None if out_proj_bias is None else out_proj_bias.to(act))
+
+
+def _cpu_reference_is_test_infrastructure(name, ref_line):
+    def _raise(*args, **kwargs):
+        raise NotImplementedError(
+            "%s (reference selective_scan_interface.py:%s) is the CPU reference of this path: it is test infrastructure "
+            "and lives in oracle/ (oracle.scan_ref.selective_scan_oracle, oracle.bimamba_ref); the product package has "
+            "no CPU path.  Use %s on CUDA tensors instead." % (name, ref_line, name.replace("_ref", "_fn")))
+    _raise.__name__ = name
+    _raise.__doc__ = "Name kept for import compatibility with the reference (:%s); raises NotImplementedError." % ref_line
+    return _raise
+
+
+# names the reference module exports (:91, :641, :678): kept importable so `from ...selective_scan_interface import
+# selective_scan_ref` does not fail at import time, but they refuse to run - the product path never touches a CPU oracle
+selective_scan_ref = _cpu_reference_is_test_infrastructure("selective_scan_ref", "91-157")
+mamba_inner_ref = _cpu_reference_is_test_infrastructure("mamba_inner_ref", "641-675")
+bimamba_inner_ref = _cpu_reference_is_test_infrastructure("bimamba_inner_ref", "678-714")

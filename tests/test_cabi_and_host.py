@@ -5,6 +5,7 @@ import ctypes
 import json
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -302,3 +303,44 @@ def test_split_k_weight_gradient_row_blocks(monkeypatch):
     assert _wgrad_nsplit(5011, 64, 48) == 1 and _wgrad_nsplit(1503, 256, 1024) == 1
     monkeypatch.setenv("CM_NO_WGRAD_SPLIT", "1")
     assert _wgrad_nsplit(12032, 1024, 144) == 1
+
+
+def test_reference_cpu_names_are_importable_but_refuse_to_run():
+    """B2 namespace parity (reference selective_scan_interface.py:91, :641, :678): the *_ref names import through the
+    package and through compat/modules, and raise - the product has no CPU path and never imports oracle/."""
+    sys.path.insert(0, os.path.join(ROOT, "compat"))
+    try:
+        from modules.mamba.selective_scan_interface import (bimamba_inner_ref, mamba_inner_ref,  # noqa: F401
+                                                            selective_scan_fn, selective_scan_ref)
+    finally:
+        sys.path.remove(os.path.join(ROOT, "compat"))
+    for fn in (selective_scan_ref, mamba_inner_ref, bimamba_inner_ref):
+        with pytest.raises(NotImplementedError, match="oracle"):
+            fn(torch.randn(1, 4, 8), torch.randn(1, 4, 8), -torch.ones(4, 16), torch.randn(1, 16, 8), torch.randn(1, 16, 8))
+
+
+def test_param_cache_never_hands_out_a_stale_copy():
+    """linear.ParamCache: a copy taken before an in-place parameter update (optimizer step, load_state_dict) must not be
+    returned afterwards (eval after a training step silently used stale bf16 weights)."""
+    from mamba_asr_b200.linear import ParamCache
+
+    class _P(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.randn(4, 8))
+
+    m = _P()
+    c = ParamCache.__new__(ParamCache)                      # the constructor filters on .is_cuda: build the CPU equivalent
+    c.params, c.dtype = [m.w], torch.bfloat16
+    c.flat = torch.zeros(32, dtype=torch.bfloat16)
+    c.views = [c.flat[:32].view(4, 8)]
+    c.index, c.versions = {id(m.w): 0}, [-1]
+    assert c.get(m.w, torch.bfloat16) is None               # never refreshed: no copy yet
+    c.refresh()
+    assert torch.equal(c.get(m.w, torch.bfloat16), m.w.detach().bfloat16())
+    with torch.no_grad():
+        m.w.add_(1.0)                                       # what optimizer.step() does
+    assert c.get(m.w, torch.bfloat16) is None
+    c.refresh()
+    assert torch.equal(c.get(m.w, torch.bfloat16), m.w.detach().bfloat16())
+    assert c.get(m.w, torch.float16) is None

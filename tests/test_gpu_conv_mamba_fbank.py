@@ -372,3 +372,87 @@ def test_bias_grad_linear_matches_nn_linear(shape, autocast):
     for a, b, nm in zip(outs[1], outs[0], ("y", "dx", "dw", "db")):
         assert a.dtype == b.dtype
         assert_close(a.float(), b.float(), dt, floor="max", what="linear " + nm)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_extension_shims_with_the_reference_tensor_geometry(dtype):
+    """The B3 shims driven with EXACTLY the tensor geometry of the reference's MambaInnerFnNoOutProj
+    (selective_scan_interface.py:180-187, 218, 249-256, 286): xz produced by `in_proj.weight @ hidden` rearranged
+    "d (b l) -> b d l" (strides (L, B*L, 1)), x / z as chunk views of it, delta with the same strided layout, B / C as
+    contiguous (b 1 n l), dz_ and dx_ as strided halves of ONE dxz buffer.  Everything is checked against the oracle."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "compat"))
+    import causal_conv1d_cuda
+    import selective_scan_cuda
+    from oracle.conv_ref import causal_conv1d_oracle
+    from oracle.scan_ref import selective_scan_oracle
+    g = torch.Generator().manual_seed(17)
+    Bt, L, dm, D, R, N, W = 3, 53, 48, 96, 3, 16, 4
+    hidden = torch.randn(Bt, L, dm, generator=g)
+    w_in = torch.randn(2 * D, dm, generator=g) * dm ** -0.5
+    conv_w, conv_b = torch.randn(D, W, generator=g) * 0.5, torch.randn(D, generator=g) * 0.1
+    w_x = torch.randn(R + 2 * N, D, generator=g) * D ** -0.5
+    w_dt = torch.randn(D, R, generator=g) * R ** -0.5
+    A = -torch.exp(torch.randn(D, N, generator=g) * 0.2)
+    Dk = torch.ones(D)
+    dt_bias = torch.log(torch.expm1(torch.full((D,), 0.02)))
+    cast = lambda t: t.to(dtype)
+    dev = lambda t: t.cuda()
+
+    def run(xz, on_gpu):
+        """selective_scan_interface.py:180-218 with the op names of that file; returns the tensors handed around."""
+        x, z = xz.chunk(2, dim=1)
+        assert x.stride() == (L, Bt * L, 1)
+        if on_gpu:
+            conv1d_out = causal_conv1d_cuda.causal_conv1d_fwd(x, dev(conv_w), dev(conv_b), None, True)
+        else:
+            conv1d_out = causal_conv1d_oracle(x, conv_w, conv_b, "silu")
+        wx, wdt = (dev(cast(w_x)), dev(cast(w_dt))) if on_gpu else (cast(w_x), cast(w_dt))
+        x_dbl = torch.nn.functional.linear(conv1d_out.permute(0, 2, 1).reshape(Bt * L, D), wx)
+        delta = (wdt @ x_dbl[:, :R].t()).view(D, Bt, L).permute(1, 0, 2)                # "d (b l) -> b d l": a strided view
+        assert delta.stride() == (L, Bt * L, 1)
+        Bm = x_dbl[:, R:R + N].view(Bt, L, N).permute(0, 2, 1).unsqueeze(1).contiguous()
+        Cm = x_dbl[:, -N:].view(Bt, L, N).permute(0, 2, 1).unsqueeze(1).contiguous()
+        return x, z, conv1d_out, delta, Bm, Cm
+
+    xz_c = cast((w_in @ hidden.permute(2, 0, 1).reshape(dm, Bt * L)).view(2 * D, Bt, L).permute(1, 0, 2))
+    assert xz_c.stride() == (L, Bt * L, 1)
+    xz_g = torch.empty_strided(xz_c.shape, xz_c.stride(), dtype=dtype, device="cuda").copy_(xz_c)
+    x, z, conv1d_out, delta, Bm, Cm = run(xz_g, True)
+    cx, cz, c_conv, c_delta, cB, cC = run(xz_c, False)
+    assert_close(conv1d_out.float(), c_conv.float(), dtype, what="conv1d_out")
+    out, inter, out_z = selective_scan_cuda.fwd(conv1d_out, delta, dev(A), Bm, Cm, dev(Dk), z, dev(dt_bias), True)
+    # oracle on what the GPU path actually fed its scan (its own conv1d_out / delta / B / C, rounded to dtype)
+    leaf = dict(u=conv1d_out.cpu().float(), delta=delta.cpu().float(), B=Bm[:, 0].cpu().float(), C=Cm[:, 0].cpu().float(),
+                z=z.cpu().float())
+    leaf = {k: v.clone().requires_grad_(True) for k, v in leaf.items()}
+    Al, Dl, bl = A.clone().requires_grad_(True), Dk.clone().requires_grad_(True), dt_bias.clone().requires_grad_(True)
+    ref = selective_scan_oracle(leaf["u"], leaf["delta"], Al, leaf["B"], leaf["C"], Dl, leaf["z"], bl, True)
+    assert_close(out_z.float(), ref.detach(), dtype, what="out_z")
+    dout = cast(torch.randn(Bt, D, L, generator=g))
+    (ref * dout.float()).sum().backward()
+    dxz = torch.empty_like(xz_g)                                                           # :249-250
+    dx, dz = dxz.chunk(2, dim=1)
+    ret = selective_scan_cuda.bwd(conv1d_out, delta, dev(A), Bm, Cm, dev(Dk), z, dev(dt_bias), dev(dout), inter, out, dz,
+                                  True, True)
+    dconv1d_out, ddelta, dA, dB, dC, dD, ddb, dz_ret, out_z2 = ret
+    assert dz_ret.data_ptr() == dz.data_ptr()
+    assert_close(dz.float(), leaf["z"].grad, dtype, what="dz (strided half of dxz)")
+    assert_close(dconv1d_out.float(), leaf["u"].grad, dtype, what="dconv1d_out")
+    assert_close(ddelta.float(), leaf["delta"].grad, dtype, what="ddelta")
+    assert_close(dB[:, 0].float(), leaf["B"].grad, dtype, floor="max", what="dB")
+    assert_close(dC[:, 0].float(), leaf["C"].grad, dtype, floor="max", what="dC")
+    assert_close(dA, Al.grad, dtype, floor="max", what="dA")
+    assert_close(dD, Dl.grad, dtype, floor="max", what="dD")
+    assert_close(ddb, bl.grad, dtype, floor="max", what="ddelta_bias")
+    assert_close(out_z2.float(), ref.detach(), dtype, what="recomputed out_z")
+    # conv backward into the strided dx half (:286), gradient handed over in the "d (b l) -> b d l" geometry of :282-283
+    dco = torch.empty_strided((Bt, D, L), (L, Bt * L, 1), dtype=dtype, device="cuda").copy_(dconv1d_out)
+    dx_ret, dcw, dcb = causal_conv1d_cuda.causal_conv1d_bwd(x, dev(conv_w), dev(conv_b), dco, None, dx, True)
+    assert dx_ret.data_ptr() == dx.data_ptr()
+    xl = cx.float().clone().requires_grad_(True)
+    wl, bl2 = conv_w.clone().requires_grad_(True), conv_b.clone().requires_grad_(True)
+    (causal_conv1d_oracle(xl, wl, bl2, "silu") * dco.cpu().float()).sum().backward()
+    assert_close(dx.float(), xl.grad, dtype, what="dx (strided half of dxz)")
+    assert_close(dcw, wl.grad, dtype, floor="max", what="dconv1d_weight")
+    assert_close(dcb, bl2.grad, dtype, floor="max", what="dconv1d_bias")

@@ -182,3 +182,77 @@ def test_config5_long_form_inference_windowed_scan_equals_whole_sequence(monkeyp
     # outputs would mean the windowed path did not run at this shape
     assert not torch.equal(outs[0][0], outs[1][0])
     assert_close(outs[0][0], outs[1][0], torch.bfloat16, floor="max", what="windowed vs whole-sequence log-probs")
+
+
+def test_graph_replays_draw_fresh_dropout_masks():
+    """under CUDA-graph replay the fused dropout kernels must not repeat their masks.  The model forward
+    advances the device seed in place (captured, so every replay advances it again)."""
+    from mamba_asr_b200.encoder import build_model
+    from mamba_asr_b200.graphs import graph_module
+    from mamba_asr_b200.layernorm import DropoutSeed, gelu_dropout
+    # (i) the kernel-level contract: seed advance + fused GELU/dropout inside one captured graph
+    x = torch.randn(64, 256, device="cuda").abs() + 0.5           # gelu(x) != 0 everywhere: zeros are dropped elements
+    DropoutSeed.tensor(x.device)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            DropoutSeed.advance(x.device)
+            gelu_dropout(x, 0.5, True)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        DropoutSeed.advance(x.device)
+        y = gelu_dropout(x, 0.5, True)
+    masks = []
+    for _ in range(3):
+        g.replay()
+        masks.append((y == 0).clone())
+    assert not torch.equal(masks[0], masks[1]) and not torch.equal(masks[1], masks[2])
+    assert 0.4 < masks[0].float().mean().item() < 0.6
+    # (ii) the model-level path bench.py uses: torch's own Dropout switched off, only the fused kernels are random
+    torch.manual_seed(0)
+    m = build_model("conmamba_small_ctc", num_layers=2).cuda().train()
+    m.custom_src_module[1].p = 0.0
+    wav = 0.1 * torch.randn(2, 8000, device="cuda")
+    with torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False):
+        gm = graph_module(m, (wav,), warmup=3)
+        outs = [gm(wav).detach().float().clone() for _ in range(3)]
+    assert not torch.equal(outs[0], outs[1]) and not torch.equal(outs[1], outs[2])
+    m.eval()                                                 # no dropout: eager forwards are deterministic
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        a, b = m(wav), m(wav)
+    assert torch.equal(a, b)
+
+
+def test_param_cache_eval_after_update_matches_uncached_model():
+    """eval under no_grad + autocast after enable_param_cache() and a parameter update must use the
+    CURRENT weights everywhere (x_proj / dt_proj included), i.e. match the same model without a cache."""
+    from mamba_asr_b200.encoder import build_model
+    from mamba_asr_b200.linear import set_param_cache
+    torch.manual_seed(1)
+    m = build_model("conmamba_small_ctc", num_layers=2).cuda().eval()
+    wav = 0.1 * torch.randn(2, 8000, device="cuda")
+    m.enable_param_cache()
+    with torch.no_grad():
+        for p in m.parameters():
+            p.mul_(1.5)                                      # an "optimizer step" after the cache was built
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            cached = m(wav).float()
+        set_param_cache(None)
+        m._param_cache = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            plain = m(wav).float()
+    assert_close(cached, plain, torch.bfloat16, floor="max", what="cached vs uncached eval")
+    # direct submodule call without a refresh after another update: the stale copies must not be used
+    m.enable_param_cache()
+    with torch.no_grad():
+        for p in m.parameters():
+            p.mul_(0.5)
+        feats = m.features(wav)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            e1 = m.encode(feats).float()
+        set_param_cache(None)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            e2 = m.encode(feats).float()
+    assert_close(e1, e2, torch.bfloat16, floor="max", what="encode() with a stale cache")

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CM_ABI_VERSION 7
+#define CM_ABI_VERSION 8
 
 /* element type of activations (u, delta, z, B, C, x, out, and their gradients) */
 enum { CM_F32 = 0, CM_BF16 = 1, CM_F16 = 2 };
@@ -142,6 +142,10 @@ typedef struct {
   cm_tensor3 dz;            /* grad of z (written when z is given) */
 } cm_scan_bwd_args;
 
+/* Channels per slab of dBC_part for THIS launch (a pure function of the argument block, pointers included - fill everything
+ * but dBC_part first): 128 when the lane-per-channel TMA kernel applies (scan_bwd_lc.cu), else cm_scan_slab_channels(lanes).
+ * n_slab = ceil(dim / slab). */
+int cm_scan_bwd_slab_channels(const cm_scan_bwd_args* args);
 int cm_scan_bwd(const cm_scan_bwd_args* args, void* stream);
 
 /* dB[b,n,l] = sum_slab part[b][slab][l][n], dC likewise with column 16+n; written in `dtype` through strides. */

@@ -17,11 +17,11 @@ CM_ERR_BAD_ARG, CM_ERR_UNSUPPORTED = -1, -2
 CM_FLAG_DELTA_SOFTPLUS = 1
 CM_FLAG_SILU = 1
 CM_SCAN_CKPT_STEPS = 8
-CM_ABI_VERSION = 7
+CM_ABI_VERSION = 8
 CM_LN_ACT_LEAKY_RELU, CM_LN_ACT_GELU = 0, 1
 
 EXPORTS = (
-    "cm_version", "cm_scan_num_ckpt", "cm_scan_slab_channels", "cm_scan_pick_lanes", "cm_scan_pick_lanes_bwd", "cm_scan_fwd",
+    "cm_version", "cm_scan_num_ckpt", "cm_scan_slab_channels", "cm_scan_pick_lanes", "cm_scan_pick_lanes_bwd", "cm_scan_bwd_slab_channels", "cm_scan_fwd",
     "cm_scan_bwd",
     "cm_reduce_dbc", "cm_reduce_rows", "cm_conv_fwd", "cm_conv_num_part", "cm_conv_bwd", "cm_conv_update",
     "cm_fbank_logmel", "cm_fbank_floor", "cm_abi_sizeof", "cm_reduce_multi", "cm_layernorm_num_part", "cm_layernorm_fwd",
@@ -179,6 +179,7 @@ def lib():
         L.cm_scan_slab_channels.argtypes = [C.c_int32]
         L.cm_scan_pick_lanes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
         L.cm_scan_pick_lanes_bwd.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+        L.cm_scan_bwd_slab_channels.argtypes = [C.POINTER(ScanBwdArgs)]
         L.cm_scan_fwd.argtypes = [C.POINTER(ScanFwdArgs), C.c_void_p]
         L.cm_scan_bwd.argtypes = [C.POINTER(ScanBwdArgs), C.c_void_p]
         L.cm_reduce_dbc.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, Tensor3, Tensor3,

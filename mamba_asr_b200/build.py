@@ -21,7 +21,7 @@ OBJDIR = os.path.join(PKG, "build")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libconmamba_b200.so")
 
-SOURCES = ["scan_fwd.cu", "scan_fwd_cl.cu", "scan_fwd_sp.cu", "scan_bwd.cu", "scan_bwd_cl.cu", "scan_bwd_sp.cu", "conv.cu", "fbank.cu", "layernorm.cu", "dwconv.cu", "colsum.cu", "step.cu", "fused_ln.cu", "act.cu", "tsmm.cu", "ln_act.cu"]
+SOURCES = ["scan_fwd.cu", "scan_fwd_cl.cu", "scan_fwd_sp.cu", "scan_fwd_lc.cu", "scan_bwd.cu", "scan_bwd_cl.cu", "scan_bwd_sp.cu", "scan_bwd_lc.cu", "conv.cu", "fbank.cu", "layernorm.cu", "dwconv.cu", "colsum.cu", "step.cu", "fused_ln.cu", "act.cu", "tsmm.cu", "ln_act.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "--extended-lambda",
@@ -50,17 +50,21 @@ def _headers():
     return hs
 
 
-def build(force=False, verbose=False):
-    os.makedirs(OBJDIR, exist_ok=True)
+def build(force=False, verbose=False, variant=None, extra_flags=None):
+    """variant / extra_flags: tuning experiments - a second library lib/libconmamba_b200_<variant>.so compiled with extra
+    -D flags next to the default one (select it at run time with CM_LIB_PATH); never used by the product path."""
+    objdir = OBJDIR if variant is None else OBJDIR + "_" + variant
+    lib = LIB if variant is None else LIB.replace(".so", "_%s.so" % variant)
+    os.makedirs(objdir, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = _nvcc()
     headers = _headers()
-    extra = os.environ.get("CM_NVCC_EXTRA", "").split()      # tuning experiments, e.g. -DCM_FWD_MINB=8
+    extra = os.environ.get("CM_NVCC_EXTRA", "").split() + list(extra_flags or [])     # e.g. -DCM_FWD_MINB=8
     flags = " ".join(NVCC_FLAGS + extra)
 
     def compile_one(src):
         path = os.path.join(CSRC, src)
-        obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
         stamp = obj + ".sha"
         dg = _digest([path] + headers, flags)
         if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dg:
@@ -78,13 +82,15 @@ def build(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         results = list(ex.map(compile_one, SOURCES))
     objs = [o for o, _ in results]
-    if force or any(ch for _, ch in results) or not os.path.exists(LIB):
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    if force or any(ch for _, ch in results) or not os.path.exists(lib):
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    var = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    ext = sys.argv[sys.argv.index("--extra") + 1].split() if "--extra" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=var, extra_flags=ext))

@@ -392,6 +392,7 @@ namespace cm {
 int scan_fwd_try_channel_last(const cm_scan_fwd_args& a, int lpc, cudaStream_t st, int* rc);   // scan_fwd_cl.cu
 int scan_fwd_try_state_parallel(const cm_scan_fwd_args& a, cudaStream_t st, int* rc);            // scan_fwd_sp.cu
 int64_t scan_fwd_sp_workspace_bytes(const cm_scan_fwd_args& a);                                  // scan_fwd_sp.cu
+int scan_fwd_try_lane_channel(const cm_scan_fwd_args& a, cudaStream_t st, int* rc);              // scan_fwd_lc.cu
 }
 
 extern "C" int64_t cm_scan_fwd_workspace_bytes(const cm_scan_fwd_args* args) {
@@ -420,8 +421,13 @@ extern "C" int cm_scan_fwd(const cm_scan_fwd_args* args, void* stream) {
   const bool bcc = a.dir[0].bc_const != 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (getenv("CM_SCAN_GENERIC") == nullptr && getenv("CM_SCAN_NO_SP") == nullptr && a.lanes_per_channel == 0) {
-    // state-parallel kernel (lane = state): the default whenever the layout is channel-last
     int rc = 0;
+    // lane-per-channel TMA kernel (scan_fwd_lc.cu): the default for channel-last operands; launches that the caller lets
+    // run as parallel time windows (few long sequences, workspace provided) stay on the state-parallel kernel
+    const bool windowed = a.workspace != nullptr && cm::scan_fwd_sp_workspace_bytes(a) > 0 &&
+                          a.workspace_bytes >= cm::scan_fwd_sp_workspace_bytes(a);
+    if (!windowed && getenv("CM_SCAN_NO_LC") == nullptr && cm::scan_fwd_try_lane_channel(a, st, &rc)) return rc;
+    // state-parallel kernel (lane = 4 states x 2 channels)
     if (cm::scan_fwd_try_state_parallel(a, st, &rc)) return rc;
   }
   if (getenv("CM_SCAN_GENERIC") == nullptr) {   // env switch only for A/B measurements of the two kernels

@@ -1,0 +1,471 @@
+// Selective-scan forward, "lc" kernel (lane = channel, TMA-staged) for sm_100a - the default forward kernel of round 2.
+//
+// Mathematics, bidirectional stash/combine protocol and checkpoint contract are those of scan_fwd.cu (see its header;
+// reference semantics: modules/mamba/selective_scan_interface.py:106-157 and modules/mamba/bimamba.py:223-253).
+//
+// What binds this op on B200 is the MUFU pipe (one ex2 per state update, 16 lanes / clk / SM), then issue slots; HBM
+// is third.  The design therefore minimises instructions per state update and spreads the
+// exponentials over two pipes:
+//   * A LANE OWNS ONE CHANNEL and its 16 states (8 packed fp32 pairs in registers): B and C are shared by all channels
+//     of a step, so they reach the lanes as BROADCAST LDS.128 (8 wavefronts per 512 state updates - the state-parallel
+//     kernel of round 1 needed 14 and was bound by the shared-memory pipe); dt and dt*u are scalars that the packed
+//     FMUL2 / FFMA2 instructions broadcast from one register.  Per step and warp: 8 FMUL2 (dt*A) + 16 ex2 + 8 FMUL2
+//     (dt*u*B) + 8 FFMA2 (state) + 8 FFMA2 (C*h) + ~25 scalar instructions.
+//   * The last NPOLY state pairs take their exponentials on the FMA pipe (round-to-nearest split + degree-4 polynomial +
+//     exponent insertion, packed two states per instruction) instead of the MUFU pipe.
+//   * A WARP IS SELF-CONTAINED: it owns 32 channels of one (batch, direction) and streams its own operands.  Lane 0
+//     issues one TMA tile load (cp.async.bulk.tensor, box = 32 channels x 16 steps) per operand - u, delta, B|C, and in
+//     the gated ranges z and the partner direction's stash - two tiles ahead into a 2-stage shared-memory ring guarded
+//     by an mbarrier per stage (transaction bytes); no register prefetch, no address arithmetic in the loop, rows
+//     outside [0, L) zero-filled by the hardware.  Warps never wait for each other except once per launch: the two
+//     directions of a channel block meet in the middle of the sequence (range 0: stash pre-gate sums in `out`; one
+//     64-thread barrier; range 1: combine with the partner's stash, gate once, final store) - no flip, no second output
+//     tensor, no add kernel.
+//   * 4 warps per CTA = 2 channel blocks x 2 directions (or 4 blocks of a unidirectional launch): a multiple of the 4
+//     SM sub-partitions, whose XU pipes are the unit that saturates.
+//
+// Requirements (else the launcher falls through to the other kernels): unit channel stride, dstate == 16, variable
+// B/C with unit state stride and C = B + 16 elements (one 32-element B|C row per step, as the module's x_dbl has it),
+// dim a multiple of 32, 16-byte aligned rows (TMA), no time windows (those launches stay on scan_fwd_sp.cu).
+#include <climits>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace cm {
+namespace lc {
+
+constexpr int kT = 16;        // steps per tile
+constexpr int kStages = 2;    // ring depth
+constexpr int kWarps = 4;     // warps per CTA
+constexpr int kG = 4;         // steps per scheduling group (independent scalar chains interleaved)
+
+struct FwdDir {
+  CUtensorMap m_u, m_dl, m_bc;             // (channel, time, batch) maps; B|C as a 32-wide row
+  const float* A;
+  int64_t A_sd, A_sn;
+  const float *Dskip, *bias;
+  float* ckpt;
+  int64_t ckpt_sb, ckpt_sd;
+  float* last;
+  int64_t ls_sb, ls_sd, ls_sn;
+  char *out, *pre;                         // byte pointers at (batch 0, channel 0, PROCESSED step 0)
+  int64_t out_sb, pre_sb;                  // batch strides (bytes)
+  int32_t out_ss, pre_ss;                  // bytes per processed step (signed)
+  int32_t s1, reverse;
+};
+struct alignas(64) FwdParams {
+  CUtensorMap m_z, m_st;                   // gate z; `out` read back (the partner direction's stash)
+  FwdDir dir[2];
+  int32_t L, dim, groups, n_items, ndir, has_z, has_pre;
+  uint32_t flags;
+  float scale;
+};
+
+template <typename T>
+struct Stage {                             // one tile of every per-step operand of a warp: [step][channel]
+  T u[kT][32], dl[kT][32], z[kT][32], st[kT][32], bc[kT][32];
+};
+template <typename T>
+struct alignas(128) WarpSmem {
+  Stage<T> stage[kStages];
+  float bcf[kT][32];                       // fp32 B|C rows of the tile in flight, processed order (16-bit I/O only)
+  uint64_t full[kStages];
+};
+
+// exp2 of two packed values on the FMA / ALU pipes.  x is clamped at -125 (result 2^-125 instead of 0: below anything the
+// recurrence can resolve); t = x + 1.5*2^23 leaves round(x) in the low mantissa bits, f = x - round(x) in [-0.5, 0.5],
+// 2^f by a degree-4 polynomial with the constant term exactly 1 (relative error < 3e-6, proportional to |f| near 0 so a
+// slow state's time constant is not biased), then round(x) is added into the exponent field.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  constexpr float kMagic = 12582912.0f;
+  x.x = fmaxf(x.x, -125.0f);
+  x.y = fmaxf(x.y, -125.0f);
+  const float2 t = fadd2(x, make_float2(kMagic, kMagic));
+  const float2 n = fadd2(t, make_float2(-kMagic, -kMagic));
+  const float2 f = fadd2(x, make_float2(-n.x, -n.y));
+  // near-minimax fit of 2^f on [-0.5, 0.5] with p(0) = 1 (Lawson iteration, evaluated in fp32: max rel. error 2.9e-6)
+  float2 p = make_float2(9.582849219441414e-3f, 9.582849219441414e-3f);
+  p = ffma2(p, f, make_float2(5.590642988681793e-2f, 5.590642988681793e-2f));
+  p = ffma2(p, f, make_float2(2.4024099111557007e-1f, 2.4024099111557007e-1f));
+  p = ffma2(p, f, make_float2(6.931241750717163e-1f, 6.931241750717163e-1f));
+  p = ffma2(p, f, make_float2(1.0f, 1.0f));
+  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)),
+                     __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
+}
+
+// Shared-memory loads are plain C++ accesses through `const char*` pointers derived from the dynamic shared array: the
+// compiler emits LDS and is free to hoist them (asm volatile loads are kept in program order with every other volatile
+// statement, which serialised each LDS behind the previous STS: short-scoreboard stalls on every use in the first version).
+template <typename T> struct Ld;
+template <> struct Ld<float> {
+  static __device__ __forceinline__ float at(const char* a) { return *reinterpret_cast<const float*>(a); }
+};
+template <> struct Ld<__nv_bfloat16> {
+  static __device__ __forceinline__ float at(const char* a) {
+    return __uint_as_float(static_cast<uint32_t>(*reinterpret_cast<const unsigned short*>(a)) << 16);
+  }
+};
+template <> struct Ld<__half> {
+  static __device__ __forceinline__ float at(const char* a) { return __half2float(*reinterpret_cast<const __half*>(a)); }
+};
+__device__ __forceinline__ float4 lds128(const char* a) { return *reinterpret_cast<const float4*>(a); }
+
+// predicated global stores of one element (a predicate instead of a branch around the store)
+template <typename T> struct St;
+template <> struct St<float> {
+  static __device__ __forceinline__ void pred(void* p, float v, bool ok) {
+    asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q st.global.f32 [%0], %1; }" ::"l"(p), "f"(v), "r"((int)ok) : "memory");
+  }
+};
+// 16-bit types: the value is converted into the low half of a 32-bit register (one F2FP) and stored from there - PTX lets a
+// store's source register be wider than the access (it is chopped), which avoids the PRMT a 16-bit register would cost
+template <> struct St<__nv_bfloat16> {
+  static __device__ __forceinline__ void pred(void* p, float v, bool ok) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.f), "f"(v));
+    asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q st.global.b16 [%0], %1; }" ::"l"(p), "r"(r), "r"((int)ok) : "memory");
+  }
+};
+template <> struct St<__half> {
+  static __device__ __forceinline__ void pred(void* p, float v, bool ok) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.f), "f"(v));
+    asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q st.global.b16 [%0], %1; }" ::"l"(p), "r"(r), "r"((int)ok) : "memory");
+  }
+};
+
+enum { FM_UNI = 0, FM_STASH = 1, FM_COMBINE = 2 };
+
+#ifndef CM_FWDLC_MINB
+#define CM_FWDLC_MINB 4
+#endif
+#ifndef CM_FWDLC_NPOLY
+#define CM_FWDLC_NPOLY 2
+#endif
+
+template <typename T, int NPOLY, bool SOFTPLUS>
+__global__ void __launch_bounds__(kWarps * 32, CM_FWDLC_MINB) scan_fwd_lc_kernel(const __grid_constant__ FwdParams P) {
+  constexpr int ES = (int)sizeof(T);
+  constexpr int ROWB = 32 * ES;
+  constexpr bool F32IO = sizeof(T) == 4;
+  constexpr bool PRECISE = F32IO;
+  constexpr uint32_t kTileBytes = kT * ROWB;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpSmem<T>& S = reinterpret_cast<WarpSmem<T>*>(smem_raw)[warp];
+
+  const int ndir = P.ndir;
+  const int item = (ndir == 2) ? blockIdx.x * (kWarps / 2) + (warp >> 1) : blockIdx.x * kWarps + warp;
+  const int DIR = (ndir == 2) ? (warp & 1) : 0;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kStages; ++i) tma::mbar_init(&S.full[i], 1);
+    tma::fence_barrier_init();
+  }
+  __syncwarp();
+  if (item >= P.n_items) return;            // both warps of a channel block leave together: the pair barrier stays consistent
+  const FwdDir& d = P.dir[DIR];
+  const int b = item / P.groups;
+  const int c0 = (item - b * P.groups) * 32;
+  const int ch = c0 + lane;
+  const int L = P.L;
+  const bool rev = d.reverse != 0;
+  const bool has_z = P.has_z != 0;
+
+  float2 kA[8], h[8];
+  {
+    const float* Ap = d.A + (int64_t)ch * d.A_sd;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      kA[j] = make_float2(__ldg(Ap + (2 * j) * d.A_sn) * kLog2e, __ldg(Ap + (2 * j + 1) * d.A_sn) * kLog2e);
+      h[j] = make_float2(0.f, 0.f);
+    }
+  }
+  const float Dsk = d.Dskip ? __ldg(d.Dskip + ch) : 0.f;
+  const float bias = d.bias ? __ldg(d.bias + ch) : 0.f;
+  char* po = d.out + b * d.out_sb + (int64_t)ch * ES;
+  char* ppre = (P.has_pre && d.pre) ? d.pre + b * d.pre_sb + (int64_t)ch * ES : nullptr;
+  float* ckp = d.ckpt ? d.ckpt + b * d.ckpt_sb + (int64_t)ch * d.ckpt_sd : nullptr;
+
+  // this lane's column in the ring; the row of processed step k is `first + k * rowstep` (descending rows for the reverse
+  // direction: a tile holds ascending time)
+  const char* const stage0 = reinterpret_cast<const char*>(&S.stage[0]);
+  constexpr int kStageBytes = (int)sizeof(Stage<T>);
+  constexpr int OFF_U = 0, OFF_DL = kTileBytes, OFF_Z = 2 * kTileBytes, OFF_ST = 3 * kTileBytes, OFF_BC = 4 * kTileBytes;
+  int rowstep = rev ? -ROWB : ROWB;
+  const int first = rev ? (kT - 1) * ROWB : 0;
+  float* const bcf = &S.bcf[0][0];
+  // loop invariants pinned in registers: read through P.dir[DIR] they are re-fetched from the constant bank (LDC with a
+  // register index + R2UR) at every use inside the unrolled tile
+  int out_ss = d.out_ss, pre_ss = d.pre_ss;
+  float bias_r = bias, Dsk_r = Dsk, scale_r = P.scale;
+  asm volatile("" : "+r"(rowstep), "+r"(out_ss), "+r"(pre_ss), "+f"(bias_r), "+f"(Dsk_r), "+f"(scale_r), "+l"(po), "+l"(ppre), "+l"(ckp));
+
+  int it = 0;                               // tiles issued == tiles consumed so far (ring slot = it & 1)
+  const int nrange = (ndir == 2) ? 2 : 1;
+#pragma unroll 1
+  for (int range = 0; range < nrange; ++range) {
+    if (range == 1) {
+      // the partner direction's stash of the other half must be complete and visible to the TMA unit (async proxy)
+      __threadfence();
+      tma::fence_proxy_async_all();
+      if (warp >> 1) asm volatile("bar.sync 2, 64;" ::: "memory"); else asm volatile("bar.sync 1, 64;" ::: "memory");
+    }
+    const int mode = (ndir == 1) ? FM_UNI : (range == 0 ? FM_STASH : FM_COMBINE);
+    const int s_begin = range == 0 ? 0 : d.s1, s_end = (ndir == 1 || range == 1) ? L : d.s1;
+    const int nst = s_end - s_begin;
+    const int ntile = nst > 0 ? cm_ceil_div(nst, kT) : 0;
+    const bool need_z = has_z && mode != FM_STASH;
+    const bool need_st = mode == FM_COMBINE;
+    const bool stash_mode = mode == FM_STASH;
+    const bool write_pre = !stash_mode && ppre != nullptr;
+    int jck = range == 0 ? 0 : cm_ceil_div(d.s1, CM_SCAN_CKPT_STEPS);   // next checkpoint slot
+
+    auto issue = [&](int t, int itx) {      // lane 0: tile t of this range -> ring slot of tile counter itx
+      const int slot = itx & 1;
+      const int s0 = s_begin + t * kT;
+      const int t0 = rev ? (L - s0 - kT) : s0;
+      Stage<T>& st = S.stage[slot];
+      uint64_t* bar = &S.full[slot];
+      tma::mbar_expect_tx(bar, kTileBytes * (3u + (need_z ? 1u : 0u) + (need_st ? 1u : 0u)));
+      tma::load_3d(&st.u[0][0], &d.m_u, bar, c0, t0, b);
+      tma::load_3d(&st.dl[0][0], &d.m_dl, bar, c0, t0, b);
+      tma::load_3d(&st.bc[0][0], &d.m_bc, bar, 0, t0, b);
+      if (need_z) tma::load_3d(&st.z[0][0], &P.m_z, bar, c0, t0, b);
+      if (need_st) tma::load_3d(&st.st[0][0], &P.m_st, bar, c0, t0, b);
+    };
+    if (lane == 0) {
+      if (ntile > 0) issue(0, it);
+      if (ntile > 1) issue(1, it + 1);
+    }
+
+#pragma unroll 1
+    for (int t = 0; t < ntile; ++t, ++it) {
+      const int slot = it & 1;
+      const int s0 = s_begin + t * kT;
+      const int nvalid = s_end - s0;        // steps of this tile inside the range (may exceed kT)
+      tma::mbar_wait(&S.full[slot], (it >> 1) & 1);
+      const char* const col = stage0 + slot * kStageBytes + first + lane * ES;   // this lane's column, processed step 0
+      if (!F32IO) {
+        // B|C rows to fp32, processed order: lane = element (B[0..15] | C[0..15]); 16 independent load -> store chains
+        float v[kT];
+#pragma unroll
+        for (int k = 0; k < kT; ++k) v[k] = Ld<T>::at(col + OFF_BC + k * rowstep);
+#pragma unroll
+        for (int k = 0; k < kT; ++k) bcf[k * 32 + lane] = v[k];
+        __syncwarp();
+      }
+      const char* const bcrow0 = stage0 + slot * kStageBytes + first + OFF_BC;    // fp32 I/O: B|C rows read in place
+      char* const pos0 = po + (int64_t)s0 * out_ss;                              // output rows of the tile's first step
+      char* const pps0 = write_pre ? ppre + (int64_t)s0 * pre_ss : nullptr;
+
+      // per-step scalars (u, dt = softplus(delta + bias), dt*u) of a group of kG steps: kG independent chains, evaluated
+      // one group AHEAD of the recurrence that consumes them
+      float uu[kG], dtv[kG], duv[kG];
+      auto scalars = [&](int g, float (&u_)[kG], float (&dt_)[kG], float (&du_)[kG]) {
+#pragma unroll
+        for (int i = 0; i < kG; ++i) {
+          const int k = g * kG + i;
+          const char* a = col + k * rowstep;
+          u_[i] = Ld<T>::at(a + OFF_U);
+          const float x = Ld<T>::at(a + OFF_DL) + bias_r;
+          float dt = SOFTPLUS ? softplus_fwd<PRECISE>(x) : x;
+          dt = (k < nvalid) ? dt : 0.f;     // a missing step leaves the state unchanged (a = 1, input 0)
+          dt_[i] = dt;
+          du_[i] = dt * u_[i];
+        }
+      };
+      scalars(0, uu, dtv, duv);
+
+#pragma unroll
+      for (int g = 0; g < kT / kG; ++g) {
+        float un[kG], dtn[kG], dun[kG];
+        if (g + 1 < kT / kG) scalars(g + 1, un, dtn, dun);
+        float yv[kG];
+#pragma unroll
+        for (int i = 0; i < kG; ++i) {
+          const int k = g * kG + i;
+          if ((k % CM_SCAN_CKPT_STEPS) == 0) {
+            if (ckp != nullptr && k < nvalid) {
+              float4* dst = reinterpret_cast<float4*>(ckp + (int64_t)jck * 16);
+              dst[0] = make_float4(h[0].x, h[0].y, h[1].x, h[1].y);
+              dst[1] = make_float4(h[2].x, h[2].y, h[3].x, h[3].y);
+              dst[2] = make_float4(h[4].x, h[4].y, h[5].x, h[5].y);
+              dst[3] = make_float4(h[6].x, h[6].y, h[7].x, h[7].y);
+            }
+            ++jck;
+          }
+          const float2 dt2 = make_float2(dtv[i], dtv[i]), du2 = make_float2(duv[i], duv[i]);
+          const char* br = F32IO ? (bcrow0 + k * rowstep) : reinterpret_cast<const char*>(bcf + k * 32);
+          float4 b4[4], c4[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) b4[q] = lds128(br + q * 16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) c4[q] = lds128(br + 64 + q * 16);
+          float2 a2[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a2[j] = fmul2(dt2, kA[j]);
+#pragma unroll
+          for (int j = 0; j < 8 - NPOLY; ++j) a2[j] = make_float2(ex2(a2[j].x), ex2(a2[j].y));
+#pragma unroll
+          for (int j = 8 - NPOLY; j < 8; ++j) a2[j] = ex2_poly2(a2[j]);
+          float2 ub[8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            ub[2 * q] = fmul2(du2, make_float2(b4[q].x, b4[q].y));
+            ub[2 * q + 1] = fmul2(du2, make_float2(b4[q].z, b4[q].w));
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) h[j] = ffma2(a2[j], h[j], ub[j]);
+          float2 ya = fmul2(make_float2(c4[0].x, c4[0].y), h[0]);
+          float2 yb = fmul2(make_float2(c4[0].z, c4[0].w), h[1]);
+#pragma unroll
+          for (int q = 1; q < 4; ++q) {
+            ya = ffma2(make_float2(c4[q].x, c4[q].y), h[2 * q], ya);
+            yb = ffma2(make_float2(c4[q].z, c4[q].w), h[2 * q + 1], yb);
+          }
+          const float2 ys = fadd2(ya, yb);
+          yv[i] = fmaf(Dsk_r, uu[i], ys.x + ys.y);
+        }
+        // ---- epilogue of the group (one uniform branch per group): stash, or combine with the partner's stash + gate
+        if (stash_mode) {
+#pragma unroll
+          for (int i = 0; i < kG; ++i) {
+            const int k = g * kG + i;
+            St<T>::pred(pos0 + (int64_t)k * out_ss, yv[i], k < nvalid);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < kG; ++i) {
+            const int k = g * kG + i;
+            const bool valid = k < nvalid;
+            const char* a = col + k * rowstep;
+            float tot = yv[i];
+            if (need_st) tot += Ld<T>::at(a + OFF_ST);
+            float val = tot * scale_r;
+            if (need_z) {
+              const float zz = Ld<T>::at(a + OFF_Z);
+              val *= zz * sigmoid_sel<PRECISE>(zz);
+            }
+            St<T>::pred(pps0 + (int64_t)k * pre_ss, tot, valid && write_pre);
+            St<T>::pred(pos0 + (int64_t)k * out_ss, val, valid);
+          }
+        }
+        if (g + 1 < kT / kG) {
+#pragma unroll
+          for (int i = 0; i < kG; ++i) { uu[i] = un[i]; dtv[i] = dtn[i]; duv[i] = dun[i]; }
+        }
+      }
+      __syncwarp();                          // every lane is done with this stage (and with bcf)
+      if (lane == 0 && t + kStages < ntile) {
+        tma::fence_proxy_async_smem();
+        issue(t + kStages, it + kStages);
+      }
+    }
+  }
+
+  if (d.last != nullptr) {
+    float* ls = d.last + b * d.ls_sb + (int64_t)ch * d.ls_sd;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ls[(2 * j) * d.ls_sn] = h[j].x;
+      ls[(2 * j + 1) * d.ls_sn] = h[j].y;
+    }
+  }
+}
+
+// ---- host --------------------------------------------------------------------------------------------------------------
+static bool step_stride32(int64_t sl_elems, int es, bool reverse, int32_t* out) {
+  const int64_t v = (reverse ? -sl_elems : sl_elems) * es;
+  if (v > INT32_MAX / 2 || v < INT32_MIN / 2) return false;
+  *out = (int32_t)v;
+  return true;
+}
+
+template <typename T>
+static bool build_params(const cm_scan_fwd_args& a, FwdParams* P) {
+  constexpr int ES = (int)sizeof(T);
+  if (a.dstate != 16 || a.dim % 32 != 0) return false;
+  if (a.out.ptr == nullptr || a.out.sd != 1) return false;
+  if (a.z.ptr != nullptr && a.z.sd != 1) return false;
+  if (a.out_pre.ptr != nullptr && a.out_pre.sd != 1) return false;
+  P->L = a.seqlen; P->dim = a.dim; P->groups = a.dim / 32; P->n_items = a.batch * (a.dim / 32); P->ndir = a.ndir;
+  P->has_z = a.z.ptr != nullptr; P->has_pre = a.out_pre.ptr != nullptr;
+  P->flags = a.flags; P->scale = a.out_scale;
+  const int64_t L = a.seqlen, Bt = a.batch, D = a.dim;
+  if (a.z.ptr != nullptr && !tma::make_map_blc(&P->m_z, a.z.ptr, ES, D, L, Bt, a.z.sl, a.z.sb, 32, kT)) return false;
+  if (a.ndir == 2) {
+    if (!tma::make_map_blc(&P->m_st, a.out.ptr, ES, D, L, Bt, a.out.sl, a.out.sb, 32, kT)) return false;
+  }
+  for (int r = 0; r < a.ndir; ++r) {
+    const cm_scan_dir& s = a.dir[r];
+    FwdDir& d = P->dir[r];
+    if (s.bc_const) return false;
+    if (s.u.sd != 1 || s.delta.sd != 1 || s.Bm.sd != 1 || s.Cm.sd != 1) return false;
+    // one 32-element B|C row per step
+    if (static_cast<const char*>(s.Cm.ptr) != static_cast<const char*>(s.Bm.ptr) + 16 * ES || s.Cm.sl != s.Bm.sl || s.Cm.sb != s.Bm.sb)
+      return false;
+    if (s.ckpt != nullptr && ((reinterpret_cast<uintptr_t>(s.ckpt) & 15) != 0 || (s.ckpt_sb % 4) != 0 || (s.ckpt_sd % 4) != 0))
+      return false;
+    if (!tma::make_map_blc(&d.m_u, s.u.ptr, ES, D, L, Bt, s.u.sl, s.u.sb, 32, kT)) return false;
+    if (!tma::make_map_blc(&d.m_dl, s.delta.ptr, ES, D, L, Bt, s.delta.sl, s.delta.sb, 32, kT)) return false;
+    if (!tma::make_map_blc(&d.m_bc, s.Bm.ptr, ES, 32, L, Bt, s.Bm.sl, s.Bm.sb, 32, kT)) return false;
+    const bool rev = s.reverse != 0;
+    d.reverse = rev;
+    const int64_t l0 = rev ? L - 1 : 0;
+    d.out = static_cast<char*>(a.out.ptr) + l0 * a.out.sl * ES;
+    d.out_sb = a.out.sb * ES;
+    if (!step_stride32(a.out.sl, ES, rev, &d.out_ss)) return false;
+    d.pre = nullptr; d.pre_sb = 0; d.pre_ss = 0;
+    if (a.out_pre.ptr != nullptr) {
+      d.pre = static_cast<char*>(a.out_pre.ptr) + l0 * a.out_pre.sl * ES;
+      d.pre_sb = a.out_pre.sb * ES;
+      if (!step_stride32(a.out_pre.sl, ES, rev, &d.pre_ss)) return false;
+    }
+    d.s1 = cm_first_range(a.seqlen, a.ndir, s.reverse);
+    d.A = s.A; d.A_sd = s.A_sd; d.A_sn = s.A_sn;
+    d.Dskip = s.Dskip; d.bias = s.delta_bias;
+    d.ckpt = s.ckpt; d.ckpt_sb = s.ckpt_sb; d.ckpt_sd = s.ckpt_sd;
+    d.last = s.last_state; d.ls_sb = s.ls_sb; d.ls_sd = s.ls_sd; d.ls_sn = s.ls_sn;
+  }
+  return true;
+}
+
+template <typename T, int NPOLY, bool SOFTPLUS>
+static int launch(const FwdParams& P, cudaStream_t st) {
+  const size_t smem = sizeof(WarpSmem<T>) * kWarps;
+  auto kern = scan_fwd_lc_kernel<T, NPOLY, SOFTPLUS>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device: every launch
+  if (e != cudaSuccess) return (int)e;
+  const int items_per_cta = kWarps / P.ndir;
+  const unsigned grid = (unsigned)((P.n_items + items_per_cta - 1) / items_per_cta);
+  kern<<<grid, kWarps * 32, smem, st>>>(P);
+  CM_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+static int try_t(const cm_scan_fwd_args& a, cudaStream_t st, int* rc) {
+  FwdParams P;
+  if (!build_params<T>(a, &P)) return 0;
+  // the FMA-pipe exponentials are for 16-bit I/O (error budget 2e-2); fp32 I/O keeps every exponential on the MUFU pipe
+  const bool sp = (a.flags & CM_FLAG_DELTA_SOFTPLUS) != 0;
+  if (sizeof(T) == 4 || getenv("CM_SCAN_NO_POLY") != nullptr) *rc = sp ? launch<T, 0, true>(P, st) : launch<T, 0, false>(P, st);
+  else *rc = sp ? launch<T, CM_FWDLC_NPOLY, true>(P, st) : launch<T, CM_FWDLC_NPOLY, false>(P, st);
+  return 1;
+}
+
+}  // namespace lc
+
+// returns 1 if launched (result in *rc), 0 if the lane-per-channel TMA path does not apply
+int scan_fwd_try_lane_channel(const cm_scan_fwd_args& a, cudaStream_t st, int* rc) {
+  switch (a.dtype) {
+    case CM_F32: return lc::try_t<float>(a, st, rc);
+    case CM_BF16: return lc::try_t<__nv_bfloat16>(a, st, rc);
+    default: return lc::try_t<__half>(a, st, rc);
+  }
+}
+
+}  // namespace cm

@@ -229,10 +229,7 @@ def scan_backward(dirs, ckpts, dout, z=None, out_pre=None, out_scale=1.0, delta_
     a.dtype = cabi.dtype_code(u0.dtype)
     a.flags = cabi.CM_FLAG_DELTA_SOFTPLUS if delta_softplus else 0
     a.out_scale = float(out_scale)
-    lpc = int(lanes) or int(os.environ.get("CM_SCAN_LANES", "0")) or lib.cm_scan_pick_lanes_bwd(Bt, D, len(dirs))
-    a.lanes_per_channel = lpc
-    slab_ch = lib.cm_scan_slab_channels(lpc)
-    n_slab = (D + slab_ch - 1) // slab_ch
+    a.lanes_per_channel = int(lanes) or int(os.environ.get("CM_SCAN_LANES", "0"))     # 0 = library default
     keep = []
     res = dict(du=[], ddelta=[], dB=[], dC=[], dA=[], dD=[], dbias=[], dz=None)
     parts = []
@@ -245,16 +242,6 @@ def scan_backward(dirs, ckpts, dout, z=None, out_pre=None, out_scale=1.0, delta_
         du = empty_like_bdl(d["u"])
         ddelta = empty_like_bdl(d["delta"])
         bd.du, bd.ddelta = cabi.t3(du), cabi.t3(ddelta)
-        if const_bc:
-            bc_part = torch.empty((Bt, D, 32), dtype=torch.float32, device=dev)
-        else:
-            bc_part = torch.empty((Bt, n_slab, L, 32), dtype=torch.float32, device=dev)
-        dA_part = torch.empty((Bt, D, 16), dtype=torch.float32, device=dev)
-        dD_part = torch.empty((Bt, D), dtype=torch.float32, device=dev) if d.get("D") is not None else None
-        db_part = torch.empty((Bt, D), dtype=torch.float32, device=dev) if d.get("delta_bias") is not None else None
-        bd.dBC_part, bd.dA_part = bc_part.data_ptr(), dA_part.data_ptr()
-        bd.dD_part, bd.dbias_part = cabi.ptr(dD_part), cabi.ptr(db_part)
-        parts.append((bc_part, dA_part, dD_part, db_part))
         res["du"].append(du)
         res["ddelta"].append(ddelta)
     _require_cuda(dout, "dout")
@@ -269,6 +256,23 @@ def scan_backward(dirs, ckpts, dout, z=None, out_pre=None, out_scale=1.0, delta_
         dz = dz_out if dz_out is not None else empty_like_bdl(z)
         a.z, a.out_pre, a.dz = cabi.t3(z), cabi.t3(out_pre), cabi.t3(dz)
         res["dz"] = dz
+    # the slab width of the dB/dC partial tensor depends on the kernel the library will take for these tensors
+    slab_ch = lib.cm_scan_bwd_slab_channels(C.byref(a))
+    if slab_ch <= 0:
+        cabi.check(slab_ch, "cm_scan_bwd_slab_channels")
+    n_slab = (D + slab_ch - 1) // slab_ch
+    for r, d in enumerate(dirs):
+        bd = a.dir[r]
+        if const_bc:
+            bc_part = torch.empty((Bt, D, 32), dtype=torch.float32, device=dev)
+        else:
+            bc_part = torch.empty((Bt, n_slab, L, 32), dtype=torch.float32, device=dev)
+        dA_part = torch.empty((Bt, D, 16), dtype=torch.float32, device=dev)
+        dD_part = torch.empty((Bt, D), dtype=torch.float32, device=dev) if d.get("D") is not None else None
+        db_part = torch.empty((Bt, D), dtype=torch.float32, device=dev) if d.get("delta_bias") is not None else None
+        bd.dBC_part, bd.dA_part = bc_part.data_ptr(), dA_part.data_ptr()
+        bd.dD_part, bd.dbias_part = cabi.ptr(dD_part), cabi.ptr(db_part)
+        parts.append((bc_part, dA_part, dD_part, db_part))
     st = cabi.stream_ptr()
     _call("cm_scan_bwd", lib.cm_scan_bwd, C.byref(a), st, tag=(Bt, D, L, len(dirs)))
 

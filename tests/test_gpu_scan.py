@@ -13,15 +13,24 @@ SUM_KEYS = ("A", "B", "C", "D", "delta_bias")     # gradients that are sums over
 
 
 def _cuda(ins, layout="tc"):
+    """layout: "tc" time-contiguous (B, D, L) memory (the reference's); "cl" channel-last memory, B and C separate tensors;
+    "xdbl" channel-last with B | C | dt-pad packed in ONE (B, L, 48) row-major buffer the way the module's x_dbl holds them
+    (mamba_inner._aligned_proj_weights) - the layout the TMA kernels (scan_fwd_lc.cu / scan_bwd_lc.cu) take."""
     out = {}
     for k, v in ins.items():
         if v is None:
             out[k] = None
             continue
         t = v.cuda()
-        if layout == "cl" and t.dim() == 3:
+        if layout in ("cl", "xdbl") and t.dim() == 3:
             t = channel_last(t)
         out[k] = t
+    if layout == "xdbl" and out.get("B") is not None and out["B"].dim() == 3 and out["B"].shape[1] == 16:
+        Bt, N, L = out["B"].shape
+        xd = torch.zeros(Bt, L, 2 * N + 16, dtype=out["B"].dtype, device="cuda")
+        xd[..., :N] = out["B"].transpose(1, 2)
+        xd[..., N:2 * N] = out["C"].transpose(1, 2)
+        out["B"], out["C"] = xd[..., :N].transpose(1, 2), xd[..., N:2 * N].transpose(1, 2)
     return out
 
 
@@ -250,14 +259,14 @@ def test_state_parallel_forward_matches_oracle(cpl, dtype, shape, monkeypatch):
     assert_close(bi["out_pre"].float(), bi_o["out_pre"].float(), dtype, floor="max", what="sp out_pre")
 
 
-def _bidir_backward_case(Bt, D, L, dtype, seed):
+def _bidir_backward_case(Bt, D, L, dtype, seed, layout="cl"):
     from mamba_asr_b200 import kernels as K
     N = 16
     f = make_scan_inputs(Bt, D, L, N, dtype, seed=seed)
     bw = make_scan_inputs(Bt, D, L, N, dtype, seed=seed + 1)
     dirs = []
     for src, rev in ((f, False), (bw, True)):
-        c = _cuda(src, "cl")
+        c = _cuda(src, layout)
         dirs.append(dict(u=c["u"], delta=c["delta"], A=c["A"], B=c["B"], C=c["C"], D=c["D"],
                          delta_bias=c["delta_bias"], reverse=rev))
     zc = channel_last(f["z"].cuda())
@@ -444,14 +453,15 @@ def _check_bidir_grads(g, lf, lb, dtype, tag):
         assert_close(g["dbias"][r], leaf["delta_bias"].grad, dtype, floor="max", what=f"{tag} dbias[{r}]")
 
 
-@pytest.mark.parametrize("kernel", ["default", "no_sp", "lanes2", "generic"])
+@pytest.mark.parametrize("kernel", ["default", "tma", "no_sp", "lanes2", "generic"])
 @pytest.mark.parametrize("shape", [(2, 64, 45), (1, 96, 203), (2, 32, 9)])
 def test_bf16_backward_matches_oracle_autograd(kernel, shape, monkeypatch):
     """bf16 I/O (what BASELINE configs 2-4 train with): every backward kernel - the default, the lane-per-channel
     kernels (1 and 2 lanes) and the generic-stride kernel ((B, D, L) memory) - against autograd through the oracle fed the
     bf16-rounded inputs and computed in fp32; tolerance rtol 2e-2 (BASELINE.json north_star)."""
     Bt, D, L = shape
-    K, f, bw, dirs, zc, cot = _bidir_backward_case(Bt, D, L, torch.bfloat16, seed=91)
+    K, f, bw, dirs, zc, cot = _bidir_backward_case(Bt, D, L, torch.bfloat16, seed=91,
+                                                   layout="xdbl" if kernel == "tma" else "cl")
     if kernel == "no_sp":
         monkeypatch.setenv("CM_SCAN_NO_SP", "1")
     elif kernel == "lanes2":
@@ -474,7 +484,7 @@ def test_bf16_backward_matches_oracle_autograd(kernel, shape, monkeypatch):
 def test_benchmark_widths_forward_backward_match_oracle(dtype, D, L):
     """The channel widths of the BASELINE configs (D = 288: configs 1/2, 512: configs 3/5, 1024: config 4) with short
     sequences the CPU oracle finishes in seconds: fused bidirectional forward and every gradient, fp32 and bf16."""
-    K, f, bw, dirs, zc, cot = _bidir_backward_case(2, D, L, dtype, seed=100 + D + L)
+    K, f, bw, dirs, zc, cot = _bidir_backward_case(2, D, L, dtype, seed=100 + D + L, layout="xdbl")
     ref, lf, lb = _oracle_bidir_grads(f, bw, cot, dtype)
     res = K.scan_forward(dirs, z=zc, out_scale=0.5, delta_softplus=True, need_ckpt=True, need_out_pre=True)
     assert_close(res["out"].float(), ref, dtype, what="out")
@@ -495,3 +505,162 @@ def test_benchmark_widths_forward_backward_match_oracle(dtype, D, L):
     assert_close(g1["dB"][0].float(), lu["B"].grad, dtype, floor="max", what="uni dB")
     assert_close(g1["dC"][0].float(), lu["C"].grad, dtype, floor="max", what="uni dC")
     assert_close(g1["dA"][0], lu["A"].grad, dtype, floor="max", what="uni dA")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(2, 64, 67), (1, 32, 131), (3, 96, 8), (2, 32, 9), (2, 32, 1), (2, 64, 16), (1, 32, 17),
+                                   (2, 32, 33), (1, 160, 300), (5, 32, 15), (1, 64, 32), (3, 32, 48)])
+def test_tma_forward_matches_oracle(dtype, shape, monkeypatch):
+    """scan_fwd_lc.cu (lane = channel, TMA-staged operands; the default for the module's x_dbl layout): unidirectional
+    (gate, last state, checkpoints, no-softplus) and fused bidirectional outputs against the oracle over tile-boundary and
+    ragged lengths, odd numbers of channel blocks (inactive warps), and against the state-parallel kernel's checkpoints."""
+    from mamba_asr_b200 import kernels as K
+    from oracle.scan_ref import selective_scan_oracle
+    Bt, D, L = shape
+    N = 16
+    f = make_scan_inputs(Bt, D, L, N, dtype, seed=131)
+    bw = make_scan_inputs(Bt, D, L, N, dtype, seed=132)
+    z = f["z"]
+    fl = lambda t: t.flip(-1)
+    of, lf = selective_scan_oracle(f["u"], f["delta"], f["A"], f["B"], f["C"], f["D"], z, f["delta_bias"], True,
+                                   return_last_state=True)
+    ob = selective_scan_oracle(fl(bw["u"]), fl(bw["delta"]), bw["A"], fl(bw["B"]), fl(bw["C"]), bw["D"], fl(z),
+                               bw["delta_bias"], True)
+    o_plain = selective_scan_oracle(f["u"], f["delta"], f["A"], f["B"], f["C"], None, None, None, False)
+    dirs = []
+    for src, rev in ((f, False), (bw, True)):
+        c = _cuda(src, "xdbl")
+        dirs.append(dict(u=c["u"], delta=c["delta"], A=c["A"], B=c["B"], C=c["C"], D=c["D"],
+                         delta_bias=c["delta_bias"], reverse=rev))
+    zc = channel_last(z.cuda())
+    uni = K.scan_forward(dirs[:1], z=zc, delta_softplus=True, need_last_state=True, need_ckpt=True)
+    assert_close(uni["out"].float(), of.float(), dtype, what="tma uni out")
+    assert_close(uni["last_state"][0], lf, dtype, what="tma last_state")
+    plain = K.scan_forward([dict(dirs[0], D=None, delta_bias=None)], z=None, delta_softplus=False)
+    assert_close(plain["out"].float(), o_plain.float(), dtype, what="tma plain out (no D, no z, no softplus)")
+    bi = K.scan_forward(dirs, z=zc, out_scale=0.5, delta_softplus=True, need_ckpt=True, need_out_pre=True)
+    assert_close(bi["out"].float(), 0.5 * of.float() + 0.5 * fl(ob).float(), dtype,
+                 floor="rms" if dtype == torch.float32 else "max", what="tma bidir out")
+    # same checkpoints / pre-gate sums as the state-parallel kernel (the backward kernels read them)
+    monkeypatch.setenv("CM_SCAN_NO_LC", "1")
+    uni_o = K.scan_forward(dirs[:1], z=zc, delta_softplus=True, need_last_state=True, need_ckpt=True)
+    bi_o = K.scan_forward(dirs, z=zc, out_scale=0.5, delta_softplus=True, need_ckpt=True, need_out_pre=True)
+    nck1, nck2 = K.num_ckpt(L, 1), K.num_ckpt(L, 2)
+    assert_close(uni["ckpt"][0][:, :, :nck1], uni_o["ckpt"][0][:, :, :nck1], dtype, floor="max", what="tma ckpt uni")
+    for r in range(2):
+        assert_close(bi["ckpt"][r][:, :, :nck2], bi_o["ckpt"][r][:, :, :nck2], dtype, floor="max", what="tma ckpt bidir")
+    assert_close(bi["out_pre"].float(), bi_o["out_pre"].float(), dtype, floor="max", what="tma out_pre")
+
+
+def test_tma_forward_full_size_config3_against_state_parallel(monkeypatch):
+    """ConMamba-large shape (B 64, D 512, L 501, bf16): the TMA kernel against the state-parallel kernel (both pinned to
+    the oracle at small sizes), plus bit-identical repeat launches."""
+    from mamba_asr_b200 import kernels as K
+    Bt, D, L, N = 64, 512, 501, 16
+    g = torch.Generator(device="cuda").manual_seed(5)
+    rn = lambda *sh: torch.randn(*sh, device="cuda", generator=g)
+    cl = lambda: rn(Bt, L, D).bfloat16().transpose(1, 2)
+    z = cl()
+    dirs = []
+    for rev in (False, True):
+        xd = rn(Bt, L, 48).bfloat16()
+        dirs.append(dict(u=cl(), delta=(0.5 * rn(Bt, L, D)).bfloat16().transpose(1, 2), A=-torch.exp(0.3 * rn(D, N)),
+                         B=xd[..., :N].transpose(1, 2), C=xd[..., N:2 * N].transpose(1, 2), D=torch.ones(D, device="cuda"),
+                         delta_bias=torch.full((D,), -4.0, device="cuda"), reverse=rev))
+    run = lambda: K.scan_forward(dirs, z=z, out_scale=0.5, delta_softplus=True, need_ckpt=True, need_out_pre=True)
+    a, b = run(), run()
+    assert torch.equal(a["out"], b["out"]) and torch.equal(a["ckpt"][0], b["ckpt"][0])
+    monkeypatch.setenv("CM_SCAN_NO_LC", "1")
+    o = run()
+    assert_close(a["out"].float(), o["out"].float(), torch.bfloat16, floor="max", what="out")
+    assert_close(a["out_pre"].float(), o["out_pre"].float(), torch.bfloat16, floor="max", what="out_pre")
+    for r in range(2):
+        assert_close(a["ckpt"][r], o["ckpt"][r], torch.bfloat16, floor="max", what="ckpt[%d]" % r)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 128, 45), (1, 128, 8), (2, 128, 9), (1, 128, 1), (2, 256, 17), (1, 128, 67), (2, 128, 16),
+                                   (3, 128, 131), (1, 384, 24)])
+def test_tma_backward_matches_autograd(dtype, shape):
+    """scan_bwd_lc.cu (lane = channel, TMA-staged; the default backward for the module's x_dbl layout when dim is a multiple
+    of 128): every gradient of the fused bidirectional block and of unidirectional scans (with and without gate / softplus)
+    against autograd through the oracle (fed the dtype-rounded inputs, computed in fp32), over ragged lengths and tile
+    boundaries."""
+    from oracle.scan_ref import selective_scan_oracle
+    Bt, D, L = shape
+    K, f, bw, dirs, zc, cot = _bidir_backward_case(Bt, D, L, dtype, seed=141, layout="xdbl")
+    ref, lf, lb = _oracle_bidir_grads(f, bw, cot, dtype)
+    res = K.scan_forward(dirs, z=zc, out_scale=0.5, delta_softplus=True, need_ckpt=True, need_out_pre=True)
+    g = K.scan_backward(dirs, res["ckpt"], channel_last(cot.cuda()), z=zc, out_pre=res["out_pre"], out_scale=0.5,
+                        delta_softplus=True)
+    _check_bidir_grads(g, lf, lb, dtype, "tma bidir")
+    # unidirectional, no gate, no softplus (reverse direction alone: the decoder never uses it, the kernel must still be right)
+    for r, src in ((0, f), (1, bw)):
+        lu = {k: v.float().clone().requires_grad_(True) for k, v in src.items() if k != "z"}
+        fl = (lambda t: t.flip(-1)) if r == 1 else (lambda t: t)
+        ou = fl(selective_scan_oracle(fl(lu["u"]), fl(lu["delta"]), lu["A"], fl(lu["B"]), fl(lu["C"]), lu["D"], None,
+                                      lu["delta_bias"], False))
+        (ou * cot.float()).sum().backward()
+        r1 = K.scan_forward(dirs[r:r + 1], delta_softplus=False, need_ckpt=True)
+        assert_close(r1["out"].float(), ou.detach(), dtype, what=f"uni[{r}] out")
+        g1 = K.scan_backward(dirs[r:r + 1], r1["ckpt"], channel_last(cot.cuda()), delta_softplus=False)
+        assert_close(g1["du"][0].float(), lu["u"].grad, dtype, what=f"uni[{r}] du")
+        assert_close(g1["ddelta"][0].float(), lu["delta"].grad, dtype, what=f"uni[{r}] ddelta")
+        assert_close(g1["dB"][0].float(), lu["B"].grad, dtype, floor="max", what=f"uni[{r}] dB")
+        assert_close(g1["dC"][0].float(), lu["C"].grad, dtype, floor="max", what=f"uni[{r}] dC")
+        assert_close(g1["dD"][0], lu["D"].grad, dtype, floor="max", what=f"uni[{r}] dD")
+        if L > 1:
+            assert_close(g1["dA"][0], lu["A"].grad, dtype, floor="max", what=f"uni[{r}] dA")
+
+
+def test_tma_backward_is_deterministic_and_agrees_with_state_parallel(monkeypatch):
+    """Two launches of scan_bwd_lc.cu are bit-identical (fixed-order sums, no atomics); the state-parallel kernel on the same
+    tensors agrees; the library reports 128-channel slabs for this layout and 32-channel slabs otherwise."""
+    import ctypes as C
+    from mamba_asr_b200 import _cabi
+    K, f, bw, dirs, zc, cot = _bidir_backward_case(2, 256, 77, torch.bfloat16, seed=151, layout="xdbl")
+    res = K.scan_forward(dirs, z=zc, out_scale=0.5, delta_softplus=True, need_ckpt=True, need_out_pre=True)
+    run = lambda d_: K.scan_backward(d_, res["ckpt"], channel_last(cot.cuda()), z=zc, out_pre=res["out_pre"], out_scale=0.5,
+                                     delta_softplus=True)
+    a, b = run(dirs), run(dirs)
+    for key in ("du", "ddelta", "dB", "dC", "dA", "dD", "dbias"):
+        for r in range(2):
+            assert torch.equal(a[key][r], b[key][r]), (key, r)
+    assert torch.equal(a["dz"], b["dz"])
+    monkeypatch.setenv("CM_SCAN_NO_LC", "1")
+    o = run(dirs)
+    for key in ("du", "ddelta", "dB", "dC"):
+        for r in range(2):
+            assert_close(a[key][r].float(), o[key][r].float(), torch.bfloat16, floor="max", what=f"{key}[{r}] lc vs sp")
+    for key in ("dA", "dD", "dbias"):
+        for r in range(2):
+            assert_close(a[key][r], o[key][r], torch.bfloat16, floor="max", what=f"{key}[{r}] lc vs sp")
+    assert_close(a["dz"].float(), o["dz"].float(), torch.bfloat16, floor="max", what="dz lc vs sp")
+
+
+def test_tma_backward_full_size_config3(monkeypatch):
+    """ConMamba-large shape (B 64, D 512, L 501, bf16), x_dbl layout: the TMA backward against the state-parallel kernel."""
+    from mamba_asr_b200 import kernels as K
+    Bt, D, L, N = 64, 512, 501, 16
+    g = torch.Generator(device="cuda").manual_seed(6)
+    rn = lambda *sh: torch.randn(*sh, device="cuda", generator=g)
+    cl = lambda: rn(Bt, L, D).bfloat16().transpose(1, 2)
+    z = cl()
+    dirs = []
+    for rev in (False, True):
+        xd = rn(Bt, L, 48).bfloat16()
+        dirs.append(dict(u=cl(), delta=(0.5 * rn(Bt, L, D)).bfloat16().transpose(1, 2), A=-torch.exp(0.3 * rn(D, N)),
+                         B=xd[..., :N].transpose(1, 2), C=xd[..., N:2 * N].transpose(1, 2), D=torch.ones(D, device="cuda"),
+                         delta_bias=torch.full((D,), -4.0, device="cuda"), reverse=rev))
+    res = K.scan_forward(dirs, z=z, out_scale=0.5, delta_softplus=True, need_ckpt=True, need_out_pre=True)
+    go = cl()
+    run = lambda: K.scan_backward(dirs, res["ckpt"], go, z=z, out_pre=res["out_pre"], out_scale=0.5, delta_softplus=True)
+    a = run()
+    monkeypatch.setenv("CM_SCAN_NO_LC", "1")
+    o = run()
+    assert_close(a["dz"].float(), o["dz"].float(), torch.bfloat16, floor="max", what="dz")
+    for r in range(2):
+        for key in ("du", "ddelta", "dB", "dC"):
+            assert_close(a[key][r].float(), o[key][r].float(), torch.bfloat16, floor="max", what=f"{key}[{r}]")
+        for key in ("dA", "dD", "dbias"):
+            assert_close(a[key][r], o[key][r], torch.bfloat16, floor="max", what=f"{key}[{r}]")

@@ -373,7 +373,7 @@ def main():
             dist.broadcast(p_.data, 0)
     n_params = sum(p.numel() for p in model.parameters())
     is_s2s = hasattr(model, "decoder")
-    opt = TrainStep(model, **OPT) if (train and not args.no_optimizer) else None
+    opt = TrainStep(model, world_size=world, **OPT) if (train and not args.no_optimizer) else None
 
     batch, seconds = wl["batch"], wl["seconds"]
     wav_h, tgt_h = make_batch(cfg, batch, seconds, cfg["seed"] + rank, dev, cfg["output_neurons"])
@@ -388,11 +388,12 @@ def main():
     eager_forward = net.forward      # torch.cuda.make_graphed_callables swaps net.forward for the graph replay
 
     def finish_step():
-        """what follows backward in a training step: the step's only collective, then the optimizer"""
-        if world > 1:
-            allreduce_gradients(model.parameters(), world)     # NCCL over NVLink
+        """what follows backward in a training step: gather the gradients into the flat buffer, the step's only collective
+        (one in-place NCCL all-reduce of that buffer over NVLink), then clip + AdamW (two launches)"""
         if opt is not None:
-            opt.step()
+            opt.step(dist if world > 1 else None)
+        elif world > 1:
+            allreduce_gradients(model.parameters(), world)
 
     def step_eager(w, t):
         if not train:
@@ -570,7 +571,7 @@ def main():
                 cpu_desc = {"kind": "port", "error": repr(ex)}
         config = config_block(args.workload, world)
         config.update({"params": n_params, "launch": graph_note,
-                       "optimizer": ("torch AdamW (fused) + clip_grad_norm_ + Noam lr, inside the timed step" if opt is not None
+                       "optimizer": ("flat-buffer clip + AdamW kernels (cm_sumsq_partial, cm_adamw_step) + Noam lr, inside the timed step" if opt is not None
                                      else ("none (forward-only workload)" if not train else "disabled (--no-optimizer)")),
                        "roofline_timing": "per-kernel CUDA events from 3 eager launches of the same step right after "
                                           "the timed region (kernels inside a graph replay cannot carry events)",

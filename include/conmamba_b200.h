@@ -413,11 +413,38 @@ int cm_ln_act_num_part(int64_t rows, int32_t cols);
 int cm_ln_act_fwd(const cm_ln_act_args* args, void* stream);
 int cm_ln_act_bwd(const cm_ln_act_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Optimizer step on flat fp32 buffers (the optimizer of the training recipes, reference
+ * train_CTC.py:716-717 with hparams/CTC/conmamba_large.yaml:91, 248-252: torch.optim.AdamW + max_grad_norm clipping).
+ *   cm_sumsq_partial: part[i] = sum of g^2 over CTA i's share (cm_optim_num_part(n) fp32 values, fixed order)
+ *   cm_adamw_step   : norm = sqrt(sum part) * grad_scale ; c = (max_grad_norm > 0 ? min(1, max_grad_norm/(norm+1e-6)) : 1)
+ *                     * grad_scale ; g' = c*g ; m = b1*m + (1-b1)*g' ; v = b2*v + (1-b2)*g'^2 ;
+ *                     p = p*(1 - lr*weight_decay) - (lr/bias_corr1) * m / (sqrt(v)/sqrt(bias_corr2) + eps)
+ *                     (bias_corr = 1 - beta^t).  sumsq_part NULL: no clipping, c = grad_scale.  p_bf16 non-NULL: also writes
+ *                     the bf16 copy of p.  n must be a multiple of 4, all pointers 16-byte aligned.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+  float* p;                 /* (n) parameters, updated in place */
+  const float* g;           /* (n) gradients (summed over ranks when grad_scale = 1/world_size) */
+  float* m;                 /* (n) first moment */
+  float* v;                 /* (n) second moment */
+  void* p_bf16;             /* (n) bf16 copy of p, or NULL */
+  const float* sumsq_part;  /* cm_sumsq_partial output, or NULL */
+  float* norm_out;          /* optional device scalar: the gradient norm that was clipped against */
+  int64_t n;
+  int32_t n_part;
+  float lr, beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2, max_grad_norm, grad_scale;
+} cm_adamw_args;
+
+int cm_optim_num_part(int64_t n);
+int cm_sumsq_partial(const float* g, int64_t n, float* part, void* stream);
+int cm_adamw_step(const cm_adamw_args* args, void* stream);
+
 /* library identification: returns CM_ABI_VERSION; writes the compiled-for arch (e.g. 100) to *sm_arch if non-NULL */
 int cm_version(int32_t* sm_arch);
 /* sizeof() of the argument structs, for binding self-checks: 0 cm_tensor3, 1 cm_scan_dir, 2 cm_scan_fwd_args,
  * 3 cm_scan_bwd_dir, 4 cm_scan_bwd_args, 5 cm_conv_dir, 6 cm_conv_args, 7 cm_fbank_args, 8 cm_reduce_job,
- * 9 cm_layernorm_args, 10 cm_dwconv_args, 11 cm_ssm_step_args, 12 cm_add_ln_args, 13 cm_ln_act_args */
+ * 9 cm_layernorm_args, 10 cm_dwconv_args, 11 cm_ssm_step_args, 12 cm_add_ln_args, 13 cm_ln_act_args, 14 cm_adamw_args */
 int cm_abi_sizeof(int32_t which);
 
 #ifdef __cplusplus

@@ -27,7 +27,7 @@ EXPORTS = (
     "cm_fbank_logmel", "cm_fbank_floor", "cm_abi_sizeof", "cm_reduce_multi", "cm_layernorm_num_part", "cm_layernorm_fwd",
     "cm_layernorm_bwd", "cm_scan_fwd_workspace_bytes", "cm_dwconv_num_part", "cm_dwconv_fwd", "cm_dwconv_bwd_weight", "cm_colsum_num_part", "cm_colsum",
     "cm_ssm_step", "cm_add_ln_fwd", "cm_add_ln_bwd", "cm_gelu_dropout_fwd", "cm_gelu_dropout_bwd", "cm_tsmm_num_part", "cm_tsmm",
-    "cm_ln_act_num_part", "cm_ln_act_fwd", "cm_ln_act_bwd",
+    "cm_ln_act_num_part", "cm_ln_act_fwd", "cm_ln_act_bwd", "cm_optim_num_part", "cm_sumsq_partial", "cm_adamw_step",
 )
 CM_REDUCE_MAX_JOBS = 8
 
@@ -160,8 +160,15 @@ class LnActArgs(C.Structure):
                 ("dbeta_part", C.c_void_p)]
 
 
+class AdamWArgs(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("p_bf16", C.c_void_p),
+                ("sumsq_part", C.c_void_p), ("norm_out", C.c_void_p), ("n", C.c_int64), ("n_part", C.c_int32),
+                ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+                ("bias_corr1", C.c_float), ("bias_corr2", C.c_float), ("max_grad_norm", C.c_float), ("grad_scale", C.c_float)]
+
+
 ABI_STRUCTS = (Tensor3, ScanDir, ScanFwdArgs, ScanBwdDir, ScanBwdArgs, ConvDir, ConvArgs, FbankArgs, ReduceJob,
-               LayerNormArgs, DwConvArgs, SsmStepArgs, AddLnArgs, LnActArgs)
+               LayerNormArgs, DwConvArgs, SsmStepArgs, AddLnArgs, LnActArgs, AdamWArgs)
 
 def lib():
     """The loaded shared library; raises (never falls back) when it is absent or stale."""
@@ -217,6 +224,9 @@ def lib():
         L.cm_ln_act_num_part.argtypes = [C.c_int64, C.c_int32]
         L.cm_ln_act_fwd.argtypes = [C.POINTER(LnActArgs), C.c_void_p]
         L.cm_ln_act_bwd.argtypes = [C.POINTER(LnActArgs), C.c_void_p]
+        L.cm_optim_num_part.argtypes = [C.c_int64]
+        L.cm_sumsq_partial.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.cm_adamw_step.argtypes = [C.POINTER(AdamWArgs), C.c_void_p]
         if L.cm_version(None) != CM_ABI_VERSION:
             raise RuntimeError("mamba_asr_b200: %s has a different ABI version; rebuild it" % LIB_PATH)
         for i, st in enumerate(ABI_STRUCTS):

@@ -153,6 +153,7 @@ extern "C" int cm_abi_sizeof(int32_t which) {
     case 11: return (int)sizeof(cm_ssm_step_args);
     case 12: return (int)sizeof(cm_add_ln_args);
     case 13: return (int)sizeof(cm_ln_act_args);
+    case 14: return (int)sizeof(cm_adamw_args);
     default: return CM_ERR_BAD_ARG;
   }
 }

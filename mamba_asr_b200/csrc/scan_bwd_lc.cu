@@ -1,4 +1,6 @@
-// Selective-scan backward, "lc" kernel (lane = channel, TMA-staged) for sm_100a - the default backward kernel of round 2.
+// Selective-scan backward, "lc" kernel (lane = channel, TMA-staged) for sm_100a.  Parity-green but slower than the
+// state-parallel kernel at every measured shape, so cm_scan_bwd takes it only with CM_SCAN_LC_BWD=1 (kept: it is the
+// measured data point behind the analysis in DESIGN.md section 3.2, and the TMA / slab-negotiation plumbing is shared).
 //
 // Same mathematics, checkpoint and partial-sum contracts as scan_bwd.cu (see its header; adjoint of
 // modules/mamba/selective_scan_interface.py:106-157).  What changes is the mapping:
@@ -147,6 +149,13 @@ template <> struct St<__half> {
 };
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+// ex2 that the compiler may not merge with an earlier evaluation of the same argument: the reverse sweep RE-evaluates the
+// decays of the first steps instead of keeping them alive in registers across the tile
+__device__ __forceinline__ float ex2v(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 template <typename T, bool SOFTPLUS>
 __global__ void __launch_bounds__(kW * 32, 2) scan_bwd_lc_kernel(const __grid_constant__ BwdParams P) {
@@ -333,7 +342,7 @@ __global__ void __launch_bounds__(kW * 32, 2) scan_bwd_lc_kernel(const __grid_co
 #pragma unroll
         for (int j = 0; j < 8; ++j) a2[j] = fmul2(dt2, kA[j]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a2[j] = f2(ex2(a2[j].x), ex2(a2[j].y));
+        for (int j = 0; j < 8; ++j) a2[j] = f2(ex2v(a2[j].x), ex2v(a2[j].y));
       }
       if (k < kHS) {
 #pragma unroll
@@ -527,6 +536,10 @@ static int try_t(const cm_scan_bwd_args& a, cudaStream_t st, int* rc) {
 // 1 if cm_scan_bwd will take the lane-per-channel TMA kernel for these arguments (a pure function of the argument block:
 // the caller sizes the dB/dC partial tensor from it through cm_scan_bwd_slab_channels)
 int scan_bwd_lane_channel_applies(const cm_scan_bwd_args& a) {
+  // Off by default: measured 0.87 ms against 0.63 ms of the state-parallel kernel at the ConMamba-large shape (two fat
+  // warps per SM sub-partition issue 0.32 instructions per cycle).  CM_SCAN_LC_BWD=1 selects it.
+  const char* on = getenv("CM_SCAN_LC_BWD");
+  if (on == nullptr || on[0] == '0') return 0;
   if (getenv("CM_SCAN_NO_LC") != nullptr || getenv("CM_SCAN_NO_SP") != nullptr || getenv("CM_SCAN_GENERIC") != nullptr) return 0;
   lcb::BwdParams P;
   switch (a.dtype) {

@@ -426,7 +426,13 @@ extern "C" int cm_scan_fwd(const cm_scan_fwd_args* args, void* stream) {
     // run as parallel time windows (few long sequences, workspace provided) stay on the state-parallel kernel
     const bool windowed = a.workspace != nullptr && cm::scan_fwd_sp_workspace_bytes(a) > 0 &&
                           a.workspace_bytes >= cm::scan_fwd_sp_workspace_bytes(a);
-    if (!windowed && getenv("CM_SCAN_NO_LC") == nullptr && cm::scan_fwd_try_lane_channel(a, st, &rc)) return rc;
+    // measured on B200 (ms, lc / sp): fp32 I/O 0.283 / 0.393 at 64 x 512 x 2 and 0.493 / 0.681 at 64 x 1024 x 2
+    // (broadcast fp32 B|C rows read in place: no conversion pass); bf16 I/O 0.250 / 0.226 and 0.421 / 0.421, 0.085 / 0.059
+    // at 32 x 288 x 2 -> the lane-per-channel kernel takes fp32 launches with enough rows, the state-parallel one the rest
+    const int64_t rows = (int64_t)a.batch * a.dim * a.ndir / 32;
+    const char* force = getenv("CM_SCAN_LC");
+    const bool use_lc = force != nullptr ? (force[0] != '0') : (a.dtype == CM_F32 && rows >= 1024);
+    if (!windowed && use_lc && getenv("CM_SCAN_NO_LC") == nullptr && cm::scan_fwd_try_lane_channel(a, st, &rc)) return rc;
     // state-parallel kernel (lane = 4 states x 2 channels)
     if (cm::scan_fwd_try_state_parallel(a, st, &rc)) return rc;
   }

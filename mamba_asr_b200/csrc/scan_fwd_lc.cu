@@ -1,4 +1,6 @@
-// Selective-scan forward, "lc" kernel (lane = channel, TMA-staged) for sm_100a - the default forward kernel of round 2.
+// Selective-scan forward, "lc" kernel (lane = channel, TMA-staged) for sm_100a.  Taken by cm_scan_fwd where it measures
+// faster than the state-parallel kernel - fp32 I/O with at least 1024 channel rows (0.283 vs 0.393 ms at the ConMamba-large
+// shape) - or when CM_SCAN_LC=1; see DESIGN.md section 3.1 for the measurements of both kernels at every shape.
 //
 // Mathematics, bidirectional stash/combine protocol and checkpoint contract are those of scan_fwd.cu (see its header;
 // reference semantics: modules/mamba/selective_scan_interface.py:106-157 and modules/mamba/bimamba.py:223-253).
@@ -142,7 +144,7 @@ enum { FM_UNI = 0, FM_STASH = 1, FM_COMBINE = 2 };
 #define CM_FWDLC_MINB 4
 #endif
 #ifndef CM_FWDLC_NPOLY
-#define CM_FWDLC_NPOLY 2
+#define CM_FWDLC_NPOLY 0     // measured on B200 (ConMamba-large shape): 0.248 ms with 0, 0.252 / 0.261 / 0.284 ms with 1 / 2 / 3 pairs
 #endif
 
 template <typename T, int NPOLY, bool SOFTPLUS>

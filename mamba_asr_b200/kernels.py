@@ -41,9 +41,19 @@ def stop_timing(by_shape=False):
     return out
 
 
+_NVTX = os.environ.get("CM_NVTX") not in (None, "", "0")   # CM_NVTX=1: one NVTX range per C-ABI entry point (nsys / ncu --nvtx)
+
+
 def _call(name, fn, *args, tag=None):
     global LAUNCHES
     LAUNCHES += 1
+    if _NVTX:
+        torch.cuda.nvtx.range_push(name if tag is None else "%s %s" % (name, tag))
+        try:
+            cabi.check(fn(*args), name)
+        finally:
+            torch.cuda.nvtx.range_pop()
+        return
     if _TIMING is None:
         cabi.check(fn(*args), name)
         return
@@ -836,3 +846,34 @@ def colsum(x2d):
     out = torch.empty((cols,), dtype=torch.float32, device=x2d.device)
     reduce_many([(part, out)])
     return out
+
+
+# ------------------------------------------------------------------------------------------------ optimizer step
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, max_grad_norm=0.0, grad_scale=1.0, p_bf16=None,
+               scratch=None, norm_out=None):
+    """cm_sumsq_partial + cm_adamw_step on flat fp32 CUDA buffers (len a multiple of 4): clip to ``max_grad_norm`` (0 = off),
+    AdamW with decoupled weight decay, ``step`` counted from 1.  ``grad_scale`` = 1 / world_size folds the DDP average in.
+    ``scratch``: optional fp32 buffer of cm_optim_num_part(n) elements (allocated when None)."""
+    lib = cabi.lib()
+    _require_cuda(p, "p")
+    n = p.numel()
+    for t, name in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != n:
+            raise ValueError("adamw_step: %s must be a contiguous fp32 buffer of the parameters' length" % name)
+    _same_device(p, g=g, m=m, v=v, p_bf16=p_bf16, scratch=scratch, norm_out=norm_out)
+    a = cabi.AdamWArgs()
+    a.p, a.g, a.m, a.v = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr()
+    a.p_bf16 = cabi.ptr(p_bf16)
+    a.norm_out = cabi.ptr(norm_out)
+    a.n = n
+    a.lr, a.beta1, a.beta2, a.eps, a.weight_decay = float(lr), float(beta1), float(beta2), float(eps), float(weight_decay)
+    a.bias_corr1, a.bias_corr2 = 1.0 - float(beta1) ** int(step), 1.0 - float(beta2) ** int(step)
+    a.max_grad_norm, a.grad_scale = float(max_grad_norm), float(grad_scale)
+    st = cabi.stream_ptr()
+    if max_grad_norm and max_grad_norm > 0.0:
+        n_part = lib.cm_optim_num_part(n)
+        if scratch is None:
+            scratch = torch.empty((n_part,), dtype=torch.float32, device=p.device)
+        _call("cm_sumsq_partial", lib.cm_sumsq_partial, g.data_ptr(), n, scratch.data_ptr(), st)
+        a.sumsq_part, a.n_part = scratch.data_ptr(), n_part
+    _call("cm_adamw_step", lib.cm_adamw_step, C.byref(a), st)

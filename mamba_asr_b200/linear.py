@@ -67,6 +67,13 @@ def set_param_cache(cache):
     _ACTIVE = cache
 
 
+def invalidate_param_cache():
+    """Mark every copy of the installed cache stale (called by code that writes parameters through raw pointers, e.g. the
+    flat-buffer optimizer kernel, which does not bump the tensors' version counters)."""
+    if _ACTIVE is not None:
+        _ACTIVE.versions = [-1] * len(_ACTIVE.versions)
+
+
 def cached_param(p, dtype):
     """The cached low-precision copy of ``p`` (no autograd link) or None."""
     return _ACTIVE.get(p, dtype) if (_ACTIVE is not None and p is not None) else None

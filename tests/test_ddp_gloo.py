@@ -51,12 +51,20 @@ def _worker(rank, world, port, q):
     loss = F.ctc_loss(out.transpose(0, 1), tgt[shard], torch.full((2,), out.shape[1]), torch.full((2,), 3), blank=0,
                       reduction="sum", zero_infinity=True)
     loss.backward()
+    local = [None if p.grad is None else p.grad.clone() for p in model.parameters()]
     allreduce_gradients(model.parameters(), world)             # one flat all-reduce over gloo, averaged
     grads = [p.grad.clone() * world for p in model.parameters() if p.grad is not None]
+    # the training step bench.py runs at N > 1: all-reduce + clip + AdamW + Noam through TrainStep (torch path on CPU)
+    from mamba_asr_b200.trainer import TrainStep
+    for p, g_ in zip(model.parameters(), local):
+        p.grad = g_
+    ts = TrainStep(model, lr=1e-2, max_grad_norm=5.0, n_warmup_steps=10, world_size=world)
+    ts.step(dist)
+    stepped = [p.detach().clone() for p in model.parameters()]
     t = torch.tensor([float(loss.detach())])
     dist.all_reduce(t)
     if rank == 0:
-        q.put((float(t), [g_.numpy().copy() for g_ in grads]))      # by value (no shared-memory handles)
+        q.put((float(t), [g_.numpy().copy() for g_ in grads], [s_.numpy().copy() for s_ in stepped]))   # by value
     dist.barrier()
     dist.destroy_process_group()
 
@@ -68,7 +76,7 @@ def test_two_rank_gloo_gradients_equal_single_process_global_batch():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    total, grads = q.get(timeout=300)
+    total, grads, stepped = q.get(timeout=300)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -87,3 +95,11 @@ def test_two_rank_gloo_gradients_equal_single_process_global_batch():
     assert len(ref) == len(grads)
     for a, b in zip(grads, ref):
         torch.testing.assert_close(torch.from_numpy(a), b, rtol=1e-4, atol=1e-5)
+    # one optimizer step on the averaged gradient = what every rank ended with
+    from mamba_asr_b200.trainer import TrainStep
+    for p in model.parameters():
+        if p.grad is not None:
+            p.grad.mul_(0.5)
+    TrainStep(model, lr=1e-2, max_grad_norm=5.0, n_warmup_steps=10).step()
+    for a, p in zip(stepped, model.parameters()):
+        torch.testing.assert_close(torch.from_numpy(a), p.detach(), rtol=1e-4, atol=1e-6)

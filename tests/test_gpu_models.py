@@ -256,3 +256,37 @@ def test_param_cache_eval_after_update_matches_uncached_model():
         with torch.autocast("cuda", dtype=torch.bfloat16):
             e2 = m.encode(feats).float()
     assert_close(e1, e2, torch.bfloat16, floor="max", what="encode() with a stale cache")
+
+
+def test_flat_adamw_step_matches_torch_adamw_with_clipping():
+    """trainer.TrainStep on CUDA (flat buffers, cm_sumsq_partial + cm_adamw_step) against torch.optim.AdamW +
+    clip_grad_norm_ + the Noam formula over several steps, with and without active clipping; parameters keep their
+    state_dict names / shapes after being re-pointed into the flat buffer."""
+    from mamba_asr_b200.trainer import TrainStep, noam_lr
+    torch.manual_seed(3)
+    def make():
+        torch.manual_seed(3)
+        return torch.nn.Sequential(torch.nn.Linear(37, 64), torch.nn.LayerNorm(64), torch.nn.Linear(64, 5)).cuda()
+    ours, ref = make(), make()
+    keys = list(ours.state_dict().keys())
+    hp = dict(lr=2e-3, betas=(0.9, 0.98), eps=1e-9, weight_decay=5e-2)
+    for max_norm in (0.05, 50.0):                       # clipping active / inactive
+        ts = TrainStep(ours, max_grad_norm=max_norm, n_warmup_steps=4, **hp)
+        assert list(ours.state_dict().keys()) == keys
+        opt = torch.optim.AdamW(ref.parameters(), **hp)
+        for step in range(1, 6):
+            x = torch.randn(16, 37, device="cuda", generator=torch.Generator(device="cuda").manual_seed(step))
+            for net in (ours, ref):
+                net.zero_grad(set_to_none=True)
+                net(x).square().mean().backward()
+            for g_ in opt.param_groups:
+                g_["lr"] = noam_lr(hp["lr"], 4, step)
+            norm_ref = torch.nn.utils.clip_grad_norm_(ref.parameters(), max_norm)
+            opt.step()
+            ts.step()
+            assert_close(ts.grad_norm, norm_ref.reshape(1), floor="max", what=f"grad norm step {step}")
+            for (n1, p1), (n2, p2) in zip(ours.named_parameters(), ref.named_parameters()):
+                assert_close(p1, p2, floor="max", what=f"{n1} after step {step} (max_norm {max_norm})")
+        # a parameter without a gradient contributes zeros (and still decays)
+        ours[2].bias.grad = None
+        ref[2].bias.grad = None

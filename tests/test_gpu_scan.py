@@ -516,6 +516,7 @@ def test_tma_forward_matches_oracle(dtype, shape, monkeypatch):
     ragged lengths, odd numbers of channel blocks (inactive warps), and against the state-parallel kernel's checkpoints."""
     from mamba_asr_b200 import kernels as K
     from oracle.scan_ref import selective_scan_oracle
+    monkeypatch.setenv("CM_SCAN_LC", "1")
     Bt, D, L = shape
     N = 16
     f = make_scan_inputs(Bt, D, L, N, dtype, seed=131)
@@ -568,6 +569,7 @@ def test_tma_forward_full_size_config3_against_state_parallel(monkeypatch):
                          B=xd[..., :N].transpose(1, 2), C=xd[..., N:2 * N].transpose(1, 2), D=torch.ones(D, device="cuda"),
                          delta_bias=torch.full((D,), -4.0, device="cuda"), reverse=rev))
     run = lambda: K.scan_forward(dirs, z=z, out_scale=0.5, delta_softplus=True, need_ckpt=True, need_out_pre=True)
+    monkeypatch.setenv("CM_SCAN_LC", "1")
     a, b = run(), run()
     assert torch.equal(a["out"], b["out"]) and torch.equal(a["ckpt"][0], b["ckpt"][0])
     monkeypatch.setenv("CM_SCAN_NO_LC", "1")
@@ -581,12 +583,14 @@ def test_tma_forward_full_size_config3_against_state_parallel(monkeypatch):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("shape", [(2, 128, 45), (1, 128, 8), (2, 128, 9), (1, 128, 1), (2, 256, 17), (1, 128, 67), (2, 128, 16),
                                    (3, 128, 131), (1, 384, 24)])
-def test_tma_backward_matches_autograd(dtype, shape):
+def test_tma_backward_matches_autograd(dtype, shape, monkeypatch):
     """scan_bwd_lc.cu (lane = channel, TMA-staged; the default backward for the module's x_dbl layout when dim is a multiple
     of 128): every gradient of the fused bidirectional block and of unidirectional scans (with and without gate / softplus)
     against autograd through the oracle (fed the dtype-rounded inputs, computed in fp32), over ragged lengths and tile
     boundaries."""
     from oracle.scan_ref import selective_scan_oracle
+    monkeypatch.setenv("CM_SCAN_LC", "1")
+    monkeypatch.setenv("CM_SCAN_LC_BWD", "1")
     Bt, D, L = shape
     K, f, bw, dirs, zc, cot = _bidir_backward_case(Bt, D, L, dtype, seed=141, layout="xdbl")
     ref, lf, lb = _oracle_bidir_grads(f, bw, cot, dtype)
@@ -618,6 +622,7 @@ def test_tma_backward_is_deterministic_and_agrees_with_state_parallel(monkeypatc
     tensors agrees; the library reports 128-channel slabs for this layout and 32-channel slabs otherwise."""
     import ctypes as C
     from mamba_asr_b200 import _cabi
+    monkeypatch.setenv("CM_SCAN_LC_BWD", "1")
     K, f, bw, dirs, zc, cot = _bidir_backward_case(2, 256, 77, torch.bfloat16, seed=151, layout="xdbl")
     res = K.scan_forward(dirs, z=zc, out_scale=0.5, delta_softplus=True, need_ckpt=True, need_out_pre=True)
     run = lambda d_: K.scan_backward(d_, res["ckpt"], channel_last(cot.cuda()), z=zc, out_pre=res["out_pre"], out_scale=0.5,
@@ -655,6 +660,7 @@ def test_tma_backward_full_size_config3(monkeypatch):
     res = K.scan_forward(dirs, z=z, out_scale=0.5, delta_softplus=True, need_ckpt=True, need_out_pre=True)
     go = cl()
     run = lambda: K.scan_backward(dirs, res["ckpt"], go, z=z, out_pre=res["out_pre"], out_scale=0.5, delta_softplus=True)
+    monkeypatch.setenv("CM_SCAN_LC_BWD", "1")
     a = run()
     monkeypatch.setenv("CM_SCAN_NO_LC", "1")
     o = run()

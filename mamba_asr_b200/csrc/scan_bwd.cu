@@ -483,6 +483,9 @@ int scan_bwd_try_state_parallel(const cm_scan_bwd_args& a, cudaStream_t st, int*
 int scan_bwd_try_lane_channel(const cm_scan_bwd_args& a, cudaStream_t st, int* rc);              // scan_bwd_lc.cu
 int scan_bwd_lane_channel_applies(const cm_scan_bwd_args& a);
 int scan_bwd_lane_channel_slab();
+int scan_bwd_try_warpgroup(const cm_scan_bwd_args& a, cudaStream_t st, int* rc);                 // scan_bwd_wg.cu
+int scan_bwd_warpgroup_applies(const cm_scan_bwd_args& a);
+int scan_bwd_warpgroup_slab();
 }
 
 extern "C" int cm_scan_bwd_slab_channels(const cm_scan_bwd_args* args) {
@@ -492,6 +495,7 @@ extern "C" int cm_scan_bwd_slab_channels(const cm_scan_bwd_args* args) {
   static float dummy_part[4] __attribute__((aligned(16)));
   for (int r = 0; r < 2; ++r) { a.dir[r].dBC_part = dummy_part; a.dir[r].dA_part = dummy_part; }
   if (cm::scan_bwd_lane_channel_applies(a)) return cm::scan_bwd_lane_channel_slab();
+  if (cm::scan_bwd_warpgroup_applies(a)) return cm::scan_bwd_warpgroup_slab();
   int lpc = a.lanes_per_channel;
   if (lpc == 0) lpc = cm_scan_pick_lanes_bwd(a.batch, a.dim, a.ndir);
   return cm_scan_slab_channels(lpc);
@@ -528,11 +532,17 @@ extern "C" int cm_scan_bwd(const cm_scan_bwd_args* args, void* stream) {
   if (lpc != 1 && lpc != 2 && lpc != 4) return CM_ERR_BAD_ARG;
   const bool bcc = a.dir[0].in.bc_const != 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (cm_scan_bwd_slab_channels(args) == cm::scan_bwd_lane_channel_slab()) {
+  const int slab = cm_scan_bwd_slab_channels(args);
+  if (slab == cm::scan_bwd_lane_channel_slab()) {
     // the caller sized dBC_part for 128-channel slabs: no other kernel may run (they write narrower slabs)
     int rc = 0;
     if (cm::scan_bwd_try_lane_channel(a, st, &rc)) return rc;
     return CM_ERR_UNSUPPORTED;                   // misaligned partial buffers, or a view the tensor-map encoder refused
+  }
+  if (slab == cm::scan_bwd_warpgroup_slab()) {   // 64-channel slabs: the warpgroup kernel (scan_bwd_wg.cu), same contract
+    int rc = 0;
+    if (cm::scan_bwd_try_warpgroup(a, st, &rc)) return rc;
+    return CM_ERR_UNSUPPORTED;
   }
   if (getenv("CM_SCAN_GENERIC") == nullptr && getenv("CM_SCAN_NO_SP") == nullptr && lpc == 1) {
     int rc = 0;

@@ -172,6 +172,11 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 }
 
 // ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 lanes per issue slot) ---------------
+#ifdef CM_SCALAR_F32X2   // A/B experiment: the packed helpers as two scalar instructions each
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+#else
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   float2 d;
   asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; "
@@ -191,6 +196,7 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
       : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
   return d;
 }
+#endif
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 

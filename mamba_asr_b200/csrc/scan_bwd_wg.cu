@@ -46,7 +46,10 @@ using cm::sp::Pair;
 constexpr int kTB = CM_SCAN_CKPT_STEPS;   // steps per tile (8)
 constexpr int kRW = 4;                    // recurrence warps (warpgroup 0)
 constexpr int kIW = 4;                    // IO warps (warpgroup 1)
-constexpr int kIA = 2;                    // IO warps that work (the other two only give their registers away and exit)
+#ifndef CM_BWDWG_IA
+#define CM_BWDWG_IA 2
+#endif
+constexpr int kIA = CM_BWDWG_IA;          // IO warps that work (the others only give their registers away and exit)
 constexpr int kRT = kRW * 32, kIT = kIA * 32;
 constexpr int kCH = 64;                   // channels per CTA (= slab width of the dB/dC partial tensor)
 constexpr int kNP = kCH / 2;              // channel pairs per CTA
@@ -62,6 +65,12 @@ constexpr int kHR = CM_BWDWG_HREG;        // last kHR steps of a tile keep their
 #define CM_BWDWG_IREG 40
 #endif
 constexpr float kLn2f = 0.6931471805599453f;
+// -DCM_ABL_*: timing ablations (tools/_run_r2n.sh); they change the results and are never part of the product build
+#ifdef CM_ABL_NOEX2
+__device__ __forceinline__ float ex2r(float x) { return x + 1.0f; }
+#else
+__device__ __forceinline__ float ex2r(float x) { return ex2(x); }
+#endif
 // dB / dC exchange buffer of a warp: the dC block of a step starts 144 floats after its dB block (128 + a 16-float pad, so
 // that the half-warp that reads dB and dC pairs side by side hits 32 distinct banks), the second step 272 floats after the first
 constexpr int kPbWhich = 8 * 16 + 16, kPbStep = kPbWhich + 8 * 16;
@@ -149,7 +158,7 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1
 }
 // Sum of x (rows g) and y (rows g + 8) over the four lanes of a quad, added into column `sel` of the accumulator: the value
 // is split into its upper 19 bits (exact in TF32) and the remainder, which the tensor core truncates to TF32 itself.
-// 16-bit I/O (PRECISE = false): one TF32 term rounded to nearest (relative error 2^-12, a sixteenth of the output's ulp).
+// 16-bit I/O (PRECISE = false): one TF32 term rounded to nearest (relative error 2^-11, an eighth of the output's ulp).
 template <bool PRECISE>
 __device__ __forceinline__ void quad_sum_mma(float (&acc)[4], float x, float y, uint32_t sel) {
   if (PRECISE) {
@@ -157,10 +166,9 @@ __device__ __forceinline__ void quad_sum_mma(float (&acc)[4], float x, float y, 
     const float lx = x - __uint_as_float(hx), ly = y - __uint_as_float(hy);
     mma_tf32(acc, hx, hy, __float_as_uint(lx), __float_as_uint(ly), sel);
   } else {
-    uint32_t hx, hy;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hx) : "f"(x));
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hy) : "f"(y));
-    mma_tf32(acc, hx, hy, 0u, 0u, sel);
+    // round to nearest by adding half a TF32 ulp to the magnitude (the tensor core drops the low 13 bits); cvt.rna.tf32
+    // expands to four instructions with an Inf / NaN test
+    mma_tf32(acc, __float_as_uint(x) + 0x1000u, __float_as_uint(y) + 0x1000u, 0u, 0u, sel);
   }
 }
 
@@ -253,6 +261,15 @@ __device__ __forceinline__ void scan_role(const BwdParams& P, Smem<T>& S, const 
     const float* bcb = &O.bc[0][4 * m];
     // ---- forward: recompute the states of the tile
     float2 hist[kHR > 0 ? kHR : 1][2][2];
+#ifdef CM_ABL_NOFWD
+#pragma unroll
+    for (int k = 0; k < kHR; ++k)
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) hist[k][c][j] = h[c][j];
+    if (mu[0][0].x == 123.456f)
+#endif
 #pragma unroll
     for (int k = 0; k < kTB; ++k) {
       const float4 dd = ddb[k * kNP];
@@ -265,7 +282,7 @@ __device__ __forceinline__ void scan_role(const BwdParams& P, Smem<T>& S, const 
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const float2 x = fmul2(dt2, kA[c][j]);
-          const float2 a = make_float2(ex2(x.x), ex2(x.y));
+          const float2 a = make_float2(ex2r(x.x), ex2r(x.y));
           h[c][j] = ffma2(a, h[c][j], fmul2(du2, Bp[j]));
         }
       }
@@ -288,7 +305,23 @@ __device__ __forceinline__ void scan_role(const BwdParams& P, Smem<T>& S, const 
       acc = fadd2(acc, fadd2(fadd2(pv[4], pv[5]), fadd2(pv[6], pv[7])));
       *reinterpret_cast<float2*>(bcw + kk * 32) = acc;
     };
-    // ---- reverse sweep
+    // ---- reverse sweep.  lambda = dy*C + mu ; mu <- a*lambda ; the adjoint of the decay is q = lambda * a * h_{k-1} = mu_new * h_{k-1}
+    // (h_{k-1}: the previous entry of the history, the checkpoint for the first step of the tile)
+    auto hist_at = [&](int j, float2 (&o)[2][2]) {         // recomputed state after step j of the tile; j = -1: the checkpoint
+      if (j >= kTB - kHR) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) o[c][q] = hist[j - (kTB - kHR)][c][q];
+      } else {
+        const float4 h0 = j >= 0 ? S.hs[warp][j >= 0 ? j : 0][0][lane] : *reinterpret_cast<const float4*>(&O.ck[0][lp][4 * m]);
+        const float4 h1 = j >= 0 ? S.hs[warp][j >= 0 ? j : 0][1][lane] : *reinterpret_cast<const float4*>(&O.ck[1][lp][4 * m]);
+        o[0][0] = make_float2(h0.x, h0.y); o[0][1] = make_float2(h0.z, h0.w);
+        o[1][0] = make_float2(h1.x, h1.y); o[1][1] = make_float2(h1.z, h1.w);
+      }
+    };
+    float2 hk[2][2];
+    hist_at(kTB - 1, hk);
 #pragma unroll
     for (int k = kTB - 1; k >= 0; --k) {
       if ((k & 1) == 1) asm volatile("" ::: "memory");   // scheduling fence: bounds how far ptxas hoists operand loads
@@ -298,48 +331,59 @@ __device__ __forceinline__ void scan_role(const BwdParams& P, Smem<T>& S, const 
       const float4 cc = *reinterpret_cast<const float4*>(bcb + k * 32 + 16);
       const float2 Bp[2] = {make_float2(bb.x, bb.y), make_float2(bb.z, bb.w)};
       const float2 Cp[2] = {make_float2(cc.x, cc.y), make_float2(cc.z, cc.w)};
-      float2 hk[2][2];
-      if (k >= kTB - kHR) {
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-#pragma unroll
-          for (int j = 0; j < 2; ++j) hk[c][j] = hist[k - (kTB - kHR)][c][j];
-      } else {
-        const float4 h0 = S.hs[warp][k][0][lane], h1 = S.hs[warp][k][1][lane];
-        hk[0][0] = make_float2(h0.x, h0.y); hk[0][1] = make_float2(h0.z, h0.w);
-        hk[1][0] = make_float2(h1.x, h1.y); hk[1][1] = make_float2(h1.z, h1.w);
-      }
+      float2 hp[2][2];
+      hist_at(k - 1, hp);
       float2 accB[2], accC[2], r1a[2], r2a[2];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const float dtc = c ? dd.y : dd.x, duc = c ? dd.w : dd.z, dyc = c ? dy.y : dy.x;
-        const float2 dt2 = make_float2(dtc, dtc), du2 = make_float2(duc, duc), ndu2 = make_float2(-duc, -duc);
+        const float2 dt2 = make_float2(dtc, dtc), du2 = make_float2(duc, duc);
         const float2 dy2 = make_float2(dyc, dyc);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const float2 x = fmul2(dt2, kA[c][j]);
-          const float2 a = make_float2(ex2(x.x), ex2(x.y));
+          const float2 a = make_float2(ex2r(x.x), ex2r(x.y));
           const float2 lam = ffma2(dy2, Cp[j], mu[c][j]);
           accC[j] = c == 0 ? fmul2(dy2, hk[c][j]) : ffma2(dy2, hk[c][j], accC[j]);
           accB[j] = c == 0 ? fmul2(du2, lam) : ffma2(du2, lam, accB[j]);
-          const float2 t = ffma2(ndu2, Bp[j], hk[c][j]);                         // a * h_{k-1}
-          const float2 q = fmul2(lam, t);
+          mu[c][j] = fmul2(a, lam);
+          const float2 q = fmul2(mu[c][j], hp[c][j]);
           dA[c][j] = ffma2(q, dt2, dA[c][j]);
           r1a[c] = j == 0 ? fmul2(lam, Bp[j]) : ffma2(lam, Bp[j], r1a[c]);
           r2a[c] = j == 0 ? fmul2(q, kA[c][j]) : ffma2(q, kA[c][j], r2a[c]);
-          mu[c][j] = fmul2(a, lam);
         }
       }
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) hk[c][j] = hp[c][j];
       // sums over the 16 states of a channel: 4 in the lane, 4 lanes on the tensor core
       {
-        const uint32_t sel = __float_as_uint(gf == (float)(2 * (k & 3) + (k >> 2)) ? 1.0f : 0.0f);
+        uint32_t sel;                                      // 1.0f in the lanes that hold column 2*(k & 3) + (k >> 2) of B
+        asm("set.eq.f32.f32 %0, %1, %2;" : "=r"(sel) : "f"(gf), "f"((float)(2 * (k & 3) + (k >> 2))));
+#ifdef CM_ABL_NOMMA
+        R1[k & 3] += r1a[0].x + r1a[0].y + r1a[1].x + r1a[1].y + __uint_as_float(sel);
+        R2[k & 3] += r2a[0].x + r2a[0].y + r2a[1].x + r2a[1].y;
+#else
         quad_sum_mma<PRECISE>(R1, r1a[0].x + r1a[0].y, r1a[1].x + r1a[1].y, sel);
         quad_sum_mma<PRECISE>(R2, r2a[0].x + r2a[0].y, r2a[1].x + r2a[1].y, sel);
+#endif
       }
       // sums over the warp's 8 channel pairs
+#ifdef CM_ABL_NOPB
+      if (accB[0].x == 123.456f)
+#endif
       *reinterpret_cast<float4*>(pbw + (k & 1) * kPbStep) = make_float4(accB[0].x, accB[0].y, accB[1].x, accB[1].y);
+#ifdef CM_ABL_NOPB
+      if (accC[0].x == 123.456f)
+#endif
       *reinterpret_cast<float4*>(pbw + (k & 1) * kPbStep + kPbWhich) = make_float4(accC[0].x, accC[0].y, accC[1].x, accC[1].y);
+#ifdef CM_ABL_NOPB
+      if (k == 0) { for (int gg = 0; gg < 8; ++gg) pv[gg] = accB[0]; pb_sum(0); }
+      if (false) {
+#else
       if ((k & 1) == 0) {
+#endif
         __syncwarp();
 #pragma unroll
         for (int gg = 0; gg < 8; ++gg) pv[gg] = *reinterpret_cast<const float2*>(pbr + gg * 16);
@@ -533,7 +577,7 @@ __device__ __forceinline__ void io_role(const BwdParams& P, Smem<T>& S, const in
       O.us[k][cp] = make_float4(u2.x, u2.y, sig.x, sig.y);
       O.dy[k][cp] = dy;
     }
-    {
+    if (io < 64) {
       const int r = rev ? kTB - 1 - bc_row : bc_row;
       *reinterpret_cast<float4*>(&O.bc[bc_row][bc_col]) = SmemQuad<T>::ld(&R.bc[r][bc_col]);
     }
@@ -578,10 +622,10 @@ __device__ __forceinline__ void io_role(const BwdParams& P, Smem<T>& S, const in
       tma::fence_proxy_async_smem();
       issue_raw(i + kRS);
     }
-    if (i > 0) rows_out(i - 1, psb0, ps_end);
+    if (i > 0 && io < 64) rows_out(i - 1, psb0, ps_end);
     psb0 = sb0; ps_end = s_end;
   }
-  if (ntot > 0) rows_out(ntot - 1, psb0, ps_end);
+  if (ntot > 0 && io < 64) rows_out(ntot - 1, psb0, ps_end);
 }
 
 template <typename T, bool SOFTPLUS, bool HAS_Z>
@@ -596,7 +640,7 @@ __global__ void __launch_bounds__(kRT + kIW * 32, 3) scan_bwd_wg_kernel(const __
       tma::mbar_init(&S.in_full[i], kIA);
       tma::mbar_init(&S.in_empty[i], kRW);
       tma::mbar_init(&S.out_full[i], kRW);
-      tma::mbar_init(&S.out_empty[i], kIA);
+      tma::mbar_init(&S.out_empty[i], 2);
     }
     tma::fence_barrier_init();
   }
@@ -725,6 +769,11 @@ static int try_t(const cm_scan_bwd_args& a, cudaStream_t st, int* rc) {
 // sizes the dB/dC partial tensor from it through cm_scan_bwd_slab_channels)
 int scan_bwd_warpgroup_applies(const cm_scan_bwd_args& a) {
   if (getenv("CM_SCAN_NO_WG") != nullptr || getenv("CM_SCAN_NO_SP") != nullptr || getenv("CM_SCAN_GENERIC") != nullptr) return 0;
+  // Below one full wave of 3 CTAs per SM the 32-channel CTAs of scan_bwd_sp.cu spread the rows over more SMs (measured at
+  // the ConMamba-small shape, 320 CTAs: 0.198 ms against 0.146 ms); CM_SCAN_WG=1 forces this kernel for measurements.
+  const char* force = getenv("CM_SCAN_WG");
+  const int64_t ctas = (int64_t)((a.dim + wgb::kCH - 1) / wgb::kCH) * a.batch * a.ndir;
+  if ((force == nullptr || force[0] == '0') && ctas < 3 * 148) return 0;
   wgb::BwdParams P;
   switch (a.dtype) {
     case CM_F32: return wgb::build_params<float>(a, &P, false) ? 1 : 0;

@@ -670,3 +670,97 @@ def test_tma_backward_full_size_config3(monkeypatch):
             assert_close(a[key][r].float(), o[key][r].float(), torch.bfloat16, floor="max", what=f"{key}[{r}]")
         for key in ("dA", "dD", "dbias"):
             assert_close(a[key][r], o[key][r], torch.bfloat16, floor="max", what=f"{key}[{r}]")
+
+
+# ---- scan_bwd_wg.cu: warpgroup-specialised backward (setmaxnreg roles, TMA operands, tensor-core state sums) ------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 64, 45), (1, 64, 8), (2, 96, 9), (1, 64, 1), (2, 288, 17), (1, 128, 67), (2, 64, 16),
+                                   (3, 160, 131), (1, 512, 24), (2, 1024, 19)])
+def test_warpgroup_backward_matches_autograd(dtype, shape, monkeypatch):
+    """scan_bwd_wg.cu (the default backward for the module's x_dbl layout once the grid fills the GPU; forced here): every
+    gradient of the fused bidirectional block and of unidirectional scans (with and without gate / softplus) against
+    autograd through the oracle (fed the dtype-rounded inputs, computed in fp32) - ragged lengths, tile boundaries, slabs
+    that are half empty (dim = 96, 160, 288) and the benchmark widths 288 / 512 / 1024."""
+    from oracle.scan_ref import selective_scan_oracle
+    monkeypatch.setenv("CM_SCAN_WG", "1")
+    Bt, D, L = shape
+    K, f, bw, dirs, zc, cot = _bidir_backward_case(Bt, D, L, dtype, seed=171, layout="xdbl")
+    ref, lf, lb = _oracle_bidir_grads(f, bw, cot, dtype)
+    res = K.scan_forward(dirs, z=zc, out_scale=0.5, delta_softplus=True, need_ckpt=True, need_out_pre=True)
+    g = K.scan_backward(dirs, res["ckpt"], channel_last(cot.cuda()), z=zc, out_pre=res["out_pre"], out_scale=0.5,
+                        delta_softplus=True)
+    _check_bidir_grads(g, lf, lb, dtype, "wg bidir")
+    for r, src in ((0, f), (1, bw)):
+        lu = {k: v.float().clone().requires_grad_(True) for k, v in src.items() if k != "z"}
+        fl = (lambda t: t.flip(-1)) if r == 1 else (lambda t: t)
+        ou = fl(selective_scan_oracle(fl(lu["u"]), fl(lu["delta"]), lu["A"], fl(lu["B"]), fl(lu["C"]), lu["D"], None,
+                                      lu["delta_bias"], False))
+        (ou * cot.float()).sum().backward()
+        r1 = K.scan_forward(dirs[r:r + 1], delta_softplus=False, need_ckpt=True)
+        g1 = K.scan_backward(dirs[r:r + 1], r1["ckpt"], channel_last(cot.cuda()), delta_softplus=False)
+        assert_close(g1["du"][0].float(), lu["u"].grad, dtype, what=f"uni[{r}] du")
+        assert_close(g1["ddelta"][0].float(), lu["delta"].grad, dtype, what=f"uni[{r}] ddelta")
+        assert_close(g1["dB"][0].float(), lu["B"].grad, dtype, floor="max", what=f"uni[{r}] dB")
+        assert_close(g1["dC"][0].float(), lu["C"].grad, dtype, floor="max", what=f"uni[{r}] dC")
+        assert_close(g1["dD"][0], lu["D"].grad, dtype, floor="max", what=f"uni[{r}] dD")
+        if L > 1:
+            assert_close(g1["dA"][0], lu["A"].grad, dtype, floor="max", what=f"uni[{r}] dA")
+
+
+def test_warpgroup_backward_is_deterministic_and_sized_by_the_library(monkeypatch):
+    """Two launches are bit-identical (fixed-order sums, no atomics); the state-parallel kernel on the same tensors agrees;
+    the library reports 64-channel slabs when it will take the warpgroup kernel and 32-channel slabs otherwise (small grids
+    stay on scan_bwd_sp.cu unless forced)."""
+    import ctypes as C
+    from mamba_asr_b200 import _cabi
+    K, f, bw, dirs, zc, cot = _bidir_backward_case(2, 288, 77, torch.bfloat16, seed=181, layout="xdbl")
+    res = K.scan_forward(dirs, z=zc, out_scale=0.5, delta_softplus=True, need_ckpt=True, need_out_pre=True)
+    run = lambda: K.scan_backward(dirs, res["ckpt"], channel_last(cot.cuda()), z=zc, out_pre=res["out_pre"], out_scale=0.5,
+                                  delta_softplus=True)
+    o = run()                                   # 2 x 5 x 2 CTAs: below a wave, the library keeps the state-parallel kernel
+    monkeypatch.setenv("CM_SCAN_WG", "1")
+    a, b = run(), run()
+    for key in ("du", "ddelta", "dB", "dC", "dA", "dD", "dbias"):
+        for r in range(2):
+            assert torch.equal(a[key][r], b[key][r]), (key, r)
+    assert torch.equal(a["dz"], b["dz"])
+    for key in ("du", "ddelta", "dB", "dC"):
+        for r in range(2):
+            assert_close(a[key][r].float(), o[key][r].float(), torch.bfloat16, floor="max", what=f"{key}[{r}] wg vs sp")
+    for key in ("dA", "dD", "dbias"):
+        for r in range(2):
+            assert_close(a[key][r], o[key][r], torch.bfloat16, floor="max", what=f"{key}[{r}] wg vs sp")
+    assert_close(a["dz"].float(), o["dz"].float(), torch.bfloat16, floor="max", what="dz wg vs sp")
+
+
+def test_warpgroup_backward_full_size_config3_is_the_default(monkeypatch):
+    """ConMamba-large shape (B 64, D 512, L 501, bf16), x_dbl layout: 1024 CTAs, so the library takes the warpgroup kernel
+    without being asked; it agrees with the state-parallel kernel (CM_SCAN_NO_WG=1) and satisfies the size-independent
+    property that the gradient is linear in dout."""
+    from mamba_asr_b200 import kernels as K
+    Bt, D, L, N = 64, 512, 501, 16
+    g = torch.Generator(device="cuda").manual_seed(7)
+    rn = lambda *sh: torch.randn(*sh, device="cuda", generator=g)
+    cl = lambda: rn(Bt, L, D).bfloat16().transpose(1, 2)
+    z = cl()
+    dirs = []
+    for rev in (False, True):
+        xd = rn(Bt, L, 64).bfloat16()
+        dirs.append(dict(u=cl(), delta=(0.5 * rn(Bt, L, D)).bfloat16().transpose(1, 2), A=-torch.exp(0.3 * rn(D, N)),
+                         B=xd[..., :N].transpose(1, 2), C=xd[..., N:2 * N].transpose(1, 2), D=torch.ones(D, device="cuda"),
+                         delta_bias=torch.full((D,), -4.0, device="cuda"), reverse=rev))
+    res = K.scan_forward(dirs, z=z, out_scale=0.5, delta_softplus=True, need_ckpt=True, need_out_pre=True)
+    go = cl()
+    run = lambda go_: K.scan_backward(dirs, res["ckpt"], go_, z=z, out_pre=res["out_pre"], out_scale=0.5, delta_softplus=True)
+    a = run(go)
+    a2 = run((2.0 * go.float()).bfloat16())     # exact in bf16: every gradient doubles (up to the rounding of the outputs)
+    monkeypatch.setenv("CM_SCAN_NO_WG", "1")
+    o = run(go)
+    assert_close(a["dz"].float(), o["dz"].float(), torch.bfloat16, floor="max", what="dz")
+    for r in range(2):
+        for key in ("du", "ddelta", "dB", "dC"):
+            assert_close(a[key][r].float(), o[key][r].float(), torch.bfloat16, floor="max", what=f"{key}[{r}]")
+            assert_close(a2[key][r].float(), 2.0 * a[key][r].float(), torch.bfloat16, floor="max", what=f"linear {key}[{r}]")
+        for key in ("dA", "dD", "dbias"):
+            assert_close(a[key][r], o[key][r], torch.bfloat16, floor="max", what=f"{key}[{r}]")
+            assert_close(a2[key][r], 2.0 * a[key][r], torch.bfloat16, floor="max", what=f"linear {key}[{r}]")

@@ -393,6 +393,7 @@ int scan_fwd_try_channel_last(const cm_scan_fwd_args& a, int lpc, cudaStream_t s
 int scan_fwd_try_state_parallel(const cm_scan_fwd_args& a, cudaStream_t st, int* rc);            // scan_fwd_sp.cu
 int64_t scan_fwd_sp_workspace_bytes(const cm_scan_fwd_args& a);                                  // scan_fwd_sp.cu
 int scan_fwd_try_lane_channel(const cm_scan_fwd_args& a, cudaStream_t st, int* rc);              // scan_fwd_lc.cu
+int scan_fwd_try_warpgroup(const cm_scan_fwd_args& a, cudaStream_t st, int* rc);                 // scan_fwd_wg.cu
 }
 
 extern "C" int64_t cm_scan_fwd_workspace_bytes(const cm_scan_fwd_args* args) {
@@ -433,6 +434,12 @@ extern "C" int cm_scan_fwd(const cm_scan_fwd_args* args, void* stream) {
     const char* force = getenv("CM_SCAN_LC");
     const bool use_lc = force != nullptr ? (force[0] != '0') : (a.dtype == CM_F32 && rows >= 1024);
     if (!windowed && use_lc && getenv("CM_SCAN_NO_LC") == nullptr && cm::scan_fwd_try_lane_channel(a, st, &rc)) return rc;
+    // warpgroup kernel (scan_fwd_wg.cu: TMA operands, tensor-core state sums, 2/3 of the instructions): measured EQUAL to the
+    // state-parallel kernel at the large shapes (0.234 / 0.229 ms at 64 x 512 x 2, 0.448 / 0.45 at 64 x 1024 x 2 - both sit at
+    // 65 % of the MUFU pipe with the issue slots at 55-70 %) and slower below a wave (0.069 / 0.058 ms at
+    // 32 x 288 x 2), so it runs only on request
+    const char* wg = getenv("CM_SCAN_WG_FWD");
+    if (!windowed && force == nullptr && wg != nullptr && wg[0] != '0' && cm::scan_fwd_try_warpgroup(a, st, &rc)) return rc;
     // state-parallel kernel (lane = 4 states x 2 channels)
     if (cm::scan_fwd_try_state_parallel(a, st, &rc)) return rc;
   }

@@ -764,3 +764,62 @@ def test_warpgroup_backward_full_size_config3_is_the_default(monkeypatch):
         for key in ("dA", "dD", "dbias"):
             assert_close(a[key][r], o[key][r], torch.bfloat16, floor="max", what=f"{key}[{r}]")
             assert_close(a2[key][r], 2.0 * a[key][r], torch.bfloat16, floor="max", what=f"linear {key}[{r}]")
+
+
+# ---- scan_fwd_wg.cu: warpgroup-specialised forward (opt-in: CM_SCAN_WG_FWD=1) ---------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 64, 45), (1, 32, 16), (2, 96, 9), (1, 64, 1), (2, 288, 17), (1, 128, 67), (3, 160, 131),
+                                   (1, 512, 33), (2, 1024, 19)])
+def test_warpgroup_forward_matches_oracle(dtype, shape, monkeypatch):
+    """scan_fwd_wg.cu: fused bidirectional output, pre-gate sum, checkpoints (through the backward pass that consumes them) and
+    unidirectional launches with last_state, against the oracle on the dtype-rounded inputs - ragged lengths, tile and
+    range boundaries, an odd number of 32-channel blocks in the unidirectional grid (dim = 96, 160, 288)."""
+    from oracle.scan_ref import selective_scan_oracle
+    monkeypatch.setenv("CM_SCAN_WG_FWD", "1")
+    Bt, D, L = shape
+    K, f, bw, dirs, zc, cot = _bidir_backward_case(Bt, D, L, dtype, seed=191, layout="xdbl")
+    ref, lf, lb = _oracle_bidir_grads(f, bw, cot, dtype)
+    res = K.scan_forward(dirs, z=zc, out_scale=0.5, delta_softplus=True, need_ckpt=True, need_out_pre=True)
+    assert_close(res["out"].float(), ref.detach(), dtype, what="wg fwd out")
+    g = K.scan_backward(dirs, res["ckpt"], channel_last(cot.cuda()), z=zc, out_pre=res["out_pre"], out_scale=0.5,
+                        delta_softplus=True)
+    _check_bidir_grads(g, lf, lb, dtype, "wg fwd ckpt -> bwd")
+    monkeypatch.delenv("CM_SCAN_WG_FWD")
+    o = K.scan_forward(dirs, z=zc, out_scale=0.5, delta_softplus=True, need_ckpt=True, need_out_pre=True)
+    monkeypatch.setenv("CM_SCAN_WG_FWD", "1")
+    assert_close(res["out_pre"].float(), o["out_pre"].float(), dtype, floor="max", what="out_pre wg vs sp")
+    for r in range(2):
+        assert_close(res["ckpt"][r], o["ckpt"][r], dtype, floor="max", what="ckpt[%d] wg vs sp" % r)
+    for r, src in ((0, f), (1, bw)):
+        fl = (lambda t: t.flip(-1)) if r == 1 else (lambda t: t)
+        s = {k: v.float() for k, v in src.items() if k != "z"}
+        ou, last = selective_scan_oracle(fl(s["u"]), fl(s["delta"]), s["A"], fl(s["B"]), fl(s["C"]), s["D"], None, s["delta_bias"],
+                                         False, return_last_state=True)
+        r1 = K.scan_forward(dirs[r:r + 1], delta_softplus=False, need_last_state=True)
+        assert_close(r1["out"].float(), fl(ou), dtype, what=f"uni[{r}] out")
+        assert_close(r1["last_state"][0], last, dtype, floor="max", what=f"uni[{r}] last_state")
+
+
+def test_warpgroup_forward_full_size_config3(monkeypatch):
+    """ConMamba-large shape (B 64, D 512, L 501, bf16): bit-identical across launches and equal to the state-parallel kernel."""
+    from mamba_asr_b200 import kernels as K
+    Bt, D, L, N = 64, 512, 501, 16
+    g = torch.Generator(device="cuda").manual_seed(8)
+    rn = lambda *sh: torch.randn(*sh, device="cuda", generator=g)
+    cl = lambda: rn(Bt, L, D).bfloat16().transpose(1, 2)
+    z = cl()
+    dirs = []
+    for rev in (False, True):
+        xd = rn(Bt, L, 64).bfloat16()
+        dirs.append(dict(u=cl(), delta=(0.5 * rn(Bt, L, D)).bfloat16().transpose(1, 2), A=-torch.exp(0.3 * rn(D, N)),
+                         B=xd[..., :N].transpose(1, 2), C=xd[..., N:2 * N].transpose(1, 2), D=torch.ones(D, device="cuda"),
+                         delta_bias=torch.full((D,), -4.0, device="cuda"), reverse=rev))
+    run = lambda: K.scan_forward(dirs, z=z, out_scale=0.5, delta_softplus=True, need_ckpt=True, need_out_pre=True)
+    o = run()
+    monkeypatch.setenv("CM_SCAN_WG_FWD", "1")
+    a, b = run(), run()
+    assert torch.equal(a["out"], b["out"]) and torch.equal(a["ckpt"][0], b["ckpt"][0]) and torch.equal(a["ckpt"][1], b["ckpt"][1])
+    assert_close(a["out"].float(), o["out"].float(), torch.bfloat16, floor="max", what="out")
+    assert_close(a["out_pre"].float(), o["out_pre"].float(), torch.bfloat16, floor="max", what="out_pre")
+    for r in range(2):
+        assert_close(a["ckpt"][r], o["ckpt"][r], torch.bfloat16, floor="max", what="ckpt[%d]" % r)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CM_ABI_VERSION 8
+#define CM_ABI_VERSION 9
 
 /* element type of activations (u, delta, z, B, C, x, out, and their gradients) */
 enum { CM_F32 = 0, CM_BF16 = 1, CM_F16 = 2 };
@@ -247,6 +247,28 @@ typedef struct {
 
 int cm_fbank_logmel(const cm_fbank_args* args, void* stream);
 int cm_fbank_floor(const cm_fbank_args* args, void* stream);
+
+/* The whole front-end in one kernel: windowed DFT -> power -> mel -> dB + per-utterance max,
+ * straight from the samples.  Replaces torch.stft (cuFFT) + cm_fbank_logmel for the transform sizes of the reference YAMLs
+ * (n_fft 400 and 512: hparams/CTC/conmamba_large.yaml:103-105, hparams/S2S/conformer_small.yaml:148); the complex STFT is
+ * never written to memory.  Framing follows torch.stft(center=True, pad_mode="constant"): frame t covers samples
+ * [t*hop - n_fft/2, t*hop + n_fft/2), zeros outside the utterance; `window` is the analysis window zero-padded (centred) to
+ * n_fft.  Follow with cm_fbank_floor on (out, utt_max). */
+typedef struct {
+  int32_t batch, n_samples, frames, nmels;
+  int32_t n_fft, hop;
+  const float* wav;         /* (batch, n_samples) fp32, row stride wav_sb elements */
+  int64_t wav_sb;
+  const float* window;      /* (n_fft) fp32 */
+  const float* fbank;       /* (n_fft/2 + 1, nmels) fp32 row-major triangular filterbank */
+  const int32_t* band;      /* (nmels, 2) int32: [first, one-past-last) non-zero bin of each filter */
+  float* out;               /* (batch, frames, nmels) fp32 contiguous */
+  float* utt_max;           /* (batch) fp32, must be pre-filled with -inf */
+  float amin, multiplier, db_offset, top_db;
+} cm_fbank_wav_args;
+
+int cm_fbank_wav_supported(int32_t n_fft);   /* 1 for the transform sizes cm_fbank_wav_logmel implements */
+int cm_fbank_wav_logmel(const cm_fbank_wav_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * LayerNorm over the last dimension (the six LayerNorms around each Mamba block,

@@ -17,7 +17,7 @@ CM_ERR_BAD_ARG, CM_ERR_UNSUPPORTED = -1, -2
 CM_FLAG_DELTA_SOFTPLUS = 1
 CM_FLAG_SILU = 1
 CM_SCAN_CKPT_STEPS = 8
-CM_ABI_VERSION = 8
+CM_ABI_VERSION = 9
 CM_LN_ACT_LEAKY_RELU, CM_LN_ACT_GELU = 0, 1
 
 EXPORTS = (
@@ -28,6 +28,7 @@ EXPORTS = (
     "cm_layernorm_bwd", "cm_scan_fwd_workspace_bytes", "cm_dwconv_num_part", "cm_dwconv_fwd", "cm_dwconv_bwd_weight", "cm_colsum_num_part", "cm_colsum",
     "cm_ssm_step", "cm_add_ln_fwd", "cm_add_ln_bwd", "cm_gelu_dropout_fwd", "cm_gelu_dropout_bwd", "cm_tsmm_num_part", "cm_tsmm",
     "cm_ln_act_num_part", "cm_ln_act_fwd", "cm_ln_act_bwd", "cm_optim_num_part", "cm_sumsq_partial", "cm_adamw_step",
+    "cm_fbank_wav_supported", "cm_fbank_wav_logmel",
 )
 CM_REDUCE_MAX_JOBS = 8
 
@@ -103,6 +104,16 @@ class FbankArgs(C.Structure):
     ]
 
 
+class FbankWavArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("n_samples", C.c_int32), ("frames", C.c_int32), ("nmels", C.c_int32),
+        ("n_fft", C.c_int32), ("hop", C.c_int32),
+        ("wav", C.c_void_p), ("wav_sb", C.c_int64),
+        ("window", C.c_void_p), ("fbank", C.c_void_p), ("band", C.c_void_p), ("out", C.c_void_p), ("utt_max", C.c_void_p),
+        ("amin", C.c_float), ("multiplier", C.c_float), ("db_offset", C.c_float), ("top_db", C.c_float),
+    ]
+
+
 class ReduceJob(C.Structure):
     _fields_ = [("part", C.c_void_p), ("out", C.c_void_p), ("rows", C.c_int64), ("cols", C.c_int64)]
 
@@ -168,7 +179,7 @@ class AdamWArgs(C.Structure):
 
 
 ABI_STRUCTS = (Tensor3, ScanDir, ScanFwdArgs, ScanBwdDir, ScanBwdArgs, ConvDir, ConvArgs, FbankArgs, ReduceJob,
-               LayerNormArgs, DwConvArgs, SsmStepArgs, AddLnArgs, LnActArgs, AdamWArgs)
+               LayerNormArgs, DwConvArgs, SsmStepArgs, AddLnArgs, LnActArgs, AdamWArgs, FbankWavArgs)
 
 def lib():
     """The loaded shared library; raises (never falls back) when it is absent or stale."""
@@ -199,6 +210,8 @@ def lib():
                                      C.c_int32, C.c_int32, C.c_uint32, C.c_void_p]
         L.cm_fbank_logmel.argtypes = [C.POINTER(FbankArgs), C.c_void_p]
         L.cm_fbank_floor.argtypes = [C.POINTER(FbankArgs), C.c_void_p]
+        L.cm_fbank_wav_supported.argtypes = [C.c_int32]
+        L.cm_fbank_wav_logmel.argtypes = [C.POINTER(FbankWavArgs), C.c_void_p]
         L.cm_abi_sizeof.argtypes = [C.c_int32]
         L.cm_reduce_multi.argtypes = [C.POINTER(ReduceJob), C.c_int32, C.c_void_p]
         L.cm_scan_fwd_workspace_bytes.argtypes = [C.POINTER(ScanFwdArgs)]

@@ -31,8 +31,8 @@ CONFIGS = {
     # hparams/S2S/conmamba_small.yaml:188-189,229-236 model block on the CTC recipe
     "conmamba_small_ctc": dict(d_model=144, d_ffn=1024, num_layers=12, n_fft=400, win_length=25, n_mels=80,
                                output_neurons=31, seed=7775),
-    # hparams/CTC/conmamba_large.yaml:153-183
-    "conmamba_large_ctc": dict(d_model=256, d_ffn=1024, num_layers=18, n_fft=512, win_length=32, n_mels=80,
+    # hparams/CTC/conmamba_large.yaml:153-183; features :101-105 (n_fft 512 with a 25 ms window: zero-padded to the transform)
+    "conmamba_large_ctc": dict(d_model=256, d_ffn=1024, num_layers=18, n_fft=512, win_length=25, n_mels=80,
                                output_neurons=31, seed=3402),
     # encoder of hparams/S2S/conmambamamba_large.yaml:251-287
     "conmamba_large_s2s_encoder": dict(d_model=512, d_ffn=2048, num_layers=12, n_fft=512, win_length=32, n_mels=80,

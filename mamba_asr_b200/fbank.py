@@ -1,12 +1,15 @@
 """``Fbank`` - drop-in for ``speechbrain.lobes.features.Fbank`` as the reference instantiates it
 (hparams/CTC/conmamba_large.yaml:322-326; call sites train_CTC.py:285, train_S2S.py:349).
 
-STFT stays cuFFT (``torch.stft`` with SpeechBrain's arguments: hamming window, centre padding with zeros,
-one-sided); everything after it - power, mel projection, dB, per-utterance max and the top_db floor - is the
-fused sm_100a kernel pair ``cm_fbank_logmel`` / ``cm_fbank_floor``.  Output (B, T, n_mels) fp32, no grad
-(the reference builds Fbank with ``requires_grad=False`` and runs it under ``torch.no_grad`` semantics).
+For the transform sizes of the reference YAMLs (n_fft 400 / 512) the whole front-end is ONE sm_100a kernel,
+``cm_fbank_wav_logmel``: windowed DFT (SpeechBrain's STFT arguments: hamming window zero-padded to n_fft, centre padding
+with zeros, one-sided), power, mel projection, dB and the per-utterance max, followed by ``cm_fbank_floor`` for the top_db
+floor - the complex STFT never exists in memory.  Other sizes (and ``CM_FBANK_CUFFT=1``, the A/B switch) take
+``torch.stft`` (cuFFT) + ``cm_fbank_logmel``.  Output (B, T, n_mels) fp32, no grad (the reference builds Fbank with
+``requires_grad=False`` and runs it under ``torch.no_grad`` semantics).
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -52,6 +55,16 @@ class Fbank(nn.Module):
         self.register_buffer("window", torch.hamming_window(self.win_length), persistent=False)
         self.register_buffer("fbank_matrix", triangular_filterbank(n_fft, n_mels, sample_rate, f_min, f_max),
                              persistent=False)
+        # analysis window zero-padded (centred) to n_fft, as torch.stft pads it; support [lo, hi) of every mel filter
+        left = (n_fft - self.win_length) // 2
+        wpad = torch.zeros(n_fft)
+        wpad[left:left + self.win_length] = self.window
+        self.register_buffer("window_padded", wpad, persistent=False)
+        nz = self.fbank_matrix != 0
+        idx = torch.arange(nz.shape[0]).unsqueeze(1)
+        lo = torch.where(nz, idx, torch.full_like(idx, nz.shape[0])).amin(0)
+        hi = torch.where(nz, idx + 1, torch.zeros_like(idx)).amax(0)
+        self.register_buffer("band", torch.stack([lo, hi], 1).to(torch.int32).contiguous(), persistent=False)
         self.top_db = 80.0
         self.amin = 1e-10
         self.multiplier = 10.0                       # power spectrogram
@@ -64,6 +77,10 @@ class Fbank(nn.Module):
             raise NotImplementedError("multi-channel audio (B, T, C) is not used by the reference recipes")
         if not wav.is_cuda:
             raise RuntimeError("mamba_asr_b200.Fbank runs on CUDA only (no CPU fallback)")
+        if self.win_length <= self.n_fft and K.fbank_wav_supported(self.n_fft) and os.environ.get("CM_FBANK_CUFFT") is None:
+            dev = wav.device
+            return K.fbank_wav_logmel(wav.float(), self.window_padded.to(dev), self.fbank_matrix.to(dev), self.band.to(dev),
+                                      self.n_fft, self.hop_length, self.top_db, self.amin, self.multiplier, self.db_offset)
         with torch.autocast("cuda", enabled=False):
             stft = torch.stft(wav.float(), self.n_fft, self.hop_length, self.win_length, self.window.to(wav.device),
                               center=True, pad_mode="constant", normalized=False, onesided=True,

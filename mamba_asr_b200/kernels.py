@@ -501,6 +501,44 @@ def fbank_logmel(stft, fbank, top_db=80.0, amin=1e-10, multiplier=10.0, db_offse
     return out
 
 
+def fbank_wav_supported(n_fft):
+    return bool(cabi.lib().cm_fbank_wav_supported(int(n_fft)))
+
+
+def fbank_wav_logmel(wav, window, fbank, band, n_fft, hop, top_db=80.0, amin=1e-10, multiplier=10.0, db_offset=0.0):
+    """cm_fbank_wav_logmel + cm_fbank_floor: the whole Fbank front-end from the samples (windowed DFT in the kernel, no cuFFT,
+    no STFT tensor).  wav: (B, n_samples) fp32 CUDA; window: (n_fft,) fp32 (analysis window zero-padded to n_fft);
+    fbank: (n_fft // 2 + 1, M) fp32; band: (M, 2) int32 support of each filter.  Returns (B, 1 + n_samples // hop, M) fp32."""
+    lib = cabi.lib()
+    _require_cuda(wav, "wav")
+    if wav.dim() != 2 or wav.dtype != torch.float32:
+        raise TypeError("wav must be a (B, n_samples) float32 tensor")
+    _same_device(wav, window=window, fbank=fbank, band=band)
+    if wav.stride(1) != 1:
+        wav = wav.contiguous()
+    Bt, n = wav.shape
+    M = fbank.shape[1]
+    if fbank.shape[0] != n_fft // 2 + 1 or window.numel() != n_fft or tuple(band.shape) != (M, 2) or band.dtype != torch.int32:
+        raise ValueError("window (n_fft,), fbank (n_fft // 2 + 1, M) and band (M, 2) int32 expected")
+    T = 1 + n // hop
+    fb, win, bd = fbank.float().contiguous(), window.float().contiguous(), band.contiguous()
+    out = torch.empty((Bt, T, M), dtype=torch.float32, device=wav.device)
+    umax = torch.full((Bt,), float("-inf"), dtype=torch.float32, device=wav.device)
+    a = cabi.FbankWavArgs()
+    a.batch, a.n_samples, a.frames, a.nmels = Bt, n, T, M
+    a.n_fft, a.hop = int(n_fft), int(hop)
+    a.wav, a.wav_sb = wav.data_ptr(), wav.stride(0)
+    a.window, a.fbank, a.band, a.out, a.utt_max = win.data_ptr(), fb.data_ptr(), bd.data_ptr(), out.data_ptr(), umax.data_ptr()
+    a.amin, a.multiplier, a.db_offset, a.top_db = amin, multiplier, db_offset, top_db
+    f = cabi.FbankArgs()
+    f.batch, f.frames, f.nbins, f.nmels = Bt, T, n_fft // 2 + 1, M
+    f.out, f.utt_max, f.top_db = out.data_ptr(), umax.data_ptr(), top_db
+    st = cabi.stream_ptr()
+    _call("cm_fbank_wav_logmel", lib.cm_fbank_wav_logmel, C.byref(a), st)
+    _call("cm_fbank_floor", lib.cm_fbank_floor, C.byref(f), st)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ LayerNorm
 def layernorm_forward(x2d, weight, bias, eps, out_dtype):
     """cm_layernorm_fwd over the rows of a (rows, C) CUDA tensor with unit column stride.

@@ -228,8 +228,13 @@ def test_extension_module_shims_follow_the_pybind_abi():
 
 
 # ------------------------------------------------------------------------------------------------ fbank
-@pytest.mark.parametrize("cfg", [dict(n_fft=512, win_length=32), dict(n_fft=400, win_length=25)])
-def test_fbank_matches_oracle(cfg):
+@pytest.mark.parametrize("route", ["dft_kernel", "cufft"])
+@pytest.mark.parametrize("cfg", [dict(n_fft=512, win_length=32), dict(n_fft=400, win_length=25), dict(n_fft=512, win_length=25)])
+def test_fbank_matches_oracle(cfg, route, monkeypatch):
+    """Both routes of the front-end against the oracle: the one-kernel windowed DFT (cm_fbank_wav_logmel, default) and
+    torch.stft + cm_fbank_logmel (CM_FBANK_CUFFT=1); n_fft 512 / win 25 ms is hparams/CTC/conmamba_large.yaml:103-105."""
+    if route == "cufft":
+        monkeypatch.setenv("CM_FBANK_CUFFT", "1")
     from mamba_asr_b200 import Fbank
     from oracle.fbank_ref import fbank_oracle
     g = torch.Generator().manual_seed(3402)
@@ -242,6 +247,24 @@ def test_fbank_matches_oracle(cfg):
     # dB values; same STFT algorithm on a different FFT library: compare with the fp32 contract on the dB scale
     assert_close(out, ref, floor="max", what="fbank dB")
     assert float((out[1].max() - out[1].min()).cpu()) <= 80.0 + 1e-3
+
+
+def test_fbank_dft_kernel_agrees_with_cufft_route_on_ragged_lengths(monkeypatch):
+    """The in-kernel DFT against cuFFT on the same samples: lengths that end inside a frame, a single frame, silence, and a
+    tone (weak bins 100 dB below the strongest: the fp32 two-stage DFT must not raise their floor)."""
+    from mamba_asr_b200 import Fbank
+    g = torch.Generator().manual_seed(77)
+    for n_fft, win in ((400, 25), (512, 32), (512, 25)):
+        fb = Fbank(sample_rate=16000, n_mels=80, n_fft=n_fft, win_length=win).cuda()
+        for n in (159, 160, 1601, 16000 + 81, 48000):
+            wav = 0.05 * torch.randn(2, n, generator=g)
+            wav[1] = torch.sin(2 * 3.14159265 * 440.0 * torch.arange(n) / 16000.0)
+            a = fb(wav.cuda())
+            monkeypatch.setenv("CM_FBANK_CUFFT", "1")
+            b = fb(wav.cuda())
+            monkeypatch.delenv("CM_FBANK_CUFFT")
+            assert a.shape == b.shape == (2, 1 + n // 160, 80)
+            assert_close(a, b, floor="max", what=f"fbank dft vs cufft n_fft={n_fft} n={n}")
 
 
 def test_fbank_frame_count_is_bit_exact():

@@ -5,7 +5,8 @@
     compute-sanitizer --tool racecheck python tools/sanitize.py
 
 Covers the kernels that synchronise through mbarrier full/empty pairs, named barriers and __syncwarp (scan_fwd_sp,
-scan_bwd_sp), the TMA kernels (scan_fwd_lc, scan_bwd_lc: async-proxy writes into shared memory), the conv kernels and the
+scan_bwd_sp), the TMA kernels (scan_fwd_lc, scan_bwd_lc, scan_fwd_wg, scan_bwd_wg: async-proxy writes into shared memory, setmaxnreg
+roles, tensor-core reductions), the one-kernel Fbank front-end, the conv kernels and the
 fused LayerNorm + activation kernels, at L in {1, 9, 17, 131} and D in {288, 128}."""
 import os
 import sys
@@ -41,7 +42,8 @@ def main():
     dt = torch.bfloat16
     n = 0
     for L in (1, 9, 17, 131):
-        for D, env in ((288, {}), (128, {}), (128, {"CM_SCAN_LC": "1", "CM_SCAN_LC_BWD": "1"})):
+        for D, env in ((288, {}), (128, {}), (128, {"CM_SCAN_LC": "1", "CM_SCAN_LC_BWD": "1"}),
+                       (288, {"CM_SCAN_WG": "1", "CM_SCAN_WG_FWD": "1"}), (128, {"CM_SCAN_WG": "1", "CM_SCAN_WG_FWD": "1"})):
             scan_case(2, D, L, dt, env)
             n += 1
         x = torch.randn(2, L, 288, device="cuda").to(dt).transpose(1, 2)
@@ -53,6 +55,9 @@ def main():
         w, b = torch.ones(640, device="cuda"), torch.zeros(640, device="cuda")
         y, mean, rstd = K.ln_act_forward(xm, w, b, 1e-5)
         K.ln_act_backward(xm, torch.ones_like(y), w, b, mean, rstd)
+        from mamba_asr_b200 import Fbank
+        for n_fft, win in ((400, 25), (512, 25)):
+            Fbank(n_fft=n_fft, n_mels=80, win_length=win).cuda()(torch.randn(2, 160 * L + 7, device="cuda"))
         torch.cuda.synchronize()
     print("sanitize.py: %d scan cases + conv + ln_act at L in (1, 9, 17, 131) completed" % n)
 

@@ -82,12 +82,17 @@ def peaks():
 
 def ncu_traffic(entry, workload):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `entry` at this workload's shape, from the committed
-    `ncu --set full` capture (profiles/r01_traffic.json, written by tools/ncu_traffic.py); None if not captured."""
-    try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        return d.get("%s@%s" % (entry, workload))
-    except Exception:
-        return None
+    `ncu --set full` capture of the kernel that ships (profiles/r02_traffic.json, written by tools/ncu_traffic.py; the
+    round-1 file holds the round-1 kernels); None if not captured."""
+    key = "%s@%s" % (entry, workload)
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            d = json.load(open(os.path.join(ROOT, "profiles", name)))
+        except Exception:
+            continue
+        if key in d:
+            return d[key]
+    return None
 
 
 class ClockSampler:

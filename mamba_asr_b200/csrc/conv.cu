@@ -14,6 +14,7 @@
 // that cm_reduce_rows() sums in a fixed order (no atomics, deterministic).
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -309,6 +310,241 @@ __global__ void __launch_bounds__(32 * kTY) conv_bwd_cl_kernel(const cm_conv_arg
 }
 
 // ---------------------------------------------------------------------------------------------------
+// channel-last backward, sliding-window form (round 2): a thread owns TWO adjacent channels and a whole 64-step chunk
+// ---------------------------------------------------------------------------------------------------
+// conv_bwd_cl_kernel above scatters every upstream-gradient row into a 16-step register window of dx: 112 instructions per
+// (channel, step) with both directions, 168 registers, 3 CTAs per SM (profiles/r02_conv_bwd_cfg3_shipped_ncu.txt: issue
+// bound at 17 % occupancy, 0.14 of the HBM peak).  Here the thread walks its chunk in time order and keeps 4-deep windows
+// in registers (the loop is unrolled by 4, so the rotation is register renaming):
+//   X  = x[l-3 .. l]                  both pre-activations of a step come from the same window:
+//        s_f[l]   = b_f + sum_j w_f[j] x[l-3+j]          s_b[l-3] = b_b + sum_j w_b[j] x[l-j]
+//   GF = ge_f[l-3 .. l]               effective gradients  ge = g * silu'(s)
+//   GB = ge_b[l-6 .. l-3]             (the anticausal direction runs three steps behind: its s needs x up to l)
+//   dx[l-3] = sum_j w_f[j] GF[l-j] + sum_j w_b[j] GB[l-6+j]
+// dweight / dbias accumulate in registers over the chunk and are written as the chunk's partial row directly (the thread
+// owns the whole chunk: no shared-memory reduction).  State pairs are packed (FFMA2 on the two channels).  Per chunk a
+// thread reads 70 rows of x and 67 / 70 of the two gradients for 64 rows of dx: 5-9 % halo instead of 37 %.
+template <typename T> struct PairLd;      // two adjacent elements -> float2 (ld_raw / cvt split: loads are issued groups ahead)
+template <> struct PairLd<float> {
+  using Raw = float2;
+  static __device__ __forceinline__ Raw ld_raw(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+  static __device__ __forceinline__ Raw zero() { return make_float2(0.f, 0.f); }
+  static __device__ __forceinline__ float2 cvt(Raw r) { return r; }
+  static __device__ __forceinline__ float2 ld(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+  static __device__ __forceinline__ void st(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+};
+template <> struct PairLd<__nv_bfloat16> {
+  using Raw = uint32_t;
+  static __device__ __forceinline__ Raw ld_raw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+  static __device__ __forceinline__ Raw zero() { return 0u; }
+  static __device__ __forceinline__ float2 cvt(Raw r) { return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u)); }
+  static __device__ __forceinline__ float2 ld(const __nv_bfloat16* p) { return cvt(ld_raw(p)); }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, float2 v) {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y);
+  }
+};
+template <> struct PairLd<__half> {
+  using Raw = uint32_t;
+  static __device__ __forceinline__ Raw ld_raw(const __half* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+  static __device__ __forceinline__ Raw zero() { return 0u; }
+  static __device__ __forceinline__ float2 cvt(Raw r) { return __half22float2(*reinterpret_cast<const __half2*>(&r)); }
+  static __device__ __forceinline__ float2 ld(const __half* p) { return cvt(ld_raw(p)); }
+  static __device__ __forceinline__ void st(__half* p, float2 v) { *reinterpret_cast<__half2*>(p) = __floats2half2_rn(v.x, v.y); }
+};
+
+template <bool PRECISE>
+__device__ __forceinline__ float2 silu_grad2(float2 s) {
+  return make_float2(silu_grad<PRECISE>(s.x), silu_grad<PRECISE>(s.y));
+}
+
+// M0 / M1: mode of direction slot 0 / 1: 0 causal, 1 anticausal, -1 absent
+#ifndef CM_CONV_SW_MINB
+#define CM_CONV_SW_MINB 3
+#endif
+template <typename T, bool SILU, int M0, int M1>
+__global__ void __launch_bounds__(128, CM_CONV_SW_MINB) conv_bwd_sw_kernel(const cm_conv_args p) {
+  constexpr bool PRECISE = sizeof(T) == 4;
+  constexpr int NS = (M0 >= 0 ? 1 : 0) + (M1 >= 0 ? 1 : 0);
+  const int d0 = (blockIdx.x * 128 + threadIdx.x) * 2;
+  if (d0 >= p.dim) return;
+  const int L = p.seqlen, W = p.width;
+  const int l0 = blockIdx.y * kChunk, l1 = min(l0 + kChunk, L);
+  const int b = blockIdx.z;
+  const T* xp = static_cast<const T*>(p.x.ptr) + b * p.x.sb + d0;
+  T* dxp = static_cast<T*>(p.dx.ptr) + b * p.dx.sb + d0;
+
+  // per direction slot: taps (pairs over the two channels), upstream-gradient pointer, accumulators
+  float2 w[2][4], bias[2], dw[2][4], db[2];
+  const T* gp[2];
+  int64_t gsl[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int mode = r == 0 ? M0 : M1;
+    if (mode < 0) continue;
+    const cm_conv_dir& dr = p.dir[r];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = j - (4 - W);
+      w[r][j] = (k >= 0) ? make_float2(__ldg(dr.weight + (int64_t)d0 * W + k), __ldg(dr.weight + (int64_t)(d0 + 1) * W + k))
+                         : make_float2(0.f, 0.f);
+      dw[r][j] = make_float2(0.f, 0.f);
+    }
+    bias[r] = dr.bias ? make_float2(__ldg(dr.bias + d0), __ldg(dr.bias + d0 + 1)) : make_float2(0.f, 0.f);
+    db[r] = make_float2(0.f, 0.f);
+    gp[r] = static_cast<const T*>(dr.out.ptr) + b * dr.out.sb + d0;
+    gsl[r] = dr.out.sl;
+  }
+  const float2 zero2 = make_float2(0.f, 0.f);
+  auto ldx = [&](int l) { return (l >= 0 && l < L) ? PairLd<T>::ld(xp + (int64_t)l * p.x.sl) : zero2; };
+  auto ldg = [&](int r, int l) { return (l >= 0 && l < L) ? PairLd<T>::ld(gp[r] + (int64_t)l * gsl[r]) : zero2; };
+
+  // windows, slot = step & 3
+  float2 X[4], GE[2][4], GD[2][4];          // GD: raw upstream gradient of an anticausal slot, delayed by three steps
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    X[i] = zero2;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) { GE[r][i] = zero2; GD[r][i] = zero2; }
+  }
+  // steps l0-3 .. l0-1 only fill the windows: x, and the delayed gradients of the anticausal slots
+#pragma unroll
+  for (int i = 1; i <= 3; ++i) {
+    X[i] = ldx(l0 - 4 + i);                  // slot of step l is (l - l0) & 3: steps l0-3, l0-2, l0-1 -> slots 1, 2, 3
+    if (M0 == 1) GD[0][i] = ldg(0, l0 - 4 + i);
+    if (M1 == 1) GD[1][i] = ldg(1, l0 - 4 + i);
+  }
+
+  // one step.  PH = (l - l0) & 3 is a compile-time constant inside the unrolled body
+  auto step = [&](auto ph_c, const int l, const float2 xv, const float2 g0v, const float2 g1v) {
+    constexpr int PH = decltype(ph_c)::value;
+    constexpr int S0 = PH, S1 = (PH + 3) & 3, S2 = (PH + 2) & 3, S3 = (PH + 1) & 3;   // slots of steps l, l-1, l-2, l-3
+    X[S0] = xv;
+    float2 dxv = zero2;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int mode = r == 0 ? M0 : M1;
+      if (mode < 0) continue;
+      if (mode == 0) {
+        // causal: s_f[l] = b + w0 x[l-3] + w1 x[l-2] + w2 x[l-1] + w3 x[l];  ge_f[l] joins the window
+        float2 ge = r == 0 ? g0v : g1v;
+        if (SILU) {
+          float2 s = ffma2(w[r][0], X[S3], bias[r]);
+          s = ffma2(w[r][1], X[S2], s); s = ffma2(w[r][2], X[S1], s); s = ffma2(w[r][3], X[S0], s);
+          ge = fmul2(ge, silu_grad2<PRECISE>(s));
+        }
+        GE[r][S0] = ge;
+        // dx[l-3] += w0 ge[l-3] + w1 ge[l-2] + w2 ge[l-1] + w3 ge[l]  ... with tap j on ge[l-3+(3-j)] = ge[l-j]
+        dxv = ffma2(w[r][0], GE[r][S0], dxv); dxv = ffma2(w[r][1], GE[r][S1], dxv);
+        dxv = ffma2(w[r][2], GE[r][S2], dxv); dxv = ffma2(w[r][3], GE[r][S3], dxv);
+        const float2 go = (l < l1) ? ge : zero2;          // every step is owned by exactly one chunk
+        dw[r][0] = ffma2(go, X[S3], dw[r][0]); dw[r][1] = ffma2(go, X[S2], dw[r][1]);
+        dw[r][2] = ffma2(go, X[S1], dw[r][2]); dw[r][3] = ffma2(go, X[S0], dw[r][3]);
+        db[r] = fadd2(db[r], go);
+      } else {
+        // anticausal, three steps behind: s_b[l-3] = b + w0 x[l] + w1 x[l-1] + w2 x[l-2] + w3 x[l-3]
+        float2 ge = GD[r][S3];                             // upstream gradient of step l-3
+        GD[r][S0] = r == 0 ? g0v : g1v;
+        if (SILU) {
+          float2 s = ffma2(w[r][0], X[S0], bias[r]);
+          s = ffma2(w[r][1], X[S1], s); s = ffma2(w[r][2], X[S2], s); s = ffma2(w[r][3], X[S3], s);
+          ge = fmul2(ge, silu_grad2<PRECISE>(s));
+        }
+        // window of effective gradients: slot S0 <- ge_b[l-3]; S1, S2, S3 hold ge_b[l-4], ge_b[l-5], ge_b[l-6]
+        GE[r][S0] = ge;
+        // dx[l-3] += sum_j w[j] ge_b[l-6+j]
+        dxv = ffma2(w[r][0], GE[r][S3], dxv); dxv = ffma2(w[r][1], GE[r][S2], dxv);
+        dxv = ffma2(w[r][2], GE[r][S1], dxv); dxv = ffma2(w[r][3], GE[r][S0], dxv);
+        const float2 go = (l - 3 >= l0 && l - 3 < l1) ? ge : zero2;
+        dw[r][0] = ffma2(go, X[S0], dw[r][0]); dw[r][1] = ffma2(go, X[S1], dw[r][1]);
+        dw[r][2] = ffma2(go, X[S2], dw[r][2]); dw[r][3] = ffma2(go, X[S3], dw[r][3]);
+        db[r] = fadd2(db[r], go);
+      }
+    }
+    if (l - 3 >= l0 && l - 3 < l1) PairLd<T>::st(dxp + (int64_t)(l - 3) * p.dx.sl, dxv);
+  };
+  // steps l0 .. l1+2 (the last three only flush the windows), in groups of 4 so that the window slots are compile-time.
+  // The rows of a group are loaded TWO GROUPS AHEAD into raw registers (12 loads in flight per thread at any time): the
+  // first version loaded each row where it was used and ran at the speed of one DRAM round trip per step.
+  using PL = PairLd<T>;
+  typename PL::Raw rx[2][4], rg0[2][4], rg1[2][4];
+  auto load_group = [&](auto buf_c, const int lb) {
+    constexpr int B = decltype(buf_c)::value;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int l = lb + i;
+      const bool in = l < L;                 // l >= l0 >= 0
+      rx[B][i] = in ? PL::ld_raw(xp + (int64_t)l * p.x.sl) : PL::zero();
+      rg0[B][i] = (M0 >= 0 && in) ? PL::ld_raw(gp[0] + (int64_t)l * gsl[0]) : PL::zero();
+      rg1[B][i] = (M1 >= 0 && in) ? PL::ld_raw(gp[1] + (int64_t)l * gsl[1]) : PL::zero();
+    }
+  };
+  auto run_group = [&](auto buf_c, const int lb) {
+    constexpr int B = decltype(buf_c)::value;
+    float2 xv[4], g0v[4], g1v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { xv[i] = PL::cvt(rx[B][i]); g0v[i] = PL::cvt(rg0[B][i]); g1v[i] = PL::cvt(rg1[B][i]); }
+    load_group(buf_c, lb + 8);               // refill the buffer just unpacked: the rows of the group after next
+    step(std::integral_constant<int, 0>{}, lb, xv[0], g0v[0], g1v[0]);
+    step(std::integral_constant<int, 1>{}, lb + 1, xv[1], g0v[1], g1v[1]);
+    step(std::integral_constant<int, 2>{}, lb + 2, xv[2], g0v[2], g1v[2]);
+    step(std::integral_constant<int, 3>{}, lb + 3, xv[3], g0v[3], g1v[3]);
+  };
+  const int lend = l1 + 3;
+  load_group(std::integral_constant<int, 0>{}, l0);
+  load_group(std::integral_constant<int, 1>{}, l0 + 4);
+#pragma unroll 1
+  for (int l = l0; l < lend; l += 8) {
+    run_group(std::integral_constant<int, 0>{}, l);
+    run_group(std::integral_constant<int, 1>{}, l + 4);
+  }
+
+  const int64_t prow = (int64_t)b * gridDim.y + blockIdx.y;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int mode = r == 0 ? M0 : M1;
+    if (mode < 0) continue;
+    const cm_conv_dir& dr = p.dir[r];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = j - (4 - W);
+      if (k >= 0) {
+        dr.dweight_part[(prow * p.dim + d0) * W + k] = dw[r][j].x;
+        dr.dweight_part[(prow * p.dim + d0 + 1) * W + k] = dw[r][j].y;
+      }
+    }
+    if (dr.dbias_part) {
+      dr.dbias_part[prow * p.dim + d0] = db[r].x;
+      dr.dbias_part[prow * p.dim + d0 + 1] = db[r].y;
+    }
+  }
+  (void)NS;
+}
+
+template <typename T>
+static bool launch_conv_bwd_sw(const cm_conv_args& a, cudaStream_t st) {
+  if (getenv("CM_CONV_NO_SW") != nullptr) return false;
+  const dim3 grid(cm_ceil_div(a.dim / 2, 128), cm_ceil_div(a.seqlen, kChunk), a.batch);
+  const bool silu = (a.flags & CM_FLAG_SILU) != 0;
+  const int m0 = a.dir[0].anticausal ? 1 : 0, m1 = a.ndir == 2 ? (a.dir[1].anticausal ? 1 : 0) : -1;
+#define CM_SW(S, A0, A1) conv_bwd_sw_kernel<T, S, A0, A1><<<grid, 128, 0, st>>>(a)
+  if (silu) {
+    if (m0 == 0 && m1 == 1) CM_SW(true, 0, 1);
+    else if (m0 == 1 && m1 == 0) CM_SW(true, 1, 0);
+    else if (m0 == 0 && m1 == -1) CM_SW(true, 0, -1);
+    else if (m0 == 1 && m1 == -1) CM_SW(true, 1, -1);
+    else return false;
+  } else {
+    if (m0 == 0 && m1 == 1) CM_SW(false, 0, 1);
+    else if (m0 == 1 && m1 == 0) CM_SW(false, 1, 0);
+    else if (m0 == 0 && m1 == -1) CM_SW(false, 0, -1);
+    else if (m0 == 1 && m1 == -1) CM_SW(false, 1, -1);
+    else return false;
+  }
+#undef CM_SW
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // generic-stride kernels: one thread per (b, d, l), lanes along time
 // ---------------------------------------------------------------------------------------------------
 template <typename T>
@@ -468,7 +704,8 @@ static int launch_conv_t(const cm_conv_args& a, bool bwd, cudaStream_t st) {
       else if (vec == 2) conv_fwd_cl_kernel<T, 2><<<grid, block, 0, st>>>(a);
       else conv_fwd_cl_kernel<T, 1><<<grid, block, 0, st>>>(a);
     } else {
-      if (vec == 2) conv_bwd_cl_kernel<T, 2><<<grid, block, 0, st>>>(a);
+      if (vec == 2 && launch_conv_bwd_sw<T>(a, st)) { /* sliding-window kernel */ }
+      else if (vec == 2) conv_bwd_cl_kernel<T, 2><<<grid, block, 0, st>>>(a);
       else conv_bwd_cl_kernel<T, 1><<<grid, block, 0, st>>>(a);
     }
   } else {

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Reads dram__bytes_read.sum + dram__bytes_write.sum of the first kernel in an .ncu-rep and records it in
-profiles/r01_traffic.json under KEY (e.g. cm_scan_bwd@conmamba_small_ctc_fwdbwd_b32x15s) - bench.py's roofline.traffic.
+profiles/r02_traffic.json under KEY (e.g. cm_scan_bwd@conmamba_small_ctc_fwdbwd_b32x15s) - bench.py's roofline.traffic.
 
     python tools/ncu_traffic.py gpurun_out/x.ncu-rep KEY
 """
@@ -26,7 +26,7 @@ def main():
     hdr, units, vals = rows[0], rows[1], rows[2]
     m = {h: (u, v) for h, u, v in zip(hdr, units, vals)}
     tot = sum(to_bytes(m[k][1], m[k][0]) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
     d = json.load(open(path)) if os.path.exists(path) else {}
     d[key] = tot
     d[key + ":source"] = "%s (%s)" % (os.path.basename(rep), m.get("Kernel Name", ("", "?"))[1])

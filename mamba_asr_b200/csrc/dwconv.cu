@@ -15,6 +15,8 @@
 //                             shared memory and each CTA writes one partial row (fixed-order reduction by cm_reduce_multi:
 //                             deterministic, no atomics)
 // Roof: HBM / FP32 issue (balanced).  Algorithmic bytes per position: 2s forward, 2s backward-data, 2s backward-weight.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cm {
@@ -121,10 +123,187 @@ __global__ void __launch_bounds__(32 * kDwWarps) dwconv_bwd_weight_kernel(const 
   }
 }
 
+// ---- shared-memory tiled kernels (round 2) --------------------------------------------------------------------------
+// The kernels above load each input row where the window needs it: one DRAM round trip per 31 outputs in front of a
+// dependent FMA chain, 126 registers, 49 / 60 us per launch at 64 x 501 x 256 against a 5 us HBM / 7 us FP32 balance
+// (0.10 of the HBM peak).  Here a warp first brings the whole slab it needs - TW + K - 1 rows of 32 channels - into its
+// private shared-memory tile with cp.async (16-byte chunks, every row in flight at once, rows outside [0, L) and channels
+// outside [0, dim) zero-filled), then walks it in groups of R = 8 outputs: R + K - 1 conflict-free LDS per lane feed R * K
+// FFMA from registers (taps in registers as before).  No global-memory latency inside the arithmetic, 80 registers.
+constexpr int kDwR = 8;                      // outputs per register group
+
+__device__ __forceinline__ void cp_async16_zfill(void* dst, const void* src, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+
+template <int K> struct DwTile {
+  static constexpr int TW = DwCfg<K>::TW;
+  static constexpr int NG = (TW + kDwR - 1) / kDwR;        // groups per slab
+  static constexpr int RX = NG * kDwR + K - 1;             // input rows of a warp tile
+  static constexpr int RG = NG * kDwR;                     // upstream-gradient rows (backward-weight)
+};
+
+// rows [r0, r0 + nrows) x channels [c_blk, c_blk + 32) of a (batch b) channel-last tensor -> tile[nrows][32]
+template <typename T>
+__device__ __forceinline__ void dw_load_tile(T* tile, const T* base, int64_t sl, int r0, int nrows, int L, int c_blk, int dim,
+                                             int lane) {
+  constexpr int EPC = 16 / (int)sizeof(T);    // elements per 16-byte chunk
+  constexpr int CPR = 32 / EPC;               // chunks per row
+  for (int i = lane; i < nrows * CPR; i += 32) {
+    const int row = i / CPR, ch = i - row * CPR;
+    const int r = r0 + row, c = c_blk + ch * EPC;
+    const bool ok = r >= 0 && r < L && c < dim;
+    cp_async16_zfill(tile + row * 32 + ch * EPC, ok ? base + (int64_t)r * sl + c : base, ok);
+  }
+}
+
+template <typename T, int K>
+__global__ void __launch_bounds__(32 * kDwWarps) dwconv_fwd_tile_kernel(const cm_dwconv_args p) {
+  using DT = DwTile<K>;
+  extern __shared__ __align__(16) unsigned char dw_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c_blk = blockIdx.x * 32;
+  const int c = c_blk + lane;
+  const bool act = c < p.dim;
+  const int b = blockIdx.z;
+  const int t0 = (blockIdx.y * kDwWarps + warp) * DT::TW;
+  const int L = p.seqlen;
+  if (t0 >= L) return;
+  T* tile = reinterpret_cast<T*>(dw_smem) + (size_t)warp * DT::RX * 32;
+  dw_load_tile<T>(tile, static_cast<const T*>(p.x.ptr) + b * p.x.sb, p.x.sl, t0 - p.pad_left, DT::RX, L, c_blk, p.dim, lane);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  const int cc = act ? c : 0;
+  float w[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) w[k] = act ? __ldg(p.weight + (int64_t)cc * K + (p.flip ? K - 1 - k : k)) : 0.f;
+  const float bias = (act && p.bias != nullptr) ? __ldg(p.bias + cc) : 0.f;
+  T* yp = static_cast<T*>(p.y.ptr) + b * p.y.sb + cc;
+  const int64_t ysl = p.y.sl;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+  const T* col = tile + lane;
+#pragma unroll 1
+  for (int o = 0; o < DT::TW; o += kDwR) {
+    if (t0 + o >= L) break;
+    float in[kDwR + K - 1];
+#pragma unroll
+    for (int i = 0; i < kDwR + K - 1; ++i) {
+      if constexpr (sizeof(T) == 4) in[i] = reinterpret_cast<const float*>(col)[(o + i) * 32];
+      else in[i] = Elem<T>::cvt(reinterpret_cast<const unsigned short*>(col)[(o + i) * 32]);
+    }
+#pragma unroll
+    for (int j = 0; j < kDwR; ++j) {
+      float acc = bias;
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc = fmaf(w[k], in[j + k], acc);
+      const int l = t0 + o + j;
+      if (act && o + j < DT::TW && l < L) Elem<T>::st(yp + l * ysl, acc);
+    }
+  }
+}
+
+template <typename T, int K>
+__global__ void __launch_bounds__(32 * kDwWarps) dwconv_bwdw_tile_kernel(const cm_dwconv_args p) {
+  using DT = DwTile<K>;
+  extern __shared__ __align__(16) unsigned char dw_smem[];
+  __shared__ float red[kDwWarps][K + 1][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c_blk = blockIdx.x * 32;
+  const int c = c_blk + lane;
+  const bool act = c < p.dim;
+  const int b = blockIdx.z;
+  const int t0 = (blockIdx.y * kDwWarps + warp) * DT::TW;
+  const int L = p.seqlen;
+  float dw[K], db = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) dw[k] = 0.f;
+  if (t0 < L) {
+    T* xt = reinterpret_cast<T*>(dw_smem) + (size_t)warp * (DT::RX + DT::RG) * 32;
+    T* gt = xt + DT::RX * 32;
+    dw_load_tile<T>(xt, static_cast<const T*>(p.x.ptr) + b * p.x.sb, p.x.sl, t0 - p.pad_left, DT::RX, L, c_blk, p.dim, lane);
+    // upstream-gradient rows of this slab only (rows of the next slab are zeroed: they belong to the next warp)
+    dw_load_tile<T>(gt, static_cast<const T*>(p.dy.ptr) + b * p.dy.sb, p.dy.sl, t0, DT::RG, min(L, t0 + DT::TW), c_blk, p.dim, lane);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    const T* xc = xt + lane;
+    const T* gc = gt + lane;
+#pragma unroll 1
+    for (int o = 0; o < DT::TW; o += kDwR) {
+      if (t0 + o >= L) break;
+      float in[kDwR + K - 1], g[kDwR];
+#pragma unroll
+      for (int i = 0; i < kDwR + K - 1; ++i) {
+        if constexpr (sizeof(T) == 4) in[i] = reinterpret_cast<const float*>(xc)[(o + i) * 32];
+        else in[i] = Elem<T>::cvt(reinterpret_cast<const unsigned short*>(xc)[(o + i) * 32]);
+      }
+#pragma unroll
+      for (int j = 0; j < kDwR; ++j) {
+        if constexpr (sizeof(T) == 4) g[j] = reinterpret_cast<const float*>(gc)[(o + j) * 32];
+        else g[j] = Elem<T>::cvt(reinterpret_cast<const unsigned short*>(gc)[(o + j) * 32]);
+        db += g[j];
+      }
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int j = 0; j < kDwR; ++j) dw[k] = fmaf(g[j], in[j + k], dw[k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) red[warp][k][lane] = dw[k];
+  red[warp][K][lane] = db;
+  __syncthreads();
+  // fixed-order sum over the CTA's warps; one partial row per CTA
+  const int64_t part = (int64_t)blockIdx.z * gridDim.y + blockIdx.y;
+  for (int i = threadIdx.x; i < (K + 1) * 32; i += blockDim.x) {
+    const int k = i / 32, ln = i % 32;
+    const int ch = blockIdx.x * 32 + ln;
+    if (ch >= p.dim) continue;
+    float a = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < kDwWarps; ++wv) a += red[wv][k][ln];
+    if (k < K) p.dweight_part[(part * p.dim + ch) * K + k] = a;
+    else if (p.dbias_part != nullptr) p.dbias_part[part * p.dim + ch] = a;
+  }
+}
+
+// the tiled kernels need channel-last tensors whose rows can be fetched in 16-byte chunks
+template <typename T>
+static bool dw_tile_ok(const cm_dwconv_args& a, bool wgrad) {
+  if (getenv("CM_DWCONV_NO_TILE") != nullptr) return false;
+  constexpr int EPC = 16 / (int)sizeof(T);
+  auto ok = [&](const cm_tensor3& t) {
+    return t.ptr != nullptr && t.sd == 1 && (reinterpret_cast<uintptr_t>(t.ptr) & 15) == 0 && t.sl % EPC == 0 && t.sb % EPC == 0;
+  };
+  if (a.dim % EPC != 0 || !ok(a.x)) return false;
+  if (wgrad) return ok(a.dy);
+  return a.y.ptr != nullptr && a.y.sd == 1;
+}
+
 template <typename T, int K>
 static int dw_launch(const cm_dwconv_args& a, bool wgrad, cudaStream_t st) {
   constexpr int TW = DwCfg<K>::TW;
   const dim3 grid(cm_ceil_div(a.dim, 32), cm_ceil_div(a.seqlen, kDwWarps * TW), a.batch);
+  if (dw_tile_ok<T>(a, wgrad)) {
+    using DT = DwTile<K>;
+    const size_t smem = (size_t)kDwWarps * (wgrad ? DT::RX + DT::RG : DT::RX) * 32 * sizeof(T);
+    if (wgrad) {
+      auto kern = dwconv_bwdw_tile_kernel<T, K>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
+      if (e != cudaSuccess) return (int)e;
+      kern<<<grid, 32 * kDwWarps, smem, st>>>(a);
+    } else {
+      auto kern = dwconv_fwd_tile_kernel<T, K>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      kern<<<grid, 32 * kDwWarps, smem, st>>>(a);
+    }
+    CM_LAUNCH_CHECK();
+    return 0;
+  }
   if (wgrad) dwconv_bwd_weight_kernel<T, K><<<grid, 32 * kDwWarps, 0, st>>>(a);
   else dwconv_fwd_kernel<T, K><<<grid, 32 * kDwWarps, 0, st>>>(a);
   CM_LAUNCH_CHECK();

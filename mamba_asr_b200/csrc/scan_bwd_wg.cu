@@ -64,6 +64,9 @@ constexpr int kHR = CM_BWDWG_HREG;        // last kHR steps of a tile keep their
 #ifndef CM_BWDWG_IREG
 #define CM_BWDWG_IREG 40
 #endif
+#ifndef CM_BWDWG_FENCE
+#define CM_BWDWG_FENCE 2
+#endif
 constexpr float kLn2f = 0.6931471805599453f;
 // -DCM_ABL_*: timing ablations (tools/_run_r2n.sh); they change the results and are never part of the product build
 #ifdef CM_ABL_NOEX2
@@ -324,7 +327,9 @@ __device__ __forceinline__ void scan_role(const BwdParams& P, Smem<T>& S, const 
     hist_at(kTB - 1, hk);
 #pragma unroll
     for (int k = kTB - 1; k >= 0; --k) {
-      if ((k & 1) == 1) asm volatile("" ::: "memory");   // scheduling fence: bounds how far ptxas hoists operand loads
+#if CM_BWDWG_FENCE > 0
+      if ((k % CM_BWDWG_FENCE) == CM_BWDWG_FENCE - 1) asm volatile("" ::: "memory");   // scheduling fence: bounds how far ptxas hoists operand loads
+#endif
       const float4 dd = ddb[k * kNP];
       const float2 dy = dyb[k * kNP];
       const float4 bb = *reinterpret_cast<const float4*>(bcb + k * 32);

@@ -94,18 +94,29 @@ __global__ void __launch_bounds__(256) gelu_dropout_fwd_kernel(const T* __restri
   const uint32_t thr = drop ? (uint32_t)(p * 65536.0f) : 0u;
   const float scale = drop ? 1.0f / (1.0f - p) : 1.0f;
   const uint32_t key = drop ? act_key(seed, call_id) : 0u;
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n8; v += (int64_t)gridDim.x * blockDim.x) {
-    float a[8];
-    Vec8<T>::ld(x + 8 * v, a);
-    const uint32_t kb = drop ? keep8(key, v, thr) : 0xffu;
+  // two 16-byte chunks per thread and iteration, both loads issued before the first use: one chunk per thread keeps only
+  // 32 KB per SM in flight at full occupancy, below the latency x bandwidth product of HBM3e
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n8; v += 2 * stride) {
+    const int64_t v1 = v + stride;
+    const bool two = v1 < n8;
+    float a[2][8];
+    Vec8<T>::ld(x + 8 * v, a[0]);
+    if (two) Vec8<T>::ld(x + 8 * v1, a[1]);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = ((kb >> i) & 1u) ? scale * gelu_f(a[i]) : 0.f;
-    Vec8<T>::st(y + 8 * v, a);
-    if (drop) {
-      uint2 m;
-      m.x = (kb & 1u) | ((kb & 2u) << 7) | ((kb & 4u) << 14) | ((kb & 8u) << 21);
-      m.y = ((kb >> 4) & 1u) | (((kb >> 4) & 2u) << 7) | (((kb >> 4) & 4u) << 14) | (((kb >> 4) & 8u) << 21);
-      *reinterpret_cast<uint2*>(mask + 8 * v) = m;
+    for (int c = 0; c < 2; ++c) {
+      if (c == 1 && !two) break;
+      const int64_t vv = c ? v1 : v;
+      const uint32_t kb = drop ? keep8(key, vv, thr) : 0xffu;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[c][i] = ((kb >> i) & 1u) ? scale * gelu_f(a[c][i]) : 0.f;
+      Vec8<T>::st(y + 8 * vv, a[c]);
+      if (drop) {
+        uint2 m;
+        m.x = (kb & 1u) | ((kb & 2u) << 7) | ((kb & 4u) << 14) | ((kb & 8u) << 21);
+        m.y = ((kb >> 4) & 1u) | (((kb >> 4) & 2u) << 7) | (((kb >> 4) & 4u) << 14) | (((kb >> 4) & 8u) << 21);
+        *reinterpret_cast<uint2*>(mask + 8 * vv) = m;
+      }
     }
   }
 }

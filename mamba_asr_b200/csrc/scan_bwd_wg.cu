@@ -67,6 +67,9 @@ constexpr int kHR = CM_BWDWG_HREG;        // last kHR steps of a tile keep their
 #ifndef CM_BWDWG_FENCE
 #define CM_BWDWG_FENCE 2
 #endif
+#ifndef CM_BWDWG_PIPE
+#define CM_BWDWG_PIPE 0   // decays of the next step evaluated one step ahead: measured 0.569 vs 0.556 ms (ptxas already overlaps them)
+#endif
 constexpr float kLn2f = 0.6931471805599453f;
 // -DCM_ABL_*: timing ablations (tools/_run_r2n.sh); they change the results and are never part of the product build
 #ifdef CM_ABL_NOEX2
@@ -273,9 +276,38 @@ __device__ __forceinline__ void scan_role(const BwdParams& P, Smem<T>& S, const 
         for (int j = 0; j < 2; ++j) hist[k][c][j] = h[c][j];
     if (mu[0][0].x == 123.456f)
 #endif
+#if CM_BWDWG_PIPE
+    // software pipeline: the decays a = 2^(dt * kA) of step k + 1 are evaluated (LDS -> FMUL2 -> MUFU) while step k's state
+    // update runs, so that neither the shared-memory nor the MUFU latency sits in front of the dependent FFMA2 chain
+    float2 an[2][2];
+    float4 ddn = ddb[0];
+    auto decays = [&](const float4& dd_, float2 (&o)[2][2]) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float dtc = c ? dd_.y : dd_.x;
+        const float2 dt2 = make_float2(dtc, dtc);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float2 x = fmul2(dt2, kA[c][j]);
+          o[c][j] = make_float2(ex2r(x.x), ex2r(x.y));
+        }
+      }
+    };
+    decays(ddn, an);
+#endif
 #pragma unroll
     for (int k = 0; k < kTB; ++k) {
+#if CM_BWDWG_PIPE
+      const float4 dd = ddn;
+      float2 ac[2][2];
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) ac[c][j] = an[c][j];
+      if (k + 1 < kTB) { ddn = ddb[(k + 1) * kNP]; decays(ddn, an); }
+#else
       const float4 dd = ddb[k * kNP];
+#endif
       const float4 bb = *reinterpret_cast<const float4*>(bcb + k * 32);
       const float2 Bp[2] = {make_float2(bb.x, bb.y), make_float2(bb.z, bb.w)};
 #pragma unroll
@@ -284,8 +316,13 @@ __device__ __forceinline__ void scan_role(const BwdParams& P, Smem<T>& S, const 
         const float2 dt2 = make_float2(dtc, dtc), du2 = make_float2(duc, duc);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
+#if CM_BWDWG_PIPE
+          const float2 a = ac[c][j];
+          (void)dt2;
+#else
           const float2 x = fmul2(dt2, kA[c][j]);
           const float2 a = make_float2(ex2r(x.x), ex2r(x.y));
+#endif
           h[c][j] = ffma2(a, h[c][j], fmul2(du2, Bp[j]));
         }
       }
@@ -325,12 +362,27 @@ __device__ __forceinline__ void scan_role(const BwdParams& P, Smem<T>& S, const 
     };
     float2 hk[2][2];
     hist_at(kTB - 1, hk);
+#if CM_BWDWG_PIPE
+    float4 ddr = ddb[(kTB - 1) * kNP];
+    float2 ar[2][2];
+    decays(ddr, ar);
+#endif
 #pragma unroll
     for (int k = kTB - 1; k >= 0; --k) {
 #if CM_BWDWG_FENCE > 0
       if ((k % CM_BWDWG_FENCE) == CM_BWDWG_FENCE - 1) asm volatile("" ::: "memory");   // scheduling fence: bounds how far ptxas hoists operand loads
 #endif
+#if CM_BWDWG_PIPE
+      const float4 dd = ddr;
+      float2 acur[2][2];
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) acur[c][j] = ar[c][j];
+      if (k > 0) { ddr = ddb[(k - 1) * kNP]; decays(ddr, ar); }
+#else
       const float4 dd = ddb[k * kNP];
+#endif
       const float2 dy = dyb[k * kNP];
       const float4 bb = *reinterpret_cast<const float4*>(bcb + k * 32);
       const float4 cc = *reinterpret_cast<const float4*>(bcb + k * 32 + 16);
@@ -346,8 +398,12 @@ __device__ __forceinline__ void scan_role(const BwdParams& P, Smem<T>& S, const 
         const float2 dy2 = make_float2(dyc, dyc);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
+#if CM_BWDWG_PIPE
+          const float2 a = acur[c][j];
+#else
           const float2 x = fmul2(dt2, kA[c][j]);
           const float2 a = make_float2(ex2r(x.x), ex2r(x.y));
+#endif
           const float2 lam = ffma2(dy2, Cp[j], mu[c][j]);
           accC[j] = c == 0 ? fmul2(dy2, hk[c][j]) : ffma2(dy2, hk[c][j], accC[j]);
           accB[j] = c == 0 ? fmul2(du2, lam) : ffma2(du2, lam, accB[j]);

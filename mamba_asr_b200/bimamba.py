@@ -117,15 +117,21 @@ class _MambaBase(nn.Module):
         if inference_params.seqlen_offset > 0:
             out, _, _ = self.step(hidden_states, conv_state, ssm_state)
             return out
+        return self.prefill(hidden_states, conv_state, ssm_state)
+
+    def prefill(self, hidden_states, conv_state, ssm_state, need_output=True):
+        """Scan a whole prefix (B, L, d_model) from zero state with the fused kernels and leave the conv window and the last
+        SSM state in ``conv_state`` / ``ssm_state`` - from there ``step`` continues token by token.  ``need_output=False``
+        skips out_proj (the decoder's cross-Mamba only wants the state its scan over ``memory`` ends in)."""
         with torch.no_grad():
             xz = F.linear(hidden_states, self.in_proj.weight, self.in_proj.bias)          # (B, L, 2D)
             L, D = xz.shape[1], self.d_inner
             W = self.d_conv
             xt = xz[..., :D].transpose(1, 2)                                              # logical (B, D, L)
-            conv_state.copy_(F.pad(xt, (W - L, 0)))                                       # bimamba.py:277
+            conv_state.copy_(F.pad(xt, (W - L, 0)) if L < W else xt[..., L - W:])          # bimamba.py:277
             y, _, _, last = inner_forward(xz, 1, 1.0, False, self._dir_params(""), need_last_state=True)
             ssm_state.copy_(last[0])                                                      # bimamba.py:314-316
-            return F.linear(y, self.out_proj.weight, self.out_proj.bias)
+            return F.linear(y, self.out_proj.weight, self.out_proj.bias) if need_output else None
 
     def step(self, hidden_states, conv_state, ssm_state):
         """One token: hidden_states (B, 1, d_model); conv_state (B, D, W) and ssm_state (B, D, N) updated in place.

@@ -248,6 +248,37 @@ class MambaDecoderLayer(nn.Module):
             tgt = self.norm3(tgt)
         return tgt, None, None
 
+    # ---- incremental decoding: the reference re-runs the whole decoder on the growing
+    # prefix at every token (TransformerASR.py:822-866), i.e. every layer rescans [memory ; tgt] (Conmamba.py:934).  Both
+    # mixers are causal, so the scan over `memory` can be done ONCE per utterance and every further token is a single-token
+    # state update (cm_conv_update + cm_ssm_step) from cached states.
+    def init_decode(self, memory):
+        """Caches for one utterance batch: zero states for self_mamba; for cross_mamba the conv window and SSM state its scan
+        over ``memory`` (B, L, d_model) ends in."""
+        Bt = memory.shape[0]
+        cache = dict(self=self.self_mamba.allocate_inference_cache(Bt, 0), cross=self.cross_mamba.allocate_inference_cache(Bt, 0))
+        self.cross_mamba.prefill(memory, *cache["cross"], need_output=False)
+        return cache
+
+    @torch.no_grad()
+    def decode_step(self, tgt_t, cache):
+        """One target position: tgt_t (B, 1, d_model) -> (B, 1, d_model); equals row t of ``forward`` on the prefix tgt[:, :t+1]."""
+        pre = self.normalize_before
+        tgt = tgt_t
+        t = self.norm1(tgt) if pre else tgt
+        tgt = tgt + self.self_mamba.step(t, *cache["self"])[0]
+        if not pre:
+            tgt = self.norm1(tgt)
+        t = self.norm2(tgt) if pre else tgt
+        tgt = tgt + self.cross_mamba.step(t, *cache["cross"])[0]
+        if not pre:
+            tgt = self.norm2(tgt)
+        t = self.norm3(tgt) if pre else tgt
+        tgt = tgt + self.pos_ffn(t)
+        if not pre:
+            tgt = self.norm3(tgt)
+        return tgt
+
 
 class MambaDecoder(nn.Module):
     def __init__(self, num_layers, d_model, d_ffn, activation=nn.ReLU, dropout=0.0, normalize_before=False,
@@ -268,3 +299,17 @@ class MambaDecoder(nn.Module):
                                      memory_key_padding_mask=memory_key_padding_mask,
                                      pos_embs_tgt=pos_embs_tgt, pos_embs_src=pos_embs_src)
         return self.norm(output), [None], [None]
+
+    @torch.no_grad()
+    def init_decode(self, memory):
+        """Per-layer caches for incremental decoding: ``memory`` is scanned once per layer here, never again."""
+        return [layer.init_decode(memory) for layer in self.layers]
+
+    @torch.no_grad()
+    def decode_step(self, tgt_t, caches):
+        """tgt_t: (B, 1, d_model) embedding (+ positional encoding) of the newest target token -> (B, 1, d_model), the row the
+        full forward would produce for it."""
+        out = tgt_t
+        for layer, cache in zip(self.layers, caches):
+            out = layer.decode_step(out, cache)
+        return self.norm(out)

@@ -130,3 +130,34 @@ def test_step_has_no_cpu_path_and_validates():
         selective_state_update(torch.zeros(2, 8, 16, device="cuda"), torch.zeros(2, 8, device="cuda"),
                                torch.zeros(2, 8, device="cuda"), torch.zeros(8, 16, device="cuda"),
                                torch.zeros(2, 4, device="cuda"), torch.zeros(2, 16, device="cuda"))
+
+
+@pytest.mark.parametrize("autocast", [False, True])
+def test_decoder_incremental_decoding_scans_memory_once(autocast):
+    """MambaDecoder.init_decode + decode_step (the cross-Mamba scan over `memory` done once per utterance, every target token a
+    single-token state update) reproduce the full decoder forward on the same (memory, tgt) - which is what the reference
+    recomputes from scratch for every new token (TransformerASR.py:822-866, Conmamba.py:934).  Decoder of BASELINE config 4
+    (d_model 512, 2 of its 6 layers), memory of 67 frames, 11 target positions."""
+    import torch.nn as nn
+    from mamba_asr_b200.conmamba import MambaDecoder
+    torch.manual_seed(12)
+    cfg = dict(d_state=16, expand=2, d_conv=4, bidirectional=True)
+    dec = MambaDecoder(num_layers=2, d_model=512, d_ffn=2048, activation=nn.GELU, dropout=0.1, normalize_before=True,
+                       mamba_config=cfg).cuda().eval()
+    for p in dec.parameters():
+        if p.dim() > 1:
+            nn.init.xavier_normal_(p)
+    memory = torch.randn(3, 67, 512, device="cuda")
+    tgt = torch.randn(3, 11, 512, device="cuda")
+    dt = torch.bfloat16 if autocast else torch.float32
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        full = dec(tgt, memory)[0]
+        caches = dec.init_decode(memory)
+        rows = [dec.decode_step(tgt[:, t:t + 1], caches) for t in range(tgt.shape[1])]
+    got = torch.cat(rows, 1)
+    assert got.shape == full.shape
+    assert_close(got.float(), full.float(), dt, floor="max", what="incremental decoder", rtol_mul=2.0 if not autocast else 1.0)
+    # the caches advanced: a second utterance needs fresh ones
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        again = dec.decode_step(tgt[:, :1], dec.init_decode(memory))
+    assert_close(again.float(), full[:, :1].float(), dt, floor="max", what="fresh caches", rtol_mul=2.0 if not autocast else 1.0)

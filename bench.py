@@ -157,7 +157,14 @@ def make_batch(model_cfg, batch, seconds, seed, device, n_classes):
 
 
 def ctc_loss_of(logp, targets):
+    """GPU arm: cm_ctc_loss (alpha, beta and the gradient in one launch); the CPU reference arm keeps torch's ctc_loss.
+    CM_BENCH_TORCH_CTC=1 is the A/B switch back to torch's three kernels on the GPU."""
     Bt, L, _ = logp.shape
+    if logp.is_cuda and os.environ.get("CM_BENCH_TORCH_CTC", "0") != "1":
+        from mamba_asr_b200.ctc import ctc_loss
+        in_len = torch.full((Bt,), L, dtype=torch.long, device=logp.device)
+        tg_len = torch.full((Bt,), targets.shape[1], dtype=torch.long, device=logp.device)
+        return ctc_loss(logp.transpose(0, 1), targets, in_len, tg_len, blank=0, reduction="mean", zero_infinity=True)
     in_len = torch.full((Bt,), L, dtype=torch.long)
     tg_len = torch.full((Bt,), targets.shape[1], dtype=torch.long)
     return F.ctc_loss(logp.float().transpose(0, 1), targets, in_len, tg_len, blank=0, reduction="mean",

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CM_ABI_VERSION 9
+#define CM_ABI_VERSION 10
 
 /* element type of activations (u, delta, z, B, C, x, out, and their gradients) */
 enum { CM_F32 = 0, CM_BF16 = 1, CM_F16 = 2 };
@@ -464,6 +464,31 @@ int cm_adamw_step(const cm_adamw_args* args, void* stream);
 
 /* library identification: returns CM_ABI_VERSION; writes the compiled-for arch (e.g. 100) to *sm_arch if non-NULL */
 int cm_version(int32_t* sm_arch);
+/* ------------------------------------------------------------------------------------------------------
+ * CTC loss and its gradient in one launch (the `ctc_loss` stand-in of the layer shell;
+ * reference call site train_CTC.py:297-302 -> speechbrain.nnet.losses.ctc_loss -> torch.nn.functional.ctc_loss).
+ * Per utterance b: nll[b] = -log p(targets_b | log_probs_b) (+inf if no alignment exists) and, if `grad` is given,
+ * grad[b, t, c] = d nll[b] / d log_probs[b, t, c] (0 for t >= input_lengths[b]); reduction and zero_infinity are the
+ * caller's.  One CTA per utterance runs the alpha and the beta recursion concurrently; up to 255 labels per utterance.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch, max_time, classes, max_target;
+  int32_t blank, ws_states;         /* ws_states = 2 * max_target + 1 */
+  const float* log_probs;           /* (batch, time, class) fp32, unit class stride */
+  int64_t lp_sb, lp_st;
+  const int64_t* targets;           /* (batch, max_target) int64, row stride tg_sb */
+  int64_t tg_sb;
+  const int64_t* input_lengths;     /* (batch) or NULL = max_time */
+  const int64_t* target_lengths;    /* (batch) or NULL = max_target */
+  float* nll;                       /* (batch) fp32 */
+  float* grad;                      /* (batch, time, class) fp32 or NULL */
+  int64_t g_sb, g_st;
+  float* workspace;                 /* cm_ctc_workspace_floats() floats: alpha and beta */
+} cm_ctc_args;
+
+int64_t cm_ctc_workspace_floats(int32_t batch, int32_t max_time, int32_t max_target);
+int cm_ctc_loss(const cm_ctc_args* args, void* stream);
+
 /* sizeof() of the argument structs, for binding self-checks: 0 cm_tensor3, 1 cm_scan_dir, 2 cm_scan_fwd_args,
  * 3 cm_scan_bwd_dir, 4 cm_scan_bwd_args, 5 cm_conv_dir, 6 cm_conv_args, 7 cm_fbank_args, 8 cm_reduce_job,
  * 9 cm_layernorm_args, 10 cm_dwconv_args, 11 cm_ssm_step_args, 12 cm_add_ln_args, 13 cm_ln_act_args, 14 cm_adamw_args */

@@ -17,7 +17,7 @@ CM_ERR_BAD_ARG, CM_ERR_UNSUPPORTED = -1, -2
 CM_FLAG_DELTA_SOFTPLUS = 1
 CM_FLAG_SILU = 1
 CM_SCAN_CKPT_STEPS = 8
-CM_ABI_VERSION = 9
+CM_ABI_VERSION = 10
 CM_LN_ACT_LEAKY_RELU, CM_LN_ACT_GELU = 0, 1
 
 EXPORTS = (
@@ -28,7 +28,7 @@ EXPORTS = (
     "cm_layernorm_bwd", "cm_scan_fwd_workspace_bytes", "cm_dwconv_num_part", "cm_dwconv_fwd", "cm_dwconv_bwd_weight", "cm_colsum_num_part", "cm_colsum",
     "cm_ssm_step", "cm_add_ln_fwd", "cm_add_ln_bwd", "cm_gelu_dropout_fwd", "cm_gelu_dropout_bwd", "cm_tsmm_num_part", "cm_tsmm",
     "cm_ln_act_num_part", "cm_ln_act_fwd", "cm_ln_act_bwd", "cm_optim_num_part", "cm_sumsq_partial", "cm_adamw_step",
-    "cm_fbank_wav_supported", "cm_fbank_wav_logmel",
+    "cm_fbank_wav_supported", "cm_fbank_wav_logmel", "cm_ctc_workspace_floats", "cm_ctc_loss",
 )
 CM_REDUCE_MAX_JOBS = 8
 
@@ -114,6 +114,18 @@ class FbankWavArgs(C.Structure):
     ]
 
 
+class CtcArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("max_time", C.c_int32), ("classes", C.c_int32), ("max_target", C.c_int32),
+        ("blank", C.c_int32), ("ws_states", C.c_int32),
+        ("log_probs", C.c_void_p), ("lp_sb", C.c_int64), ("lp_st", C.c_int64),
+        ("targets", C.c_void_p), ("tg_sb", C.c_int64),
+        ("input_lengths", C.c_void_p), ("target_lengths", C.c_void_p),
+        ("nll", C.c_void_p), ("grad", C.c_void_p), ("g_sb", C.c_int64), ("g_st", C.c_int64),
+        ("workspace", C.c_void_p),
+    ]
+
+
 class ReduceJob(C.Structure):
     _fields_ = [("part", C.c_void_p), ("out", C.c_void_p), ("rows", C.c_int64), ("cols", C.c_int64)]
 
@@ -179,7 +191,7 @@ class AdamWArgs(C.Structure):
 
 
 ABI_STRUCTS = (Tensor3, ScanDir, ScanFwdArgs, ScanBwdDir, ScanBwdArgs, ConvDir, ConvArgs, FbankArgs, ReduceJob,
-               LayerNormArgs, DwConvArgs, SsmStepArgs, AddLnArgs, LnActArgs, AdamWArgs, FbankWavArgs)
+               LayerNormArgs, DwConvArgs, SsmStepArgs, AddLnArgs, LnActArgs, AdamWArgs, FbankWavArgs, CtcArgs)
 
 def lib():
     """The loaded shared library; raises (never falls back) when it is absent or stale."""
@@ -212,6 +224,9 @@ def lib():
         L.cm_fbank_floor.argtypes = [C.POINTER(FbankArgs), C.c_void_p]
         L.cm_fbank_wav_supported.argtypes = [C.c_int32]
         L.cm_fbank_wav_logmel.argtypes = [C.POINTER(FbankWavArgs), C.c_void_p]
+        L.cm_ctc_workspace_floats.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+        L.cm_ctc_workspace_floats.restype = C.c_int64
+        L.cm_ctc_loss.argtypes = [C.POINTER(CtcArgs), C.c_void_p]
         L.cm_abi_sizeof.argtypes = [C.c_int32]
         L.cm_reduce_multi.argtypes = [C.POINTER(ReduceJob), C.c_int32, C.c_void_p]
         L.cm_scan_fwd_workspace_bytes.argtypes = [C.POINTER(ScanFwdArgs)]

@@ -539,6 +539,52 @@ def fbank_wav_logmel(wav, window, fbank, band, n_fft, hop, top_db=80.0, amin=1e-
     return out
 
 
+# ------------------------------------------------------------------------------------------------ CTC
+def ctc_supported(max_target):
+    """The kernel gives every extended-label state a thread in each of its two groups: up to 255 labels per utterance."""
+    return ((2 * int(max_target) + 1 + 31) // 32 * 32) * 2 <= 1024
+
+
+def ctc_nll_and_grad(log_probs, targets, input_lengths=None, target_lengths=None, blank=0, need_grad=True):
+    """cm_ctc_loss: per-utterance negative log-likelihood and its gradient in one launch.
+
+    log_probs: (B, T, C) fp32 CUDA, unit class stride; targets: (B, S) int64 (padded); lengths: (B,) int64 CUDA or None
+    (= full).  Returns (nll (B,) fp32, grad (B, T, C) fp32 or None) with grad[b] = d nll[b] / d log_probs[b]."""
+    lib = cabi.lib()
+    _require_cuda(log_probs, "log_probs")
+    if log_probs.dim() != 3 or log_probs.dtype != torch.float32:
+        raise TypeError("log_probs must be a (B, T, C) float32 tensor")
+    if log_probs.stride(2) != 1:
+        log_probs = log_probs.contiguous()
+    Bt, T, Cn = log_probs.shape
+    if targets.dim() != 2 or targets.shape[0] != Bt or targets.dtype != torch.int64:
+        raise TypeError("targets must be a (B, S) int64 tensor")
+    _same_device(log_probs, targets=targets, input_lengths=input_lengths, target_lengths=target_lengths)
+    if targets.stride(1) != 1:
+        targets = targets.contiguous()
+    S = targets.shape[1]
+    for name, t in (("input_lengths", input_lengths), ("target_lengths", target_lengths)):
+        if t is not None and (t.dtype != torch.int64 or t.shape != (Bt,) or not t.is_contiguous()):
+            raise TypeError("%s must be a contiguous (B,) int64 tensor" % name)
+    dev = log_probs.device
+    nll = torch.empty((Bt,), dtype=torch.float32, device=dev)
+    grad = torch.empty((Bt, T, Cn), dtype=torch.float32, device=dev) if need_grad else None
+    ws = torch.empty((max(1, lib.cm_ctc_workspace_floats(Bt, T, S)),), dtype=torch.float32, device=dev)
+    a = cabi.CtcArgs()
+    a.batch, a.max_time, a.classes, a.max_target = Bt, T, Cn, S
+    a.blank, a.ws_states = int(blank), 2 * S + 1
+    a.log_probs, a.lp_sb, a.lp_st = log_probs.data_ptr(), log_probs.stride(0), log_probs.stride(1)
+    a.targets, a.tg_sb = targets.data_ptr(), targets.stride(0)
+    a.input_lengths, a.target_lengths = cabi.ptr(input_lengths), cabi.ptr(target_lengths)
+    a.nll = nll.data_ptr()
+    a.grad = cabi.ptr(grad)
+    if grad is not None:
+        a.g_sb, a.g_st = grad.stride(0), grad.stride(1)
+    a.workspace = ws.data_ptr()
+    _call("cm_ctc_loss", lib.cm_ctc_loss, C.byref(a), cabi.stream_ptr(), tag=(Bt, T, Cn, S))
+    return nll, grad
+
+
 # ------------------------------------------------------------------------------------------------ LayerNorm
 def layernorm_forward(x2d, weight, bias, eps, out_dtype):
     """cm_layernorm_fwd over the rows of a (rows, C) CUDA tensor with unit column stride.

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CM_ABI_VERSION 10
+#define CM_ABI_VERSION 11
 
 /* element type of activations (u, delta, z, B, C, x, out, and their gradients) */
 enum { CM_F32 = 0, CM_BF16 = 1, CM_F16 = 2 };
@@ -489,9 +489,46 @@ typedef struct {
 int64_t cm_ctc_workspace_floats(int32_t batch, int32_t max_time, int32_t max_target);
 int cm_ctc_loss(const cm_ctc_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * First block of the CNN front-end in one kernel each way (the layer shell; reference
+ * speechbrain ConvolutionFrontEnd block 1 as configured by hparams/CTC/conmamba_large.yaml:187-199, reached from
+ * train_CTC.py:288):
+ *   y = LeakyReLU(LayerNorm_[F', C](Conv2d(1 -> C, 3 x 3, stride 2, zero padding 1)(in) + bias)),  T' = (frames-1)/2+1,
+ *   F' = (feats-1)/2+1.  in: dense (batch, frames, feats); y, dy: dense (batch, T', F', C); weight (C, 3, 3) fp32 (= torch's
+ *   (C, 1, 3, 3)); gamma / beta (F', C) fp32; mean / rstd (batch * T') fp32 written by forward, read by backward.
+ *   backward recomputes the conv output from `in` and writes cm_stem_num_part(batch, frames) partial rows of dgamma / dbeta
+ *   ([n_part][F' * C]), dweight ([n_part][C * 9]) and dbias ([n_part][C]) for cm_reduce_multi; no input gradient.
+ * Envelope (cm_stem_supported): C % 4 == 0, C <= 128, 512 % C == 0, feats <= 168, F' * C <= 2560; 16-byte aligned y, dy,
+ * gamma, beta, bias and partial buffers.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch, frames, feats, channels;
+  int32_t in_dtype, out_dtype;
+  float eps, slope;
+  const void* in;
+  const float* weight;
+  const float* bias;         /* (C) fp32 or NULL */
+  const float* gamma;
+  const float* beta;
+  void* y;                   /* forward output */
+  float* mean;
+  float* rstd;
+  const void* dy;            /* backward: grad of y (out_dtype) */
+  float* dgamma_part;
+  float* dbeta_part;
+  float* dweight_part;
+  float* dbias_part;
+} cm_stem_args;
+
+int cm_stem_supported(int32_t feats, int32_t channels);
+int cm_stem_num_part(int32_t batch, int32_t frames);
+int cm_stem_fwd(const cm_stem_args* args, void* stream);
+int cm_stem_bwd(const cm_stem_args* args, void* stream);
+
 /* sizeof() of the argument structs, for binding self-checks: 0 cm_tensor3, 1 cm_scan_dir, 2 cm_scan_fwd_args,
  * 3 cm_scan_bwd_dir, 4 cm_scan_bwd_args, 5 cm_conv_dir, 6 cm_conv_args, 7 cm_fbank_args, 8 cm_reduce_job,
- * 9 cm_layernorm_args, 10 cm_dwconv_args, 11 cm_ssm_step_args, 12 cm_add_ln_args, 13 cm_ln_act_args, 14 cm_adamw_args */
+ * 9 cm_layernorm_args, 10 cm_dwconv_args, 11 cm_ssm_step_args, 12 cm_add_ln_args, 13 cm_ln_act_args, 14 cm_adamw_args,
+ * 15 cm_fbank_wav_args, 16 cm_ctc_args, 17 cm_stem_args */
 int cm_abi_sizeof(int32_t which);
 
 #ifdef __cplusplus

@@ -17,7 +17,7 @@ CM_ERR_BAD_ARG, CM_ERR_UNSUPPORTED = -1, -2
 CM_FLAG_DELTA_SOFTPLUS = 1
 CM_FLAG_SILU = 1
 CM_SCAN_CKPT_STEPS = 8
-CM_ABI_VERSION = 10
+CM_ABI_VERSION = 11
 CM_LN_ACT_LEAKY_RELU, CM_LN_ACT_GELU = 0, 1
 
 EXPORTS = (
@@ -29,6 +29,7 @@ EXPORTS = (
     "cm_ssm_step", "cm_add_ln_fwd", "cm_add_ln_bwd", "cm_gelu_dropout_fwd", "cm_gelu_dropout_bwd", "cm_tsmm_num_part", "cm_tsmm",
     "cm_ln_act_num_part", "cm_ln_act_fwd", "cm_ln_act_bwd", "cm_optim_num_part", "cm_sumsq_partial", "cm_adamw_step",
     "cm_fbank_wav_supported", "cm_fbank_wav_logmel", "cm_ctc_workspace_floats", "cm_ctc_loss",
+    "cm_stem_supported", "cm_stem_num_part", "cm_stem_fwd", "cm_stem_bwd",
 )
 CM_REDUCE_MAX_JOBS = 8
 
@@ -126,6 +127,16 @@ class CtcArgs(C.Structure):
     ]
 
 
+class StemArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("frames", C.c_int32), ("feats", C.c_int32), ("channels", C.c_int32),
+        ("in_dtype", C.c_int32), ("out_dtype", C.c_int32), ("eps", C.c_float), ("slope", C.c_float),
+        ("inp", C.c_void_p), ("weight", C.c_void_p), ("bias", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("y", C.c_void_p), ("mean", C.c_void_p), ("rstd", C.c_void_p), ("dy", C.c_void_p),
+        ("dgamma_part", C.c_void_p), ("dbeta_part", C.c_void_p), ("dweight_part", C.c_void_p), ("dbias_part", C.c_void_p),
+    ]
+
+
 class ReduceJob(C.Structure):
     _fields_ = [("part", C.c_void_p), ("out", C.c_void_p), ("rows", C.c_int64), ("cols", C.c_int64)]
 
@@ -191,7 +202,8 @@ class AdamWArgs(C.Structure):
 
 
 ABI_STRUCTS = (Tensor3, ScanDir, ScanFwdArgs, ScanBwdDir, ScanBwdArgs, ConvDir, ConvArgs, FbankArgs, ReduceJob,
-               LayerNormArgs, DwConvArgs, SsmStepArgs, AddLnArgs, LnActArgs, AdamWArgs, FbankWavArgs, CtcArgs)
+               LayerNormArgs, DwConvArgs, SsmStepArgs, AddLnArgs, LnActArgs, AdamWArgs, FbankWavArgs, CtcArgs,
+               StemArgs)
 
 def lib():
     """The loaded shared library; raises (never falls back) when it is absent or stale."""
@@ -227,6 +239,10 @@ def lib():
         L.cm_ctc_workspace_floats.argtypes = [C.c_int32, C.c_int32, C.c_int32]
         L.cm_ctc_workspace_floats.restype = C.c_int64
         L.cm_ctc_loss.argtypes = [C.POINTER(CtcArgs), C.c_void_p]
+        L.cm_stem_supported.argtypes = [C.c_int32, C.c_int32]
+        L.cm_stem_num_part.argtypes = [C.c_int32, C.c_int32]
+        L.cm_stem_fwd.argtypes = [C.POINTER(StemArgs), C.c_void_p]
+        L.cm_stem_bwd.argtypes = [C.POINTER(StemArgs), C.c_void_p]
         L.cm_abi_sizeof.argtypes = [C.c_int32]
         L.cm_reduce_multi.argtypes = [C.POINTER(ReduceJob), C.c_int32, C.c_void_p]
         L.cm_scan_fwd_workspace_bytes.argtypes = [C.POINTER(ScanFwdArgs)]

@@ -156,6 +156,7 @@ extern "C" int cm_abi_sizeof(int32_t which) {
     case 14: return (int)sizeof(cm_adamw_args);
     case 15: return (int)sizeof(cm_fbank_wav_args);
     case 16: return (int)sizeof(cm_ctc_args);
+    case 17: return (int)sizeof(cm_stem_args);
     default: return CM_ERR_BAD_ARG;
   }
 }

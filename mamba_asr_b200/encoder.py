@@ -20,7 +20,7 @@ import torch.nn.functional as F
 import math
 import os
 
-from .layernorm import DropoutSeed, layer_norm_leaky_relu
+from .layernorm import DropoutSeed, conv_ln_act_stem, conv_ln_act_stem_supported, layer_norm_leaky_relu
 from .linear import BiasGradLinear, ParamCache, set_param_cache
 from .bimamba import precomputed_A
 from .conmamba import ConmambaEncoder, MambaDecoder
@@ -90,7 +90,13 @@ class ConvFrontEnd(nn.Module):
         # the ambiguity to NCHW, which makes cuDNN convert the 64-channel output back and forth
         x = feats.as_strided((Bt, 1, T, Fd), (T * Fd, 1, Fd, 1))
         fused = self.use_kernel and os.environ.get("CM_NO_FUSE_FRONTEND_LN") is None
-        for conv, norm in zip(self.convs, self.norms):
+        stem = (fused and os.environ.get("CM_NO_FUSE_STEM") is None
+                and conv_ln_act_stem_supported(feats, self.convs[0], self.norms[0]))
+        for i, (conv, norm) in enumerate(zip(self.convs, self.norms)):
+            if i == 0 and stem:
+                # block 1 (one input channel) as ONE kernel: the conv output is never written (cm_stem_fwd / cm_stem_bwd)
+                x = conv_ln_act_stem(feats, conv, norm).permute(0, 3, 1, 2)
+                continue
             # fused: the conv bias is added inside the norm kernel (as a separate torch add it is one more pass over the
             # largest activation of the step)
             x = F.conv2d(x, conv.weight.contiguous(memory_format=torch.channels_last), None if fused else conv.bias,

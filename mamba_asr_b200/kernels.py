@@ -711,6 +711,77 @@ def ln_act_backward(x2d, dy2d, weight, bias, mean, rstd, slope=0.01, act="leaky_
     return dx, dg, db
 
 
+# ------------------------------------------------------------------------------------------------ front-end block 1
+def stem_supported(feats, conv_weight):
+    """True when cm_stem_* implements Conv2d(1 -> C, 3 x 3, stride 2, padding 1) + LayerNorm([F', C]) + LeakyReLU for this input."""
+    if not (feats.is_cuda and feats.dim() == 3 and feats.dtype in cabi._DTYPES):
+        return False
+    if conv_weight.dim() != 4 or tuple(conv_weight.shape[1:]) != (1, 3, 3):
+        return False
+    return bool(cabi.lib().cm_stem_supported(feats.shape[2], conv_weight.shape[0]))
+
+
+def _stem_args(feats, weight, bias, gamma, beta, eps, slope, out_dtype, mean, rstd):
+    _require_cuda(feats, "feats")
+    _same_device(feats, weight=weight, bias=bias, gamma=gamma, beta=beta)
+    a = cabi.StemArgs()
+    a.batch, a.frames, a.feats = feats.shape
+    a.channels = weight.shape[0]
+    a.in_dtype, a.out_dtype = cabi.dtype_code(feats.dtype), cabi.dtype_code(out_dtype)
+    a.eps, a.slope = float(eps), float(slope)
+    a.inp = feats.data_ptr()
+    a.weight = _f32c(weight, "weight").data_ptr()
+    a.bias = cabi.ptr(None if bias is None else _f32c(bias, "bias"))
+    a.gamma, a.beta = _f32c(gamma, "gamma").data_ptr(), _f32c(beta, "beta").data_ptr()
+    a.mean, a.rstd = mean.data_ptr(), rstd.data_ptr()
+    return a
+
+
+def stem_forward(feats, weight, bias, gamma, beta, eps, slope, out_dtype):
+    """cm_stem_fwd: feats (B, T, F) dense -> y (B, T', F', C) in out_dtype, mean / rstd (B * T') fp32.
+    weight (C, 1, 3, 3) / bias (C) / gamma, beta (F', C): fp32 contiguous."""
+    lib = cabi.lib()
+    if not feats.is_contiguous():
+        feats = feats.contiguous()
+    Bt, T, Fd = feats.shape
+    Cn = weight.shape[0]
+    To, Fo = (T - 1) // 2 + 1, (Fd - 1) // 2 + 1
+    y = torch.empty((Bt, To, Fo, Cn), dtype=out_dtype, device=feats.device)
+    mean = torch.empty((Bt * To,), dtype=torch.float32, device=feats.device)
+    rstd = torch.empty((Bt * To,), dtype=torch.float32, device=feats.device)
+    a = _stem_args(feats, weight, bias, gamma, beta, eps, slope, out_dtype, mean, rstd)
+    a.y = y.data_ptr()
+    _call("cm_stem_fwd", lib.cm_stem_fwd, C.byref(a), cabi.stream_ptr(), tag=(Bt, T, Fd, Cn))
+    return y, mean, rstd
+
+
+def stem_backward(feats, dy, weight, bias, gamma, beta, mean, rstd, slope):
+    """cm_stem_bwd + one deterministic reduction launch.  Returns (dweight (C, 1, 3, 3), dbias (C), dgamma, dbeta (F', C)) fp32."""
+    lib = cabi.lib()
+    Bt, T, Fd = feats.shape
+    Cn = weight.shape[0]
+    Fo = (Fd - 1) // 2 + 1
+    if not dy.is_contiguous():
+        dy = dy.contiguous()
+    dev = feats.device
+    n_part = lib.cm_stem_num_part(Bt, T)
+    dg_part = torch.empty((n_part, Fo * Cn), dtype=torch.float32, device=dev)
+    db_part = torch.empty((n_part, Fo * Cn), dtype=torch.float32, device=dev)
+    dw_part = torch.empty((n_part, Cn * 9), dtype=torch.float32, device=dev)
+    dcb_part = torch.empty((n_part, Cn), dtype=torch.float32, device=dev)
+    a = _stem_args(feats, weight, bias, gamma, beta, 0.0, slope, dy.dtype, mean, rstd)
+    a.dy = dy.data_ptr()
+    a.dgamma_part, a.dbeta_part = dg_part.data_ptr(), db_part.data_ptr()
+    a.dweight_part, a.dbias_part = dw_part.data_ptr(), dcb_part.data_ptr()
+    _call("cm_stem_bwd", lib.cm_stem_bwd, C.byref(a), cabi.stream_ptr(), tag=(Bt, T, Fd, Cn))
+    dg = torch.empty((Fo, Cn), dtype=torch.float32, device=dev)
+    db = torch.empty((Fo, Cn), dtype=torch.float32, device=dev)
+    dw = torch.empty((Cn, 1, 3, 3), dtype=torch.float32, device=dev)
+    dcb = torch.empty((Cn,), dtype=torch.float32, device=dev)
+    reduce_many([(dg_part, dg), (db_part, db), (dw_part, dw), (dcb_part, dcb)])
+    return dw, dcb, dg, db
+
+
 # ------------------------------------------------------------------------------------------------ add + dropout + LayerNorm
 ADD_LN_COMBOS = {(torch.float32, torch.bfloat16, torch.bfloat16), (torch.float32, torch.bfloat16, torch.float32),
                  (torch.float32, torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16, torch.bfloat16),

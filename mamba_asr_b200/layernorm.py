@@ -137,6 +137,55 @@ def layer_norm_leaky_relu(x, norm, negative_slope=0.01, pre_bias=None):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# first block of the CNN front-end: Conv2d(1 -> C, 3 x 3, stride 2, padding 1) + LayerNorm([F', C]) + LeakyReLU as one kernel
+# each way (cm_stem_fwd / cm_stem_bwd; reference hparams/CTC/conmamba_large.yaml:187-199).  Only the features, mean and rstd
+# are saved: the conv output is recomputed in backward and never written.
+class _StemFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, weight, bias, gamma, beta, eps, slope, out_dtype):
+        y, mean, rstd = K.stem_forward(feats, weight, bias, gamma, beta, eps, slope, out_dtype)
+        ctx.save_for_backward(feats, weight, bias, gamma, beta, mean, rstd)
+        ctx.slope = slope
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        feats, weight, bias, gamma, beta, mean, rstd = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("conv_ln_act_stem: no gradient with respect to the features (they are the network input)")
+        dw, dcb, dg, db = K.stem_backward(feats, dy, weight, bias, gamma, beta, mean, rstd, ctx.slope)
+        return (None, dw if ctx.needs_input_grad[1] else None, dcb if bias is not None and ctx.needs_input_grad[2] else None,
+                dg if ctx.needs_input_grad[3] else None, db if ctx.needs_input_grad[4] else None, None, None, None)
+
+
+def conv_ln_act_stem_supported(feats, conv, norm):
+    """True when ``conv_ln_act_stem`` can run this block: CUDA features (B, T, F) without gradient, a 1-input-channel 3 x 3
+    stride-2 padding-1 zero-padded conv, an affine LayerNorm over (F', C) inside the kernel envelope."""
+    if not isinstance(conv, torch.nn.Conv2d) or conv.in_channels != 1 or conv.kernel_size != (3, 3) or conv.stride != (2, 2):
+        return False
+    if conv.padding != (1, 1) or conv.dilation != (1, 1) or conv.groups != 1 or conv.padding_mode != "zeros":
+        return False
+    if norm.weight is None or norm.bias is None or feats.dim() != 3 or feats.requires_grad:
+        return False
+    if tuple(norm.normalized_shape) != ((feats.shape[2] - 1) // 2 + 1, conv.out_channels):
+        return False
+    return K.stem_supported(feats, conv.weight)
+
+
+def conv_ln_act_stem(feats, conv, norm, negative_slope=0.01):
+    """``leaky_relu(norm(conv(feats[:, None]).permute(0, 2, 3, 1)))`` -> (B, T', F', C) in the autocast dtype (fp32 outside
+    autocast), computed in fp32 from the features as given.  No CPU path."""
+    if not feats.is_cuda:
+        raise RuntimeError("mamba_asr_b200.conv_ln_act_stem runs on the sm_100a kernel only (no CPU fallback)")
+    if not conv_ln_act_stem_supported(feats, conv, norm):
+        raise NotImplementedError("conv_ln_act_stem: block outside the kernel envelope")
+    out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else feats.dtype
+    with torch.autocast("cuda", enabled=False):
+        return _StemFn.apply(feats.contiguous(), conv.weight.float(), None if conv.bias is None else conv.bias.float(),
+                             norm.weight.float(), norm.bias.float(), norm.eps, float(negative_slope), out_dtype)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # residual add + dropout + LayerNorm in one pass (cm_add_ln_fwd / cm_add_ln_bwd)
 class DropoutSeed:
     """Device-resident seed of the fused dropout masks.  Every call site gets its own ``call_id`` (a host counter); the

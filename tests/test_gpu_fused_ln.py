@@ -284,14 +284,16 @@ def test_conv_front_end_same_with_and_without_the_fused_norm(autocast, monkeypat
         res.append((out.float().detach(), [p.grad.clone() for p in fe.parameters()]))
     dt = torch.bfloat16 if autocast else torch.float32
     assert res[0][0].shape == (3, 51, fe.out_features)
-    assert_close(res[0][0], res[1][0], dt, what="front-end output")
+    # autocast: block 1 keeps its conv output in fp32 registers (cm_stem_fwd) where cuDNN rounds it to bf16 before the norm
+    assert_close(res[0][0], res[1][0], dt, what="front-end output", rtol_mul=2.0 if autocast else 1.0)
     for (name, _), ga, gb in zip(fe.named_parameters(), res[0][1], res[1][1]):
         if autocast:
             # the fused path adds the conv bias in fp32, cuDNN rounds x + bias to bf16 first: pre-activations within
             # ~1e-2 of zero take the other LeakyReLU branch (a 0.99 * dy step in single terms of the sums), so the
             # bf16 gradients are compared in norm rather than element by element
+            # (block 1 on cm_stem_* also keeps the conv output itself in fp32: a few more flips, 0.051 measured)
             rel = float((ga - gb).norm() / gb.norm())
-            assert rel < 0.05, (name, rel)
+            assert rel < 0.08, (name, rel)
         else:
             assert_close(ga, gb, dt, floor="max", what="d " + name, rtol_mul=4.0)
 
@@ -323,3 +325,91 @@ def test_convolution_module_same_with_and_without_the_fused_norm_gelu(autocast, 
     assert_close(res[0][1], res[1][1], dt, floor="max", what="conv module dx", rtol_mul=2.0)
     for (name, _), ga, gb in zip(m.named_parameters(), res[0][2], res[1][2]):
         assert_close(ga, gb, dt, floor="max", what="d " + name, rtol_mul=4.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# front-end block 1 as one kernel each way (cm_stem_fwd / cm_stem_bwd): Conv2d(1 -> C, 3 x 3, stride 2, padding 1) +
+# LayerNorm([F', C]) + LeakyReLU against the three torch ops in fp32 (reference hparams/CTC/conmamba_large.yaml:187-199)
+def _stem_reference(feats, conv, norm, slope=0.01):
+    x = F.conv2d(feats.float()[:, None], conv.weight, conv.bias, conv.stride, conv.padding)     # (B, C, T', F')
+    return F.leaky_relu(norm(x.permute(0, 2, 3, 1)), slope)
+
+
+@pytest.mark.parametrize("shape", [(3, 203, 80, 64), (2, 50, 80, 64), (1, 1, 80, 64), (2, 37, 81, 32), (4, 64, 40, 128),
+                                   (2, 19, 7, 16), (5, 2, 80, 64), (1, 700, 80, 64), (2, 33, 160, 32)])
+@pytest.mark.parametrize("in_dtype", [torch.float32, torch.bfloat16])
+def test_stem_matches_conv_layernorm_leaky_relu(shape, in_dtype, monkeypatch):
+    from mamba_asr_b200.layernorm import conv_ln_act_stem, conv_ln_act_stem_supported
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    Bt, T, Fd, Cn = shape
+    torch.manual_seed(Bt * 7 + T + Cn)
+    conv = torch.nn.Conv2d(1, Cn, 3, stride=2, padding=1).cuda()
+    norm = torch.nn.LayerNorm([(Fd - 1) // 2 + 1, Cn]).cuda()
+    with torch.no_grad():
+        norm.weight.add_(0.2 * torch.randn_like(norm.weight))
+        norm.bias.add_(0.2 * torch.randn_like(norm.bias))
+    feats = torch.randn(Bt, T, Fd, device="cuda").to(in_dtype)
+    assert conv_ln_act_stem_supported(feats, conv, norm)
+    y = conv_ln_act_stem(feats, conv, norm)
+    cy = torch.randn(y.shape, device="cuda")
+    (y.float() * cy).sum().backward()
+    got = [y.float().detach()] + [p.grad.clone() for p in list(conv.parameters()) + list(norm.parameters())]
+    conv.zero_grad(); norm.zero_grad()
+    ref = _stem_reference(feats, conv, norm)
+    (ref * cy.to(ref.dtype)).sum().backward()
+    want = [ref.detach()] + [p.grad.clone() for p in list(conv.parameters()) + list(norm.parameters())]
+    assert y.dtype == in_dtype and y.shape == ref.shape
+    assert_close(got[0], want[0], in_dtype, what="stem output")
+    # bf16 case: y is bf16, so autograd hands the kernel dy = cy rounded to bf16 (the fp32 reference sees cy itself)
+    for name, a, b in zip(("dweight", "dbias", "dgamma", "dbeta"), got[1:], want[1:]):
+        if in_dtype == torch.float32:
+            assert_close(a, b, torch.float32, floor="max", what=name, rtol_mul=4.0)
+        else:
+            assert_close(a, b, torch.bfloat16, floor="max", what=name)
+
+
+def test_stem_under_autocast_writes_bf16_and_is_deterministic():
+    from mamba_asr_b200.layernorm import conv_ln_act_stem
+    torch.manual_seed(1)
+    conv = torch.nn.Conv2d(1, 64, 3, stride=2, padding=1).cuda()
+    norm = torch.nn.LayerNorm([40, 64]).cuda()
+    feats = torch.randn(4, 301, 80, device="cuda")
+    outs = []
+    for _ in range(2):
+        conv.zero_grad(); norm.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = conv_ln_act_stem(feats, conv, norm)
+        y.float().square().sum().backward()
+        outs.append([y.detach().clone()] + [p.grad.clone() for p in list(conv.parameters()) + list(norm.parameters())])
+    assert outs[0][0].dtype == torch.bfloat16 and outs[0][0].shape == (4, 151, 40, 64)
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    ref = _stem_reference(feats, conv, norm)
+    assert_close(outs[0][0].float(), ref, torch.bfloat16, what="stem output (autocast)")
+
+
+def test_stem_envelope_and_ab_switch(monkeypatch):
+    from mamba_asr_b200.encoder import ConvFrontEnd
+    from mamba_asr_b200.layernorm import conv_ln_act_stem, conv_ln_act_stem_supported
+    from mamba_asr_b200 import kernels as K
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    feats = torch.randn(2, 21, 80, device="cuda")
+    norm = torch.nn.LayerNorm([40, 64]).cuda()
+    assert not conv_ln_act_stem_supported(feats, torch.nn.Conv2d(1, 64, 3, stride=1, padding=1).cuda(), norm)
+    assert not conv_ln_act_stem_supported(feats, torch.nn.Conv2d(1, 64, 3, stride=2, padding=1, padding_mode="reflect").cuda(), norm)
+    assert not conv_ln_act_stem_supported(feats, torch.nn.Conv2d(1, 48, 3, stride=2, padding=1).cuda(),
+                                          torch.nn.LayerNorm([40, 48]).cuda())            # 512 % 48 != 0
+    assert not conv_ln_act_stem_supported(feats.requires_grad_(True), torch.nn.Conv2d(1, 64, 3, stride=2, padding=1).cuda(), norm)
+    with pytest.raises(RuntimeError):
+        conv_ln_act_stem(torch.randn(2, 21, 80), torch.nn.Conv2d(1, 64, 3, stride=2, padding=1), torch.nn.LayerNorm([40, 64]))
+    # the front-end takes the kernel by itself; CM_NO_FUSE_STEM=1 is the A/B switch back to cuDNN + cm_ln_act
+    fe = ConvFrontEnd(80).cuda()
+    x = torch.randn(2, 101, 80, device="cuda")
+    n0 = K.LAUNCHES
+    a = fe(x)
+    used = K.LAUNCHES - n0
+    monkeypatch.setenv("CM_NO_FUSE_STEM", "1")
+    n0 = K.LAUNCHES
+    b = fe(x)
+    assert K.LAUNCHES - n0 == used            # one cm_stem_fwd instead of one cm_ln_act_fwd
+    assert_close(a, b, torch.float32, what="front-end with / without the stem kernel", rtol_mul=10.0)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CM_ABI_VERSION 11
+#define CM_ABI_VERSION 12
 
 /* element type of activations (u, delta, z, B, C, x, out, and their gradients) */
 enum { CM_F32 = 0, CM_BF16 = 1, CM_F16 = 2 };
@@ -302,10 +302,11 @@ int cm_layernorm_bwd(const cm_layernorm_args* args, void* stream);
  * every sub-block of a ConMamba layer ends in  s = a + alpha * dropout(b)  and the next starts with  y = LayerNorm(s)).
  *   forward : s = a + alpha * keep/(1-p) * b ; y = (s - mean) * rstd * gamma + beta ; writes s, y, mean, rstd, mask
  *   backward: t = LayerNorm'(dy; s) + ds ; da = t ; db = alpha * keep/(1-p) * t ; dgamma / dbeta partial rows
- *             (cm_layernorm_num_part(rows) rows each, summed by cm_reduce_multi)
+ *             (cm_add_ln_num_part(rows, cols) rows each, summed by cm_reduce_multi)
  * a, s, ds, da share a_dtype; b, db share b_dtype; y, dy share y_dtype.  Supported (a, b, y): (f32, bf16, bf16),
  * (f32, bf16, f32), (f32, f32, f32), (bf16, bf16, bf16), (bf16, bf16, f32); cols even and <= 1024, even strides.
- * The keep mask is a counter-based hash of (*seed, call_id, element index), stored as one byte per element.
+ * The keep mask is a counter-based hash of (*seed, call_id, row, column); p_drop > 0 with b non-NULL applies dropout.  The
+ * mask is either stored as one byte per element (mask non-NULL) or regenerated by backward from the key forward wrote.
  * ---------------------------------------------------------------------------------------------------- */
 typedef struct {
   int64_t rows;
@@ -330,7 +331,17 @@ typedef struct {
   void* db;       int64_t db_stride;  /* NULL when b was NULL */
   float* dgamma_part;
   float* dbeta_part;
+  uint32_t* key;                      /* v12: forward writes the 32-bit mask key here (if non-NULL); with mask NULL and
+                                         p_drop > 0 backward regenerates the keep bits from it instead of reading a mask */
+  float* dbsum_part;                  /* v12, backward, optional: cm_add_ln_num_part(rows, cols) partial rows of the column sums
+                                         of db (the bias gradient of the Linear that produced b); cols % 4 == 0 layouts only */
 } cm_add_ln_args;
+
+/* 1 when cm_add_ln_bwd can also produce dbsum_part for this geometry (the quad-vectorised kernels: cols % 4 == 0, row strides
+ * % 4 == 0, 16-byte aligned fp32 / 8-byte aligned 16-bit rows) */
+int cm_add_ln_dbsum_supported(int32_t cols, int64_t min_stride);
+/* v12: partial rows of cm_add_ln_bwd's dgamma_part / dbeta_part / dbsum_part (was cm_layernorm_num_part) */
+int cm_add_ln_num_part(int64_t rows, int32_t cols);
 
 int cm_add_ln_fwd(const cm_add_ln_args* args, void* stream);
 int cm_add_ln_bwd(const cm_add_ln_args* args, void* stream);
@@ -346,6 +357,31 @@ int cm_gelu_dropout_fwd(const void* x, void* y, uint8_t* mask, int64_t n, int32_
                         const int64_t* seed, uint32_t call_id, void* stream);
 int cm_gelu_dropout_bwd(const void* x, const void* dy, const uint8_t* mask, void* dx, int64_t n, int32_t dtype,
                         float p_drop, void* stream);
+
+/* Struct form (ABI v12).  The dropout mask need not be stored: forward writes its 32-bit mask key to *key and backward
+ * regenerates the keep bits from it (mask NULL); with cols > 0 (cols % 8 == 0, 256 % (cols / 8) == 0, n % cols == 0:
+ * cm_act_colsum_supported) backward also writes cm_act_num_part(n) partial rows of the column sums of dx over the
+ * (n / cols, cols) matrix - the bias gradient of the Linear that produced x - for cm_reduce_multi. */
+typedef struct {
+  const void* x;
+  void* y;                  /* forward output */
+  const void* dy;           /* backward */
+  void* dx;
+  uint8_t* mask;            /* optional byte mask (forward writes, backward reads); NULL: regenerate from *key */
+  const int64_t* seed;      /* forward: device seed (NULL: a fixed default) */
+  uint32_t* key;            /* forward writes the mask key; backward reads it when mask is NULL */
+  uint32_t call_id;
+  int32_t dtype;
+  float p_drop;
+  int32_t cols;             /* backward: > 0 = also column sums of dx */
+  int64_t n;
+  float* colsum_part;       /* [cm_act_num_part(n)][cols] fp32 */
+} cm_act_args;
+
+int cm_act_colsum_supported(int64_t n, int32_t cols);
+int cm_act_num_part(int64_t n);
+int cm_gelu_dropout_fwd_v2(const cm_act_args* args, void* stream);
+int cm_gelu_dropout_bwd_v2(const cm_act_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Tall-skinny weight-gradient GEMM  C[M, N] = sum_r A[r, m] * B[r, n]  (A^T B): the gradients of the Mamba block's skinny
@@ -528,7 +564,7 @@ int cm_stem_bwd(const cm_stem_args* args, void* stream);
 /* sizeof() of the argument structs, for binding self-checks: 0 cm_tensor3, 1 cm_scan_dir, 2 cm_scan_fwd_args,
  * 3 cm_scan_bwd_dir, 4 cm_scan_bwd_args, 5 cm_conv_dir, 6 cm_conv_args, 7 cm_fbank_args, 8 cm_reduce_job,
  * 9 cm_layernorm_args, 10 cm_dwconv_args, 11 cm_ssm_step_args, 12 cm_add_ln_args, 13 cm_ln_act_args, 14 cm_adamw_args,
- * 15 cm_fbank_wav_args, 16 cm_ctc_args, 17 cm_stem_args */
+ * 15 cm_fbank_wav_args, 16 cm_ctc_args, 17 cm_stem_args, 18 cm_act_args */
 int cm_abi_sizeof(int32_t which);
 
 #ifdef __cplusplus

@@ -17,7 +17,7 @@ CM_ERR_BAD_ARG, CM_ERR_UNSUPPORTED = -1, -2
 CM_FLAG_DELTA_SOFTPLUS = 1
 CM_FLAG_SILU = 1
 CM_SCAN_CKPT_STEPS = 8
-CM_ABI_VERSION = 11
+CM_ABI_VERSION = 12
 CM_LN_ACT_LEAKY_RELU, CM_LN_ACT_GELU = 0, 1
 
 EXPORTS = (
@@ -30,6 +30,7 @@ EXPORTS = (
     "cm_ln_act_num_part", "cm_ln_act_fwd", "cm_ln_act_bwd", "cm_optim_num_part", "cm_sumsq_partial", "cm_adamw_step",
     "cm_fbank_wav_supported", "cm_fbank_wav_logmel", "cm_ctc_workspace_floats", "cm_ctc_loss",
     "cm_stem_supported", "cm_stem_num_part", "cm_stem_fwd", "cm_stem_bwd",
+    "cm_add_ln_dbsum_supported", "cm_add_ln_num_part", "cm_act_colsum_supported", "cm_act_num_part", "cm_gelu_dropout_fwd_v2", "cm_gelu_dropout_bwd_v2",
 )
 CM_REDUCE_MAX_JOBS = 8
 
@@ -137,6 +138,14 @@ class StemArgs(C.Structure):
     ]
 
 
+class ActArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("y", C.c_void_p), ("dy", C.c_void_p), ("dx", C.c_void_p), ("mask", C.c_void_p),
+        ("seed", C.c_void_p), ("key", C.c_void_p), ("call_id", C.c_uint32), ("dtype", C.c_int32), ("p_drop", C.c_float),
+        ("cols", C.c_int32), ("n", C.c_int64), ("colsum_part", C.c_void_p),
+    ]
+
+
 class ReduceJob(C.Structure):
     _fields_ = [("part", C.c_void_p), ("out", C.c_void_p), ("rows", C.c_int64), ("cols", C.c_int64)]
 
@@ -183,7 +192,7 @@ class AddLnArgs(C.Structure):
                 ("rstd", C.c_void_p),
                 ("dy", C.c_void_p), ("dy_stride", C.c_int64), ("ds", C.c_void_p), ("ds_stride", C.c_int64),
                 ("da", C.c_void_p), ("da_stride", C.c_int64), ("db", C.c_void_p), ("db_stride", C.c_int64),
-                ("dgamma_part", C.c_void_p), ("dbeta_part", C.c_void_p)]
+                ("dgamma_part", C.c_void_p), ("dbeta_part", C.c_void_p), ("key", C.c_void_p), ("dbsum_part", C.c_void_p)]
 
 
 class LnActArgs(C.Structure):
@@ -203,7 +212,7 @@ class AdamWArgs(C.Structure):
 
 ABI_STRUCTS = (Tensor3, ScanDir, ScanFwdArgs, ScanBwdDir, ScanBwdArgs, ConvDir, ConvArgs, FbankArgs, ReduceJob,
                LayerNormArgs, DwConvArgs, SsmStepArgs, AddLnArgs, LnActArgs, AdamWArgs, FbankWavArgs, CtcArgs,
-               StemArgs)
+               StemArgs, ActArgs)
 
 def lib():
     """The loaded shared library; raises (never falls back) when it is absent or stale."""
@@ -243,6 +252,12 @@ def lib():
         L.cm_stem_num_part.argtypes = [C.c_int32, C.c_int32]
         L.cm_stem_fwd.argtypes = [C.POINTER(StemArgs), C.c_void_p]
         L.cm_stem_bwd.argtypes = [C.POINTER(StemArgs), C.c_void_p]
+        L.cm_add_ln_dbsum_supported.argtypes = [C.c_int32, C.c_int64]
+        L.cm_add_ln_num_part.argtypes = [C.c_int64, C.c_int32]
+        L.cm_act_colsum_supported.argtypes = [C.c_int64, C.c_int32]
+        L.cm_act_num_part.argtypes = [C.c_int64]
+        L.cm_gelu_dropout_fwd_v2.argtypes = [C.POINTER(ActArgs), C.c_void_p]
+        L.cm_gelu_dropout_bwd_v2.argtypes = [C.POINTER(ActArgs), C.c_void_p]
         L.cm_abi_sizeof.argtypes = [C.c_int32]
         L.cm_reduce_multi.argtypes = [C.POINTER(ReduceJob), C.c_int32, C.c_void_p]
         L.cm_scan_fwd_workspace_bytes.argtypes = [C.POINTER(ScanFwdArgs)]

@@ -23,8 +23,8 @@ import torch.nn.functional as F
 from .bimamba import Mamba as BiMamba
 from .bimamba import UniMamba as Mamba
 from .dwconv import depthwise_conv1d
-from .kernels import DWCONV_KSIZES
-from .layernorm import FusedLayerNorm, add_dropout_layer_norm, gelu_dropout, layer_norm_act
+from .kernels import DWCONV_KSIZES, gelu_dropout_supported
+from .layernorm import FusedLayerNorm, _BiasGradRoute, add_dropout_layer_norm, gelu_dropout, layer_norm_act
 from .linear import BiasGradLinear, linear as _linear
 
 LAYER_NORM_EPS = 1e-6        # reference ConMambaConstants.LAYER_NORM_EPS (Conmamba.py:687)
@@ -61,12 +61,24 @@ class PositionalwiseFeedForward(nn.Module):
         self.ffn = nn.Sequential(BiasGradLinear(input_size, d_ffn), activation(), nn.Dropout(dropout),
                                  BiasGradLinear(d_ffn, input_size))
 
-    def forward(self, x):
+    def forward(self, x, out_bias_grad=True):
+        """``out_bias_grad=False``: the caller takes the gradient of the last Linear's bias from the consumer of the output
+        (``add_dropout_layer_norm(..., b_bias=self.ffn[3].bias)``)."""
         act, drop = self.ffn[1], self.ffn[2]
+        lin2 = self.ffn[3]
+        last = lin2 if out_bias_grad else (lambda h: _linear(h, lin2.weight, lin2.bias, bias_grad=False))
         if x.is_cuda and type(act) is nn.GELU and act.approximate == "none" and os.environ.get("CM_NO_FUSE_GELU") is None:
-            # Linear -> [GELU + Dropout: one sm_100a kernel] -> Linear
-            return self.ffn[3](gelu_dropout(self.ffn[0](x), drop.p, self.training))
-        return self.ffn(x)
+            # Linear -> [GELU + Dropout: one sm_100a kernel] -> Linear; the first Linear's bias gradient is the column sum of
+            # the activation's input gradient and is formed inside that backward kernel
+            lin1 = self.ffn[0]
+            if (type(lin1) is BiasGradLinear and lin1.bias is not None and torch.is_grad_enabled() and lin1.bias.requires_grad
+                    and os.environ.get("CM_NO_FUSE_BIAS_GRAD") is None):
+                h = _linear(x, lin1.weight, lin1.bias, bias_grad=False)
+                if gelu_dropout_supported(h):
+                    return last(gelu_dropout(h, drop.p, self.training, bias_for_grad=lin1.bias))
+                return last(gelu_dropout(_BiasGradRoute.apply(h, lin1.bias), drop.p, self.training))
+            return last(gelu_dropout(lin1(x), drop.p, self.training))
+        return last(drop(act(self.ffn[0](x))))
 
 
 class ConvolutionModule(nn.Module):
@@ -110,9 +122,10 @@ class ConvolutionModule(nn.Module):
         return out
 
 
-def _conv_body(self, normed, final_dropout=True):
+def _conv_body(self, normed, final_dropout=True, out_bias_grad=True):
     """Everything of the kernel path after ``layer_norm`` (channel-last, no transposes); ``final_dropout=False`` leaves the
-    trailing Dropout to the caller (the encoder layer fuses it into the next add + LayerNorm)."""
+    trailing Dropout to the caller (the encoder layer fuses it into the next add + LayerNorm); ``out_bias_grad=False``
+    likewise leaves the gradient of the last Linear's bias to that kernel (``b_bias=self.after_conv[2].bias``)."""
     pw = self.bottleneck[0]                                           # pointwise conv = Linear over channel-last rows
     out = F.glu(_linear(normed, pw.weight.squeeze(-1), pw.bias), dim=-1)
     out = depthwise_conv1d(out, self.conv.weight, self.conv.bias, pad_left=self.padding)
@@ -125,7 +138,8 @@ def _conv_body(self, normed, final_dropout=True):
         out = layer_norm_act(out, norm, "gelu")
     else:
         out = act(norm(out))
-    out = self.after_conv[2](out)
+    lin = self.after_conv[2]
+    out = lin(out) if out_bias_grad else _linear(out, lin.weight, lin.bias, bias_grad=False)
     return self.after_conv[3](out) if final_dropout else out
 
 
@@ -173,13 +187,19 @@ class ConmambaEncoderLayer(nn.Module):
             # Same arithmetic with every "residual add (+ dropout, + 0.5 scale) -> next LayerNorm" pair evaluated by one
             # sm_100a kernel (cm_add_ln_*); sub-module structure and state_dict are untouched.
             tr = self.training
-            f1 = self.ffn_module1[1](self.ffn_module1[0](x))
-            x, h = add_dropout_layer_norm(x, f1, self.norm1.norm, FFN_RESIDUAL_SCALE, self.ffn_module1[2].p, tr)
+            # the bias gradients of the Linears that end the three branches are the column sums of the branch gradients the
+            # add + LayerNorm backward kernels write: formed there (b_bias=...), not by a pass of their own
+            route = torch.is_grad_enabled() and os.environ.get("CM_NO_FUSE_BIAS_GRAD") is None
+            bias1 = self.ffn_module1[1].ffn[3].bias if route else None
+            bias2 = self.ffn_module2[1].ffn[3].bias if route else None
+            biasc = cm.after_conv[2].bias if route else None
+            f1 = self.ffn_module1[1](self.ffn_module1[0](x), out_bias_grad=bias1 is None)
+            x, h = add_dropout_layer_norm(x, f1, self.norm1.norm, FFN_RESIDUAL_SCALE, self.ffn_module1[2].p, tr, b_bias=bias1)
             x, c_in = add_dropout_layer_norm(x, self.mamba(h), cm.layer_norm, 1.0, 0.0, tr)
-            c_out = cm.body(c_in, final_dropout=False)
-            x, f_in = add_dropout_layer_norm(x, c_out, self.ffn_module2[0], 1.0, cm.after_conv[3].p, tr)
-            f2 = self.ffn_module2[1](f_in)
-            _, out = add_dropout_layer_norm(x, f2, self.norm2.norm, FFN_RESIDUAL_SCALE, self.ffn_module2[2].p, tr)
+            c_out = cm.body(c_in, final_dropout=False, out_bias_grad=biasc is None)
+            x, f_in = add_dropout_layer_norm(x, c_out, self.ffn_module2[0], 1.0, cm.after_conv[3].p, tr, b_bias=biasc)
+            f2 = self.ffn_module2[1](f_in, out_bias_grad=bias2 is None)
+            _, out = add_dropout_layer_norm(x, f2, self.norm2.norm, FFN_RESIDUAL_SCALE, self.ffn_module2[2].p, tr, b_bias=bias2)
             return out
         x = x + FFN_RESIDUAL_SCALE * self.ffn_module1(x)
         skip = x

@@ -89,11 +89,12 @@ __device__ __forceinline__ uint32_t keep8(uint32_t key, int64_t v, uint32_t thr)
 template <typename T>
 __global__ void __launch_bounds__(256) gelu_dropout_fwd_kernel(const T* __restrict__ x, T* __restrict__ y,
                                                                uint8_t* __restrict__ mask, int64_t n8, float p,
-                                                               const int64_t* __restrict__ seed, uint32_t call_id) {
-  const bool drop = mask != nullptr;
+                                                               const int64_t* __restrict__ seed, uint32_t call_id,
+                                                               uint32_t* __restrict__ key_out, bool drop) {
   const uint32_t thr = drop ? (uint32_t)(p * 65536.0f) : 0u;
   const float scale = drop ? 1.0f / (1.0f - p) : 1.0f;
   const uint32_t key = drop ? act_key(seed, call_id) : 0u;
+  if (key_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *key_out = key;   // backward regenerates the mask from it
   // two 16-byte chunks per thread and iteration, both loads issued before the first use: one chunk per thread keeps only
   // 32 KB per SM in flight at full occupancy, below the latency x bandwidth product of HBM3e
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(256) gelu_dropout_fwd_kernel(const T* __restri
 #pragma unroll
       for (int i = 0; i < 8; ++i) a[c][i] = ((kb >> i) & 1u) ? scale * gelu_f(a[c][i]) : 0.f;
       Vec8<T>::st(y + 8 * vv, a[c]);
-      if (drop) {
+      if (mask != nullptr) {
         uint2 m;
         m.x = (kb & 1u) | ((kb & 2u) << 7) | ((kb & 4u) << 14) | ((kb & 8u) << 21);
         m.y = ((kb >> 4) & 1u) | (((kb >> 4) & 2u) << 7) | (((kb >> 4) & 4u) << 14) | (((kb >> 4) & 8u) << 21);
@@ -121,25 +122,56 @@ __global__ void __launch_bounds__(256) gelu_dropout_fwd_kernel(const T* __restri
   }
 }
 
-template <typename T>
+// mask source of the backward: the byte mask the forward stored, or the forward's key (the same hash, regenerated)
+// COLS8 > 0 (vec8 groups per row; 256 % COLS8 == 0 so a thread's eight columns never change across its grid-stride
+// iterations): also the column sums of dx, one partial row per CTA (fixed order) - the bias gradient of the Linear that
+// produced x, which would otherwise be one more pass over dx (cm_colsum).
+template <typename T, bool COLSUM>
 __global__ void __launch_bounds__(256) gelu_dropout_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy,
-                                                               const uint8_t* __restrict__ mask, T* __restrict__ dx,
-                                                               int64_t n8, float p) {
-  const bool drop = mask != nullptr;
+                                                               const uint8_t* __restrict__ mask,
+                                                               const uint32_t* __restrict__ key_in, T* __restrict__ dx,
+                                                               int64_t n8, float p, int cols8, float* __restrict__ cs_part) {
+  const bool drop = p > 0.f;
+  const bool regen = drop && mask == nullptr;
   const float scale = drop ? 1.0f / (1.0f - p) : 1.0f;
+  const uint32_t thr = drop ? (uint32_t)(p * 65536.0f) : 0u;
+  const uint32_t key = regen ? __ldg(key_in) : 0u;
+  float cs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) cs[i] = 0.f;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n8; v += (int64_t)gridDim.x * blockDim.x) {
     float a[8], g[8];
     Vec8<T>::ld(x + 8 * v, a);
     Vec8<T>::ld(dy + 8 * v, g);
-    uint2 m = make_uint2(0x01010101u, 0x01010101u);
-    if (drop) m = __ldg(reinterpret_cast<const uint2*>(mask + 8 * v));
+    uint32_t kb = 0xffu;
+    if (regen) {
+      kb = keep8(key, v, thr);
+    } else if (drop) {
+      const uint2 m = __ldg(reinterpret_cast<const uint2*>(mask + 8 * v));
+      kb = 0u;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const uint32_t w = i < 4 ? m.x : m.y;
-      const bool k = (w >> (8 * (i & 3))) & 0xffu;
-      a[i] = k ? scale * g[i] * gelu_grad_f(a[i]) : 0.f;
+      for (int i = 0; i < 8; ++i) kb |= ((((i < 4 ? m.x : m.y) >> (8 * (i & 3))) & 0xffu) ? 1u : 0u) << i;
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = ((kb >> i) & 1u) ? scale * g[i] * gelu_grad_f(a[i]) : 0.f;
     Vec8<T>::st(dx + 8 * v, a);
+    if (COLSUM) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cs[i] += a[i];       // the fp32 values, before the store rounds them
+    }
+  }
+  if (COLSUM) {
+    __shared__ float4 part_s[256][2];
+    part_s[threadIdx.x][0] = make_float4(cs[0], cs[1], cs[2], cs[3]);
+    part_s[threadIdx.x][1] = make_float4(cs[4], cs[5], cs[6], cs[7]);
+    __syncthreads();
+    // column c <- threads t = c / 8 + j * cols8 (their vec index is congruent to c / 8 modulo cols8), increasing j
+    float* out = cs_part + (int64_t)blockIdx.x * cols8 * 8;
+    for (int c = threadIdx.x; c < cols8 * 8; c += 256) {
+      float sum = 0.f;
+      for (int t = c >> 3; t < 256; t += cols8) sum += reinterpret_cast<const float*>(&part_s[t][0])[c & 7];
+      out[c] = sum;
+    }
   }
 }
 
@@ -153,21 +185,41 @@ static unsigned act_grid(int64_t n8) {
 
 static bool act_al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+static int act_fwd_launch(const void* x, void* y, uint8_t* mask, int64_t n, int32_t dtype, float p_drop, const int64_t* seed,
+                          uint32_t call_id, uint32_t* key_out, bool drop, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n8 = n >> 3;
+  const unsigned grid = cm::act_grid(n8);
+  switch (dtype) {
+    case CM_F32: cm::gelu_dropout_fwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), static_cast<float*>(y), mask, n8, p_drop, seed, call_id, key_out, drop); break;
+    case CM_BF16: cm::gelu_dropout_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), mask, n8, p_drop, seed, call_id, key_out, drop); break;
+    default: cm::gelu_dropout_fwd_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), static_cast<__half*>(y), mask, n8, p_drop, seed, call_id, key_out, drop); break;
+  }
+  CM_LAUNCH_CHECK();
+  return 0;
+}
+
+template <bool COLSUM>
+static int act_bwd_launch(const void* x, const void* dy, const uint8_t* mask, const uint32_t* key, void* dx, int64_t n,
+                          int32_t dtype, float p_drop, int cols8, float* cs_part, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n8 = n >> 3;
+  const unsigned grid = cm::act_grid(n8);
+  switch (dtype) {
+    case CM_F32: cm::gelu_dropout_bwd_kernel<float, COLSUM><<<grid, 256, 0, st>>>(static_cast<const float*>(x), static_cast<const float*>(dy), mask, key, static_cast<float*>(dx), n8, p_drop, cols8, cs_part); break;
+    case CM_BF16: cm::gelu_dropout_bwd_kernel<__nv_bfloat16, COLSUM><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), mask, key, static_cast<__nv_bfloat16*>(dx), n8, p_drop, cols8, cs_part); break;
+    default: cm::gelu_dropout_bwd_kernel<__half, COLSUM><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), static_cast<const __half*>(dy), mask, key, static_cast<__half*>(dx), n8, p_drop, cols8, cs_part); break;
+  }
+  CM_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int cm_gelu_dropout_fwd(const void* x, void* y, uint8_t* mask, int64_t n, int32_t dtype, float p_drop,
                                    const int64_t* seed, uint32_t call_id, void* stream) {
   if (!x || !y || n <= 0 || !cm::dtype_ok(dtype) || p_drop < 0.f || p_drop >= 1.f) return CM_ERR_BAD_ARG;
   if ((n & 7) || !act_al16(x) || !act_al16(y) || (mask && (reinterpret_cast<uintptr_t>(mask) & 7))) return CM_ERR_UNSUPPORTED;
   if (mask && p_drop <= 0.f) return CM_ERR_BAD_ARG;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int64_t n8 = n >> 3;
-  const unsigned grid = cm::act_grid(n8);
-  switch (dtype) {
-    case CM_F32: cm::gelu_dropout_fwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), static_cast<float*>(y), mask, n8, p_drop, seed, call_id); break;
-    case CM_BF16: cm::gelu_dropout_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), mask, n8, p_drop, seed, call_id); break;
-    default: cm::gelu_dropout_fwd_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), static_cast<__half*>(y), mask, n8, p_drop, seed, call_id); break;
-  }
-  CM_LAUNCH_CHECK();
-  return 0;
+  return act_fwd_launch(x, y, mask, n, dtype, p_drop, seed, call_id, nullptr, mask != nullptr, stream);
 }
 
 extern "C" int cm_gelu_dropout_bwd(const void* x, const void* dy, const uint8_t* mask, void* dx, int64_t n, int32_t dtype,
@@ -175,14 +227,37 @@ extern "C" int cm_gelu_dropout_bwd(const void* x, const void* dy, const uint8_t*
   if (!x || !dy || !dx || n <= 0 || !cm::dtype_ok(dtype) || p_drop < 0.f || p_drop >= 1.f) return CM_ERR_BAD_ARG;
   if ((n & 7) || !act_al16(x) || !act_al16(dy) || !act_al16(dx) || (mask && (reinterpret_cast<uintptr_t>(mask) & 7)))
     return CM_ERR_UNSUPPORTED;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int64_t n8 = n >> 3;
-  const unsigned grid = cm::act_grid(n8);
-  switch (dtype) {
-    case CM_F32: cm::gelu_dropout_bwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), static_cast<const float*>(dy), mask, static_cast<float*>(dx), n8, p_drop); break;
-    case CM_BF16: cm::gelu_dropout_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), mask, static_cast<__nv_bfloat16*>(dx), n8, p_drop); break;
-    default: cm::gelu_dropout_bwd_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), static_cast<const __half*>(dy), mask, static_cast<__half*>(dx), n8, p_drop); break;
+  return act_bwd_launch<false>(x, dy, mask, nullptr, dx, n, dtype, mask ? p_drop : 0.f, 0, nullptr, stream);
+}
+
+// struct form: the mask regenerated in backward from the forward's key (nothing stored), column sums of dx
+static bool act_cols_ok(int64_t n, int32_t cols) {
+  return cols > 0 && (cols & 7) == 0 && 256 % (cols >> 3) == 0 && n % cols == 0;
+}
+
+extern "C" int cm_act_colsum_supported(int64_t n, int32_t cols) { return act_cols_ok(n, cols) ? 1 : 0; }
+
+extern "C" int cm_act_num_part(int64_t n) { return n > 0 ? (int)cm::act_grid(n >> 3) : 1; }
+
+extern "C" int cm_gelu_dropout_fwd_v2(const cm_act_args* a, void* stream) {
+  if (!a || !a->x || !a->y || a->n <= 0 || !cm::dtype_ok(a->dtype) || a->p_drop < 0.f || a->p_drop >= 1.f) return CM_ERR_BAD_ARG;
+  if ((a->n & 7) || !act_al16(a->x) || !act_al16(a->y) || (a->mask && (reinterpret_cast<uintptr_t>(a->mask) & 7)))
+    return CM_ERR_UNSUPPORTED;
+  if (a->p_drop > 0.f && !a->mask && !a->key) return CM_ERR_BAD_ARG;       // backward would have no way to rebuild the mask
+  return act_fwd_launch(a->x, a->y, a->p_drop > 0.f ? a->mask : nullptr, a->n, a->dtype, a->p_drop, a->seed, a->call_id,
+                        a->key, a->p_drop > 0.f, stream);
+}
+
+extern "C" int cm_gelu_dropout_bwd_v2(const cm_act_args* a, void* stream) {
+  if (!a || !a->x || !a->dy || !a->dx || a->n <= 0 || !cm::dtype_ok(a->dtype) || a->p_drop < 0.f || a->p_drop >= 1.f)
+    return CM_ERR_BAD_ARG;
+  if ((a->n & 7) || !act_al16(a->x) || !act_al16(a->dy) || !act_al16(a->dx) || (a->mask && (reinterpret_cast<uintptr_t>(a->mask) & 7)))
+    return CM_ERR_UNSUPPORTED;
+  if (a->p_drop > 0.f && !a->mask && !a->key) return CM_ERR_BAD_ARG;
+  if (a->cols > 0) {
+    if (!a->colsum_part) return CM_ERR_BAD_ARG;
+    if (!act_cols_ok(a->n, a->cols)) return CM_ERR_UNSUPPORTED;
+    return act_bwd_launch<true>(a->x, a->dy, a->mask, a->key, a->dx, a->n, a->dtype, a->p_drop, a->cols >> 3, a->colsum_part, stream);
   }
-  CM_LAUNCH_CHECK();
-  return 0;
+  return act_bwd_launch<false>(a->x, a->dy, a->mask, a->key, a->dx, a->n, a->dtype, a->p_drop, 0, nullptr, stream);
 }

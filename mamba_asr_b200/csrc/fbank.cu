@@ -157,6 +157,7 @@ extern "C" int cm_abi_sizeof(int32_t which) {
     case 15: return (int)sizeof(cm_fbank_wav_args);
     case 16: return (int)sizeof(cm_ctc_args);
     case 17: return (int)sizeof(cm_stem_args);
+    case 18: return (int)sizeof(cm_act_args);
     default: return CM_ERR_BAD_ARG;
   }
 }

@@ -348,7 +348,10 @@ static int ln_bwd_launch(const void* x, const void* dy, const float* g, const fl
 
 extern "C" int cm_layernorm_num_part(int64_t rows) {
   const int64_t need = (rows + cm::kLnWarps - 1) / cm::kLnWarps;
-  const int64_t cap = 148 * 4;                      // 4 CTAs of 8 warps per SM
+#ifndef CM_LN_CTAS_PER_SM
+#define CM_LN_CTAS_PER_SM 4
+#endif
+  const int64_t cap = 148 * CM_LN_CTAS_PER_SM;      // 4 CTAs of 8 warps per SM
   return (int)(need < cap ? (need < 1 ? 1 : need) : cap);
 }
 

@@ -6,6 +6,7 @@ enqueues the sm_100a kernels on torch's current stream.  Logical shapes follow t
 (a ``(B, L, D)`` buffer viewed through ``.transpose(1, 2)``) is the fast path.  No host synchronisation.
 """
 import ctypes as C
+import functools
 import os
 
 import torch
@@ -802,9 +803,11 @@ def add_ln_supported(a2d, b2d, out_dtype):
     return True
 
 
-def add_ln_forward(a2d, b2d, weight, bias, eps, alpha, p_drop, seed, call_id, out_dtype, need_s=True):
+def add_ln_forward(a2d, b2d, weight, bias, eps, alpha, p_drop, seed, call_id, out_dtype, need_s=True, store_mask=None):
     """cm_add_ln_fwd: s = a + alpha * dropout_p(b); y = LayerNorm(s).  a2d (rows, C); b2d (rows, C) or None; seed: int64
-    CUDA scalar tensor or None.  Returns (s, y, mean, rstd, mask); mask is None when p_drop == 0."""
+    CUDA scalar tensor or None.  Returns (s, y, mean, rstd, saved): ``saved`` is what backward needs to rebuild the dropout
+    mask - None (no dropout), a (1,) int32 key tensor (default: regenerated, nothing stored) or the uint8 byte mask
+    (``store_mask=True`` / CM_DROPOUT_STORE_MASK=1)."""
     lib = cabi.lib()
     _require_cuda(a2d, "a")
     rows, Cn = a2d.shape
@@ -813,13 +816,19 @@ def add_ln_forward(a2d, b2d, weight, bias, eps, alpha, p_drop, seed, call_id, ou
     y = torch.empty((rows, Cn), dtype=out_dtype, device=dev)
     mean = torch.empty((rows,), dtype=torch.float32, device=dev)
     rstd = torch.empty((rows,), dtype=torch.float32, device=dev)
-    mask = torch.empty((rows, Cn), dtype=torch.uint8, device=dev) if (p_drop > 0.0 and b2d is not None) else None
+    drop = p_drop > 0.0 and b2d is not None
+    if store_mask is None:
+        store_mask = os.environ.get("CM_DROPOUT_STORE_MASK", "0") == "1"
+    saved = None
+    if drop:
+        saved = (torch.empty((rows, Cn), dtype=torch.uint8, device=dev) if store_mask
+                 else torch.empty((1,), dtype=torch.int32, device=dev))
     _same_device(a2d, b=b2d, weight=weight, bias=bias, seed=seed)
     a = cabi.AddLnArgs()
     a.rows, a.cols = rows, Cn
     a.a_dtype, a.y_dtype = cabi.dtype_code(a2d.dtype), cabi.dtype_code(out_dtype)
     a.b_dtype = cabi.dtype_code(b2d.dtype) if b2d is not None else a.a_dtype
-    a.eps, a.alpha, a.p_drop = float(eps), float(alpha), float(p_drop if mask is not None else 0.0)
+    a.eps, a.alpha, a.p_drop = float(eps), float(alpha), float(p_drop if drop else 0.0)
     a.call_id = int(call_id) & 0xffffffff
     a.seed = cabi.ptr(seed)
     a.a, a.a_stride = a2d.data_ptr(), a2d.stride(0)
@@ -828,16 +837,22 @@ def add_ln_forward(a2d, b2d, weight, bias, eps, alpha, p_drop, seed, call_id, ou
     if s is not None:
         a.s, a.s_stride = s.data_ptr(), s.stride(0)
     a.y, a.y_stride = y.data_ptr(), y.stride(0)
-    a.mask = cabi.ptr(mask)
+    if saved is not None:
+        if saved.dtype == torch.uint8:
+            a.mask = saved.data_ptr()
+        else:
+            a.key = saved.data_ptr()
     a.gamma, a.beta = cabi.ptr(weight), cabi.ptr(bias)
     a.mean, a.rstd = mean.data_ptr(), rstd.data_ptr()
     _call("cm_add_ln_fwd", lib.cm_add_ln_fwd, C.byref(a), cabi.stream_ptr())
-    return s, y, mean, rstd, mask
+    return s, y, mean, rstd, saved
 
 
-def add_ln_backward(s2d, dy2d, ds2d, weight, mean, rstd, mask, alpha, p_drop, b_dtype, need_db=True, need_wgrad=True):
-    """cm_add_ln_bwd + deterministic reduction of the dgamma / dbeta partial rows.
-    Returns (da in s's dtype, db in b_dtype or None, dgamma fp32 (C,), dbeta fp32 (C,))."""
+def add_ln_backward(s2d, dy2d, ds2d, weight, mean, rstd, saved, alpha, p_drop, b_dtype, need_db=True, need_wgrad=True,
+                    need_dbsum=False):
+    """cm_add_ln_bwd + deterministic reduction of the dgamma / dbeta partial rows.  ``saved`` as returned by
+    ``add_ln_forward``.  Returns (da in s's dtype, db in b_dtype or None, dgamma fp32 (C,), dbeta fp32 (C,)); with
+    ``need_dbsum`` a fifth value: the fp32 column sums of db (None when the geometry is outside the quad kernels)."""
     lib = cabi.lib()
     rows, Cn = s2d.shape
     dev = s2d.device
@@ -847,15 +862,19 @@ def add_ln_backward(s2d, dy2d, ds2d, weight, mean, rstd, mask, alpha, p_drop, b_
         ds2d = ds2d.to(s2d.dtype).contiguous()
     da = torch.empty((rows, Cn), dtype=s2d.dtype, device=dev)
     db = torch.empty((rows, Cn), dtype=b_dtype, device=dev) if need_db else None
-    n_part = lib.cm_layernorm_num_part(rows)
+    n_part = lib.cm_add_ln_num_part(rows, Cn)
     dg_part = torch.empty((n_part, Cn), dtype=torch.float32, device=dev)
     db_part = torch.empty((n_part, Cn), dtype=torch.float32, device=dev)
     a = cabi.AddLnArgs()
     a.rows, a.cols = rows, Cn
     a.a_dtype, a.b_dtype, a.y_dtype = cabi.dtype_code(s2d.dtype), cabi.dtype_code(b_dtype), cabi.dtype_code(dy2d.dtype)
-    a.alpha, a.p_drop = float(alpha), float(p_drop if mask is not None else 0.0)
+    a.alpha, a.p_drop = float(alpha), float(p_drop if saved is not None else 0.0)
     a.s, a.s_stride = s2d.data_ptr(), s2d.stride(0)
-    a.mask = cabi.ptr(mask)
+    if saved is not None:
+        if saved.dtype == torch.uint8:
+            a.mask = saved.data_ptr()
+        else:
+            a.key = saved.data_ptr()
     a.gamma = cabi.ptr(weight)
     a.mean, a.rstd = mean.data_ptr(), rstd.data_ptr()
     a.dy, a.dy_stride = dy2d.data_ptr(), dy2d.stride(0)
@@ -865,12 +884,26 @@ def add_ln_backward(s2d, dy2d, ds2d, weight, mean, rstd, mask, alpha, p_drop, b_
     if db is not None:
         a.db, a.db_stride = db.data_ptr(), db.stride(0)
     a.dgamma_part, a.dbeta_part = dg_part.data_ptr(), db_part.data_ptr()
+    dbs_part = None
+    if need_dbsum and db is not None:
+        strides = [s2d.stride(0), dy2d.stride(0), da.stride(0), db.stride(0)] + ([ds2d.stride(0)] if ds2d is not None else [])
+        ptrs_ok = all(t is None or t.data_ptr() % 16 == 0 for t in (s2d, dy2d, ds2d, da, db, weight))
+        if ptrs_ok and lib.cm_add_ln_dbsum_supported(Cn, functools.reduce(lambda u, v: u | v, strides) & 3):
+            dbs_part = torch.empty((n_part, Cn), dtype=torch.float32, device=dev)
+            a.dbsum_part = dbs_part.data_ptr()
     _call("cm_add_ln_bwd", lib.cm_add_ln_bwd, C.byref(a), cabi.stream_ptr())
-    if not need_wgrad:
-        return da, db, None, None
-    dg = torch.empty((Cn,), dtype=torch.float32, device=dev)
-    dbt = torch.empty((Cn,), dtype=torch.float32, device=dev)
-    reduce_many([(dg_part, dg), (db_part, dbt)])
+    jobs, dg, dbt, dbs = [], None, None, None
+    if need_wgrad:
+        dg = torch.empty((Cn,), dtype=torch.float32, device=dev)
+        dbt = torch.empty((Cn,), dtype=torch.float32, device=dev)
+        jobs += [(dg_part, dg), (db_part, dbt)]
+    if dbs_part is not None:
+        dbs = torch.empty((Cn,), dtype=torch.float32, device=dev)
+        jobs.append((dbs_part, dbs))
+    if jobs:
+        reduce_many(jobs)
+    if need_dbsum:
+        return da, db, dg, dbt, dbs
     return da, db, dg, dbt
 
 
@@ -880,25 +913,57 @@ def gelu_dropout_supported(x):
         x.dtype in (torch.float32, torch.bfloat16, torch.float16)
 
 
-def gelu_dropout_forward(x, p_drop, seed, call_id):
-    """cm_gelu_dropout_fwd on a contiguous tensor: returns (y, mask) with mask None when p_drop == 0."""
+def gelu_dropout_forward(x, p_drop, seed, call_id, store_mask=None):
+    """cm_gelu_dropout_fwd_v2 on a contiguous tensor: returns (y, saved) where ``saved`` is what backward needs to rebuild the
+    dropout mask - None (no dropout), a (1,) int32 key tensor (default: the mask is regenerated, nothing stored) or the
+    uint8 byte mask (``store_mask=True`` or CM_DROPOUT_STORE_MASK=1: the A/B switch back to the stored mask)."""
     lib = cabi.lib()
     _require_cuda(x, "x")
     y = torch.empty_like(x)
-    mask = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if p_drop > 0.0 else None
-    _call("cm_gelu_dropout_fwd", lib.cm_gelu_dropout_fwd, x.data_ptr(), y.data_ptr(), cabi.ptr(mask), x.numel(),
-          cabi.dtype_code(x.dtype), float(p_drop), cabi.ptr(seed), int(call_id) & 0xffffffff, cabi.stream_ptr())
-    return y, mask
+    if store_mask is None:
+        store_mask = os.environ.get("CM_DROPOUT_STORE_MASK", "0") == "1"
+    a = cabi.ActArgs()
+    a.x, a.y, a.n, a.dtype = x.data_ptr(), y.data_ptr(), x.numel(), cabi.dtype_code(x.dtype)
+    a.p_drop, a.seed, a.call_id = float(p_drop), cabi.ptr(seed), int(call_id) & 0xffffffff
+    saved = None
+    if p_drop > 0.0:
+        if store_mask:
+            saved = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+            a.mask = saved.data_ptr()
+        else:
+            saved = torch.empty((1,), dtype=torch.int32, device=x.device)
+            a.key = saved.data_ptr()
+    _call("cm_gelu_dropout_fwd", lib.cm_gelu_dropout_fwd_v2, C.byref(a), cabi.stream_ptr())
+    return y, saved
 
 
-def gelu_dropout_backward(x, dy, mask, p_drop):
+def gelu_dropout_backward(x, dy, saved, p_drop, colsum_cols=0):
+    """cm_gelu_dropout_bwd_v2.  ``saved`` as returned by ``gelu_dropout_forward``.  colsum_cols > 0: also returns the fp32
+    column sums of dx viewed as (-1, colsum_cols) (None if that width is outside the fused envelope)."""
     lib = cabi.lib()
     if not dy.is_contiguous() or dy.dtype != x.dtype:
         dy = dy.to(x.dtype).contiguous()
     dx = torch.empty_like(x)
-    _call("cm_gelu_dropout_bwd", lib.cm_gelu_dropout_bwd, x.data_ptr(), dy.data_ptr(), cabi.ptr(mask), dx.data_ptr(),
-          x.numel(), cabi.dtype_code(x.dtype), float(p_drop if mask is not None else 0.0), cabi.stream_ptr())
-    return dx
+    a = cabi.ActArgs()
+    a.x, a.dy, a.dx, a.n, a.dtype = x.data_ptr(), dy.data_ptr(), dx.data_ptr(), x.numel(), cabi.dtype_code(x.dtype)
+    a.p_drop = float(p_drop) if saved is not None else 0.0
+    if saved is not None:
+        if saved.dtype == torch.uint8:
+            a.mask = saved.data_ptr()
+        else:
+            a.key = saved.data_ptr()
+    part = None
+    if colsum_cols > 0 and lib.cm_act_colsum_supported(x.numel(), colsum_cols):
+        part = torch.empty((lib.cm_act_num_part(x.numel()), colsum_cols), dtype=torch.float32, device=x.device)
+        a.cols, a.colsum_part = colsum_cols, part.data_ptr()
+    _call("cm_gelu_dropout_bwd", lib.cm_gelu_dropout_bwd_v2, C.byref(a), cabi.stream_ptr())
+    if colsum_cols <= 0:
+        return dx
+    if part is None:
+        return dx, None
+    cs = torch.empty((colsum_cols,), dtype=torch.float32, device=x.device)
+    reduce_many([(part, cs)])
+    return dx, cs
 
 
 # ------------------------------------------------------------------------------------------------ tall-skinny A^T B

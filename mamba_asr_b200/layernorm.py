@@ -216,40 +216,67 @@ class DropoutSeed:
 
 class _AddDropoutLayerNormFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, a, b, weight, bias, eps, alpha, p_drop, out_dtype):
+    def forward(ctx, a, b, weight, bias, eps, alpha, p_drop, out_dtype, b_bias):
+        # b_bias: the bias parameter of the Linear that produced b (or None).  It does not enter the forward; its gradient -
+        # the column sums of db - comes out of the backward kernel instead of one more pass over db in that Linear's backward.
         Cn = a.shape[-1]
         a2 = a.reshape(-1, Cn)
         b2 = None if b is None else b.reshape(-1, Cn)
         seed = DropoutSeed.tensor(a.device) if p_drop > 0.0 else None
-        s, y, mean, rstd, mask = K.add_ln_forward(a2, b2, weight, bias, eps, alpha, p_drop, seed,
-                                                  DropoutSeed.next_call_id(), out_dtype)
-        ctx.save_for_backward(s, weight, mean, rstd, mask)
+        s, y, mean, rstd, saved = K.add_ln_forward(a2, b2, weight, bias, eps, alpha, p_drop, seed,
+                                                   DropoutSeed.next_call_id(), out_dtype)
+        ctx.save_for_backward(s, weight, mean, rstd, saved)
         ctx.shape = a.shape
         ctx.alpha, ctx.p_drop = alpha, p_drop
         ctx.b_dtype = None if b is None else b.dtype
         ctx.has_bias = bias is not None
+        ctx.b_bias_dtype = None if b_bias is None else b_bias.dtype
         return s.view(a.shape), y.view(a.shape)
 
     @staticmethod
     def backward(ctx, ds, dy):
-        s, weight, mean, rstd, mask = ctx.saved_tensors
+        s, weight, mean, rstd, saved = ctx.saved_tensors
         Cn = s.shape[1]
         if dy is None:
             dy = torch.zeros(ctx.shape, dtype=s.dtype, device=s.device)
         need_w = weight is not None and (ctx.needs_input_grad[2] or ctx.needs_input_grad[3])
-        da, db, dg, dbt = K.add_ln_backward(s, dy.reshape(-1, Cn), None if ds is None else ds.reshape(-1, Cn), weight,
-                                            mean, rstd, mask, ctx.alpha, ctx.p_drop, ctx.b_dtype or s.dtype,
-                                            need_db=ctx.b_dtype is not None, need_wgrad=need_w)
+        need_bb = ctx.b_bias_dtype is not None and ctx.needs_input_grad[8] and ctx.b_dtype is not None
+        da, db, dg, dbt, dbs = K.add_ln_backward(s, dy.reshape(-1, Cn), None if ds is None else ds.reshape(-1, Cn), weight,
+                                                 mean, rstd, saved, ctx.alpha, ctx.p_drop, ctx.b_dtype or s.dtype,
+                                                 need_db=ctx.b_dtype is not None, need_wgrad=need_w, need_dbsum=True)
+        dbb = None
+        if need_bb:
+            if dbs is None:                                      # geometry outside the quad kernels: the separate pass
+                dbs = K.colsum(db)
+                if dbs is None:
+                    dbs = db.float().sum(0)
+            dbb = dbs.to(ctx.b_bias_dtype)
         return (da.view(ctx.shape), None if db is None else db.view(ctx.shape),
                 dg.to(weight.dtype) if (need_w and ctx.needs_input_grad[2]) else None,
                 dbt.to(weight.dtype) if (need_w and ctx.has_bias and ctx.needs_input_grad[3]) else None,
-                None, None, None, None)
+                None, None, None, None, dbb)
 
 
-def add_dropout_layer_norm(a, b, norm, alpha=1.0, p_drop=0.0, training=True):
+def add_ln_kernel_ok(a, b, norm):
+    """True when ``add_dropout_layer_norm(a, b, norm, ...)`` runs on the fused kernel (cm_add_ln_*) in the current autocast
+    state - the condition under which ``b_bias`` may be passed."""
+    if norm.keep_dtype:
+        out_dtype = torch.float32 if torch.is_autocast_enabled("cuda") else a.dtype
+    elif torch.is_autocast_enabled("cuda"):
+        out_dtype = torch.get_autocast_dtype("cuda")
+    else:
+        out_dtype = a.dtype
+    Cn = a.shape[-1]
+    return (b is not None and a.is_cuda and a.is_contiguous() and b.is_contiguous() and b.shape == a.shape
+            and K.add_ln_supported(a.reshape(-1, Cn), b.reshape(-1, Cn), out_dtype))
+
+
+def add_dropout_layer_norm(a, b, norm, alpha=1.0, p_drop=0.0, training=True, b_bias=None):
     """(s, y) with  s = a + alpha * dropout(b, p_drop)  and  y = norm(s)  for a ``FusedLayerNorm`` ``norm`` - one kernel
     forward, one backward (cm_add_ln_*) when the combination is implemented, else the separate ops.  ``b`` may be None
-    (s = a)."""
+    (s = a).  ``b_bias``: the bias parameter of the Linear that produced b, when that Linear was evaluated with
+    ``linear(..., bias_grad=False)``: its gradient (the column sums of db) then comes out of this op's backward kernel
+    (only valid when ``add_ln_kernel_ok``)."""
     p = float(p_drop) if training else 0.0
     out_dtype = None
     if norm.keep_dtype:
@@ -261,40 +288,79 @@ def add_dropout_layer_norm(a, b, norm, alpha=1.0, p_drop=0.0, training=True):
     Cn = a.shape[-1]
     ok = (b is not None and a.is_cuda and a.is_contiguous() and b.is_contiguous() and b.shape == a.shape
           and K.add_ln_supported(a.reshape(-1, Cn), b.reshape(-1, Cn), out_dtype))
+    if b_bias is not None and not (torch.is_grad_enabled() and b_bias.requires_grad):
+        b_bias = None
     if not ok:
         if b is None:
             s = a
         else:
+            if b_bias is not None:                               # the promised bias gradient, by the separate pass
+                b = _BiasGradRoute.apply(b, b_bias)
             s = a + alpha * (torch.nn.functional.dropout(b, p, training=True) if p > 0 else b)
         return s, norm(s)
     w = norm.weight if norm.weight is None or norm.weight.dtype == torch.float32 else norm.weight.float()
     bb = norm.bias if norm.bias is None or norm.bias.dtype == torch.float32 else norm.bias.float()
     with torch.autocast("cuda", enabled=False):
-        return _AddDropoutLayerNormFn.apply(a, b, w, bb, norm.eps, float(alpha), p, out_dtype)
+        return _AddDropoutLayerNormFn.apply(a, b, w, bb, norm.eps, float(alpha), p, out_dtype, b_bias)
+
+
+class _BiasGradRoute(torch.autograd.Function):
+    """Identity on ``y``; the gradient of ``bias`` is the column sum of the gradient of ``y`` (for a Linear evaluated with
+    ``bias_grad=False`` whose consumer cannot form that sum itself)."""
+
+    @staticmethod
+    def forward(ctx, y, bias):
+        ctx.bias_dtype = bias.dtype
+        return y.view_as(y)
+
+    @staticmethod
+    def backward(ctx, dy):
+        d2 = dy.reshape(-1, dy.shape[-1])
+        cs = K.colsum(d2 if d2.stride(-1) == 1 else d2.contiguous()) if d2.is_cuda else None
+        if cs is None:
+            cs = d2.float().sum(0)
+        return dy, cs.to(ctx.bias_dtype)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
 # GELU + dropout in one pass (cm_gelu_dropout_fwd / cm_gelu_dropout_bwd)
 class _GeluDropoutFn(torch.autograd.Function):
+    """``bias`` is the bias of the Linear that produced ``x`` (or None): it does not enter the forward, but its gradient - the
+    column sums of dx - is formed inside the backward kernel instead of by one more pass over dx in the Linear's backward."""
+
     @staticmethod
-    def forward(ctx, x, p_drop):
+    def forward(ctx, x, p_drop, bias):
         seed = DropoutSeed.tensor(x.device) if p_drop > 0.0 else None
-        y, mask = K.gelu_dropout_forward(x, p_drop, seed, DropoutSeed.next_call_id())
-        ctx.save_for_backward(x, mask)
+        y, saved = K.gelu_dropout_forward(x, p_drop, seed, DropoutSeed.next_call_id())
+        ctx.save_for_backward(x, saved)
         ctx.p_drop = p_drop
+        ctx.bias_dtype = None if bias is None else bias.dtype
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, mask = ctx.saved_tensors
-        return K.gelu_dropout_backward(x, dy, mask, ctx.p_drop), None
+        x, saved = ctx.saved_tensors
+        if ctx.bias_dtype is None or not ctx.needs_input_grad[2]:
+            return K.gelu_dropout_backward(x, dy, saved, ctx.p_drop), None, None
+        cols = x.shape[-1]
+        dx, cs = K.gelu_dropout_backward(x, dy, saved, ctx.p_drop, colsum_cols=cols)
+        if cs is None:
+            cs = K.colsum(dx.reshape(-1, cols))
+            if cs is None:
+                cs = dx.reshape(-1, cols).float().sum(0)
+        return dx, None, cs.to(ctx.bias_dtype)
 
 
-def gelu_dropout(x, p_drop=0.0, training=True):
+def gelu_dropout(x, p_drop=0.0, training=True, bias_for_grad=None):
     """dropout(gelu(x)) (exact erf GELU, as ``nn.GELU()``) - one sm_100a kernel forward and one backward on CUDA tensors
-    the kernel supports, the two torch ops otherwise."""
+    the kernel supports, the two torch ops otherwise.  ``bias_for_grad``: the bias parameter of the Linear that produced x,
+    when that Linear was evaluated with ``linear(..., bias_grad=False)``: its gradient then comes out of this op's backward."""
     p = float(p_drop) if training else 0.0
     if not K.gelu_dropout_supported(x):
+        if bias_for_grad is not None:
+            raise NotImplementedError("gelu_dropout: bias_for_grad needs the kernel path (check gelu_dropout_supported first)")
         y = torch.nn.functional.gelu(x)
         return torch.nn.functional.dropout(y, p, training=True) if p > 0 else y
-    return _GeluDropoutFn.apply(x, p)
+    if bias_for_grad is not None and not (torch.is_grad_enabled() and bias_for_grad.requires_grad):
+        bias_for_grad = None
+    return _GeluDropoutFn.apply(x, p, bias_for_grad)

@@ -138,15 +138,21 @@ class _LinearFn(torch.autograd.Function):
         return dx, dw, db, None, None
 
 
-def linear(x, weight, bias=None):
+def linear(x, weight, bias=None, bias_grad=True):
     """F.linear for CUDA training: bias gradient on cm_colsum, parameter casts from the ``ParamCache`` when one is
-    installed, fp32 weight gradients straight from the GEMM.  Plain F.linear on CPU or without grad."""
+    installed, fp32 weight gradients straight from the GEMM.  Plain F.linear on CPU or without grad.
+    ``bias_grad=False``: the caller obtains the bias gradient elsewhere (the consumer of the output sums its own input
+    gradient over the rows, e.g. ``gelu_dropout(..., bias_for_grad=bias)``): no column-sum pass here."""
     if not x.is_cuda or not torch.is_grad_enabled() or not (weight.requires_grad or (bias is not None and bias.requires_grad)):
         return F.linear(x, weight, bias)
+    if bias is not None and not bias_grad:
+        b_src, bias = bias, bias.detach()
+    else:
+        b_src = bias
     if torch.is_autocast_enabled("cuda"):          # the casts autocast would insert
         dt = torch.get_autocast_dtype("cuda")
         w_lp = cached_param(weight, dt)
-        b_lp = cached_param(bias, dt)
+        b_lp = cached_param(b_src, dt)
         if w_lp is None:
             w_lp = weight.detach().to(dt)
         if bias is not None and b_lp is None:

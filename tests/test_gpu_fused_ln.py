@@ -70,7 +70,9 @@ def test_fused_dropout_mask_statistics_and_gradient(combo):
     a, b, w, bias, cs, cy = _inputs((rows, C), ta, tb, seed=1)
     a, b, w, bias = a.cuda(), b.cuda(), w.cuda(), bias.cuda()
     seed = DropoutSeed.tensor(a.device)
-    s, y, mean, rstd, mask = K.add_ln_forward(a, b, w, bias, 1e-5, alpha, p, seed, 7, ty)
+    s, y, mean, rstd, mask = K.add_ln_forward(a, b, w, bias, 1e-5, alpha, p, seed, 7, ty, store_mask=True)
+    s_k, y_k, _, _, key = K.add_ln_forward(a, b, w, bias, 1e-5, alpha, p, seed, 7, ty)     # default: nothing stored but the key
+    assert key.dtype == torch.int32 and key.numel() == 1 and torch.equal(s, s_k) and torch.equal(y, y_k)
     keep = mask.float()
     assert set(mask.unique().tolist()) <= {0, 1}
     assert abs(float(keep.mean()) - (1 - p)) < 3e-3                               # 1M samples: sigma = 3e-4
@@ -80,18 +82,24 @@ def test_fused_dropout_mask_statistics_and_gradient(combo):
     y_ref = F.layer_norm(s_ref.to(ta).float(), (C,), w, bias, 1e-5)
     assert_close(y.float(), y_ref, ty, what="y with dropout")
     # same (seed, call id) -> same mask; another call id or an advanced seed -> a different one
-    m2 = K.add_ln_forward(a, b, w, bias, 1e-5, alpha, p, seed, 7, ty)[4]
-    m3 = K.add_ln_forward(a, b, w, bias, 1e-5, alpha, p, seed, 8, ty)[4]
+    m2 = K.add_ln_forward(a, b, w, bias, 1e-5, alpha, p, seed, 7, ty, store_mask=True)[4]
+    m3 = K.add_ln_forward(a, b, w, bias, 1e-5, alpha, p, seed, 8, ty, store_mask=True)[4]
     assert torch.equal(mask, m2) and not torch.equal(mask, m3)
     assert abs(float((mask == m3).float().mean()) - (p * p + (1 - p) ** 2)) < 5e-3  # independent masks
     DropoutSeed.advance(a.device)
-    m4 = K.add_ln_forward(a, b, w, bias, 1e-5, alpha, p, seed, 7, ty)[4]
+    m4 = K.add_ln_forward(a, b, w, bias, 1e-5, alpha, p, seed, 7, ty, store_mask=True)[4]
     assert not torch.equal(mask, m4)
     # backward: db = alpha / (1 - p) * keep * da
     dy = cy.cuda().to(ty)
     ds = cs.cuda().to(ta)
     da, db, dg, dbt = K.add_ln_backward(s, dy, ds, w, mean, rstd, mask, alpha, p, tb)
     assert_close(db.float(), (alpha / (1 - p)) * keep * da.float(), tb, floor="max", what="db vs mask * da")
+    # the mask regenerated from the forward's key (captured before the seed advanced) gives the same gradients, and the
+    # column sums of db (the bias gradient of the Linear behind b) come out of the same launch
+    da_k, db_k, dg_k, dbt_k, dbs = K.add_ln_backward(s, dy, ds, w, mean, rstd, key, alpha, p, tb, need_dbsum=True)
+    assert torch.equal(da, da_k) and torch.equal(db, db_k) and torch.equal(dg, dg_k) and torch.equal(dbt, dbt_k)
+    assert_close(dbs, db.double().sum(0).float(), torch.float32 if tb == torch.float32 else torch.bfloat16, floor="max",
+                 what="column sums of db")
     sr = s.float().requires_grad_(True)
     (F.layer_norm(sr, (C,), w, bias, 1e-5) * dy.float()).sum().backward()
     assert_close(da.float(), sr.grad + ds.float(), ta, floor="max", what="da")
@@ -413,3 +421,98 @@ def test_stem_envelope_and_ab_switch(monkeypatch):
     b = fe(x)
     assert K.LAUNCHES - n0 == used            # one cm_stem_fwd instead of one cm_ln_act_fwd
     assert_close(a, b, torch.float32, what="front-end with / without the stem kernel", rtol_mul=10.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# cm_gelu_dropout_*_v2: the dropout mask regenerated in backward from the forward's key, bias gradient inside the kernel
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(3, 37, 1024), (64, 501, 1024), (5, 7, 2048), (9, 64), (4, 33, 576), (2, 11, 8)])
+def test_gelu_dropout_regenerated_mask_and_fused_bias_gradient(dtype, shape):
+    from mamba_asr_b200 import kernels as K
+    from mamba_asr_b200.layernorm import DropoutSeed
+    g = torch.Generator().manual_seed(11)
+    x = (2.0 * torch.randn(*shape, generator=g)).to(dtype).cuda()
+    dy = torch.randn(*shape, generator=g).to(dtype).cuda()
+    seed = DropoutSeed.tensor(x.device)
+    cols = shape[-1]
+    y0, mask = K.gelu_dropout_forward(x, 0.1, seed, 77, store_mask=True)
+    y1, key = K.gelu_dropout_forward(x, 0.1, seed, 77, store_mask=False)
+    assert mask.dtype == torch.uint8 and key.dtype == torch.int32 and key.numel() == 1
+    assert torch.equal(y0, y1)
+    DropoutSeed.advance(x.device)                       # the key was captured at forward time: a later advance is harmless
+    dx0 = K.gelu_dropout_backward(x, dy, mask, 0.1)
+    dx1, cs = K.gelu_dropout_backward(x, dy, key, 0.1, colsum_cols=cols)
+    assert torch.equal(dx0, dx1)
+    assert torch.equal((dx1 == 0) | (dy == 0), (mask == 0) | (dy == 0) | (dx1 == 0))
+    fused = bool(K.cabi.lib().cm_act_colsum_supported(x.numel(), cols))
+    assert fused == (cols in (1024, 2048, 64, 8))
+    if fused:
+        ref = dx1.reshape(-1, cols).double().sum(0)
+        # the kernel sums its fp32 values before the store rounds them: for 16-bit dx the reference (sum of the rounded dx)
+        # differs by the rounding of every term
+        assert_close(cs, ref.float(), dtype, floor="max", what="fused column sums of dx")
+        dx2, cs2 = K.gelu_dropout_backward(x, dy, key, 0.1, colsum_cols=cols)
+        assert torch.equal(cs, cs2)                     # fixed summation order
+    else:
+        assert cs is None
+
+
+@pytest.mark.parametrize("autocast", [False, True])
+def test_feed_forward_bias_gradient_from_the_activation_kernel(autocast, monkeypatch):
+    """PositionalwiseFeedForward: the first Linear's bias gradient formed inside cm_gelu_dropout_bwd against the column-sum
+    pass in the Linear's own backward (CM_NO_FUSE_BIAS_GRAD=1)."""
+    from mamba_asr_b200.conmamba import PositionalwiseFeedForward
+    from mamba_asr_b200 import kernels as K
+    torch.manual_seed(4)
+    ffn = PositionalwiseFeedForward(d_ffn=1024, input_size=256, dropout=0.0, activation=torch.nn.GELU).cuda()
+    x = torch.randn(4, 101, 256, device="cuda", requires_grad=True)
+    cy = torch.randn(4, 101, 256, device="cuda")
+    res, launches = [], []
+    for fused in (True, False):
+        if not fused:
+            monkeypatch.setenv("CM_NO_FUSE_BIAS_GRAD", "1")
+        ffn.zero_grad()
+        x.grad = None
+        n0 = K.LAUNCHES
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            y = ffn(x)
+        (y.float() * cy).sum().backward()
+        launches.append(K.LAUNCHES - n0)
+        res.append([y.detach().float(), x.grad.clone()] + [p.grad.clone() for p in ffn.parameters()])
+    assert launches[0] == launches[1] - 1               # one cm_colsum + its reducer less, one reducer more
+    dt = torch.bfloat16 if autocast else torch.float32
+    for (a, b) in zip(*res):
+        assert_close(a, b, dt, floor="max", what="ffn with / without the fused bias gradient")
+    assert torch.equal(res[0][0], res[1][0])
+
+
+@pytest.mark.parametrize("autocast", [False, True])
+def test_encoder_layer_bias_gradients_from_the_consumer_kernels(autocast, monkeypatch):
+    """ConmambaEncoderLayer in training mode (dropout on): the bias gradients of the four FFN Linears and of the conv module's
+    last Linear formed inside cm_gelu_dropout_bwd / cm_add_ln_bwd against the column-sum passes (CM_NO_FUSE_BIAS_GRAD=1).
+    Same seed and call ids in both runs, so the dropout masks agree."""
+    from mamba_asr_b200.conmamba import ConmambaEncoderLayer
+    from mamba_asr_b200.layernorm import DropoutSeed
+    from mamba_asr_b200 import kernels as K
+    torch.manual_seed(0)
+    layer = ConmambaEncoderLayer(d_model=64, d_ffn=256, activation=torch.nn.GELU, dropout=0.1,
+                                 mamba_config=dict(d_state=16, expand=2, d_conv=4, bidirectional=True)).cuda().train()
+    x = torch.randn(3, 45, 64, device="cuda")
+    cot = torch.randn(3, 45, 64, device="cuda")
+    res, launches = [], []
+    for fused in (True, False):
+        if not fused:
+            monkeypatch.setenv("CM_NO_FUSE_BIAS_GRAD", "1")
+        DropoutSeed._calls = 1000                       # the same call ids -> the same masks in both runs
+        layer.zero_grad(set_to_none=True)
+        n0 = K.LAUNCHES
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            o = layer(x)
+        (o.float() * cot).sum().backward()
+        launches.append(K.LAUNCHES - n0)
+        res.append((o.float().detach(), {n: p.grad.clone() for n, p in layer.named_parameters()}))
+    assert torch.equal(res[0][0], res[1][0])
+    assert launches[0] < launches[1]                    # five cm_colsum passes (and their reducers) fewer
+    dt = torch.bfloat16 if autocast else torch.float32
+    for n in res[0][1]:
+        assert_close(res[0][1][n], res[1][1][n], dt, floor="max", what="d " + n)

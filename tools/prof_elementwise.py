@@ -43,10 +43,15 @@ def timeit(name, fn, nbytes, iters=12):
 
 
 n, nf = rows * d, rows * dff
-timeit("add_ln_fwd 32064x256", lambda: K.add_ln_forward(a, b, w, bb, 1e-5, 0.5, 0.1, seed, 1, torch.bfloat16), n * 13)
-timeit("add_ln_bwd 32064x256", lambda: K.add_ln_backward(s, dy, ds, w, mean, rstd, mask, 0.5, 0.1, torch.bfloat16), n * 17)
+timeit("add_ln_fwd 32064x256", lambda: K.add_ln_forward(a, b, w, bb, 1e-5, 0.5, 0.1, seed, 1, torch.bfloat16), n * 12)
+timeit("add_ln_bwd 32064x256", lambda: K.add_ln_backward(s, dy, ds, w, mean, rstd, mask, 0.5, 0.1, torch.bfloat16), n * 16)
+timeit("add_ln_bwd +dbsum", lambda: K.add_ln_backward(s, dy, ds, w, mean, rstd, mask, 0.5, 0.1, torch.bfloat16, need_dbsum=True), n * 16)
+_s2, _y2, _m2, _r2, mask_b = K.add_ln_forward(a, b, w, bb, 1e-5, 0.5, 0.1, seed, 0, torch.bfloat16, store_mask=True)
+timeit("add_ln_fwd stored mask", lambda: K.add_ln_forward(a, b, w, bb, 1e-5, 0.5, 0.1, seed, 1, torch.bfloat16, store_mask=True), n * 13)
+timeit("add_ln_bwd stored mask", lambda: K.add_ln_backward(s, dy, ds, w, mean, rstd, mask_b, 0.5, 0.1, torch.bfloat16), n * 17)
 timeit("gelu_dropout_fwd 32064x1024", lambda: K.gelu_dropout_forward(x, 0.1, seed, 1), nf * 5)
-timeit("gelu_dropout_bwd 32064x1024", lambda: K.gelu_dropout_backward(x, dyf, m2, 0.1), nf * 7)
+timeit("gelu_dropout_bwd 32064x1024", lambda: K.gelu_dropout_backward(x, dyf, m2, 0.1), nf * 6)
+timeit("gelu_dropout_bwd +colsum", lambda: K.gelu_dropout_backward(x, dyf, m2, 0.1, colsum_cols=dff), nf * 6)
 timeit("layernorm_fwd 32064x256", lambda: K.layernorm_forward(xb, w, bb, 1e-5, torch.bfloat16), n * 4)
 timeit("layernorm_bwd 32064x256", lambda: K.layernorm_backward(xb, dy, w, ml, rl), n * 6)
 timeit("colsum 32064x1024", lambda: K.colsum(dyf), nf * 2)

@@ -4,7 +4,8 @@ CTC branch of train_S2S.py:518-530, which reach it through ``speechbrain.nnet.lo
 One sm_100a kernel (``cm_ctc_loss``) computes the per-utterance negative log-likelihood AND its gradient with respect to the
 log-probabilities (alpha and beta recursions run concurrently in one CTA per utterance); the autograd backward only scales
 the stored gradient.  Arguments follow torch: ``log_probs`` (T, B, C) log-softmax outputs, ``targets`` (B, S) padded int64,
-``input_lengths`` / ``target_lengths`` (B,), ``reduction`` in {"none", "sum", "mean"}, ``zero_infinity``.  No CPU path."""
+``input_lengths`` / ``target_lengths`` (B,), ``reduction`` in {"none", "sum", "mean"}, ``zero_infinity``.  The kernel gives
+every extended-label state a thread: up to 255 labels per utterance; longer targets go to torch's CUDA kernels.  No CPU path."""
 import torch
 
 from . import kernels as K
@@ -35,6 +36,10 @@ def ctc_loss(log_probs, targets, input_lengths, target_lengths, blank=0, reducti
         raise NotImplementedError("unbatched (T, C) input")
     if targets.dim() != 2:
         raise NotImplementedError("concatenated 1-D targets: pass the padded (B, S) form the recipes use")
+    if not K.ctc_supported(targets.shape[1]):
+        # more than 255 labels per utterance (e.g. 300 s of speech): torch's own CUDA kernels - same semantics, still no CPU
+        return torch.nn.functional.ctc_loss(log_probs.float(), targets, input_lengths, target_lengths, blank=blank,
+                                            reduction=reduction, zero_infinity=zero_infinity)
     dev = log_probs.device
     il = torch.as_tensor(input_lengths, dtype=torch.int64).to(dev).contiguous()
     tl = torch.as_tensor(target_lengths, dtype=torch.int64).to(dev).contiguous()

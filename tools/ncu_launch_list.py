@@ -28,13 +28,14 @@ def main():
         a[1] += us
         tot += us
         n += 1
-    ours = sum(us for k, (c, us) in agg.items() if "cm::" in k or k.startswith("cm::") or " sp::" in k or " spb::" in k
-               or k.startswith("void sp") or "spb::" in k)
+    # ncu prints the innermost namespace only: the kernels of namespace cm::<x> appear as <x>::name
+    inner = ("cm::", "sp::", "spb::", "lc::", "lcb::", "wgb::", "wgf::", "dft::", "stem::", "ctc::", "lna::", "tma::")
+    ours = sum(us for k, (c, us) in agg.items() if any(t in k for t in inner))
     with open(dst, "w") as f:
         f.write("ncu launch list of `%s` (first %d launches of the process, gpu__time_duration.sum, --clock-control none)\n" % (cmd, n))
         f.write("per-launch times are cold-cache and serialised by the profiler: the SHARE of each kernel is what is comparable "
                 "with bench.py's kernel_time_share_ms\n")
-        f.write("total %.1f us over %d launches; hand-written sm_100a kernels (cm::*) %.1f us = %.1f %%\n\n"
+        f.write("total %.1f us over %d launches; hand-written sm_100a kernels (namespace cm) %.1f us = %.1f %%\n\n"
                 % (tot, n, ours, 100 * ours / tot))
         for k, (c, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:80]:
             f.write("%9.1f us %5.1f%% %5d x  %s\n" % (us, 100 * us / tot, c, k[:150]))

@@ -131,6 +131,31 @@ __global__ void __launch_bounds__(32 * kDwWarps) dwconv_bwd_weight_kernel(const 
 // outside [0, dim) zero-filled), then walks it in groups of R = 8 outputs: R + K - 1 conflict-free LDS per lane feed R * K
 // FFMA from registers (taps in registers as before).  No global-memory latency inside the arithmetic, 80 registers.
 constexpr int kDwR = 8;                      // outputs per register group
+// Forward tile kernel, launch shape.  One warp per CTA: with the 4-warp CTAs of the backward-weight kernel the ConMamba-large
+// launch (64 x 501 x 256) was 1024 CTAs of which half had two idle warps, in 1.38 waves of 5 CTAs / SM - the SMs were active
+// 71 % of the 45 us (profiles/r02_dwconv_fwd_tile_kernel_cfg3_ncu.txt).  Single-warp CTAs of 96 registers and < 10 KB of
+// shared memory are all resident at once (21 per SM).  A warp's slab is FTW outputs = a whole number of periods of its
+// circular register window (below).
+template <int K> struct DwFwd {
+  static constexpr int WB = (kDwR + K - 1 + kDwR - 1) / kDwR * kDwR;   // window registers: R + K - 1 rounded up to groups
+  static constexpr int PG = WB / kDwR;                                 // groups per period of the circular window
+  static constexpr int FTW = WB * ((96 + WB - 1) / WB);                // outputs per warp slab (K = 31: 120)
+  static constexpr int RX = FTW + K - 1;                               // input rows of the slab
+};
+
+// store under a predicate the compiler cannot sink the arithmetic into (an `if` around the store moves the 31 FFMA of the
+// output under the branch as well: BSSY / BRA / BSYNC per output)
+template <typename T>
+__device__ __forceinline__ void dw_st_pred(T* ptr, float v, bool ok) {
+  if constexpr (sizeof(T) == 4) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p st.global.f32 [%0], %1;\n}" ::"l"(ptr), "f"(v), "r"((int)ok) : "memory");
+  } else {
+    T t;
+    Elem<T>::st(&t, v);
+    const unsigned short r = *reinterpret_cast<const unsigned short*>(&t);
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p st.global.b16 [%0], %1;\n}" ::"l"(ptr), "h"(r), "r"((int)ok) : "memory");
+  }
+}
 
 __device__ __forceinline__ void cp_async16_zfill(void* dst, const void* src, bool valid) {
   const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
@@ -160,19 +185,19 @@ __device__ __forceinline__ void dw_load_tile(T* tile, const T* base, int64_t sl,
 }
 
 template <typename T, int K>
-__global__ void __launch_bounds__(32 * kDwWarps) dwconv_fwd_tile_kernel(const cm_dwconv_args p) {
-  using DT = DwTile<K>;
+__global__ void __maxnreg__(96) dwconv_fwd_tile_kernel(const cm_dwconv_args p) {
+  using DF = DwFwd<K>;
+  constexpr int WB = DF::WB;
   extern __shared__ __align__(16) unsigned char dw_smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x;
   const int c_blk = blockIdx.x * 32;
   const int c = c_blk + lane;
   const bool act = c < p.dim;
   const int b = blockIdx.z;
-  const int t0 = (blockIdx.y * kDwWarps + warp) * DT::TW;
+  const int t0 = blockIdx.y * DF::FTW;
   const int L = p.seqlen;
-  if (t0 >= L) return;
-  T* tile = reinterpret_cast<T*>(dw_smem) + (size_t)warp * DT::RX * 32;
-  dw_load_tile<T>(tile, static_cast<const T*>(p.x.ptr) + b * p.x.sb, p.x.sl, t0 - p.pad_left, DT::RX, L, c_blk, p.dim, lane);
+  T* tile = reinterpret_cast<T*>(dw_smem);
+  dw_load_tile<T>(tile, static_cast<const T*>(p.x.ptr) + b * p.x.sb, p.x.sl, t0 - p.pad_left, DF::RX, L, c_blk, p.dim, lane);
   asm volatile("cp.async.commit_group;" ::: "memory");
   const int cc = act ? c : 0;
   float w[K];
@@ -184,22 +209,32 @@ __global__ void __launch_bounds__(32 * kDwWarps) dwconv_fwd_tile_kernel(const cm
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncwarp();
   const T* col = tile + lane;
+  auto ld_in = [&](int row) -> float {
+    if constexpr (sizeof(T) == 4) return reinterpret_cast<const float*>(col)[row * 32];
+    else return Elem<T>::cvt(reinterpret_cast<const unsigned short*>(col)[row * 32]);
+  };
+  // Circular register window: input row x of the slab lives in in[x % WB].  A group of kDwR outputs loads only its kDwR new
+  // rows; a period of PG groups is unrolled so that every index is a compile-time register name (no moves), and the loop
+  // over periods is rolled (K = 31: 5 groups = 1240 FFMA per iteration; the fully unrolled slab is 64 KB of code).
+  float in[WB];
+#pragma unroll
+  for (int i = 0; i < K - 1; ++i) in[i] = ld_in(i);
 #pragma unroll 1
-  for (int o = 0; o < DT::TW; o += kDwR) {
-    if (t0 + o >= L) break;
-    float in[kDwR + K - 1];
+  for (int o = 0; o < DF::FTW; o += WB) {
 #pragma unroll
-    for (int i = 0; i < kDwR + K - 1; ++i) {
-      if constexpr (sizeof(T) == 4) in[i] = reinterpret_cast<const float*>(col)[(o + i) * 32];
-      else in[i] = Elem<T>::cvt(reinterpret_cast<const unsigned short*>(col)[(o + i) * 32]);
-    }
+    for (int g = 0; g < DF::PG; ++g) {
+      const int og = o + g * kDwR;
+      if (t0 + og >= L) return;               // an exit, not a join
 #pragma unroll
-    for (int j = 0; j < kDwR; ++j) {
-      float acc = bias;
+      for (int j = 0; j < kDwR; ++j) in[(g * kDwR + K - 1 + j) % WB] = ld_in(og + K - 1 + j);
 #pragma unroll
-      for (int k = 0; k < K; ++k) acc = fmaf(w[k], in[j + k], acc);
-      const int l = t0 + o + j;
-      if (act && o + j < DT::TW && l < L) Elem<T>::st(yp + l * ysl, acc);
+      for (int j = 0; j < kDwR; ++j) {
+        float acc = bias;
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc = fmaf(w[k], in[(g * kDwR + j + k) % WB], acc);
+        const int l = t0 + og + j;
+        dw_st_pred<T>(yp + l * ysl, acc, act && l < L);
+      }
     }
   }
 }
@@ -289,17 +324,19 @@ static int dw_launch(const cm_dwconv_args& a, bool wgrad, cudaStream_t st) {
   const dim3 grid(cm_ceil_div(a.dim, 32), cm_ceil_div(a.seqlen, kDwWarps * TW), a.batch);
   if (dw_tile_ok<T>(a, wgrad)) {
     using DT = DwTile<K>;
-    const size_t smem = (size_t)kDwWarps * (wgrad ? DT::RX + DT::RG : DT::RX) * 32 * sizeof(T);
     if (wgrad) {
+      const size_t smem = (size_t)kDwWarps * (DT::RX + DT::RG) * 32 * sizeof(T);
       auto kern = dwconv_bwdw_tile_kernel<T, K>;
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
       if (e != cudaSuccess) return (int)e;
       kern<<<grid, 32 * kDwWarps, smem, st>>>(a);
     } else {
+      const size_t smem = (size_t)DwFwd<K>::RX * 32 * sizeof(T);
+      const dim3 fgrid(cm_ceil_div(a.dim, 32), cm_ceil_div(a.seqlen, DwFwd<K>::FTW), a.batch);
       auto kern = dwconv_fwd_tile_kernel<T, K>;
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
-      kern<<<grid, 32 * kDwWarps, smem, st>>>(a);
+      kern<<<fgrid, 32, smem, st>>>(a);
     }
     CM_LAUNCH_CHECK();
     return 0;

@@ -332,6 +332,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", action="store_true", help="(default) replay the model forward / backward as CUDA graphs: the eager step is host-launch-bound (2.4 k launches, 41 ms wall for 30 ms of kernels on B200)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly")
+    ap.add_argument("--no-defer-reduce", action="store_true",
+                    help="A/B: reduce every backward kernel's partial sums where they are produced (one launch per operator) "
+                         "instead of in one batch at the end of the backward graph")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-param-cache", action="store_true", help="per-use autocast-style parameter casts (A/B)")
     ap.add_argument("--no-optimizer", action="store_true", help="training workloads: stop after backward (A/B)")
@@ -433,7 +436,10 @@ def main():
             if train:
                 # capture under the same autocast policy the step runs with (weight-cast caching off: the cached casts
                 # of a warm-up iteration would otherwise be baked out of the graph)
-                with torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False):
+                # the partial sums of all backward kernels are reduced in one batch at the end of the backward graph
+                # (kernels.deferred_reductions: valid here because the graph hands the gradients out after the pass)
+                with torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False), \
+                        K.deferred_reductions(not args.no_defer_reduce):
                     gnet = graph_module(net, sample, warmup=3)
                 launches_per_step = (K.LAUNCHES - l0) // 4          # 3 warm-ups + 1 capture
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CM_ABI_VERSION 12
+#define CM_ABI_VERSION 13
 
 /* element type of activations (u, delta, z, B, C, x, out, and their gradients) */
 enum { CM_F32 = 0, CM_BF16 = 1, CM_F16 = 2 };
@@ -161,6 +161,18 @@ typedef struct {
   int64_t rows, cols;
 } cm_reduce_job;
 int cm_reduce_multi(const cm_reduce_job* jobs, int32_t njobs, void* stream);
+/* Up to CM_REDUCE_BATCH_MAX jobs of any shapes in ONE launch (a 1-D grid; every CTA looks its job up): what a host that
+ * queues the partial sums of a whole backward pass calls once at its end (kernels.reduce_many with deferral on; replaces the
+ * per-operator reducer launches and the .sum(0) of split-K weight-gradient products).  `stride` = floats between two rows
+ * of `part` (>= cols): a job may sum a column block of a wider partial buffer.  Rows are added in index order per column
+ * within fixed groups: deterministic. */
+#define CM_REDUCE_BATCH_MAX 64
+typedef struct {
+  const float* part;
+  float* out;
+  int64_t rows, cols, stride;
+} cm_reduce_job2;
+int cm_reduce_batch(const cm_reduce_job2* jobs, int32_t njobs, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Depthwise causal conv1d (+ SiLU).  Replaces causal_conv1d_cuda.causal_conv1d_fwd / _bwd of
@@ -564,7 +576,7 @@ int cm_stem_bwd(const cm_stem_args* args, void* stream);
 /* sizeof() of the argument structs, for binding self-checks: 0 cm_tensor3, 1 cm_scan_dir, 2 cm_scan_fwd_args,
  * 3 cm_scan_bwd_dir, 4 cm_scan_bwd_args, 5 cm_conv_dir, 6 cm_conv_args, 7 cm_fbank_args, 8 cm_reduce_job,
  * 9 cm_layernorm_args, 10 cm_dwconv_args, 11 cm_ssm_step_args, 12 cm_add_ln_args, 13 cm_ln_act_args, 14 cm_adamw_args,
- * 15 cm_fbank_wav_args, 16 cm_ctc_args, 17 cm_stem_args, 18 cm_act_args */
+ * 15 cm_fbank_wav_args, 16 cm_ctc_args, 17 cm_stem_args, 18 cm_act_args, 19 cm_reduce_job2 */
 int cm_abi_sizeof(int32_t which);
 
 #ifdef __cplusplus

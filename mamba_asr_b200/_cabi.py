@@ -17,7 +17,7 @@ CM_ERR_BAD_ARG, CM_ERR_UNSUPPORTED = -1, -2
 CM_FLAG_DELTA_SOFTPLUS = 1
 CM_FLAG_SILU = 1
 CM_SCAN_CKPT_STEPS = 8
-CM_ABI_VERSION = 12
+CM_ABI_VERSION = 13
 CM_LN_ACT_LEAKY_RELU, CM_LN_ACT_GELU = 0, 1
 
 EXPORTS = (
@@ -30,9 +30,11 @@ EXPORTS = (
     "cm_ln_act_num_part", "cm_ln_act_fwd", "cm_ln_act_bwd", "cm_optim_num_part", "cm_sumsq_partial", "cm_adamw_step",
     "cm_fbank_wav_supported", "cm_fbank_wav_logmel", "cm_ctc_workspace_floats", "cm_ctc_loss",
     "cm_stem_supported", "cm_stem_num_part", "cm_stem_fwd", "cm_stem_bwd",
+    "cm_reduce_batch",
     "cm_add_ln_dbsum_supported", "cm_add_ln_num_part", "cm_act_colsum_supported", "cm_act_num_part", "cm_gelu_dropout_fwd_v2", "cm_gelu_dropout_bwd_v2",
 )
 CM_REDUCE_MAX_JOBS = 8
+CM_REDUCE_BATCH_MAX = 64
 
 _DTYPES = {torch.float32: CM_F32, torch.bfloat16: CM_BF16, torch.float16: CM_F16}
 
@@ -150,6 +152,10 @@ class ReduceJob(C.Structure):
     _fields_ = [("part", C.c_void_p), ("out", C.c_void_p), ("rows", C.c_int64), ("cols", C.c_int64)]
 
 
+class ReduceJob2(C.Structure):
+    _fields_ = [("part", C.c_void_p), ("out", C.c_void_p), ("rows", C.c_int64), ("cols", C.c_int64), ("stride", C.c_int64)]
+
+
 class LayerNormArgs(C.Structure):
     _fields_ = [
         ("rows", C.c_int64), ("cols", C.c_int32), ("x_dtype", C.c_int32), ("y_dtype", C.c_int32), ("eps", C.c_float),
@@ -212,7 +218,7 @@ class AdamWArgs(C.Structure):
 
 ABI_STRUCTS = (Tensor3, ScanDir, ScanFwdArgs, ScanBwdDir, ScanBwdArgs, ConvDir, ConvArgs, FbankArgs, ReduceJob,
                LayerNormArgs, DwConvArgs, SsmStepArgs, AddLnArgs, LnActArgs, AdamWArgs, FbankWavArgs, CtcArgs,
-               StemArgs, ActArgs)
+               StemArgs, ActArgs, ReduceJob2)
 
 def lib():
     """The loaded shared library; raises (never falls back) when it is absent or stale."""
@@ -283,6 +289,7 @@ def lib():
         L.cm_ln_act_num_part.argtypes = [C.c_int64, C.c_int32]
         L.cm_ln_act_fwd.argtypes = [C.POINTER(LnActArgs), C.c_void_p]
         L.cm_ln_act_bwd.argtypes = [C.POINTER(LnActArgs), C.c_void_p]
+        L.cm_reduce_batch.argtypes = [C.POINTER(ReduceJob2), C.c_int32, C.c_void_p]
         L.cm_optim_num_part.argtypes = [C.c_int64]
         L.cm_sumsq_partial.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.cm_adamw_step.argtypes = [C.POINTER(AdamWArgs), C.c_void_p]

@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import kernels as K
 from .causal_conv1d import causal_conv1d_update
 from .linear import linear
 from .mamba_inner import MambaInnerCL, inner_forward
@@ -187,6 +188,7 @@ class _NegExpMany(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         As = ctx.saved_tensors
+        K.flush_reductions()                    # the dA this node reads may still be queued (kernels.deferred_reductions)
         idx = [i for i, g in enumerate(grads) if g is not None]
         prods = torch._foreach_mul([grads[i] for i in idx], [As[i] for i in idx]) if idx else []
         out = [None] * len(As)
@@ -216,6 +218,7 @@ class precomputed_A:
             for m in self.mods:
                 m._A_pre = {}
             for (m, suffix), A in zip(slots, As):
+                A._cm_batched_A = True          # lets the inner block queue its dA reduction (see _NegExpMany.backward)
                 m._A_pre[suffix] = A
         return self
 

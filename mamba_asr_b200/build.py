@@ -21,7 +21,7 @@ OBJDIR = os.path.join(PKG, "build")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libconmamba_b200.so")
 
-SOURCES = ["scan_fwd.cu", "scan_fwd_cl.cu", "scan_fwd_sp.cu", "scan_fwd_lc.cu", "scan_fwd_wg.cu", "scan_bwd.cu", "scan_bwd_cl.cu", "scan_bwd_sp.cu", "scan_bwd_lc.cu", "scan_bwd_wg.cu", "conv.cu", "fbank.cu", "fbank_dft.cu", "layernorm.cu", "dwconv.cu", "colsum.cu", "step.cu", "fused_ln.cu", "act.cu", "tsmm.cu", "ln_act.cu", "optim.cu", "ctc.cu", "stem.cu"]
+SOURCES = ["scan_fwd.cu", "scan_fwd_cl.cu", "scan_fwd_sp.cu", "scan_fwd_lc.cu", "scan_fwd_wg.cu", "scan_bwd.cu", "scan_bwd_cl.cu", "scan_bwd_sp.cu", "scan_bwd_lc.cu", "scan_bwd_wg.cu", "conv.cu", "fbank.cu", "fbank_dft.cu", "layernorm.cu", "dwconv.cu", "colsum.cu", "step.cu", "fused_ln.cu", "act.cu", "tsmm.cu", "ln_act.cu", "optim.cu", "ctc.cu", "stem.cu", "reduce.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "--extended-lambda",

@@ -158,6 +158,7 @@ extern "C" int cm_abi_sizeof(int32_t which) {
     case 16: return (int)sizeof(cm_ctc_args);
     case 17: return (int)sizeof(cm_stem_args);
     case 18: return (int)sizeof(cm_act_args);
+    case 19: return (int)sizeof(cm_reduce_job2);
     default: return CM_ERR_BAD_ARG;
   }
 }

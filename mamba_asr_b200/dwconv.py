@@ -35,11 +35,11 @@ class _DwConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = K.dwconv_forward(dy, w2, None, Kk - 1 - ctx.pad_left, flip=True)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dw2, db2 = K.dwconv_backward_weight(x, dy, Kk, ctx.pad_left, need_bias=ctx.has_bias)
+            dw2, db2 = K.dwconv_backward_weight(x, dy, Kk, ctx.pad_left, need_bias=ctx.has_bias, defer=True)
             if ctx.needs_input_grad[1]:
-                dw = dw2.view(ctx.w_shape).to(ctx.w_dtype)
+                dw = K.grad_cast(dw2.view(ctx.w_shape), ctx.w_dtype)
             if ctx.has_bias and ctx.needs_input_grad[2]:
-                db = db2.to(ctx.b_dtype)
+                db = K.grad_cast(db2, ctx.b_dtype)
         return dx, dw, db, None
 
 

@@ -65,18 +65,110 @@ def _call(name, fn, *args, tag=None):
     _TIMING.setdefault((name, tag), []).append((s, e))
 
 
-def reduce_many(jobs):
-    """cm_reduce_multi: jobs = [(part (rows, cols) fp32 contiguous, out (cols,) fp32)], batched 8 per launch."""
+def grad_cast(t, dtype):
+    """``t.to(dtype)`` for a gradient that may still be queued (deferred_reductions): a real cast reads it, so the queue is
+    run first; the usual fp32 -> fp32 case returns ``t`` itself and leaves the queue alone."""
+    if t is None or t.dtype == dtype:
+        return t
+    flush_reductions()
+    return t.to(dtype)
+
+
+# ---- fixed-order sums of partial buffers, optionally queued until the end of the backward pass --------------------------
+# A job is (part, out) - part (rows, ...) fp32 contiguous, out fp32 with part[0].numel() elements - or
+# (part, out, rows, cols, stride) with explicit geometry (part[r * stride + c], c < cols).
+_DEFER = False          # set by deferred_reductions()
+_DEFER_POISON = os.environ.get("CM_DEFER_POISON") not in (None, "", "0")   # tests: NaN-fill queued outputs until the flush
+_PENDING = []
+_CB_QUEUED = False
+
+
+class deferred_reductions:
+    """Context manager: inside it, ``reduce_many(jobs, defer=True)`` calls made during a backward pass are queued and run in
+    ONE batch (cm_reduce_batch, 64 jobs per launch) by an autograd-engine callback at the end of that pass, instead of one
+    reducer launch per operator (440 launches of ~4 us per ConMamba-large step).
+
+    Contract (why this is opt-in): a queued output holds no data until the pass ends, so it must not be READ inside the pass.
+    The library's own backward functions only mark jobs whose output goes straight to a parameter gradient; the caller
+    guarantees that nothing accumulates into those gradients during the pass: use it around ``torch.autograd.grad`` /
+    ``torch.cuda.make_graphed_callables`` capture (gradients are handed out at the end of the pass), with every parameter
+    used by one autograd node.  Plain ``loss.backward()`` into existing ``.grad`` tensors (accumulation) is NOT covered."""
+
+    def __init__(self, enabled=True):
+        self.enabled = enabled
+
+    def __enter__(self):
+        global _DEFER
+        self.prev, _DEFER = _DEFER, self.enabled
+        return self
+
+    def __exit__(self, *exc):
+        global _DEFER
+        _DEFER = self.prev
+        flush_reductions()
+        return False
+
+
+def _norm_job(job):
+    if len(job) == 2:
+        part, out = job
+        rows = part.shape[0]
+        cols = part.numel() // rows
+        return part, out, part.data_ptr(), out.data_ptr(), rows, cols, cols
+    part, out, rows, cols, stride, off = job
+    return part, out, part.data_ptr() + 4 * off, out.data_ptr(), rows, cols, stride
+
+
+def _launch_reduce(jobs):
     lib = cabi.lib()
     st = cabi.stream_ptr()
-    for i in range(0, len(jobs), cabi.CM_REDUCE_MAX_JOBS):
-        chunk = jobs[i:i + cabi.CM_REDUCE_MAX_JOBS]
-        arr = (cabi.ReduceJob * len(chunk))()
-        for k, (part, out) in enumerate(chunk):
-            rows = part.shape[0]
-            arr[k].part, arr[k].out = part.data_ptr(), out.data_ptr()
-            arr[k].rows, arr[k].cols = rows, part.numel() // rows
-        _call("cm_reduce_multi", lib.cm_reduce_multi, arr, len(chunk), st)
+    for i in range(0, len(jobs), cabi.CM_REDUCE_BATCH_MAX):
+        chunk = jobs[i:i + cabi.CM_REDUCE_BATCH_MAX]
+        arr = (cabi.ReduceJob2 * len(chunk))()
+        for k, (_, _, pp, op, rows, cols, stride) in enumerate(chunk):
+            arr[k].part, arr[k].out, arr[k].rows, arr[k].cols, arr[k].stride = pp, op, rows, cols, stride
+        _call("cm_reduce_batch", lib.cm_reduce_batch, arr, len(chunk), st)
+
+
+def flush_reductions():
+    """Run every queued reduction now (the engine callback; also safe to call by hand)."""
+    global _CB_QUEUED
+    _CB_QUEUED = False
+    if _PENDING:
+        jobs = list(_PENDING)
+        _PENDING.clear()
+        _launch_reduce(jobs)
+
+
+def reduce_many(jobs, defer=False):
+    """Fixed-order column sums of partial buffers (cm_reduce_batch).  ``defer=True`` marks outputs that nobody reads before the
+    end of the current backward pass: under ``deferred_reductions()`` they are queued (see there), otherwise run now."""
+    global _CB_QUEUED
+    jobs = [_norm_job(j) for j in jobs]
+    if not jobs:
+        return
+    if defer and _DEFER:
+        if not _CB_QUEUED:
+            try:
+                torch.autograd.Variable._execution_engine.queue_callback(flush_reductions)
+                _CB_QUEUED = True
+            except RuntimeError:                    # not inside a backward pass: nothing would ever flush the queue
+                pass
+        if _CB_QUEUED:
+            if _DEFER_POISON:
+                for j in jobs:
+                    j[1].view(-1)[:j[5]].fill_(float("nan"))
+            _PENDING.extend(jobs)                   # the tensors stay referenced (and their memory theirs) until the flush
+            return
+    _launch_reduce(jobs)
+
+
+def sum_leading(part, defer=False):
+    """part.sum(0) for a contiguous fp32 (rows, ...) CUDA tensor through the batched reducer (the split-K weight-gradient
+    sums: 219 at::reduce_kernel launches per ConMamba-large step otherwise)."""
+    out = torch.empty(part.shape[1:], dtype=torch.float32, device=part.device)
+    reduce_many([(part, out)], defer=defer)
+    return out
 
 
 def _require_cuda(t, name, like=None):
@@ -223,7 +315,7 @@ def scan_forward(dirs, z=None, out_scale=1.0, delta_softplus=False, need_ckpt=Fa
 
 
 def scan_backward(dirs, ckpts, dout, z=None, out_pre=None, out_scale=1.0, delta_softplus=False, lanes=0,
-                  dz_out=None, dBC_like=None):
+                  dz_out=None, dBC_like=None, defer=False, defer_dA=False):
     """Fused selective scan backward (cm_scan_bwd + deterministic reducers).
 
     Returns dict(du[list], ddelta[list], dz, dB[list], dC[list], dA[list], dD[list], dbias[list]).
@@ -287,12 +379,14 @@ def scan_backward(dirs, ckpts, dout, z=None, out_pre=None, out_scale=1.0, delta_
     st = cabi.stream_ptr()
     _call("cm_scan_bwd", lib.cm_scan_bwd, C.byref(a), st, tag=(Bt, D, L, len(dirs)))
 
-    jobs = []
+    # defer: dD / d(delta_bias) go straight to parameter gradients (see deferred_reductions); dA usually does not - the node
+    # that made A = -exp(A_log) reads it - unless the caller says so (defer_dA: that node runs the queue before reading)
+    jobs, jobs_now = [], []
     outs = []
     for r, d in enumerate(dirs):
         bc_part, dA_part, dD_part, db_part = parts[r]
         dA = torch.empty((D, 16), dtype=torch.float32, device=dev)
-        jobs.append((dA_part, dA))
+        (jobs if defer_dA else jobs_now).append((dA_part, dA))
         dD = db = dBC = None
         if dD_part is not None:
             dD = torch.empty((D,), dtype=torch.float32, device=dev)
@@ -302,9 +396,10 @@ def scan_backward(dirs, ckpts, dout, z=None, out_pre=None, out_scale=1.0, delta_
             jobs.append((db_part, db))
         if const_bc:
             dBC = torch.empty((D, 32), dtype=torch.float32, device=dev)
-            jobs.append((bc_part, dBC))
+            jobs_now.append((bc_part, dBC))                   # constant B / C gradients are cast (read) below
         outs.append((dA, dD, db, dBC))
-    reduce_many(jobs)
+    reduce_many(jobs, defer=defer)
+    reduce_many(jobs_now)
     for r, d in enumerate(dirs):
         bc_part = parts[r][0]
         dA, dD, db, dBC = outs[r]
@@ -379,7 +474,7 @@ def conv_forward(x, dirs, silu=True, outs=None):
     return res
 
 
-def conv_backward(x, dirs, douts, silu=True, dx_out=None):
+def conv_backward(x, dirs, douts, silu=True, dx_out=None, defer=False):
     """cm_conv_bwd.  Returns (dx, [dweight (D, W) fp32], [dbias (D,) fp32 or None])."""
     lib, a, keep, (Bt, D, L, W) = _conv_common(x, dirs, silu)
     dev = x.device
@@ -413,7 +508,7 @@ def conv_backward(x, dirs, douts, silu=True, dx_out=None):
             dbs.append(db)
         else:
             dbs.append(None)
-    reduce_many(jobs)
+    reduce_many(jobs, defer=defer)
     return dx, dws, dbs
 
 
@@ -611,7 +706,7 @@ def layernorm_forward(x2d, weight, bias, eps, out_dtype):
     return y, mean, rstd
 
 
-def layernorm_backward(x2d, dy2d, weight, mean, rstd, need_wgrad=True):
+def layernorm_backward(x2d, dy2d, weight, mean, rstd, need_wgrad=True, defer=False):
     """cm_layernorm_bwd + deterministic reduction of the per-CTA dgamma / dbeta partial rows.
     Returns (dx in x's dtype, dgamma fp32 (C,), dbeta fp32 (C,))."""
     lib = cabi.lib()
@@ -636,7 +731,7 @@ def layernorm_backward(x2d, dy2d, weight, mean, rstd, need_wgrad=True):
         return dx, None, None
     dg = torch.empty((Cn,), dtype=torch.float32, device=x2d.device)
     db = torch.empty((Cn,), dtype=torch.float32, device=x2d.device)
-    reduce_many([(dg_part, dg), (db_part, db)])
+    reduce_many([(dg_part, dg), (db_part, db)], defer=defer)
     return dx, dg, db
 
 
@@ -689,7 +784,8 @@ def ln_act_forward(x2d, weight, bias, eps, slope=0.01, act="leaky_relu", pre_bia
     return y, mean, rstd
 
 
-def ln_act_backward(x2d, dy2d, weight, bias, mean, rstd, slope=0.01, act="leaky_relu", pre_bias=None, need_wgrad=True):
+def ln_act_backward(x2d, dy2d, weight, bias, mean, rstd, slope=0.01, act="leaky_relu", pre_bias=None, need_wgrad=True,
+                    defer=False):
     """cm_ln_act_bwd + deterministic reduction of the per-CTA dgamma / dbeta partial rows.
     Returns (dx in x's dtype (= the gradient of x + pre_bias), dgamma fp32 (C,), dbeta fp32 (C,))."""
     lib = cabi.lib()
@@ -708,7 +804,7 @@ def ln_act_backward(x2d, dy2d, weight, bias, mean, rstd, slope=0.01, act="leaky_
         return dx, None, None
     dg = torch.empty((Cn,), dtype=torch.float32, device=x2d.device)
     db = torch.empty((Cn,), dtype=torch.float32, device=x2d.device)
-    reduce_many([(dg_part, dg), (db_part, db)])
+    reduce_many([(dg_part, dg), (db_part, db)], defer=defer)
     return dx, dg, db
 
 
@@ -756,7 +852,7 @@ def stem_forward(feats, weight, bias, gamma, beta, eps, slope, out_dtype):
     return y, mean, rstd
 
 
-def stem_backward(feats, dy, weight, bias, gamma, beta, mean, rstd, slope):
+def stem_backward(feats, dy, weight, bias, gamma, beta, mean, rstd, slope, defer=False):
     """cm_stem_bwd + one deterministic reduction launch.  Returns (dweight (C, 1, 3, 3), dbias (C), dgamma, dbeta (F', C)) fp32."""
     lib = cabi.lib()
     Bt, T, Fd = feats.shape
@@ -779,7 +875,7 @@ def stem_backward(feats, dy, weight, bias, gamma, beta, mean, rstd, slope):
     db = torch.empty((Fo, Cn), dtype=torch.float32, device=dev)
     dw = torch.empty((Cn, 1, 3, 3), dtype=torch.float32, device=dev)
     dcb = torch.empty((Cn,), dtype=torch.float32, device=dev)
-    reduce_many([(dg_part, dg), (db_part, db), (dw_part, dw), (dcb_part, dcb)])
+    reduce_many([(dg_part, dg), (db_part, db), (dw_part, dw), (dcb_part, dcb)], defer=defer)
     return dw, dcb, dg, db
 
 
@@ -849,7 +945,7 @@ def add_ln_forward(a2d, b2d, weight, bias, eps, alpha, p_drop, seed, call_id, ou
 
 
 def add_ln_backward(s2d, dy2d, ds2d, weight, mean, rstd, saved, alpha, p_drop, b_dtype, need_db=True, need_wgrad=True,
-                    need_dbsum=False):
+                    need_dbsum=False, defer=False):
     """cm_add_ln_bwd + deterministic reduction of the dgamma / dbeta partial rows.  ``saved`` as returned by
     ``add_ln_forward``.  Returns (da in s's dtype, db in b_dtype or None, dgamma fp32 (C,), dbeta fp32 (C,)); with
     ``need_dbsum`` a fifth value: the fp32 column sums of db (None when the geometry is outside the quad kernels)."""
@@ -901,7 +997,7 @@ def add_ln_backward(s2d, dy2d, ds2d, weight, mean, rstd, saved, alpha, p_drop, b
         dbs = torch.empty((Cn,), dtype=torch.float32, device=dev)
         jobs.append((dbs_part, dbs))
     if jobs:
-        reduce_many(jobs)
+        reduce_many(jobs, defer=defer)
     if need_dbsum:
         return da, db, dg, dbt, dbs
     return da, db, dg, dbt
@@ -937,7 +1033,7 @@ def gelu_dropout_forward(x, p_drop, seed, call_id, store_mask=None):
     return y, saved
 
 
-def gelu_dropout_backward(x, dy, saved, p_drop, colsum_cols=0):
+def gelu_dropout_backward(x, dy, saved, p_drop, colsum_cols=0, defer=False):
     """cm_gelu_dropout_bwd_v2.  ``saved`` as returned by ``gelu_dropout_forward``.  colsum_cols > 0: also returns the fp32
     column sums of dx viewed as (-1, colsum_cols) (None if that width is outside the fused envelope)."""
     lib = cabi.lib()
@@ -962,7 +1058,7 @@ def gelu_dropout_backward(x, dy, saved, p_drop, colsum_cols=0):
     if part is None:
         return dx, None
     cs = torch.empty((colsum_cols,), dtype=torch.float32, device=x.device)
-    reduce_many([(part, cs)])
+    reduce_many([(part, cs)], defer=defer)
     return dx, cs
 
 
@@ -979,7 +1075,7 @@ def tsmm_supported(a2d, b2d):
     return a2d.stride(0) % 8 == 0 and b2d.stride(0) % 8 == 0 and a2d.data_ptr() % 16 == 0 and b2d.data_ptr() % 16 == 0
 
 
-def tsmm(a2d, b2d):
+def tsmm(a2d, b2d, defer=False):
     """a2d^T @ b2d -> (M, N) fp32 through cm_tsmm (tensor-core partial blocks per 256-row chunk) and the deterministic
     reducer.  a2d (rows, M), b2d (rows, N <= 64), 16-bit, unit column stride."""
     lib = cabi.lib()
@@ -992,7 +1088,7 @@ def tsmm(a2d, b2d):
     if n_part == 1:
         return part.view(M, N)
     out = torch.empty((M * N,), dtype=torch.float32, device=a2d.device)
-    reduce_many([(part, out)])
+    reduce_many([(part, out)], defer=defer)
     return out.view(M, N)
 
 
@@ -1029,7 +1125,7 @@ def dwconv_forward(x_blc, weight_ck, bias, pad_left, flip=False):
     return y
 
 
-def dwconv_backward_weight(x_blc, dy_blc, ksize, pad_left, need_bias=True):
+def dwconv_backward_weight(x_blc, dy_blc, ksize, pad_left, need_bias=True, defer=False):
     """cm_dwconv_bwd_weight + deterministic reduction: returns (dweight (C, K) fp32, dbias (C,) fp32 or None)."""
     lib = cabi.lib()
     Bt, L, Cn = x_blc.shape
@@ -1046,12 +1142,12 @@ def dwconv_backward_weight(x_blc, dy_blc, ksize, pad_left, need_bias=True):
     if need_bias:
         db = torch.empty((Cn,), dtype=torch.float32, device=x_blc.device)
         jobs.append((db_part, db))
-    reduce_many(jobs)
+    reduce_many(jobs, defer=defer)
     return dw.view(Cn, ksize), db
 
 
 # ------------------------------------------------------------------------------------------------ column sums (bias grads)
-def colsum(x2d):
+def colsum(x2d, defer=False):
     """fp32 column sums of a (rows, cols) CUDA matrix with unit column stride (cm_colsum + fixed-order reduction).
     Returns None when the shape is outside the kernel's envelope (odd cols / stride): the caller uses torch.sum."""
     lib = cabi.lib()
@@ -1064,7 +1160,7 @@ def colsum(x2d):
     _call("cm_colsum", lib.cm_colsum, x2d.data_ptr(), rows, cols, x2d.stride(0), cabi.dtype_code(x2d.dtype), part.data_ptr(),
           cabi.stream_ptr())
     out = torch.empty((cols,), dtype=torch.float32, device=x2d.device)
-    reduce_many([(part, out)])
+    reduce_many([(part, out)], defer=defer)
     return out
 
 

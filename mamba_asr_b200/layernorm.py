@@ -34,9 +34,9 @@ class _LayerNormFn(torch.autograd.Function):
         x2, weight, mean, rstd = ctx.saved_tensors
         Cn = x2.shape[1]
         need_w = weight is not None and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
-        dx, dg, db = K.layernorm_backward(x2, dy.reshape(-1, Cn), weight, mean, rstd, need_wgrad=need_w)
-        dgw = dg.to(weight.dtype) if (need_w and ctx.needs_input_grad[1]) else None
-        dbw = db.to(weight.dtype) if (need_w and ctx.has_bias and ctx.needs_input_grad[2]) else None
+        dx, dg, db = K.layernorm_backward(x2, dy.reshape(-1, Cn), weight, mean, rstd, need_wgrad=need_w, defer=True)
+        dgw = K.grad_cast(dg, weight.dtype) if (need_w and ctx.needs_input_grad[1]) else None
+        dbw = K.grad_cast(db, weight.dtype) if (need_w and ctx.has_bias and ctx.needs_input_grad[2]) else None
         return dx.view(ctx.x_shape), dgw, dbw, None, None
 
 
@@ -92,7 +92,7 @@ class _LayerNormActFn(torch.autograd.Function):
         x2, w, b, pre_bias, mean, rstd = ctx.saved_tensors
         need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
         dx, dg, db = K.ln_act_backward(x2, dy.reshape(-1, x2.shape[1]), w, b, mean, rstd, ctx.slope, ctx.act, pre_bias,
-                                       need_wgrad=need_w)
+                                       need_wgrad=need_w, defer=True)
         dpb = None
         if pre_bias is not None and ctx.needs_input_grad[3]:
             cs = K.colsum(dx)                                     # (n_norm,) fp32, fixed-order sums
@@ -153,7 +153,7 @@ class _StemFn(torch.autograd.Function):
         feats, weight, bias, gamma, beta, mean, rstd = ctx.saved_tensors
         if ctx.needs_input_grad[0]:
             raise NotImplementedError("conv_ln_act_stem: no gradient with respect to the features (they are the network input)")
-        dw, dcb, dg, db = K.stem_backward(feats, dy, weight, bias, gamma, beta, mean, rstd, ctx.slope)
+        dw, dcb, dg, db = K.stem_backward(feats, dy, weight, bias, gamma, beta, mean, rstd, ctx.slope, defer=True)
         return (None, dw if ctx.needs_input_grad[1] else None, dcb if bias is not None and ctx.needs_input_grad[2] else None,
                 dg if ctx.needs_input_grad[3] else None, db if ctx.needs_input_grad[4] else None, None, None, None)
 
@@ -243,17 +243,18 @@ class _AddDropoutLayerNormFn(torch.autograd.Function):
         need_bb = ctx.b_bias_dtype is not None and ctx.needs_input_grad[8] and ctx.b_dtype is not None
         da, db, dg, dbt, dbs = K.add_ln_backward(s, dy.reshape(-1, Cn), None if ds is None else ds.reshape(-1, Cn), weight,
                                                  mean, rstd, saved, ctx.alpha, ctx.p_drop, ctx.b_dtype or s.dtype,
-                                                 need_db=ctx.b_dtype is not None, need_wgrad=need_w, need_dbsum=True)
+                                                 need_db=ctx.b_dtype is not None, need_wgrad=need_w, need_dbsum=True,
+                                                 defer=True)
         dbb = None
         if need_bb:
             if dbs is None:                                      # geometry outside the quad kernels: the separate pass
-                dbs = K.colsum(db)
+                dbs = K.colsum(db, defer=True)
                 if dbs is None:
                     dbs = db.float().sum(0)
-            dbb = dbs.to(ctx.b_bias_dtype)
+            dbb = K.grad_cast(dbs, ctx.b_bias_dtype)
         return (da.view(ctx.shape), None if db is None else db.view(ctx.shape),
-                dg.to(weight.dtype) if (need_w and ctx.needs_input_grad[2]) else None,
-                dbt.to(weight.dtype) if (need_w and ctx.has_bias and ctx.needs_input_grad[3]) else None,
+                K.grad_cast(dg, weight.dtype) if (need_w and ctx.needs_input_grad[2]) else None,
+                K.grad_cast(dbt, weight.dtype) if (need_w and ctx.has_bias and ctx.needs_input_grad[3]) else None,
                 None, None, None, None, dbb)
 
 
@@ -316,10 +317,10 @@ class _BiasGradRoute(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         d2 = dy.reshape(-1, dy.shape[-1])
-        cs = K.colsum(d2 if d2.stride(-1) == 1 else d2.contiguous()) if d2.is_cuda else None
+        cs = K.colsum(d2 if d2.stride(-1) == 1 else d2.contiguous(), defer=True) if d2.is_cuda else None
         if cs is None:
             cs = d2.float().sum(0)
-        return dy, cs.to(ctx.bias_dtype)
+        return dy, K.grad_cast(cs, ctx.bias_dtype)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -343,12 +344,12 @@ class _GeluDropoutFn(torch.autograd.Function):
         if ctx.bias_dtype is None or not ctx.needs_input_grad[2]:
             return K.gelu_dropout_backward(x, dy, saved, ctx.p_drop), None, None
         cols = x.shape[-1]
-        dx, cs = K.gelu_dropout_backward(x, dy, saved, ctx.p_drop, colsum_cols=cols)
+        dx, cs = K.gelu_dropout_backward(x, dy, saved, ctx.p_drop, colsum_cols=cols, defer=True)
         if cs is None:
-            cs = K.colsum(dx.reshape(-1, cols))
+            cs = K.colsum(dx.reshape(-1, cols), defer=True)
             if cs is None:
                 cs = dx.reshape(-1, cols).float().sum(0)
-        return dx, None, cs.to(ctx.bias_dtype)
+        return dx, None, K.grad_cast(cs, ctx.bias_dtype)
 
 
 def gelu_dropout(x, p_drop=0.0, training=True, bias_for_grad=None):

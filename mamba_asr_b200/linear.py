@@ -105,7 +105,7 @@ def _wgrad_f32(dy2, x2):
         return torch.mm(dy2.t(), x2, out_dtype=torch.float32)          # fp32 straight out of the GEMM: no cast kernel
     d3 = dy2.reshape(ns, rows // ns, dy2.shape[1])
     x3 = x2.reshape(ns, rows // ns, x2.shape[1])
-    return torch.bmm(d3.transpose(1, 2), x3, out_dtype=torch.float32).sum(0)
+    return K.sum_leading(torch.bmm(d3.transpose(1, 2), x3, out_dtype=torch.float32), defer=True)   # queued under deferral
 
 
 class _LinearFn(torch.autograd.Function):
@@ -133,8 +133,8 @@ class _LinearFn(torch.autograd.Function):
             else:
                 dw = torch.mm(dy2.t(), x2).to(ctx.w_dtype)
         if ctx.b_dtype is not None and ctx.needs_input_grad[2]:
-            s = K.colsum(dy2 if dy2.stride(-1) == 1 else dy2.contiguous())
-            db = (s if s is not None else dy2.sum(0)).to(ctx.b_dtype)
+            s = K.colsum(dy2 if dy2.stride(-1) == 1 else dy2.contiguous(), defer=True)
+            db = K.grad_cast(s if s is not None else dy2.sum(0), ctx.b_dtype)
         return dx, dw, db, None, None
 
 

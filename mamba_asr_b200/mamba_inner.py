@@ -48,25 +48,46 @@ _USE_TSMM = True      # A/B switch: CM_NO_TSMM=1 (or this flag) restores the cuB
 _TSMM_MAX_ELEMS = 1 << 22
 
 
-def _wgrad(a, b, nsplit):
+def _wgrad(a, b, nsplit, defer=False, row_perm=None):
     """a^T @ b for tall-skinny operands (a: (K, M), b: (K, N), K = batch * L in the tens of thousands, M or N <= 64), fp32.
     16-bit operands go to the sm_100a kernel cm_tsmm (tensor-core partial blocks per row chunk + the deterministic
     reducer); otherwise one bmm over `nsplit` row blocks plus a sum (as a single GEMM cuBLAS picks a serial-K sm_75 CUTLASS
-    kernel for these shapes on B200: 85 us per call at K = 32064, measured)."""
+    kernel for these shapes on B200: 85 us per call at K = 32064, measured).
+    ``defer``: the result goes straight to a parameter gradient (kernels.deferred_reductions).  ``row_perm`` = (r0, r1, r2):
+    return rows [r1:r2] followed by rows [r0:r1] of the product (x_proj's rows back in the reference's [dt | B | C] order) -
+    formed by the reducer itself where the split path runs, by a copy otherwise."""
+    def permuted(full):
+        if row_perm is None:
+            return full
+        r0, r1, r2 = row_perm
+        return torch.cat([full[r1:r2], full[r0:r1]], dim=0)
+
     # measured in the bench step on B200: 16.15 vs 16.27 ms with cm_tsmm at 12032 x 288 (ConMamba-small), 54.9 vs 54.6 ms at
     # 32064 x 512 (ConMamba-large) - the kernel takes the shapes where it wins, the cuBLAS bmm split keeps the rest
     if _USE_TSMM and os.environ.get("CM_NO_TSMM") is None and a.shape[0] * max(a.shape[1], b.shape[1]) <= _TSMM_MAX_ELEMS:
         if K.tsmm_supported(a, b):
-            return K.tsmm(a, b)
+            return permuted(K.tsmm(a, b, defer=defer and row_perm is None))
         if K.tsmm_supported(b, a):
-            return K.tsmm(b, a).t()
+            return permuted(K.tsmm(b, a, defer=defer and row_perm is None).t())
     Kr = a.shape[0]
     od = {} if a.dtype == torch.float32 else {"out_dtype": torch.float32}   # fp32 straight out of the GEMM
     if nsplit <= 1 or Kr % nsplit != 0:
-        return torch.mm(a.t(), b, **od)
+        return permuted(torch.mm(a.t(), b, **od))
     a3 = a.unflatten(0, (nsplit, Kr // nsplit))
     b3 = b.unflatten(0, (nsplit, Kr // nsplit))
-    return torch.bmm(a3.transpose(1, 2), b3, **od).sum(0)
+    part = torch.bmm(a3.transpose(1, 2), b3, **od)
+    if part.dtype != torch.float32 or not part.is_cuda or not part.is_contiguous():
+        return permuted(part.sum(0))
+    if row_perm is None:
+        return K.sum_leading(part, defer=defer)
+    r0, r1, r2 = row_perm
+    M, Nc = part.shape[1], part.shape[2]
+    out = torch.empty((r2 - r0, Nc), dtype=torch.float32, device=part.device)
+    flat = out.view(-1)
+    n1 = (r2 - r1) * Nc
+    K.reduce_many([(part, flat[:n1], nsplit, n1, M * Nc, r1 * Nc),
+                   (part, flat[n1:], nsplit, (r1 - r0) * Nc, M * Nc, r0 * Nc)], defer=defer)
+    return out
 
 
 def inner_forward(xz, ndir, out_scale, reverse0, params, need_grad=False, need_last_state=False):
@@ -127,6 +148,8 @@ class MambaInnerCL(torch.autograd.Function):
         y, saved, rev, _ = inner_forward(xz, ndir, out_scale, reverse0, params, need_grad=need_grad)
         if need_grad:
             ctx.ndir, ctx.out_scale, ctx.rev = ndir, out_scale, rev
+            # A made by bimamba._NegExpMany: that node runs the reduction queue before it reads dA
+            ctx.defer_dA = all(getattr(params[r * 7 + 4], "_cm_batched_A", False) for r in range(ndir))
             ctx.save_for_backward(*saved)
         return y
 
@@ -163,7 +186,8 @@ class MambaInnerCL(torch.autograd.Function):
                 dbc_like.append((_as_bdl(dv[..., :N]), _as_bdl(dv[..., N:2 * N])))
                 dx_dbls.append(dxd)
             g = K.scan_backward(scan_dirs, ckpts, _as_bdl(dy), z=z, out_pre=out_pre, out_scale=ctx.out_scale,
-                                delta_softplus=True, dz_out=_as_bdl(dxz[..., D:]), dBC_like=dbc_like)
+                                delta_softplus=True, dz_out=_as_bdl(dxz[..., D:]), dBC_like=dbc_like, defer=True,
+                                defer_dA=ctx.defer_dA)
             grads = []
             conv_dirs, conv_douts = [], []
             for r, p in enumerate(P):
@@ -173,18 +197,18 @@ class MambaInnerCL(torch.autograd.Function):
                 ddelta = g["ddelta"][r].transpose(1, 2).reshape(Bt * L, D)
                 du = g["du"][r].transpose(1, 2).reshape(Bt * L, D)
                 dxd = dx_dbls[r]
-                d_dtw = _wgrad(ddelta, x_dbls[r][:, 2 * N:], Bt)[:, :R]               # (D, R)
+                d_dtw = _wgrad(ddelta, x_dbls[r][:, 2 * N:], Bt, defer=True)[:, :R]   # (D, R)
                 dxd[:, 2 * N:] = torch.mm(ddelta, wdt[r])                            # (B*L, Rp); pad columns get 0
-                d_xw_perm = _wgrad(dxd, u_mem, Bt)                                   # (2N + Rp, D)
-                d_xw = torch.cat([d_xw_perm[2 * N:2 * N + R], d_xw_perm[:2 * N]], dim=0)   # back to [dt | B | C] rows
+                d_xw = _wgrad(dxd, u_mem, Bt, defer=True, row_perm=(0, 2 * N, 2 * N + R))   # (R + 2N, D): [dt | B | C] rows
                 du.addmm_(dxd, wx[r])                                                # + x_proj back-prop (:282)
                 conv_dirs.append(dict(weight=p[0][:, 0, :], bias=p[1], anticausal=rev[r]))
                 conv_douts.append(g["du"][r])
-                grads.append([None, None, d_xw.to(p[2].dtype), d_dtw.to(p[3].dtype), g["dA"][r].to(p[4].dtype),
+                grads.append([None, None, K.grad_cast(d_xw, p[2].dtype), K.grad_cast(d_dtw, p[3].dtype),
+                              K.grad_cast(g["dA"][r], p[4].dtype),
                               g["dD"][r], g["dbias"][r]])
-            _, dws, dbs = K.conv_backward(x, conv_dirs, conv_douts, silu=True, dx_out=_as_bdl(dxz[..., :D]))
+            _, dws, dbs = K.conv_backward(x, conv_dirs, conv_douts, silu=True, dx_out=_as_bdl(dxz[..., :D]), defer=True)
             for r, p in enumerate(P):
-                grads[r][0] = dws[r].to(p[0].dtype).unsqueeze(1)
-                grads[r][1] = None if p[1] is None else dbs[r].to(p[1].dtype)
+                grads[r][0] = K.grad_cast(dws[r], p[0].dtype).unsqueeze(1)
+                grads[r][1] = None if p[1] is None else K.grad_cast(dbs[r], p[1].dtype)
         flat = [t for gr in grads for t in gr]
         return (dxz, None, None, None, *flat)

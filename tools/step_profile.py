@@ -18,6 +18,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default=bench.DEFAULT_WORKLOAD)
     ap.add_argument("--top", type=int, default=40)
+    ap.add_argument("--graphed", action="store_true",
+                    help="profile the step bench.py times by default: forward and backward replayed as CUDA graphs, the "
+                         "backward's partial sums reduced in one batch (kernels.deferred_reductions)")
     args = ap.parse_args()
     wl = bench.WORKLOADS[args.workload]
     cfg = CONFIGS[wl["model"]]
@@ -26,6 +29,13 @@ def main():
     model.enable_param_cache()
     wav, targets = bench.make_batch(cfg, wl["batch"], wl["seconds"], 1234, dev, cfg["output_neurons"])
     wav, targets = wav.to(dev), targets.to(dev)
+    if args.graphed:
+        from mamba_asr_b200 import kernels as K
+        from mamba_asr_b200.graphs import graph_module
+        is_s2s = hasattr(model, "decoder")
+        sample = (wav,) if not is_s2s else (wav, torch.cat([torch.ones_like(targets[:, :1]), targets], dim=1))
+        with torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False), K.deferred_reductions():
+            model = graph_module(model, sample, warmup=3)
     for _ in range(3):
         model.zero_grad(set_to_none=True)
         bench.ctc_step(model, wav, targets, True)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CM_ABI_VERSION 13
+#define CM_ABI_VERSION 14
 
 /* element type of activations (u, delta, z, B, C, x, out, and their gradients) */
 enum { CM_F32 = 0, CM_BF16 = 1, CM_F16 = 2 };
@@ -572,6 +572,17 @@ int cm_stem_supported(int32_t feats, int32_t channels);
 int cm_stem_num_part(int32_t batch, int32_t frames);
 int cm_stem_fwd(const cm_stem_args* args, void* stream);
 int cm_stem_bwd(const cm_stem_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * GLU over the last dimension of a channel-last tensor (the gate of the ConMamba convolution module, reference
+ * modules/Conmamba.py:268-279: Conv1d(C, 2C, 1) -> nn.GLU):
+ *   forward   y[r, c]  = h[r, c] * sigmoid(h[r, dim + c])                                   h: rows x 2*dim, y: rows x dim
+ *   backward  dh[r, c] = dy[r, c] * s,  dh[r, dim + c] = dy[r, c] * h[r, c] * s * (1 - s),  s = sigmoid(h[r, dim + c])
+ * Strides are in elements per row; dim and the strides multiples of 8, pointers 16-byte aligned (else CM_ERR_UNSUPPORTED).
+ * ---------------------------------------------------------------------------------------------------- */
+int cm_glu_fwd(const void* h, void* y, int64_t rows, int32_t dim, int64_t h_stride, int64_t y_stride, int32_t dtype, void* stream);
+int cm_glu_bwd(const void* h, const void* dy, void* dh, int64_t rows, int32_t dim, int64_t h_stride, int64_t dy_stride,
+               int64_t dh_stride, int32_t dtype, void* stream);
 
 /* sizeof() of the argument structs, for binding self-checks: 0 cm_tensor3, 1 cm_scan_dir, 2 cm_scan_fwd_args,
  * 3 cm_scan_bwd_dir, 4 cm_scan_bwd_args, 5 cm_conv_dir, 6 cm_conv_args, 7 cm_fbank_args, 8 cm_reduce_job,

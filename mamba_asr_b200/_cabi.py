@@ -17,7 +17,7 @@ CM_ERR_BAD_ARG, CM_ERR_UNSUPPORTED = -1, -2
 CM_FLAG_DELTA_SOFTPLUS = 1
 CM_FLAG_SILU = 1
 CM_SCAN_CKPT_STEPS = 8
-CM_ABI_VERSION = 13
+CM_ABI_VERSION = 14
 CM_LN_ACT_LEAKY_RELU, CM_LN_ACT_GELU = 0, 1
 
 EXPORTS = (
@@ -30,7 +30,7 @@ EXPORTS = (
     "cm_ln_act_num_part", "cm_ln_act_fwd", "cm_ln_act_bwd", "cm_optim_num_part", "cm_sumsq_partial", "cm_adamw_step",
     "cm_fbank_wav_supported", "cm_fbank_wav_logmel", "cm_ctc_workspace_floats", "cm_ctc_loss",
     "cm_stem_supported", "cm_stem_num_part", "cm_stem_fwd", "cm_stem_bwd",
-    "cm_reduce_batch",
+    "cm_reduce_batch", "cm_glu_fwd", "cm_glu_bwd",
     "cm_add_ln_dbsum_supported", "cm_add_ln_num_part", "cm_act_colsum_supported", "cm_act_num_part", "cm_gelu_dropout_fwd_v2", "cm_gelu_dropout_bwd_v2",
 )
 CM_REDUCE_MAX_JOBS = 8
@@ -290,6 +290,9 @@ def lib():
         L.cm_ln_act_fwd.argtypes = [C.POINTER(LnActArgs), C.c_void_p]
         L.cm_ln_act_bwd.argtypes = [C.POINTER(LnActArgs), C.c_void_p]
         L.cm_reduce_batch.argtypes = [C.POINTER(ReduceJob2), C.c_int32, C.c_void_p]
+        L.cm_glu_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]
+        L.cm_glu_bwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64,
+                                 C.c_int32, C.c_void_p]
         L.cm_optim_num_part.argtypes = [C.c_int64]
         L.cm_sumsq_partial.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.cm_adamw_step.argtypes = [C.POINTER(AdamWArgs), C.c_void_p]

@@ -24,7 +24,7 @@ from .bimamba import Mamba as BiMamba
 from .bimamba import UniMamba as Mamba
 from .dwconv import depthwise_conv1d
 from .kernels import DWCONV_KSIZES, gelu_dropout_supported
-from .layernorm import FusedLayerNorm, _BiasGradRoute, add_dropout_layer_norm, gelu_dropout, layer_norm_act
+from .layernorm import FusedLayerNorm, _BiasGradRoute, add_dropout_layer_norm, gelu_dropout, glu, layer_norm_act
 from .linear import BiasGradLinear, linear as _linear
 
 LAYER_NORM_EPS = 1e-6        # reference ConMambaConstants.LAYER_NORM_EPS (Conmamba.py:687)
@@ -127,7 +127,7 @@ def _conv_body(self, normed, final_dropout=True, out_bias_grad=True):
     trailing Dropout to the caller (the encoder layer fuses it into the next add + LayerNorm); ``out_bias_grad=False``
     likewise leaves the gradient of the last Linear's bias to that kernel (``b_bias=self.after_conv[2].bias``)."""
     pw = self.bottleneck[0]                                           # pointwise conv = Linear over channel-last rows
-    out = F.glu(_linear(normed, pw.weight.squeeze(-1), pw.bias), dim=-1)
+    out = glu(_linear(normed, pw.weight.squeeze(-1), pw.bias))      # cm_glu_fwd / cm_glu_bwd
     out = depthwise_conv1d(out, self.conv.weight, self.conv.bias, pad_left=self.padding)
     norm, act = self.after_conv[0], self.after_conv[1]
     # LayerNorm -> GELU as one cm_ln_act kernel each way is opt-in (CM_FUSE_LN_GELU=1): at these narrow rows (144 / 256

@@ -214,6 +214,118 @@ static int act_bwd_launch(const void* x, const void* dy, const uint8_t* mask, co
   return 0;
 }
 
+// ---- GLU over the last dimension, forward and backward ------------------------------------------------------------------
+// The ConMamba convolution module gates its pointwise-conv output before the depthwise conv (reference modules/Conmamba.py:
+// 268-279: Conv1d(C, 2C, 1) -> nn.GLU(dim=1)); channel-last that is y[r, c] = h[r, c] * sigmoid(h[r, C + c]).  torch's
+// glu / glu_backward kernels run it at 2.1 TB/s on B200 (23 / 36 us per layer at 32064 x 512 bf16); these are the same passes
+// with 16-byte accesses, two chunks per thread in flight.  (Gating inside the depthwise-conv kernels was built and measured
+// slower: they are FP32-issue-bound, profiles/r02_glu_in_dwconv_negative.txt.)  Roof: HBM; bytes per gated element: 3 s
+// forward, 5 s backward.
+namespace cm {
+
+template <typename T>
+__global__ void __launch_bounds__(256) glu_fwd_kernel(const T* __restrict__ h, T* __restrict__ y, int64_t rows, int32_t c8,
+                                                      int64_t h_stride, int64_t y_stride) {
+  const int64_t n = rows * c8, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 2 * stride) {
+    const int64_t j = i + stride;
+    const bool two = j < n;
+    const int64_t r0 = i / c8, r1 = two ? j / c8 : r0;
+    const int k0 = (int)(i - r0 * c8) * 8, k1 = two ? (int)(j - r1 * c8) * 8 : k0;
+    float a0[8], b0[8], a1[8], b1[8];
+    Vec8<T>::ld(h + r0 * h_stride + k0, a0);
+    Vec8<T>::ld(h + r0 * h_stride + 8 * c8 + k0, b0);
+    if (two) { Vec8<T>::ld(h + r1 * h_stride + k1, a1); Vec8<T>::ld(h + r1 * h_stride + 8 * c8 + k1, b1); }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a0[e] *= sigmoidf_fast(b0[e]);
+    Vec8<T>::st(y + r0 * y_stride + k0, a0);
+    if (two) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a1[e] *= sigmoidf_fast(b1[e]);
+      Vec8<T>::st(y + r1 * y_stride + k1, a1);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) glu_bwd_kernel(const T* __restrict__ h, const T* __restrict__ dy, T* __restrict__ dh,
+                                                      int64_t rows, int32_t c8, int64_t h_stride, int64_t dy_stride,
+                                                      int64_t dh_stride) {
+  const int64_t n = rows * c8, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t r = i / c8;
+    const int k = (int)(i - r * c8) * 8;
+    float a[8], b[8], g[8];
+    Vec8<T>::ld(h + r * h_stride + k, a);
+    Vec8<T>::ld(h + r * h_stride + 8 * c8 + k, b);
+    Vec8<T>::ld(dy + r * dy_stride + k, g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float sg = sigmoidf_fast(b[e]);
+      const float gs = g[e] * sg;
+      b[e] = gs * a[e] * (1.0f - sg);
+      a[e] = gs;
+    }
+    Vec8<T>::st(dh + r * dh_stride + k, a);
+    Vec8<T>::st(dh + r * dh_stride + 8 * c8 + k, b);
+  }
+}
+
+template <typename T>
+static int glu_launch(const void* h, const void* dy, void* out, int64_t rows, int32_t dim, int64_t h_stride, int64_t dy_stride,
+                      int64_t out_stride, bool bwd, void* stream) {
+  const int c8 = dim / 8;
+  const int64_t n = rows * c8;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (bwd) {
+    const unsigned grid = (unsigned)((n + 255) / 256 < 148 * 64 ? (n + 255) / 256 : 148 * 64);
+    glu_bwd_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(h), static_cast<const T*>(dy), static_cast<T*>(out), rows, c8,
+                                            h_stride, dy_stride, out_stride);
+  } else {
+    const int64_t want = (n + 511) / 512;
+    const unsigned grid = (unsigned)(want < 148 * 64 ? (want > 0 ? want : 1) : 148 * 64);
+    glu_fwd_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(h), static_cast<T*>(out), rows, c8, h_stride, out_stride);
+  }
+  CM_LAUNCH_CHECK();
+  return 0;
+}
+
+static int glu_check(const void* h, const void* other, const void* out, int64_t rows, int32_t dim, int64_t s0, int64_t s1,
+                     int64_t s2, int32_t dtype, bool bwd) {
+  if (!h || !out || (bwd && !other) || rows <= 0 || dim <= 0 || !dtype_ok(dtype)) return CM_ERR_BAD_ARG;
+  const int es = dtype == CM_F32 ? 4 : 2;
+  // 16-byte chunks of 8 elements: with fp32 the chunk is two float4 (32-byte alignment of the 8-element group is not needed)
+  if ((dim & 7) || ((s0 | s1 | s2) & 7) || s0 < 2 * (int64_t)dim) return CM_ERR_UNSUPPORTED;
+  auto al = [&](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al(h) || !al(out) || (bwd && !al(other))) return CM_ERR_UNSUPPORTED;
+  (void)es;
+  return 0;
+}
+
+}  // namespace cm
+
+extern "C" int cm_glu_fwd(const void* h, void* y, int64_t rows, int32_t dim, int64_t h_stride, int64_t y_stride, int32_t dtype,
+                          void* stream) {
+  if (int e = cm::glu_check(h, nullptr, y, rows, dim, h_stride, y_stride, 8, dtype, false)) return e;
+  if (y_stride < dim) return CM_ERR_BAD_ARG;
+  switch (dtype) {
+    case CM_F32: return cm::glu_launch<float>(h, nullptr, y, rows, dim, h_stride, 0, y_stride, false, stream);
+    case CM_BF16: return cm::glu_launch<__nv_bfloat16>(h, nullptr, y, rows, dim, h_stride, 0, y_stride, false, stream);
+    default: return cm::glu_launch<__half>(h, nullptr, y, rows, dim, h_stride, 0, y_stride, false, stream);
+  }
+}
+
+extern "C" int cm_glu_bwd(const void* h, const void* dy, void* dh, int64_t rows, int32_t dim, int64_t h_stride, int64_t dy_stride,
+                          int64_t dh_stride, int32_t dtype, void* stream) {
+  if (int e = cm::glu_check(h, dy, dh, rows, dim, h_stride, dy_stride, dh_stride, dtype, true)) return e;
+  if (dy_stride < dim || dh_stride < 2 * (int64_t)dim) return CM_ERR_BAD_ARG;
+  switch (dtype) {
+    case CM_F32: return cm::glu_launch<float>(h, dy, dh, rows, dim, h_stride, dy_stride, dh_stride, true, stream);
+    case CM_BF16: return cm::glu_launch<__nv_bfloat16>(h, dy, dh, rows, dim, h_stride, dy_stride, dh_stride, true, stream);
+    default: return cm::glu_launch<__half>(h, dy, dh, rows, dim, h_stride, dy_stride, dh_stride, true, stream);
+  }
+}
+
 extern "C" int cm_gelu_dropout_fwd(const void* x, void* y, uint8_t* mask, int64_t n, int32_t dtype, float p_drop,
                                    const int64_t* seed, uint32_t call_id, void* stream) {
   if (!x || !y || n <= 0 || !cm::dtype_ok(dtype) || p_drop < 0.f || p_drop >= 1.f) return CM_ERR_BAD_ARG;

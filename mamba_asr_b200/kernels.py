@@ -1062,6 +1062,42 @@ def gelu_dropout_backward(x, dy, saved, p_drop, colsum_cols=0, defer=False):
     return dx, cs
 
 
+# ------------------------------------------------------------------------------------------------ GLU (last dimension)
+def glu_supported(h):
+    """True when cm_glu_fwd / cm_glu_bwd take this tensor: CUDA, unit last stride, rows of 2C elements with C % 8 == 0 that
+    collapse to one row stride, 16-byte aligned."""
+    if not (h.is_cuda and h.dim() >= 2 and h.dtype in (torch.float32, torch.bfloat16, torch.float16)):
+        return False
+    Cn2 = h.shape[-1]
+    return Cn2 % 16 == 0 and h.is_contiguous() and h.data_ptr() % 16 == 0 and h.numel() > 0
+
+
+def glu_forward(h):
+    """y = h[..., :C] * sigmoid(h[..., C:]) (cm_glu_fwd) for a contiguous tensor; see glu_supported."""
+    lib = cabi.lib()
+    Cn = h.shape[-1] // 2
+    rows = h.numel() // (2 * Cn)
+    y = torch.empty(h.shape[:-1] + (Cn,), dtype=h.dtype, device=h.device)
+    _call("cm_glu_fwd", lib.cm_glu_fwd, h.data_ptr(), y.data_ptr(), rows, Cn, 2 * Cn, Cn, cabi.dtype_code(h.dtype), cabi.stream_ptr())
+    return y
+
+
+def glu_backward(h, dy):
+    """Gradient of glu_forward with respect to h (cm_glu_bwd); dy contiguous, h's dtype."""
+    lib = cabi.lib()
+    Cn = h.shape[-1] // 2
+    rows = h.numel() // (2 * Cn)
+    _same_device(h, dy=dy)
+    if dy.dtype != h.dtype:
+        dy = dy.to(h.dtype)
+    if not dy.is_contiguous() or dy.data_ptr() % 16:
+        dy = dy.contiguous()
+    dh = torch.empty_like(h)
+    _call("cm_glu_bwd", lib.cm_glu_bwd, h.data_ptr(), dy.data_ptr(), dh.data_ptr(), rows, Cn, 2 * Cn, Cn, 2 * Cn,
+          cabi.dtype_code(h.dtype), cabi.stream_ptr())
+    return dh
+
+
 # ------------------------------------------------------------------------------------------------ tall-skinny A^T B
 def tsmm_supported(a2d, b2d):
     """cm_tsmm computes a2d^T @ b2d for 16-bit row-major operands with b2d at most 64 columns wide."""

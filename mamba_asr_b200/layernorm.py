@@ -10,6 +10,8 @@ would cast to), one launch forward, one launch + one deterministic reduction bac
 ``FusedLayerNorm`` subclasses ``nn.LayerNorm`` so parameters, ``state_dict`` keys and ``extra_repr`` are unchanged.
 There is no CPU path: the CPU reference arm (oracle/cpu_encoder.py) swaps the class back to ``nn.LayerNorm``.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -350,6 +352,26 @@ class _GeluDropoutFn(torch.autograd.Function):
             if cs is None:
                 cs = dx.reshape(-1, cols).float().sum(0)
         return dx, None, K.grad_cast(cs, ctx.bias_dtype)
+
+
+class _GluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h):
+        ctx.save_for_backward(h)
+        return K.glu_forward(h)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (h,) = ctx.saved_tensors
+        return K.glu_backward(h, dy)
+
+
+def glu(h):
+    """F.glu(h, dim=-1) on the sm_100a kernels (cm_glu_fwd / cm_glu_bwd: 16-byte accesses at the HBM rate) for contiguous CUDA
+    tensors the kernels take; torch's op otherwise (and under CM_NO_GLU_KERNEL=1, the A/B switch)."""
+    if os.environ.get("CM_NO_GLU_KERNEL") is None and K.glu_supported(h):
+        return _GluFn.apply(h)
+    return torch.nn.functional.glu(h, dim=-1)
 
 
 def gelu_dropout(x, p_drop=0.0, training=True, bias_for_grad=None):

@@ -321,6 +321,33 @@ def test_layernorm_module_follows_autocast_and_has_no_cpu_path():
         FusedLayerNorm(144)(torch.randn(2, 144))
 
 
+@pytest.mark.parametrize("shape", [(64, 501, 512), (3, 67, 288), (1, 5, 64), (7, 16), (2, 3, 4, 32)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_glu_kernels_match_torch_glu(shape, dtype):
+    """cm_glu_fwd / cm_glu_bwd (the gate of the convolution module, reference modules/Conmamba.py:268-279) against F.glu and
+    its autograd gradient evaluated in fp32 on the same rounded inputs; unsupported geometries fall back to torch."""
+    from mamba_asr_b200 import kernels as K
+    from mamba_asr_b200.layernorm import glu
+    g = torch.Generator().manual_seed(23)
+    h = (2.0 * torch.randn(*shape, generator=g)).to(dtype).cuda()
+    cot = torch.randn(*shape[:-1], shape[-1] // 2, generator=g).to(dtype).cuda()
+    assert K.glu_supported(h)
+    hr = h.float().clone().requires_grad_(True)
+    ref = F.glu(hr, dim=-1)
+    (ref * cot.float()).sum().backward()
+    hk = h.clone().requires_grad_(True)
+    l0 = K.LAUNCHES
+    out = glu(hk)
+    (out.float() * cot.float()).sum().backward()
+    assert K.LAUNCHES == l0 + 2                               # one kernel each way
+    assert out.shape == ref.shape and out.dtype == dtype
+    assert_close(out.float(), ref, dtype, what="glu y")
+    assert_close(hk.grad.float(), hr.grad, dtype, what="glu dh")
+    odd = torch.randn(4, 5, 24, device="cuda").to(dtype)     # 12 gated channels: not a multiple of 8 -> torch's op
+    assert not K.glu_supported(odd)
+    assert torch.equal(glu(odd), F.glu(odd, dim=-1))
+
+
 @pytest.mark.parametrize("ksize,causal", [(31, False), (31, True), (15, False), (7, False), (3, True)])
 @pytest.mark.parametrize("shape", [(2, 501, 256), (3, 67, 144), (1, 5, 33), (2, 94, 64)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])

@@ -344,3 +344,47 @@ def test_param_cache_never_hands_out_a_stale_copy():
     c.refresh()
     assert torch.equal(c.get(m.w, torch.bfloat16), m.w.detach().bfloat16())
     assert c.get(m.w, torch.float16) is None
+
+
+def test_reduce_batch_and_glu_entry_points_validate_arguments_without_a_gpu(lib):
+    """cm_reduce_batch / cm_glu_fwd / cm_glu_bwd (include/conmamba_b200.h): null or empty -> BAD_ARG, geometry outside the
+    envelope -> UNSUPPORTED, before any launch."""
+    from mamba_asr_b200 import _cabi
+    arr = (_cabi.ReduceJob2 * 2)()
+    assert lib.cm_reduce_batch(arr, 2, None) == _cabi.CM_ERR_BAD_ARG                  # null pointers
+    assert lib.cm_reduce_batch(None, 1, None) == _cabi.CM_ERR_BAD_ARG
+    arr[0].part, arr[0].out, arr[0].rows, arr[0].cols, arr[0].stride = 256, 512, 4, 8, 7
+    assert lib.cm_reduce_batch(arr, 1, None) == _cabi.CM_ERR_BAD_ARG                  # stride < cols
+    assert lib.cm_reduce_batch(arr, _cabi.CM_REDUCE_BATCH_MAX + 1, None) == _cabi.CM_ERR_BAD_ARG
+    assert lib.cm_glu_fwd(None, 256, 4, 64, 128, 64, _cabi.CM_BF16, None) == _cabi.CM_ERR_BAD_ARG
+    assert lib.cm_glu_fwd(256, 512, 0, 64, 128, 64, _cabi.CM_BF16, None) == _cabi.CM_ERR_BAD_ARG
+    assert lib.cm_glu_fwd(256, 512, 4, 60, 120, 60, _cabi.CM_BF16, None) == _cabi.CM_ERR_UNSUPPORTED    # dim % 8
+    assert lib.cm_glu_fwd(258, 512, 4, 64, 128, 64, _cabi.CM_BF16, None) == _cabi.CM_ERR_UNSUPPORTED    # alignment
+    assert lib.cm_glu_fwd(256, 512, 4, 64, 64, 64, _cabi.CM_BF16, None) == _cabi.CM_ERR_UNSUPPORTED     # h rows narrower than 2 dim
+    assert lib.cm_glu_bwd(256, None, 512, 4, 64, 128, 64, 128, _cabi.CM_F32, None) == _cabi.CM_ERR_BAD_ARG
+    assert lib.cm_glu_bwd(256, 512, 768, 4, 64, 128, 64, 64, _cabi.CM_F32, None) == _cabi.CM_ERR_BAD_ARG  # dh rows narrower than 2 dim
+
+
+def test_deferred_reduction_queue_host_logic():
+    """kernels.deferred_reductions / reduce_many bookkeeping that needs no GPU: job geometry of both tuple forms, the context
+    manager restores the previous mode and leaves nothing queued, grad_cast returns the tensor itself when no cast is needed
+    (a queued gradient must not be read), and a deferred call outside a backward pass is not queued (it would never run)."""
+    import torch
+    from mamba_asr_b200 import kernels as K
+    part = torch.zeros(6, 4, 10)
+    out = torch.zeros(4, 10)
+    j = K._norm_job((part, out))
+    assert j[4:] == (6, 40, 40) and j[2] == part.data_ptr() and j[3] == out.data_ptr()
+    j = K._norm_job((part, out.view(-1)[8:], 6, 16, 40, 24))
+    assert j[4:] == (6, 16, 40) and j[2] == part.data_ptr() + 4 * 24 and j[3] == out.data_ptr() + 4 * 8
+    assert K._DEFER is False
+    with K.deferred_reductions():
+        assert K._DEFER is True
+        with K.deferred_reductions(False):
+            assert K._DEFER is False
+        assert K._DEFER is True
+    assert K._DEFER is False and not K._PENDING
+    g = torch.zeros(3)
+    assert K.grad_cast(g, torch.float32) is g and K.grad_cast(None, torch.float32) is None
+    assert K.grad_cast(g, torch.float64).dtype == torch.float64
+    K.reduce_many([])                                            # nothing to do, no library call

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CM_ABI_VERSION 14
+#define CM_ABI_VERSION 15
 
 /* element type of activations (u, delta, z, B, C, x, out, and their gradients) */
 enum { CM_F32 = 0, CM_BF16 = 1, CM_F16 = 2 };
@@ -303,7 +303,13 @@ typedef struct {
   void* dx;       int64_t dx_stride;     /* backward: grad of x */
   float* dgamma_part;
   float* dbeta_part;
+  int32_t act;                           /* 0, or CM_LN_OUT_GELU: y = gelu(LayerNorm(x)) (exact erf GELU; the LayerNorm -> GELU
+                                            pair after the depthwise conv of the convolution module, modules/Conmamba.py:
+                                            292-301).  Backward then takes dy for the activated output and needs beta.
+                                            Only for even cols / strides and 8-byte aligned pointers (else UNSUPPORTED). */
+  int32_t reserved;
 } cm_layernorm_args;
+#define CM_LN_OUT_GELU 1
 
 int cm_layernorm_num_part(int64_t rows);
 int cm_layernorm_fwd(const cm_layernorm_args* args, void* stream);

@@ -17,8 +17,9 @@ CM_ERR_BAD_ARG, CM_ERR_UNSUPPORTED = -1, -2
 CM_FLAG_DELTA_SOFTPLUS = 1
 CM_FLAG_SILU = 1
 CM_SCAN_CKPT_STEPS = 8
-CM_ABI_VERSION = 14
+CM_ABI_VERSION = 15
 CM_LN_ACT_LEAKY_RELU, CM_LN_ACT_GELU = 0, 1
+CM_LN_OUT_GELU = 1
 
 EXPORTS = (
     "cm_version", "cm_scan_num_ckpt", "cm_scan_slab_channels", "cm_scan_pick_lanes", "cm_scan_pick_lanes_bwd", "cm_scan_bwd_slab_channels", "cm_scan_fwd",
@@ -162,7 +163,7 @@ class LayerNormArgs(C.Structure):
         ("x", C.c_void_p), ("x_stride", C.c_int64), ("y", C.c_void_p), ("y_stride", C.c_int64),
         ("gamma", C.c_void_p), ("beta", C.c_void_p), ("mean", C.c_void_p), ("rstd", C.c_void_p),
         ("dy", C.c_void_p), ("dy_stride", C.c_int64), ("dx", C.c_void_p), ("dx_stride", C.c_int64),
-        ("dgamma_part", C.c_void_p), ("dbeta_part", C.c_void_p),
+        ("dgamma_part", C.c_void_p), ("dbeta_part", C.c_void_p), ("act", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -24,7 +24,8 @@ from .bimamba import Mamba as BiMamba
 from .bimamba import UniMamba as Mamba
 from .dwconv import depthwise_conv1d
 from .kernels import DWCONV_KSIZES, gelu_dropout_supported
-from .layernorm import FusedLayerNorm, _BiasGradRoute, add_dropout_layer_norm, gelu_dropout, glu, layer_norm_act
+from .layernorm import (FusedLayerNorm, _BiasGradRoute, add_dropout_layer_norm, gelu_dropout, glu, layer_norm_act,
+                        layer_norm_gelu_supported)
 from .linear import BiasGradLinear, linear as _linear
 
 LAYER_NORM_EPS = 1e-6        # reference ConMambaConstants.LAYER_NORM_EPS (Conmamba.py:687)
@@ -136,6 +137,9 @@ def _conv_body(self, normed, final_dropout=True, out_bias_grad=True):
     if (os.environ.get("CM_FUSE_LN_GELU") is not None and type(act) is nn.GELU and act.approximate == "none"
             and norm.normalized_shape[0] % 4 == 0):
         out = layer_norm_act(out, norm, "gelu")
+    elif (type(act) is nn.GELU and act.approximate == "none" and isinstance(norm, FusedLayerNorm)
+          and layer_norm_gelu_supported(out)):
+        out = norm(out, gelu=True)            # GELU as the epilogue of cm_layernorm_fwd / _bwd (A/B: CM_NO_LN_GELU_EPILOGUE=1)
     else:
         out = act(norm(out))
     lin = self.after_conv[2]

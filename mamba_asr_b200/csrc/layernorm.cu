@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(32 * kLnWarps) layernorm_fwd2_kernel(const Tin
                                                                      const float* __restrict__ beta, Tout* __restrict__ y,
                                                                      float* __restrict__ mean, float* __restrict__ rstd,
                                                                      int64_t rows, int C, int64_t x_stride, int64_t y_stride,
-                                                                     float eps) {
+                                                                     float eps, int act) {
   const int lane = threadIdx.x & 31;
   const int64_t row0 = ((int64_t)blockIdx.x * kLnWarps + (threadIdx.x >> 5)) * 2;
   if (row0 >= rows) return;
@@ -203,8 +203,9 @@ __global__ void __launch_bounds__(32 * kLnWarps) layernorm_fwd2_kernel(const Tin
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         if (r == 1 && !two) break;
-        Ln2<Tout>::st(y + (row0 + r) * y_stride + 2 * pi,
-                      make_float2(fmaf((v[r][i].x - mu[r]) * rs[r], g.x, bb.x), fmaf((v[r][i].y - mu[r]) * rs[r], g.y, bb.y)));
+        float2 o = make_float2(fmaf((v[r][i].x - mu[r]) * rs[r], g.x, bb.x), fmaf((v[r][i].y - mu[r]) * rs[r], g.y, bb.y));
+        if (act) o = make_float2(gelu_f(o.x), gelu_f(o.y));          // CM_LN_ACT_GELU epilogue (exact erf GELU)
+        Ln2<Tout>::st(y + (row0 + r) * y_stride + 2 * pi, o);
       }
     }
   }
@@ -220,7 +221,8 @@ __global__ void __launch_bounds__(32 * kLnWarps) layernorm_bwd2_kernel(const Tin
                                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                      Tin* __restrict__ dx, float* __restrict__ dgamma_part,
                                                                      float* __restrict__ dbeta_part, int64_t rows, int C,
-                                                                     int64_t x_stride, int64_t dy_stride, int64_t dx_stride) {
+                                                                     int64_t x_stride, int64_t dy_stride, int64_t dx_stride,
+                                                                     const float* __restrict__ beta, int act) {
   __shared__ float2 red[kLnWarps][32 * NPP + 1];   // reused for dgamma, then dbeta
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int np = C >> 1;
@@ -255,8 +257,14 @@ __global__ void __launch_bounds__(32 * kLnWarps) layernorm_bwd2_kernel(const Tin
 #pragma unroll
       for (int i = 0; i < NPP; ++i) {
         const int pi = lane + 32 * i;
-        const float2 dv = gy[r][i];
+        float2 dv = gy[r][i];
         const float2 h = (pi < np) ? make_float2((xh[r][i].x - mu[r]) * rs[r], (xh[r][i].y - mu[r]) * rs[r]) : make_float2(0.f, 0.f);
+        if (act && pi < np) {
+          // GELU epilogue of the forward: dy arrives for gelu(n), n = h * gamma + beta is recomputed (beta re-read: L1)
+          const float2 bt = beta ? __ldg(reinterpret_cast<const float2*>(beta + 2 * pi)) : make_float2(0.f, 0.f);
+          dv.x *= gelu_grad_f(fmaf(h.x, g[i].x, bt.x));
+          dv.y *= gelu_grad_f(fmaf(h.y, g[i].y, bt.y));
+        }
         xh[r][i] = h;
         gy[r][i] = make_float2(dv.x * g[i].x, dv.y * g[i].y);
         dg[i].x = fmaf(dv.x, h.x, dg[i].x); dg[i].y = fmaf(dv.y, h.y, dg[i].y);
@@ -300,18 +308,19 @@ __global__ void __launch_bounds__(32 * kLnWarps) layernorm_bwd2_kernel(const Tin
 
 template <typename Tin, typename Tout>
 static int ln_fwd_launch(const void* x, const float* g, const float* b, void* y, float* mean, float* rstd, int64_t rows,
-                         int C, int64_t xs, int64_t ys, float eps, cudaStream_t st) {
+                         int C, int64_t xs, int64_t ys, float eps, int act, cudaStream_t st) {
   if ((C & 1) == 0 && (xs & 1) == 0 && (ys & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0 &&
       (reinterpret_cast<uintptr_t>(y) & 7) == 0 && (!g || (reinterpret_cast<uintptr_t>(g) & 7) == 0) &&
       (!b || (reinterpret_cast<uintptr_t>(b) & 7) == 0)) {
     const unsigned grid2 = (unsigned)((rows + 2 * kLnWarps - 1) / (2 * kLnWarps));
 #define LN_FWD2(N) layernorm_fwd2_kernel<Tin, Tout, N><<<grid2, 32 * kLnWarps, 0, st>>>( \
-      static_cast<const Tin*>(x), g, b, static_cast<Tout*>(y), mean, rstd, rows, C, xs, ys, eps)
+      static_cast<const Tin*>(x), g, b, static_cast<Tout*>(y), mean, rstd, rows, C, xs, ys, eps, act)
     if (C <= 192) LN_FWD2(3); else if (C <= 256) LN_FWD2(4); else if (C <= 512) LN_FWD2(8); else LN_FWD2(16);
 #undef LN_FWD2
     CM_LAUNCH_CHECK();
     return 0;
   }
+  if (act) return CM_ERR_UNSUPPORTED;          // the activation epilogue exists on the pair-vectorised kernels only
   const unsigned grid = (unsigned)((rows + kLnWarps - 1) / kLnWarps);
 #define LN_FWD(N) layernorm_fwd_kernel<Tin, Tout, N><<<grid, 32 * kLnWarps, 0, st>>>( \
       static_cast<const Tin*>(x), g, b, static_cast<Tout*>(y), mean, rstd, rows, C, xs, ys, eps)
@@ -324,18 +333,19 @@ static int ln_fwd_launch(const void* x, const float* g, const float* b, void* y,
 template <typename Tin, typename Tdy>
 static int ln_bwd_launch(const void* x, const void* dy, const float* g, const float* mean, const float* rstd, void* dx,
                          float* dgp, float* dbp, int64_t rows, int C, int64_t xs, int64_t dys, int64_t dxs, int nblk,
-                         cudaStream_t st) {
+                         const float* beta, int act, cudaStream_t st) {
   if ((C & 1) == 0 && (xs & 1) == 0 && (dys & 1) == 0 && (dxs & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0 &&
       (reinterpret_cast<uintptr_t>(dy) & 7) == 0 && (reinterpret_cast<uintptr_t>(dx) & 7) == 0 &&
       (!g || (reinterpret_cast<uintptr_t>(g) & 7) == 0) && (reinterpret_cast<uintptr_t>(dgp) & 7) == 0 &&
       (reinterpret_cast<uintptr_t>(dbp) & 7) == 0) {
 #define LN_BWD2(N) layernorm_bwd2_kernel<Tin, Tdy, N><<<nblk, 32 * kLnWarps, 0, st>>>( \
-      static_cast<const Tin*>(x), static_cast<const Tdy*>(dy), g, mean, rstd, static_cast<Tin*>(dx), dgp, dbp, rows, C, xs, dys, dxs)
+      static_cast<const Tin*>(x), static_cast<const Tdy*>(dy), g, mean, rstd, static_cast<Tin*>(dx), dgp, dbp, rows, C, xs, dys, dxs, beta, act)
     if (C <= 192) LN_BWD2(3); else if (C <= 256) LN_BWD2(4); else if (C <= 512) LN_BWD2(8); else LN_BWD2(16);
 #undef LN_BWD2
     CM_LAUNCH_CHECK();
     return 0;
   }
+  if (act) return CM_ERR_UNSUPPORTED;
 #define LN_BWD(N) layernorm_bwd_kernel<Tin, Tdy, N><<<nblk, 32 * kLnWarps, 0, st>>>( \
       static_cast<const Tin*>(x), static_cast<const Tdy*>(dy), g, mean, rstd, static_cast<Tin*>(dx), dgp, dbp, rows, C, xs, dys, dxs)
   if (C <= 160) LN_BWD(5); else if (C <= 256) LN_BWD(8); else if (C <= 512) LN_BWD(16); else LN_BWD(32);
@@ -358,9 +368,10 @@ extern "C" int cm_layernorm_num_part(int64_t rows) {
 extern "C" int cm_layernorm_fwd(const cm_layernorm_args* a, void* stream) {
   if (!a || !a->x || !a->y || !a->mean || !a->rstd || a->rows <= 0 || a->cols <= 0) return CM_ERR_BAD_ARG;
   if (a->cols > 1024) return CM_ERR_UNSUPPORTED;
+  if (a->act != 0 && a->act != CM_LN_OUT_GELU) return CM_ERR_BAD_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define FWD(TI, TO) return cm::ln_fwd_launch<TI, TO>(a->x, a->gamma, a->beta, a->y, a->mean, a->rstd, a->rows, a->cols, \
-                                                     a->x_stride, a->y_stride, a->eps, st)
+                                                     a->x_stride, a->y_stride, a->eps, a->act, st)
   if (a->x_dtype == CM_F32 && a->y_dtype == CM_F32) FWD(float, float);
   if (a->x_dtype == CM_BF16 && a->y_dtype == CM_F32) FWD(__nv_bfloat16, float);
   if (a->x_dtype == CM_BF16 && a->y_dtype == CM_BF16) FWD(__nv_bfloat16, __nv_bfloat16);
@@ -377,8 +388,11 @@ extern "C" int cm_layernorm_bwd(const cm_layernorm_args* a, void* stream) {
   if (a->cols > 1024) return CM_ERR_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nblk = cm_layernorm_num_part(a->rows);
+  if (a->act != 0 && a->act != CM_LN_OUT_GELU) return CM_ERR_BAD_ARG;
+  if (a->act != 0 && a->beta != nullptr && (reinterpret_cast<uintptr_t>(a->beta) & 7) != 0) return CM_ERR_UNSUPPORTED;
 #define BWD(TI, TD) return cm::ln_bwd_launch<TI, TD>(a->x, a->dy, a->gamma, a->mean, a->rstd, a->dx, a->dgamma_part, \
-                                                     a->dbeta_part, a->rows, a->cols, a->x_stride, a->dy_stride, a->dx_stride, nblk, st)
+                                                     a->dbeta_part, a->rows, a->cols, a->x_stride, a->dy_stride, a->dx_stride, nblk, \
+                                                     a->beta, a->act, st)
   if (a->x_dtype == CM_F32 && a->y_dtype == CM_F32) BWD(float, float);
   if (a->x_dtype == CM_BF16 && a->y_dtype == CM_F32) BWD(__nv_bfloat16, float);
   if (a->x_dtype == CM_BF16 && a->y_dtype == CM_BF16) BWD(__nv_bfloat16, __nv_bfloat16);

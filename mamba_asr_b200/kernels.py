@@ -682,9 +682,16 @@ def ctc_nll_and_grad(log_probs, targets, input_lengths=None, target_lengths=None
 
 
 # ------------------------------------------------------------------------------------------------ LayerNorm
-def layernorm_forward(x2d, weight, bias, eps, out_dtype):
+def layernorm_gelu_supported(x2d):
+    """True when the GELU epilogue of cm_layernorm_fwd / _bwd takes these rows (the pair-vectorised kernels: even column
+    count and row stride, 8-byte aligned)."""
+    return (x2d.is_cuda and x2d.dim() == 2 and x2d.stride(1) == 1 and x2d.shape[1] % 2 == 0 and x2d.shape[1] <= 1024
+            and x2d.stride(0) % 2 == 0 and x2d.data_ptr() % 8 == 0)
+
+
+def layernorm_forward(x2d, weight, bias, eps, out_dtype, gelu=False):
     """cm_layernorm_fwd over the rows of a (rows, C) CUDA tensor with unit column stride.
-    Returns (y (rows, C) in out_dtype, mean (rows,) fp32, rstd (rows,) fp32)."""
+    Returns (y (rows, C) in out_dtype, mean (rows,) fp32, rstd (rows,) fp32).  gelu=True: y = gelu(LayerNorm(x))."""
     lib = cabi.lib()
     _require_cuda(x2d, "x")
     rows, Cn = x2d.shape
@@ -702,13 +709,15 @@ def layernorm_forward(x2d, weight, bias, eps, out_dtype):
     a.y, a.y_stride = y.data_ptr(), y.stride(0)
     a.gamma, a.beta = cabi.ptr(weight), cabi.ptr(bias)
     a.mean, a.rstd = mean.data_ptr(), rstd.data_ptr()
+    a.act = cabi.CM_LN_OUT_GELU if gelu else 0
     _call("cm_layernorm_fwd", lib.cm_layernorm_fwd, C.byref(a), cabi.stream_ptr())
     return y, mean, rstd
 
 
-def layernorm_backward(x2d, dy2d, weight, mean, rstd, need_wgrad=True, defer=False):
+def layernorm_backward(x2d, dy2d, weight, mean, rstd, need_wgrad=True, defer=False, gelu=False, bias=None):
     """cm_layernorm_bwd + deterministic reduction of the per-CTA dgamma / dbeta partial rows.
-    Returns (dx in x's dtype, dgamma fp32 (C,), dbeta fp32 (C,))."""
+    Returns (dx in x's dtype, dgamma fp32 (C,), dbeta fp32 (C,)).  gelu=True: dy is the gradient of gelu(LayerNorm(x))
+    (the forward's GELU epilogue; ``bias`` = the LayerNorm's beta, needed to recompute the pre-activation)."""
     lib = cabi.lib()
     rows, Cn = x2d.shape
     if dy2d.stride(1) != 1:
@@ -726,6 +735,8 @@ def layernorm_backward(x2d, dy2d, weight, mean, rstd, need_wgrad=True, defer=Fal
     a.dy, a.dy_stride = dy2d.data_ptr(), dy2d.stride(0)
     a.dx, a.dx_stride = dx.data_ptr(), dx.stride(0)
     a.dgamma_part, a.dbeta_part = dg_part.data_ptr(), db_part.data_ptr()
+    if gelu:
+        a.act, a.beta = cabi.CM_LN_OUT_GELU, cabi.ptr(bias)
     _call("cm_layernorm_bwd", lib.cm_layernorm_bwd, C.byref(a), cabi.stream_ptr())
     if not need_wgrad:
         return dx, None, None

@@ -20,30 +20,44 @@ from . import kernels as K
 
 class _LayerNormFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, out_dtype):
+    def forward(ctx, x, weight, bias, eps, out_dtype, gelu=False):
         Cn = x.shape[-1]
         x2 = x.reshape(-1, Cn)
         if x2.stride(1) != 1 or (x2.shape[0] > 1 and x2.stride(0) < Cn):
             x2 = x2.contiguous()
-        y, mean, rstd = K.layernorm_forward(x2, weight, bias, eps, out_dtype)
-        ctx.save_for_backward(x2, weight, mean, rstd)
+        y, mean, rstd = K.layernorm_forward(x2, weight, bias, eps, out_dtype, gelu=gelu)
+        ctx.gelu = gelu
+        ctx.save_for_backward(x2, weight, mean, rstd, *([bias] if (gelu and bias is not None) else []))
         ctx.x_shape = x.shape
         ctx.has_bias = bias is not None
         return y.view(x.shape)
 
     @staticmethod
     def backward(ctx, dy):
-        x2, weight, mean, rstd = ctx.saved_tensors
+        x2, weight, mean, rstd = ctx.saved_tensors[:4]
+        beta = ctx.saved_tensors[4] if len(ctx.saved_tensors) > 4 else None
         Cn = x2.shape[1]
         need_w = weight is not None and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
-        dx, dg, db = K.layernorm_backward(x2, dy.reshape(-1, Cn), weight, mean, rstd, need_wgrad=need_w, defer=True)
+        dx, dg, db = K.layernorm_backward(x2, dy.reshape(-1, Cn), weight, mean, rstd, need_wgrad=need_w, defer=True,
+                                          gelu=ctx.gelu, bias=beta)
         dgw = K.grad_cast(dg, weight.dtype) if (need_w and ctx.needs_input_grad[1]) else None
         dbw = K.grad_cast(db, weight.dtype) if (need_w and ctx.has_bias and ctx.needs_input_grad[2]) else None
-        return dx.view(ctx.x_shape), dgw, dbw, None, None
+        return dx.view(ctx.x_shape), dgw, dbw, None, None, None
 
 
-def layer_norm(x, weight, bias, eps=1e-5, out_dtype=None):
-    """Functional form.  ``out_dtype`` None: the autocast dtype if CUDA autocast is enabled, else x.dtype."""
+def layer_norm_gelu_supported(x):
+    """True when ``layer_norm(..., gelu=True)`` can take x (see kernels.layernorm_gelu_supported) - checked on the 2-D view the
+    kernel sees."""
+    if not x.is_cuda or x.dim() < 2 or os.environ.get("CM_NO_LN_GELU_EPILOGUE") is not None:
+        return False
+    Cn = x.shape[-1]
+    return x.is_contiguous() and Cn % 2 == 0 and Cn <= 1024 and x.data_ptr() % 8 == 0
+
+
+def layer_norm(x, weight, bias, eps=1e-5, out_dtype=None, gelu=False):
+    """Functional form.  ``out_dtype`` None: the autocast dtype if CUDA autocast is enabled, else x.dtype.
+    ``gelu=True``: gelu(LayerNorm(x)) (exact erf GELU, as nn.GELU()) as an epilogue of the same kernels - the LayerNorm ->
+    GELU pair after the depthwise conv of the convolution module (reference modules/Conmamba.py:292-301)."""
     if not x.is_cuda:
         raise RuntimeError("mamba_asr_b200.layer_norm runs on the sm_100a kernel only (no CPU fallback)")
     if out_dtype is None:
@@ -52,7 +66,7 @@ def layer_norm(x, weight, bias, eps=1e-5, out_dtype=None):
         weight = weight.float()
     if bias is not None and bias.dtype != torch.float32:
         bias = bias.float()
-    return _LayerNormFn.apply(x, weight, bias, eps, out_dtype)
+    return _LayerNormFn.apply(x, weight, bias, eps, out_dtype, bool(gelu))
 
 
 class FusedLayerNorm(nn.LayerNorm):
@@ -67,11 +81,11 @@ class FusedLayerNorm(nn.LayerNorm):
             raise NotImplementedError("FusedLayerNorm normalises one trailing dimension of at most 1024 channels")
         self.keep_dtype = keep_dtype
 
-    def forward(self, x):
+    def forward(self, x, gelu=False):
         out_dtype = None
         if self.keep_dtype:
             out_dtype = torch.float32 if torch.is_autocast_enabled("cuda") else x.dtype
-        return layer_norm(x, self.weight, self.bias, self.eps, out_dtype=out_dtype)
+        return layer_norm(x, self.weight, self.bias, self.eps, out_dtype=out_dtype, gelu=gelu)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

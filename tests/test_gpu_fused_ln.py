@@ -308,20 +308,22 @@ def test_conv_front_end_same_with_and_without_the_fused_norm(autocast, monkeypat
 
 @pytest.mark.parametrize("autocast", [False, True])
 def test_convolution_module_same_with_and_without_the_fused_norm_gelu(autocast, monkeypatch):
-    """ConvolutionModule (reference modules/Conmamba.py:182-454) with LayerNorm -> GELU after the depthwise conv on
-    cm_ln_act_* (opt-in, CM_FUSE_LN_GELU=1) against the default cm_layernorm + torch GELU evaluation: output and every
-    parameter gradient."""
+    """ConvolutionModule (reference modules/Conmamba.py:182-454) with LayerNorm -> GELU after the depthwise conv as the
+    GELU epilogue of cm_layernorm_* (the default) and on cm_ln_act_* (opt-in, CM_FUSE_LN_GELU=1), each against the separate
+    cm_layernorm + torch GELU evaluation (CM_NO_LN_GELU_EPILOGUE=1): output and every parameter gradient."""
     from mamba_asr_b200.conmamba import ConvolutionModule
     torch.manual_seed(5)
     m = ConvolutionModule(144, kernel_size=31, activation=torch.nn.GELU, dropout=0.0).cuda()
     x = torch.randn(3, 77, 144, device="cuda")
     cy = torch.randn(3, 77, 144, device="cuda")
     res = []
-    for fused in (True, False):
-        if fused:
+    for mode in ("ln_act", "epilogue", "separate"):
+        monkeypatch.delenv("CM_FUSE_LN_GELU", raising=False)
+        monkeypatch.delenv("CM_NO_LN_GELU_EPILOGUE", raising=False)
+        if mode == "ln_act":
             monkeypatch.setenv("CM_FUSE_LN_GELU", "1")
-        else:
-            monkeypatch.delenv("CM_FUSE_LN_GELU", raising=False)
+        elif mode == "separate":
+            monkeypatch.setenv("CM_NO_LN_GELU_EPILOGUE", "1")
         m.zero_grad()
         xg = x.clone().requires_grad_(True)
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
@@ -329,10 +331,47 @@ def test_convolution_module_same_with_and_without_the_fused_norm_gelu(autocast, 
         (out.float() * cy).sum().backward()
         res.append((out.float().detach(), xg.grad.clone(), [p.grad.clone() for p in m.parameters()]))
     dt = torch.bfloat16 if autocast else torch.float32
-    assert_close(res[0][0], res[1][0], dt, what="conv module output")
-    assert_close(res[0][1], res[1][1], dt, floor="max", what="conv module dx", rtol_mul=2.0)
-    for (name, _), ga, gb in zip(m.named_parameters(), res[0][2], res[1][2]):
-        assert_close(ga, gb, dt, floor="max", what="d " + name, rtol_mul=4.0)
+    for k, what in ((0, "cm_ln_act"), (1, "epilogue")):
+        assert_close(res[k][0], res[2][0], dt, what=what + ": conv module output")
+        assert_close(res[k][1], res[2][1], dt, floor="max", what=what + ": conv module dx", rtol_mul=2.0)
+        for (name, _), ga, gb in zip(m.named_parameters(), res[k][2], res[2][2]):
+            assert_close(ga, gb, dt, floor="max", what=what + ": d " + name, rtol_mul=4.0)
+
+
+@pytest.mark.parametrize("shape", [(3, 67, 256), (2, 501, 144), (5, 64), (1, 1, 16), (4, 33, 1024), (2, 9, 288)])
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "autocast"])
+def test_layer_norm_gelu_epilogue_matches_torch(shape, mode):
+    """cm_layernorm_fwd / _bwd with the GELU epilogue (cm_layernorm_args.act = CM_LN_OUT_GELU; the LayerNorm -> GELU pair of
+    the convolution module, reference modules/Conmamba.py:292-301) against F.gelu(F.layer_norm(x)) in fp32 on the same
+    rounded input: y, dx, dgamma, dbeta; one kernel each way."""
+    from mamba_asr_b200 import kernels as K
+    from mamba_asr_b200.layernorm import FusedLayerNorm, layer_norm_gelu_supported
+    g = torch.Generator().manual_seed(31)
+    Cn = shape[-1]
+    dt = torch.float32 if mode != "bf16" else torch.bfloat16
+    x = (1.5 * torch.randn(*shape, generator=g) + 0.3).to(dt).cuda()
+    cot = torch.randn(*shape, generator=g).cuda()
+    norm = FusedLayerNorm(Cn).cuda()
+    with torch.no_grad():
+        norm.weight.copy_(1.0 + 0.2 * torch.randn(Cn, generator=g))
+        norm.bias.copy_(0.3 * torch.randn(Cn, generator=g))
+    assert layer_norm_gelu_supported(x)
+    xr = x.float().clone().requires_grad_(True)
+    wr, br = norm.weight.detach().clone().requires_grad_(True), norm.bias.detach().clone().requires_grad_(True)
+    ref = F.gelu(F.layer_norm(xr, (Cn,), wr, br, norm.eps))
+    (ref * cot).sum().backward()
+    xk = x.clone().requires_grad_(True)
+    l0 = K.LAUNCHES
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode == "autocast"):
+        out = norm(xk, gelu=True)
+    (out.float() * cot).sum().backward()
+    assert K.LAUNCHES - l0 <= 3                                # forward, backward, the dgamma / dbeta reduction
+    odt = torch.bfloat16 if mode != "fp32" else torch.float32
+    assert out.dtype == odt
+    assert_close(out.float(), ref, odt, what="ln+gelu y")
+    assert_close(xk.grad.float(), xr.grad, odt, floor="max", what="ln+gelu dx")
+    assert_close(norm.weight.grad, wr.grad, odt, floor="max", what="ln+gelu dgamma")
+    assert_close(norm.bias.grad, br.grad, odt, floor="max", what="ln+gelu dbeta")
 
 
 # ---------------------------------------------------------------------------------------------------------------------

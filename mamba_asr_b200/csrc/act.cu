@@ -110,7 +110,9 @@ __global__ void __launch_bounds__(256) gelu_dropout_fwd_kernel(const T* __restri
       const int64_t vv = c ? v1 : v;
       const uint32_t kb = drop ? keep8(key, vv, thr) : 0xffu;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[c][i] = ((kb >> i) & 1u) ? scale * gelu_f(a[c][i]) : 0.f;
+      // the keep bit as a factor (scale or 0), not as a branch: written as a select around gelu_f ptxas put every element's
+      // GELU under its own divergent branch (BSSY / BRA / BSYNC per element, no overlap between the 8 chains)
+      for (int i = 0; i < 8; ++i) a[c][i] = (((kb >> i) & 1u) ? scale : 0.f) * gelu_f(a[c][i]);
       Vec8<T>::st(y + 8 * vv, a[c]);
       if (mask != nullptr) {
         uint2 m;
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(256) gelu_dropout_bwd_kernel(const T* __restri
       for (int i = 0; i < 8; ++i) kb |= ((((i < 4 ? m.x : m.y) >> (8 * (i & 3))) & 0xffu) ? 1u : 0u) << i;
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = ((kb >> i) & 1u) ? scale * g[i] * gelu_grad_f(a[i]) : 0.f;
+    for (int i = 0; i < 8; ++i) a[i] = ((((kb >> i) & 1u) ? scale : 0.f) * g[i]) * gelu_grad_f(a[i]);   // factor, not branch
     Vec8<T>::st(dx + 8 * v, a);
     if (COLSUM) {
 #pragma unroll

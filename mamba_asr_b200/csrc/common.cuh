@@ -148,15 +148,15 @@ constexpr float kInvSqrt2Pi = 0.3989422804014327f;
 // in profiles/r01_fused_addln_gelu_cfg3_ncu.txt); this form is 2 MUFU + 10 FMA-pipe instructions and shares the
 // exponential with the derivative.
 __device__ __forceinline__ void gelu_parts(float x, float* Phi, float* phi) {
-  const float y = fabsf(x) * kInvSqrt2;
-  const float e = ex2(-y * y * kLog2e);                 // exp(-x^2 / 2)
-  const float t = rcp(fmaf(0.3275911f, y, 1.0f));
-  float p = 1.061405429f;
-  p = fmaf(p, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float q = 0.5f * p * t * e;                     // 0.5 * erfc(|y|) = Phi(-|x|)
+  // constants folded (y = |x| / sqrt 2 never formed, the 0.5 inside the coefficients): 4 FMUL + 5 FFMA + 2 MUFU
+  const float e = ex2(x * x * (-0.5f * kLog2e));        // exp(-x^2 / 2)
+  const float t = rcp(fmaf(0.3275911f * kInvSqrt2, fabsf(x), 1.0f));
+  float p = 0.5f * 1.061405429f;
+  p = fmaf(p, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  const float q = p * t * e;                            // 0.5 * erfc(|x| / sqrt 2) = Phi(-|x|)
   *Phi = x >= 0.f ? 1.0f - q : q;
   *phi = kInvSqrt2Pi * e;
 }

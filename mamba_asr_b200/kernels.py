@@ -80,7 +80,6 @@ def grad_cast(t, dtype):
 _DEFER = False          # set by deferred_reductions()
 _DEFER_POISON = os.environ.get("CM_DEFER_POISON") not in (None, "", "0")   # tests: NaN-fill queued outputs until the flush
 _PENDING = []
-_CB_QUEUED = False
 
 
 class deferred_reductions:
@@ -102,9 +101,11 @@ class deferred_reductions:
         self.prev, _DEFER = _DEFER, self.enabled
         return self
 
-    def __exit__(self, *exc):
+    def __exit__(self, exc_type, *exc):
         global _DEFER
         _DEFER = self.prev
+        if exc_type is not None:
+            _PENDING.clear()            # a pass that raised: its queued jobs point at tensors nobody will use
         flush_reductions()
         return False
 
@@ -131,9 +132,7 @@ def _launch_reduce(jobs):
 
 
 def flush_reductions():
-    """Run every queued reduction now (the engine callback; also safe to call by hand)."""
-    global _CB_QUEUED
-    _CB_QUEUED = False
+    """Run every queued reduction now (the engine callback; also safe to call by hand, and a no-op on an empty queue)."""
     if _PENDING:
         jobs = list(_PENDING)
         _PENDING.clear()
@@ -143,18 +142,18 @@ def flush_reductions():
 def reduce_many(jobs, defer=False):
     """Fixed-order column sums of partial buffers (cm_reduce_batch).  ``defer=True`` marks outputs that nobody reads before the
     end of the current backward pass: under ``deferred_reductions()`` they are queued (see there), otherwise run now."""
-    global _CB_QUEUED
     jobs = [_norm_job(j) for j in jobs]
     if not jobs:
         return
     if defer and _DEFER:
-        if not _CB_QUEUED:
-            try:
+        queued = bool(_PENDING)                     # a non-empty queue already has its end-of-pass callback
+        if not queued:
+            try:                                    # (one more callback after a mid-pass flush is a no-op at the end)
                 torch.autograd.Variable._execution_engine.queue_callback(flush_reductions)
-                _CB_QUEUED = True
+                queued = True
             except RuntimeError:                    # not inside a backward pass: nothing would ever flush the queue
                 pass
-        if _CB_QUEUED:
+        if queued:
             if _DEFER_POISON:
                 for j in jobs:
                     j[1].view(-1)[:j[5]].fill_(float("nan"))

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CM_ABI_VERSION 15
+#define CM_ABI_VERSION 16
 
 /* element type of activations (u, delta, z, B, C, x, out, and their gradients) */
 enum { CM_F32 = 0, CM_BF16 = 1, CM_F16 = 2 };
@@ -394,6 +394,9 @@ typedef struct {
   int32_t cols;             /* backward: > 0 = also column sums of dx */
   int64_t n;
   float* colsum_part;       /* [cm_act_num_part(n)][cols] fp32 */
+  uint8_t* keep_bits;       /* optional, n / 8 bytes: bit i of byte v = element 8 v + i is kept.  Forward writes it (next to
+                               whatever else it stores), backward reads it in preference to mask / key: one byte per eight
+                               elements instead of four hashes */
 } cm_act_args;
 
 int cm_act_colsum_supported(int64_t n, int32_t cols);

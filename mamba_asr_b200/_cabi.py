@@ -17,7 +17,7 @@ CM_ERR_BAD_ARG, CM_ERR_UNSUPPORTED = -1, -2
 CM_FLAG_DELTA_SOFTPLUS = 1
 CM_FLAG_SILU = 1
 CM_SCAN_CKPT_STEPS = 8
-CM_ABI_VERSION = 15
+CM_ABI_VERSION = 16
 CM_LN_ACT_LEAKY_RELU, CM_LN_ACT_GELU = 0, 1
 CM_LN_OUT_GELU = 1
 
@@ -145,7 +145,7 @@ class ActArgs(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("y", C.c_void_p), ("dy", C.c_void_p), ("dx", C.c_void_p), ("mask", C.c_void_p),
         ("seed", C.c_void_p), ("key", C.c_void_p), ("call_id", C.c_uint32), ("dtype", C.c_int32), ("p_drop", C.c_float),
-        ("cols", C.c_int32), ("n", C.c_int64), ("colsum_part", C.c_void_p),
+        ("cols", C.c_int32), ("n", C.c_int64), ("colsum_part", C.c_void_p), ("keep_bits", C.c_void_p),
     ]
 
 

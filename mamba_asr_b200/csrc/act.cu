@@ -90,7 +90,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) gelu_dropout_fwd_kernel(const T* __restrict__ x, T* __restrict__ y,
                                                                uint8_t* __restrict__ mask, int64_t n8, float p,
                                                                const int64_t* __restrict__ seed, uint32_t call_id,
-                                                               uint32_t* __restrict__ key_out, bool drop) {
+                                                               uint32_t* __restrict__ key_out, bool drop,
+                                                               uint8_t* __restrict__ bits) {
   const uint32_t thr = drop ? (uint32_t)(p * 65536.0f) : 0u;
   const float scale = drop ? 1.0f / (1.0f - p) : 1.0f;
   const uint32_t key = drop ? act_key(seed, call_id) : 0u;
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(256) gelu_dropout_fwd_kernel(const T* __restri
       // GELU under its own divergent branch (BSSY / BRA / BSYNC per element, no overlap between the 8 chains)
       for (int i = 0; i < 8; ++i) a[c][i] = (((kb >> i) & 1u) ? scale : 0.f) * gelu_f(a[c][i]);
       Vec8<T>::st(y + 8 * vv, a[c]);
+      if (bits != nullptr) bits[vv] = (uint8_t)kb;          // one keep bit per element: what backward reads instead of re-hashing
       if (mask != nullptr) {
         uint2 m;
         m.x = (kb & 1u) | ((kb & 2u) << 7) | ((kb & 4u) << 14) | ((kb & 8u) << 21);
@@ -132,9 +134,10 @@ template <typename T, bool COLSUM>
 __global__ void __launch_bounds__(256) gelu_dropout_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                                const uint8_t* __restrict__ mask,
                                                                const uint32_t* __restrict__ key_in, T* __restrict__ dx,
-                                                               int64_t n8, float p, int cols8, float* __restrict__ cs_part) {
+                                                               int64_t n8, float p, int cols8, float* __restrict__ cs_part,
+                                                               const uint8_t* __restrict__ bits) {
   const bool drop = p > 0.f;
-  const bool regen = drop && mask == nullptr;
+  const bool regen = drop && mask == nullptr && bits == nullptr;
   const float scale = drop ? 1.0f / (1.0f - p) : 1.0f;
   const uint32_t thr = drop ? (uint32_t)(p * 65536.0f) : 0u;
   const uint32_t key = regen ? __ldg(key_in) : 0u;
@@ -146,7 +149,9 @@ __global__ void __launch_bounds__(256) gelu_dropout_bwd_kernel(const T* __restri
     Vec8<T>::ld(x + 8 * v, a);
     Vec8<T>::ld(dy + 8 * v, g);
     uint32_t kb = 0xffu;
-    if (regen) {
+    if (drop && bits != nullptr) {
+      kb = __ldg(bits + v);                // the forward's keep bits (1 byte per 8 elements): no hash in backward
+    } else if (regen) {
       kb = keep8(key, v, thr);
     } else if (drop) {
       const uint2 m = __ldg(reinterpret_cast<const uint2*>(mask + 8 * v));
@@ -188,14 +193,14 @@ static unsigned act_grid(int64_t n8) {
 static bool act_al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static int act_fwd_launch(const void* x, void* y, uint8_t* mask, int64_t n, int32_t dtype, float p_drop, const int64_t* seed,
-                          uint32_t call_id, uint32_t* key_out, bool drop, void* stream) {
+                          uint32_t call_id, uint32_t* key_out, bool drop, void* stream, uint8_t* bits = nullptr) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t n8 = n >> 3;
   const unsigned grid = cm::act_grid(n8);
   switch (dtype) {
-    case CM_F32: cm::gelu_dropout_fwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), static_cast<float*>(y), mask, n8, p_drop, seed, call_id, key_out, drop); break;
-    case CM_BF16: cm::gelu_dropout_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), mask, n8, p_drop, seed, call_id, key_out, drop); break;
-    default: cm::gelu_dropout_fwd_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), static_cast<__half*>(y), mask, n8, p_drop, seed, call_id, key_out, drop); break;
+    case CM_F32: cm::gelu_dropout_fwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), static_cast<float*>(y), mask, n8, p_drop, seed, call_id, key_out, drop, bits); break;
+    case CM_BF16: cm::gelu_dropout_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), mask, n8, p_drop, seed, call_id, key_out, drop, bits); break;
+    default: cm::gelu_dropout_fwd_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), static_cast<__half*>(y), mask, n8, p_drop, seed, call_id, key_out, drop, bits); break;
   }
   CM_LAUNCH_CHECK();
   return 0;
@@ -203,14 +208,14 @@ static int act_fwd_launch(const void* x, void* y, uint8_t* mask, int64_t n, int3
 
 template <bool COLSUM>
 static int act_bwd_launch(const void* x, const void* dy, const uint8_t* mask, const uint32_t* key, void* dx, int64_t n,
-                          int32_t dtype, float p_drop, int cols8, float* cs_part, void* stream) {
+                          int32_t dtype, float p_drop, int cols8, float* cs_part, void* stream, const uint8_t* bits = nullptr) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t n8 = n >> 3;
   const unsigned grid = cm::act_grid(n8);
   switch (dtype) {
-    case CM_F32: cm::gelu_dropout_bwd_kernel<float, COLSUM><<<grid, 256, 0, st>>>(static_cast<const float*>(x), static_cast<const float*>(dy), mask, key, static_cast<float*>(dx), n8, p_drop, cols8, cs_part); break;
-    case CM_BF16: cm::gelu_dropout_bwd_kernel<__nv_bfloat16, COLSUM><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), mask, key, static_cast<__nv_bfloat16*>(dx), n8, p_drop, cols8, cs_part); break;
-    default: cm::gelu_dropout_bwd_kernel<__half, COLSUM><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), static_cast<const __half*>(dy), mask, key, static_cast<__half*>(dx), n8, p_drop, cols8, cs_part); break;
+    case CM_F32: cm::gelu_dropout_bwd_kernel<float, COLSUM><<<grid, 256, 0, st>>>(static_cast<const float*>(x), static_cast<const float*>(dy), mask, key, static_cast<float*>(dx), n8, p_drop, cols8, cs_part, bits); break;
+    case CM_BF16: cm::gelu_dropout_bwd_kernel<__nv_bfloat16, COLSUM><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), mask, key, static_cast<__nv_bfloat16*>(dx), n8, p_drop, cols8, cs_part, bits); break;
+    default: cm::gelu_dropout_bwd_kernel<__half, COLSUM><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), static_cast<const __half*>(dy), mask, key, static_cast<__half*>(dx), n8, p_drop, cols8, cs_part, bits); break;
   }
   CM_LAUNCH_CHECK();
   return 0;
@@ -357,9 +362,9 @@ extern "C" int cm_gelu_dropout_fwd_v2(const cm_act_args* a, void* stream) {
   if (!a || !a->x || !a->y || a->n <= 0 || !cm::dtype_ok(a->dtype) || a->p_drop < 0.f || a->p_drop >= 1.f) return CM_ERR_BAD_ARG;
   if ((a->n & 7) || !act_al16(a->x) || !act_al16(a->y) || (a->mask && (reinterpret_cast<uintptr_t>(a->mask) & 7)))
     return CM_ERR_UNSUPPORTED;
-  if (a->p_drop > 0.f && !a->mask && !a->key) return CM_ERR_BAD_ARG;       // backward would have no way to rebuild the mask
+  if (a->p_drop > 0.f && !a->mask && !a->key && !a->keep_bits) return CM_ERR_BAD_ARG;   // backward could not rebuild the mask
   return act_fwd_launch(a->x, a->y, a->p_drop > 0.f ? a->mask : nullptr, a->n, a->dtype, a->p_drop, a->seed, a->call_id,
-                        a->key, a->p_drop > 0.f, stream);
+                        a->key, a->p_drop > 0.f, stream, a->p_drop > 0.f ? a->keep_bits : nullptr);
 }
 
 extern "C" int cm_gelu_dropout_bwd_v2(const cm_act_args* a, void* stream) {
@@ -367,11 +372,12 @@ extern "C" int cm_gelu_dropout_bwd_v2(const cm_act_args* a, void* stream) {
     return CM_ERR_BAD_ARG;
   if ((a->n & 7) || !act_al16(a->x) || !act_al16(a->dy) || !act_al16(a->dx) || (a->mask && (reinterpret_cast<uintptr_t>(a->mask) & 7)))
     return CM_ERR_UNSUPPORTED;
-  if (a->p_drop > 0.f && !a->mask && !a->key) return CM_ERR_BAD_ARG;
+  if (a->p_drop > 0.f && !a->mask && !a->key && !a->keep_bits) return CM_ERR_BAD_ARG;
+  const uint8_t* bits = a->p_drop > 0.f ? a->keep_bits : nullptr;
   if (a->cols > 0) {
     if (!a->colsum_part) return CM_ERR_BAD_ARG;
     if (!act_cols_ok(a->n, a->cols)) return CM_ERR_UNSUPPORTED;
-    return act_bwd_launch<true>(a->x, a->dy, a->mask, a->key, a->dx, a->n, a->dtype, a->p_drop, a->cols >> 3, a->colsum_part, stream);
+    return act_bwd_launch<true>(a->x, a->dy, a->mask, a->key, a->dx, a->n, a->dtype, a->p_drop, a->cols >> 3, a->colsum_part, stream, bits);
   }
-  return act_bwd_launch<false>(a->x, a->dy, a->mask, a->key, a->dx, a->n, a->dtype, a->p_drop, 0, nullptr, stream);
+  return act_bwd_launch<false>(a->x, a->dy, a->mask, a->key, a->dx, a->n, a->dtype, a->p_drop, 0, nullptr, stream, bits);
 }

@@ -1021,8 +1021,10 @@ def gelu_dropout_supported(x):
 
 def gelu_dropout_forward(x, p_drop, seed, call_id, store_mask=None):
     """cm_gelu_dropout_fwd_v2 on a contiguous tensor: returns (y, saved) where ``saved`` is what backward needs to rebuild the
-    dropout mask - None (no dropout), a (1,) int32 key tensor (default: the mask is regenerated, nothing stored) or the
-    uint8 byte mask (``store_mask=True`` or CM_DROPOUT_STORE_MASK=1: the A/B switch back to the stored mask)."""
+    dropout mask - None (no dropout); by default the keep BITS, a uint8 tensor of numel / 8 bytes (one bit per element: the
+    backward kernel is issue-bound and the four hashes per eight elements of a regenerated mask were a quarter of its
+    instructions); a (1,) int32 key tensor with CM_DROPOUT_REGEN=1 (nothing stored, the mask is re-hashed); or the uint8
+    byte mask (``store_mask=True`` or CM_DROPOUT_STORE_MASK=1)."""
     lib = cabi.lib()
     _require_cuda(x, "x")
     y = torch.empty_like(x)
@@ -1036,9 +1038,12 @@ def gelu_dropout_forward(x, p_drop, seed, call_id, store_mask=None):
         if store_mask:
             saved = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
             a.mask = saved.data_ptr()
-        else:
+        elif os.environ.get("CM_DROPOUT_REGEN", "0") == "1":
             saved = torch.empty((1,), dtype=torch.int32, device=x.device)
             a.key = saved.data_ptr()
+        else:
+            saved = torch.empty((x.numel() // 8,), dtype=torch.uint8, device=x.device)
+            a.keep_bits = saved.data_ptr()
     _call("cm_gelu_dropout_fwd", lib.cm_gelu_dropout_fwd_v2, C.byref(a), cabi.stream_ptr())
     return y, saved
 
@@ -1054,8 +1059,10 @@ def gelu_dropout_backward(x, dy, saved, p_drop, colsum_cols=0, defer=False):
     a.x, a.dy, a.dx, a.n, a.dtype = x.data_ptr(), dy.data_ptr(), dx.data_ptr(), x.numel(), cabi.dtype_code(x.dtype)
     a.p_drop = float(p_drop) if saved is not None else 0.0
     if saved is not None:
-        if saved.dtype == torch.uint8:
+        if saved.dtype == torch.uint8 and saved.numel() == x.numel():
             a.mask = saved.data_ptr()
+        elif saved.dtype == torch.uint8:
+            a.keep_bits = saved.data_ptr()
         else:
             a.key = saved.data_ptr()
     part = None

@@ -466,7 +466,10 @@ def test_stem_envelope_and_ab_switch(monkeypatch):
 # cm_gelu_dropout_*_v2: the dropout mask regenerated in backward from the forward's key, bias gradient inside the kernel
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("shape", [(3, 37, 1024), (64, 501, 1024), (5, 7, 2048), (9, 64), (4, 33, 576), (2, 11, 8)])
-def test_gelu_dropout_regenerated_mask_and_fused_bias_gradient(dtype, shape):
+def test_gelu_dropout_regenerated_mask_and_fused_bias_gradient(dtype, shape, monkeypatch):
+    """The three ways backward can learn the dropout mask - the stored byte mask, the forward's key (mask re-hashed, nothing
+    stored: CM_DROPOUT_REGEN=1) and the keep bits (the default: one byte per eight elements) - give the same output and the
+    same gradient bit for bit; the fused column sums of dx."""
     from mamba_asr_b200 import kernels as K
     from mamba_asr_b200.layernorm import DropoutSeed
     g = torch.Generator().manual_seed(11)
@@ -475,13 +478,20 @@ def test_gelu_dropout_regenerated_mask_and_fused_bias_gradient(dtype, shape):
     seed = DropoutSeed.tensor(x.device)
     cols = shape[-1]
     y0, mask = K.gelu_dropout_forward(x, 0.1, seed, 77, store_mask=True)
+    y2, bits = K.gelu_dropout_forward(x, 0.1, seed, 77, store_mask=False)
+    monkeypatch.setenv("CM_DROPOUT_REGEN", "1")
     y1, key = K.gelu_dropout_forward(x, 0.1, seed, 77, store_mask=False)
     assert mask.dtype == torch.uint8 and key.dtype == torch.int32 and key.numel() == 1
-    assert torch.equal(y0, y1)
+    assert bits.dtype == torch.uint8 and bits.numel() == x.numel() // 8
+    assert torch.equal(y0, y1) and torch.equal(y0, y2)
+    packed = (mask.reshape(-1, 8) != 0).to(torch.int32) * (2 ** torch.arange(8, device="cuda", dtype=torch.int32))
+    assert torch.equal(packed.sum(1).to(torch.uint8), bits)            # bit i of byte v = element 8 v + i kept
     DropoutSeed.advance(x.device)                       # the key was captured at forward time: a later advance is harmless
     dx0 = K.gelu_dropout_backward(x, dy, mask, 0.1)
     dx1, cs = K.gelu_dropout_backward(x, dy, key, 0.1, colsum_cols=cols)
-    assert torch.equal(dx0, dx1)
+    dx3, cs3 = K.gelu_dropout_backward(x, dy, bits, 0.1, colsum_cols=cols)
+    assert torch.equal(dx0, dx1) and torch.equal(dx0, dx3)
+    assert (cs is None and cs3 is None) or torch.equal(cs, cs3)
     assert torch.equal((dx1 == 0) | (dy == 0), (mask == 0) | (dy == 0) | (dx1 == 0))
     fused = bool(K.cabi.lib().cm_act_colsum_supported(x.numel(), cols))
     assert fused == (cols in (1024, 2048, 64, 8))

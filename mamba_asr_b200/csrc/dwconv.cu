@@ -305,6 +305,158 @@ __global__ void __launch_bounds__(32 * kDwWarps) dwconv_bwdw_tile_kernel(const c
   }
 }
 
+// ---- tensor-pipe forward / backward-data for 16-bit tensors (round 2, last session) ---------------------------------------
+// The tile kernel above is FP32-issue-bound: 31 FFMA-instructions per 32 outputs.  Per channel the conv is a banded Toeplitz
+// product, so it fits mma.sync.m16n8k16 (bf16 / fp16 operands, fp32 accumulate):
+//     Y[i][n] = sum_s sum_j A_s[i][j] * B_s[j][n],   i = time inside a 16-block, n = one of 8 consecutive 16-blocks,
+//     A_s[i][j] = w[16 s + j - i]  (0 outside the taps),   B_s[j][n] = x[16 n + 16 s + j]  (slab-relative time),  s < NS
+// i.e. 128 outputs of one channel take NS = 3 MMAs (K = 31) whose B fragments are two aligned 32-bit loads from a
+// [channel][time] shared tile, and the A fragments are built once per (CTA, channel) from the taps (a Toeplitz block has only
+// 3 distinct register pairs per slice: A[g+8][2t+8..] = A[g][2t..]).  The taps are rounded to the tensors' 16-bit type - what
+// the reference's autocast conv does with its fp32 weights.  CTA = 4 warps = 32 channels x 128 times of one batch: 16-byte
+// global loads scattered into the channel-major tile (odd word stride: conflict-free) -> a warp takes 8 channels in turn and
+// keeps their accumulators, so that a lane stores 16-byte rows (8 adjacent channels) of its 4 times.  fp32 tensors keep the
+// FFMA kernel.
+constexpr int kDmT = 128;                    // output times per CTA
+template <int K> struct DwMma {
+  static constexpr int NS = (16 + K - 1 + 15) / 16;      // K slices of 16 input times (K = 31: 3)
+  static constexpr int RX = kDmT - 16 + 16 * NS;         // slab rows (input times) the MMAs read (K = 31: 160)
+  static constexpr int XT = RX + 2;                      // row stride of the transposed tile in elements: 81 words for K = 31
+  static_assert((XT / 2) % 2 == 1, "odd word stride keeps the transpose conflict-free");
+};
+
+template <typename T> struct Mma16;
+template <> struct Mma16<__nv_bfloat16> {
+  static __device__ __forceinline__ void mma(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  }
+  static __device__ __forceinline__ unsigned short cvt(float v) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    return *reinterpret_cast<const unsigned short*>(&h);
+  }
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+};
+template <> struct Mma16<__half> {
+  static __device__ __forceinline__ void mma(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  }
+  static __device__ __forceinline__ unsigned short cvt(float v) {
+    const __half h = __float2half_rn(v);
+    return *reinterpret_cast<const unsigned short*>(&h);
+  }
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+};
+
+template <typename T, int K>
+__global__ void __launch_bounds__(128) dwconv_fwd_mma_kernel(const cm_dwconv_args p) {
+  using DM = DwMma<K>;
+  constexpr int NS = DM::NS, RX = DM::RX, XT = DM::XT;
+  constexpr int WP = 16 * NS + 32;             // padded tap row: index k + 16 for k in [-16, 16 NS + 16)
+  extern __shared__ __align__(16) unsigned char dw_smem[];
+  unsigned short* xt = reinterpret_cast<unsigned short*>(dw_smem);             // [32][XT]   slab, channel-major
+  unsigned short* wp = xt + 32 * XT;                                           // [32][WP]   zero-padded 16-bit taps
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c_blk = blockIdx.x * 32;
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.y * kDmT;
+  const int L = p.seqlen;
+  // slab rows t0 - pad_left .. + RX: every 16-byte chunk (one time, 8 channels) is requested first, ...
+  constexpr int NCH = (RX * 4 + 127) / 128;     // chunks per thread
+  uint4 chunk[NCH];
+  {
+    const T* xb = static_cast<const T*>(p.x.ptr) + b * p.x.sb;
+#pragma unroll
+    for (int q = 0; q < NCH; ++q) {
+      const int i = tid + 128 * q;
+      const int row = i >> 2, ch = i & 3;
+      const int r = t0 - p.pad_left + row, c = c_blk + ch * 8;
+      const bool ok = i < RX * 4 && r >= 0 && r < L && c < p.dim;
+      chunk[q] = ok ? __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)r * p.x.sl + c)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  // taps of the CTA's 32 channels, rounded to T, zero outside [0, K)
+  for (int i = tid; i < 32 * WP; i += 128) {
+    const int c = i / WP, k = i - c * WP - 16;
+    const int ch = c_blk + c;
+    float v = 0.f;
+    if (k >= 0 && k < K && ch < p.dim) v = __ldg(p.weight + (int64_t)ch * K + (p.flip ? K - 1 - k : k));
+    wp[i] = Mma16<T>::cvt(v);
+  }
+  // ... then scattered into the channel-major tile: 8 two-byte stores per chunk.  A warp covers 8 rows x 4 chunks; for one
+  // channel of the chunk the banks are 8 * chunk + row / 2 (word stride XT / 2 is odd): conflict-free
+#pragma unroll
+  for (int q = 0; q < NCH; ++q) {
+    const int i = tid + 128 * q;
+    if (i < RX * 4) {
+      const int row = i >> 2, ch = i & 3;
+      unsigned short* dst = xt + (ch * 8) * XT + row;
+      const uint32_t w4[4] = {chunk[q].x, chunk[q].y, chunk[q].z, chunk[q].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        dst[(2 * e) * XT] = (unsigned short)(w4[e] & 0xffffu);
+        dst[(2 * e + 1) * XT] = (unsigned short)(w4[e] >> 16);
+      }
+    }
+  }
+  __syncthreads();
+  const int g = lane >> 2, t = lane & 3;
+  const int cw = c_blk + 8 * warp;              // the warp's 8 channels
+  if (cw >= p.dim) return;                      // dim is a multiple of 8: a warp's channels are all inside or all outside
+  float acc[8][4];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int cl = 8 * warp + q;                // channel inside the CTA
+    const unsigned short* wrow = wp + cl * WP + 16;
+    const unsigned short* xrow = xt + cl * XT;
+    const float bias = p.bias != nullptr ? __ldg(p.bias + cw + q) : 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[q][e] = bias;
+#pragma unroll
+    for (int sl = 0; sl < NS; ++sl) {
+      // A_s[i][j] = w[16 s + j - i]: a0 = (row g, cols 2t, 2t+1), a1 = (row g + 8, same cols), a2 = (row g, cols 2t + 8, + 9),
+      // a3 = (row g + 8, cols 2t + 8, + 9) = a0
+      const int kb = 16 * sl + 2 * t - g;
+      const uint32_t a0 = (uint32_t)wrow[kb] | ((uint32_t)wrow[kb + 1] << 16);
+      const uint32_t a1 = (uint32_t)wrow[kb - 8] | ((uint32_t)wrow[kb - 7] << 16);
+      const uint32_t a2 = (uint32_t)wrow[kb + 8] | ((uint32_t)wrow[kb + 9] << 16);
+      // B_s[j][n] = x[16 n + 16 s + j]: b0 = (rows 2t, 2t+1, col g), b1 = (rows 2t + 8, + 9, col g)
+      const uint32_t* xb32 = reinterpret_cast<const uint32_t*>(xrow + 16 * g + 16 * sl + 2 * t);
+      Mma16<T>::mma(acc[q], a0, a1, a2, a0, xb32[0], xb32[4]);
+    }
+  }
+  // accumulators of channel q: (time 16 * 2t + g, 16 * (2t + 1) + g) in slots 0, 1 and the same + 8 in slots 2, 3
+  T* yb = static_cast<T*>(p.y.ptr) + b * p.y.sb + cw;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int tt = t0 + 16 * (2 * t + (e & 1)) + g + 8 * (e >> 1);
+    if (tt < L) {
+      uint4 v;
+      v.x = Mma16<T>::pack(acc[0][e], acc[1][e]); v.y = Mma16<T>::pack(acc[2][e], acc[3][e]);
+      v.z = Mma16<T>::pack(acc[4][e], acc[5][e]); v.w = Mma16<T>::pack(acc[6][e], acc[7][e]);
+      *reinterpret_cast<uint4*>(yb + (int64_t)tt * p.y.sl) = v;
+    }
+  }
+}
+
+template <typename T>
+static bool dw_mma_ok(const cm_dwconv_args& a) {
+  // opt-in (CM_DWCONV_MMA=1): measured EQUAL to the FFMA tile kernel at 64 x 501 x 256 (22.4 vs 22.5 us in the step, 9.6 M vs
+  // 13.1 M instructions: the 16-bit shared-memory traffic of the transposed tile and of the Toeplitz fragments - 34 % LSU, mio
+  // throttle 3.9 per issue - replaces the FFMA issue slots it removes), and the FFMA kernel keeps fp32 taps
+  const char* on = getenv("CM_DWCONV_MMA");
+  if (sizeof(T) != 2 || on == nullptr || on[0] == '0') return false;
+  // 16-byte output rows of 8 channels: y rows and the channel offset of a warp must be 16-byte aligned
+  return a.y.ptr != nullptr && a.y.sd == 1 && (reinterpret_cast<uintptr_t>(a.y.ptr) & 15) == 0 && a.y.sl % 8 == 0 && a.y.sb % 8 == 0;
+}
+
 // the tiled kernels need channel-last tensors whose rows can be fetched in 16-byte chunks
 template <typename T>
 static bool dw_tile_ok(const cm_dwconv_args& a, bool wgrad) {
@@ -330,6 +482,13 @@ static int dw_launch(const cm_dwconv_args& a, bool wgrad, cudaStream_t st) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
       if (e != cudaSuccess) return (int)e;
       kern<<<grid, 32 * kDwWarps, smem, st>>>(a);
+    } else if (dw_mma_ok<T>(a)) {
+      if constexpr (sizeof(T) == 2) {
+        using DM = DwMma<K>;
+        const size_t smem = (size_t)(32 * DM::XT + 32 * (16 * DM::NS + 32)) * 2;
+        const dim3 mgrid(cm_ceil_div(a.dim, 32), cm_ceil_div(a.seqlen, kDmT), a.batch);
+        dwconv_fwd_mma_kernel<T, K><<<mgrid, 128, smem, st>>>(a);
+      }
     } else {
       const size_t smem = (size_t)DwFwd<K>::RX * 32 * sizeof(T);
       const dim3 fgrid(cm_ceil_div(a.dim, 32), cm_ceil_div(a.seqlen, DwFwd<K>::FTW), a.batch);

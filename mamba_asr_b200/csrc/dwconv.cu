@@ -359,10 +359,11 @@ template <typename T, int K>
 __global__ void __launch_bounds__(128) dwconv_fwd_mma_kernel(const cm_dwconv_args p) {
   using DM = DwMma<K>;
   constexpr int NS = DM::NS, RX = DM::RX, XT = DM::XT;
-  constexpr int WP = 16 * NS + 32;             // padded tap row: index k + 16 for k in [-16, 16 NS + 16)
+  constexpr int WP = 64;                       // tap-pair row: entry k + 16 = (w[k], w[k + 1]) for k in [-16, 48)
+  static_assert(NS <= 3, "the tap-pair row covers three K slices");
   extern __shared__ __align__(16) unsigned char dw_smem[];
-  unsigned short* xt = reinterpret_cast<unsigned short*>(dw_smem);             // [32][XT]   slab, channel-major
-  unsigned short* wp = xt + 32 * XT;                                           // [32][WP]   zero-padded 16-bit taps
+  uint32_t* wp = reinterpret_cast<uint32_t*>(dw_smem);                         // [32][WP]   packed 16-bit tap pairs
+  unsigned short* xt = reinterpret_cast<unsigned short*>(wp + 32 * WP);        // [32][XT]   slab, channel-major
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c_blk = blockIdx.x * 32;
   const int b = blockIdx.z;
@@ -382,13 +383,26 @@ __global__ void __launch_bounds__(128) dwconv_fwd_mma_kernel(const cm_dwconv_arg
       chunk[q] = ok ? __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)r * p.x.sl + c)) : make_uint4(0u, 0u, 0u, 0u);
     }
   }
-  // taps of the CTA's 32 channels, rounded to T, zero outside [0, K)
-  for (int i = tid; i < 32 * WP; i += 128) {
-    const int c = i / WP, k = i - c * WP - 16;
-    const int ch = c_blk + c;
-    float v = 0.f;
-    if (k >= 0 && k < K && ch < p.dim) v = __ldg(p.weight + (int64_t)ch * K + (p.flip ? K - 1 - k : k));
-    wp[i] = Mma16<T>::cvt(v);
+  // taps of the CTA's 32 channels as PAIRS (w[k], w[k + 1]) rounded to T, zero outside [0, K): a Toeplitz fragment register
+  // is then one 32-bit load (as single 16-bit entries the fragment build was 18 loads + 9 merges per channel and lane)
+  // (all 32 tap loads of a thread are requested before the first is used: rolled, this loop was 16 L2 round trips in a row)
+  {
+    constexpr int NW = 32 * WP / 128;
+    float v0[NW], v1[NW];
+#pragma unroll
+    for (int q = 0; q < NW; ++q) {
+      const int i = tid + 128 * q;
+      const int c = i >> 6, k = (i & 63) - 16;
+      const int ch = c_blk + c;
+      const bool in0 = ch < p.dim && k >= 0 && k < K, in1 = ch < p.dim && k + 1 >= 0 && k + 1 < K;
+      const float* wr = p.weight + (int64_t)(ch < p.dim ? ch : 0) * K;
+      v0[q] = __ldg(wr + (in0 ? (p.flip ? K - 1 - k : k) : 0));
+      v1[q] = __ldg(wr + (in1 ? (p.flip ? K - 2 - k : k + 1) : 0));
+      if (!in0) v0[q] = 0.f;
+      if (!in1) v1[q] = 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < NW; ++q) wp[tid + 128 * q] = Mma16<T>::pack(v0[q], v1[q]);
   }
   // ... then scattered into the channel-major tile: 8 two-byte stores per chunk.  A warp covers 8 rows x 4 chunks; for one
   // channel of the chunk the banks are 8 * chunk + row / 2 (word stride XT / 2 is odd): conflict-free
@@ -414,7 +428,7 @@ __global__ void __launch_bounds__(128) dwconv_fwd_mma_kernel(const cm_dwconv_arg
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const int cl = 8 * warp + q;                // channel inside the CTA
-    const unsigned short* wrow = wp + cl * WP + 16;
+    const uint32_t* wrow = wp + cl * WP + 16;
     const unsigned short* xrow = xt + cl * XT;
     const float bias = p.bias != nullptr ? __ldg(p.bias + cw + q) : 0.f;
 #pragma unroll
@@ -424,9 +438,7 @@ __global__ void __launch_bounds__(128) dwconv_fwd_mma_kernel(const cm_dwconv_arg
       // A_s[i][j] = w[16 s + j - i]: a0 = (row g, cols 2t, 2t+1), a1 = (row g + 8, same cols), a2 = (row g, cols 2t + 8, + 9),
       // a3 = (row g + 8, cols 2t + 8, + 9) = a0
       const int kb = 16 * sl + 2 * t - g;
-      const uint32_t a0 = (uint32_t)wrow[kb] | ((uint32_t)wrow[kb + 1] << 16);
-      const uint32_t a1 = (uint32_t)wrow[kb - 8] | ((uint32_t)wrow[kb - 7] << 16);
-      const uint32_t a2 = (uint32_t)wrow[kb + 8] | ((uint32_t)wrow[kb + 9] << 16);
+      const uint32_t a0 = wrow[kb], a1 = wrow[kb - 8], a2 = wrow[kb + 8];
       // B_s[j][n] = x[16 n + 16 s + j]: b0 = (rows 2t, 2t+1, col g), b1 = (rows 2t + 8, + 9, col g)
       const uint32_t* xb32 = reinterpret_cast<const uint32_t*>(xrow + 16 * g + 16 * sl + 2 * t);
       Mma16<T>::mma(acc[q], a0, a1, a2, a0, xb32[0], xb32[4]);
@@ -448,11 +460,9 @@ __global__ void __launch_bounds__(128) dwconv_fwd_mma_kernel(const cm_dwconv_arg
 
 template <typename T>
 static bool dw_mma_ok(const cm_dwconv_args& a) {
-  // opt-in (CM_DWCONV_MMA=1): measured EQUAL to the FFMA tile kernel at 64 x 501 x 256 (22.4 vs 22.5 us in the step, 9.6 M vs
-  // 13.1 M instructions: the 16-bit shared-memory traffic of the transposed tile and of the Toeplitz fragments - 34 % LSU, mio
-  // throttle 3.9 per issue - replaces the FFMA issue slots it removes), and the FFMA kernel keeps fp32 taps
-  const char* on = getenv("CM_DWCONV_MMA");
-  if (sizeof(T) != 2 || on == nullptr || on[0] == '0') return false;
+  // default for 16-bit tensors (17.5 us against 22.5 us for the FFMA tile kernel at 64 x 501 x 256 in the step);
+  // CM_DWCONV_NO_MMA=1 keeps the FFMA kernel (fp32 taps)
+  if (sizeof(T) != 2 || getenv("CM_DWCONV_NO_MMA") != nullptr) return false;
   // 16-byte output rows of 8 channels: y rows and the channel offset of a warp must be 16-byte aligned
   return a.y.ptr != nullptr && a.y.sd == 1 && (reinterpret_cast<uintptr_t>(a.y.ptr) & 15) == 0 && a.y.sl % 8 == 0 && a.y.sb % 8 == 0;
 }
@@ -485,7 +495,7 @@ static int dw_launch(const cm_dwconv_args& a, bool wgrad, cudaStream_t st) {
     } else if (dw_mma_ok<T>(a)) {
       if constexpr (sizeof(T) == 2) {
         using DM = DwMma<K>;
-        const size_t smem = (size_t)(32 * DM::XT + 32 * (16 * DM::NS + 32)) * 2;
+        const size_t smem = (size_t)32 * DM::XT * 2 + (size_t)32 * 64 * 4;
         const dim3 mgrid(cm_ceil_div(a.dim, 32), cm_ceil_div(a.seqlen, kDmT), a.batch);
         dwconv_fwd_mma_kernel<T, K><<<mgrid, 128, smem, st>>>(a);
       }

@@ -350,14 +350,16 @@ def test_glu_kernels_match_torch_glu(shape, dtype):
 
 @pytest.mark.parametrize("ksize,causal", [(31, False), (31, True), (15, False), (7, False), (3, True)])
 @pytest.mark.parametrize("shape", [(2, 501, 256), (3, 67, 144), (1, 5, 33), (2, 94, 64)])
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, "bf16-mma", "fp16-mma"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16, "bf16-ffma"])
 def test_depthwise_conv1d_matches_torch_conv1d(ksize, causal, shape, dtype, monkeypatch):
     """cm_dwconv_fwd / cm_dwconv_bwd_weight against the reference's own op (nn.Conv1d(C, C, K, padding, groups=C),
     modules/Conmamba.py:281-290) evaluated in fp32 on the same (rounded) inputs: y, dx, dweight, dbias."""
     from mamba_asr_b200.dwconv import depthwise_conv1d
-    if isinstance(dtype, str):        # the opt-in tensor-pipe forward / backward-data kernel (taps rounded to the 16-bit type)
-        monkeypatch.setenv("CM_DWCONV_MMA", "1")
-        dtype = torch.bfloat16 if dtype.startswith("bf16") else torch.float16
+    # 16-bit tensors take the tensor-pipe forward / backward-data kernel (taps rounded to the 16-bit type) by default;
+    # "bf16-ffma" keeps them on the FFMA tile kernel (CM_DWCONV_NO_MMA=1)
+    if isinstance(dtype, str):
+        monkeypatch.setenv("CM_DWCONV_NO_MMA", "1")
+        dtype = torch.bfloat16
     Bt, L, Cn = shape
     g = torch.Generator().manual_seed(9)
     x = torch.randn(Bt, L, Cn, generator=g).to(dtype).cuda()

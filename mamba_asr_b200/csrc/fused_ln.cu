@@ -386,9 +386,42 @@ __global__ void __launch_bounds__(32 * kFlWarps) add_ln_fwd_q_kernel(const cm_ad
 #ifndef CM_FLQ_MINB
 #define CM_FLQ_MINB 3
 #endif
-template <typename Ta, typename Tb, typename Ty, int NQ, bool COLSUM>
+// NST > 0: the rows of s, ds and dy come through shared memory - lane 0 of a warp requests the warp's rows NST - 1
+// iterations ahead as 1-D bulk copies (cp.async.bulk, one mbarrier per warp and stage), so a warp keeps NST - 1 rows of
+// loads in flight while it reduces and stores the current one.  With one row per warp and iteration in registers the SM
+// holds ~30 KB of loads in flight on average, below the latency x bandwidth product of HBM3e (53-65 % of the copy peak).
+__device__ __forceinline__ uint32_t fl_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void fl_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(fl_smem_u32(dst)), "l"(src), "r"(bytes), "r"(fl_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fl_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(fl_smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+template <typename T> struct Fl4s;     // a quad out of a staged row (plain shared-memory loads)
+template <> struct Fl4s<float> {
+  static __device__ __forceinline__ void ld(const unsigned char* p, float* o) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+};
+template <> struct Fl4s<__nv_bfloat16> {
+  static __device__ __forceinline__ void ld(const unsigned char* p, float* o) {
+    const uint2 r = *reinterpret_cast<const uint2*>(p);
+    o[0] = __uint_as_float(r.x << 16); o[1] = __uint_as_float(r.x & 0xffff0000u);
+    o[2] = __uint_as_float(r.y << 16); o[3] = __uint_as_float(r.y & 0xffff0000u);
+  }
+};
+
+template <typename Ta, typename Tb, typename Ty, int NQ, bool COLSUM, int NST = 0>
 __global__ void __launch_bounds__(32 * kFlWarps, (NQ <= 2 ? CM_FLQ_MINB : NQ <= 4 ? 2 : 1)) add_ln_bwd_q_kernel(const cm_add_ln_args A) {
   __shared__ float4 red[kFlWarps][32 * NQ + 1];   // reused for dgamma, dbeta and the db column sums
+  extern __shared__ __align__(128) unsigned char fl_stage[];          // NST > 0: [warp][stage][s | ds | dy]
+  __shared__ uint64_t fl_bar[kFlWarps][NST > 0 ? NST : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int C = A.cols, nq = C >> 2;
   const Ta* sx = static_cast<const Ta*>(A.s);
@@ -411,9 +444,47 @@ __global__ void __launch_bounds__(32 * kFlWarps, (NQ <= 2 ? CM_FLQ_MINB : NQ <= 
     }
   const float invC = 1.f / (float)C;
   const int64_t rstep = (int64_t)gridDim.x * kFlWarps;
+  const uint32_t seg_a = (uint32_t)C * (uint32_t)sizeof(Ta), seg_y = (uint32_t)C * (uint32_t)sizeof(Ty);
+  const uint32_t row_bytes = 2 * seg_a + seg_y;
+  unsigned char* const stage0 = fl_stage + (size_t)warp * (NST > 0 ? NST : 1) * row_bytes;
+  auto request = [&](int64_t r, int st_i) {         // lane 0: the three row segments of row r into stage st_i
+    uint64_t* bar = &fl_bar[warp][st_i];
+    unsigned char* dst = stage0 + (size_t)st_i * row_bytes;
+    const uint32_t total = seg_a + seg_y + (ds != nullptr ? seg_a : 0u);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fl_smem_u32(bar)), "r"(total) : "memory");
+    fl_bulk_g2s(dst, sx + r * A.s_stride, seg_a, bar);
+    if (ds != nullptr) fl_bulk_g2s(dst + seg_a, ds + r * A.ds_stride, seg_a, bar);
+    fl_bulk_g2s(dst + 2 * seg_a, dy + r * A.dy_stride, seg_y, bar);
+  };
+  int st_cur = 0;
+  uint32_t st_par = 0;
+  if (NST > 0) {
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < (NST > 0 ? NST : 1); ++i)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fl_smem_u32(&fl_bar[warp][i])) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      int64_t r = (int64_t)blockIdx.x * kFlWarps + warp;
+      for (int i = 0; i < NST - 1 && r < A.rows; ++i, r += rstep) request(r, i);
+    }
+    __syncwarp();
+  }
   for (int64_t row = (int64_t)blockIdx.x * kFlWarps + warp; row < A.rows; row += rstep) {
     float xh[NQ][4], gy[NQ][4], e4[NQ][4];
     const float mu = __ldg(A.mean + row), rs = __ldg(A.rstd + row);
+    if (NST > 0) {
+      // the stage read in the previous iteration is free (every lane's loads fed the shuffles of that iteration): refill it
+      __syncwarp();
+      if (lane == 0) {
+        const int64_t rn = row + (int64_t)(NST - 1) * rstep;
+        if (rn < A.rows) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          request(rn, st_cur == 0 ? NST - 1 : st_cur - 1);
+        }
+      }
+      fl_mbar_wait(&fl_bar[warp][st_cur], st_par);
+    }
+    const unsigned char* const stg = stage0 + (size_t)st_cur * row_bytes;
 #pragma unroll
     for (int i = 0; i < NQ; ++i) {
       const int qi = lane + 32 * i;
@@ -421,10 +492,19 @@ __global__ void __launch_bounds__(32 * kFlWarps, (NQ <= 2 ? CM_FLQ_MINB : NQ <= 
 #pragma unroll
       for (int e = 0; e < 4; ++e) xh[i][e] = gy[i][e] = e4[i][e] = 0.f;
       if (in) {
-        Fl4<Ta>::ld(sx + row * A.s_stride + 4 * qi, xh[i]);
-        Fl4<Ty>::ld(dy + row * A.dy_stride + 4 * qi, gy[i]);
-        if (ds != nullptr) Fl4<Ta>::ld(ds + row * A.ds_stride + 4 * qi, e4[i]);
+        if (NST > 0) {
+          Fl4s<Ta>::ld(stg + 4 * sizeof(Ta) * qi, xh[i]);
+          Fl4s<Ty>::ld(stg + 2 * seg_a + 4 * sizeof(Ty) * qi, gy[i]);
+          if (ds != nullptr) Fl4s<Ta>::ld(stg + seg_a + 4 * sizeof(Ta) * qi, e4[i]);
+        } else {
+          Fl4<Ta>::ld(sx + row * A.s_stride + 4 * qi, xh[i]);
+          Fl4<Ty>::ld(dy + row * A.dy_stride + 4 * qi, gy[i]);
+          if (ds != nullptr) Fl4<Ta>::ld(ds + row * A.ds_stride + 4 * qi, e4[i]);
+        }
       }
+    }
+    if (NST > 0) {
+      if (++st_cur == NST) { st_cur = 0; st_par ^= 1u; }
     }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -522,6 +602,43 @@ static bool quad_ok(const cm_add_ln_args& a, bool bwd) {
          al(a.dbsum_part, 16);
 }
 
+// the staged backward (bulk copies): whole 16-byte units per row segment, 16-byte aligned rows
+template <typename Ta, typename Ty>
+static bool staged_ok(const cm_add_ln_args& a) {
+  static const bool off = getenv("CM_ADD_LN_NO_STAGE") != nullptr;     // A/B switch: rows loaded straight into registers
+  if (off || (a.cols & 7)) return false;
+  auto ok = [](const void* p, int64_t stride, size_t es) {
+    return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && ((stride * (int64_t)es) & 15) == 0);
+  };
+  return ok(a.s, a.s_stride, sizeof(Ta)) && ok(a.ds, a.ds_stride, sizeof(Ta)) && ok(a.dy, a.dy_stride, sizeof(Ty));
+}
+template <typename Ta, typename Tb, typename Ty>
+static int add_ln_bwd_staged(const cm_add_ln_args& a, int nblk, cudaStream_t st) {
+  const int C = a.cols;
+  const size_t row_bytes = (size_t)C * (2 * sizeof(Ta) + sizeof(Ty));
+  // three stages (two rows of loads in flight per warp) while 3 CTAs / SM still fit beside the reduction buffer, else two
+  const bool three = 3 * (3 * kFlWarps * row_bytes + 10 * 1024) <= 227 * 1024;
+  const size_t smem = (three ? 3 : 2) * kFlWarps * row_bytes;
+  const bool cs = a.dbsum_part != nullptr && a.db != nullptr;
+#define FL_BS(N, CS, NS)                                                                            \
+  do {                                                                                              \
+    auto kern = add_ln_bwd_q_kernel<Ta, Tb, Ty, N, CS, NS>;                                         \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return (int)e;                                                            \
+    kern<<<nblk, 32 * kFlWarps, smem, st>>>(a);                                                     \
+  } while (0)
+#define FL_BS2(N)                                                                                   \
+  do {                                                                                              \
+    if (cs) { if (three) FL_BS(N, true, 3); else FL_BS(N, true, 2); }                               \
+    else    { if (three) FL_BS(N, false, 3); else FL_BS(N, false, 2); }                             \
+  } while (0)
+  if (C <= 128) FL_BS2(1); else FL_BS2(2);
+#undef FL_BS2
+#undef FL_BS
+  CM_LAUNCH_CHECK();
+  return 0;
+}
+
 template <typename Ta, typename Tb, typename Ty>
 static int add_ln_launch(const cm_add_ln_args& a, bool bwd, cudaStream_t st) {
   const int C = a.cols;
@@ -533,6 +650,7 @@ static int add_ln_launch(const cm_add_ln_args& a, bool bwd, cudaStream_t st) {
 #undef FL_FQ
     } else {
       const int nblk = cm_add_ln_num_part(a.rows, a.cols);
+      if (C <= 256 && staged_ok<Ta, Ty>(a)) return add_ln_bwd_staged<Ta, Tb, Ty>(a, nblk, st);
 #define FL_BQ(N)                                                                                   \
   do {                                                                                             \
     if (a.dbsum_part != nullptr && a.db != nullptr)                                                \

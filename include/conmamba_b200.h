@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CM_ABI_VERSION 16
+#define CM_ABI_VERSION 17
 
 /* element type of activations (u, delta, z, B, C, x, out, and their gradients) */
 enum { CM_F32 = 0, CM_BF16 = 1, CM_F16 = 2 };
@@ -307,11 +307,15 @@ typedef struct {
                                             pair after the depthwise conv of the convolution module, modules/Conmamba.py:
                                             292-301).  Backward then takes dy for the activated output and needs beta.
                                             Only for even cols / strides and 8-byte aligned pointers (else UNSUPPORTED). */
-  int32_t reserved;
+  int32_t n_part;                        /* v17 (was reserved): partial rows allocated for dgamma_part / dbeta_part =
+                                            cm_layernorm_num_part2(rows, cols); 0 = cm_layernorm_num_part(rows) */
 } cm_layernorm_args;
 #define CM_LN_OUT_GELU 1
 
 int cm_layernorm_num_part(int64_t rows);
+/* v17: partial rows of cm_layernorm_bwd for this row width; pass the value as args.n_part.  For cols % 4 == 0 the backward
+ * then runs the 16-byte-access kernels of cm_add_ln_bwd (rows staged through shared memory by bulk copies for cols <= 256). */
+int cm_layernorm_num_part2(int64_t rows, int32_t cols);
 int cm_layernorm_fwd(const cm_layernorm_args* args, void* stream);
 int cm_layernorm_bwd(const cm_layernorm_args* args, void* stream);
 

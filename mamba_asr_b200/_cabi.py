@@ -17,7 +17,7 @@ CM_ERR_BAD_ARG, CM_ERR_UNSUPPORTED = -1, -2
 CM_FLAG_DELTA_SOFTPLUS = 1
 CM_FLAG_SILU = 1
 CM_SCAN_CKPT_STEPS = 8
-CM_ABI_VERSION = 16
+CM_ABI_VERSION = 17
 CM_LN_ACT_LEAKY_RELU, CM_LN_ACT_GELU = 0, 1
 CM_LN_OUT_GELU = 1
 
@@ -25,7 +25,7 @@ EXPORTS = (
     "cm_version", "cm_scan_num_ckpt", "cm_scan_slab_channels", "cm_scan_pick_lanes", "cm_scan_pick_lanes_bwd", "cm_scan_bwd_slab_channels", "cm_scan_fwd",
     "cm_scan_bwd",
     "cm_reduce_dbc", "cm_reduce_rows", "cm_conv_fwd", "cm_conv_num_part", "cm_conv_bwd", "cm_conv_update",
-    "cm_fbank_logmel", "cm_fbank_floor", "cm_abi_sizeof", "cm_reduce_multi", "cm_layernorm_num_part", "cm_layernorm_fwd",
+    "cm_fbank_logmel", "cm_fbank_floor", "cm_abi_sizeof", "cm_reduce_multi", "cm_layernorm_num_part", "cm_layernorm_num_part2", "cm_layernorm_fwd",
     "cm_layernorm_bwd", "cm_scan_fwd_workspace_bytes", "cm_dwconv_num_part", "cm_dwconv_fwd", "cm_dwconv_bwd_weight", "cm_colsum_num_part", "cm_colsum",
     "cm_ssm_step", "cm_add_ln_fwd", "cm_add_ln_bwd", "cm_gelu_dropout_fwd", "cm_gelu_dropout_bwd", "cm_tsmm_num_part", "cm_tsmm",
     "cm_ln_act_num_part", "cm_ln_act_fwd", "cm_ln_act_bwd", "cm_optim_num_part", "cm_sumsq_partial", "cm_adamw_step",
@@ -163,7 +163,7 @@ class LayerNormArgs(C.Structure):
         ("x", C.c_void_p), ("x_stride", C.c_int64), ("y", C.c_void_p), ("y_stride", C.c_int64),
         ("gamma", C.c_void_p), ("beta", C.c_void_p), ("mean", C.c_void_p), ("rstd", C.c_void_p),
         ("dy", C.c_void_p), ("dy_stride", C.c_int64), ("dx", C.c_void_p), ("dx_stride", C.c_int64),
-        ("dgamma_part", C.c_void_p), ("dbeta_part", C.c_void_p), ("act", C.c_int32), ("reserved", C.c_int32),
+        ("dgamma_part", C.c_void_p), ("dbeta_part", C.c_void_p), ("act", C.c_int32), ("n_part", C.c_int32),
     ]
 
 
@@ -270,6 +270,7 @@ def lib():
         L.cm_scan_fwd_workspace_bytes.argtypes = [C.POINTER(ScanFwdArgs)]
         L.cm_scan_fwd_workspace_bytes.restype = C.c_int64
         L.cm_layernorm_num_part.argtypes = [C.c_int64]
+        L.cm_layernorm_num_part2.argtypes = [C.c_int64, C.c_int32]
         L.cm_layernorm_fwd.argtypes = [C.POINTER(LayerNormArgs), C.c_void_p]
         L.cm_layernorm_bwd.argtypes = [C.POINTER(LayerNormArgs), C.c_void_p]
         L.cm_colsum_num_part.argtypes = [C.c_int64]

@@ -417,7 +417,9 @@ template <> struct Fl4s<__nv_bfloat16> {
   }
 };
 
-template <typename Ta, typename Tb, typename Ty, int NQ, bool COLSUM, int NST = 0>
+// ACT: dy is the gradient of gelu(LayerNorm(s)) (the GELU epilogue of cm_layernorm_fwd, routed here by cm_layernorm_bwd):
+// the pre-activation h * gamma + beta is recomputed and dy multiplied by gelu'(.) on the way in.
+template <typename Ta, typename Tb, typename Ty, int NQ, bool COLSUM, int NST = 0, bool ACT = false>
 __global__ void __launch_bounds__(32 * kFlWarps, (NQ <= 2 ? CM_FLQ_MINB : NQ <= 4 ? 2 : 1)) add_ln_bwd_q_kernel(const cm_add_ln_args A) {
   __shared__ float4 red[kFlWarps][32 * NQ + 1];   // reused for dgamma, dbeta and the db column sums
   extern __shared__ __align__(128) unsigned char fl_stage[];          // NST > 0: [warp][stage][s | ds | dy]
@@ -513,10 +515,13 @@ __global__ void __launch_bounds__(32 * kFlWarps, (NQ <= 2 ? CM_FLQ_MINB : NQ <= 
       const bool in = qi < nq;
       const float4 gv = (A.gamma && in) ? __ldg(reinterpret_cast<const float4*>(A.gamma) + qi) : make_float4(1.f, 1.f, 1.f, 1.f);
       const float g4[4] = {gv.x, gv.y, gv.z, gv.w};
+      const float4 bv = (ACT && A.beta && in) ? __ldg(reinterpret_cast<const float4*>(A.beta) + qi) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float dv = gy[i][e];
+        float dv = gy[i][e];
         const float h = in ? (xh[i][e] - mu) * rs : 0.f;
+        if (ACT) dv *= gelu_grad_f(fmaf(h, g4[e], b4[e]));
         xh[i][e] = h;
         const float gg = dv * g4[e];
         gy[i][e] = gg;
@@ -612,24 +617,24 @@ static bool staged_ok(const cm_add_ln_args& a) {
   };
   return ok(a.s, a.s_stride, sizeof(Ta)) && ok(a.ds, a.ds_stride, sizeof(Ta)) && ok(a.dy, a.dy_stride, sizeof(Ty));
 }
-template <typename Ta, typename Tb, typename Ty>
+template <typename Ta, typename Tb, typename Ty, bool ACT = false>
 static int add_ln_bwd_staged(const cm_add_ln_args& a, int nblk, cudaStream_t st) {
   const int C = a.cols;
   const size_t row_bytes = (size_t)C * (2 * sizeof(Ta) + sizeof(Ty));
   // three stages (two rows of loads in flight per warp) while 3 CTAs / SM still fit beside the reduction buffer, else two
   const bool three = 3 * (3 * kFlWarps * row_bytes + 10 * 1024) <= 227 * 1024;
   const size_t smem = (three ? 3 : 2) * kFlWarps * row_bytes;
-  const bool cs = a.dbsum_part != nullptr && a.db != nullptr;
+  const bool cs = !ACT && a.dbsum_part != nullptr && a.db != nullptr;
 #define FL_BS(N, CS, NS)                                                                            \
   do {                                                                                              \
-    auto kern = add_ln_bwd_q_kernel<Ta, Tb, Ty, N, CS, NS>;                                         \
+    auto kern = add_ln_bwd_q_kernel<Ta, Tb, Ty, N, CS, NS, ACT>;                                    \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return (int)e;                                                            \
     kern<<<nblk, 32 * kFlWarps, smem, st>>>(a);                                                     \
   } while (0)
 #define FL_BS2(N)                                                                                   \
   do {                                                                                              \
-    if (cs) { if (three) FL_BS(N, true, 3); else FL_BS(N, true, 2); }                               \
+    if (cs) { if (three) FL_BS(N, (!ACT), 3); else FL_BS(N, (!ACT), 2); }                           \
     else    { if (three) FL_BS(N, false, 3); else FL_BS(N, false, 2); }                             \
   } while (0)
   if (C <= 128) FL_BS2(1); else FL_BS2(2);
@@ -688,6 +693,32 @@ static int add_ln_dispatch(const cm_add_ln_args& a, bool bwd, cudaStream_t st) {
   if (a.a_dtype == CM_F32 && bd == CM_F32 && a.y_dtype == CM_F32) GO(float, float, float);
   if (a.a_dtype == CM_BF16 && bd == CM_BF16 && a.y_dtype == CM_BF16) GO(__nv_bfloat16, __nv_bfloat16, __nv_bfloat16);
   if (a.a_dtype == CM_BF16 && bd == CM_BF16 && a.y_dtype == CM_F32) GO(__nv_bfloat16, __nv_bfloat16, float);
+#undef GO
+  return CM_ERR_UNSUPPORTED;
+}
+
+// cm_layernorm_bwd through the quad kernels above (layernorm.cu): LayerNorm backward is cm_add_ln_bwd without ds / db.  `a`
+// carries s = x, da = dx, alpha = 1, p_drop = 0; `act`: the forward had the GELU epilogue (beta needed).  Any grid is valid
+// (persistent row loop); nblk = the partial rows the caller allocated.  CM_ERR_UNSUPPORTED: geometry not covered here.
+template <typename Ta, typename Ty, bool ACT>
+static int ln_bwd_routed_t(const cm_add_ln_args& a, int nblk, cudaStream_t st) {
+  using Tb = __nv_bfloat16;                                   // no b / db in this use
+  if (!quad_ok<Ta, Tb, Ty>(a, true)) return CM_ERR_UNSUPPORTED;
+  if (ACT && !al(a.beta, 16)) return CM_ERR_UNSUPPORTED;
+  const int C = a.cols;
+  if (C <= 256 && staged_ok<Ta, Ty>(a)) return add_ln_bwd_staged<Ta, Tb, Ty, ACT>(a, nblk, st);
+#define FL_BR(N) add_ln_bwd_q_kernel<Ta, Tb, Ty, N, false, 0, ACT><<<nblk, 32 * kFlWarps, 0, st>>>(a)
+  if (C <= 128) FL_BR(1); else if (C <= 256) FL_BR(2); else if (C <= 512) FL_BR(4); else FL_BR(8);
+#undef FL_BR
+  CM_LAUNCH_CHECK();
+  return 0;
+}
+int ln_bwd_routed(const cm_add_ln_args& a, int nblk, bool act, cudaStream_t st) {
+#define GO(TA, TY) return act ? ln_bwd_routed_t<TA, TY, true>(a, nblk, st) : ln_bwd_routed_t<TA, TY, false>(a, nblk, st)
+  if (a.a_dtype == CM_F32 && a.y_dtype == CM_BF16) GO(float, __nv_bfloat16);
+  if (a.a_dtype == CM_F32 && a.y_dtype == CM_F32) GO(float, float);
+  if (a.a_dtype == CM_BF16 && a.y_dtype == CM_BF16) GO(__nv_bfloat16, __nv_bfloat16);
+  if (a.a_dtype == CM_BF16 && a.y_dtype == CM_F32) GO(__nv_bfloat16, float);
 #undef GO
   return CM_ERR_UNSUPPORTED;
 }

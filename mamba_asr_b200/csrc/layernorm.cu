@@ -10,6 +10,7 @@
 // forms dx with two warp reductions per row and accumulates its lanes' columns of dgamma / dbeta in registers; CTAs
 // write one partial row each, summed in fixed order by cm_reduce_multi (deterministic, no atomics).
 // Roof: HBM; algorithmic bytes per row: forward C*(s_in + s_out), backward C*(s_in + 2*s_dy).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace cm {
@@ -382,14 +383,42 @@ extern "C" int cm_layernorm_fwd(const cm_layernorm_args* a, void* stream) {
   return CM_ERR_UNSUPPORTED;
 }
 
+namespace cm { int ln_bwd_routed(const cm_add_ln_args& a, int nblk, bool act, cudaStream_t st); }   // fused_ln.cu
+
+static bool ln_route_on() {
+  static const bool off = getenv("CM_LN_NO_ROUTE") != nullptr;      // A/B switch: the pair kernels of this file
+  return !off;
+}
+
+// v17: the partial rows cm_layernorm_bwd writes when the caller passes them as args.n_part - the grid of the kernel that
+// will run for this row width (the quad / staged kernels of fused_ln.cu for cols % 4 == 0)
+extern "C" int cm_layernorm_num_part2(int64_t rows, int32_t cols) {
+  if (ln_route_on() && cols > 0 && (cols & 3) == 0) return cm_add_ln_num_part(rows, cols);
+  return cm_layernorm_num_part(rows);
+}
+
 extern "C" int cm_layernorm_bwd(const cm_layernorm_args* a, void* stream) {
   if (!a || !a->x || !a->dy || !a->dx || !a->mean || !a->rstd || !a->dgamma_part || !a->dbeta_part) return CM_ERR_BAD_ARG;
-  if (a->rows <= 0 || a->cols <= 0) return CM_ERR_BAD_ARG;
+  if (a->rows <= 0 || a->cols <= 0 || a->n_part < 0) return CM_ERR_BAD_ARG;
   if (a->cols > 1024) return CM_ERR_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int nblk = cm_layernorm_num_part(a->rows);
+  const int nblk = a->n_part > 0 ? a->n_part : cm_layernorm_num_part(a->rows);
   if (a->act != 0 && a->act != CM_LN_OUT_GELU) return CM_ERR_BAD_ARG;
   if (a->act != 0 && a->beta != nullptr && (reinterpret_cast<uintptr_t>(a->beta) & 7) != 0) return CM_ERR_UNSUPPORTED;
+  if (a->n_part > 0 && ln_route_on() && (a->cols & 3) == 0) {
+    // LayerNorm backward = the residual-add LayerNorm backward without ds / db: 16-byte accesses, rows staged by bulk copies
+    cm_add_ln_args q{};
+    q.rows = a->rows; q.cols = a->cols;
+    q.a_dtype = a->x_dtype; q.b_dtype = CM_BF16; q.y_dtype = a->y_dtype;
+    q.alpha = 1.0f; q.p_drop = 0.0f;
+    q.s = const_cast<void*>(a->x); q.s_stride = a->x_stride;
+    q.dy = a->dy; q.dy_stride = a->dy_stride;
+    q.da = a->dx; q.da_stride = a->dx_stride;
+    q.gamma = a->gamma; q.beta = a->beta; q.mean = a->mean; q.rstd = a->rstd;
+    q.dgamma_part = a->dgamma_part; q.dbeta_part = a->dbeta_part;
+    const int rc = cm::ln_bwd_routed(q, nblk, a->act == CM_LN_OUT_GELU, st);
+    if (rc != CM_ERR_UNSUPPORTED) return rc;
+  }
 #define BWD(TI, TD) return cm::ln_bwd_launch<TI, TD>(a->x, a->dy, a->gamma, a->mean, a->rstd, a->dx, a->dgamma_part, \
                                                      a->dbeta_part, a->rows, a->cols, a->x_stride, a->dy_stride, a->dx_stride, nblk, \
                                                      a->beta, a->act, st)

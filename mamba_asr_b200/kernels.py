@@ -722,7 +722,7 @@ def layernorm_backward(x2d, dy2d, weight, mean, rstd, need_wgrad=True, defer=Fal
     if dy2d.stride(1) != 1:
         dy2d = dy2d.contiguous()
     dx = torch.empty((rows, Cn), dtype=x2d.dtype, device=x2d.device)
-    n_part = lib.cm_layernorm_num_part(rows)
+    n_part = lib.cm_layernorm_num_part2(rows, Cn)
     dg_part = torch.empty((n_part, Cn), dtype=torch.float32, device=x2d.device)
     db_part = torch.empty((n_part, Cn), dtype=torch.float32, device=x2d.device)
     a = cabi.LayerNormArgs()
@@ -734,6 +734,7 @@ def layernorm_backward(x2d, dy2d, weight, mean, rstd, need_wgrad=True, defer=Fal
     a.dy, a.dy_stride = dy2d.data_ptr(), dy2d.stride(0)
     a.dx, a.dx_stride = dx.data_ptr(), dx.stride(0)
     a.dgamma_part, a.dbeta_part = dg_part.data_ptr(), db_part.data_ptr()
+    a.n_part = n_part
     if gelu:
         a.act, a.beta = cabi.CM_LN_OUT_GELU, cabi.ptr(bias)
     _call("cm_layernorm_bwd", lib.cm_layernorm_bwd, C.byref(a), cabi.stream_ptr())

@@ -70,6 +70,12 @@ def test_checkpoint_and_partial_counts_follow_the_documented_formulas(lib):
     # backward: 32-channel dB/dC slabs (the state-parallel kernel's CTA width) at every shape
     assert lib.cm_scan_pick_lanes_bwd(64, 512, 2) == 1 and lib.cm_scan_pick_lanes_bwd(4, 512, 2) == 1
     assert lib.cm_layernorm_num_part(8) == 1 and lib.cm_layernorm_num_part(10 ** 6) == 148 * 4
+    # v17: the LayerNorm backward negotiates its partial rows per row width - the grid of cm_add_ln_bwd's kernels where they
+    # apply (cols % 4 == 0: 3 / 2 / 1 CTAs per SM by width), the pair kernels' grid otherwise
+    for cols, per_sm in ((144, 3), (256, 3), (512, 2), (1024, 1)):
+        assert lib.cm_layernorm_num_part2(10 ** 6, cols) == lib.cm_add_ln_num_part(10 ** 6, cols) == 148 * per_sm
+    assert lib.cm_layernorm_num_part2(10 ** 6, 150) == lib.cm_layernorm_num_part(10 ** 6)
+    assert lib.cm_layernorm_num_part2(8, 256) == 1
 
 
 def test_mamba_module_keeps_reference_state_dict_layout(golden_dir):
@@ -388,3 +394,23 @@ def test_deferred_reduction_queue_host_logic():
     assert K.grad_cast(g, torch.float32) is g and K.grad_cast(None, torch.float32) is None
     assert K.grad_cast(g, torch.float64).dtype == torch.float64
     K.reduce_many([])                                            # nothing to do, no library call
+
+
+def test_layernorm_backward_argument_validation(lib):
+    """cm_layernorm_bwd (include/conmamba_b200.h, ABI v17): missing pointers, empty shapes and a negative partial-row count
+    are BAD_ARG, more than 1024 columns and an unknown epilogue are refused - all before any launch (no GPU needed)."""
+    from mamba_asr_b200 import _cabi
+    a = _cabi.LayerNormArgs()
+    assert lib.cm_layernorm_bwd(ctypes.byref(a), None) == _cabi.CM_ERR_BAD_ARG
+    for f in ("x", "dy", "dx", "mean", "rstd", "dgamma_part", "dbeta_part"):
+        setattr(a, f, 256)
+    a.rows, a.cols = 16, 256
+    a.x_dtype = a.y_dtype = _cabi.CM_BF16
+    a.x_stride = a.dy_stride = a.dx_stride = 256
+    a.n_part = -1
+    assert lib.cm_layernorm_bwd(ctypes.byref(a), None) == _cabi.CM_ERR_BAD_ARG
+    a.n_part = 0
+    a.cols = 2048
+    assert lib.cm_layernorm_bwd(ctypes.byref(a), None) == _cabi.CM_ERR_UNSUPPORTED
+    a.cols, a.act = 256, 7
+    assert lib.cm_layernorm_bwd(ctypes.byref(a), None) == _cabi.CM_ERR_BAD_ARG
